@@ -1,0 +1,159 @@
+/*
+ * zoomfft_b200.h -- C ABI of the B200-native zoom-FFT PSD engine.
+ *
+ * This is the drop-in boundary for the one hot path of alfille/pypanadapter:
+ * sample chunk -> LO mix -> cascade of decimate-by-2 -> Welch PSD ->
+ * fftshift/crop -> 20*log10 -> (EMA) -> waterfall row.  The reference has no
+ * FFI for this path (it is inline numpy/scipy in Qt methods); every entry
+ * point below cites the reference lines whose work it replaces.
+ *   S: = pypanadapter_spectrum.py   T: = pypanadapter_thread.py
+ *
+ * Conventions: plain C, no torch/CUDA types in signatures (streams and device
+ * pointers travel as void*), every call returns 0 or a negative errno-style
+ * code and never throws/aborts; zfb_last_error() gives the message.  Caller
+ * owns every host/device buffer it passes; the engine owns its workspaces.
+ * One engine = one CUDA device; calls on one engine must be serialised by the
+ * caller (the Python shim holds a lock), different engines are independent.
+ * There is no CPU fallback: without a CUDA device zfb_create fails.
+ */
+#ifndef ZOOMFFT_B200_H
+#define ZOOMFFT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ZFB_ABI_VERSION 1
+
+/* status codes */
+#define ZFB_OK            0
+#define ZFB_EINVAL      (-22)  /* bad argument / unsupported configuration   */
+#define ZFB_ENOMEM      (-12)  /* host or device allocation failed           */
+#define ZFB_ENODEV      (-19)  /* no usable CUDA device                      */
+#define ZFB_ECUDA       (-5)   /* CUDA runtime error (see zfb_last_error)    */
+#define ZFB_ESTATE      (-1)   /* call out of order (e.g. not configured)    */
+#define ZFB_ETOOSHORT   (-34)  /* chunk shorter than the reference accepts   */
+
+/* sample wire formats (zfb_config.dtype) */
+#define ZFB_DTYPE_C64   0      /* interleaved float32 I,Q  (SoapySDR CF32, S:602) */
+#define ZFB_DTYPE_U8    1      /* interleaved uint8 offset-binary I,Q (RTL-SDR;
+                                  converted as pyrtlsdr does: u/127.5 - 1, S:543) */
+
+/* decimator implementations (zfb_config.mode) */
+#define ZFB_MODE_EXACT  0      /* per-chunk zero-phase cheby1 IIR, scipy semantics */
+
+/* zfb_config.flags */
+#define ZFB_FLAG_NO_LO   1     /* skip the LO mix (amplitude 1, f = 0): the chain is
+                                  then exactly scipy.signal.decimate(x, 2) x log2(R)
+                                  -- the call S:2098 / T:1534 makes -- plus welch   */
+#define ZFB_FLAG_LINEAR  2     /* rows hold the linear PSD (welch's Pxx, S:2111)
+                                  instead of 20*log10(abs(.)) (S:2117-2119)         */
+
+typedef struct zfb_engine zfb_engine;
+
+/*
+ * One frame configuration == the AppState the reference reads each frame
+ * (S:1492-1497: fft_size, fft_ratio, fft_avg, fft_tapering; SampleRate).
+ */
+typedef struct zfb_config {
+    double  fs;          /* AppState.panadapter.SampleRate (S:2091,2111)       */
+    int32_t fft_size;    /* AppState.fft_size N, power of two 32..262144       */
+    int32_t fft_ratio;   /* AppState.fft_ratio R, power of two 1..512 (S:2079) */
+    int32_t frame_len;   /* samples per chunk (avg*N in S:1764; any in T:1516) */
+    int32_t row_width;   /* W bins kept around DC (S:2114 N_WIN; T:1542)       */
+    int32_t nperseg;     /* window length = min(N, decimated length)           */
+    int32_t dtype;       /* ZFB_DTYPE_*                                        */
+    int32_t flip;        /* 1 = np.flip the chunk first (S:460,543; T:460)     */
+    int32_t mode;        /* ZFB_MODE_*                                         */
+    int32_t flags;       /* ZFB_FLAG_* bits                                    */
+    double  f_demod;     /* software LO in Hz; reference hard-wires 1.0 (S:2090) */
+    double  ema_alpha;   /* <0: off.  a=alpha*p+(1-alpha)*a on linear power    */
+    const double *window;/* nperseg taps = scipy.signal.get_window(taper,nperseg) */
+} zfb_config;
+
+/* ---- life cycle ------------------------------------------------------- */
+int  zfb_abi_version(void);
+/* "sm_100a" for the product library. */
+const char *zfb_build_kind(void);
+/* create an engine on CUDA device `device`; fails with ZFB_ENODEV when there
+ * is no GPU (no CPU fallback exists). */
+int  zfb_create(int device, zfb_engine **out);
+void zfb_destroy(zfb_engine *e);
+/* message of the last failure on `e` (or of the last failed zfb_create when
+ * e == NULL).  Valid until the next call on the same engine/thread. */
+const char *zfb_last_error(const zfb_engine *e);
+
+/* ---- configuration ---------------------------------------------------- */
+/* (Re)plan for a frame shape.  Cheap when only frame_len changes; the
+ * reference lets N, R, window, avg change between any two frames (S:1753,
+ * S:2079-2086).  Resets the EMA state when the row geometry changes. */
+int  zfb_configure(zfb_engine *e, const zfb_config *cfg);
+/* Use the caller's CUDA stream (cudaStream_t as void*) for all kernels;
+ * NULL restores the engine's own stream. */
+int  zfb_set_stream(zfb_engine *e, void *cuda_stream);
+/* Frames processed per launch group (intermediates of one group are sized to
+ * stay L2-resident).  0 = automatic. */
+int  zfb_set_group(zfb_engine *e, int frames_per_group);
+int  zfb_reset_ema(zfb_engine *e);
+
+/* ---- the hot path ----------------------------------------------------- */
+/*
+ * Replaces the bodies of ApplicationDisplay.zoomfft+update (S:2088-2119) and
+ * PSD.update (T:1525-1548) for `nframes` independent chunks laid out
+ * back to back ([nframes][frame_len] samples of cfg.dtype).
+ *   d_in   : device pointer to the chunks
+ *   d_rows : device pointer, [nframes][row_width] float32 dB20 rows, or NULL
+ * Rows are also appended to the engine's device-resident waterfall ring.
+ * Asynchronous: kernels are enqueued on the engine's stream and the call
+ * returns; use zfb_synchronize / zfb_read_rows to wait.
+ */
+int  zfb_process_device(zfb_engine *e, const void *d_in, int nframes,
+                        float *d_rows);
+/*
+ * Same, for HOST buffers: h_in is copied to the device in groups with async
+ * H2D copies on a dedicated copy stream (directly if h_in is pinned, through
+ * the engine's pinned staging ring otherwise), overlapped with compute; the
+ * rows are copied back to h_rows.  Blocks until h_rows is complete.
+ */
+int  zfb_process_host(zfb_engine *e, const void *h_in, int nframes,
+                      float *h_rows);
+int  zfb_synchronize(zfb_engine *e);
+
+/* mixed + decimated chunk of the last processed frame group's FIRST frame
+ * (what zoomfft returns, S:2100), for parity tests of the decimator alone:
+ * copies up to `max_samples` complex64 samples to h_out, returns the count
+ * (>=0) or a negative status. */
+int  zfb_debug_read_decimated(zfb_engine *e, float *h_out_iq, int max_samples);
+
+/* ---- device-resident waterfall ring (replaces Waterfall.img_array,
+ *      S:1631,1651-1652: rows stay on the device until displayed) -------- */
+int  zfb_ring_configure(zfb_engine *e, int rows);      /* default 256 rows  */
+int64_t zfb_ring_rows_written(const zfb_engine *e);    /* monotone counter  */
+/* copy `nrows` rows ending `age` rows before the newest one to host
+ * (age 0 = newest); blocks only until those rows are complete. */
+int  zfb_read_rows(zfb_engine *e, int age, int nrows, float *h_out);
+
+/* ---- pinned host memory for the sample ring (replaces Data.data,
+ *      T:1415,1421) ------------------------------------------------------ */
+int  zfb_alloc_pinned(size_t bytes, void **out);
+int  zfb_free_pinned(void *p);
+
+/* ---- introspection (host only; usable without a GPU) ------------------- */
+/* the 4x6 SOS of scipy.signal.cheby1(8, 0.05, 0.4) the decimator realises
+ * (scipy:_signaltools.py:5317-5319), row-major [b0 b1 b2 a0 a1 a2]. */
+int  zfb_decim_sos(double out24[24]);
+/* geometry of a configuration without touching the device: fills
+ * out[0]=decimated length, out[1]=nperseg, out[2]=hop, out[3]=nseg,
+ * out[4]=number of decimation stages. */
+int  zfb_plan_geometry(int frame_len, int fft_size, int fft_ratio, int out5[5]);
+/* counters since create: [0] frames, [1] input samples, [2] kernels launched,
+ * [3] H2D bytes, [4] D2H bytes. */
+int  zfb_get_counters(const zfb_engine *e, uint64_t out5[5]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZOOMFFT_B200_H */

@@ -1,0 +1,224 @@
+// Welch PSD for FFT sizes that do not fit one CTA (N = 2^14 .. 2^18): a
+// four-step FFT, N = N1 * N2, as two kernels per group of frames.
+//
+// Same reference lines as zfb_welch.cuh (scipy.signal.welch called from
+// pypanadapter_spectrum.py:2111 / pypanadapter_thread.py:1536,1538); this is
+// the path BASELINE.json's offline-waterfall config (65536-pt, Hann, 50 %
+// overlap) and the N sweep up to 262144 take.
+//
+//   n = n1*N2 + n2,  k = k1 + N1*k2
+//   col pass : for every n2, window, N1-point FFT over n1, times W_N^(n2*k1)
+//              -> Y[seg][k1][n2] (scratch, sized to stay L2 resident)
+//   row pass : for every k1, N2-point FFT over n2 -> X[k1 + N1*k2]; |X|^2 is
+//              accumulated over the segments in registers.
+// Each CTA owns a 4096-point tile = B sub-FFTs of length M (M*B = 4096), 512
+// threads x 8 points, radix-8/4 Stockham passes through padded shared memory.
+//
+// detrend='constant' needs the segment mean before windowing, but a column
+// tile only sees 1/16..1/64 of a segment.  FFT(w*(x-m)) = FFT(w*x) - m*FFT(w),
+// so the col pass also emits per-tile sums of the raw samples and the row pass
+// subtracts m * Wf[k] (Wf = FFT of the window, fp64 on the host) per segment.
+#pragma once
+#include "zfb_welch.cuh"
+
+namespace zfb {
+
+struct BigParams {
+    const void   *in;          // [frames][in_stride]
+    long long     in_stride;
+    int           len;
+    int           flip;
+    int           log2N;
+    int           hop;
+    int           nseg;
+    int           seg_per_split;
+    int           nsplit;
+    int           ntiles_col;  // col-pass tiles per segment
+    const float  *window;      // N taps
+    const float2 *twiddle;     // N entries exp(-2 pi i k / N)
+    const float2 *winfft;      // N entries FFT(window)
+    float2       *scratch;     // [frames][nseg][N]  (k1-major)
+    float2       *partial;     // [frames][nseg][ntiles_col] raw sums
+    int           W;
+    float        *pow_out;     // [frames][nsplit][W]
+};
+
+constexpr int BIG_TILE = 4096;
+constexpr int BIG_THREADS = BIG_TILE / 8;
+
+__host__ __device__ constexpr int big_stride(int M) { return (M + (M >> 4)) | 1; }
+constexpr size_t big_smem(int M) { return (size_t)(BIG_TILE / M) * big_stride(M) * sizeof(float2); }
+
+// M-point forward FFT of the 8 values v[q] = a[j + q*M/8] of one sub-FFT that
+// lives at `sub` in shared memory; twiddles from the N-entry table.
+template <int LM>
+__device__ __forceinline__ void sub_fft(float2 (&v)[8], int j, float2 *sub, const float2 *tw, int log2N) {
+    constexpr int M = 1 << LM;
+    constexpr int NT = M / 8;
+    static_assert(LM >= 7 && LM <= 9, "sub-FFT length");
+    fft_pass<8, 8>(v, j, NT, log2N, 0, tw, sub, false, true);
+    if (LM == 7) {
+        fft_pass<4, 8>(v, j, NT, log2N, 3, tw, sub, false, true);
+        fft_pass<4, 8>(v, j, NT, log2N, 5, tw, sub, true, true);
+    } else if (LM == 8) {
+        fft_pass<8, 8>(v, j, NT, log2N, 3, tw, sub, false, true);
+        fft_pass<4, 8>(v, j, NT, log2N, 6, tw, sub, true, true);
+    } else {
+        fft_pass<8, 8>(v, j, NT, log2N, 3, tw, sub, false, true);
+        fft_pass<8, 8>(v, j, NT, log2N, 6, tw, sub, true, true);
+    }
+}
+
+template <int LM, int KIND>
+__global__ void __launch_bounds__(BIG_THREADS) bigfft_col_kernel(const BigParams p) {
+    constexpr int M = 1 << LM;            // N1
+    constexpr int C = BIG_TILE / M;       // columns per tile
+    constexpr int S = big_stride(M);
+    ZFB_DYN_SMEM(smem_raw);
+    float2 *sm = reinterpret_cast<float2 *>(smem_raw);
+    __shared__ float2 red[33];
+
+    const int t = threadIdx.x;
+    const int c = t % C, j = t / C;
+    const int tile = blockIdx.x, s = blockIdx.y, frame = blockIdx.z;
+    const int N = 1 << p.log2N;
+    const int log2N2 = p.log2N - LM;
+    const int n2 = tile * C + c;
+    const size_t esz = (KIND == KIND_U8_RAW) ? 2 : 8;
+    const char *frame_in = (const char *)p.in + (size_t)frame * (size_t)p.in_stride * esz;
+    const int base = s * p.hop;
+
+    float2 v[8];
+    float2 sum = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const int idx = ((j + q * (M / 8)) << log2N2) + n2;
+        const float2 x = welch_fetch<KIND>(frame_in, base + idx, p.len, p.flip);
+        const float w = __ldg(p.window + idx);
+        sum = cadd(sum, x);
+        v[q] = make_float2(x.x * w, x.y * w);
+    }
+    sum = block_sum<BIG_THREADS>(sum, t, red);
+    const size_t seg = (size_t)frame * p.nseg + s;
+    if (t == 0) p.partial[seg * p.ntiles_col + tile] = sum;
+
+    sub_fft<LM>(v, j, sm + c * S, p.twiddle, p.log2N);
+
+    float2 *y = p.scratch + (seg << p.log2N);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const int k1 = j + q * (M / 8);
+        const float2 tw = __ldg(p.twiddle + ((n2 * k1) & (N - 1)));
+        y[((size_t)k1 << log2N2) + n2] = cmul(v[q], tw);
+    }
+}
+
+template <int LM>
+__global__ void __launch_bounds__(BIG_THREADS) bigfft_row_kernel(const BigParams p) {
+    constexpr int M = 1 << LM;            // N2
+    constexpr int RR = BIG_TILE / M;      // rows (k1 values) per tile
+    constexpr int S = big_stride(M);
+    ZFB_DYN_SMEM(smem_raw);
+    float2 *sm = reinterpret_cast<float2 *>(smem_raw);
+    __shared__ float2 red[33];
+
+    const int t = threadIdx.x;
+    const int r = t / (M / 8), j = t % (M / 8);
+    const int tile = blockIdx.x, split = blockIdx.y, frame = blockIdx.z;
+    const int N = 1 << p.log2N;
+    const int log2N1 = p.log2N - LM;
+    const int k1 = tile * RR + r;
+
+    float2 wf[8];
+    float acc[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        wf[q] = __ldg(p.winfft + k1 + ((j + q * (M / 8)) << log2N1));
+        acc[q] = 0.f;
+    }
+    const float inv_n = 1.0f / (float)N;
+    const int s_begin = split * p.seg_per_split;
+    const int s_end = min(p.nseg, s_begin + p.seg_per_split);
+    for (int s = s_begin; s < s_end; ++s) {
+        const size_t seg = (size_t)frame * p.nseg + s;
+        const float2 *y = p.scratch + (seg << p.log2N) + ((size_t)k1 << LM);
+        float2 v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = y[j + q * (M / 8)];
+        float2 ps = (t < p.ntiles_col) ? p.partial[seg * p.ntiles_col + t] : make_float2(0.f, 0.f);
+        ps = block_sum<BIG_THREADS>(ps, t, red);
+        const float2 mean = make_float2(ps.x * inv_n, ps.y * inv_n);
+        sub_fft<LM>(v, j, sm + r * S, p.twiddle, p.log2N);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const float2 d = cmul(mean, wf[q]);
+            const float re = v[q].x - d.x, im = v[q].y - d.y;
+            acc[q] = fmaf(re, re, fmaf(im, im, acc[q]));
+        }
+    }
+
+    // transpose through shared memory so that the global write runs along k
+    __syncthreads();
+    float *smf = reinterpret_cast<float *>(smem_raw);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) smf[(j + q * (M / 8)) * (RR + 1) + r] = acc[q];
+    __syncthreads();
+    const int c0 = N / 2 - p.W / 2;
+    float *row = p.pow_out + ((size_t)frame * p.nsplit + split) * p.W;
+    for (int i = t; i < BIG_TILE; i += BIG_THREADS) {
+        const int k2 = i / RR, rr = i % RR;
+        const int k = tile * RR + rr + (k2 << log2N1);
+        const int col = ((k + N / 2) & (N - 1)) - c0;
+        if (col >= 0 && col < p.W) row[col] = smf[k2 * (RR + 1) + rr];
+    }
+}
+
+// N = N1*N2 split used for a given log2N
+inline void big_split(int log2N, int &lm1, int &lm2) {
+    lm1 = (log2N + 1) / 2;
+    lm2 = log2N - lm1;
+}
+
+inline int big_ntiles_col(int log2N) {
+    int lm1, lm2;
+    big_split(log2N, lm1, lm2);
+    return (1 << lm2) / (BIG_TILE >> lm1);
+}
+
+inline size_t big_scratch_bytes(int log2N, int nseg, int frames) {
+    return (size_t)frames * (size_t)nseg * (((size_t)1 << log2N) + (size_t)big_ntiles_col(log2N)) * sizeof(float2);
+}
+
+template <int LM1>
+inline void big_launch_col(const BigParams &p, int kind, dim3 grid, cudaStream_t st) {
+    const size_t smem = big_smem(1 << LM1);
+    if (kind == KIND_C64_RAW) {
+        ZFB_LAUNCH((bigfft_col_kernel<LM1, KIND_C64_RAW>), grid, dim3(BIG_THREADS), smem, st, p);
+    } else if (kind == KIND_U8_RAW) {
+        ZFB_LAUNCH((bigfft_col_kernel<LM1, KIND_U8_RAW>), grid, dim3(BIG_THREADS), smem, st, p);
+    } else {
+        ZFB_LAUNCH((bigfft_col_kernel<LM1, KIND_C64_MID>), grid, dim3(BIG_THREADS), smem, st, p);
+    }
+}
+
+// enqueue col + row pass for `frames` frames; returns the number of launches
+inline int big_run(const BigParams &p, int kind, int frames, cudaStream_t st) {
+    int lm1, lm2;
+    big_split(p.log2N, lm1, lm2);
+    dim3 gcol((unsigned)p.ntiles_col, (unsigned)p.nseg, (unsigned)frames);
+    switch (lm1) {
+        case 7: big_launch_col<7>(p, kind, gcol, st); break;
+        case 8: big_launch_col<8>(p, kind, gcol, st); break;
+        default: big_launch_col<9>(p, kind, gcol, st); break;
+    }
+    const int rr = BIG_TILE >> lm2;
+    dim3 grow((unsigned)((1 << lm1) / rr), (unsigned)p.nsplit, (unsigned)frames);
+    switch (lm2) {
+        case 7: ZFB_LAUNCH(bigfft_row_kernel<7>, grow, dim3(BIG_THREADS), big_smem(1 << 7), st, p); break;
+        case 8: ZFB_LAUNCH(bigfft_row_kernel<8>, grow, dim3(BIG_THREADS), big_smem(1 << 8), st, p); break;
+        default: ZFB_LAUNCH(bigfft_row_kernel<9>, grow, dim3(BIG_THREADS), big_smem(1 << 9), st, p); break;
+    }
+    return 2;
+}
+
+}  // namespace zfb

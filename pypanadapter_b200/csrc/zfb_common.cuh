@@ -1,0 +1,68 @@
+// Shared device helpers and constants for the zoom-FFT PSD kernels (sm_100a).
+#pragma once
+#include <stdint.h>
+
+#include "zfb_platform.h"
+
+namespace zfb {
+
+// ---- decimator geometry -------------------------------------------------
+// One CTA filters a REGION of one frame that lives in shared memory; each
+// thread owns a BLK-sample run of it.  Outputs are only taken from the middle
+// T <= TMAX samples; WARM samples on either side absorb the start-up
+// transient of regions that do not begin/end at a true chunk edge (the slow
+// pole pair of cheby1(8,.05,.4) has radius 0.935: 0.935^320 = 5e-10 in state,
+// 4.9e-8 worst-case in output -- below fp32 resolution).
+constexpr int BLK      = 64;                 // samples per thread
+constexpr int NTHR     = 256;                // threads per CTA
+constexpr int REGION   = BLK * NTHR;         // 16384 samples in smem
+constexpr int WARM     = 320;                // warm-up halo each side
+constexpr int TMAX     = REGION - 2 * WARM;  // 15744 outputs per tile
+constexpr int BLK_PAD  = BLK + 1;            // +1 complex: conflict-free LDS.64
+constexpr int PADLEN   = 27;                 // scipy sosfiltfilt odd extension
+constexpr int NSEC     = 4;                  // biquads in cheby1 order 8
+constexpr int NSTATE   = 2 * NSEC;
+constexpr int JTERMS   = 5;                  // blocks of history in hand-off
+
+// input kinds of a decimation stage / of the Welch kernel
+constexpr int KIND_C64_RAW = 0;  // complex64 chunk: flip + LO mix on load
+constexpr int KIND_U8_RAW  = 1;  // uint8 IQ chunk: convert + flip + LO mix
+constexpr int KIND_C64_MID = 2;  // complex64 intermediate (already mixed)
+
+struct DecimConst {
+    float na1[NSEC], na2[NSEC];          // -a1, -a2 of each section
+    float g;                             // b0 of section 0 (overall gain)
+    float zi[NSEC];                      // DF2 steady state per unit scaled input
+    float Mp[JTERMS][NSTATE][NSTATE];    // Mp[j] = (state transition over BLK)^j
+};
+
+// packed fp32x2 arithmetic (Blackwell FFMA2/FADD2/FMUL2): re and im of a
+// sample share every real filter coefficient, so one issue slot does both.
+__device__ __forceinline__ float2 pk_fma(float a, float2 x, float2 y) {
+    return __ffma2_rn(make_float2(a, a), x, y);
+}
+__device__ __forceinline__ float2 pk_add(float2 x, float2 y) {
+    return __fadd2_rn(x, y);
+}
+__device__ __forceinline__ float2 pk_mul(float a, float2 x) {
+    return __fmul2_rn(make_float2(a, a), x);
+}
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+    return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+}
+
+// exp(-2*pi*i * frac) for frac = (pos * inc mod 2^64) / 2^64
+__device__ __forceinline__ float2 lo_phasor(long long pos, unsigned long long inc) {
+    unsigned long long ph = (unsigned long long)pos * inc;
+    int p32 = (int)(ph >> 32);
+    float s, c;
+    sincospif((float)p32 * 4.656612873077393e-10f, &s, &c);   // 2^-31
+    return make_float2(c, -s);
+}
+
+// pyrtlsdr: u / 127.5 - 1
+__device__ __forceinline__ float u8_to_f(unsigned int u) {
+    return fmaf((float)u, 1.0f / 127.5f, -1.0f);
+}
+
+}  // namespace zfb

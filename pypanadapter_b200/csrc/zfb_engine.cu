@@ -1,0 +1,965 @@
+// zfb_engine.cu -- host side of the B200 zoom-FFT PSD engine and its C ABI
+// (include/zoomfft_b200.h).  Plans a frame shape, owns the device workspaces,
+// the pinned staging buffers, the copy stream and the device-resident
+// waterfall ring, and enqueues the kernels of zfb_decim.cuh / zfb_welch.cuh.
+//
+// Reference lines replaced (S: = pypanadapter_spectrum.py, T: = _thread.py):
+//   zoomfft + update bodies S:2088-2119, PSD.update T:1513-1549,
+//   Data.data storage T:1415-1421, Waterfall.img_array S:1631,1651-1652.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "zoomfft_b200.h"
+#include "zfb_decim.cuh"
+#include "zfb_welch.cuh"
+#include "zfb_bigfft.cuh"
+
+using namespace zfb;
+
+namespace {
+
+constexpr int kMaxStages = 16;
+constexpr int kMinLog2N = 5;          // 32
+constexpr int kMaxLog2Small = 13;     // 8192: one CTA per segment
+constexpr int kMaxLog2N = 18;         // 262144: four-step path
+constexpr double kPi = 3.14159265358979323846264338327950288;
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+    void  *p = nullptr;
+    size_t cap = 0;
+};
+
+}  // namespace
+
+struct zfb_engine {
+    int device = 0;
+    int sm_count = 148;
+    mutable std::mutex mu;
+    std::string err;
+
+    cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+    bool slot_busy[2] = {false, false};
+
+    bool configured = false;
+    zfb_config cfg{};
+    // plan
+    int nstages = 0;
+    int len[kMaxStages + 1] = {0};     // len[s] = input length of stage s; len[nstages] = Welch input
+    int tiles[kMaxStages] = {0}, T[kMaxStages] = {0};
+    int nperseg = 0, hop = 0, nseg = 0, W = 0, log2N = 0;
+    double sum_w2 = 0.0;
+    int group = 1, group_user = 0;
+    int nsplit_cap = 1;
+    StageParams sp0{};                 // LO tables of stage 0
+
+    DevBuf window, winfft, twiddle, mid[2], pow, rows_tmp, ema, ema_valid, ring, stage_in[2], big;
+    void  *h_stage[2] = {nullptr, nullptr};
+    size_t h_stage_cap[2] = {0, 0};
+    float *h_rows = nullptr;
+    size_t h_rows_cap = 0;
+    int ring_rows = 256, ring_rows_req = 256, ring_W = 0;
+    int64_t ring_written = 0;
+    int last_group_frames = 0;
+
+    uint64_t counters[5] = {0, 0, 0, 0, 0};
+};
+
+namespace {
+
+int fail(zfb_engine *e, int code, const char *fmt, ...) __attribute__((format(printf, 3, 4)));
+int fail(zfb_engine *e, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (e) e->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CK(e, call)                                                                     \
+    do {                                                                                \
+        cudaError_t _st = (call);                                                       \
+        if (_st != cudaSuccess)                                                         \
+            return fail(e, ZFB_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_st), \
+                        __FILE__, __LINE__);                                            \
+    } while (0)
+
+int ensure(zfb_engine *e, DevBuf &b, size_t need) {
+    if (need <= b.cap && b.p) return ZFB_OK;
+    if (b.p) {
+        CK(e, cudaStreamSynchronize(e->stream));
+        CK(e, cudaFree(b.p));
+        b.p = nullptr;
+        b.cap = 0;
+    }
+    size_t cap = need < 256 ? 256 : need;
+    cudaError_t st = cudaMalloc(&b.p, cap);
+    if (st != cudaSuccess) {
+        b.p = nullptr;
+        return fail(e, ZFB_ENOMEM, "cudaMalloc(%zu) failed: %s", cap, cudaGetErrorString(st));
+    }
+    b.cap = cap;
+    return ZFB_OK;
+}
+
+void release(DevBuf &b) {
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+}
+
+// ---- the reference's decimation filter --------------------------------------
+// scipy.signal.cheby1(8, 0.05, 0.8/2, output='sos') (scipy:_signaltools.py:
+// 5317-5319), designed here from the closed form: analog Chebyshev-I
+// prototype, pre-warped low-pass transform, bilinear transform; conjugate pole
+// pairs become sections ordered by pole radius (sharpest last) and the whole
+// gain sits in the first section, as scipy's zpk2sos does for this filter.
+void design_cheby1_sos(double sos[NSEC][6]) {
+    const int n = 2 * NSEC;
+    const double rp = 0.05, wn = 0.4;
+    const double eps = sqrt(pow(10.0, 0.1 * rp) - 1.0);
+    const double mu = asinh(1.0 / eps) / n;
+    const double fs2 = 4.0;                              // 2*fs with fs = 2
+    const double warped = fs2 * tan(kPi * wn / 2.0);
+    double pre[NSEC], pim[NSEC];                         // upper-half-plane analog poles
+    double kre = 1.0, kim = 0.0;                         // prod(-p) over all poles
+    for (int k = 0; k < NSEC; ++k) {
+        const double theta = kPi * (2.0 * (k + 1) - 1.0) / (2.0 * n);
+        pre[k] = -sinh(mu) * sin(theta) * warped;
+        pim[k] = cosh(mu) * cos(theta) * warped;
+        const double m2 = pre[k] * pre[k] + pim[k] * pim[k];   // (-p)(-conj p)
+        kre *= m2;
+    }
+    (void)kim;
+    double gain = kre / sqrt(1.0 + eps * eps);           // even order: ripple at DC
+    // bilinear: z = (fs2 + s)/(fs2 - s); gain *= real(prod(fs2 - z_analog)/prod(fs2 - p))
+    // (no finite analog zeros: numerator product is 1; n zeros land at z = -1)
+    double zr[NSEC], zi_[NSEC], rad[NSEC];
+    for (int k = 0; k < NSEC; ++k) {
+        const double dr = fs2 - pre[k], di = -pim[k];
+        const double d2 = dr * dr + di * di;
+        gain /= d2;                                      // (fs2-p)(fs2-conj p) = |fs2-p|^2
+        const double nr = fs2 + pre[k], ni = pim[k];
+        zr[k] = (nr * dr + ni * di) / d2;
+        zi_[k] = (ni * dr - nr * di) / d2;
+        rad[k] = sqrt(zr[k] * zr[k] + zi_[k] * zi_[k]);
+    }
+    int order[NSEC];
+    for (int k = 0; k < NSEC; ++k) order[k] = k;
+    for (int a = 0; a < NSEC; ++a)
+        for (int b = a + 1; b < NSEC; ++b)
+            if (rad[order[b]] < rad[order[a]]) { int t = order[a]; order[a] = order[b]; order[b] = t; }
+    for (int s = 0; s < NSEC; ++s) {
+        const int k = order[s];
+        const double b0 = (s == 0) ? gain : 1.0;
+        sos[s][0] = b0;
+        sos[s][1] = 2.0 * b0;
+        sos[s][2] = b0;
+        sos[s][3] = 1.0;
+        sos[s][4] = -2.0 * zr[k];
+        sos[s][5] = rad[k] * rad[k];
+    }
+}
+
+void mat_mul(const double a[NSTATE][NSTATE], const double b[NSTATE][NSTATE], double out[NSTATE][NSTATE]) {
+    double t[NSTATE][NSTATE];
+    for (int i = 0; i < NSTATE; ++i)
+        for (int j = 0; j < NSTATE; ++j) {
+            double s = 0.0;
+            for (int k = 0; k < NSTATE; ++k) s += a[i][k] * b[k][j];
+            t[i][j] = s;
+        }
+    memcpy(out, t, sizeof t);
+}
+
+// constants of the block-parallel IIR (zfb_decim.cuh): -a1, -a2, the squared
+// gain (forward and backward pass folded into one input scale), the DF2
+// steady state per unit (scaled) input, and powers of the zero-input state
+// transition over one BLK-sample run.
+void build_decim_const(DecimConst &dc) {
+    double sos[NSEC][6];
+    design_cheby1_sos(sos);
+    double a1[NSEC], a2[NSEC];
+    for (int k = 0; k < NSEC; ++k) {
+        a1[k] = sos[k][4];
+        a2[k] = sos[k][5];
+        dc.na1[k] = (float)(-a1[k]);
+        dc.na2[k] = (float)(-a2[k]);
+    }
+    dc.g = (float)(sos[0][0] * sos[0][0]);
+    double c = 1.0;
+    for (int k = 0; k < NSEC; ++k) {
+        const double wss = c / (1.0 + a1[k] + a2[k]);
+        dc.zi[k] = (float)wss;
+        c = 4.0 * wss;
+    }
+    // one-sample zero-input transition A of the DF2 cascade, state order
+    // (w1_0, w2_0, w1_1, w2_1, ...): column j = response to unit state j
+    double A[NSTATE][NSTATE];
+    for (int j = 0; j < NSTATE; ++j) {
+        double w1[NSEC], w2[NSEC];
+        for (int k = 0; k < NSEC; ++k) {
+            w1[k] = (j == 2 * k) ? 1.0 : 0.0;
+            w2[k] = (j == 2 * k + 1) ? 1.0 : 0.0;
+        }
+        double v = 0.0;
+        for (int k = 0; k < NSEC; ++k) {
+            const double w = v - a1[k] * w1[k] - a2[k] * w2[k];
+            v = w + 2.0 * w1[k] + w2[k];
+            w2[k] = w1[k];
+            w1[k] = w;
+        }
+        for (int k = 0; k < NSEC; ++k) {
+            A[2 * k][j] = w1[k];
+            A[2 * k + 1][j] = w2[k];
+        }
+    }
+    double M[NSTATE][NSTATE];
+    memcpy(M, A, sizeof M);
+    for (int i = 1; i < BLK; i <<= 1) mat_mul(M, M, M);   // BLK is a power of two
+    double P[NSTATE][NSTATE];
+    for (int i = 0; i < NSTATE; ++i)
+        for (int j = 0; j < NSTATE; ++j) P[i][j] = (i == j) ? 1.0 : 0.0;
+    for (int j = 0; j < JTERMS; ++j) {
+        for (int r = 0; r < NSTATE; ++r)
+            for (int cc = 0; cc < NSTATE; ++cc) dc.Mp[j][r][cc] = (float)P[r][cc];
+        mat_mul(M, P, P);
+    }
+}
+
+// in-place radix-2 FFT in double (host; window spectra only)
+void host_fft(std::vector<double> &re, std::vector<double> &im) {
+    const size_t n = re.size();
+    for (size_t i = 1, j = 0; i < n; ++i) {
+        size_t bit = n >> 1;
+        for (; j & bit; bit >>= 1) j ^= bit;
+        j ^= bit;
+        if (i < j) { std::swap(re[i], re[j]); std::swap(im[i], im[j]); }
+    }
+    for (size_t len = 2; len <= n; len <<= 1) {
+        const size_t half = len >> 1;
+        for (size_t k = 0; k < half; ++k) {
+            const double a = -2.0 * kPi * (double)k / (double)len;
+            const double wr = cos(a), wi = sin(a);
+            for (size_t i = k; i < n; i += len) {
+                const size_t j2 = i + half;
+                const double xr = re[j2] * wr - im[j2] * wi, xi = re[j2] * wi + im[j2] * wr;
+                re[j2] = re[i] - xr; im[j2] = im[i] - xi;
+                re[i] += xr; im[i] += xi;
+            }
+        }
+    }
+}
+
+int ilog2_floor(long long v) {
+    int l = -1;
+    while (v > 0) { v >>= 1; ++l; }
+    return l;
+}
+
+struct Geometry {
+    int nstages, ndec, nperseg, hop, nseg;
+    int len[kMaxStages + 1];
+};
+
+// lengths the reference produces: decimate keeps y[::2] (ceil), needs len > 27
+// (scipy:_signaltools.py:4944-4947); welch: nperseg = min(N, n), noverlap =
+// nperseg//2, nseg = (n - noverlap)//hop (scipy:_spectral_py.py:897-912,932-937)
+int geometry(int frame_len, int fft_size, int fft_ratio, Geometry &g) {
+    if (frame_len < 1 || fft_size < 1 || fft_ratio < 1) return ZFB_EINVAL;
+    g.nstages = ilog2_floor(fft_ratio);                  // int(np.log2(ratio)), S:2096
+    if (g.nstages > kMaxStages) return ZFB_EINVAL;
+    int L = frame_len;
+    for (int s = 0; s < g.nstages; ++s) {
+        g.len[s] = L;
+        if (L <= PADLEN) return ZFB_ETOOSHORT;
+        L = (L + 1) / 2;
+    }
+    g.len[g.nstages] = L;
+    g.ndec = L;
+    g.nperseg = fft_size < L ? fft_size : L;
+    const int noverlap = g.nperseg / 2;
+    g.hop = g.nperseg - noverlap;
+    g.nseg = (L - noverlap) / g.hop;
+    return ZFB_OK;
+}
+
+// exp(-2 pi i * frac(r * m)) in double, with the product reduced exactly
+void lo_entry(double r, long long m, double amp, float2 &out) {
+    // r in [0,1); r*m may be large: split m to keep the fractional part accurate
+    long double ph = (long double)r * (long double)m;
+    ph -= floorl(ph);
+    const double a = -2.0 * kPi * (double)ph;
+    out.x = (float)(amp * cos(a));
+    out.y = (float)(amp * sin(a));
+}
+
+// ---- kernel tables ------------------------------------------------------------
+typedef void (*WelchFn)(const WelchParams);
+struct WelchEntry { WelchFn fn; int threads; size_t smem; };
+
+template <int LOG2N, int KIND>
+WelchEntry welch_entry() {
+    constexpr int PPT = (LOG2N >= 13) ? 16 : 8;
+    using S = WelchShape<LOG2N, PPT>;
+    return WelchEntry{welch_kernel<LOG2N, PPT, KIND>, S::NTHREADS, S::SMEM};
+}
+
+template <int KIND>
+WelchEntry welch_lookup_kind(int log2n) {
+    switch (log2n) {
+        case 5: return welch_entry<5, KIND>();
+        case 6: return welch_entry<6, KIND>();
+        case 7: return welch_entry<7, KIND>();
+        case 8: return welch_entry<8, KIND>();
+        case 9: return welch_entry<9, KIND>();
+        case 10: return welch_entry<10, KIND>();
+        case 11: return welch_entry<11, KIND>();
+        case 12: return welch_entry<12, KIND>();
+        case 13: return welch_entry<13, KIND>();
+        default: return WelchEntry{nullptr, 0, 0};
+    }
+}
+
+WelchEntry welch_lookup(int log2n, int kind) {
+    switch (kind) {
+        case KIND_C64_RAW: return welch_lookup_kind<KIND_C64_RAW>(log2n);
+        case KIND_U8_RAW: return welch_lookup_kind<KIND_U8_RAW>(log2n);
+        default: return welch_lookup_kind<KIND_C64_MID>(log2n);
+    }
+}
+
+typedef void (*DecimFn)(const StageParams);
+DecimFn decim_lookup(int kind) {
+    switch (kind) {
+        case KIND_C64_RAW: return decim2_exact_kernel<KIND_C64_RAW>;
+        case KIND_U8_RAW: return decim2_exact_kernel<KIND_U8_RAW>;
+        default: return decim2_exact_kernel<KIND_C64_MID>;
+    }
+}
+
+constexpr size_t kDecimSmem = (size_t)(NTHR * BLK_PAD + NSTATE * NTHR) * sizeof(float2);
+
+int setup_device_once(zfb_engine *e) {
+    DecimConst dc;
+    build_decim_const(dc);
+    CK(e, cudaMemcpyToSymbol(c_dec, &dc, sizeof dc));
+    for (int kind = 0; kind < 3; ++kind)
+        CK(e, cudaFuncSetAttribute(decim_lookup(kind), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)kDecimSmem));
+    for (int kind = 0; kind < 3; ++kind)
+        for (int l = kMinLog2N; l <= kMaxLog2Small; ++l) {
+            WelchEntry w = welch_lookup(l, kind);
+            if (w.smem > 48 * 1024)
+                CK(e, cudaFuncSetAttribute(w.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.smem));
+        }
+    return ZFB_OK;
+}
+
+int raw_kind(const zfb_config &c) { return c.dtype == ZFB_DTYPE_U8 ? KIND_U8_RAW : KIND_C64_RAW; }
+size_t sample_bytes(const zfb_config &c) { return c.dtype == ZFB_DTYPE_U8 ? 2 : 8; }
+
+int choose_group(const zfb_engine *e) {
+    if (e->group_user > 0) return e->group_user;
+    // keep the two largest intermediates of a group inside ~half of L2
+    size_t per_frame = 0;
+    if (e->nstages >= 1) per_frame += (size_t)e->len[1] * 8;
+    if (e->nstages >= 2) per_frame += (size_t)e->len[2] * 8;
+    if (e->log2N > kMaxLog2Small) per_frame += (size_t)e->nseg * ((size_t)8 << e->log2N);
+    if (per_frame == 0) return 2048;
+    long long g = (long long)(64ull << 20) / (long long)per_frame;
+    if (g < 1) g = 1;
+    if (g > 2048) g = 2048;
+    return (int)g;
+}
+
+// one group of frames, all resident on the device, through the whole chain
+int run_group(zfb_engine *e, const void *d_in, int gf, float *d_rows) {
+    const zfb_config &c = e->cfg;
+    cudaStream_t st = e->stream;
+    const void *src = d_in;
+    long long src_stride = c.frame_len;
+    int kind = raw_kind(c);
+
+    for (int s = 0; s < e->nstages; ++s) {
+        StageParams p = e->sp0;           // LO tables only matter for stage 0
+        float2 *out = (float2 *)e->mid[s & 1].p;
+        const long long out_stride = e->len[s + 1];
+        p.in = src;
+        p.out = out;
+        p.in_stride = src_stride;
+        p.out_stride = out_stride;
+        p.L = e->len[s];
+        p.T = e->T[s];
+        p.flip = (s == 0) ? c.flip : 0;
+        dim3 grid((unsigned)e->tiles[s], (unsigned)gf);
+        ZFB_LAUNCH(decim_lookup(kind), grid, dim3(NTHR), kDecimSmem, st, p);
+        e->counters[2] += 1;
+        src = out;
+        src_stride = out_stride;
+        kind = KIND_C64_MID;
+    }
+
+    // Welch
+    int nsplit = 1;
+    if (e->log2N <= kMaxLog2Small) {
+        int want = (2 * e->sm_count + gf - 1) / gf;
+        if (want > e->nseg) want = e->nseg;
+        if (want > e->nsplit_cap) want = e->nsplit_cap;
+        if (want < 1) want = 1;
+        const int per = (e->nseg + want - 1) / want;
+        nsplit = (e->nseg + per - 1) / per;
+        WelchParams w{};
+        w.in = src;
+        w.in_stride = src_stride;
+        w.len = e->len[e->nstages];
+        w.flip = (e->nstages == 0) ? c.flip : 0;
+        w.nperseg = e->nperseg;
+        w.hop = e->hop;
+        w.nseg = e->nseg;
+        w.seg_per_split = per;
+        w.nsplit = nsplit;
+        w.reuse = (e->nperseg == (1 << e->log2N) && e->hop * 2 == e->nperseg) ? 1 : 0;
+        w.window = (const float *)e->window.p;
+        w.twiddle = (const float2 *)e->twiddle.p;
+        w.W = e->W;
+        w.pow_out = (float *)e->pow.p;
+        WelchEntry we = welch_lookup(e->log2N, kind);
+        ZFB_LAUNCH(we.fn, dim3((unsigned)nsplit, (unsigned)gf), dim3((unsigned)we.threads), we.smem, st, w);
+        e->counters[2] += 1;
+    } else {
+        int want = (2 * e->sm_count + gf * 16 - 1) / (gf * 16);
+        if (want > e->nseg) want = e->nseg;
+        if (want > e->nsplit_cap) want = e->nsplit_cap;
+        if (want < 1) want = 1;
+        const int per = (e->nseg + want - 1) / want;
+        nsplit = (e->nseg + per - 1) / per;
+        BigParams b{};
+        b.in = src;
+        b.in_stride = src_stride;
+        b.len = e->len[e->nstages];
+        b.flip = (e->nstages == 0) ? c.flip : 0;
+        b.log2N = e->log2N;
+        b.hop = e->hop;
+        b.nseg = e->nseg;
+        b.seg_per_split = per;
+        b.nsplit = nsplit;
+        b.ntiles_col = big_ntiles_col(e->log2N);
+        b.window = (const float *)e->window.p;
+        b.twiddle = (const float2 *)e->twiddle.p;
+        b.winfft = (const float2 *)e->winfft.p;
+        b.scratch = (float2 *)e->big.p;
+        b.partial = b.scratch + ((size_t)e->group * (size_t)e->nseg << e->log2N);
+        b.W = e->W;
+        b.pow_out = (float *)e->pow.p;
+        e->counters[2] += (uint64_t)big_run(b, kind, gf, st);
+    }
+
+    FinalizeParams f{};
+    f.pow_in = (const float *)e->pow.p;
+    f.nframes = gf;
+    f.nsplit = nsplit;
+    f.W = e->W;
+    f.scale = (float)(1.0 / (c.fs * e->sum_w2) / (double)e->nseg);
+    f.alpha = (c.ema_alpha >= 0.0) ? (float)c.ema_alpha : -1.f;
+    f.linear = (c.flags & ZFB_FLAG_LINEAR) ? 1 : 0;
+    f.ema_state = (float *)e->ema.p;
+    f.ema_valid = (int *)e->ema_valid.p;
+    f.rows = d_rows;
+    f.ring = (float *)e->ring.p;
+    f.ring_pos = (long long)(e->ring_written % e->ring_rows);
+    f.ring_rows = e->ring_rows;
+    ZFB_LAUNCH(finalize_rows_kernel, dim3((unsigned)((e->W + 127) / 128)), dim3(128), 0, st, f);
+    e->counters[2] += 1;
+    if (f.alpha >= 0.f) {
+        ZFB_LAUNCH(set_flag_kernel, dim3(1), dim3(1), 0, st, (int *)e->ema_valid.p, 1);
+        e->counters[2] += 1;
+    }
+    CK(e, cudaGetLastError());
+    e->ring_written += gf;
+    e->last_group_frames = gf;
+    e->counters[0] += (uint64_t)gf;
+    e->counters[1] += (uint64_t)gf * (uint64_t)c.frame_len;
+    return ZFB_OK;
+}
+
+bool is_pinned(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+
+}  // namespace
+
+// =============================================================================
+extern "C" {
+
+int zfb_abi_version(void) { return ZFB_ABI_VERSION; }
+
+const char *zfb_build_kind(void) { return ZFB_BUILD_KIND; }
+
+const char *zfb_last_error(const zfb_engine *e) {
+    return e ? e->err.c_str() : g_create_error.c_str();
+}
+
+int zfb_create(int device, zfb_engine **out) {
+    if (!out) return fail(nullptr, ZFB_EINVAL, "zfb_create: out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t st = cudaGetDeviceCount(&ndev);
+    if (st != cudaSuccess || ndev <= 0) {
+        cudaGetLastError();
+        return fail(nullptr, ZFB_ENODEV,
+                    "no CUDA device (%s); this engine has no CPU fallback",
+                    st != cudaSuccess ? cudaGetErrorString(st) : "device count is 0");
+    }
+    if (device < 0 || device >= ndev)
+        return fail(nullptr, ZFB_ENODEV, "device %d out of range (%d present)", device, ndev);
+    zfb_engine *e = new (std::nothrow) zfb_engine();
+    if (!e) return fail(nullptr, ZFB_ENOMEM, "out of host memory");
+    e->device = device;
+    int rc = ZFB_OK;
+    do {
+        if (cudaSetDevice(device) != cudaSuccess) { rc = fail(nullptr, ZFB_ENODEV, "cudaSetDevice(%d) failed", device); break; }
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) e->sm_count = prop.multiProcessorCount;
+        if (cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
+            rc = fail(nullptr, ZFB_ECUDA, "stream creation failed: %s", cudaGetErrorString(cudaGetLastError()));
+            break;
+        }
+        e->stream = e->own_stream;
+        for (int i = 0; i < 2; ++i) {
+            if (cudaEventCreateWithFlags(&e->ev_h2d[i], cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&e->ev_free[i], cudaEventDisableTiming) != cudaSuccess) {
+                rc = fail(nullptr, ZFB_ECUDA, "event creation failed");
+                break;
+            }
+        }
+        if (rc != ZFB_OK) break;
+        rc = setup_device_once(e);
+        if (rc != ZFB_OK) { g_create_error = e->err; break; }
+        rc = ensure(e, e->ema_valid, sizeof(int));
+        if (rc != ZFB_OK) { g_create_error = e->err; break; }
+        if (cudaMemset(e->ema_valid.p, 0, sizeof(int)) != cudaSuccess) { rc = fail(nullptr, ZFB_ECUDA, "memset failed"); break; }
+    } while (0);
+    if (rc != ZFB_OK) {
+        zfb_destroy(e);
+        return rc;
+    }
+    *out = e;
+    return ZFB_OK;
+}
+
+void zfb_destroy(zfb_engine *e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    if (e->own_stream) cudaStreamSynchronize(e->own_stream);
+    if (e->copy_stream) cudaStreamSynchronize(e->copy_stream);
+    DevBuf *bufs[] = {&e->window, &e->winfft, &e->twiddle, &e->mid[0], &e->mid[1], &e->pow, &e->rows_tmp, &e->ema,
+                      &e->ema_valid, &e->ring, &e->stage_in[0], &e->stage_in[1], &e->big};
+    for (DevBuf *b : bufs) release(*b);
+    for (int i = 0; i < 2; ++i) {
+        if (e->h_stage[i]) cudaFreeHost(e->h_stage[i]);
+        if (e->ev_h2d[i]) cudaEventDestroy(e->ev_h2d[i]);
+        if (e->ev_free[i]) cudaEventDestroy(e->ev_free[i]);
+    }
+    if (e->h_rows) cudaFreeHost(e->h_rows);
+    if (e->own_stream) cudaStreamDestroy(e->own_stream);
+    if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+    delete e;
+}
+
+int zfb_decim_sos(double out24[24]) {
+    if (!out24) return ZFB_EINVAL;
+    double sos[NSEC][6];
+    design_cheby1_sos(sos);
+    memcpy(out24, sos, sizeof sos);
+    return ZFB_OK;
+}
+
+int zfb_plan_geometry(int frame_len, int fft_size, int fft_ratio, int out5[5]) {
+    if (!out5) return ZFB_EINVAL;
+    Geometry g;
+    int rc = geometry(frame_len, fft_size, fft_ratio, g);
+    if (rc != ZFB_OK) return rc;
+    out5[0] = g.ndec;
+    out5[1] = g.nperseg;
+    out5[2] = g.hop;
+    out5[3] = g.nseg;
+    out5[4] = g.nstages;
+    return ZFB_OK;
+}
+
+int zfb_configure(zfb_engine *e, const zfb_config *cfg) {
+    if (!e) return ZFB_EINVAL;
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (!cfg) return fail(e, ZFB_EINVAL, "configure: cfg is NULL");
+    CK(e, cudaSetDevice(e->device));
+    const int N = cfg->fft_size;
+    const int l2 = ilog2_floor(N);
+    if (N < (1 << kMinLog2N) || N > (1 << kMaxLog2N) || (1 << l2) != N)
+        return fail(e, ZFB_EINVAL, "fft_size %d: must be a power of two in [%d, %d]", N, 1 << kMinLog2N,
+                    1 << kMaxLog2N);
+    if (!(cfg->fs > 0.0)) return fail(e, ZFB_EINVAL, "fs must be positive");
+    if (cfg->fft_ratio < 1) return fail(e, ZFB_EINVAL, "fft_ratio %d: must be >= 1", cfg->fft_ratio);
+    if (cfg->dtype != ZFB_DTYPE_C64 && cfg->dtype != ZFB_DTYPE_U8)
+        return fail(e, ZFB_EINVAL, "unknown dtype %d", cfg->dtype);
+    if (cfg->mode != ZFB_MODE_EXACT) return fail(e, ZFB_EINVAL, "unknown mode %d", cfg->mode);
+    if (cfg->row_width < 2 || cfg->row_width > N || (cfg->row_width & 1))
+        return fail(e, ZFB_EINVAL, "row_width %d: must be even and in [2, fft_size]", cfg->row_width);
+    if (!cfg->window) return fail(e, ZFB_EINVAL, "window is NULL");
+    Geometry g;
+    int rc = geometry(cfg->frame_len, N, cfg->fft_ratio, g);
+    if (rc == ZFB_ETOOSHORT)
+        return fail(e, rc, "frame_len %d too short: every decimate-by-2 stage needs more than %d samples "
+                    "(scipy padlen)", cfg->frame_len, PADLEN);
+    if (rc != ZFB_OK) return fail(e, rc, "bad geometry (frame_len %d, fft_size %d, fft_ratio %d)",
+                                  cfg->frame_len, N, cfg->fft_ratio);
+    if (cfg->nperseg != g.nperseg)
+        return fail(e, ZFB_EINVAL, "nperseg %d does not match the plan (%d): call zfb_plan_geometry first",
+                    cfg->nperseg, g.nperseg);
+    if (l2 > kMaxLog2Small && g.nperseg != N)
+        return fail(e, ZFB_EINVAL, "fft_size %d needs a decimated chunk of at least fft_size samples (got %d)",
+                    N, g.ndec);
+
+    const bool geom_changed = !e->configured || e->W != cfg->row_width || e->cfg.fft_size != N ||
+                              e->cfg.fft_ratio != cfg->fft_ratio;
+    // everything below may replace buffers still in use
+    CK(e, cudaStreamSynchronize(e->stream));
+
+    // window -> float, sum w^2 in double (scale = 1/(fs*sum w^2), scipy:_spectral_py.py 'density')
+    std::vector<float> wf((size_t)g.nperseg);
+    double s2 = 0.0;
+    for (int i = 0; i < g.nperseg; ++i) {
+        const double w = cfg->window[i];
+        if (!(w == w) || fabs(w) > 1e30) return fail(e, ZFB_EINVAL, "window[%d] is not finite", i);
+        s2 += w * w;
+        wf[(size_t)i] = (float)w;
+    }
+    if (!(s2 > 0.0)) return fail(e, ZFB_EINVAL, "window has zero energy");
+    rc = ensure(e, e->window, wf.size() * sizeof(float));
+    if (rc) return rc;
+    CK(e, cudaMemcpyAsync(e->window.p, wf.data(), wf.size() * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+    if (l2 > kMaxLog2Small) {
+        // FFT(window) in fp64 for the post-FFT mean removal of the four-step path
+        std::vector<double> re((size_t)N), im((size_t)N, 0.0);
+        for (int i = 0; i < N; ++i) re[(size_t)i] = cfg->window[i];
+        host_fft(re, im);
+        std::vector<float2> wff((size_t)N);
+        for (int i = 0; i < N; ++i) wff[(size_t)i] = make_float2((float)re[(size_t)i], (float)im[(size_t)i]);
+        rc = ensure(e, e->winfft, wff.size() * sizeof(float2));
+        if (rc) return rc;
+        CK(e, cudaMemcpyAsync(e->winfft.p, wff.data(), wff.size() * sizeof(float2), cudaMemcpyHostToDevice, e->stream));
+        CK(e, cudaStreamSynchronize(e->stream));
+    }
+
+    if (!e->configured || e->cfg.fft_size != N) {
+        std::vector<float2> tw((size_t)N);
+        for (int k = 0; k < N; ++k) {
+            const double a = -2.0 * kPi * (double)k / (double)N;
+            tw[(size_t)k] = make_float2((float)cos(a), (float)sin(a));
+        }
+        rc = ensure(e, e->twiddle, tw.size() * sizeof(float2));
+        if (rc) return rc;
+        CK(e, cudaMemcpyAsync(e->twiddle.p, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice, e->stream));
+        CK(e, cudaStreamSynchronize(e->stream));
+    }
+    CK(e, cudaStreamSynchronize(e->stream));       // wf goes out of scope
+
+    // plan
+    e->cfg = *cfg;
+    e->cfg.window = nullptr;
+    e->nstages = g.nstages;
+    memcpy(e->len, g.len, sizeof g.len);
+    e->nperseg = g.nperseg;
+    e->hop = g.hop;
+    e->nseg = g.nseg;
+    e->W = cfg->row_width;
+    e->log2N = l2;
+    e->sum_w2 = s2;
+    for (int s = 0; s < g.nstages; ++s) {
+        const int L = g.len[s];
+        const int tiles = (L + TMAX - 1) / TMAX;
+        int T = (L + tiles - 1) / tiles;
+        T = (T + 15) / 16 * 16;
+        e->tiles[s] = (L + T - 1) / T;
+        e->T[s] = T;
+    }
+    // stage-0 LO tables
+    {
+        StageParams &p = e->sp0;
+        memset(&p, 0, sizeof p);
+        const bool no_lo = (cfg->flags & ZFB_FLAG_NO_LO) != 0;
+        double r = no_lo ? 0.0 : cfg->f_demod / cfg->fs;
+        r -= floor(r);
+        if (r >= 1.0) r = 0.0;
+        const double scaled = ldexp(r, 64);
+        p.phase_inc = (scaled >= 18446744073709551615.0) ? 0ull : (unsigned long long)scaled;
+        DecimConst dc;
+        build_decim_const(dc);
+        const double amp = (no_lo ? 1.0 : sqrt(2.0)) * (double)dc.g;
+        const int vec = (cfg->dtype == ZFB_DTYPE_U8) ? 8 : 2;
+        for (int v = 0; v < 8; ++v) lo_entry(r, v, amp, p.lo_small[v]);
+        for (int it = 0; it < 32; ++it) lo_entry(r, (long long)it * NTHR * vec, 1.0, p.lo_big[it]);
+    }
+    e->group = choose_group(e);
+    e->nsplit_cap = 16;
+
+    // workspaces
+    if (g.nstages >= 1) {
+        rc = ensure(e, e->mid[0], (size_t)e->group * (size_t)g.len[1] * sizeof(float2));
+        if (rc) return rc;
+    }
+    if (g.nstages >= 2) {
+        rc = ensure(e, e->mid[1], (size_t)e->group * (size_t)g.len[2] * sizeof(float2));
+        if (rc) return rc;
+    }
+    rc = ensure(e, e->pow, (size_t)e->group * (size_t)e->nsplit_cap * (size_t)e->W * sizeof(float));
+    if (rc) return rc;
+    if (l2 > kMaxLog2Small) {
+        rc = ensure(e, e->big, big_scratch_bytes(l2, g.nseg, e->group));
+        if (rc) return rc;
+    }
+    rc = ensure(e, e->ema, (size_t)e->W * sizeof(float));
+    if (rc) return rc;
+    if (geom_changed || e->ring_W != e->W || e->ring_rows != e->ring_rows_req) {
+        e->ring_rows = e->ring_rows_req;
+        rc = ensure(e, e->ring, (size_t)e->ring_rows * (size_t)e->W * sizeof(float));
+        if (rc) return rc;
+        e->ring_W = e->W;
+        e->ring_written = 0;
+        CK(e, cudaMemsetAsync(e->ema_valid.p, 0, sizeof(int), e->stream));
+    }
+    e->configured = true;
+    return ZFB_OK;
+}
+
+int zfb_set_stream(zfb_engine *e, void *cuda_stream) {
+    if (!e) return ZFB_EINVAL;
+    std::lock_guard<std::mutex> lk(e->mu);
+    CK(e, cudaSetDevice(e->device));
+    CK(e, cudaStreamSynchronize(e->stream));
+    e->stream = cuda_stream ? (cudaStream_t)cuda_stream : e->own_stream;
+    return ZFB_OK;
+}
+
+int zfb_set_group(zfb_engine *e, int frames_per_group) {
+    if (!e) return ZFB_EINVAL;
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (frames_per_group < 0) return fail(e, ZFB_EINVAL, "frames_per_group must be >= 0");
+    e->group_user = frames_per_group;
+    e->configured = false;      // workspaces are sized per group: re-plan on next configure
+    return ZFB_OK;
+}
+
+int zfb_reset_ema(zfb_engine *e) {
+    if (!e) return ZFB_EINVAL;
+    std::lock_guard<std::mutex> lk(e->mu);
+    CK(e, cudaSetDevice(e->device));
+    CK(e, cudaMemsetAsync(e->ema_valid.p, 0, sizeof(int), e->stream));
+    return ZFB_OK;
+}
+
+int zfb_process_device(zfb_engine *e, const void *d_in, int nframes, float *d_rows) {
+    if (!e) return ZFB_EINVAL;
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (!e->configured) return fail(e, ZFB_ESTATE, "process: engine is not configured");
+    if (!d_in || nframes < 0) return fail(e, ZFB_EINVAL, "process: bad arguments");
+    CK(e, cudaSetDevice(e->device));
+    const size_t fbytes = (size_t)e->cfg.frame_len * sample_bytes(e->cfg);
+    for (int g0 = 0; g0 < nframes; g0 += e->group) {
+        const int gf = (nframes - g0 < e->group) ? nframes - g0 : e->group;
+        int rc = run_group(e, (const char *)d_in + (size_t)g0 * fbytes, gf,
+                           d_rows ? d_rows + (size_t)g0 * e->W : nullptr);
+        if (rc) return rc;
+    }
+    return ZFB_OK;
+}
+
+int zfb_process_host(zfb_engine *e, const void *h_in, int nframes, float *h_rows) {
+    if (!e) return ZFB_EINVAL;
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (!e->configured) return fail(e, ZFB_ESTATE, "process: engine is not configured");
+    if (!h_in || !h_rows || nframes < 0) return fail(e, ZFB_EINVAL, "process: bad arguments");
+    if (nframes == 0) return ZFB_OK;
+    CK(e, cudaSetDevice(e->device));
+    const size_t fbytes = (size_t)e->cfg.frame_len * sample_bytes(e->cfg);
+    // host path pipelines in sub-groups so that copies overlap compute
+    int hg = e->group;
+    if (nframes > 1 && hg > (nframes + 3) / 4) hg = (nframes + 3) / 4;
+    if (hg < 1) hg = 1;
+    const bool pinned_src = is_pinned(h_in);
+    int rc;
+    for (int i = 0; i < 2; ++i) {
+        rc = ensure(e, e->stage_in[i], (size_t)hg * fbytes);
+        if (rc) return rc;
+        if (!pinned_src && e->h_stage_cap[i] < (size_t)hg * fbytes) {
+            if (e->h_stage[i]) CK(e, cudaFreeHost(e->h_stage[i]));
+            e->h_stage[i] = nullptr;
+            e->h_stage_cap[i] = 0;
+            CK(e, cudaMallocHost(&e->h_stage[i], (size_t)hg * fbytes));
+            e->h_stage_cap[i] = (size_t)hg * fbytes;
+        }
+    }
+    const size_t rows_bytes = (size_t)nframes * e->W * sizeof(float);
+    rc = ensure(e, e->rows_tmp, rows_bytes);
+    if (rc) return rc;
+    const bool pinned_dst = is_pinned(h_rows);
+    if (!pinned_dst && e->h_rows_cap < rows_bytes) {
+        if (e->h_rows) CK(e, cudaFreeHost(e->h_rows));
+        e->h_rows = nullptr;
+        e->h_rows_cap = 0;
+        CK(e, cudaMallocHost(&e->h_rows, rows_bytes));
+        e->h_rows_cap = rows_bytes;
+    }
+
+    int it = 0;
+    for (int g0 = 0; g0 < nframes; g0 += hg, ++it) {
+        const int gf = (nframes - g0 < hg) ? nframes - g0 : hg;
+        const int slot = it & 1;
+        const char *src = (const char *)h_in + (size_t)g0 * fbytes;
+        const size_t bytes = (size_t)gf * fbytes;
+        if (e->slot_busy[slot]) {
+            // the device staging slot (and its pinned mirror) is free once the
+            // compute that read it has finished
+            if (!pinned_src) CK(e, cudaEventSynchronize(e->ev_free[slot]));
+            CK(e, cudaStreamWaitEvent(e->copy_stream, e->ev_free[slot], 0));
+        }
+        if (!pinned_src) {
+            memcpy(e->h_stage[slot], src, bytes);
+            src = (const char *)e->h_stage[slot];
+        }
+        CK(e, cudaMemcpyAsync(e->stage_in[slot].p, src, bytes, cudaMemcpyHostToDevice, e->copy_stream));
+        CK(e, cudaEventRecord(e->ev_h2d[slot], e->copy_stream));
+        CK(e, cudaStreamWaitEvent(e->stream, e->ev_h2d[slot], 0));
+        e->counters[3] += bytes;
+        for (int q0 = 0; q0 < gf; q0 += e->group) {
+            const int qf = (gf - q0 < e->group) ? gf - q0 : e->group;
+            rc = run_group(e, (const char *)e->stage_in[slot].p + (size_t)q0 * fbytes, qf,
+                           (float *)e->rows_tmp.p + (size_t)(g0 + q0) * e->W);
+            if (rc) return rc;
+        }
+        CK(e, cudaEventRecord(e->ev_free[slot], e->stream));
+        e->slot_busy[slot] = true;
+    }
+    float *dst = pinned_dst ? h_rows : e->h_rows;
+    CK(e, cudaMemcpyAsync(dst, e->rows_tmp.p, rows_bytes, cudaMemcpyDeviceToHost, e->stream));
+    CK(e, cudaStreamSynchronize(e->stream));
+    if (!pinned_dst) memcpy(h_rows, e->h_rows, rows_bytes);
+    e->counters[4] += rows_bytes;
+    e->slot_busy[0] = e->slot_busy[1] = false;
+    return ZFB_OK;
+}
+
+int zfb_synchronize(zfb_engine *e) {
+    if (!e) return ZFB_EINVAL;
+    std::lock_guard<std::mutex> lk(e->mu);
+    CK(e, cudaSetDevice(e->device));
+    CK(e, cudaStreamSynchronize(e->stream));
+    return ZFB_OK;
+}
+
+int zfb_debug_read_decimated(zfb_engine *e, float *h_out_iq, int max_samples) {
+    if (!e) return ZFB_EINVAL;
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (!e->configured) return fail(e, ZFB_ESTATE, "engine is not configured");
+    if (e->nstages < 1 || e->last_group_frames < 1)
+        return fail(e, ZFB_ESTATE, "no decimated chunk available (fft_ratio < 2 or nothing processed)");
+    if (!h_out_iq || max_samples < 0) return fail(e, ZFB_EINVAL, "bad arguments");
+    CK(e, cudaSetDevice(e->device));
+    int n = e->len[e->nstages];
+    if (n > max_samples) n = max_samples;
+    CK(e, cudaStreamSynchronize(e->stream));
+    CK(e, cudaMemcpy(h_out_iq, e->mid[(e->nstages - 1) & 1].p, (size_t)n * sizeof(float2), cudaMemcpyDeviceToHost));
+    e->counters[4] += (size_t)n * sizeof(float2);
+    return n;
+}
+
+int zfb_ring_configure(zfb_engine *e, int rows) {
+    if (!e) return ZFB_EINVAL;
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (rows < 1) return fail(e, ZFB_EINVAL, "ring rows must be >= 1");
+    e->ring_rows_req = rows;
+    if (e->configured && rows != e->ring_rows) {
+        CK(e, cudaSetDevice(e->device));
+        CK(e, cudaStreamSynchronize(e->stream));
+        e->ring_rows = rows;
+        int rc = ensure(e, e->ring, (size_t)rows * (size_t)e->W * sizeof(float));
+        if (rc) return rc;
+        e->ring_written = 0;
+    }
+    return ZFB_OK;
+}
+
+int64_t zfb_ring_rows_written(const zfb_engine *e) {
+    if (!e) return ZFB_EINVAL;
+    std::lock_guard<std::mutex> lk(e->mu);
+    return e->ring_written;
+}
+
+int zfb_read_rows(zfb_engine *e, int age, int nrows, float *h_out) {
+    if (!e) return ZFB_EINVAL;
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (!e->configured) return fail(e, ZFB_ESTATE, "engine is not configured");
+    if (age < 0 || nrows < 1 || !h_out) return fail(e, ZFB_EINVAL, "read_rows: bad arguments");
+    const int64_t have = e->ring_written < e->ring_rows ? e->ring_written : e->ring_rows;
+    if ((int64_t)age + nrows > have)
+        return fail(e, ZFB_EINVAL, "read_rows: asked for rows %d..%d back but the ring holds %lld", age,
+                    age + nrows - 1, (long long)have);
+    CK(e, cudaSetDevice(e->device));
+    const int64_t first = e->ring_written - age - nrows;          // chronological index
+    const size_t rb = (size_t)e->W * sizeof(float);
+    int done = 0;
+    while (done < nrows) {
+        const int64_t slot = (first + done) % e->ring_rows;
+        int run = nrows - done;
+        if (slot + run > e->ring_rows) run = (int)(e->ring_rows - slot);
+        CK(e, cudaMemcpyAsync((char *)h_out + (size_t)done * rb, (const char *)e->ring.p + (size_t)slot * rb,
+                              (size_t)run * rb, cudaMemcpyDeviceToHost, e->stream));
+        done += run;
+    }
+    CK(e, cudaStreamSynchronize(e->stream));
+    e->counters[4] += (size_t)nrows * rb;
+    return ZFB_OK;
+}
+
+int zfb_alloc_pinned(size_t bytes, void **out) {
+    if (!out) return ZFB_EINVAL;
+    *out = nullptr;
+    cudaError_t st = cudaMallocHost(out, bytes ? bytes : 1);
+    if (st != cudaSuccess) {
+        cudaGetLastError();
+        return fail(nullptr, ZFB_ENOMEM, "cudaMallocHost(%zu) failed: %s", bytes, cudaGetErrorString(st));
+    }
+    return ZFB_OK;
+}
+
+int zfb_free_pinned(void *p) {
+    if (!p) return ZFB_OK;
+    return cudaFreeHost(p) == cudaSuccess ? ZFB_OK : ZFB_ECUDA;
+}
+
+int zfb_get_counters(const zfb_engine *e, uint64_t out5[5]) {
+    if (!e || !out5) return ZFB_EINVAL;
+    std::lock_guard<std::mutex> lk(e->mu);
+    memcpy(out5, e->counters, sizeof e->counters);
+    return ZFB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,328 @@
+// Welch PSD of (decimated) chunks, fused with detrend, window, shared-memory
+// Stockham FFT, |X|^2, segment mean, density scale, fftshift and centre crop;
+// plus the row finalisation (EMA on linear power, 20*log10).
+//
+// Replaces scipy.signal.welch(chunk, fs, window=taper, nperseg=N, nfft=N)
+// (pypanadapter_spectrum.py:2111, pypanadapter_thread.py:1536/1538 ->
+// scipy/signal/_spectral_py.py:515-972), np.fft.fftshift(spec)[N//2-W//2:
+// N//2+W//2] (S:2114, T:1543) and 20*np.log10(abs(spec)) (S:2117-2119, T:1548).
+//
+// FFT: N = 2^m points, N/PPT threads, PPT (8 or 16) points per thread.
+// Radix-8 passes (+ radix-4 passes when m % 3 != 0); butterflies are done in
+// registers, passes exchange data through shared memory in Stockham autosort
+// order with a +1/16 padding.  The first pass is fed straight from global
+// memory and the last pass accumulates |X|^2 in registers, so a segment
+// touches smem only between passes.  With 50 % overlap the second half of a
+// segment is the first half of the next one *in the same thread's registers*
+// (element tid + m*N/PPT moves from m to m - PPT/2), so every sample is read
+// from global memory exactly once.  Twiddles come from an fp64-generated
+// table exp(-2 pi i k / N).
+#pragma once
+#include "zfb_common.cuh"
+
+namespace zfb {
+
+struct WelchParams {
+    const void  *in;          // [frames][in_stride], kind per template
+    long long    in_stride;
+    int          len;         // samples per frame available to Welch
+    int          flip;        // only for raw kinds (R == 1 path)
+    int          nperseg;     // window length (== N unless the chunk is short)
+    int          hop;
+    int          nseg;
+    int          seg_per_split;   // segments handled by one CTA
+    int          nsplit;          // CTAs per frame (gridDim.x)
+    int          reuse;           // hop == N/2 && nperseg == N: register reuse
+    const float *window;      // nperseg taps
+    const float2*twiddle;     // N entries exp(-2 pi i k / N)
+    int          W;           // row width
+    float       *pow_out;     // [frames][nsplit][W] sum_s |X|^2, fftshifted + cropped
+};
+
+__device__ __forceinline__ int fpad(int a) { return a + (a >> 4); }
+
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// multiply by -i (forward FFT quarter turn)
+__device__ __forceinline__ float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }
+
+__device__ __forceinline__ void bfly2(float2 &a, float2 &b) {
+    float2 t = csub(a, b);
+    a = cadd(a, b);
+    b = t;
+}
+
+// in-place 4-point DFT, natural order output
+__device__ __forceinline__ void dft4(float2 &a0, float2 &a1, float2 &a2, float2 &a3) {
+    bfly2(a0, a2);
+    bfly2(a1, a3);
+    a3 = mul_mi(a3);
+    bfly2(a0, a1);
+    bfly2(a2, a3);
+    // now a0=X0, a1=X2, a2=X1, a3=X3
+    float2 t = a1; a1 = a2; a2 = t;
+}
+
+// in-place 8-point DFT, natural order output
+__device__ __forceinline__ void dft8(float2 *v) {
+    const float h = 0.70710678118654752440f;
+    bfly2(v[0], v[4]); bfly2(v[1], v[5]); bfly2(v[2], v[6]); bfly2(v[3], v[7]);
+    v[5] = make_float2((v[5].x + v[5].y) * h, (v[5].y - v[5].x) * h);    // * exp(-i pi/4)
+    v[6] = mul_mi(v[6]);                                                  // * exp(-i pi/2)
+    v[7] = make_float2((v[7].y - v[7].x) * h, -(v[7].x + v[7].y) * h);   // * exp(-3i pi/4)
+    bfly2(v[0], v[2]); bfly2(v[1], v[3]); bfly2(v[4], v[6]); bfly2(v[5], v[7]);
+    v[3] = mul_mi(v[3]);
+    v[7] = mul_mi(v[7]);
+    bfly2(v[0], v[1]); bfly2(v[2], v[3]); bfly2(v[4], v[5]); bfly2(v[6], v[7]);
+    // bit-reversed -> natural: (0,4,2,6,1,5,3,7)
+    float2 t;
+    t = v[1]; v[1] = v[4]; v[4] = t;
+    t = v[3]; v[3] = v[6]; v[6] = t;
+}
+
+template <int RADIX> struct Log2R;
+template <> struct Log2R<2> { static constexpr int v = 1; };
+template <> struct Log2R<4> { static constexpr int v = 2; };
+template <> struct Log2R<8> { static constexpr int v = 3; };
+
+// One Stockham pass of radix RADIX over the PPT values a thread holds.
+// Thread `tid` of nt = N/PPT holds v[m] = data[tid + m*nt].  A thread does
+// NB = PPT/RADIX butterflies j = tid + c*nt whose inputs j + q*N/RADIX are
+// exactly its own v[c + NB*q].  Ns = product of the radices done so far.
+// Threads with tid >= nt (only when N/PPT < 32) idle but keep the barriers.
+// `tw` is the table exp(-2 pi i k / 2^log2tw) (log2tw may exceed log2 of this
+// FFT's length: sub-FFTs of the four-step path share the big table).
+template <int RADIX, int PPT>
+__device__ __forceinline__ void fft_pass(float2 (&v)[PPT], int tid, int nt, int log2tw, int log2Ns,
+                                         const float2 *__restrict__ tw, float2 *sm, bool last,
+                                         bool active) {
+    constexpr int NB = PPT / RADIX;               // butterflies per thread
+    constexpr int LR = Log2R<RADIX>::v;
+    const int Ns = 1 << log2Ns;
+#pragma unroll
+    for (int c = 0; c < NB; ++c) {
+        const int j = tid + c * nt;
+        const int k = j & (Ns - 1);
+        float2 a[RADIX];
+#pragma unroll
+        for (int r = 0; r < RADIX; ++r) a[r] = v[c + NB * r];
+        if (log2Ns > 0 && active) {
+            // twiddle exp(-2 pi i r k / (Ns*RADIX)) = tw[r * k * 2^log2tw/(Ns*RADIX)]
+            const int step = k << (log2tw - log2Ns - LR);
+#pragma unroll
+            for (int r = 1; r < RADIX; ++r) a[r] = cmul(a[r], __ldg(tw + r * step));
+        }
+        if (RADIX == 8) dft8(a);
+        else if (RADIX == 4) dft4(a[0], a[1], a[2], a[3]);
+        else bfly2(a[0], a[1]);
+        if (last) {
+#pragma unroll
+            for (int r = 0; r < RADIX; ++r) v[c + NB * r] = a[r];
+        } else if (active) {
+            const int j0 = ((j >> log2Ns) << (log2Ns + LR)) + k;
+#pragma unroll
+            for (int r = 0; r < RADIX; ++r) sm[fpad(j0 + r * Ns)] = a[r];
+        }
+    }
+    if (!last) {
+        __syncthreads();
+        if (active) {
+#pragma unroll
+            for (int m = 0; m < PPT; ++m) v[m] = sm[fpad(tid + m * nt)];
+        }
+        __syncthreads();
+    }
+}
+
+// full N-point forward FFT of the thread-distributed array; on return
+// v[m] = X[tid + m*N/PPT] (natural order)
+template <int LOG2N, int PPT>
+__device__ __forceinline__ void fft_block(float2 (&v)[PPT], int tid, const float2 *tw, float2 *sm) {
+    constexpr int NT = (1 << LOG2N) / PPT;
+    constexpr int R8 = (LOG2N % 3 == 1) ? (LOG2N / 3 - 1) : (LOG2N / 3);   // radix-8 passes
+    constexpr int REM = LOG2N - 3 * R8;                                   // 0, 2 or 4 bits
+    const bool active = tid < NT;
+    int log2Ns = 0;
+#pragma unroll
+    for (int p = 0; p < R8; ++p) {
+        const bool last = (REM == 0) && (p == R8 - 1);
+        fft_pass<8, PPT>(v, tid, NT, LOG2N, log2Ns, tw, sm, last, active);
+        log2Ns += 3;
+    }
+    if (REM == 2) {
+        fft_pass<4, PPT>(v, tid, NT, LOG2N, log2Ns, tw, sm, true, active);
+    } else if (REM == 4) {
+        fft_pass<4, PPT>(v, tid, NT, LOG2N, log2Ns, tw, sm, false, active);
+        log2Ns += 2;
+        fft_pass<4, PPT>(v, tid, NT, LOG2N, log2Ns, tw, sm, true, active);
+    }
+}
+
+template <int KIND>
+__device__ __forceinline__ float2 welch_fetch(const void *frame_in, int idx, int len, int flip) {
+    if (KIND == KIND_U8_RAW) {
+        const unsigned char *s = (const unsigned char *)frame_in;
+        const int i = flip ? (len - 1 - idx) : idx;
+        const unsigned short h = __ldg((const unsigned short *)(s + 2 * (size_t)i));
+        return make_float2(u8_to_f(h & 0xffu), u8_to_f(h >> 8));
+    } else {
+        const float2 *s = (const float2 *)frame_in;
+        const int i = (KIND == KIND_C64_RAW && flip) ? (len - 1 - idx) : idx;
+        return __ldg(s + i);
+    }
+}
+
+// sum a complex value over the CTA (all threads get the result)
+template <int NTHREADS>
+__device__ __forceinline__ float2 block_sum(float2 sum, int tid, float2 *red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sum.x += __shfl_xor_sync(0xffffffffu, sum.x, o);
+        sum.y += __shfl_xor_sync(0xffffffffu, sum.y, o);
+    }
+    if (NTHREADS > 32) {
+        if ((tid & 31) == 0) red[tid >> 5] = sum;
+        __syncthreads();
+        if (tid < 32) {
+            float2 t = (tid < NTHREADS / 32) ? red[tid] : make_float2(0.f, 0.f);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                t.x += __shfl_xor_sync(0xffffffffu, t.x, o);
+                t.y += __shfl_xor_sync(0xffffffffu, t.y, o);
+            }
+            if (tid == 0) red[32] = t;
+        }
+        __syncthreads();
+        sum = red[32];
+    }
+    return sum;
+}
+
+template <int LOG2N, int PPT>
+struct WelchShape {
+    static constexpr int N = 1 << LOG2N;
+    static constexpr int NT = N / PPT;                       // working threads
+    static constexpr int NTHREADS = NT < 32 ? 32 : NT;       // launched threads
+    static constexpr size_t SMEM = (size_t)(N + (N >> 4) + 1) * sizeof(float2);
+};
+
+template <int LOG2N, int PPT, int KIND>
+__global__ void __launch_bounds__((WelchShape<LOG2N, PPT>::NTHREADS))
+welch_kernel(const WelchParams p) {
+    using S = WelchShape<LOG2N, PPT>;
+    constexpr int N = S::N;
+    constexpr int NT = S::NT;
+    constexpr int H = PPT / 2;
+    ZFB_DYN_SMEM(smem_raw);
+    float2 *sm = reinterpret_cast<float2 *>(smem_raw);     // fpad(N) complex
+    __shared__ float2 red[33];
+
+    const int tid = threadIdx.x;
+    const bool active = tid < NT;
+    const int split = blockIdx.x;
+    const int frame = blockIdx.y;
+    const size_t esz = (KIND == KIND_U8_RAW) ? 2 : 8;
+    const char *frame_in = (const char *)p.in + (size_t)frame * (size_t)p.in_stride * esz;
+
+    float acc[PPT];
+#pragma unroll
+    for (int m = 0; m < PPT; ++m) acc[m] = 0.f;
+    const float inv_n = 1.0f / (float)p.nperseg;
+
+    const int s_begin = split * p.seg_per_split;
+    const int s_end = min(p.nseg, s_begin + p.seg_per_split);
+    float2 raw[PPT];
+
+    for (int s = s_begin; s < s_end; ++s) {
+        const int base = s * p.hop;
+        const bool carry = p.reuse && (s > s_begin);
+#pragma unroll
+        for (int m = 0; m < PPT; ++m) {
+            const int idx = tid + m * NT;
+            if (m < H && carry) {
+                raw[m] = raw[m + H];
+            } else {
+                raw[m] = (active && idx < p.nperseg)
+                             ? welch_fetch<KIND>(frame_in, base + idx, p.len, p.flip)
+                             : make_float2(0.f, 0.f);
+            }
+        }
+        float2 sum = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int m = 0; m < PPT; ++m) sum = cadd(sum, raw[m]);
+        // detrend='constant': subtract the segment's complex mean
+        sum = block_sum<S::NTHREADS>(sum, tid, red);
+        const float2 mean = make_float2(sum.x * inv_n, sum.y * inv_n);
+        float2 v[PPT];
+#pragma unroll
+        for (int m = 0; m < PPT; ++m) {
+            const int idx = tid + m * NT;
+            const float w = (active && idx < p.nperseg) ? __ldg(p.window + idx) : 0.f;
+            v[m].x = (raw[m].x - mean.x) * w;
+            v[m].y = (raw[m].y - mean.y) * w;
+        }
+        fft_block<LOG2N, PPT>(v, tid, p.twiddle, sm);
+#pragma unroll
+        for (int m = 0; m < PPT; ++m) acc[m] = fmaf(v[m].x, v[m].x, fmaf(v[m].y, v[m].y, acc[m]));
+    }
+
+    // fftshift + centre crop: natural bin k sits at column (k + N/2) mod N
+    if (!active) return;
+    const int c0 = N / 2 - p.W / 2;
+    float *row = p.pow_out + ((size_t)frame * p.nsplit + split) * p.W;
+#pragma unroll
+    for (int m = 0; m < PPT; ++m) {
+        const int k = tid + m * NT;
+        const int col = ((k + N / 2) & (N - 1)) - c0;
+        if (col >= 0 && col < p.W) row[col] = acc[m];
+    }
+}
+
+// rows: sum the per-split partial sums in fixed order, scale, optional EMA
+// across consecutive frames on linear power, then dB20.
+//   a_0 = p_0 (when the state is empty), a_i = alpha p_i + (1-alpha) a_(i-1)
+// One thread per column; frames are walked in order (EMA is order dependent).
+struct FinalizeParams {
+    const float *pow_in;      // [nframes][nsplit][W]
+    int    nframes, nsplit, W;
+    float  scale;             // 1 / (fs * sum w^2) / nseg
+    float  alpha;             // < 0: EMA off
+    int    linear;            // 1: emit linear power instead of dB20
+    float *ema_state;         // [W]
+    int   *ema_valid;         // device flag: state holds a row
+    float *rows;              // [nframes][W] or null
+    float *ring;              // [ring_rows][W] or null
+    long long ring_pos;       // ring slot of frame 0
+    int    ring_rows;
+};
+
+__global__ void finalize_rows_kernel(const FinalizeParams p) {
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= p.W) return;
+    const bool use_ema = p.alpha >= 0.f;
+    float a = 0.f;
+    bool have = false;
+    if (use_ema) {
+        have = (*p.ema_valid != 0);
+        if (have) a = p.ema_state[col];
+    }
+    for (int f = 0; f < p.nframes; ++f) {
+        const float *src = p.pow_in + (size_t)f * p.nsplit * p.W + col;
+        float pw = 0.f;
+        for (int s = 0; s < p.nsplit; ++s) pw += src[(size_t)s * p.W];
+        pw *= p.scale;
+        if (use_ema) {
+            a = have ? fmaf(p.alpha, pw - a, a) : pw;
+            have = true;
+            pw = a;
+        }
+        const float out = p.linear ? pw : 20.0f * log10f(fabsf(pw));
+        if (p.rows) p.rows[(size_t)f * p.W + col] = out;
+        if (p.ring) p.ring[(size_t)((p.ring_pos + f) % p.ring_rows) * p.W + col] = out;
+    }
+    if (use_ema) p.ema_state[col] = a;
+}
+
+__global__ void set_flag_kernel(int *flag, int v) { *flag = v; }
+
+}  // namespace zfb

@@ -1,0 +1,296 @@
+"""Python face of the zoom-FFT PSD engine (thin layer over the C ABI).
+
+``ZoomPSD`` wraps one ``zfb_engine`` (one CUDA device).  ``zoom_psd`` is the
+fused frame call that replaces the bodies of the reference's
+``ApplicationDisplay.zoomfft`` + ``update`` (pypanadapter_spectrum.py:2088-2119)
+and ``PSD.update`` (pypanadapter_thread.py:1513-1549):
+
+    chunk -> [uint8 -> complex, np.flip] -> x * sqrt(2) exp(-2j pi f_demod t)
+          -> scipy.signal.decimate(., 2) x log2(R) -> scipy.signal.welch
+          -> fftshift + centre crop -> 20*log10(abs(.)) [-> EMA]
+
+All arithmetic happens in the sm_100a kernels; this file only validates
+arguments, builds the window table (host, ``scipy.signal.get_window`` -- the
+same call the reference's welch makes, scipy:_spectral_py.py:901) and moves
+pointers.  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+
+import numpy as np
+
+from . import _lib
+
+_ERRNAMES = {
+    _lib.ZFB_EINVAL: "EINVAL", _lib.ZFB_ENOMEM: "ENOMEM", _lib.ZFB_ENODEV: "ENODEV",
+    _lib.ZFB_ECUDA: "ECUDA", _lib.ZFB_ESTATE: "ESTATE", _lib.ZFB_ETOOSHORT: "ETOOSHORT",
+}
+
+
+class ZoomFFTError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__("%s (%s)" % (message, _ERRNAMES.get(code, code)))
+        self.code = code
+
+
+_window_cache: dict = {}
+_window_lock = threading.Lock()
+
+
+def window_table(window, nperseg: int) -> np.ndarray:
+    """Periodic window of ``nperseg`` taps exactly as ``scipy.signal.welch``
+    builds it (``get_window(window, nperseg)``, fftbins=True); accepts the
+    taper dialog's ``str`` or ``(name, p0[, p1])`` forms (S:1354-1363) or an
+    explicit array (scipy's array_like window)."""
+    if isinstance(window, (str, tuple)):
+        key = (window if isinstance(window, str) else tuple(window), int(nperseg))
+        with _window_lock:
+            w = _window_cache.get(key)
+        if w is None:
+            from scipy.signal import get_window
+            w = np.ascontiguousarray(get_window(window, int(nperseg)), dtype=np.float64)
+            w.setflags(write=False)
+            with _window_lock:
+                _window_cache[key] = w
+        return w
+    w = np.ascontiguousarray(window, dtype=np.float64)
+    if w.ndim != 1 or w.shape[0] != nperseg:
+        raise ValueError("window must have length nperseg")   # scipy:_spectral_py.py _triage_segments
+    return w
+
+
+def crop_width(fft_size: int, fft_ratio, crop) -> int:
+    """Row width W: ``'thread'`` -> ``2*int(.5*N/R)`` (T:1542); int -> the
+    ``N_WIN`` of S:2114 (rounded down to even, as the slice does); None -> N."""
+    if crop is None:
+        return int(fft_size)
+    if isinstance(crop, str):
+        if crop != "thread":
+            raise ValueError("crop must be 'thread', an int or None")
+        return 2 * int(.5 * fft_size / fft_ratio)
+    return 2 * (int(crop) // 2)
+
+
+def plan_geometry(frame_len: int, fft_size: int, fft_ratio: int, lib=None) -> dict:
+    """Lengths the reference's scipy calls produce for this frame shape."""
+    lib = lib or _lib.product_library()
+    out = (C.c_int * 5)()
+    rc = lib.zfb_plan_geometry(int(frame_len), int(fft_size), int(fft_ratio), out)
+    if rc == _lib.ZFB_ETOOSHORT:
+        # scipy raises ValueError from sosfiltfilt's _validate_pad
+        raise ValueError("The length of the input vector x must be greater than padlen, which is 27.")
+    if rc != 0:
+        raise ZoomFFTError(rc, "bad frame geometry (frame_len=%r, fft_size=%r, fft_ratio=%r)"
+                           % (frame_len, fft_size, fft_ratio))
+    return dict(ndec=out[0], nperseg=out[1], hop=out[2], nseg=out[3], nstages=out[4])
+
+
+class ZoomPSD:
+    """One engine on one CUDA device.  Thread-safe (the C side serialises)."""
+
+    def __init__(self, device: int = 0, *, lib=None):
+        self._lib = lib or _lib.product_library()
+        self._h = C.c_void_p()
+        rc = self._lib.zfb_create(int(device), C.byref(self._h))
+        if rc != 0:
+            msg = self._lib.zfb_last_error(None)
+            raise ZoomFFTError(rc, "zfb_create(device=%d): %s" % (device, msg.decode() if msg else "?"))
+        self.device = int(device)
+        self._key = None
+        self.row_width = 0
+        self.frame_len = 0
+        self.dtype = None
+        self.geometry = None
+
+    # -- life cycle ------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.zfb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, rc, what):
+        if rc < 0:
+            msg = self._lib.zfb_last_error(self._h)
+            raise ZoomFFTError(rc, "%s: %s" % (what, msg.decode() if msg else "?"))
+        return rc
+
+    # -- configuration ---------------------------------------------------
+    def configure(self, fs, fft_size, fft_ratio, frame_len, window="hamming", *,
+                  dtype="c64", flip=False, f_demod=1.0, crop="thread",
+                  ema_alpha=None, no_lo=False, linear=False):
+        """Plan for a frame shape (cheap if nothing changed).  Mirrors the
+        AppState the reference reads per frame (S:1492-1497)."""
+        fft_ratio_i = int(fft_ratio)
+        wkey = window if isinstance(window, (str, tuple)) else ("array", np.asarray(window).tobytes())
+        key = (float(fs), int(fft_size), float(fft_ratio), int(frame_len), wkey, dtype, bool(flip),
+               float(f_demod), crop, ema_alpha, bool(no_lo), bool(linear))
+        if key == self._key:
+            return self
+        geo = plan_geometry(frame_len, fft_size, fft_ratio_i, self._lib)
+        W = crop_width(fft_size, fft_ratio, crop)
+        w = window_table(window, geo["nperseg"])
+        cfg = _lib.ZfbConfig()
+        cfg.fs = float(fs)
+        cfg.fft_size = int(fft_size)
+        cfg.fft_ratio = fft_ratio_i
+        cfg.frame_len = int(frame_len)
+        cfg.row_width = int(W)
+        cfg.nperseg = geo["nperseg"]
+        cfg.dtype = {"c64": _lib.ZFB_DTYPE_C64, "u8": _lib.ZFB_DTYPE_U8}[dtype]
+        cfg.flip = 1 if flip else 0
+        cfg.mode = _lib.ZFB_MODE_EXACT
+        cfg.flags = (_lib.ZFB_FLAG_NO_LO if no_lo else 0) | (_lib.ZFB_FLAG_LINEAR if linear else 0)
+        cfg.f_demod = float(f_demod)
+        cfg.ema_alpha = -1.0 if ema_alpha is None else float(ema_alpha)
+        cfg.window = w.ctypes.data_as(C.POINTER(C.c_double))
+        self._check(self._lib.zfb_configure(self._h, C.byref(cfg)), "zfb_configure")
+        self._key = key
+        self.row_width = int(W)
+        self.frame_len = int(frame_len)
+        self.dtype = dtype
+        self.geometry = geo
+        return self
+
+    def set_group(self, frames_per_group: int):
+        self._check(self._lib.zfb_set_group(self._h, int(frames_per_group)), "zfb_set_group")
+        self._key = None
+
+    def set_stream(self, cuda_stream_ptr):
+        self._check(self._lib.zfb_set_stream(self._h, C.c_void_p(cuda_stream_ptr or 0)), "zfb_set_stream")
+
+    def reset_ema(self):
+        self._check(self._lib.zfb_reset_ema(self._h), "zfb_reset_ema")
+
+    def ring_configure(self, rows: int):
+        self._check(self._lib.zfb_ring_configure(self._h, int(rows)), "zfb_ring_configure")
+
+    # -- hot path --------------------------------------------------------
+    def _as_wire(self, frames):
+        """(nframes, frame_len) in the configured wire dtype, C-contiguous.
+        complex128 (what pyrtlsdr / the reference's Data hand over) is cast to
+        complex64 here -- the device computes in fp32."""
+        a = np.asarray(frames)
+        if self.dtype == "u8":
+            if a.dtype != np.uint8:
+                raise TypeError("engine is configured for uint8 IQ, got %s" % a.dtype)
+            per = 2 * self.frame_len
+        else:
+            if a.dtype != np.complex64:
+                if not np.issubdtype(a.dtype, np.number):
+                    raise TypeError("unsupported sample dtype %s" % a.dtype)
+                a = a.astype(np.complex64)
+            per = self.frame_len
+        if a.ndim == 1:
+            a = a.reshape(1, -1)
+        if a.ndim != 2 or a.shape[1] != per:
+            raise ValueError("frames must have shape (nframes, %d), got %r" % (per, a.shape))
+        return np.ascontiguousarray(a)
+
+    def process(self, frames, out=None) -> np.ndarray:
+        """HOST buffers in, HOST rows out (float32 (nframes, W)); H2D / D2H are
+        overlapped with compute on the engine's copy stream."""
+        if self._key is None:
+            raise ZoomFFTError(_lib.ZFB_ESTATE, "process: engine is not configured")
+        a = self._as_wire(frames)
+        n = a.shape[0]
+        if out is None:
+            out = np.empty((n, self.row_width), dtype=np.float32)
+        elif out.dtype != np.float32 or out.shape != (n, self.row_width) or not out.flags.c_contiguous:
+            raise ValueError("out must be C-contiguous float32 of shape (%d, %d)" % (n, self.row_width))
+        self._check(self._lib.zfb_process_host(self._h, C.c_void_p(a.ctypes.data), n,
+                                               C.c_void_p(out.ctypes.data)), "zfb_process_host")
+        return out
+
+    def process_device(self, d_in_ptr: int, nframes: int, d_rows_ptr: int | None = None):
+        """DEVICE pointers in/out (asynchronous; rows also land in the ring)."""
+        self._check(self._lib.zfb_process_device(self._h, C.c_void_p(d_in_ptr), int(nframes),
+                                                 C.c_void_p(d_rows_ptr or 0)), "zfb_process_device")
+
+    def synchronize(self):
+        self._check(self._lib.zfb_synchronize(self._h), "zfb_synchronize")
+
+    def read_decimated(self) -> np.ndarray:
+        """Mixed + decimated chunk of the last group's first frame (what the
+        reference's zoomfft returns, S:2100), complex64."""
+        n = self.geometry["ndec"]
+        out = np.empty(n, dtype=np.complex64)
+        got = self._check(self._lib.zfb_debug_read_decimated(self._h, C.c_void_p(out.ctypes.data), n),
+                          "zfb_debug_read_decimated")
+        return out[:got]
+
+    # -- device-resident waterfall ring ------------------------------------
+    @property
+    def rows_written(self) -> int:
+        return int(self._lib.zfb_ring_rows_written(self._h))
+
+    def read_rows(self, nrows: int = 1, age: int = 0) -> np.ndarray:
+        out = np.empty((int(nrows), self.row_width), dtype=np.float32)
+        self._check(self._lib.zfb_read_rows(self._h, int(age), int(nrows), C.c_void_p(out.ctypes.data)),
+                    "zfb_read_rows")
+        return out
+
+    def counters(self) -> dict:
+        c = (C.c_uint64 * 5)()
+        self._check(self._lib.zfb_get_counters(self._h, c), "zfb_get_counters")
+        return dict(frames=int(c[0]), samples=int(c[1]), kernels=int(c[2]),
+                    h2d_bytes=int(c[3]), d2h_bytes=int(c[4]))
+
+
+def decim_sos(lib=None) -> np.ndarray:
+    """The cheby1(8, 0.05, 0.4) SOS the device decimator realises."""
+    lib = lib or _lib.product_library()
+    out = (C.c_double * 24)()
+    lib.zfb_decim_sos(out)
+    return np.array(out[:], dtype=np.float64).reshape(4, 6)
+
+
+# ---------------------------------------------------------------------------
+# module-level convenience: one cached engine per device
+# ---------------------------------------------------------------------------
+_engines: dict = {}
+_engines_lock = threading.Lock()
+
+
+def default_engine(device: int = 0) -> ZoomPSD:
+    with _engines_lock:
+        e = _engines.get(device)
+        if e is None:
+            e = _engines[device] = ZoomPSD(device)
+        return e
+
+
+def zoom_psd(chunk, fs, fft_size, fft_ratio, window, *, f_demod=1.0, crop="thread",
+             flip=False, ema_alpha=None, engine: ZoomPSD | None = None) -> np.ndarray:
+    """One dB20 waterfall row of one chunk (float64 ndarray[W]).
+
+    ``chunk``: 1-D complex64/complex128, or interleaved uint8 I,Q (RTL-SDR).
+    ``crop``: ``'thread'`` reproduces PSD.update (T:1542-1543); an int N_WIN
+    reproduces ApplicationDisplay.update (S:2114); None keeps all N bins.
+    """
+    chunk = np.asarray(chunk)
+    if chunk.ndim != 1:
+        raise ValueError("chunk must be 1-D")
+    eng = engine or default_engine()
+    if chunk.dtype == np.uint8:
+        if chunk.size % 2:
+            raise ValueError("uint8 IQ stream must hold an even number of bytes")
+        dtype, n = "u8", chunk.size // 2
+    else:
+        dtype, n = "c64", chunk.size
+    eng.configure(fs, fft_size, fft_ratio, n, window, dtype=dtype, flip=flip,
+                  f_demod=f_demod, crop=crop, ema_alpha=ema_alpha)
+    return eng.process(chunk)[0].astype(np.float64)
