@@ -153,6 +153,21 @@ int  zfb_plan_geometry(int frame_len, int fft_size, int fft_ratio, int out5[5]);
  * [3] H2D bytes, [4] D2H bytes. */
 int  zfb_get_counters(const zfb_engine *e, uint64_t out5[5]);
 
+
+/* ---- per-kernel device timing (bench.py's roofline leg) ------------------ */
+/* kernel classes: 0..15 = decimate-by-2 stage s (replaces scipy.signal.
+ * decimate call s of the loop at S:2097-2098), 16 = Welch kernel / four-step
+ * column pass, 17 = four-step row pass (both: scipy.signal.welch, S:2111),
+ * 18 = row finalisation (S:2114-2119 + EMA). */
+#define ZFB_PROF_CLASSES 19
+/* on != 0: bracket every kernel launch with CUDA events on the engine's
+ * stream (no host synchronisation is added). */
+int  zfb_set_profiling(zfb_engine *e, int on);
+/* synchronise, add up the recorded intervals per class and clear them:
+ * ms_out[c] = total device milliseconds, launches_out[c] = launches timed. */
+int  zfb_get_profile(zfb_engine *e, double ms_out[ZFB_PROF_CLASSES],
+                     uint64_t launches_out[ZFB_PROF_CLASSES]);
+
 #ifdef __cplusplus
 }
 #endif

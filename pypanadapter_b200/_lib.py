@@ -29,6 +29,7 @@ ZFB_FLAG_NO_LO = 1
 ZFB_FLAG_LINEAR = 2
 
 ABI_VERSION = 1
+PROF_CLASSES = 19
 
 
 class ZfbConfig(C.Structure):
@@ -74,6 +75,8 @@ SYMBOLS = {
     "zfb_decim_sos": (C.c_int, [C.POINTER(C.c_double)]),
     "zfb_plan_geometry": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]),
     "zfb_get_counters": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
+    "zfb_set_profiling": (C.c_int, [_P, C.c_int]),
+    "zfb_get_profile": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
 }
 
 

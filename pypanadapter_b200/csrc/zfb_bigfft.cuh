@@ -201,8 +201,8 @@ inline void big_launch_col(const BigParams &p, int kind, dim3 grid, cudaStream_t
     }
 }
 
-// enqueue col + row pass for `frames` frames; returns the number of launches
-inline int big_run(const BigParams &p, int kind, int frames, cudaStream_t st) {
+// enqueue the column pass for `frames` frames
+inline void big_run_col(const BigParams &p, int kind, int frames, cudaStream_t st) {
     int lm1, lm2;
     big_split(p.log2N, lm1, lm2);
     dim3 gcol((unsigned)p.ntiles_col, (unsigned)p.nseg, (unsigned)frames);
@@ -211,6 +211,12 @@ inline int big_run(const BigParams &p, int kind, int frames, cudaStream_t st) {
         case 8: big_launch_col<8>(p, kind, gcol, st); break;
         default: big_launch_col<9>(p, kind, gcol, st); break;
     }
+}
+
+// enqueue the row pass
+inline void big_run_row(const BigParams &p, int frames, cudaStream_t st) {
+    int lm1, lm2;
+    big_split(p.log2N, lm1, lm2);
     const int rr = BIG_TILE >> lm2;
     dim3 grow((unsigned)((1 << lm1) / rr), (unsigned)p.nsplit, (unsigned)frames);
     switch (lm2) {
@@ -218,7 +224,6 @@ inline int big_run(const BigParams &p, int kind, int frames, cudaStream_t st) {
         case 8: ZFB_LAUNCH(bigfft_row_kernel<8>, grow, dim3(BIG_THREADS), big_smem(1 << 8), st, p); break;
         default: ZFB_LAUNCH(bigfft_row_kernel<9>, grow, dim3(BIG_THREADS), big_smem(1 << 9), st, p); break;
     }
-    return 2;
 }
 
 }  // namespace zfb

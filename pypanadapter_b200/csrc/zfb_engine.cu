@@ -73,6 +73,11 @@ struct zfb_engine {
     int last_group_frames = 0;
 
     uint64_t counters[5] = {0, 0, 0, 0, 0};
+
+    // optional per-kernel timing
+    struct ProfRec { cudaEvent_t a, b; int cls; };
+    bool profiling = false;
+    std::vector<ProfRec> prof_used, prof_free;
 };
 
 namespace {
@@ -385,6 +390,28 @@ int choose_group(const zfb_engine *e) {
     return (int)g;
 }
 
+constexpr size_t kMaxProfRecs = 1 << 16;
+
+// returns the index of the open record, or -1 when profiling is off
+int prof_begin(zfb_engine *e, int cls) {
+    if (!e->profiling || e->prof_used.size() >= kMaxProfRecs) return -1;
+    zfb_engine::ProfRec r;
+    if (!e->prof_free.empty()) {
+        r = e->prof_free.back();
+        e->prof_free.pop_back();
+    } else {
+        if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return -1;
+    }
+    r.cls = cls;
+    cudaEventRecord(r.a, e->stream);
+    e->prof_used.push_back(r);
+    return (int)e->prof_used.size() - 1;
+}
+
+void prof_end(zfb_engine *e, int idx) {
+    if (idx >= 0) cudaEventRecord(e->prof_used[(size_t)idx].b, e->stream);
+}
+
 // one group of frames, all resident on the device, through the whole chain
 int run_group(zfb_engine *e, const void *d_in, int gf, float *d_rows) {
     const zfb_config &c = e->cfg;
@@ -405,7 +432,9 @@ int run_group(zfb_engine *e, const void *d_in, int gf, float *d_rows) {
         p.T = e->T[s];
         p.flip = (s == 0) ? c.flip : 0;
         dim3 grid((unsigned)e->tiles[s], (unsigned)gf);
+        const int pr = prof_begin(e, s);
         ZFB_LAUNCH(decim_lookup(kind), grid, dim3(NTHR), kDecimSmem, st, p);
+        prof_end(e, pr);
         e->counters[2] += 1;
         src = out;
         src_stride = out_stride;
@@ -437,7 +466,9 @@ int run_group(zfb_engine *e, const void *d_in, int gf, float *d_rows) {
         w.W = e->W;
         w.pow_out = (float *)e->pow.p;
         WelchEntry we = welch_lookup(e->log2N, kind);
+        const int pr = prof_begin(e, 16);
         ZFB_LAUNCH(we.fn, dim3((unsigned)nsplit, (unsigned)gf), dim3((unsigned)we.threads), we.smem, st, w);
+        prof_end(e, pr);
         e->counters[2] += 1;
     } else {
         int want = (2 * e->sm_count + gf * 16 - 1) / (gf * 16);
@@ -464,7 +495,13 @@ int run_group(zfb_engine *e, const void *d_in, int gf, float *d_rows) {
         b.partial = b.scratch + ((size_t)e->group * (size_t)e->nseg << e->log2N);
         b.W = e->W;
         b.pow_out = (float *)e->pow.p;
-        e->counters[2] += (uint64_t)big_run(b, kind, gf, st);
+        const int pr = prof_begin(e, 16);
+        big_run_col(b, kind, gf, st);
+        prof_end(e, pr);
+        const int pr2 = prof_begin(e, 17);
+        big_run_row(b, gf, st);
+        prof_end(e, pr2);
+        e->counters[2] += 2;
     }
 
     FinalizeParams f{};
@@ -481,7 +518,9 @@ int run_group(zfb_engine *e, const void *d_in, int gf, float *d_rows) {
     f.ring = (float *)e->ring.p;
     f.ring_pos = (long long)(e->ring_written % e->ring_rows);
     f.ring_rows = e->ring_rows;
+    const int prf = prof_begin(e, 18);
     ZFB_LAUNCH(finalize_rows_kernel, dim3((unsigned)((e->W + 127) / 128)), dim3(128), 0, st, f);
+    prof_end(e, prf);
     e->counters[2] += 1;
     if (f.alpha >= 0.f) {
         ZFB_LAUNCH(set_flag_kernel, dim3(1), dim3(1), 0, st, (int *)e->ema_valid.p, 1);
@@ -579,6 +618,8 @@ void zfb_destroy(zfb_engine *e) {
         if (e->ev_h2d[i]) cudaEventDestroy(e->ev_h2d[i]);
         if (e->ev_free[i]) cudaEventDestroy(e->ev_free[i]);
     }
+    for (auto *v : {&e->prof_used, &e->prof_free})
+        for (auto &r : *v) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     if (e->h_rows) cudaFreeHost(e->h_rows);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
@@ -953,6 +994,32 @@ int zfb_alloc_pinned(size_t bytes, void **out) {
 int zfb_free_pinned(void *p) {
     if (!p) return ZFB_OK;
     return cudaFreeHost(p) == cudaSuccess ? ZFB_OK : ZFB_ECUDA;
+}
+
+int zfb_set_profiling(zfb_engine *e, int on) {
+    if (!e) return ZFB_EINVAL;
+    std::lock_guard<std::mutex> lk(e->mu);
+    e->profiling = on != 0;
+    return ZFB_OK;
+}
+
+int zfb_get_profile(zfb_engine *e, double ms_out[ZFB_PROF_CLASSES], uint64_t launches_out[ZFB_PROF_CLASSES]) {
+    if (!e || !ms_out || !launches_out) return ZFB_EINVAL;
+    std::lock_guard<std::mutex> lk(e->mu);
+    CK(e, cudaSetDevice(e->device));
+    CK(e, cudaStreamSynchronize(e->stream));
+    for (int c = 0; c < ZFB_PROF_CLASSES; ++c) { ms_out[c] = 0.0; launches_out[c] = 0; }
+    for (auto &r : e->prof_used) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess && r.cls >= 0 && r.cls < ZFB_PROF_CLASSES) {
+            ms_out[r.cls] += (double)ms;
+            launches_out[r.cls] += 1;
+        }
+        e->prof_free.push_back(r);
+    }
+    cudaGetLastError();
+    e->prof_used.clear();
+    return ZFB_OK;
 }
 
 int zfb_get_counters(const zfb_engine *e, uint64_t out5[5]) {

@@ -190,6 +190,8 @@ class ZoomPSD:
             per = 2 * self.frame_len
         else:
             if a.dtype != np.complex64:
+                if a.dtype == np.uint8:
+                    raise TypeError("engine is configured for complex samples, got raw uint8 IQ")
                 if not np.issubdtype(a.dtype, np.number):
                     raise TypeError("unsupported sample dtype %s" % a.dtype)
                 a = a.astype(np.complex64)
@@ -243,11 +245,27 @@ class ZoomPSD:
                     "zfb_read_rows")
         return out
 
+    def set_profiling(self, on: bool):
+        self._check(self._lib.zfb_set_profiling(self._h, 1 if on else 0), "zfb_set_profiling")
+
+    def profile(self) -> dict:
+        """{kernel class: (total device ms, launches)} since the last call."""
+        ms = (C.c_double * _lib.PROF_CLASSES)()
+        n = (C.c_uint64 * _lib.PROF_CLASSES)()
+        self._check(self._lib.zfb_get_profile(self._h, ms, n), "zfb_get_profile")
+        return {_prof_name(c): (float(ms[c]), int(n[c])) for c in range(_lib.PROF_CLASSES) if n[c]}
+
     def counters(self) -> dict:
         c = (C.c_uint64 * 5)()
         self._check(self._lib.zfb_get_counters(self._h, c), "zfb_get_counters")
         return dict(frames=int(c[0]), samples=int(c[1]), kernels=int(c[2]),
                     h2d_bytes=int(c[3]), d2h_bytes=int(c[4]))
+
+
+def _prof_name(c: int) -> str:
+    if c < 16:
+        return "decimate_stage%d" % c
+    return {16: "welch", 17: "welch_rowpass", 18: "finalize"}[c]
 
 
 def decim_sos(lib=None) -> np.ndarray:

@@ -1,0 +1,141 @@
+"""Engine-level checks shared by tests/test_emu_engine.py (CPU emulation of
+the same sources -- logic only) and tests/test_gpu_parity.py (the product, on
+a B200, through the C ABI).  Every function takes a configured-or-not
+``ZoomPSD`` and asserts."""
+from __future__ import annotations
+
+import numpy as np
+import pytest
+
+from oracle import golden_cases as gc
+from oracle import zoompsd_oracle as zo
+from pypanadapter_b200 import synth
+from pypanadapter_b200.engine import ZoomFFTError
+from tests import parity
+
+
+def golden_case(engine, name):
+    return parity.check_case(engine, name)
+
+
+def ema_rows(engine, nframes=4):
+    """cfg2: uint8 + flip + EMA 0.3 across rows (EMA = builder-defined
+    extension, oracle ema_rows_db20).  Frames pushed in two calls to check
+    that the state carries across calls and groups."""
+    w = synth.CFG2
+    frames = synth.make_frames(w, nframes)
+    engine.configure(w.fs, w.fft_size, w.fft_ratio, w.frame_len, w.window, dtype="u8",
+                     flip=True, crop="thread", ema_alpha=w.ema_alpha)
+    engine.reset_ema()
+    got = np.concatenate([engine.process(frames[:1]), engine.process(frames[1:])])
+    pw = np.stack([zo.zoom_psd_power(f, w.fs, w.fft_size, w.fft_ratio, w.window, flip=True)
+                   for f in frames])
+    want = zo.ema_rows_db20(pw, w.ema_alpha)
+    floor = parity.floor_db20(w.fs, w.window, w.fft_size, True)
+    for i in range(nframes):
+        parity.assert_row_parity(got[i], want[i], floor, "ema row %d" % i)
+    # and without EMA each row equals the golden reference row
+    engine.configure(w.fs, w.fft_size, w.fft_ratio, w.frame_len, w.window, dtype="u8",
+                     flip=True, crop="thread", ema_alpha=None)
+    plain = engine.process(frames)
+    for i in range(nframes):
+        parity.assert_row_parity(plain[i], parity.golden_rows()["cfg2_T_f%d" % i], floor,
+                                 "cfg2 frame %d" % i)
+
+
+def batch_equals_single(engine, lib):
+    """Frames are independent (S:2092, S:2098, S:2111 restart per chunk): a
+    batch must give bit-identical rows to one-at-a-time calls, in any group
+    size."""
+    w = synth.CFG1
+    n = 2048 * 24
+    frames = synth.make_frames(w, 5, n=n)
+    engine.configure(w.fs, w.fft_size, w.fft_ratio, n, w.window, crop=1024)
+    single = np.stack([engine.process(frames[i])[0] for i in range(5)])
+    batch = engine.process(frames)
+    assert np.array_equal(single, batch)
+    engine.set_group(2)
+    engine.configure(w.fs, w.fft_size, w.fft_ratio, n, w.window, crop=1024)
+    assert np.array_equal(engine.process(frames), batch)
+    engine.set_group(0)
+
+
+def ring_behaviour(engine):
+    w = synth.CFG1
+    n = 2048 * 10
+    frames = synth.make_frames(w, 7, n=n)
+    engine.ring_configure(4)
+    engine.configure(w.fs, w.fft_size, w.fft_ratio, n, w.window, crop="thread")
+    assert engine.rows_written == 0
+    rows = engine.process(frames)
+    assert engine.rows_written == 7
+    assert np.array_equal(engine.read_rows(1)[0], rows[6])
+    assert np.array_equal(engine.read_rows(4), rows[3:7])          # wraps the 4-row ring
+    assert np.array_equal(engine.read_rows(2, age=1), rows[4:6])
+    with pytest.raises(ZoomFFTError):
+        engine.read_rows(5)
+    engine.ring_configure(256)
+
+
+def decimated_chunk(engine):
+    """zoomfft output (S:2100) against the golden mixed+decimated chunk."""
+    import os
+    z = np.load(os.path.join(parity.GOLDEN_DIR, "zoomfft.npz"))
+    for case in gc.ZOOMFFT_CASES:
+        x = gc.make_input(case)
+        engine.configure(case["fs"], case["N"], case["R"], len(x), "hamming", crop=None)
+        engine.process(x)
+        y = engine.read_decimated()
+        ref = z[case["name"]]
+        assert y.shape == ref.shape
+        err = np.abs(y - ref).max() / np.abs(ref).max()
+        assert err < 2e-5, "%s: relative error %.2e" % (case["name"], err)
+
+
+def plain_decimate_and_linear(engine):
+    """no_lo + linear: the chain is scipy.signal.decimate x log2(R) + welch's
+    Pxx itself (the two scipy calls the reference makes, S:2098 / S:2111)."""
+    import scipy.signal
+    rng = np.random.default_rng(5)
+    x = (rng.standard_normal(4096 * 3) + 1j * rng.standard_normal(4096 * 3)).astype(np.complex64)
+    engine.configure(1e6, 512, 4, len(x), "hann", crop=None, no_lo=True, linear=True)
+    p = engine.process(x)[0].astype(np.float64)
+    y = scipy.signal.decimate(scipy.signal.decimate(x.astype(np.complex128), 2), 2)
+    _f, want = scipy.signal.welch(y, 1e6, window="hann", nperseg=512, nfft=512)
+    want = np.fft.fftshift(want)
+    dec = engine.read_decimated()
+    assert np.abs(dec - y).max() < 2e-5 * np.abs(y).max()
+    rel = np.abs(p - want) / want
+    assert rel[want > want.max() * 1e-6].max() < 1e-3
+
+
+def error_paths(engine):
+    with pytest.raises(ValueError):                      # scipy: padlen 27
+        engine.configure(2.4e6, 32, 2, 27, "hamming")
+    with pytest.raises(ZoomFFTError):
+        engine.configure(2.4e6, 1000, 2, 4096, "hamming")        # not a power of two
+    with pytest.raises(ZoomFFTError):
+        engine.configure(2.4e6, 16, 2, 4096, "hamming")          # too small
+    engine.configure(2.4e6, 64, 2, 256, "hamming")
+    with pytest.raises(ValueError):
+        engine.process(np.zeros(255, dtype=np.complex64))          # wrong frame length
+    with pytest.raises(TypeError):
+        engine.process(np.zeros(512, dtype=np.uint8))              # wrong wire dtype
+    row = engine.process(np.zeros(256, dtype=np.complex64))[0]
+    assert np.all(np.isneginf(row))                                # zero power -> -inf like numpy
+
+
+def f_demod_extension(engine):
+    """General software LO (the reference hard-wires 1 Hz, S:2090): tone at
+    f_demod + delta must land where the oracle puts it."""
+    fs, N, R = 20e6, 1024, 16
+    n = N * R * 6
+    fc = -7.3e6
+    k = np.arange(n)
+    x = (0.3 * np.exp(2j * np.pi * ((fc + 2100.0) / fs) * k)).astype(np.complex64)
+    rng = np.random.default_rng(3)
+    x += (1e-3 * (rng.standard_normal(n) + 1j * rng.standard_normal(n))).astype(np.complex64)
+    engine.configure(fs, N, R, n, "hamming", f_demod=fc, crop="thread")
+    row = engine.process(x)[0].astype(np.float64)
+    want = zo.zoom_psd(x, fs, N, R, "hamming", f_demod=fc, crop="thread")
+    parity.assert_row_parity(row, want, parity.floor_db20(fs, "hamming", N, True), "f_demod")

@@ -1,0 +1,43 @@
+"""Kernel + host logic of the engine on the CPU emulation build (tests/emu):
+the SAME csrc sources nvcc compiles for sm_100a, run as fibers.  Proves the
+indexing / hand-off / edge-case logic in the GPU-less container; numerical
+parity proper is tests/test_gpu_parity.py on the B200."""
+import pytest
+
+from oracle import golden_cases as gc
+from tests import engine_suite as es
+
+EMU_CASES = [c["name"] for c in gc.CASES]
+
+
+@pytest.mark.parametrize("name", EMU_CASES)
+def test_golden_case(emu_engine, name):
+    es.golden_case(emu_engine, name)
+
+
+def test_ema_rows(emu_engine):
+    es.ema_rows(emu_engine, 3)
+
+
+def test_batch_equals_single(emu_engine, emu_lib):
+    es.batch_equals_single(emu_engine, emu_lib)
+
+
+def test_ring(emu_engine):
+    es.ring_behaviour(emu_engine)
+
+
+def test_decimated_chunk(emu_engine):
+    es.decimated_chunk(emu_engine)
+
+
+def test_plain_decimate_and_linear(emu_engine):
+    es.plain_decimate_and_linear(emu_engine)
+
+
+def test_error_paths(emu_engine):
+    es.error_paths(emu_engine)
+
+
+def test_f_demod(emu_engine):
+    es.f_demod_extension(emu_engine)

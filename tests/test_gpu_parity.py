@@ -1,0 +1,117 @@
+"""Parity tests proper: the sm_100a library on a real B200, called through the
+C ABI (ctypes), against the golden reference rows and the oracle.
+Run with ``pytest -m gpu``.  Tolerances: tests/parity.py (0.01 dB20 above
+-100 dBFS, argmax exact)."""
+import numpy as np
+import pytest
+
+from oracle import golden_cases as gc
+from oracle import zoompsd_oracle as zo
+from pypanadapter_b200 import synth
+from tests import engine_suite as es
+from tests import parity
+
+pytestmark = pytest.mark.gpu
+
+ALL = [c["name"] for c in gc.CASES]
+
+
+def test_product_library_is_sm100a(gpu_lib):
+    assert gpu_lib.zfb_build_kind() == b"sm_100a"
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_golden_case(gpu_engine, name):
+    es.golden_case(gpu_engine, name)
+
+
+def test_ema_rows(gpu_engine):
+    es.ema_rows(gpu_engine, 4)
+
+
+def test_batch_equals_single(gpu_engine, gpu_lib):
+    es.batch_equals_single(gpu_engine, gpu_lib)
+
+
+def test_ring(gpu_engine):
+    es.ring_behaviour(gpu_engine)
+
+
+def test_decimated_chunk(gpu_engine):
+    es.decimated_chunk(gpu_engine)
+
+
+def test_plain_decimate_and_linear(gpu_engine):
+    es.plain_decimate_and_linear(gpu_engine)
+
+
+def test_error_paths(gpu_engine):
+    es.error_paths(gpu_engine)
+
+
+def test_f_demod(gpu_engine):
+    es.f_demod_extension(gpu_engine)
+
+
+def test_cfg3_row_full_size(gpu_engine):
+    """BASELINE configs[2]: one 2^20-sample row, 65536-pt Hann, 31 segments."""
+    w = synth.CFG3
+    x = synth.make_frame(w, 3)
+    gpu_engine.configure(w.fs, w.fft_size, 1, len(x), w.window, crop=None)
+    row = gpu_engine.process(x)[0].astype(np.float64)
+    want = zo.zoom_psd(x, w.fs, w.fft_size, 1, w.window, crop=None)
+    parity.assert_row_parity(row, want, parity.floor_db20(w.fs, w.window, w.fft_size, False), "cfg3")
+
+
+@pytest.mark.parametrize("channel", [0, 37, 63])
+def test_cfg4_channel_full_size(gpu_engine, channel):
+    """BASELINE configs[3]: one of 64 virtual receivers over a 20 MS/s stream."""
+    w = synth.CFG4
+    x = synth.make_frame(w, 0)
+    fc = float(synth.cfg4_centres()[channel])
+    gpu_engine.configure(w.fs, w.fft_size, w.fft_ratio, len(x), w.window, f_demod=fc)
+    row = gpu_engine.process(x)[0].astype(np.float64)
+    want = zo.zoom_psd(x, w.fs, w.fft_size, w.fft_ratio, w.window, f_demod=fc)
+    parity.assert_row_parity(row, want, parity.floor_db20(w.fs, w.window, w.fft_size, True),
+                             "cfg4 ch%d" % channel)
+    # the channel's own tone sits 7 kHz above its centre
+    W = len(row)
+    assert int(np.argmax(row)) == W // 2 + int(round(7000.0 / (w.fs / w.fft_ratio / w.fft_size)))
+
+
+@pytest.mark.parametrize("N,R", [(1024, 64), (4096, 2), (16384, 4), (32768, 1), (131072, 1),
+                                 (262144, 2)])
+def test_sweep_corner(gpu_engine, N, R):
+    """BASELINE configs[4] corners: decim 1..64 x N 1024..262144."""
+    fs = 2.4e6
+    avg = max(R, 4)
+    n = N * avg
+    x = gc.tone_noise(n, fs, [(0.013 * fs / R, 0.4), (-0.02 * fs / R, 0.03)], 2e-3, 900 + N % 97 + R,
+                      np.complex64)
+    gpu_engine.configure(fs, N, R, n, "hamming", crop="thread")
+    row = gpu_engine.process(x)[0].astype(np.float64)
+    want = zo.zoom_psd(x, fs, N, R, "hamming", crop="thread")
+    parity.assert_row_parity(row, want, parity.floor_db20(fs, "hamming", N, R > 1), "N%d R%d" % (N, R))
+
+
+def test_device_path_equals_host_path(gpu_engine):
+    """zfb_process_device on resident buffers == zfb_process_host, bit for bit,
+    at a batch that spans several groups (size-independent property)."""
+    import torch
+    w = synth.CFG2
+    frames = synth.make_frames(w, 40, distinct=4)
+    gpu_engine.configure(w.fs, w.fft_size, w.fft_ratio, w.frame_len, w.window, dtype="u8",
+                         flip=True, crop="thread")
+    host_rows = gpu_engine.process(frames)
+    d_in = torch.from_numpy(frames).cuda()
+    d_rows = torch.empty((40, gpu_engine.row_width), dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+    gpu_engine.process_device(d_in.data_ptr(), 40, d_rows.data_ptr())
+    gpu_engine.synchronize()
+    dev_rows = d_rows.cpu().numpy()
+    assert np.array_equal(dev_rows, host_rows)
+    # repeated frames give identical rows (frames are independent)
+    for i in range(4, 40):
+        assert np.array_equal(host_rows[i], host_rows[i % 4])
+    c = gpu_engine.counters()
+    assert c["frames"] == 80 and c["kernels"] > 0
