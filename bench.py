@@ -246,9 +246,15 @@ def run_b200(args, w):
     eng = ZoomPSD(local_rank)
     if args.group:
         eng.set_group(args.group)
+    if args.decim_threads:
+        eng.set_option("decim_threads", args.decim_threads)
     eng.configure(w.fs, w.fft_size, w.fft_ratio, w.frame_len, w.window, dtype=w.dtype, flip=w.flip,
                   f_demod=w.f_demod, crop=w.crop, ema_alpha=w.ema_alpha)
-    stream = torch.cuda.current_stream()
+    # a real (non-default) stream: the engine launches on it, NCCL enqueues on
+    # it and the timing events are recorded on it
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     eng.set_stream(stream.cuda_stream)
     W = eng.row_width
 
@@ -359,6 +365,7 @@ def run_b200(args, w):
         cfg["l2"] = "inputs larger than L2: %.0f MB per step per GPU" % (in_bytes / 1e6)
         cfg["parallelism"] = "frames sharded, %d rank(s), rows gathered to rank 0 over NCCL" % world
         cfg["group_frames"] = args.group or "auto"
+        cfg["decim_threads"] = args.decim_threads or "auto"
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -390,6 +397,7 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(synth.WORKLOADS))
     ap.add_argument("--frames", type=int, default=256, help="frames per step per GPU")
     ap.add_argument("--group", type=int, default=0, help="frames per launch group (0 = auto)")
+    ap.add_argument("--decim-threads", type=int, default=0, help="tuning: 0 auto, 128 or 256")
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

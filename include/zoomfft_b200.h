@@ -98,6 +98,10 @@ int  zfb_set_stream(zfb_engine *e, void *cuda_stream);
  * stay L2-resident).  0 = automatic. */
 int  zfb_set_group(zfb_engine *e, int frames_per_group);
 int  zfb_reset_ema(zfb_engine *e);
+/* tuning knobs (no effect on results): "decim_threads" = 0 (auto) | 128 | 256
+ * threads per decimator CTA (8192- / 16384-sample shared-memory region);
+ * "welch_splits" = CTAs per frame in the Welch kernel, 0 = auto. */
+int  zfb_set_option(zfb_engine *e, const char *name, long long value);
 
 /* ---- the hot path ----------------------------------------------------- */
 /*

@@ -63,6 +63,7 @@ SYMBOLS = {
     "zfb_set_stream": (C.c_int, [_P, _P]),
     "zfb_set_group": (C.c_int, [_P, C.c_int]),
     "zfb_reset_ema": (C.c_int, [_P]),
+    "zfb_set_option": (C.c_int, [_P, C.c_char_p, C.c_longlong]),
     "zfb_process_device": (C.c_int, [_P, _P, C.c_int, _P]),
     "zfb_process_host": (C.c_int, [_P, _P, C.c_int, _P]),
     "zfb_synchronize": (C.c_int, [_P]),

@@ -14,10 +14,13 @@ namespace zfb {
 // pole pair of cheby1(8,.05,.4) has radius 0.935: 0.935^320 = 5e-10 in state,
 // 4.9e-8 worst-case in output -- below fp32 resolution).
 constexpr int BLK      = 64;                 // samples per thread
-constexpr int NTHR     = 256;                // threads per CTA
-constexpr int REGION   = BLK * NTHR;         // 16384 samples in smem
 constexpr int WARM     = 320;                // warm-up halo each side
-constexpr int TMAX     = REGION - 2 * WARM;  // 15744 outputs per tile
+// threads per CTA is a kernel template parameter NT (256 or 128):
+//   REGION = BLK*NT samples in smem, at most REGION - 2*WARM outputs per tile
+constexpr int NTHR_BIG   = 256;              // 16384-sample region, 1 CTA / SM
+constexpr int NTHR_SMALL = 128;              //  8192-sample region, 3 CTAs / SM
+__host__ __device__ constexpr int region_of(int nt) { return BLK * nt; }
+__host__ __device__ constexpr int tmax_of(int nt) { return BLK * nt - 2 * WARM; }
 constexpr int BLK_PAD  = BLK + 1;            // +1 complex: conflict-free LDS.64
 constexpr int PADLEN   = 27;                 // scipy sosfiltfilt odd extension
 constexpr int NSEC     = 4;                  // biquads in cheby1 order 8

@@ -37,7 +37,7 @@ struct StageParams {
     int         flip;
     unsigned long long phase_inc;   // frac(f_demod/fs) * 2^64
     float2      lo_small[8];   // sqrt(2)*g*exp(-2pi i f/fs v), v = 0..7
-    float2      lo_big[32];    // exp(-2pi i f/fs * it*NTHR*VEC)
+    float2      lo_big[32];    // exp(-2pi i f/fs * it*NT*VEC)
 };
 
 struct Sec4 {
@@ -52,7 +52,7 @@ __device__ __forceinline__ void sec_zero(Sec4 &s) {
     }
 }
 
-// steady state for the constant (already g-scaled) input x0
+// steady state of the all-pole cascade for the constant (already scaled) input x0
 __device__ __forceinline__ void sec_steady(Sec4 &s, float2 x0) {
 #pragma unroll
     for (int k = 0; k < NSEC; ++k) {
@@ -62,51 +62,153 @@ __device__ __forceinline__ void sec_steady(Sec4 &s, float2 x0) {
     }
 }
 
-// one sample through the cascade, direct form II with numerator (1+z^-1)^2:
-//   w = v - a1 w1 - a2 w2 ;  y = w + 2 w1 + w2
-__device__ __forceinline__ float2 cascade(float2 v, Sec4 &s, const float (&na1)[NSEC],
-                                          const float (&na2)[NSEC]) {
-#pragma unroll
-    for (int k = 0; k < NSEC; ++k) {
-        float2 t = pk_fma(na2[k], s.w2[k], v);
-        float2 w = pk_fma(na1[k], s.w1[k], t);
-        float2 u = pk_add(w, s.w2[k]);
-        v = pk_fma(2.0f, s.w1[k], u);
-        s.w2[k] = s.w1[k];
-        s.w1[k] = w;
+// The filter of one pass is H(z) = g (1+z^-1)^8 / prod_k A_k(z).  All of it is
+// LTI, so the numerator is pulled out of the recursion: the sweeps run only
+// the all-pole cascade 1/prod A_k (2 packed FMAs per section and sample,
+//   w = v - a1 w1 - a2 w2, section output = w),
+// and the binomial FIR (1+z^-1)^8 is applied once per pass afterwards
+// (fir_causal / fir_anticausal_even below).  With the constant-past /
+// constant-future boundary model of sosfiltfilt this is exact, not an
+// approximation.
+__device__ __forceinline__ float2 pole(float2 v, float2 &w1, float2 &w2, float na1, float na2) {
+    float2 t = pk_fma(na2, w2, v);
+    float2 w = pk_fma(na1, w1, t);
+    w2 = w1;
+    w1 = w;
+    return w;
+}
+
+// Full BLK-sample run, software-pipelined across the cascade: in step i
+// section k works on sample i-k, so the four recurrences are independent
+// instruction streams (the serial form leaves the FMA pipe idle ~60 %).
+template <bool BWD, bool STORE>
+__device__ __forceinline__ void sweep_full(float2 *blk, Sec4 &s, const float (&na1)[NSEC],
+                                           const float (&na2)[NSEC]) {
+#define ZFB_POS(i) (BWD ? (BLK - 1 - (i)) : (i))
+    float2 p0, p1, p2;
+    p0 = pole(blk[ZFB_POS(0)], s.w1[0], s.w2[0], na1[0], na2[0]);
+    {
+        float2 n1 = pole(p0, s.w1[1], s.w2[1], na1[1], na2[1]);
+        p0 = pole(blk[ZFB_POS(1)], s.w1[0], s.w2[0], na1[0], na2[0]);
+        p1 = n1;
     }
-    return v;
+    {
+        float2 n2 = pole(p1, s.w1[2], s.w2[2], na1[2], na2[2]);
+        float2 n1 = pole(p0, s.w1[1], s.w2[1], na1[1], na2[1]);
+        p0 = pole(blk[ZFB_POS(2)], s.w1[0], s.w2[0], na1[0], na2[0]);
+        p2 = n2;
+        p1 = n1;
+    }
+#pragma unroll 4
+    for (int i = 3; i < BLK; ++i) {
+        float2 y = pole(p2, s.w1[3], s.w2[3], na1[3], na2[3]);
+        float2 n2 = pole(p1, s.w1[2], s.w2[2], na1[2], na2[2]);
+        float2 n1 = pole(p0, s.w1[1], s.w2[1], na1[1], na2[1]);
+        float2 n0 = pole(blk[ZFB_POS(i)], s.w1[0], s.w2[0], na1[0], na2[0]);
+        if (STORE) blk[ZFB_POS(i - 3)] = y;
+        p2 = n2;
+        p1 = n1;
+        p0 = n0;
+    }
+    {
+        float2 y = pole(p2, s.w1[3], s.w2[3], na1[3], na2[3]);
+        float2 n2 = pole(p1, s.w1[2], s.w2[2], na1[2], na2[2]);
+        float2 n1 = pole(p0, s.w1[1], s.w2[1], na1[1], na2[1]);
+        if (STORE) blk[ZFB_POS(BLK - 3)] = y;
+        p2 = n2;
+        p1 = n1;
+    }
+    {
+        float2 y = pole(p2, s.w1[3], s.w2[3], na1[3], na2[3]);
+        float2 n2 = pole(p1, s.w1[2], s.w2[2], na1[2], na2[2]);
+        if (STORE) blk[ZFB_POS(BLK - 2)] = y;
+        p2 = n2;
+    }
+    {
+        float2 y = pole(p2, s.w1[3], s.w2[3], na1[3], na2[3]);
+        if (STORE) blk[ZFB_POS(BLK - 1)] = y;
+    }
+#undef ZFB_POS
 }
 
 template <bool BWD, bool STORE>
 __device__ __forceinline__ void sweep(float2 *blk, int lo, int hi, Sec4 &s,
                                       const float (&na1)[NSEC], const float (&na2)[NSEC]) {
     if (lo == 0 && hi == BLK) {
-#pragma unroll 8
-        for (int i = 0; i < BLK; ++i) {
-            const int q = BWD ? (BLK - 1 - i) : i;
-            float2 v = cascade(blk[q], s, na1, na2);
-            if (STORE) blk[q] = v;
-        }
+        sweep_full<BWD, STORE>(blk, s, na1, na2);
     } else {
         for (int i = lo; i < hi; ++i) {
             const int q = BWD ? (hi - 1 - (i - lo)) : i;
-            float2 v = cascade(blk[q], s, na1, na2);
+            float2 v = blk[q];
+#pragma unroll
+            for (int k = 0; k < NSEC; ++k) v = pole(v, s.w1[k], s.w2[k], na1[k], na2[k]);
             if (STORE) blk[q] = v;
         }
     }
 }
 
+// 9-tap binomial (1+z^-1)^8 over a 9-sample window w[0..8]
+__device__ __forceinline__ float2 binom9(const float2 *w) {
+    float2 a = pk_add(w[0], w[8]);
+    float2 b = pk_add(w[1], w[7]);
+    float2 c = pk_add(w[2], w[6]);
+    float2 d = pk_add(w[3], w[5]);
+    float2 r = pk_mul(70.0f, w[4]);
+    r = pk_fma(56.0f, d, r);
+    r = pk_fma(28.0f, c, r);
+    r = pk_fma(8.0f, b, r);
+    return pk_add(a, r);
+}
+
+// y[n] = sum_j C(8,j) x[n-j] over one thread's run, in place; hist = x[-8..-1]
+__device__ __forceinline__ void fir_causal(float2 *blk, const float2 (&hist)[8]) {
+    float2 win[16];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) win[j] = hist[j];
+#pragma unroll 2
+    for (int b = 0; b < BLK; b += 8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) win[8 + j] = blk[b + j];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) blk[b + j] = binom9(win + j);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) win[j] = win[8 + j];
+    }
+}
+
+// y[n] = sum_j C(8,j) x[n+j] at the even n of one thread's run, in place
+// (odd positions keep x); ahead = x[BLK .. BLK+7]
+__device__ __forceinline__ void fir_anticausal_even(float2 *blk, const float2 (&ahead)[8]) {
+    float2 win[16];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) win[j] = blk[j];
+#pragma unroll 2
+    for (int b = 0; b < BLK; b += 8) {
+        if (b + 8 < BLK) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) win[8 + j] = blk[b + 8 + j];
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) win[8 + j] = ahead[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) blk[b + j] = binom9(win + j);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) win[j] = win[8 + j];
+    }
+}
+
+template <int NT>
 __device__ __forceinline__ void publish(float2 *zbuf, int t, const Sec4 &s) {
 #pragma unroll
     for (int k = 0; k < NSEC; ++k) {
-        zbuf[(2 * k) * NTHR + t]     = s.w1[k];
-        zbuf[(2 * k + 1) * NTHR + t] = s.w2[k];
+        zbuf[(2 * k) * NT + t]     = s.w1[k];
+        zbuf[(2 * k + 1) * NT + t] = s.w2[k];
     }
 }
 
 // s = sum_{j=1..jmax} Mp[j-1] * z_{t -/+ j}
-template <bool BWD>
+template <bool BWD, int NT>
 __device__ __forceinline__ void handoff(const float2 *zbuf, int t, int jmax, Sec4 &s) {
     float2 acc[NSTATE];
 #pragma unroll
@@ -115,7 +217,7 @@ __device__ __forceinline__ void handoff(const float2 *zbuf, int t, int jmax, Sec
         const int tt = BWD ? t + j : t - j;
         float2 z[NSTATE];
 #pragma unroll
-        for (int r = 0; r < NSTATE; ++r) z[r] = zbuf[r * NTHR + tt];
+        for (int r = 0; r < NSTATE; ++r) z[r] = zbuf[r * NT + tt];
         if (j == 1) {
 #pragma unroll
             for (int r = 0; r < NSTATE; ++r) acc[r] = z[r];
@@ -138,75 +240,76 @@ __device__ __forceinline__ void handoff(const float2 *zbuf, int t, int jmax, Sec
 __device__ __forceinline__ int sidx(int q) { return q + (q >> 6); }   // BLK_PAD layout
 
 // ---- region load: convert / flip / mix / gain, zero outside [0, L) -------
-template <int KIND>
+// 128-bit coalesced loads, CH of them in flight per thread before the first
+// use; the scalar path only serves ragged frame ends and unaligned frames.
+// uint8 -> float without the slow I2F pipe: the byte is dropped into the
+// mantissa of 2^23 (PRMT), minus 2^23 is exact, then u/127.5 - 1 (pyrtlsdr).
+__device__ __forceinline__ float2 u8pair_to_iq(unsigned int word, int hi) {
+    const unsigned int fi = __byte_perm(word, 0x4B000000u, hi ? 0x7442 : 0x7440);
+    const unsigned int fq = __byte_perm(word, 0x4B000000u, hi ? 0x7443 : 0x7441);
+    float2 f = make_float2(__uint_as_float(fi), __uint_as_float(fq));
+    f = pk_add(f, make_float2(-8388608.0f, -8388608.0f));
+    return __ffma2_rn(f, make_float2(1.0f / 127.5f, 1.0f / 127.5f), make_float2(-1.0f, -1.0f));
+}
+
+template <int KIND, int NT>
 __device__ __forceinline__ void load_region(float2 *buf, const StageParams &p,
                                             const char *frame_in, int rs, int tid) {
     constexpr int VEC = (KIND == KIND_U8_RAW) ? 8 : 2;
-    constexpr int ITERS = REGION / (NTHR * VEC);
+    constexpr int ITERS = BLK / VEC;
+    constexpr int CH = 8;
     const int L = p.L;
+    const bool fl = (KIND != KIND_C64_MID) && p.flip;
     float2 b0 = make_float2(1.f, 0.f);
     if (KIND != KIND_C64_MID) b0 = lo_phasor((long long)rs + (long long)tid * VEC, p.phase_inc);
     const float g = c_dec.g;
+    const size_t esz = (KIND == KIND_U8_RAW) ? 2 : 8;
 
-#pragma unroll 2
-    for (int it = 0; it < ITERS; ++it) {
-        const int q = (it * NTHR + tid) * VEC;
-        const int pos = rs + q;
-        float2 v[VEC];
-        if (pos >= L || pos + VEC <= 0) {
+#pragma unroll 1
+    for (int it0 = 0; it0 < ITERS; it0 += CH) {
+        uint4 raw[CH];
+        bool vec_ok[CH];
 #pragma unroll
-            for (int e = 0; e < VEC; ++e) v[e] = make_float2(0.f, 0.f);
-        } else {
-            const bool full = (pos >= 0) && (pos + VEC <= L);
-            if (KIND == KIND_U8_RAW) {
-                const unsigned char *src = (const unsigned char *)frame_in;
-                // sample index of element e: flip ? L-1-(pos+e) : pos+e
-                const long long i0 = p.flip ? (long long)L - VEC - pos : (long long)pos;
-                const unsigned char *a = src + 2 * i0;
-                if (full && ((((uintptr_t)a) & 15) == 0)) {
-                    uint4 raw = __ldg((const uint4 *)a);
-                    unsigned int wds[4] = {raw.x, raw.y, raw.z, raw.w};
+        for (int c = 0; c < CH; ++c) {
+            const int pos = rs + ((it0 + c) * NT + tid) * VEC;
+            // sample index of element e: flip ? L-1-(pos+e) : pos+e
+            const long long i0 = fl ? (long long)L - VEC - pos : (long long)pos;
+            const char *a = frame_in + (size_t)i0 * esz;
+            vec_ok[c] = (pos >= 0) && (pos + VEC <= L) && ((((uintptr_t)a) & 15) == 0);
+            raw[c] = vec_ok[c] ? __ldg((const uint4 *)a) : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+            const int it = it0 + c;
+            const int q = (it * NT + tid) * VEC;
+            const int pos = rs + q;
+            float2 v[VEC];
+            if (vec_ok[c]) {
+                if (KIND == KIND_U8_RAW) {
+                    const unsigned int wds[4] = {raw[c].x, raw[c].y, raw[c].z, raw[c].w};
 #pragma unroll
                     for (int e = 0; e < VEC; ++e) {
-                        const int ee = p.flip ? (VEC - 1 - e) : e;
-                        unsigned int h = (wds[ee >> 1] >> ((ee & 1) * 16)) & 0xffffu;
-                        v[e] = make_float2(u8_to_f(h & 0xffu), u8_to_f(h >> 8));
+                        const int ee = fl ? (VEC - 1 - e) : e;
+                        v[e] = u8pair_to_iq(wds[ee >> 1], ee & 1);
                     }
                 } else {
-#pragma unroll
-                    for (int e = 0; e < VEC; ++e) {
-                        const int pe = pos + e;
-                        if (pe >= 0 && pe < L) {
-                            const long long ie = p.flip ? (long long)L - 1 - pe : (long long)pe;
-                            v[e] = make_float2(u8_to_f(src[2 * ie]), u8_to_f(src[2 * ie + 1]));
-                        } else {
-                            v[e] = make_float2(0.f, 0.f);
-                        }
-                    }
+                    const float2 lo2 = make_float2(__uint_as_float(raw[c].x), __uint_as_float(raw[c].y));
+                    const float2 hi2 = make_float2(__uint_as_float(raw[c].z), __uint_as_float(raw[c].w));
+                    v[0] = fl ? hi2 : lo2;
+                    v[VEC - 1] = fl ? lo2 : hi2;
                 }
             } else {
-                const float2 *src = (const float2 *)frame_in;
-                const bool fl = (KIND == KIND_C64_RAW) && p.flip;
-                const long long i0 = fl ? (long long)L - VEC - pos : (long long)pos;
-                const float2 *a = src + i0;
-                if (full && ((((uintptr_t)a) & 15) == 0)) {
-                    float4 raw = __ldg((const float4 *)a);
-                    if (fl) {
-                        v[0] = make_float2(raw.z, raw.w);
-                        v[1] = make_float2(raw.x, raw.y);
-                    } else {
-                        v[0] = make_float2(raw.x, raw.y);
-                        v[1] = make_float2(raw.z, raw.w);
-                    }
-                } else {
 #pragma unroll
-                    for (int e = 0; e < VEC; ++e) {
-                        const int pe = pos + e;
-                        if (pe >= 0 && pe < L) {
-                            const long long ie = fl ? (long long)L - 1 - pe : (long long)pe;
-                            v[e] = __ldg(src + ie);
+                for (int e = 0; e < VEC; ++e) {
+                    const int pe = pos + e;
+                    v[e] = make_float2(0.f, 0.f);
+                    if (pe >= 0 && pe < L) {
+                        const long long ie = fl ? (long long)L - 1 - pe : (long long)pe;
+                        if (KIND == KIND_U8_RAW) {
+                            const unsigned char *src = (const unsigned char *)frame_in;
+                            v[e] = make_float2(u8_to_f(src[2 * ie]), u8_to_f(src[2 * ie + 1]));
                         } else {
-                            v[e] = make_float2(0.f, 0.f);
+                            v[e] = __ldg((const float2 *)frame_in + ie);
                         }
                     }
                 }
@@ -219,18 +322,19 @@ __device__ __forceinline__ void load_region(float2 *buf, const StageParams &p,
 #pragma unroll
                 for (int e = 0; e < VEC; ++e) v[e] = cmul(v[e], cmul(bi, p.lo_small[e]));
             }
-        }
-        const int s0 = sidx(q);           // VEC consecutive samples share a block
+            const int s0 = sidx(q);           // VEC consecutive samples share a block
 #pragma unroll
-        for (int e = 0; e < VEC; ++e) buf[s0 + e] = v[e];
+            for (int e = 0; e < VEC; ++e) buf[s0 + e] = v[e];
+        }
     }
 }
 
-template <int KIND>
-__global__ void __launch_bounds__(NTHR, 1) decim2_exact_kernel(const StageParams p) {
+template <int KIND, int NT>
+__global__ void __launch_bounds__(NT, (NT == NTHR_BIG ? 1 : 3)) decim2_exact_kernel(const StageParams p) {
+    constexpr int REGION = region_of(NT);
     ZFB_DYN_SMEM(smem_raw);
-    float2 *buf  = reinterpret_cast<float2 *>(smem_raw);          // NTHR*BLK_PAD
-    float2 *zbuf = buf + NTHR * BLK_PAD;                          // NSTATE*NTHR
+    float2 *buf  = reinterpret_cast<float2 *>(smem_raw);          // NT*BLK_PAD
+    float2 *zbuf = buf + NT * BLK_PAD;                            // NSTATE*NT
 
     const int tid   = threadIdx.x;
     const int tile  = blockIdx.x;
@@ -242,7 +346,7 @@ __global__ void __launch_bounds__(NTHR, 1) decim2_exact_kernel(const StageParams
     const size_t esz = (KIND == KIND_U8_RAW) ? 2 : 8;
     const char *frame_in = (const char *)p.in + (size_t)frame * (size_t)p.in_stride * esz;
 
-    load_region<KIND>(buf, p, frame_in, rs, tid);
+    load_region<KIND, NT>(buf, p, frame_in, rs, tid);
     __syncthreads();
 
     // odd extension (scipy odd_ext, 27 samples each side) where it falls in the region
@@ -285,26 +389,47 @@ __global__ void __launch_bounds__(NTHR, 1) decim2_exact_kernel(const StageParams
     if (active) {
         if (tid == a_f) sec_steady(s, blk[lo]); else sec_zero(s);
         sweep<false, false>(blk, lo, hi, s, na1, na2);
-        publish(zbuf, tid, s);
+        publish<NT>(zbuf, tid, s);
     }
     __syncthreads();
     if (active) {
         if (tid == a_f) sec_steady(s, blk[lo]);
-        else handoff<false>(zbuf, tid, min(JTERMS, tid - a_f), s);
+        else handoff<false, NT>(zbuf, tid, min(JTERMS, tid - a_f), s);
         sweep<false, true>(blk, lo, hi, s, na1, na2);
+    }
+    __syncthreads();
+    // numerator of the forward pass: (1+z^-1)^8 over the whole region.  The 8
+    // samples before a run belong to the neighbour, who rewrites them in place.
+    {
+        float2 hist[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            hist[j] = (tid > 0) ? buf[sidx(tid * BLK - 8 + j)] : make_float2(0.f, 0.f);
+        __syncthreads();
+        fir_causal(blk, hist);
     }
     __syncthreads();
     // ---------------- backward ----------------
     if (active) {
         if (tid == a_b) sec_steady(s, blk[hi - 1]); else sec_zero(s);
         sweep<true, false>(blk, lo, hi, s, na1, na2);
-        publish(zbuf, tid, s);
+        publish<NT>(zbuf, tid, s);
     }
     __syncthreads();
     if (active) {
         if (tid == a_b) sec_steady(s, blk[hi - 1]);
-        else handoff<true>(zbuf, tid, min(JTERMS, a_b - tid), s);
+        else handoff<true, NT>(zbuf, tid, min(JTERMS, a_b - tid), s);
         sweep<true, true>(blk, lo, hi, s, na1, na2);
+    }
+    __syncthreads();
+    // numerator of the backward pass, (1+z)^8, only where a sample is kept
+    {
+        float2 ahead[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            ahead[j] = (tid < NT - 1) ? buf[sidx((tid + 1) * BLK + j)] : make_float2(0.f, 0.f);
+        __syncthreads();
+        fir_anticausal_even(blk, ahead);
     }
     __syncthreads();
 
@@ -312,7 +437,7 @@ __global__ void __launch_bounds__(NTHR, 1) decim2_exact_kernel(const StageParams
     const int span = min(p.T, L - p0);
     const int nout = (span + 1) >> 1;
     float2 *out = p.out + (size_t)frame * (size_t)p.out_stride + (p0 >> 1);
-    for (int i = tid; i < nout; i += NTHR) out[i] = buf[sidx(WARM + 2 * i)];
+    for (int i = tid; i < nout; i += NT) out[i] = buf[sidx(WARM + 2 * i)];
 }
 
 }  // namespace zfb

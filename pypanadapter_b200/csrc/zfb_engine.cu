@@ -56,12 +56,14 @@ struct zfb_engine {
     // plan
     int nstages = 0;
     int len[kMaxStages + 1] = {0};     // len[s] = input length of stage s; len[nstages] = Welch input
-    int tiles[kMaxStages] = {0}, T[kMaxStages] = {0};
+    int tiles[kMaxStages][2] = {{0}}, T[kMaxStages][2] = {{0}};   // [stage][0: NT=256, 1: NT=128]
+    int decim_threads = 0;             // 0 = automatic per launch
+    int welch_splits = 0;              // 0 = automatic
     int nperseg = 0, hop = 0, nseg = 0, W = 0, log2N = 0;
     double sum_w2 = 0.0;
     int group = 1, group_user = 0;
     int nsplit_cap = 1;
-    StageParams sp0{};                 // LO tables of stage 0
+    StageParams sp0[2]{};              // LO tables of stage 0 for NT = 256 / 128
 
     DevBuf window, winfft, twiddle, mid[2], pow, rows_tmp, ema, ema_valid, ring, stage_in[2], big;
     void  *h_stage[2] = {nullptr, nullptr};
@@ -190,9 +192,9 @@ void mat_mul(const double a[NSTATE][NSTATE], const double b[NSTATE][NSTATE], dou
 }
 
 // constants of the block-parallel IIR (zfb_decim.cuh): -a1, -a2, the squared
-// gain (forward and backward pass folded into one input scale), the DF2
-// steady state per unit (scaled) input, and powers of the zero-input state
-// transition over one BLK-sample run.
+// gain (forward and backward pass folded into one input scale), the steady
+// state of the all-pole cascade per unit (scaled) input, and powers of its
+// zero-input state transition over one BLK-sample run.
 void build_decim_const(DecimConst &dc) {
     double sos[NSEC][6];
     design_cheby1_sos(sos);
@@ -206,9 +208,8 @@ void build_decim_const(DecimConst &dc) {
     dc.g = (float)(sos[0][0] * sos[0][0]);
     double c = 1.0;
     for (int k = 0; k < NSEC; ++k) {
-        const double wss = c / (1.0 + a1[k] + a2[k]);
-        dc.zi[k] = (float)wss;
-        c = 4.0 * wss;
+        c /= (1.0 + a1[k] + a2[k]);       // all-pole section: constant in -> constant out
+        dc.zi[k] = (float)c;
     }
     // one-sample zero-input transition A of the DF2 cascade, state order
     // (w1_0, w2_0, w1_1, w2_1, ...): column j = response to unit state j
@@ -222,7 +223,7 @@ void build_decim_const(DecimConst &dc) {
         double v = 0.0;
         for (int k = 0; k < NSEC; ++k) {
             const double w = v - a1[k] * w1[k] - a2[k] * w2[k];
-            v = w + 2.0 * w1[k] + w2[k];
+            v = w;                              // all-pole cascade (zfb_decim.cuh)
             w2[k] = w1[k];
             w1[k] = w;
         }
@@ -347,23 +348,28 @@ WelchEntry welch_lookup(int log2n, int kind) {
 }
 
 typedef void (*DecimFn)(const StageParams);
-DecimFn decim_lookup(int kind) {
+template <int NT>
+DecimFn decim_lookup_nt(int kind) {
     switch (kind) {
-        case KIND_C64_RAW: return decim2_exact_kernel<KIND_C64_RAW>;
-        case KIND_U8_RAW: return decim2_exact_kernel<KIND_U8_RAW>;
-        default: return decim2_exact_kernel<KIND_C64_MID>;
+        case KIND_C64_RAW: return decim2_exact_kernel<KIND_C64_RAW, NT>;
+        case KIND_U8_RAW: return decim2_exact_kernel<KIND_U8_RAW, NT>;
+        default: return decim2_exact_kernel<KIND_C64_MID, NT>;
     }
 }
+DecimFn decim_lookup(int kind, int nt) {
+    return nt == NTHR_BIG ? decim_lookup_nt<NTHR_BIG>(kind) : decim_lookup_nt<NTHR_SMALL>(kind);
+}
 
-constexpr size_t kDecimSmem = (size_t)(NTHR * BLK_PAD + NSTATE * NTHR) * sizeof(float2);
+constexpr size_t decim_smem(int nt) { return (size_t)(nt * BLK_PAD + NSTATE * nt) * sizeof(float2); }
 
 int setup_device_once(zfb_engine *e) {
     DecimConst dc;
     build_decim_const(dc);
     CK(e, cudaMemcpyToSymbol(c_dec, &dc, sizeof dc));
     for (int kind = 0; kind < 3; ++kind)
-        CK(e, cudaFuncSetAttribute(decim_lookup(kind), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)kDecimSmem));
+        for (int nt : {NTHR_BIG, NTHR_SMALL})
+            CK(e, cudaFuncSetAttribute(decim_lookup(kind, nt), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)decim_smem(nt)));
     for (int kind = 0; kind < 3; ++kind)
         for (int l = kMinLog2N; l <= kMaxLog2Small; ++l) {
             WelchEntry w = welch_lookup(l, kind);
@@ -378,16 +384,32 @@ size_t sample_bytes(const zfb_config &c) { return c.dtype == ZFB_DTYPE_U8 ? 2 : 
 
 int choose_group(const zfb_engine *e) {
     if (e->group_user > 0) return e->group_user;
-    // keep the two largest intermediates of a group inside ~half of L2
+    // enough frames per launch that the late, small stages still fill the GPU
+    // (the chain is fp32-bound, not bandwidth-bound: L2 residency of the
+    // intermediates is worth less than full waves); bounded to 256 MB of workspace
     size_t per_frame = 0;
     if (e->nstages >= 1) per_frame += (size_t)e->len[1] * 8;
     if (e->nstages >= 2) per_frame += (size_t)e->len[2] * 8;
     if (e->log2N > kMaxLog2Small) per_frame += (size_t)e->nseg * ((size_t)8 << e->log2N);
     if (per_frame == 0) return 2048;
-    long long g = (long long)(64ull << 20) / (long long)per_frame;
+    long long g = (long long)(256ull << 20) / (long long)per_frame;
     if (g < 1) g = 1;
     if (g > 2048) g = 2048;
     return (int)g;
+}
+
+// tile geometry per stage for both region sizes; run_group picks per launch
+void plan_tiles(zfb_engine *e) {
+    for (int s = 0; s < e->nstages; ++s)
+        for (int v = 0; v < 2; ++v) {
+            const int L = e->len[s];
+            const int tmax = tmax_of(v == 0 ? NTHR_BIG : NTHR_SMALL);
+            const int tiles = (L + tmax - 1) / tmax;
+            int T = (L + tiles - 1) / tiles;
+            T = (T + 15) / 16 * 16;
+            e->tiles[s][v] = (L + T - 1) / T;
+            e->T[s][v] = T;
+        }
 }
 
 constexpr size_t kMaxProfRecs = 1 << 16;
@@ -421,7 +443,13 @@ int run_group(zfb_engine *e, const void *d_in, int gf, float *d_rows) {
     int kind = raw_kind(c);
 
     for (int s = 0; s < e->nstages; ++s) {
-        StageParams p = e->sp0;           // LO tables only matter for stage 0
+        // 8192-sample region (3 CTAs/SM: one CTA's load overlaps another's sweeps)
+        // unless zfb_set_option asked for the 16384-sample one (1 CTA/SM, half the halo)
+        // (fixed per engine, never per launch: a frame's row must not depend on
+        // how many frames share its launch)
+        const int v = (e->decim_threads == NTHR_BIG) ? 0 : 1;
+        const int nt = v == 0 ? NTHR_BIG : NTHR_SMALL;
+        StageParams p = e->sp0[v];        // LO tables only matter for stage 0
         float2 *out = (float2 *)e->mid[s & 1].p;
         const long long out_stride = e->len[s + 1];
         p.in = src;
@@ -429,11 +457,11 @@ int run_group(zfb_engine *e, const void *d_in, int gf, float *d_rows) {
         p.in_stride = src_stride;
         p.out_stride = out_stride;
         p.L = e->len[s];
-        p.T = e->T[s];
+        p.T = e->T[s][v];
         p.flip = (s == 0) ? c.flip : 0;
-        dim3 grid((unsigned)e->tiles[s], (unsigned)gf);
+        dim3 grid((unsigned)e->tiles[s][v], (unsigned)gf);
         const int pr = prof_begin(e, s);
-        ZFB_LAUNCH(decim_lookup(kind), grid, dim3(NTHR), kDecimSmem, st, p);
+        ZFB_LAUNCH(decim_lookup(kind, nt), grid, dim3((unsigned)nt), decim_smem(nt), st, p);
         prof_end(e, pr);
         e->counters[2] += 1;
         src = out;
@@ -444,7 +472,9 @@ int run_group(zfb_engine *e, const void *d_in, int gf, float *d_rows) {
     // Welch
     int nsplit = 1;
     if (e->log2N <= kMaxLog2Small) {
-        int want = (2 * e->sm_count + gf - 1) / gf;
+        // CTAs per frame: fixed per configuration (not per launch) so that the
+        // summation order, hence every bit of a row, is independent of batching
+        int want = e->welch_splits > 0 ? e->welch_splits : 4;
         if (want > e->nseg) want = e->nseg;
         if (want > e->nsplit_cap) want = e->nsplit_cap;
         if (want < 1) want = 1;
@@ -471,7 +501,7 @@ int run_group(zfb_engine *e, const void *d_in, int gf, float *d_rows) {
         prof_end(e, pr);
         e->counters[2] += 1;
     } else {
-        int want = (2 * e->sm_count + gf * 16 - 1) / (gf * 16);
+        int want = e->welch_splits > 0 ? e->welch_splits : 4;
         if (want > e->nseg) want = e->nseg;
         if (want > e->nsplit_cap) want = e->nsplit_cap;
         if (want < 1) want = 1;
@@ -505,7 +535,7 @@ int run_group(zfb_engine *e, const void *d_in, int gf, float *d_rows) {
     }
 
     FinalizeParams f{};
-    f.pow_in = (const float *)e->pow.p;
+    f.pow_io = (float *)e->pow.p;
     f.nframes = gf;
     f.nsplit = nsplit;
     f.W = e->W;
@@ -519,13 +549,16 @@ int run_group(zfb_engine *e, const void *d_in, int gf, float *d_rows) {
     f.ring_pos = (long long)(e->ring_written % e->ring_rows);
     f.ring_rows = e->ring_rows;
     const int prf = prof_begin(e, 18);
-    ZFB_LAUNCH(finalize_rows_kernel, dim3((unsigned)((e->W + 127) / 128)), dim3(128), 0, st, f);
-    prof_end(e, prf);
+    const long long cells = (long long)gf * e->W;
+    ZFB_LAUNCH(reduce_rows_kernel, dim3((unsigned)((cells + 255) / 256)), dim3(256), 0, st, f);
     e->counters[2] += 1;
     if (f.alpha >= 0.f) {
+        ZFB_LAUNCH(ema_rows_kernel, dim3((unsigned)((e->W + 31) / 32)), dim3(32), 0, st, f);
         ZFB_LAUNCH(set_flag_kernel, dim3(1), dim3(1), 0, st, (int *)e->ema_valid.p, 1);
-        e->counters[2] += 1;
+        ZFB_LAUNCH(emit_rows_kernel, dim3((unsigned)((cells + 255) / 256)), dim3(256), 0, st, f);
+        e->counters[2] += 3;
     }
+    prof_end(e, prf);
     CK(e, cudaGetLastError());
     e->ring_written += gf;
     e->last_group_frames = gf;
@@ -734,17 +767,10 @@ int zfb_configure(zfb_engine *e, const zfb_config *cfg) {
     e->W = cfg->row_width;
     e->log2N = l2;
     e->sum_w2 = s2;
-    for (int s = 0; s < g.nstages; ++s) {
-        const int L = g.len[s];
-        const int tiles = (L + TMAX - 1) / TMAX;
-        int T = (L + tiles - 1) / tiles;
-        T = (T + 15) / 16 * 16;
-        e->tiles[s] = (L + T - 1) / T;
-        e->T[s] = T;
-    }
-    // stage-0 LO tables
-    {
-        StageParams &p = e->sp0;
+    // stage-0 LO tables (one per tile geometry)
+    for (int v = 0; v < 2; ++v) {
+        const int nt = v == 0 ? NTHR_BIG : NTHR_SMALL;
+        StageParams &p = e->sp0[v];
         memset(&p, 0, sizeof p);
         const bool no_lo = (cfg->flags & ZFB_FLAG_NO_LO) != 0;
         double r = no_lo ? 0.0 : cfg->f_demod / cfg->fs;
@@ -756,10 +782,11 @@ int zfb_configure(zfb_engine *e, const zfb_config *cfg) {
         build_decim_const(dc);
         const double amp = (no_lo ? 1.0 : sqrt(2.0)) * (double)dc.g;
         const int vec = (cfg->dtype == ZFB_DTYPE_U8) ? 8 : 2;
-        for (int v = 0; v < 8; ++v) lo_entry(r, v, amp, p.lo_small[v]);
-        for (int it = 0; it < 32; ++it) lo_entry(r, (long long)it * NTHR * vec, 1.0, p.lo_big[it]);
+        for (int i = 0; i < 8; ++i) lo_entry(r, i, amp, p.lo_small[i]);
+        for (int it = 0; it < 32; ++it) lo_entry(r, (long long)it * nt * vec, 1.0, p.lo_big[it]);
     }
     e->group = choose_group(e);
+    plan_tiles(e);
     e->nsplit_cap = 16;
 
     // workspaces
@@ -807,6 +834,23 @@ int zfb_set_group(zfb_engine *e, int frames_per_group) {
     e->group_user = frames_per_group;
     e->configured = false;      // workspaces are sized per group: re-plan on next configure
     return ZFB_OK;
+}
+
+int zfb_set_option(zfb_engine *e, const char *name, long long value) {
+    if (!e || !name) return ZFB_EINVAL;
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (strcmp(name, "decim_threads") == 0) {
+        if (value != 0 && value != NTHR_BIG && value != NTHR_SMALL)
+            return fail(e, ZFB_EINVAL, "decim_threads must be 0 (auto), %d or %d", NTHR_SMALL, NTHR_BIG);
+        e->decim_threads = (int)value;
+        return ZFB_OK;
+    }
+    if (strcmp(name, "welch_splits") == 0) {
+        if (value < 0 || value > 16) return fail(e, ZFB_EINVAL, "welch_splits must be in [0, 16]");
+        e->welch_splits = (int)value;
+        return ZFB_OK;
+    }
+    return fail(e, ZFB_EINVAL, "unknown option '%s'", name);
 }
 
 int zfb_reset_ema(zfb_engine *e) {

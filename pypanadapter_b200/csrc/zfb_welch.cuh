@@ -281,9 +281,8 @@ welch_kernel(const WelchParams p) {
 // rows: sum the per-split partial sums in fixed order, scale, optional EMA
 // across consecutive frames on linear power, then dB20.
 //   a_0 = p_0 (when the state is empty), a_i = alpha p_i + (1-alpha) a_(i-1)
-// One thread per column; frames are walked in order (EMA is order dependent).
 struct FinalizeParams {
-    const float *pow_in;      // [nframes][nsplit][W]
+    float *pow_io;            // [nframes][nsplit][W]; slot 0 of a frame receives its reduced row
     int    nframes, nsplit, W;
     float  scale;             // 1 / (fs * sum w^2) / nseg
     float  alpha;             // < 0: EMA off
@@ -296,31 +295,58 @@ struct FinalizeParams {
     int    ring_rows;
 };
 
-__global__ void finalize_rows_kernel(const FinalizeParams p) {
+__device__ __forceinline__ void emit_row_value(const FinalizeParams &p, int f, int col, float v) {
+    const float out = p.linear ? v : 20.0f * log10f(fabsf(v));
+    if (p.rows) p.rows[(size_t)f * p.W + col] = out;
+    if (p.ring) p.ring[(size_t)((p.ring_pos + f) % p.ring_rows) * p.W + col] = out;
+}
+
+// one thread per (frame, column): fully parallel part
+__global__ void reduce_rows_kernel(const FinalizeParams p) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)p.nframes * p.W) return;
+    const int f = (int)(idx / p.W), col = (int)(idx % p.W);
+    float *src = p.pow_io + (size_t)f * p.nsplit * p.W + col;
+    float pw = 0.f;
+    for (int s = 0; s < p.nsplit; ++s) pw += src[(size_t)s * p.W];
+    pw *= p.scale;
+    if (p.alpha >= 0.f) src[0] = pw;          // the EMA kernel walks the frames in order
+    else emit_row_value(p, f, col, pw);
+}
+
+// EMA is order dependent: one thread per column walks the frames (loads of CH
+// frames in flight together), doing nothing but the recurrence; the averaged
+// power goes back to slot 0 and emit_rows_kernel turns it into rows in parallel
+__global__ void ema_rows_kernel(const FinalizeParams p) {
     const int col = blockIdx.x * blockDim.x + threadIdx.x;
     if (col >= p.W) return;
-    const bool use_ema = p.alpha >= 0.f;
-    float a = 0.f;
-    bool have = false;
-    if (use_ema) {
-        have = (*p.ema_valid != 0);
-        if (have) a = p.ema_state[col];
-    }
-    for (int f = 0; f < p.nframes; ++f) {
-        const float *src = p.pow_in + (size_t)f * p.nsplit * p.W + col;
-        float pw = 0.f;
-        for (int s = 0; s < p.nsplit; ++s) pw += src[(size_t)s * p.W];
-        pw *= p.scale;
-        if (use_ema) {
-            a = have ? fmaf(p.alpha, pw - a, a) : pw;
-            have = true;
-            pw = a;
+    bool have = (*p.ema_valid != 0);
+    float a = have ? p.ema_state[col] : 0.f;
+    constexpr int CH = 16;
+    const size_t stride = (size_t)p.nsplit * p.W;
+    for (int f0 = 0; f0 < p.nframes; f0 += CH) {
+        float pw[CH];
+#pragma unroll
+        for (int i = 0; i < CH; ++i)
+            pw[i] = (f0 + i < p.nframes) ? p.pow_io[(size_t)(f0 + i) * stride + col] : 0.f;
+#pragma unroll
+        for (int i = 0; i < CH; ++i) {
+            if (f0 + i < p.nframes) {
+                a = have ? fmaf(p.alpha, pw[i] - a, a) : pw[i];
+                have = true;
+                p.pow_io[(size_t)(f0 + i) * stride + col] = a;
+            }
         }
-        const float out = p.linear ? pw : 20.0f * log10f(fabsf(pw));
-        if (p.rows) p.rows[(size_t)f * p.W + col] = out;
-        if (p.ring) p.ring[(size_t)((p.ring_pos + f) % p.ring_rows) * p.W + col] = out;
     }
-    if (use_ema) p.ema_state[col] = a;
+    p.ema_state[col] = a;       // ema_valid is raised by set_flag_kernel afterwards (other
+                                // CTAs of this launch may not have read it yet)
+}
+
+__global__ void emit_rows_kernel(const FinalizeParams p) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)p.nframes * p.W) return;
+    const int f = (int)(idx / p.W), col = (int)(idx % p.W);
+    emit_row_value(p, f, col, p.pow_io[(size_t)f * p.nsplit * p.W + col]);
 }
 
 __global__ void set_flag_kernel(int *flag, int v) { *flag = v; }

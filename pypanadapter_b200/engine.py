@@ -172,6 +172,10 @@ class ZoomPSD:
     def set_stream(self, cuda_stream_ptr):
         self._check(self._lib.zfb_set_stream(self._h, C.c_void_p(cuda_stream_ptr or 0)), "zfb_set_stream")
 
+    def set_option(self, name: str, value: int):
+        """Tuning knobs that never change results (zfb_set_option)."""
+        self._check(self._lib.zfb_set_option(self._h, name.encode(), int(value)), "zfb_set_option")
+
     def reset_ema(self):
         self._check(self._lib.zfb_reset_ema(self._h), "zfb_reset_ema")
 

@@ -147,6 +147,17 @@ static inline void sincospif(float x, float *s, float *c) {
     *s = (float)sin(a);
     *c = (float)cos(a);
 }
+static inline unsigned int __byte_perm(unsigned int x, unsigned int y, unsigned int sel) {
+    const uint64_t src = ((uint64_t)y << 32) | x;
+    unsigned int r = 0;
+    for (int i = 0; i < 4; ++i) {
+        const unsigned int n = (sel >> (4 * i)) & 0x7u;
+        r |= (unsigned int)((src >> (8 * n)) & 0xffu) << (8 * i);
+    }
+    return r;
+}
+static inline float __uint_as_float(unsigned int u) { float f; memcpy(&f, &u, 4); return f; }
+static inline unsigned int __float_as_uint(float f) { unsigned int u; memcpy(&u, &f, 4); return u; }
 static inline int min(int a, int b) { return a < b ? a : b; }
 static inline int max(int a, int b) { return a > b ? a : b; }
 

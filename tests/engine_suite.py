@@ -139,3 +139,20 @@ def f_demod_extension(engine):
     row = engine.process(x)[0].astype(np.float64)
     want = zo.zoom_psd(x, fs, N, R, "hamming", f_demod=fc, crop="thread")
     parity.assert_row_parity(row, want, parity.floor_db20(fs, "hamming", N, True), "f_demod")
+
+
+def tile_geometries(engine, names=("cfg1_T", "cfg2_T_f0", "ragged_T", "zoom_R64")):
+    """Both decimator region sizes (zfb_set_option decim_threads) meet parity;
+    multi-tile frames exercise interior warm-up tiles, true-edge tiles and the
+    odd extension in both."""
+    try:
+        for nt in (256, 128):
+            engine.set_option("decim_threads", nt)
+            for name in names:
+                parity.check_case(engine, name)
+    finally:
+        engine.set_option("decim_threads", 0)
+    with pytest.raises(ZoomFFTError):
+        engine.set_option("decim_threads", 64)
+    with pytest.raises(ZoomFFTError):
+        engine.set_option("no_such_option", 1)

@@ -41,3 +41,7 @@ def test_error_paths(emu_engine):
 
 def test_f_demod(emu_engine):
     es.f_demod_extension(emu_engine)
+
+
+def test_tile_geometries(emu_engine):
+    es.tile_geometries(emu_engine)
