@@ -140,6 +140,30 @@ int64_t zfb_ring_rows_written(const zfb_engine *e);    /* monotone counter  */
  * (age 0 = newest); blocks only until those rows are complete. */
 int  zfb_read_rows(zfb_engine *e, int age, int nrows, float *h_out);
 
+/* append `nrows` host rows (float32 [nrows][row_width]) to the device ring, as
+ * if the engine had produced them (Waterfall.image_update(psd) with a row
+ * that was computed elsewhere, S:1638-1652). */
+int  zfb_ring_push_rows(zfb_engine *e, const float *h_rows, int nrows);
+
+/* ---- pinned sample ring with double-buffered device mirror -------------
+ * Replaces Data.data (T:1415-1421) and the copy-in of Data.add (T:1447): the
+ * producer thread writes chunks into pinned host memory and each chunk is sent
+ * to the device at once by an async H2D copy on the engine's copy stream, so
+ * the samples are already resident when PSD.update (T:1513) asks for a row.
+ * Fold-back bookkeeping (size / real_size / total_size) stays with the caller. */
+int  zfb_samples_create(zfb_engine *e, int64_t capacity_samples, int dtype);
+/* pinned host storage of the ring (capacity * sample size bytes) or NULL */
+void *zfb_samples_host_ptr(zfb_engine *e);
+/* call before writing host samples [offset, offset+n): waits until no earlier
+ * H2D copy still reads that memory */
+int  zfb_samples_begin_write(zfb_engine *e, int64_t offset, int64_t n);
+/* samples [offset, offset+n) are written: enqueue their H2D copy */
+int  zfb_samples_commit(zfb_engine *e, int64_t offset, int64_t n);
+/* run the configured chain on samples [0, cfg.frame_len) of the device mirror
+ * (one frame), copy the row to h_row (row_width floats) and switch the
+ * producer to the other device mirror.  Blocks until h_row is complete. */
+int  zfb_samples_process(zfb_engine *e, float *h_row);
+
 /* ---- pinned host memory for the sample ring (replaces Data.data,
  *      T:1415,1421) ------------------------------------------------------ */
 int  zfb_alloc_pinned(size_t bytes, void **out);

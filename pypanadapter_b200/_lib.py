@@ -71,6 +71,12 @@ SYMBOLS = {
     "zfb_ring_configure": (C.c_int, [_P, C.c_int]),
     "zfb_ring_rows_written": (C.c_int64, [_P]),
     "zfb_read_rows": (C.c_int, [_P, C.c_int, C.c_int, _P]),
+    "zfb_ring_push_rows": (C.c_int, [_P, _P, C.c_int]),
+    "zfb_samples_create": (C.c_int, [_P, C.c_int64, C.c_int]),
+    "zfb_samples_host_ptr": (_P, [_P]),
+    "zfb_samples_begin_write": (C.c_int, [_P, C.c_int64, C.c_int64]),
+    "zfb_samples_commit": (C.c_int, [_P, C.c_int64, C.c_int64]),
+    "zfb_samples_process": (C.c_int, [_P, _P]),
     "zfb_alloc_pinned": (C.c_int, [C.c_size_t, C.POINTER(_P)]),
     "zfb_free_pinned": (C.c_int, [_P]),
     "zfb_decim_sos": (C.c_int, [C.POINTER(C.c_double)]),

@@ -74,6 +74,17 @@ struct zfb_engine {
     int64_t ring_written = 0;
     int last_group_frames = 0;
 
+    // pinned sample ring + double-buffered device mirror
+    void   *sr_host = nullptr;
+    DevBuf  sr_dev[2];
+    int64_t sr_cap = 0;
+    int     sr_dtype = 0;
+    int     sr_active = 0;               // mirror the producer currently fills
+    cudaEvent_t sr_copied = nullptr;     // last H2D enqueued on the copy stream
+    cudaEvent_t sr_free[2] = {nullptr, nullptr};   // compute finished reading mirror i
+    bool    sr_free_pending[2] = {false, false};
+    bool    sr_copy_pending = false;
+
     uint64_t counters[5] = {0, 0, 0, 0, 0};
 
     // optional per-kernel timing
@@ -653,6 +664,11 @@ void zfb_destroy(zfb_engine *e) {
     }
     for (auto *v : {&e->prof_used, &e->prof_free})
         for (auto &r : *v) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    if (e->sr_host) cudaFreeHost(e->sr_host);
+    release(e->sr_dev[0]);
+    release(e->sr_dev[1]);
+    if (e->sr_copied) cudaEventDestroy(e->sr_copied);
+    for (int i = 0; i < 2; ++i) if (e->sr_free[i]) cudaEventDestroy(e->sr_free[i]);
     if (e->h_rows) cudaFreeHost(e->h_rows);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
@@ -1021,6 +1037,121 @@ int zfb_read_rows(zfb_engine *e, int age, int nrows, float *h_out) {
     }
     CK(e, cudaStreamSynchronize(e->stream));
     e->counters[4] += (size_t)nrows * rb;
+    return ZFB_OK;
+}
+
+int zfb_ring_push_rows(zfb_engine *e, const float *h_rows, int nrows) {
+    if (!e) return ZFB_EINVAL;
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (!e->configured) return fail(e, ZFB_ESTATE, "engine is not configured");
+    if (!h_rows || nrows < 0) return fail(e, ZFB_EINVAL, "push_rows: bad arguments");
+    CK(e, cudaSetDevice(e->device));
+    const size_t rb = (size_t)e->W * sizeof(float);
+    for (int i = 0; i < nrows; ++i) {
+        const int64_t slot = e->ring_written % e->ring_rows;
+        CK(e, cudaMemcpyAsync((char *)e->ring.p + (size_t)slot * rb, (const char *)h_rows + (size_t)i * rb, rb,
+                              cudaMemcpyHostToDevice, e->stream));
+        e->ring_written += 1;
+    }
+    CK(e, cudaStreamSynchronize(e->stream));      // caller's buffer may be pageable / reused
+    e->counters[3] += (size_t)nrows * rb;
+    return ZFB_OK;
+}
+
+int zfb_samples_create(zfb_engine *e, int64_t capacity_samples, int dtype) {
+    if (!e) return ZFB_EINVAL;
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (capacity_samples < 1 || capacity_samples > (1ll << 31))
+        return fail(e, ZFB_EINVAL, "sample ring capacity out of range");
+    if (dtype != ZFB_DTYPE_C64 && dtype != ZFB_DTYPE_U8) return fail(e, ZFB_EINVAL, "unknown dtype %d", dtype);
+    CK(e, cudaSetDevice(e->device));
+    CK(e, cudaStreamSynchronize(e->stream));
+    CK(e, cudaStreamSynchronize(e->copy_stream));
+    const size_t bytes = (size_t)capacity_samples * (dtype == ZFB_DTYPE_U8 ? 2 : 8);
+    if (e->sr_host) { CK(e, cudaFreeHost(e->sr_host)); e->sr_host = nullptr; }
+    CK(e, cudaMallocHost(&e->sr_host, bytes));
+    memset(e->sr_host, 0, bytes);
+    for (int i = 0; i < 2; ++i) {
+        int rc = ensure(e, e->sr_dev[i], bytes);
+        if (rc) return rc;
+        CK(e, cudaMemsetAsync(e->sr_dev[i].p, 0, bytes, e->stream));
+        if (!e->sr_free[i]) CK(e, cudaEventCreateWithFlags(&e->sr_free[i], cudaEventDisableTiming));
+        e->sr_free_pending[i] = false;
+    }
+    if (!e->sr_copied) CK(e, cudaEventCreateWithFlags(&e->sr_copied, cudaEventDisableTiming));
+    CK(e, cudaStreamSynchronize(e->stream));
+    e->sr_cap = capacity_samples;
+    e->sr_dtype = dtype;
+    e->sr_active = 0;
+    e->sr_copy_pending = false;
+    return ZFB_OK;
+}
+
+void *zfb_samples_host_ptr(zfb_engine *e) { return e ? e->sr_host : nullptr; }
+
+int zfb_samples_begin_write(zfb_engine *e, int64_t offset, int64_t n) {
+    if (!e) return ZFB_EINVAL;
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (!e->sr_host) return fail(e, ZFB_ESTATE, "no sample ring (zfb_samples_create)");
+    if (offset < 0 || n < 0 || offset + n > e->sr_cap) return fail(e, ZFB_EINVAL, "sample span out of range");
+    // copies are enqueued in order on one stream: once the newest has finished, none reads host memory
+    if (e->sr_copy_pending) {
+        CK(e, cudaSetDevice(e->device));
+        CK(e, cudaEventSynchronize(e->sr_copied));
+        e->sr_copy_pending = false;
+    }
+    return ZFB_OK;
+}
+
+int zfb_samples_commit(zfb_engine *e, int64_t offset, int64_t n) {
+    if (!e) return ZFB_EINVAL;
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (!e->sr_host) return fail(e, ZFB_ESTATE, "no sample ring (zfb_samples_create)");
+    if (offset < 0 || n < 0 || offset + n > e->sr_cap) return fail(e, ZFB_EINVAL, "sample span out of range");
+    if (n == 0) return ZFB_OK;
+    CK(e, cudaSetDevice(e->device));
+    const size_t esz = e->sr_dtype == ZFB_DTYPE_U8 ? 2 : 8;
+    const int m = e->sr_active;
+    if (e->sr_free_pending[m]) {       // a kernel may still be reading this mirror
+        CK(e, cudaStreamWaitEvent(e->copy_stream, e->sr_free[m], 0));
+        e->sr_free_pending[m] = false;
+    }
+    CK(e, cudaMemcpyAsync((char *)e->sr_dev[m].p + (size_t)offset * esz, (const char *)e->sr_host + (size_t)offset * esz,
+                          (size_t)n * esz, cudaMemcpyHostToDevice, e->copy_stream));
+    CK(e, cudaEventRecord(e->sr_copied, e->copy_stream));
+    e->sr_copy_pending = true;
+    e->counters[3] += (size_t)n * esz;
+    return ZFB_OK;
+}
+
+int zfb_samples_process(zfb_engine *e, float *h_row) {
+    if (!e) return ZFB_EINVAL;
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (!e->configured) return fail(e, ZFB_ESTATE, "process: engine is not configured");
+    if (!e->sr_host) return fail(e, ZFB_ESTATE, "no sample ring (zfb_samples_create)");
+    if (!h_row) return fail(e, ZFB_EINVAL, "process: h_row is NULL");
+    if (e->cfg.dtype != e->sr_dtype) return fail(e, ZFB_EINVAL, "configured dtype differs from the sample ring's");
+    if ((int64_t)e->cfg.frame_len > e->sr_cap) return fail(e, ZFB_EINVAL, "frame_len exceeds the sample ring");
+    CK(e, cudaSetDevice(e->device));
+    const int m = e->sr_active;
+    if (e->sr_copy_pending) CK(e, cudaStreamWaitEvent(e->stream, e->sr_copied, 0));
+    int rc = ensure(e, e->rows_tmp, (size_t)e->W * sizeof(float));
+    if (rc) return rc;
+    rc = run_group(e, e->sr_dev[m].p, 1, (float *)e->rows_tmp.p);
+    if (rc) return rc;
+    CK(e, cudaEventRecord(e->sr_free[m], e->stream));
+    e->sr_free_pending[m] = true;
+    e->sr_active = m ^ 1;                          // the producer moves to the other mirror
+    if (e->h_rows_cap < (size_t)e->W * sizeof(float)) {
+        if (e->h_rows) CK(e, cudaFreeHost(e->h_rows));
+        e->h_rows = nullptr;
+        CK(e, cudaMallocHost(&e->h_rows, (size_t)e->W * sizeof(float)));
+        e->h_rows_cap = (size_t)e->W * sizeof(float);
+    }
+    CK(e, cudaMemcpyAsync(e->h_rows, e->rows_tmp.p, (size_t)e->W * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    CK(e, cudaStreamSynchronize(e->stream));
+    memcpy(h_row, e->h_rows, (size_t)e->W * sizeof(float));
+    e->counters[4] += (size_t)e->W * sizeof(float);
     return ZFB_OK;
 }
 

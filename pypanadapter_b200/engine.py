@@ -259,6 +259,39 @@ class ZoomPSD:
         self._check(self._lib.zfb_get_profile(self._h, ms, n), "zfb_get_profile")
         return {_prof_name(c): (float(ms[c]), int(n[c])) for c in range(_lib.PROF_CLASSES) if n[c]}
 
+    def push_rows(self, rows):
+        """Append host rows to the device ring (rows computed elsewhere)."""
+        r = np.ascontiguousarray(rows, dtype=np.float32)
+        if r.ndim == 1:
+            r = r.reshape(1, -1)
+        if r.shape[1] != self.row_width:
+            raise ValueError("rows must be %d wide" % self.row_width)
+        self._check(self._lib.zfb_ring_push_rows(self._h, C.c_void_p(r.ctypes.data), r.shape[0]),
+                    "zfb_ring_push_rows")
+
+    # -- pinned sample ring (storage of buffers.Data) ------------------------
+    def samples_create(self, capacity: int, dtype: str = "c64") -> np.ndarray:
+        """Allocate the pinned sample ring + device mirrors; returns a numpy
+        view of the pinned host storage (complex64[capacity] or uint8[2*capacity])."""
+        code = {"c64": _lib.ZFB_DTYPE_C64, "u8": _lib.ZFB_DTYPE_U8}[dtype]
+        self._check(self._lib.zfb_samples_create(self._h, int(capacity), code), "zfb_samples_create")
+        ptr = self._lib.zfb_samples_host_ptr(self._h)
+        nbytes = int(capacity) * (2 if dtype == "u8" else 8)
+        raw = (C.c_ubyte * nbytes).from_address(ptr)
+        a = np.frombuffer(raw, dtype=np.uint8)
+        return a if dtype == "u8" else a.view(np.complex64)
+
+    def samples_begin_write(self, offset: int, n: int):
+        self._check(self._lib.zfb_samples_begin_write(self._h, int(offset), int(n)), "zfb_samples_begin_write")
+
+    def samples_commit(self, offset: int, n: int):
+        self._check(self._lib.zfb_samples_commit(self._h, int(offset), int(n)), "zfb_samples_commit")
+
+    def samples_process(self) -> np.ndarray:
+        out = np.empty(self.row_width, dtype=np.float32)
+        self._check(self._lib.zfb_samples_process(self._h, C.c_void_p(out.ctypes.data)), "zfb_samples_process")
+        return out
+
     def counters(self) -> dict:
         c = (C.c_uint64 * 5)()
         self._check(self._lib.zfb_get_counters(self._h, c), "zfb_get_counters")

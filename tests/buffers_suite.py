@@ -1,0 +1,222 @@
+"""Checks of the buffer mirrors (pypanadapter_b200.buffers), shared by the CPU
+emulation tests and the GPU tests."""
+from __future__ import annotations
+
+import os
+import types
+
+import numpy as np
+
+from oracle import golden_cases as gc
+from oracle import make_golden as mg
+from oracle import zoompsd_oracle as zo
+from pypanadapter_b200 import synth
+from pypanadapter_b200.buffers import PSD, Data, Waterfall
+from tests import parity
+
+
+def data_foldback(engine):
+    """Data.add / get_data_* reproduce the reference's fold-back trace
+    (golden data_trace.npz, recorded from T:1400-1483) and contents."""
+    g = np.load(os.path.join(parity.GOLDEN_DIR, "data_trace.npz"))
+    d = Data(engine=engine).new_complex()
+    assert d.max_size == int(g["max_size"]) and d.maxsize == d.max_size
+    assert d.data.dtype == np.complex64 and len(d.data) == d.max_size
+    trace = []
+    for chunk in mg.data_trace_chunks():
+        d.add(chunk)
+        trace.append((d.size, d.real_size, d.total_size))
+    assert np.array_equal(np.array(trace), g["trace"])
+    d.get_data_start()
+    tail = d.data[:d.real_size].copy()
+    d.get_data_end()
+    assert (d.size, d.real_size, d.total_size) == (0, 0, 0)
+    assert np.array_equal(tail, g["tail"].astype(np.complex64))
+
+
+def psd_update_matches_reference(engine):
+    """PSD.update on Data fed chunk by chunk == the golden row the reference's
+    own PSD.update produced for the same samples (cfg1_T)."""
+    case = gc.case_by_name("cfg1_T")
+    x = gc.make_input(case)
+    state = types.SimpleNamespace(fft_size=case["N"], fft_ratio=case["R"], fft_tapering=case["window"],
+                                  panadapter=types.SimpleNamespace(SampleRate=case["fs"]))
+    d = Data(engine=engine).new_complex()
+    psd = PSD(d, state)
+    assert psd.psd.shape == (case["N"],) and not psd.psd.any()
+    for i in range(0, len(x), d.chunk_size):
+        d.add(x[i:i + d.chunk_size])
+    assert d.real_size == len(x)
+    psd.update()
+    psd.lock.lock()
+    row = psd.psd
+    psd.lock.unlock()
+    floor = parity.floor_db20(case["fs"], case["window"], case["N"], True)
+    parity.assert_row_parity(row, parity.golden_rows()["cfg1_T"], floor, "PSD.update")
+    assert (d.size, d.real_size, d.total_size) == (0, 0, 0)
+    # too little data: psd stays as it is (T:1522)
+    d.add(x[:1000])
+    before = psd.psd
+    psd.update()
+    assert psd.psd is before
+    # a second, different frame goes through the other device mirror
+    x2 = synth.make_frame(synth.CFG1, 1)
+    for i in range(0, len(x2), d.chunk_size):
+        d.add(x2[i:i + d.chunk_size])
+    psd.update()
+    want = zo.zoom_psd(x2, case["fs"], case["N"], case["R"], case["window"])
+    parity.assert_row_parity(psd.psd, want, floor, "PSD.update frame 2")
+
+
+def psd_update_u8(engine):
+    """uint8 wire format through Data.new_u8 (conversion on the device)."""
+    w = synth.CFG2
+    raw = synth.make_frame(w, 0, n=4096 * 32)
+    state = types.SimpleNamespace(fft_size=w.fft_size, fft_ratio=w.fft_ratio, fft_tapering=w.window,
+                                  panadapter=types.SimpleNamespace(SampleRate=w.fs))
+    d = Data(engine=engine).new_u8()
+    psd = PSD(d, state, flip=True)
+    step = 2 * d.chunk_size
+    for i in range(0, len(raw), step):
+        d.add(raw[i:i + step])
+    psd.update()
+    want = zo.zoom_psd(raw, w.fs, w.fft_size, w.fft_ratio, w.window, flip=True)
+    parity.assert_row_parity(psd.psd, want, parity.floor_db20(w.fs, w.window, w.fft_size, True), "u8 PSD.update")
+
+
+def waterfall_image(engine):
+    """Waterfall.img_array assembled from the device ring == the reference's
+    img_array after the same image_update calls (golden waterfall.npz)."""
+    g = np.load(os.path.join(parity.GOLDEN_DIR, "waterfall.npz"))
+    rows = [np.full(256, -100.0 - i) + np.arange(256) * 0.01 for i in range(70)]
+    engine.configure(2.4e6, 2048, 8, 2048 * 10, "hamming", crop="thread")      # row_width 256
+    for scroll, key in ((1, "img_pos"), (-1, "img_neg")):
+        wf = Waterfall(engine, scroll=scroll)
+        img = None
+        for n, r in enumerate(rows, 1):
+            r = r.copy()
+            wf.image_update(r)
+            assert r[0] == 0 and r[128] == 0 and r[255] == 0       # mutated in place like the reference
+            if n in (1, 2, 5, 6, 7, 20, 63, 64, 65, 70):
+                ref = None
+                for rr in rows[:n]:
+                    ref = zo.waterfall_update(ref, rr.copy(), scroll)
+                got = wf.img_array
+                # device rows are float32
+                assert got.shape == ref.shape
+                assert np.abs(got - ref).max() < 1e-4, (scroll, n)
+        assert np.abs(wf.img_array - g[key]).max() < 1e-4
+
+
+def waterfall_from_engine_rows(engine):
+    """Rows the engine produced itself are not pushed twice."""
+    w = synth.CFG1
+    n = 2048 * 10
+    frames = synth.make_frames(w, 3, n=n)
+    engine.configure(w.fs, w.fft_size, w.fft_ratio, n, w.window, crop="thread")
+    wf = Waterfall(engine)
+    wf.fftwidth = 256
+    wf.init_image()
+    for f in frames:
+        row = engine.process(f)[0].astype(np.float64)
+        wf.note_engine_rows(1)
+        wf.image_update(row)
+    assert engine.rows_written == 3
+    img = wf.img_array
+    h = img.shape[0]
+    last = engine.read_rows(1)[0].astype(np.float64)
+    last[[0, 128, 255]] = 0
+    assert np.array_equal(img[h - 2], last)
+
+
+def scipy_shaped_calls(engine):
+    """pypanadapter_b200.signal.decimate / welch against scipy's own."""
+    import scipy.signal
+    from pypanadapter_b200 import signal as zsig
+    rng = np.random.default_rng(17)
+    x = (rng.standard_normal(6000) + 1j * rng.standard_normal(6000)) * 0.3
+    x += 0.5 * np.exp(2j * np.pi * 0.0123 * np.arange(6000))
+    y = zsig.decimate(x, 2, engine=engine)
+    ref = scipy.signal.decimate(x, 2)
+    assert y.dtype == np.complex128 and y.shape == ref.shape
+    assert np.abs(y - ref).max() < 2e-6 * np.abs(ref).max() + 1e-7
+    y4 = zsig.decimate(x.astype(np.complex64), 4, engine=engine)
+    ref4 = scipy.signal.decimate(scipy.signal.decimate(x, 2), 2)
+    assert y4.dtype == np.complex64 and np.abs(y4 - ref4).max() < 5e-6
+    f, p = zsig.welch(x, 48e3, window="hamming", nperseg=512, nfft=512, engine=engine)
+    fr, pr = scipy.signal.welch(x, 48e3, window="hamming", nperseg=512, nfft=512)
+    assert np.array_equal(f, fr) and p.dtype == np.float64
+    assert np.abs(10 * np.log10(p / pr)).max() < 0.005
+    import pytest
+    with pytest.raises(NotImplementedError):
+        zsig.decimate(x, 3, engine=engine)
+    with pytest.raises(NotImplementedError):
+        zsig.welch(x.real, 48e3, nperseg=512, engine=engine)
+    with pytest.raises(ValueError):
+        zsig.decimate(x[:27], 2, engine=engine)          # scipy: padlen
+
+
+def dropin_on_reference_modules(engine):
+    """dropin.install on the UNMODIFIED reference modules (build container
+    only): their own update()/PSD.update() call sequences now produce the
+    golden rows through the engine."""
+    import types
+    from oracle import ref_harness as rh
+    from pypanadapter_b200 import dropin
+    if not rh.available():
+        import pytest
+        pytest.skip("reference tree not present")
+    # ---- spectrum variant: ApplicationDisplay.update(chunk) ----
+    mod = rh.load("spectrum")
+    saved = dropin.install(mod, engine=engine)
+    try:
+        for name in ("cfg1_S1024", "cfg1_S256", "defaults_S"):
+            case = gc.case_by_name(name)
+            x = gc.make_input(case)
+            rh._set_state(mod, case["fs"], case["N"], case["R"], len(x) // case["N"], case["window"])
+            got = {}
+            fake = types.SimpleNamespace(N_WIN=case["n_win"], win=rh._Anything(), spectrum_plot=rh._Anything(),
+                                         waterfall=types.SimpleNamespace(
+                                             image_update=lambda psd: got.__setitem__("psd", psd.copy())))
+            mod.ApplicationDisplay.update(fake, x)
+            floor = parity.floor_db20(case["fs"], case["window"], case["N"], case["R"] > 1)
+            parity.assert_row_parity(got["psd"], parity.golden_rows()[name], floor, "dropin " + name)
+        case = gc.ZOOMFFT_CASES[0]
+        x = gc.make_input(case)
+        rh._set_state(mod, case["fs"], case["N"], case["R"], len(x) // case["N"], "hamming")
+        z = mod.ApplicationDisplay.zoomfft(types.SimpleNamespace(), x, case["R"])
+        ref = np.load(os.path.join(parity.GOLDEN_DIR, "zoomfft.npz"))[case["name"]]
+        assert np.abs(z - ref).max() < 2e-5 * np.abs(ref).max()
+    finally:
+        dropin.uninstall(mod, saved)
+    assert mod.ApplicationDisplay.update is saved["ApplicationDisplay.update"]
+    # ---- thread variant: Data + PSD.update ----
+    mod = rh.load("thread")
+    saved = dropin.install(mod, engine=engine)
+    try:
+        case = gc.case_by_name("cfg1_T")
+        x = gc.make_input(case)
+        rh._set_state(mod, case["fs"], case["N"], case["R"], 1, case["window"])
+        d = mod.Data()
+        assert isinstance(d, buffers_Data())
+        d.NR = types.SimpleNamespace(next=lambda y: 0.0, target=0)
+        d.new_complex()
+        d.delay_time = 0.
+        for i in range(0, len(x), d.chunk_size):
+            d.add(x[i:i + d.chunk_size])
+            d.delay_time = 0.
+        psd = types.SimpleNamespace(dataclass=d, lock=rh._Mutex(), psd=None)
+        mod.PSD.update(psd)
+        floor = parity.floor_db20(case["fs"], case["window"], case["N"], True)
+        parity.assert_row_parity(psd.psd, parity.golden_rows()["cfg1_T"], floor, "dropin PSD.update")
+        d.target = 100000
+        assert d.target == 100000
+        d.target = 10             # below fft_size: ignored (T:1476)
+        assert d.target == 100000
+    finally:
+        dropin.uninstall(mod, saved)
+
+
+def buffers_Data():
+    from pypanadapter_b200.buffers import Data as D
+    return D

@@ -45,3 +45,35 @@ def test_f_demod(emu_engine):
 
 def test_tile_geometries(emu_engine):
     es.tile_geometries(emu_engine)
+
+
+# ---- buffer mirrors (Data / PSD / Waterfall) on the emulated engine ----------
+from tests import buffers_suite as bs  # noqa: E402
+
+
+def test_data_foldback(emu_engine):
+    bs.data_foldback(emu_engine)
+
+
+def test_psd_update(emu_engine):
+    bs.psd_update_matches_reference(emu_engine)
+
+
+def test_psd_update_u8(emu_engine):
+    bs.psd_update_u8(emu_engine)
+
+
+def test_waterfall_image(emu_engine):
+    bs.waterfall_image(emu_engine)
+
+
+def test_waterfall_engine_rows(emu_engine):
+    bs.waterfall_from_engine_rows(emu_engine)
+
+
+def test_scipy_shaped_calls(emu_engine):
+    bs.scipy_shaped_calls(emu_engine)
+
+
+def test_dropin_on_reference_modules(emu_engine):
+    bs.dropin_on_reference_modules(emu_engine)

@@ -121,3 +121,35 @@ def test_device_path_equals_host_path(gpu_engine):
 
 def test_tile_geometries(gpu_engine):
     es.tile_geometries(gpu_engine)
+
+
+# ---- buffer mirrors (Data / PSD / Waterfall) on the GPU ------------------------
+from tests import buffers_suite as bs  # noqa: E402
+
+
+def test_data_foldback(gpu_engine):
+    bs.data_foldback(gpu_engine)
+
+
+def test_psd_update(gpu_engine):
+    bs.psd_update_matches_reference(gpu_engine)
+
+
+def test_psd_update_u8(gpu_engine):
+    bs.psd_update_u8(gpu_engine)
+
+
+def test_waterfall_image(gpu_engine):
+    bs.waterfall_image(gpu_engine)
+
+
+def test_waterfall_engine_rows(gpu_engine):
+    bs.waterfall_from_engine_rows(gpu_engine)
+
+
+def test_scipy_shaped_calls(gpu_engine):
+    bs.scipy_shaped_calls(gpu_engine)
+
+
+def test_dropin_on_reference_modules(gpu_engine):
+    bs.dropin_on_reference_modules(gpu_engine)       # skipped where /root/reference is absent
