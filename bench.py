@@ -195,12 +195,14 @@ def measured_hbm_peak():
         return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(workload, kernel):
-    """Per-launch DRAM bytes of the dominant kernel from the committed ncu
-    --set full capture (profiles/roofline_traffic.json), or None."""
+def ncu_traffic(workload, kernel, frames_per_launch):
+    """Per-launch DRAM bytes (read + write) of the dominant kernel, from the
+    committed ncu --set full capture (profiles/roofline_traffic.json holds it
+    per frame; a launch processes ``frames_per_launch`` frames), or None."""
     try:
         with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
-            return json.load(f).get(workload, {}).get(kernel)
+            rec = json.load(f).get(workload, {}).get(kernel)
+        return None if rec is None else rec["dram_bytes_per_frame"] * frames_per_launch
     except Exception:
         return None
 
@@ -243,7 +245,13 @@ def run_b200(args, w):
             dist.barrier()
         torch.cuda.synchronize()
 
-    eng = ZoomPSD(local_rank)
+    if args.lib:        # tuning experiments: an alternative sm_100a build of the same sources
+        from pypanadapter_b200 import _lib
+        alt = _lib.load_library(args.lib)
+        assert alt.zfb_build_kind() == b"sm_100a"
+        eng = ZoomPSD(local_rank, lib=alt)
+    else:
+        eng = ZoomPSD(local_rank)
     if args.group:
         eng.set_group(args.group)
     if args.decim_threads:
@@ -352,7 +360,8 @@ def run_b200(args, w):
         step_bytes = F * (w.frame_len * b_in + 4 * W * (3 if w.ema_alpha is not None else 1))
         roofline = {
             "bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
-            "frac": achieved / peak, "traffic": ncu_traffic(w.name, top), "peak_source": peak_src,
+            "frac": achieved / peak,
+            "traffic": ncu_traffic(w.name, top, args.steps * F / max(1, top_n)), "peak_source": peak_src,
             "launches": top_n, "avg_launch_ms": top_ms / max(1, top_n),
             "algorithmic_bytes_per_launch": algo_bytes_total / max(1, top_n),
             "kernel_share_of_step": top_ms / total_kernel_ms,
@@ -398,6 +407,7 @@ def main():
     ap.add_argument("--frames", type=int, default=256, help="frames per step per GPU")
     ap.add_argument("--group", type=int, default=0, help="frames per launch group (0 = auto)")
     ap.add_argument("--decim-threads", type=int, default=0, help="tuning: 0 auto, 128 or 256")
+    ap.add_argument("--lib", default=None, help="tuning: path of an alternative sm_100a build")
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -23,7 +23,13 @@
 #pragma once
 #include "zfb_common.cuh"
 
+#ifndef ZFB_SWEEP_UNROLL
+#define ZFB_SWEEP_UNROLL 12
+#endif
+
 namespace zfb {
+
+constexpr int SWEEP_UNROLL = ZFB_SWEEP_UNROLL;     // steps of the pipelined sweep per loop trip
 
 __constant__ DecimConst c_dec;
 
@@ -99,17 +105,22 @@ __device__ __forceinline__ void sweep_full(float2 *blk, Sec4 &s, const float (&n
         p2 = n2;
         p1 = n1;
     }
-#pragma unroll 4
-    for (int i = 3; i < BLK; ++i) {
-        float2 y = pole(p2, s.w1[3], s.w2[3], na1[3], na2[3]);
-        float2 n2 = pole(p1, s.w1[2], s.w2[2], na1[2], na2[2]);
-        float2 n1 = pole(p0, s.w1[1], s.w2[1], na1[1], na2[1]);
-        float2 n0 = pole(blk[ZFB_POS(i)], s.w1[0], s.w2[0], na1[0], na2[0]);
-        if (STORE) blk[ZFB_POS(i - 3)] = y;
-        p2 = n2;
-        p1 = n1;
-        p0 = n0;
+    // steady part: BLK - 3 = 61 steps = 1 + 60, the 60 unrolled by ZFB_SWEEP_UNROLL
+#define ZFB_SWEEP_STEP(i)                                                         \
+    {                                                                             \
+        float2 y = pole(p2, s.w1[3], s.w2[3], na1[3], na2[3]);                    \
+        float2 n2 = pole(p1, s.w1[2], s.w2[2], na1[2], na2[2]);                   \
+        float2 n1 = pole(p0, s.w1[1], s.w2[1], na1[1], na2[1]);                   \
+        float2 n0 = pole(blk[ZFB_POS(i)], s.w1[0], s.w2[0], na1[0], na2[0]);      \
+        if (STORE) blk[ZFB_POS((i) - 3)] = y;                                     \
+        p2 = n2;                                                                  \
+        p1 = n1;                                                                  \
+        p0 = n0;                                                                  \
     }
+    ZFB_SWEEP_STEP(3)
+#pragma unroll SWEEP_UNROLL
+    for (int i = 4; i < BLK; ++i) ZFB_SWEEP_STEP(i)
+#undef ZFB_SWEEP_STEP
     {
         float2 y = pole(p2, s.w1[3], s.w2[3], na1[3], na2[3]);
         float2 n2 = pole(p1, s.w1[2], s.w2[2], na1[2], na2[2]);

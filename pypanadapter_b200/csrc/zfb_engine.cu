@@ -406,6 +406,7 @@ int choose_group(const zfb_engine *e) {
     long long g = (long long)(256ull << 20) / (long long)per_frame;
     if (g < 1) g = 1;
     if (g > 2048) g = 2048;
+    if (g > 32) g -= g % 32;              // typical batches (powers of two) split into equal groups
     return (int)g;
 }
 
