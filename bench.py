@@ -257,7 +257,7 @@ def run_b200(args, w):
     if args.decim_threads:
         eng.set_option("decim_threads", args.decim_threads)
     eng.configure(w.fs, w.fft_size, w.fft_ratio, w.frame_len, w.window, dtype=w.dtype, flip=w.flip,
-                  f_demod=w.f_demod, crop=w.crop, ema_alpha=w.ema_alpha)
+                  f_demod=w.f_demod, crop=w.crop, ema_alpha=w.ema_alpha, mode=args.mode)
     # a real (non-default) stream: the engine launches on it, NCCL enqueues on
     # it and the timing events are recorded on it
     stream = torch.cuda.Stream()
@@ -401,6 +401,7 @@ def run_b200(args, w):
         cfg["parallelism"] = "frames sharded, %d rank(s), rows gathered to rank 0 over NCCL" % world
         cfg["group_frames"] = args.group or "auto"
         cfg["decim_threads"] = args.decim_threads or "auto"
+        cfg["decimator_mode"] = "fast" if eng.fast_active else "exact"
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -433,6 +434,8 @@ def main():
     ap.add_argument("--frames", type=int, default=256, help="frames per step per GPU")
     ap.add_argument("--group", type=int, default=0, help="frames per launch group (0 = auto)")
     ap.add_argument("--decim-threads", type=int, default=0, help="tuning: 0 auto, 128 or 256")
+    ap.add_argument("--mode", default="exact", choices=["exact", "fast"],
+                    help="decimator: exact zero-phase IIR everywhere, or polyphase-FIR interior + exact edges")
     ap.add_argument("--lib", default=None, help="tuning: path of an alternative sm_100a build")
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -45,6 +45,12 @@ extern "C" {
 /* decimator implementations (zfb_config.mode) */
 #define ZFB_MODE_EXACT  0      /* per-chunk zero-phase cheby1 IIR, scipy semantics */
 
+#define ZFB_MODE_FAST   1      /* interior: fused NCO mix + multistage polyphase FIR
+                                  decimator + compensator for all but the last
+                                  decimate call, last call and both chunk edges by
+                                  the exact kernels (needs zfb_set_fast_plan; falls
+                                  back to EXACT for fft_ratio < 4 or short chunks) */
+
 /* zfb_config.flags */
 #define ZFB_FLAG_NO_LO   1     /* skip the LO mix (amplitude 1, f = 0): the chain is
                                   then exactly scipy.signal.decimate(x, 2) x log2(R)
@@ -86,11 +92,32 @@ void zfb_destroy(zfb_engine *e);
  * e == NULL).  Valid until the next call on the same engine/thread. */
 const char *zfb_last_error(const zfb_engine *e);
 
+/* FIR plan of ZFB_MODE_FAST for one fft_ratio: nstages = log2(R) - 1 symmetric
+ * decimate-by-2 FIRs (stage s at rate fs/2^s, 2*half[s]+1 taps, centre tap
+ * first) that replace the first log2(R)-1 scipy.signal.decimate calls of
+ * S:2097-2098 in the chunk interior, one symmetric compensator at rate
+ * 2fs/R, and the number of decimated samples at either chunk end that the
+ * exact path recomputes.  Designed by pypanadapter_b200/fastdesign.py. */
+#define ZFB_FAST_MAX_STAGES 12
+typedef struct zfb_fast_plan {
+    int32_t nstages;
+    int32_t half[ZFB_FAST_MAX_STAGES];
+    const double *taps[ZFB_FAST_MAX_STAGES];   /* half[s] + 1 values each */
+    int32_t comp_half;
+    const double *comp_taps;                   /* comp_half + 1 values */
+    int32_t strip;                             /* even, >= 64 */
+} zfb_fast_plan;
+
 /* ---- configuration ---------------------------------------------------- */
 /* (Re)plan for a frame shape.  Cheap when only frame_len changes; the
  * reference lets N, R, window, avg change between any two frames (S:1753,
  * S:2079-2086).  Resets the EMA state when the row geometry changes. */
 int  zfb_configure(zfb_engine *e, const zfb_config *cfg);
+/* Hand over (a copy of) the FIR plan the next zfb_configure with
+ * mode == ZFB_MODE_FAST uses; plan->nstages must be log2(fft_ratio) - 1. */
+int  zfb_set_fast_plan(zfb_engine *e, const zfb_fast_plan *plan);
+/* 1 if the current configuration runs the FAST interior, 0 if it runs EXACT. */
+int  zfb_fast_active(const zfb_engine *e);
 /* Use the caller's CUDA stream (cudaStream_t as void*) for all kernels;
  * NULL restores the engine's own stream. */
 int  zfb_set_stream(zfb_engine *e, void *cuda_stream);

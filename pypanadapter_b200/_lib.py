@@ -25,6 +25,8 @@ ZFB_ETOOSHORT = -34
 ZFB_DTYPE_C64 = 0
 ZFB_DTYPE_U8 = 1
 ZFB_MODE_EXACT = 0
+ZFB_MODE_FAST = 1
+FAST_MAX_STAGES = 12
 ZFB_FLAG_NO_LO = 1
 ZFB_FLAG_LINEAR = 2
 
@@ -51,6 +53,18 @@ class ZfbConfig(C.Structure):
     ]
 
 
+class ZfbFastPlan(C.Structure):
+    """struct zfb_fast_plan (include/zoomfft_b200.h)."""
+    _fields_ = [
+        ("nstages", C.c_int32),
+        ("half", C.c_int32 * FAST_MAX_STAGES),
+        ("taps", C.POINTER(C.c_double) * FAST_MAX_STAGES),
+        ("comp_half", C.c_int32),
+        ("comp_taps", C.POINTER(C.c_double)),
+        ("strip", C.c_int32),
+    ]
+
+
 # every symbol the header declares: name -> (restype, argtypes)
 _P = C.c_void_p
 SYMBOLS = {
@@ -60,6 +74,8 @@ SYMBOLS = {
     "zfb_destroy": (None, [_P]),
     "zfb_last_error": (C.c_char_p, [_P]),
     "zfb_configure": (C.c_int, [_P, C.POINTER(ZfbConfig)]),
+    "zfb_set_fast_plan": (C.c_int, [_P, C.POINTER(ZfbFastPlan)]),
+    "zfb_fast_active": (C.c_int, [_P]),
     "zfb_set_stream": (C.c_int, [_P, _P]),
     "zfb_set_group": (C.c_int, [_P, C.c_int]),
     "zfb_reset_ema": (C.c_int, [_P]),

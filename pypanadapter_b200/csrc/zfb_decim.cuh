@@ -42,6 +42,14 @@ struct StageParams {
     int         T;             // outputs span per tile (input-index units, %16==0)
     int         flip;
     unsigned long long phase_inc;   // frac(f_demod/fs) * 2^64
+    // strip mode (ZFB_MODE_FAST edge strips): blockIdx.y = 2*frame + side; each
+    // side is a short chunk of its own (L samples) cut from the frame's ends
+    int         strips;
+    long long   side_in_off;   // element offset of side 1 inside a frame's input
+    long long   side_out_off;  // element offset of side 1 inside a frame's output
+    int         pos_off;       // raw kinds: absolute position of side 1's sample 0 (LO phase, flip)
+    int         Lfull;         // raw kinds: length of the whole frame (flip index); L otherwise
+    int         w_lo[2], w_hi[2];   // outputs [w_lo, w_hi) of a side are written
     float2      lo_small[8];   // sqrt(2)*g*exp(-2pi i f/fs v), v = 0..7
     float2      lo_big[32];    // exp(-2pi i f/fs * it*NT*VEC)
 };
@@ -265,16 +273,18 @@ __device__ __forceinline__ float2 u8pair_to_iq(unsigned int word, int hi) {
 
 template <int KIND, int NT>
 __device__ __forceinline__ void load_region(float2 *buf, const StageParams &p,
-                                            const char *frame_in, int rs, int tid) {
+                                            const char *frame_in, int rs, int tid, int posoff) {
     constexpr int VEC = (KIND == KIND_U8_RAW) ? 8 : 2;
     constexpr int ITERS = BLK / VEC;
     constexpr int CH = 8;
     const int L = p.L;
     const bool fl = (KIND != KIND_C64_MID) && p.flip;
     float2 b0 = make_float2(1.f, 0.f);
-    if (KIND != KIND_C64_MID) b0 = lo_phasor((long long)rs + (long long)tid * VEC, p.phase_inc);
+    if (KIND != KIND_C64_MID)
+        b0 = lo_phasor((long long)rs + (long long)posoff + (long long)tid * VEC, p.phase_inc);
     const float g = c_dec.g;
     const size_t esz = (KIND == KIND_U8_RAW) ? 2 : 8;
+    const int Lf = p.Lfull;               // raw kinds index the whole frame: element = posoff + pos
 
 #pragma unroll 1
     for (int it0 = 0; it0 < ITERS; it0 += CH) {
@@ -283,8 +293,8 @@ __device__ __forceinline__ void load_region(float2 *buf, const StageParams &p,
 #pragma unroll
         for (int c = 0; c < CH; ++c) {
             const int pos = rs + ((it0 + c) * NT + tid) * VEC;
-            // sample index of element e: flip ? L-1-(pos+e) : pos+e
-            const long long i0 = fl ? (long long)L - VEC - pos : (long long)pos;
+            // sample index of element e: flip ? Lf-1-(posoff+pos+e) : posoff+pos+e
+            const long long i0 = fl ? (long long)Lf - VEC - pos - posoff : (long long)pos + posoff;
             const char *a = frame_in + (size_t)i0 * esz;
             vec_ok[c] = (pos >= 0) && (pos + VEC <= L) && ((((uintptr_t)a) & 15) == 0);
             raw[c] = vec_ok[c] ? __ldg((const uint4 *)a) : make_uint4(0u, 0u, 0u, 0u);
@@ -315,7 +325,7 @@ __device__ __forceinline__ void load_region(float2 *buf, const StageParams &p,
                     const int pe = pos + e;
                     v[e] = make_float2(0.f, 0.f);
                     if (pe >= 0 && pe < L) {
-                        const long long ie = fl ? (long long)L - 1 - pe : (long long)pe;
+                        const long long ie = fl ? (long long)Lf - 1 - pe - posoff : (long long)pe + posoff;
                         if (KIND == KIND_U8_RAW) {
                             const unsigned char *src = (const unsigned char *)frame_in;
                             v[e] = make_float2(u8_to_f(src[2 * ie]), u8_to_f(src[2 * ie + 1]));
@@ -349,15 +359,20 @@ __global__ void __launch_bounds__(NT, (NT == NTHR_BIG ? 1 : 3)) decim2_exact_ker
 
     const int tid   = threadIdx.x;
     const int tile  = blockIdx.x;
-    const int frame = blockIdx.y;
+    int frame = blockIdx.y, side = 0;
+    if (p.strips) {
+        side = frame & 1;
+        frame >>= 1;
+    }
     const int L     = p.L;
     const int p0    = tile * p.T;                 // first output position (even)
     const int rs    = p0 - WARM;                  // region start, ext coordinates
 
     const size_t esz = (KIND == KIND_U8_RAW) ? 2 : 8;
-    const char *frame_in = (const char *)p.in + (size_t)frame * (size_t)p.in_stride * esz;
+    const char *frame_in = (const char *)p.in +
+                           ((size_t)frame * (size_t)p.in_stride + (size_t)side * (size_t)p.side_in_off) * esz;
 
-    load_region<KIND, NT>(buf, p, frame_in, rs, tid);
+    load_region<KIND, NT>(buf, p, frame_in, rs, tid, (KIND != KIND_C64_MID && side) ? p.pos_off : 0);
     __syncthreads();
 
     // odd extension (scipy odd_ext, 27 samples each side) where it falls in the region
@@ -447,8 +462,10 @@ __global__ void __launch_bounds__(NT, (NT == NTHR_BIG ? 1 : 3)) decim2_exact_ker
     // ---------------- keep every 2nd sample of [p0, min(p0+T, L)) ----------------
     const int span = min(p.T, L - p0);
     const int nout = (span + 1) >> 1;
-    float2 *out = p.out + (size_t)frame * (size_t)p.out_stride + (p0 >> 1);
-    for (int i = tid; i < nout; i += NT) out[i] = buf[sidx(WARM + 2 * i)];
+    float2 *out = p.out + (size_t)frame * (size_t)p.out_stride + (size_t)side * (size_t)p.side_out_off + (p0 >> 1);
+    const int wlo = p.w_lo[side] - (p0 >> 1), whi = p.w_hi[side] - (p0 >> 1);
+    for (int i = tid; i < nout; i += NT)
+        if (i >= wlo && i < whi) out[i] = buf[sidx(WARM + 2 * i)];
 }
 
 }  // namespace zfb

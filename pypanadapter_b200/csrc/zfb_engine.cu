@@ -11,6 +11,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <limits.h>
+
 #include <algorithm>
 #include <mutex>
 #include <new>
@@ -21,6 +23,7 @@
 #include "zfb_decim.cuh"
 #include "zfb_welch.cuh"
 #include "zfb_bigfft.cuh"
+#include "zfb_firchain.cuh"
 
 using namespace zfb;
 
@@ -73,6 +76,27 @@ struct zfb_engine {
     int ring_rows = 256, ring_rows_req = 256, ring_W = 0;
     int64_t ring_written = 0;
     int last_group_frames = 0;
+
+    // ZFB_MODE_FAST
+    struct FastPlan {
+        bool set = false;
+        int ne = 0;                                   // FIR stages
+        int M[ZFB_FAST_MAX_STAGES] = {0};
+        float h[ZFB_FAST_MAX_STAGES][FIR_MAX_HALF + 1] = {{0}};
+        int Mc = -1;
+        float hc[FIR_COMP_MAX_HALF + 1] = {0};
+        int K = 128;
+    } fplan;
+    bool fast_active = false;
+    int nchains = 0;
+    FirChainParams chain[4]{};
+    int chain_level_out[4] = {0};      // decimation level (stage count) after chain j
+    size_t chain_smem[4] = {0};
+    int strip_len[kMaxStages] = {0};   // i_s: samples per strip at the input of stage s
+    int strip_q[kMaxStages] = {0};     // Q_s: absolute position of the right strip's first sample
+    int strip_cap = 0;
+    DevBuf sbuf[2];
+    int final_buf = 0;                 // mid[] index holding the decimated chunk of the last group
 
     // pinned sample ring + double-buffered device mirror
     void   *sr_host = nullptr;
@@ -373,6 +397,15 @@ DecimFn decim_lookup(int kind, int nt) {
 
 constexpr size_t decim_smem(int nt) { return (size_t)(nt * BLK_PAD + NSTATE * nt) * sizeof(float2); }
 
+typedef void (*ChainFn0)(const FirChainParams);
+ChainFn0 chain_lookup_fn(int kind) {
+    switch (kind) {
+        case KIND_C64_RAW: return fir_chain_kernel<KIND_C64_RAW>;
+        case KIND_U8_RAW: return fir_chain_kernel<KIND_U8_RAW>;
+        default: return fir_chain_kernel<KIND_C64_MID>;
+    }
+}
+
 int setup_device_once(zfb_engine *e) {
     DecimConst dc;
     build_decim_const(dc);
@@ -387,6 +420,8 @@ int setup_device_once(zfb_engine *e) {
             if (w.smem > 48 * 1024)
                 CK(e, cudaFuncSetAttribute(w.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.smem));
         }
+    for (int kind = 0; kind < 3; ++kind)
+        CK(e, cudaFuncSetAttribute(chain_lookup_fn(kind), cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     return ZFB_OK;
 }
 
@@ -446,6 +481,117 @@ void prof_end(zfb_engine *e, int idx) {
     if (idx >= 0) cudaEventRecord(e->prof_used[(size_t)idx].b, e->stream);
 }
 
+typedef void (*ChainFn)(const FirChainParams);
+ChainFn chain_lookup(int kind) {
+    switch (kind) {
+        case KIND_C64_RAW: return fir_chain_kernel<KIND_C64_RAW>;
+        case KIND_U8_RAW: return fir_chain_kernel<KIND_U8_RAW>;
+        default: return fir_chain_kernel<KIND_C64_MID>;
+    }
+}
+
+void launch_stage(zfb_engine *e, int kind, int v, const StageParams &p, unsigned tiles, unsigned ny, int cls) {
+    const int nt = v == 0 ? NTHR_BIG : NTHR_SMALL;
+    const int pr = prof_begin(e, cls);
+    ZFB_LAUNCH(decim_lookup(kind, nt), dim3(tiles, ny), dim3((unsigned)nt), decim_smem(nt), e->stream, p);
+    prof_end(e, pr);
+    e->counters[2] += 1;
+}
+
+// ZFB_MODE_FAST: FIR chains + exact last stage over the whole frames, then the
+// exact cascade on the two end strips of every frame; leaves the decimated
+// chunks in mid[*out_buf]
+void run_decimation_fast(zfb_engine *e, const void *d_in, int gf, int *out_buf) {
+    const zfb_config &c = e->cfg;
+    cudaStream_t st = e->stream;
+    const int k = e->nstages;
+    const void *src = d_in;
+    long long src_stride = c.frame_len;
+    int kind = raw_kind(c);
+    int b = 0;
+    for (int j = 0; j < e->nchains; ++j) {
+        FirChainParams p = e->chain[j];
+        const int lvl = e->chain_level_out[j];
+        p.in = src;
+        p.in_stride = src_stride;
+        p.out = (float2 *)e->mid[b].p;
+        p.out_stride = e->len[lvl];
+        const unsigned tiles = (unsigned)((e->len[lvl] + p.TO - 1) / p.TO);
+        const int pr = prof_begin(e, j == 0 ? 0 : 1);
+        ZFB_LAUNCH(chain_lookup(kind), dim3(tiles, (unsigned)gf), dim3(FIR_NT), e->chain_smem[j], st, p);
+        prof_end(e, pr);
+        e->counters[2] += 1;
+        src = p.out;
+        src_stride = p.out_stride;
+        kind = KIND_C64_MID;
+        b ^= 1;
+    }
+    const int v = (e->decim_threads == NTHR_BIG) ? 0 : 1;
+    {   // the last decimate call, exact, over the whole (FIR-filtered) chunk
+        const int s = k - 1;
+        StageParams p = e->sp0[v];
+        p.in = src;
+        p.in_stride = src_stride;
+        p.out = (float2 *)e->mid[b].p;
+        p.out_stride = e->len[k];
+        p.L = e->len[s];
+        p.T = e->T[s][v];
+        p.flip = 0;
+        p.strips = 0;
+        p.Lfull = p.L;
+        p.w_lo[0] = p.w_lo[1] = 0;
+        p.w_hi[0] = p.w_hi[1] = INT_MAX;
+        launch_stage(e, KIND_C64_MID, v, p, (unsigned)e->tiles[s][v], (unsigned)gf, k - 1);
+    }
+    *out_buf = b;
+    // exact edge strips: every stage on two short chunks per frame
+    const int tmax = tmax_of(v == 0 ? NTHR_BIG : NTHR_SMALL);
+    const long long cap = e->strip_cap;
+    for (int s = 0; s < k; ++s) {
+        StageParams p = e->sp0[v];
+        const int L = e->strip_len[s];
+        const int nout = (L + 1) / 2;
+        p.strips = 1;
+        p.L = L;
+        const int tiles = (L + tmax - 1) / tmax;
+        int T = (L + tiles - 1) / tiles;
+        T = (T + 15) / 16 * 16;
+        p.T = T;
+        if (s == 0) {
+            p.in = d_in;
+            p.in_stride = c.frame_len;
+            p.side_in_off = 0;
+            p.pos_off = e->strip_q[0];
+            p.Lfull = c.frame_len;
+            p.flip = c.flip;
+        } else {
+            p.in = e->sbuf[(s - 1) & 1].p;
+            p.in_stride = 2 * cap;
+            p.side_in_off = cap + (e->strip_q[s] - e->strip_q[s - 1] / 2);
+            p.pos_off = 0;
+            p.Lfull = L;
+            p.flip = 0;
+        }
+        if (s == k - 1) {
+            p.out = (float2 *)e->mid[b].p;
+            p.out_stride = e->len[k];
+            p.side_out_off = e->len[k] - nout;
+            p.w_lo[0] = 0;
+            p.w_hi[0] = e->fplan.K;
+            p.w_lo[1] = nout - e->fplan.K;
+            p.w_hi[1] = nout;
+        } else {
+            p.out = (float2 *)e->sbuf[s & 1].p;
+            p.out_stride = 2 * cap;
+            p.side_out_off = cap;
+            p.w_lo[0] = p.w_lo[1] = 0;
+            p.w_hi[0] = p.w_hi[1] = INT_MAX;
+        }
+        launch_stage(e, s == 0 ? raw_kind(c) : KIND_C64_MID, v, p, (unsigned)((L + T - 1) / T),
+                     (unsigned)(2 * gf), 15);
+    }
+}
+
 // one group of frames, all resident on the device, through the whole chain
 int run_group(zfb_engine *e, const void *d_in, int gf, float *d_rows) {
     const zfb_config &c = e->cfg;
@@ -454,6 +600,14 @@ int run_group(zfb_engine *e, const void *d_in, int gf, float *d_rows) {
     long long src_stride = c.frame_len;
     int kind = raw_kind(c);
 
+    if (e->fast_active) {
+        int ob = 0;
+        run_decimation_fast(e, d_in, gf, &ob);
+        e->final_buf = ob;
+        src = e->mid[ob].p;
+        src_stride = e->len[e->nstages];
+        kind = KIND_C64_MID;
+    } else
     for (int s = 0; s < e->nstages; ++s) {
         // 8192-sample region (3 CTAs/SM: one CTA's load overlaps another's sweeps)
         // unless zfb_set_option asked for the 16384-sample one (1 CTA/SM, half the halo)
@@ -471,6 +625,10 @@ int run_group(zfb_engine *e, const void *d_in, int gf, float *d_rows) {
         p.L = e->len[s];
         p.T = e->T[s][v];
         p.flip = (s == 0) ? c.flip : 0;
+        p.strips = 0;
+        p.Lfull = p.L;
+        p.w_lo[0] = p.w_lo[1] = 0;
+        p.w_hi[0] = p.w_hi[1] = INT_MAX;
         dim3 grid((unsigned)e->tiles[s][v], (unsigned)gf);
         const int pr = prof_begin(e, s);
         ZFB_LAUNCH(decim_lookup(kind, nt), grid, dim3((unsigned)nt), decim_smem(nt), st, p);
@@ -479,6 +637,7 @@ int run_group(zfb_engine *e, const void *d_in, int gf, float *d_rows) {
         src = out;
         src_stride = out_stride;
         kind = KIND_C64_MID;
+        e->final_buf = s & 1;
     }
 
     // Welch
@@ -579,6 +738,89 @@ int run_group(zfb_engine *e, const void *d_in, int gf, float *d_rows) {
     return ZFB_OK;
 }
 
+// ZFB_MODE_FAST planning: strip geometry, FIR chains (<= 3 stages per launch),
+// tile sizes; decides whether the frame is long enough for the FAST interior
+int plan_fast(zfb_engine *e) {
+    const zfb_config &c = e->cfg;
+    e->fast_active = false;
+    e->nchains = 0;
+    if (c.mode != ZFB_MODE_FAST) return ZFB_OK;
+    const int k = e->nstages;
+    if (k < 2) return ZFB_OK;                                  // nothing to replace
+    if (!e->fplan.set || e->fplan.ne != k - 1)
+        return fail(e, ZFB_ESTATE, "mode FAST needs zfb_set_fast_plan with %d stages (got %d)", k - 1,
+                    e->fplan.set ? e->fplan.ne : -1);
+    // strips: i_{k-1} = 2K + D, i_s = 2 i_{s+1} + D, right strip starts at an even position
+    const int K = e->fplan.K;
+    const int D = 384;
+    int need = 2 * K + D;
+    for (int s = k - 1; s >= 0; --s) {
+        int i = need;
+        if ((e->len[s] - i) & 1) i += 1;
+        e->strip_len[s] = i;
+        e->strip_q[s] = e->len[s] - i;
+        need = 2 * i + D;
+    }
+    if (e->len[0] < 4 * e->strip_len[0] || e->len[k] < 4 * K) return ZFB_OK;   // too short: EXACT
+    e->strip_cap = (e->strip_len[0] + 1) / 2 + 8;
+    for (int i = 0; i < 2; ++i) {
+        int rc = ensure(e, e->sbuf[i], (size_t)e->group * 2 * (size_t)e->strip_cap * sizeof(float2));
+        if (rc) return rc;
+    }
+    // chains
+    const int ne = k - 1;
+    const bool no_lo = (c.flags & ZFB_FLAG_NO_LO) != 0;
+    double r = no_lo ? 0.0 : c.f_demod / c.fs;
+    r -= floor(r);
+    if (r >= 1.0) r = 0.0;
+    int done = 0;
+    while (done < ne) {
+        if (e->nchains >= 4) return fail(e, ZFB_EINVAL, "fft_ratio too deep for mode FAST");
+        FirChainParams &p = e->chain[e->nchains];
+        memset(&p, 0, sizeof p);
+        const int ns = (ne - done > FIR_MAX_STAGES) ? FIR_MAX_STAGES : ne - done;
+        p.ns = ns;
+        for (int s = 0; s < ns; ++s) {
+            p.M[s] = e->fplan.M[done + s];
+            memcpy(p.h[s], e->fplan.h[done + s], sizeof p.h[s]);
+        }
+        const bool lastc = (done + ns == ne);
+        p.Mc = lastc ? e->fplan.Mc : -1;
+        if (lastc) memcpy(p.hc, e->fplan.hc, sizeof p.hc);
+        p.L = e->len[done];
+        p.flip = (done == 0) ? c.flip : 0;
+        if (done == 0) {
+            const double scaled = ldexp(r, 64);
+            p.phase_inc = (scaled >= 18446744073709551615.0) ? 0ull : (unsigned long long)scaled;
+            const int vec = (c.dtype == ZFB_DTYPE_U8) ? 8 : 2;
+            const double amp = no_lo ? 1.0 : sqrt(2.0);
+            for (int i = 0; i < 8; ++i) lo_entry(r, i, amp, p.lo_small[i]);
+            for (int it = 0; it < 32; ++it) lo_entry(r, (long long)it * FIR_NT * vec, 1.0, p.lo_big[it]);
+        }
+        // tile: as many outputs as keep level 0 near 4096 samples (about 50 KB of smem)
+        const int vec0 = (done == 0 && c.dtype == ZFB_DTYPE_U8) ? 8 : 2;
+        int best = 0;
+        for (int to = 16; to <= 4096; to += 16) {
+            p.TO = to;
+            FirTile t;
+            fir_tile_geometry(p, 0, t);
+            if (t.n[0] > 4352 || t.n[0] / vec0 > 32 * FIR_NT) break;
+            best = to;
+        }
+        if (best == 0) return fail(e, ZFB_EINVAL, "FIR plan too long for one tile");
+        p.TO = best;
+        FirTile t;
+        fir_tile_geometry(p, 0, t);
+        for (int l = 0; l <= ns; ++l) p.n[l] = t.n[l];
+        e->chain_smem[e->nchains] = fir_chain_smem(p);
+        done += ns;
+        e->chain_level_out[e->nchains] = done;
+        e->nchains += 1;
+    }
+    e->fast_active = true;
+    return ZFB_OK;
+}
+
 bool is_pinned(const void *p) {
     cudaPointerAttributes a;
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
@@ -668,6 +910,8 @@ void zfb_destroy(zfb_engine *e) {
     if (e->sr_host) cudaFreeHost(e->sr_host);
     release(e->sr_dev[0]);
     release(e->sr_dev[1]);
+    release(e->sbuf[0]);
+    release(e->sbuf[1]);
     if (e->sr_copied) cudaEventDestroy(e->sr_copied);
     for (int i = 0; i < 2; ++i) if (e->sr_free[i]) cudaEventDestroy(e->sr_free[i]);
     if (e->h_rows) cudaFreeHost(e->h_rows);
@@ -711,7 +955,8 @@ int zfb_configure(zfb_engine *e, const zfb_config *cfg) {
     if (cfg->fft_ratio < 1) return fail(e, ZFB_EINVAL, "fft_ratio %d: must be >= 1", cfg->fft_ratio);
     if (cfg->dtype != ZFB_DTYPE_C64 && cfg->dtype != ZFB_DTYPE_U8)
         return fail(e, ZFB_EINVAL, "unknown dtype %d", cfg->dtype);
-    if (cfg->mode != ZFB_MODE_EXACT) return fail(e, ZFB_EINVAL, "unknown mode %d", cfg->mode);
+    if (cfg->mode != ZFB_MODE_EXACT && cfg->mode != ZFB_MODE_FAST)
+        return fail(e, ZFB_EINVAL, "unknown mode %d", cfg->mode);
     if (cfg->row_width < 2 || cfg->row_width > N || (cfg->row_width & 1))
         return fail(e, ZFB_EINVAL, "row_width %d: must be even and in [2, fft_size]", cfg->row_width);
     if (!cfg->window) return fail(e, ZFB_EINVAL, "window is NULL");
@@ -805,6 +1050,8 @@ int zfb_configure(zfb_engine *e, const zfb_config *cfg) {
     e->group = choose_group(e);
     plan_tiles(e);
     e->nsplit_cap = 16;
+    rc = plan_fast(e);
+    if (rc) return rc;
 
     // workspaces
     if (g.nstages >= 1) {
@@ -833,6 +1080,44 @@ int zfb_configure(zfb_engine *e, const zfb_config *cfg) {
     }
     e->configured = true;
     return ZFB_OK;
+}
+
+int zfb_set_fast_plan(zfb_engine *e, const zfb_fast_plan *plan) {
+    if (!e) return ZFB_EINVAL;
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (!plan) return fail(e, ZFB_EINVAL, "fast plan is NULL");
+    if (plan->nstages < 1 || plan->nstages > ZFB_FAST_MAX_STAGES)
+        return fail(e, ZFB_EINVAL, "fast plan: nstages %d out of range", plan->nstages);
+    if (plan->strip < 64 || (plan->strip & 1)) return fail(e, ZFB_EINVAL, "fast plan: strip must be even and >= 64");
+    if (plan->comp_half < 0 || plan->comp_half > FIR_COMP_MAX_HALF || !plan->comp_taps)
+        return fail(e, ZFB_EINVAL, "fast plan: compensator half length %d out of range", plan->comp_half);
+    zfb_engine::FastPlan f;
+    f.ne = plan->nstages;
+    for (int s = 0; s < f.ne; ++s) {
+        if (plan->half[s] < 1 || plan->half[s] > FIR_MAX_HALF || !plan->taps[s])
+            return fail(e, ZFB_EINVAL, "fast plan: stage %d half length %d out of range", s, plan->half[s]);
+        f.M[s] = plan->half[s];
+        double dc = plan->taps[s][0];
+        for (int j = 0; j <= f.M[s]; ++j) {
+            if (!(plan->taps[s][j] == plan->taps[s][j])) return fail(e, ZFB_EINVAL, "fast plan: NaN tap");
+            f.h[s][j] = (float)plan->taps[s][j];
+            if (j) dc += 2.0 * plan->taps[s][j];
+        }
+        if (fabs(dc - 1.0) > 1e-6) return fail(e, ZFB_EINVAL, "fast plan: stage %d DC gain %.9f != 1", s, dc);
+    }
+    f.Mc = plan->comp_half;
+    for (int j = 0; j <= f.Mc; ++j) f.hc[j] = (float)plan->comp_taps[j];
+    f.K = plan->strip;
+    f.set = true;
+    e->fplan = f;
+    e->configured = false;
+    return ZFB_OK;
+}
+
+int zfb_fast_active(const zfb_engine *e) {
+    if (!e) return ZFB_EINVAL;
+    std::lock_guard<std::mutex> lk(e->mu);
+    return (e->configured && e->fast_active) ? 1 : 0;
 }
 
 int zfb_set_stream(zfb_engine *e, void *cuda_stream) {
@@ -988,7 +1273,7 @@ int zfb_debug_read_decimated(zfb_engine *e, float *h_out_iq, int max_samples) {
     int n = e->len[e->nstages];
     if (n > max_samples) n = max_samples;
     CK(e, cudaStreamSynchronize(e->stream));
-    CK(e, cudaMemcpy(h_out_iq, e->mid[(e->nstages - 1) & 1].p, (size_t)n * sizeof(float2), cudaMemcpyDeviceToHost));
+    CK(e, cudaMemcpy(h_out_iq, e->mid[e->final_buf].p, (size_t)n * sizeof(float2), cudaMemcpyDeviceToHost));
     e->counters[4] += (size_t)n * sizeof(float2);
     return n;
 }

@@ -1,0 +1,244 @@
+// ZFB_MODE_FAST interior: fused NCO mix + multistage polyphase FIR decimator.
+//
+// Replaces, for the INTERIOR of a chunk, all but the last scipy.signal.
+// decimate(x, 2) call of the reference's zoom loop (pypanadapter_spectrum.py:
+// 2096-2098, pypanadapter_thread.py:1532-1534).  Every stage of the reference
+// is a zero-phase LTI filter |H(f)|^2 (cheby1 order 8, applied forwards and
+// backwards) followed by [::2].  Only the band |f| <= B = 0.7 fs/R of the
+// early stages' output can reach the row: the last stage -- which stays the
+// exact IIR kernel -- rejects everything beyond B by >= 178 dB.  So an early
+// stage only has to (a) keep aliases out of |f| <= B and (b) have a smooth,
+// known gain there.  Short symmetric FIRs (7..27 taps, designed on the host
+// in fp64, pypanadapter_b200/fastdesign.py) do (a) to >= 140 dB, and one
+// 33-tap compensator at the last stage's input rate restores the product of
+// the reference's |H_s|^2 over |f| <= B to 1e-5.  The per-chunk edge semantics
+// of the reference (odd extension, steady-state initial conditions at every
+// stage) are NOT LTI; the first and last samples of the decimated chunk are
+// therefore recomputed by the exact kernels on two short strips and overwrite
+// what this kernel produced there (zfb_engine.cu).
+//
+// One CTA = one tile of TO outputs.  Levels: 0 = mixed input, s = after s
+// decimating stages; each level lives in shared memory in polyphase (even/odd)
+// layout so that the stride-2 reads of a decimator are unit-stride across
+// threads.  Values outside a level's [0, L_level) are zero (zero extension),
+// independent of the tiling.
+#pragma once
+#include "zfb_decim.cuh"
+
+namespace zfb {
+
+constexpr int FIR_MAX_STAGES = 3;     // decimating stages per launch
+constexpr int FIR_MAX_HALF = 20;      // half length M of a stage (2M+1 taps)
+constexpr int FIR_COMP_MAX_HALF = 24;
+constexpr int FIR_NT = 256;
+
+struct FirChainParams {
+    const void *in;            // [frames][in_stride] samples of the chain's input kind
+    long long   in_stride;
+    int         L;             // input length per frame
+    int         flip;
+    unsigned long long phase_inc;
+    float2      lo_small[8];   // amp * exp(-2 pi i f/fs v), v = 0..7
+    float2      lo_big[32];    // exp(-2 pi i f/fs * it*FIR_NT*VEC)
+    int         ns;            // decimating stages, 1..FIR_MAX_STAGES
+    int         M[FIR_MAX_STAGES];
+    float       h[FIR_MAX_STAGES][FIR_MAX_HALF + 1];   // h[s][j], j = 0..M[s] (centre first)
+    int         Mc;            // compensator half length, -1: none
+    float       hc[FIR_COMP_MAX_HALF + 1];
+    float2     *out;           // [frames][out_stride]
+    long long   out_stride;
+    int         TO;            // outputs per tile
+    int         n[FIR_MAX_STAGES + 1];   // samples held per level (level 0 rounded to the load vector)
+};
+
+// geometry of one tile, shared by host (smem sizing) and device
+struct FirTile {
+    int lo[FIR_MAX_STAGES + 1];   // first position held per level (level 0 aligned down to 8)
+    int n[FIR_MAX_STAGES + 1];    // count per level
+    int c[FIR_MAX_STAGES + 1];    // c[l]: index in level l-1 of the centre tap of level-l output 0 (l >= 1)
+};
+
+__host__ __device__ inline void fir_tile_geometry(const FirChainParams &p, int o0, FirTile &t) {
+    const int mc = p.Mc < 0 ? 0 : p.Mc;
+    t.lo[p.ns] = o0 - mc;
+    t.n[p.ns] = p.TO + 2 * mc;
+    for (int l = p.ns; l >= 1; --l) {
+        const int M = p.M[l - 1];
+        int lo = 2 * t.lo[l] - M;
+        int n = 2 * (t.n[l] - 1) + 2 * M + 1;
+        if (l == 1) {                      // level 0: align to the 8-sample load vector
+            const int lo_al = lo - (((lo % 8) + 8) % 8);
+            n += lo - lo_al;
+            n = (n + 7) / 8 * 8;
+            t.c[1] = M + (lo - lo_al);
+            lo = lo_al;
+        } else {
+            t.c[l] = M;
+        }
+        t.lo[l - 1] = lo;
+        t.n[l - 1] = n;
+    }
+}
+
+// even/odd arrays of a level with n samples: E at base, O at base + eo_half(n)
+__host__ __device__ constexpr int eo_half(int n) { return ((n + 1) / 2 + 3) | 1; }
+
+template <int KIND>
+__global__ void __launch_bounds__(FIR_NT) fir_chain_kernel(const FirChainParams p) {
+    constexpr int VEC = (KIND == KIND_U8_RAW) ? 8 : 2;
+    ZFB_DYN_SMEM(smem_raw);
+    float2 *sm = reinterpret_cast<float2 *>(smem_raw);
+    const int tid = threadIdx.x;
+    const int frame = blockIdx.y;
+    const int o0 = blockIdx.x * p.TO;
+
+    FirTile t;
+    fir_tile_geometry(p, o0, t);
+    int Llev[FIR_MAX_STAGES + 1];
+    Llev[0] = p.L;
+    for (int l = 1; l <= p.ns; ++l) Llev[l] = (Llev[l - 1] + 1) >> 1;
+
+    // buffers: level l (polyphase) alternates between bufA and bufB
+    const int sizeA = 2 * eo_half(t.n[0]);
+    float2 *bufA = sm;
+    float2 *bufB = sm + sizeA;
+
+    // ---------------- level 0: load, convert, flip, LO mix ----------------
+    {
+        const size_t esz = (KIND == KIND_U8_RAW) ? 2 : 8;
+        const char *frame_in = (const char *)p.in + (size_t)frame * (size_t)p.in_stride * esz;
+        const int L = p.L;
+        const bool fl = (KIND != KIND_C64_MID) && p.flip;
+        const int half0 = eo_half(t.n[0]);
+        float2 *E = bufA, *O = bufA + half0;
+        const int nvec = t.n[0] / VEC;
+        float2 b0 = make_float2(1.f, 0.f);
+        if (KIND != KIND_C64_MID)
+            b0 = lo_phasor((long long)t.lo[0] + (long long)tid * VEC, p.phase_inc);
+        for (int it = 0; it * FIR_NT < nvec; ++it) {
+            const int v = it * FIR_NT + tid;
+            if (v >= nvec) break;
+            const int r0 = v * VEC;                 // index within the level (even)
+            const int pos = t.lo[0] + r0;
+            float2 s[VEC];
+            const long long i0 = fl ? (long long)L - VEC - pos : (long long)pos;
+            const char *a = frame_in + (size_t)i0 * esz;
+            if (pos >= 0 && pos + VEC <= L && ((((uintptr_t)a) & 15) == 0)) {
+                const uint4 raw = __ldg((const uint4 *)a);
+                if (KIND == KIND_U8_RAW) {
+                    const unsigned int wds[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) {
+                        const int ee = fl ? (VEC - 1 - e) : e;
+                        s[e] = u8pair_to_iq(wds[ee >> 1], ee & 1);
+                    }
+                } else {
+                    const float2 lo2 = make_float2(__uint_as_float(raw.x), __uint_as_float(raw.y));
+                    const float2 hi2 = make_float2(__uint_as_float(raw.z), __uint_as_float(raw.w));
+                    s[0] = fl ? hi2 : lo2;
+                    s[VEC - 1] = fl ? lo2 : hi2;
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) {
+                    const int pe = pos + e;
+                    s[e] = make_float2(0.f, 0.f);
+                    if (pe >= 0 && pe < L) {
+                        const long long ie = fl ? (long long)L - 1 - pe : (long long)pe;
+                        if (KIND == KIND_U8_RAW) {
+                            const unsigned char *src = (const unsigned char *)frame_in;
+                            s[e] = make_float2(u8_to_f(src[2 * ie]), u8_to_f(src[2 * ie + 1]));
+                        } else {
+                            s[e] = __ldg((const float2 *)frame_in + ie);
+                        }
+                    }
+                }
+            }
+            if (KIND != KIND_C64_MID) {
+                const float2 bi = cmul(b0, p.lo_big[it]);
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) s[e] = cmul(s[e], cmul(bi, p.lo_small[e]));
+            }
+#pragma unroll
+            for (int e = 0; e < VEC; e += 2) {
+                E[(r0 + e) >> 1] = s[e];
+                O[(r0 + e) >> 1] = s[e + 1];
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---------------- decimating stages ----------------
+    float2 *src = bufA, *dst = bufB;
+    for (int l = 1; l <= p.ns; ++l) {
+        const int M = p.M[l - 1];
+        const float *h = p.h[l - 1];
+        const int half_in = eo_half(t.n[l - 1]);
+        const float2 *E = src, *O = src + half_in;
+        const int c = t.c[l];
+        const bool last = (l == p.ns);
+        const bool to_global = last && p.Mc < 0;
+        // output layout: polyphase if another decimator follows, linear before the compensator
+        const int half_out = eo_half(t.n[l]);
+        float2 *frame_out = p.out + (size_t)frame * (size_t)p.out_stride;
+        for (int i = tid; i < t.n[l]; i += FIR_NT) {
+            const int pos = t.lo[l] + i;
+            float2 acc = make_float2(0.f, 0.f);
+            if (pos >= 0 && pos < Llev[l]) {
+                const int ctr = 2 * i + c;                         // centre index in level l-1
+                {
+                    const float2 x0 = (ctr & 1) ? O[ctr >> 1] : E[ctr >> 1];
+                    acc = pk_mul(h[0], x0);
+                }
+#pragma unroll 4
+                for (int j = 1; j <= M; ++j) {
+                    const int a = ctr - j, b = ctr + j;
+                    const float2 xa = (a & 1) ? O[a >> 1] : E[a >> 1];
+                    const float2 xb = (b & 1) ? O[b >> 1] : E[b >> 1];
+                    acc = pk_fma(h[j], pk_add(xa, xb), acc);
+                }
+            }
+            if (to_global) {
+                if (pos >= o0 && pos < o0 + p.TO && pos < Llev[l]) frame_out[pos] = acc;
+            } else if (last) {
+                dst[i] = acc;                                      // linear, for the compensator
+            } else {
+                ((i & 1) ? dst + half_out : dst)[i >> 1] = acc;
+            }
+        }
+        __syncthreads();
+        float2 *tmp = src; src = dst; dst = tmp;
+    }
+
+    // ---------------- compensator at the output rate ----------------
+    if (p.Mc >= 0) {
+        const int Mc = p.Mc;
+        const int Lout = Llev[p.ns];
+        float2 *frame_out = p.out + (size_t)frame * (size_t)p.out_stride;
+        for (int i = tid; i < p.TO; i += FIR_NT) {
+            const int pos = o0 + i;
+            if (pos >= Lout) break;
+            const float2 *x = src + i + Mc;                        // level ns index of pos
+            float2 acc = pk_mul(p.hc[0], x[0]);
+#pragma unroll 4
+            for (int j = 1; j <= Mc; ++j) acc = pk_fma(p.hc[j], pk_add(x[-j], x[j]), acc);
+            frame_out[pos] = acc;
+        }
+    }
+}
+
+// dynamic shared memory of a launch: level 0 in bufA, the largest later level in bufB,
+// and (ping-pong) level 2 back in bufA, which always fits
+inline size_t fir_chain_smem(const FirChainParams &p) {
+    FirTile t;
+    fir_tile_geometry(p, 0, t);
+    const size_t a = 2 * (size_t)eo_half(t.n[0]);
+    size_t b = 0;
+    for (int l = 1; l <= p.ns; ++l) {
+        const size_t need = (l == p.ns && p.Mc >= 0) ? (size_t)t.n[l] + 8 : 2 * (size_t)eo_half(t.n[l]);
+        if (need > b) b = need;
+    }
+    return (a + b) * sizeof(float2);
+}
+
+}  // namespace zfb

@@ -131,13 +131,18 @@ class ZoomPSD:
     # -- configuration ---------------------------------------------------
     def configure(self, fs, fft_size, fft_ratio, frame_len, window="hamming", *,
                   dtype="c64", flip=False, f_demod=1.0, crop="thread",
-                  ema_alpha=None, no_lo=False, linear=False):
+                  ema_alpha=None, no_lo=False, linear=False, mode="exact"):
         """Plan for a frame shape (cheap if nothing changed).  Mirrors the
-        AppState the reference reads per frame (S:1492-1497)."""
+        AppState the reference reads per frame (S:1492-1497).
+
+        ``mode``: ``"exact"`` -- every decimate call by the zero-phase IIR
+        kernels; ``"fast"`` -- polyphase-FIR interior + exact last stage +
+        exact chunk edges (same parity bar; falls back to exact for
+        fft_ratio < 4 or short chunks, see ``fast_active``)."""
         fft_ratio_i = int(fft_ratio)
         wkey = window if isinstance(window, (str, tuple)) else ("array", np.asarray(window).tobytes())
         key = (float(fs), int(fft_size), float(fft_ratio), int(frame_len), wkey, dtype, bool(flip),
-               float(f_demod), crop, ema_alpha, bool(no_lo), bool(linear))
+               float(f_demod), crop, ema_alpha, bool(no_lo), bool(linear), mode)
         if key == self._key:
             return self
         geo = plan_geometry(frame_len, fft_size, fft_ratio_i, self._lib)
@@ -152,7 +157,12 @@ class ZoomPSD:
         cfg.nperseg = geo["nperseg"]
         cfg.dtype = {"c64": _lib.ZFB_DTYPE_C64, "u8": _lib.ZFB_DTYPE_U8}[dtype]
         cfg.flip = 1 if flip else 0
+        if mode not in ("exact", "fast"):
+            raise ValueError("mode must be 'exact' or 'fast'")
         cfg.mode = _lib.ZFB_MODE_EXACT
+        if mode == "fast" and geo["nstages"] >= 2:
+            self._set_fast_plan(1 << geo["nstages"])
+            cfg.mode = _lib.ZFB_MODE_FAST
         cfg.flags = (_lib.ZFB_FLAG_NO_LO if no_lo else 0) | (_lib.ZFB_FLAG_LINEAR if linear else 0)
         cfg.f_demod = float(f_demod)
         cfg.ema_alpha = -1.0 if ema_alpha is None else float(ema_alpha)
@@ -164,6 +174,26 @@ class ZoomPSD:
         self.dtype = dtype
         self.geometry = geo
         return self
+
+    def _set_fast_plan(self, ratio: int):
+        from . import fastdesign
+        plan = fastdesign.design(ratio, decim_sos(self._lib))
+        fp = _lib.ZfbFastPlan()
+        fp.nstages = len(plan["stages"])
+        keep = []
+        for i, a in enumerate(plan["stages"]):
+            fp.half[i] = len(a) - 1
+            fp.taps[i] = a.ctypes.data_as(C.POINTER(C.c_double))
+            keep.append(a)
+        fp.comp_half = len(plan["comp"]) - 1
+        fp.comp_taps = plan["comp"].ctypes.data_as(C.POINTER(C.c_double))
+        fp.strip = plan["strip"]
+        self._check(self._lib.zfb_set_fast_plan(self._h, C.byref(fp)), "zfb_set_fast_plan")
+        self.fast_plan = plan
+
+    @property
+    def fast_active(self) -> bool:
+        return bool(self._lib.zfb_fast_active(self._h))
 
     def set_group(self, frames_per_group: int):
         self._check(self._lib.zfb_set_group(self._h, int(frames_per_group)), "zfb_set_group")

@@ -156,3 +156,88 @@ def tile_geometries(engine, names=("cfg1_T", "cfg2_T_f0", "ragged_T", "zoom_R64"
         engine.set_option("decim_threads", 64)
     with pytest.raises(ZoomFFTError):
         engine.set_option("no_such_option", 1)
+
+
+# ---- ZFB_MODE_FAST: polyphase-FIR interior + exact last stage + exact edge strips ----
+FAST_CASES = [c["name"] for c in gc.CASES if c["R"] >= 4]
+
+
+def fast_golden_case(engine, name):
+    """Same golden rows, same tolerance, through mode='fast'."""
+    err = parity.check_case(engine, name, mode="fast")
+    return err, engine.fast_active
+
+
+def fast_activation(engine):
+    """FAST engages for long chunks with R >= 4 and silently stays EXACT otherwise."""
+    engine.configure(2.4e6, 2048, 8, 239616, "hamming", mode="fast")
+    assert engine.fast_active
+    engine.configure(2.4e6, 2048, 2, 65536, "hamming", mode="fast")        # one stage: nothing to replace
+    assert not engine.fast_active
+    engine.configure(2.4e6, 1024, 8, 8192, "hamming", mode="fast")         # strips would cover the chunk
+    assert not engine.fast_active
+    engine.configure(2.4e6, 2048, 8, 239616, "hamming", mode="exact")
+    assert not engine.fast_active
+
+
+def fast_matches_exact_chunk(engine):
+    """The decimated chunk (zoomfft output, S:2100) of FAST agrees with EXACT
+    to fp32 resolution over the whole chunk, edges included; odd lengths and
+    uint8 + flip covered."""
+    rng = np.random.default_rng(99)
+    for n, R, dtype, flip in ((100003, 8, "c64", False), (319488, 16, "u8", True), (77777, 4, "c64", True),
+                              (262144 + 10, 32, "c64", False)):
+        k = np.arange(n)
+        x = 0.4 * np.exp(2j * np.pi * 0.0031 / R * k) + 0.2 * np.exp(-2j * np.pi * 0.37 * k)
+        x += 0.01 * (rng.standard_normal(n) + 1j * rng.standard_normal(n))
+        wire = synth.quantise_u8(x) if dtype == "u8" else x.astype(np.complex64)
+        out = {}
+        for mode in ("exact", "fast"):
+            engine.configure(1e6, 256, R, n, "hann", dtype=dtype, flip=flip, crop=None, mode=mode)
+            engine.process(wire)
+            out[mode] = engine.read_decimated().astype(np.complex128)
+            assert engine.fast_active == (mode == "fast")
+        err = np.abs(out["fast"] - out["exact"]).max() / np.abs(out["exact"]).max()
+        assert err < 1e-5, (n, R, dtype, flip, err)
+
+
+def fast_batch_and_ema(engine):
+    """FAST over a batch == FAST frame by frame (bit-exact), EMA state carried."""
+    w = synth.CFG2
+    frames = synth.make_frames(w, 3)
+    engine.configure(w.fs, w.fft_size, w.fft_ratio, w.frame_len, w.window, dtype="u8", flip=True,
+                     crop="thread", mode="fast")
+    assert engine.fast_active
+    batch = engine.process(frames)
+    single = np.stack([engine.process(frames[i])[0] for i in range(3)])
+    assert np.array_equal(batch, single)
+    floor = parity.floor_db20(w.fs, w.window, w.fft_size, True)
+    for i in range(3):
+        parity.assert_row_parity(batch[i], parity.golden_rows()["cfg2_T_f%d" % i], floor, "fast cfg2 %d" % i)
+    engine.configure(w.fs, w.fft_size, w.fft_ratio, w.frame_len, w.window, dtype="u8", flip=True,
+                     crop="thread", ema_alpha=0.3, mode="fast")
+    engine.reset_ema()
+    got = engine.process(frames)
+    pw = np.stack([zo.zoom_psd_power(f, w.fs, w.fft_size, w.fft_ratio, w.window, flip=True) for f in frames])
+    want = zo.ema_rows_db20(pw, 0.3)
+    for i in range(3):
+        parity.assert_row_parity(got[i], want[i], floor, "fast ema %d" % i)
+
+
+def fast_strong_out_of_band(engine):
+    """Full-scale interferers outside the returned band (adjacent stations):
+    alias rejection and transition-band fidelity of the FIR interior."""
+    fs, N, R = 2.4e6, 2048, 16
+    n = N * R * 6
+    k = np.arange(n)
+    rng = np.random.default_rng(7)
+    x = 1e-3 * (rng.standard_normal(n) + 1j * rng.standard_normal(n))
+    for f, a in ((0.23 * fs, 0.25), (-0.49 * fs, 0.25), (fs / R * 0.31, 0.2), (-fs / R * 0.22, 0.2),
+                 (1700.0, 0.02)):
+        x = x + a * np.exp(2j * np.pi * f / fs * k)
+    x = x.astype(np.complex64)
+    want = zo.zoom_psd(x, fs, N, R, "hamming", crop=None)
+    engine.configure(fs, N, R, n, "hamming", crop=None, mode="fast")
+    assert engine.fast_active
+    row = engine.process(x)[0].astype(np.float64)
+    parity.assert_row_parity(row, want, parity.floor_db20(fs, "hamming", N, True), "fast interferers")

@@ -58,20 +58,20 @@ def case_config(case):
     return crop, dtype
 
 
-def run_case(engine, case, x=None):
+def run_case(engine, case, x=None, mode="exact"):
     """One golden case through an engine's HOST path -> float64 row."""
     if x is None:
         x = gc.make_input(case)
     crop, dtype = case_config(case)
     n = len(x) // 2 if dtype == "u8" else len(x)
     engine.configure(case["fs"], case["N"], case["R"], n, case["window"], dtype=dtype,
-                     flip=bool(case.get("flip")), crop=crop)
+                     flip=bool(case.get("flip")), crop=crop, mode=mode)
     return engine.process(x)[0].astype(np.float64)
 
 
-def check_case(engine, name):
+def check_case(engine, name, mode="exact"):
     case = gc.case_by_name(name)
-    row = run_case(engine, case)
+    row = run_case(engine, case, mode=mode)
     floor = floor_db20(case["fs"], case["window"], engine.geometry["nperseg"], case["R"] > 1)
     return assert_row_parity(row, golden_rows()[name], floor, name)
 

@@ -77,3 +77,25 @@ def test_scipy_shaped_calls(emu_engine):
 
 def test_dropin_on_reference_modules(emu_engine):
     bs.dropin_on_reference_modules(emu_engine)
+
+
+# ---- ZFB_MODE_FAST ------------------------------------------------------------------
+@pytest.mark.parametrize("name", es.FAST_CASES)
+def test_fast_golden_case(emu_engine, name):
+    es.fast_golden_case(emu_engine, name)
+
+
+def test_fast_activation(emu_engine):
+    es.fast_activation(emu_engine)
+
+
+def test_fast_matches_exact_chunk(emu_engine):
+    es.fast_matches_exact_chunk(emu_engine)
+
+
+def test_fast_batch_and_ema(emu_engine):
+    es.fast_batch_and_ema(emu_engine)
+
+
+def test_fast_strong_out_of_band(emu_engine):
+    es.fast_strong_out_of_band(emu_engine)

@@ -153,3 +153,25 @@ def test_scipy_shaped_calls(gpu_engine):
 
 def test_dropin_on_reference_modules(gpu_engine):
     bs.dropin_on_reference_modules(gpu_engine)       # skipped where /root/reference is absent
+
+
+# ---- ZFB_MODE_FAST ------------------------------------------------------------------
+@pytest.mark.parametrize("name", es.FAST_CASES)
+def test_fast_golden_case(gpu_engine, name):
+    es.fast_golden_case(gpu_engine, name)
+
+
+def test_fast_activation(gpu_engine):
+    es.fast_activation(gpu_engine)
+
+
+def test_fast_matches_exact_chunk(gpu_engine):
+    es.fast_matches_exact_chunk(gpu_engine)
+
+
+def test_fast_batch_and_ema(gpu_engine):
+    es.fast_batch_and_ema(gpu_engine)
+
+
+def test_fast_strong_out_of_band(gpu_engine):
+    es.fast_strong_out_of_band(gpu_engine)
