@@ -432,7 +432,7 @@ __global__ void __launch_bounds__(NT, (NT == NTHR_BIG ? 1 : 3)) decim2_exact_ker
         for (int j = 0; j < 8; ++j)
             hist[j] = (tid > 0) ? buf[sidx(tid * BLK - 8 + j)] : make_float2(0.f, 0.f);
         __syncthreads();
-        fir_causal(blk, hist);
+        if (active) fir_causal(blk, hist);        // runs without valid samples hold zeros
     }
     __syncthreads();
     // ---------------- backward ----------------
@@ -455,7 +455,7 @@ __global__ void __launch_bounds__(NT, (NT == NTHR_BIG ? 1 : 3)) decim2_exact_ker
         for (int j = 0; j < 8; ++j)
             ahead[j] = (tid < NT - 1) ? buf[sidx((tid + 1) * BLK + j)] : make_float2(0.f, 0.f);
         __syncthreads();
-        fir_anticausal_even(blk, ahead);
+        if (active) fir_anticausal_even(blk, ahead);
     }
     __syncthreads();
 

@@ -29,7 +29,7 @@ namespace zfb {
 
 constexpr int FIR_MAX_STAGES = 3;     // decimating stages per launch
 constexpr int FIR_MAX_HALF = 20;      // half length M of a stage (2M+1 taps)
-constexpr int FIR_COMP_MAX_HALF = 24;
+constexpr int FIR_COMP_MAX_HALF = 24;   // (dispatch tables below enumerate 1..20 / 1..24)
 constexpr int FIR_NT = 256;
 
 struct FirChainParams {
@@ -82,6 +82,88 @@ __host__ __device__ inline void fir_tile_geometry(const FirChainParams &p, int o
 
 // even/odd arrays of a level with n samples: E at base, O at base + eo_half(n)
 __host__ __device__ constexpr int eo_half(int n) { return ((n + 1) / 2 + 3) | 1; }
+
+struct StageIO {
+    const float2 *E, *O;     // polyphase input level
+    int c;                   // input index of the centre tap of output 0
+    int n, i_lo, i_hi;       // outputs held / first and one-past-last non-zero output
+    int mode;                // 0: polyphase smem, 1: linear smem, 2: global
+    float2 *dstE, *dstO;
+};
+
+__device__ __forceinline__ void stage_store(const StageIO &io, int i, float2 v) {
+    if (io.mode == 0) ((i & 1) ? io.dstO : io.dstE)[i >> 1] = v;
+    else io.dstE[i] = v;
+}
+
+// One decimate-by-2 FIR stage with compile-time half length M: the taps sit in
+// registers and every tap is an LDS with an immediate offset from two base
+// pointers (A: the polyphase array holding the centre tap, B: the other one).
+// Output i: centre = 2i + c; even tap offsets stay in A, odd ones are in B.
+template <int M>
+__device__ __forceinline__ void fir_stage(const float *hp, const StageIO &io, int tid) {
+    float h[M + 1];
+#pragma unroll
+    for (int j = 0; j <= M; ++j) h[j] = hp[j];
+    const bool c_odd = io.c & 1;
+    const float2 *A = (c_odd ? io.O : io.E) + (io.c >> 1);
+    const float2 *B = (c_odd ? io.E + 1 : io.O) + (io.c >> 1);
+    for (int i = tid; i < io.n; i += FIR_NT) {
+        float2 acc = make_float2(0.f, 0.f);
+        if (i >= io.i_lo && i < io.i_hi) {
+            const float2 *a = A + i, *b = B + i;
+            acc = pk_mul(h[0], a[0]);
+#pragma unroll
+            for (int j = 1; j <= M; ++j) {
+                float2 xs;
+                if (j & 1) xs = pk_add(b[(j - 1) / 2], b[-(j + 1) / 2]);     // offsets +-j, j odd
+                else xs = pk_add(a[j / 2], a[-j / 2]);
+                acc = pk_fma(h[j], xs, acc);
+            }
+        }
+        if (io.mode != 2 || (i >= io.i_lo && i < io.i_hi)) stage_store(io, i, acc);
+    }
+}
+
+__device__ __forceinline__ void fir_stage_dispatch(int M, const float *hp, const StageIO &io, int tid) {
+    // exact half length only: a padded instantiation would read past the halo
+#define ZFB_CASE(m) case m: fir_stage<m>(hp, io, tid); break;
+    switch (M) {
+        ZFB_CASE(1) ZFB_CASE(2) ZFB_CASE(3) ZFB_CASE(4) ZFB_CASE(5) ZFB_CASE(6) ZFB_CASE(7) ZFB_CASE(8)
+        ZFB_CASE(9) ZFB_CASE(10) ZFB_CASE(11) ZFB_CASE(12) ZFB_CASE(13) ZFB_CASE(14) ZFB_CASE(15)
+        ZFB_CASE(16) ZFB_CASE(17) ZFB_CASE(18) ZFB_CASE(19) ZFB_CASE(20)
+        default: break;
+    }
+#undef ZFB_CASE
+}
+
+// symmetric compensator (no decimation): out[i] = sum_j hc[|j|] x[i + j], x linear in smem
+template <int MC>
+__device__ __forceinline__ void comp_stage(const float *hp, const float2 *x, float2 *out, int n_out, int tid) {
+    float h[MC + 1];
+#pragma unroll
+    for (int j = 0; j <= MC; ++j) h[j] = hp[j];
+    for (int i = tid; i < n_out; i += FIR_NT) {
+        const float2 *a = x + i;
+        float2 acc = pk_mul(h[0], a[0]);
+#pragma unroll
+        for (int j = 1; j <= MC; ++j) acc = pk_fma(h[j], pk_add(a[j], a[-j]), acc);
+        out[i] = acc;
+    }
+}
+
+__device__ __forceinline__ void comp_dispatch(int Mc, const float *hp, const float2 *x, float2 *out, int n_out,
+                                              int tid) {
+#define ZFB_CASE(m) case m: comp_stage<m>(hp, x, out, n_out, tid); break;
+    switch (Mc) {
+        ZFB_CASE(1) ZFB_CASE(2) ZFB_CASE(3) ZFB_CASE(4) ZFB_CASE(5) ZFB_CASE(6) ZFB_CASE(7) ZFB_CASE(8)
+        ZFB_CASE(9) ZFB_CASE(10) ZFB_CASE(11) ZFB_CASE(12) ZFB_CASE(13) ZFB_CASE(14) ZFB_CASE(15)
+        ZFB_CASE(16) ZFB_CASE(17) ZFB_CASE(18) ZFB_CASE(19) ZFB_CASE(20) ZFB_CASE(21) ZFB_CASE(22)
+        ZFB_CASE(23) ZFB_CASE(24)
+        default: break;
+    }
+#undef ZFB_CASE
+}
 
 template <int KIND>
 __global__ void __launch_bounds__(FIR_NT) fir_chain_kernel(const FirChainParams p) {
@@ -170,60 +252,40 @@ __global__ void __launch_bounds__(FIR_NT) fir_chain_kernel(const FirChainParams 
 
     // ---------------- decimating stages ----------------
     float2 *src = bufA, *dst = bufB;
+    float2 *frame_out = p.out + (size_t)frame * (size_t)p.out_stride;
     for (int l = 1; l <= p.ns; ++l) {
-        const int M = p.M[l - 1];
-        const float *h = p.h[l - 1];
-        const int half_in = eo_half(t.n[l - 1]);
-        const float2 *E = src, *O = src + half_in;
-        const int c = t.c[l];
         const bool last = (l == p.ns);
-        const bool to_global = last && p.Mc < 0;
-        // output layout: polyphase if another decimator follows, linear before the compensator
-        const int half_out = eo_half(t.n[l]);
-        float2 *frame_out = p.out + (size_t)frame * (size_t)p.out_stride;
-        for (int i = tid; i < t.n[l]; i += FIR_NT) {
-            const int pos = t.lo[l] + i;
-            float2 acc = make_float2(0.f, 0.f);
-            if (pos >= 0 && pos < Llev[l]) {
-                const int ctr = 2 * i + c;                         // centre index in level l-1
-                {
-                    const float2 x0 = (ctr & 1) ? O[ctr >> 1] : E[ctr >> 1];
-                    acc = pk_mul(h[0], x0);
-                }
-#pragma unroll 4
-                for (int j = 1; j <= M; ++j) {
-                    const int a = ctr - j, b = ctr + j;
-                    const float2 xa = (a & 1) ? O[a >> 1] : E[a >> 1];
-                    const float2 xb = (b & 1) ? O[b >> 1] : E[b >> 1];
-                    acc = pk_fma(h[j], pk_add(xa, xb), acc);
-                }
-            }
-            if (to_global) {
-                if (pos >= o0 && pos < o0 + p.TO && pos < Llev[l]) frame_out[pos] = acc;
-            } else if (last) {
-                dst[i] = acc;                                      // linear, for the compensator
-            } else {
-                ((i & 1) ? dst + half_out : dst)[i >> 1] = acc;
-            }
+        StageIO io;
+        io.E = src;
+        io.O = src + eo_half(t.n[l - 1]);
+        io.c = t.c[l];
+        io.n = t.n[l];
+        // outputs whose position lies outside the level are zero (zero extension)
+        io.i_lo = max(0, -t.lo[l]);
+        io.i_hi = min(t.n[l], Llev[l] - t.lo[l]);
+        if (last && p.Mc < 0) {
+            io.mode = 2;                                  // straight to global
+            io.dstE = frame_out + t.lo[l];
+            io.dstO = nullptr;
+        } else if (last) {
+            io.mode = 1;                                  // linear, for the compensator
+            io.dstE = dst;
+            io.dstO = nullptr;
+        } else {
+            io.mode = 0;                                  // polyphase, for the next decimator
+            io.dstE = dst;
+            io.dstO = dst + eo_half(t.n[l]);
         }
+        fir_stage_dispatch(p.M[l - 1], p.h[l - 1], io, tid);
         __syncthreads();
         float2 *tmp = src; src = dst; dst = tmp;
     }
 
     // ---------------- compensator at the output rate ----------------
     if (p.Mc >= 0) {
-        const int Mc = p.Mc;
         const int Lout = Llev[p.ns];
-        float2 *frame_out = p.out + (size_t)frame * (size_t)p.out_stride;
-        for (int i = tid; i < p.TO; i += FIR_NT) {
-            const int pos = o0 + i;
-            if (pos >= Lout) break;
-            const float2 *x = src + i + Mc;                        // level ns index of pos
-            float2 acc = pk_mul(p.hc[0], x[0]);
-#pragma unroll 4
-            for (int j = 1; j <= Mc; ++j) acc = pk_fma(p.hc[j], pk_add(x[-j], x[j]), acc);
-            frame_out[pos] = acc;
-        }
+        const int n_out = min(p.TO, Lout - o0);
+        comp_dispatch(p.Mc, p.hc, src + p.Mc, frame_out + o0, n_out, tid);
     }
 }
 
