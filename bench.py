@@ -434,7 +434,7 @@ def main():
     ap.add_argument("--frames", type=int, default=256, help="frames per step per GPU")
     ap.add_argument("--group", type=int, default=0, help="frames per launch group (0 = auto)")
     ap.add_argument("--decim-threads", type=int, default=0, help="tuning: 0 auto, 128 or 256")
-    ap.add_argument("--mode", default="exact", choices=["exact", "fast"],
+    ap.add_argument("--mode", default="fast", choices=["exact", "fast"],
                     help="decimator: exact zero-phase IIR everywhere, or polyphase-FIR interior + exact edges")
     ap.add_argument("--lib", default=None, help="tuning: path of an alternative sm_100a build")
     ap.add_argument("--e2e-steps", type=int, default=20)

@@ -350,31 +350,13 @@ __device__ __forceinline__ void load_region(float2 *buf, const StageParams &p,
     }
 }
 
-template <int KIND, int NT>
-__global__ void __launch_bounds__(NT, (NT == NTHR_BIG ? 1 : 3)) decim2_exact_kernel(const StageParams p) {
+// One exact zero-phase stage on a region that already sits in shared memory
+// (stage input of length L at region coordinate q = pos - rs, g^2-scaled).
+// On return (after a barrier) the filtered samples are at the EVEN positions:
+// output m of the stage = buf[sidx(2m - rs)].
+template <int NT>
+__device__ __forceinline__ void exact_stage_inplace(float2 *buf, float2 *zbuf, int L, int rs, int tid) {
     constexpr int REGION = region_of(NT);
-    ZFB_DYN_SMEM(smem_raw);
-    float2 *buf  = reinterpret_cast<float2 *>(smem_raw);          // NT*BLK_PAD
-    float2 *zbuf = buf + NT * BLK_PAD;                            // NSTATE*NT
-
-    const int tid   = threadIdx.x;
-    const int tile  = blockIdx.x;
-    int frame = blockIdx.y, side = 0;
-    if (p.strips) {
-        side = frame & 1;
-        frame >>= 1;
-    }
-    const int L     = p.L;
-    const int p0    = tile * p.T;                 // first output position (even)
-    const int rs    = p0 - WARM;                  // region start, ext coordinates
-
-    const size_t esz = (KIND == KIND_U8_RAW) ? 2 : 8;
-    const char *frame_in = (const char *)p.in +
-                           ((size_t)frame * (size_t)p.in_stride + (size_t)side * (size_t)p.side_in_off) * esz;
-
-    load_region<KIND, NT>(buf, p, frame_in, rs, tid, (KIND != KIND_C64_MID && side) ? p.pos_off : 0);
-    __syncthreads();
-
     // odd extension (scipy odd_ext, 27 samples each side) where it falls in the region
     if (tid < PADLEN) {
         const int pos = -1 - tid;                 // 2*x[0] - x[-pos]
@@ -432,7 +414,7 @@ __global__ void __launch_bounds__(NT, (NT == NTHR_BIG ? 1 : 3)) decim2_exact_ker
         for (int j = 0; j < 8; ++j)
             hist[j] = (tid > 0) ? buf[sidx(tid * BLK - 8 + j)] : make_float2(0.f, 0.f);
         __syncthreads();
-        if (active) fir_causal(blk, hist);        // runs without valid samples hold zeros
+        if (active) fir_causal(blk, hist);        // runs without valid samples are never read
     }
     __syncthreads();
     // ---------------- backward ----------------
@@ -458,6 +440,33 @@ __global__ void __launch_bounds__(NT, (NT == NTHR_BIG ? 1 : 3)) decim2_exact_ker
         if (active) fir_anticausal_even(blk, ahead);
     }
     __syncthreads();
+}
+
+template <int KIND, int NT>
+__global__ void __launch_bounds__(NT, (NT == NTHR_BIG ? 1 : 3)) decim2_exact_kernel(const StageParams p) {
+    ZFB_DYN_SMEM(smem_raw);
+    float2 *buf  = reinterpret_cast<float2 *>(smem_raw);          // NT*BLK_PAD
+    float2 *zbuf = buf + NT * BLK_PAD;                            // NSTATE*NT
+
+    const int tid   = threadIdx.x;
+    const int tile  = blockIdx.x;
+    int frame = blockIdx.y, side = 0;
+    if (p.strips) {
+        side = frame & 1;
+        frame >>= 1;
+    }
+    const int L     = p.L;
+    const int p0    = tile * p.T;                 // first output position (even)
+    const int rs    = p0 - WARM;                  // region start, ext coordinates
+
+    const size_t esz = (KIND == KIND_U8_RAW) ? 2 : 8;
+    const char *frame_in = (const char *)p.in +
+                           ((size_t)frame * (size_t)p.in_stride + (size_t)side * (size_t)p.side_in_off) * esz;
+
+    load_region<KIND, NT>(buf, p, frame_in, rs, tid, (KIND != KIND_C64_MID && side) ? p.pos_off : 0);
+    __syncthreads();
+
+    exact_stage_inplace<NT>(buf, zbuf, L, rs, tid);
 
     // ---------------- keep every 2nd sample of [p0, min(p0+T, L)) ----------------
     const int span = min(p.T, L - p0);
@@ -466,6 +475,74 @@ __global__ void __launch_bounds__(NT, (NT == NTHR_BIG ? 1 : 3)) decim2_exact_ker
     const int wlo = p.w_lo[side] - (p0 >> 1), whi = p.w_hi[side] - (p0 >> 1);
     for (int i = tid; i < nout; i += NT)
         if (i >= wlo && i < whi) out[i] = buf[sidx(WARM + 2 * i)];
+}
+
+// ZFB_MODE_FAST edge strips: the whole exact cascade on one short chunk cut from
+// a frame's left (side 0) or right (side 1) end, in ONE CTA: stage s leaves its
+// outputs in shared memory, the part the next stage needs is compacted to the
+// front of the region, and only the last stage's `keep` outputs reach global
+// memory (they overwrite the FIR interior's values at the chunk edge).
+struct StripParams {
+    StageParams st;            // stage 0 load: in, in_stride, L = len[0], flip, Lfull, pos_off, LO tables
+    int   nstages;
+    int   len[16];             // strip length at the input of stage s
+    int   keep;                // outputs of the last stage that are written (K)
+    float2 *out;               // decimated chunks [frames][out_stride]
+    long long out_stride;
+    int   ndec;                // decimated chunk length
+};
+
+template <int KIND>
+__global__ void __launch_bounds__(NTHR_SMALL, 3) strip_cascade_kernel(const StripParams sp) {
+    constexpr int NT = NTHR_SMALL;
+    ZFB_DYN_SMEM(smem_raw);
+    float2 *buf  = reinterpret_cast<float2 *>(smem_raw);
+    float2 *zbuf = buf + NT * BLK_PAD;
+    const int tid = threadIdx.x;
+    const int side = blockIdx.x;
+    const int frame = blockIdx.y;
+    const StageParams &p = sp.st;
+    const size_t esz = (KIND == KIND_U8_RAW) ? 2 : 8;
+    const char *frame_in = (const char *)p.in +
+                           ((size_t)frame * (size_t)p.in_stride + (size_t)side * (size_t)p.side_in_off) * esz;
+    const int rs = -WARM;
+
+    load_region<KIND, NT>(buf, p, frame_in, rs, tid, (KIND != KIND_C64_MID && side) ? p.pos_off : 0);
+    __syncthreads();
+    const float g = c_dec.g;
+    for (int s = 0; s < sp.nstages; ++s) {
+        const int L = sp.len[s];
+        exact_stage_inplace<NT>(buf, zbuf, L, rs, tid);
+        const int nout = (L + 1) >> 1;
+        if (s == sp.nstages - 1) {
+            float2 *out = sp.out + (size_t)frame * (size_t)sp.out_stride;
+            const int m0 = side ? nout - sp.keep : 0;
+            const int d0 = side ? sp.ndec - sp.keep : 0;
+            for (int i = tid; i < sp.keep; i += NT) out[d0 + i] = buf[sidx(WARM + 2 * (m0 + i))];
+        } else {
+            // the next stage works on the first (side 0) / last (side 1) len[s+1] outputs:
+            // move them, gain-scaled, to region positions WARM + j.  dst <= src, so
+            // ascending chunks are safe once a chunk's reads precede its writes.
+            const int Ln = sp.len[s + 1];
+            const int off = side ? nout - Ln : 0;
+            constexpr int CH = 8;
+            for (int j0 = 0; j0 < Ln; j0 += CH * NT) {
+                float2 v[CH];
+#pragma unroll
+                for (int c = 0; c < CH; ++c) {
+                    const int j = j0 + c * NT + tid;
+                    v[c] = (j < Ln) ? buf[sidx(WARM + 2 * (off + j))] : make_float2(0.f, 0.f);
+                }
+                __syncthreads();
+#pragma unroll
+                for (int c = 0; c < CH; ++c) {
+                    const int j = j0 + c * NT + tid;
+                    if (j < Ln) buf[sidx(WARM + j)] = pk_mul(g, v[c]);
+                }
+                __syncthreads();
+            }
+        }
+    }
 }
 
 }  // namespace zfb

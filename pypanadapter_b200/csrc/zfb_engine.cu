@@ -420,6 +420,12 @@ int setup_device_once(zfb_engine *e) {
             if (w.smem > 48 * 1024)
                 CK(e, cudaFuncSetAttribute(w.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.smem));
         }
+    CK(e, cudaFuncSetAttribute(strip_cascade_kernel<KIND_U8_RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)decim_smem(NTHR_SMALL)));
+    CK(e, cudaFuncSetAttribute(strip_cascade_kernel<KIND_C64_RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)decim_smem(NTHR_SMALL)));
+    CK(e, cudaFuncSetAttribute(strip_cascade_kernel<KIND_C64_MID>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)decim_smem(NTHR_SMALL)));
     for (int kind = 0; kind < 3; ++kind)
         CK(e, cudaFuncSetAttribute(chain_lookup_fn(kind), cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     return ZFB_OK;
@@ -544,13 +550,16 @@ void run_decimation_fast(zfb_engine *e, const void *d_in, int gf, int *out_buf) 
         launch_stage(e, KIND_C64_MID, v, p, (unsigned)e->tiles[s][v], (unsigned)gf, k - 1);
     }
     *out_buf = b;
-    // exact edge strips: every stage on two short chunks per frame
+    // exact edge strips.  The last (up to) 4 stages of a strip fit one 8192-sample
+    // region and run fused in ONE CTA per strip (strip_cascade_kernel); for deeper
+    // zooms the first stages' strips are longer and go through the tiled kernel.
+    const int kf = k < 4 ? k : 4;
+    const int s0 = k - kf;
     const int tmax = tmax_of(v == 0 ? NTHR_BIG : NTHR_SMALL);
     const long long cap = e->strip_cap;
-    for (int s = 0; s < k; ++s) {
+    for (int s = 0; s < s0; ++s) {
         StageParams p = e->sp0[v];
         const int L = e->strip_len[s];
-        const int nout = (L + 1) / 2;
         p.strips = 1;
         p.L = L;
         const int tiles = (L + tmax - 1) / tmax;
@@ -572,23 +581,55 @@ void run_decimation_fast(zfb_engine *e, const void *d_in, int gf, int *out_buf) 
             p.Lfull = L;
             p.flip = 0;
         }
-        if (s == k - 1) {
-            p.out = (float2 *)e->mid[b].p;
-            p.out_stride = e->len[k];
-            p.side_out_off = e->len[k] - nout;
-            p.w_lo[0] = 0;
-            p.w_hi[0] = e->fplan.K;
-            p.w_lo[1] = nout - e->fplan.K;
-            p.w_hi[1] = nout;
-        } else {
-            p.out = (float2 *)e->sbuf[s & 1].p;
-            p.out_stride = 2 * cap;
-            p.side_out_off = cap;
-            p.w_lo[0] = p.w_lo[1] = 0;
-            p.w_hi[0] = p.w_hi[1] = INT_MAX;
-        }
+        p.out = (float2 *)e->sbuf[s & 1].p;
+        p.out_stride = 2 * cap;
+        p.side_out_off = cap;
+        p.w_lo[0] = p.w_lo[1] = 0;
+        p.w_hi[0] = p.w_hi[1] = INT_MAX;
         launch_stage(e, s == 0 ? raw_kind(c) : KIND_C64_MID, v, p, (unsigned)((L + T - 1) / T),
                      (unsigned)(2 * gf), 15);
+    }
+    {
+        StripParams sp{};
+        sp.st = e->sp0[1];                       // NT = 128 LO tables
+        sp.st.L = e->strip_len[s0];
+        sp.st.T = 0;
+        sp.st.strips = 1;
+        int skind;
+        if (s0 == 0) {
+            skind = raw_kind(c);
+            sp.st.in = d_in;
+            sp.st.in_stride = c.frame_len;
+            sp.st.side_in_off = 0;
+            sp.st.flip = c.flip;
+            sp.st.pos_off = e->strip_q[0];
+            sp.st.Lfull = c.frame_len;
+        } else {
+            skind = KIND_C64_MID;
+            sp.st.in = e->sbuf[(s0 - 1) & 1].p;
+            sp.st.in_stride = 2 * cap;
+            sp.st.side_in_off = cap + (e->strip_q[s0] - e->strip_q[s0 - 1] / 2);
+            sp.st.flip = 0;
+            sp.st.pos_off = 0;
+            sp.st.Lfull = sp.st.L;
+        }
+        sp.nstages = kf;
+        for (int s = 0; s < kf; ++s) sp.len[s] = e->strip_len[s0 + s];
+        sp.keep = e->fplan.K;
+        sp.out = (float2 *)e->mid[b].p;
+        sp.out_stride = e->len[k];
+        sp.ndec = e->len[k];
+        const int pr = prof_begin(e, 15);
+        const dim3 grid(2, (unsigned)gf);
+        if (skind == KIND_U8_RAW) {
+            ZFB_LAUNCH(strip_cascade_kernel<KIND_U8_RAW>, grid, dim3(NTHR_SMALL), decim_smem(NTHR_SMALL), st, sp);
+        } else if (skind == KIND_C64_RAW) {
+            ZFB_LAUNCH(strip_cascade_kernel<KIND_C64_RAW>, grid, dim3(NTHR_SMALL), decim_smem(NTHR_SMALL), st, sp);
+        } else {
+            ZFB_LAUNCH(strip_cascade_kernel<KIND_C64_MID>, grid, dim3(NTHR_SMALL), decim_smem(NTHR_SMALL), st, sp);
+        }
+        prof_end(e, pr);
+        e->counters[2] += 1;
     }
 }
 
@@ -752,7 +793,7 @@ int plan_fast(zfb_engine *e) {
                     e->fplan.set ? e->fplan.ne : -1);
     // strips: i_{k-1} = 2K + D, i_s = 2 i_{s+1} + D, right strip starts at an even position
     const int K = e->fplan.K;
-    const int D = 384;
+    const int D = 320;                 // >= WARM: the artificial strip edge has decayed (0.935^320 = 5e-10)
     int need = 2 * K + D;
     for (int s = k - 1; s >= 0; --s) {
         int i = need;

@@ -131,7 +131,7 @@ class ZoomPSD:
     # -- configuration ---------------------------------------------------
     def configure(self, fs, fft_size, fft_ratio, frame_len, window="hamming", *,
                   dtype="c64", flip=False, f_demod=1.0, crop="thread",
-                  ema_alpha=None, no_lo=False, linear=False, mode="exact"):
+                  ema_alpha=None, no_lo=False, linear=False, mode="fast"):
         """Plan for a frame shape (cheap if nothing changed).  Mirrors the
         AppState the reference reads per frame (S:1492-1497).
 
@@ -359,7 +359,7 @@ def default_engine(device: int = 0) -> ZoomPSD:
 
 
 def zoom_psd(chunk, fs, fft_size, fft_ratio, window, *, f_demod=1.0, crop="thread",
-             flip=False, ema_alpha=None, engine: ZoomPSD | None = None) -> np.ndarray:
+             flip=False, ema_alpha=None, mode="fast", engine: ZoomPSD | None = None) -> np.ndarray:
     """One dB20 waterfall row of one chunk (float64 ndarray[W]).
 
     ``chunk``: 1-D complex64/complex128, or interleaved uint8 I,Q (RTL-SDR).
@@ -377,5 +377,5 @@ def zoom_psd(chunk, fs, fft_size, fft_ratio, window, *, f_demod=1.0, crop="threa
     else:
         dtype, n = "c64", chunk.size
     eng.configure(fs, fft_size, fft_ratio, n, window, dtype=dtype, flip=flip,
-                  f_demod=f_demod, crop=crop, ema_alpha=ema_alpha)
+                  f_demod=f_demod, crop=crop, ema_alpha=ema_alpha, mode=mode)
     return eng.process(chunk)[0].astype(np.float64)
