@@ -9,6 +9,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <limits.h>
@@ -62,6 +63,7 @@ struct zfb_engine {
     int tiles[kMaxStages][2] = {{0}}, T[kMaxStages][2] = {{0}};   // [stage][0: NT=256, 1: NT=128]
     int decim_threads = 0;             // 0 = automatic per launch
     int welch_splits = 0;              // 0 = automatic
+    int fir_generic = 0;               // 1: never use the register-blocked FIR kernel (tests)
     int nperseg = 0, hop = 0, nseg = 0, W = 0, log2N = 0;
     double sum_w2 = 0.0;
     int group = 1, group_user = 0;
@@ -92,6 +94,8 @@ struct zfb_engine {
     FirChainParams chain[4]{};
     int chain_level_out[4] = {0};      // decimation level (stage count) after chain j
     size_t chain_smem[4] = {0};
+    int chain_run[4] = {0};            // 0: generic kernel; 1..3: fir_run_kernel with NS = that
+    FirRunParams runp[4]{};
     int strip_len[kMaxStages] = {0};   // i_s: samples per strip at the input of stage s
     int strip_q[kMaxStages] = {0};     // Q_s: absolute position of the right strip's first sample
     int strip_cap = 0;
@@ -406,6 +410,8 @@ ChainFn0 chain_lookup_fn(int kind) {
     }
 }
 
+template <int KIND> int fir_run_setup_kind(zfb_engine *e);
+
 int setup_device_once(zfb_engine *e) {
     DecimConst dc;
     build_decim_const(dc);
@@ -428,7 +434,10 @@ int setup_device_once(zfb_engine *e) {
                                (int)decim_smem(NTHR_SMALL)));
     for (int kind = 0; kind < 3; ++kind)
         CK(e, cudaFuncSetAttribute(chain_lookup_fn(kind), cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    return ZFB_OK;
+    int rc = fir_run_setup_kind<KIND_C64_RAW>(e);
+    if (rc == ZFB_OK) rc = fir_run_setup_kind<KIND_U8_RAW>(e);
+    if (rc == ZFB_OK) rc = fir_run_setup_kind<KIND_C64_MID>(e);
+    return rc;
 }
 
 int raw_kind(const zfb_config &c) { return c.dtype == ZFB_DTYPE_U8 ? KIND_U8_RAW : KIND_C64_RAW; }
@@ -487,6 +496,51 @@ void prof_end(zfb_engine *e, int idx) {
     if (idx >= 0) cudaEventRecord(e->prof_used[(size_t)idx].b, e->stream);
 }
 
+// the tap sets fastdesign.py produces for the last chain of R = 4 / 8 / >= 16
+#define ZFB_RUN_COMBOS(X, KIND) \
+    X(1, KIND, 1, 13, 0, 0, 15)  \
+    X(2, KIND, 2, 5, 13, 0, 16)  \
+    X(3, KIND, 3, 4, 5, 13, 16)
+
+template <int KIND>
+void launch_fir_run_kind(int variant, const FirRunParams &rp, int L_out, int gf, cudaStream_t st) {
+#define ZFB_X(ID, K, NS, A, B, C, D)                                                              \
+    if (variant == ID) {                                                                          \
+        using SH = FirRunShape<NS, A, B, C, D>;                                                   \
+        const int per_tile = SH::SPAN >> NS;                                                      \
+        const unsigned tiles = (unsigned)((L_out + per_tile - 1) / per_tile);                     \
+        ZFB_LAUNCH((fir_run_kernel<K, NS, A, B, C, D>), dim3(tiles, (unsigned)gf), dim3(FIR_NT), SH::SMEM, st, rp); \
+        return;                                                                                   \
+    }
+    ZFB_RUN_COMBOS(ZFB_X, KIND)
+#undef ZFB_X
+}
+
+void launch_fir_run(int variant, int kind, const FirRunParams &rp, int L_out, int gf, cudaStream_t st) {
+    if (kind == KIND_U8_RAW) launch_fir_run_kind<KIND_U8_RAW>(variant, rp, L_out, gf, st);
+    else if (kind == KIND_C64_RAW) launch_fir_run_kind<KIND_C64_RAW>(variant, rp, L_out, gf, st);
+    else launch_fir_run_kind<KIND_C64_MID>(variant, rp, L_out, gf, st);
+}
+
+// which specialised variant (0 = none) handles this chain
+int fir_run_variant(const FirChainParams &p) {
+#define ZFB_X(ID, K, NS, A, B, C, D)                                                             \
+    if (p.ns == NS && p.Mc == D && p.M[0] == A && (NS < 2 || p.M[1] == B) && (NS < 3 || p.M[2] == C)) return ID;
+    ZFB_RUN_COMBOS(ZFB_X, 0)
+#undef ZFB_X
+    return 0;
+}
+
+template <int KIND>
+int fir_run_setup_kind(zfb_engine *e) {
+#define ZFB_X(ID, K, NS, A, B, C, D)                                                              \
+    CK(e, cudaFuncSetAttribute((fir_run_kernel<K, NS, A, B, C, D>), cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                               (int)FirRunShape<NS, A, B, C, D>::SMEM));
+    ZFB_RUN_COMBOS(ZFB_X, KIND)
+#undef ZFB_X
+    return ZFB_OK;
+}
+
 typedef void (*ChainFn)(const FirChainParams);
 ChainFn chain_lookup(int kind) {
     switch (kind) {
@@ -522,9 +576,18 @@ void run_decimation_fast(zfb_engine *e, const void *d_in, int gf, int *out_buf) 
         p.in_stride = src_stride;
         p.out = (float2 *)e->mid[b].p;
         p.out_stride = e->len[lvl];
-        const unsigned tiles = (unsigned)((e->len[lvl] + p.TO - 1) / p.TO);
         const int pr = prof_begin(e, j == 0 ? 0 : 1);
-        ZFB_LAUNCH(chain_lookup(kind), dim3(tiles, (unsigned)gf), dim3(FIR_NT), e->chain_smem[j], st, p);
+        if (e->chain_run[j]) {
+            FirRunParams rp = e->runp[j];
+            rp.in = p.in;
+            rp.in_stride = p.in_stride;
+            rp.out = p.out;
+            rp.out_stride = p.out_stride;
+            launch_fir_run(e->chain_run[j], kind, rp, e->len[lvl], gf, st);
+        } else {
+            const unsigned tiles = (unsigned)((e->len[lvl] + p.TO - 1) / p.TO);
+            ZFB_LAUNCH(chain_lookup(kind), dim3(tiles, (unsigned)gf), dim3(FIR_NT), e->chain_smem[j], st, p);
+        }
         prof_end(e, pr);
         e->counters[2] += 1;
         src = p.out;
@@ -819,7 +882,10 @@ int plan_fast(zfb_engine *e) {
         if (e->nchains >= 4) return fail(e, ZFB_EINVAL, "fft_ratio too deep for mode FAST");
         FirChainParams &p = e->chain[e->nchains];
         memset(&p, 0, sizeof p);
-        const int ns = (ne - done > FIR_MAX_STAGES) ? FIR_MAX_STAGES : ne - done;
+        // the LAST chain takes up to 3 stages (it has the specialised kernel);
+        // what is left over goes to the first chain
+        int ns = (ne - done) % FIR_MAX_STAGES;
+        if (ns == 0) ns = FIR_MAX_STAGES;
         p.ns = ns;
         for (int s = 0; s < ns; ++s) {
             p.M[s] = e->fplan.M[done + s];
@@ -854,6 +920,24 @@ int plan_fast(zfb_engine *e) {
         fir_tile_geometry(p, 0, t);
         for (int l = 0; l <= ns; ++l) p.n[l] = t.n[l];
         e->chain_smem[e->nchains] = fir_chain_smem(p);
+        // register-blocked kernel when the tap set is one it is built for
+        e->chain_run[e->nchains] = e->fir_generic ? 0 : fir_run_variant(p);
+        if (getenv("ZFB_DEBUG_PLAN")) fprintf(stderr, "chain %d: ns %d M %d %d %d Mc %d L %d variant %d TO %d\n", e->nchains, p.ns, p.M[0], p.M[1], p.M[2], p.Mc, p.L, e->chain_run[e->nchains], p.TO);
+        if (e->chain_run[e->nchains]) {
+            FirRunParams &rp = e->runp[e->nchains];
+            memset(&rp, 0, sizeof rp);
+            rp.L = p.L;
+            rp.flip = p.flip;
+            rp.phase_inc = p.phase_inc;
+            if (done == 0) {
+                const double amp = no_lo ? 1.0 : sqrt(2.0);
+                for (int i = 0; i < RUN0; ++i) lo_entry(r, i, amp, rp.lo_run[i]);
+            }
+            memcpy(rp.h0, p.h[0], sizeof rp.h0);
+            memcpy(rp.h1, p.h[1], sizeof rp.h1);
+            memcpy(rp.h2, p.h[2], sizeof rp.h2);
+            memcpy(rp.hc, p.hc, sizeof rp.hc);
+        }
         done += ns;
         e->chain_level_out[e->nchains] = done;
         e->nchains += 1;
@@ -1191,6 +1275,11 @@ int zfb_set_option(zfb_engine *e, const char *name, long long value) {
     if (strcmp(name, "welch_splits") == 0) {
         if (value < 0 || value > 16) return fail(e, ZFB_EINVAL, "welch_splits must be in [0, 16]");
         e->welch_splits = (int)value;
+        return ZFB_OK;
+    }
+    if (strcmp(name, "fir_generic") == 0) {
+        e->fir_generic = value ? 1 : 0;
+        e->configured = false;
         return ZFB_OK;
     }
     return fail(e, ZFB_EINVAL, "unknown option '%s'", name);

@@ -304,3 +304,263 @@ inline size_t fir_chain_smem(const FirChainParams &p) {
 }
 
 }  // namespace zfb
+
+// ===========================================================================
+// Register-blocked variant of the FIR chain for the tap sets the design
+// actually produces for R = 4, 8, >= 16 (last chain): every thread owns a run
+// of RUN0 = 32 consecutive level-0 samples, keeps its data in registers through
+// all stages (sliding windows with static indexing) and goes to shared memory
+// only for the M samples it needs from its neighbours' runs.  ~3x less shared
+// memory traffic than fir_chain_kernel (which stays as the general fallback:
+// ncu showed it at 83 % of the LSU/shared-memory wavefront peak).
+// ===========================================================================
+namespace zfb {
+
+constexpr int RUN0 = 32;
+
+struct FirRunParams {
+    const void *in;
+    long long   in_stride;
+    int         L;
+    int         flip;
+    unsigned long long phase_inc;
+    float2      lo_run[RUN0];      // amp * exp(-2 pi i f/fs j), j = 0..31
+    float       h0[FIR_MAX_HALF + 1], h1[FIR_MAX_HALF + 1], h2[FIR_MAX_HALF + 1];
+    float       hc[FIR_COMP_MAX_HALF + 1];
+    float2     *out;
+    long long   out_stride;
+    int         ht;                // halo threads per side
+};
+
+// neighbour exchange of one level: a thread publishes its run (or only the M
+// samples at either end when that is all a neighbour can need) and reads the
+// M samples left / right of its run with compile-time offsets
+template <int RUN, int M>
+struct LevelStore {
+    static constexpr bool EDGES = (2 * M <= RUN);
+    static constexpr int STRIDE = (EDGES ? 2 * M : RUN) | 1;       // odd: conflict-free LDS.64
+    static constexpr int SIZE = FIR_NT * STRIDE;                   // float2 elements
+
+    __device__ static __forceinline__ void publish(float2 *sm, int t, const float2 (&x)[RUN]) {
+        float2 *p = sm + t * STRIDE;
+        if (EDGES) {
+#pragma unroll
+            for (int j = 0; j < M; ++j) {
+                p[j] = x[j];
+                p[M + j] = x[RUN - M + j];
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < RUN; ++j) p[j] = x[j];
+        }
+    }
+    // win[0..M) = samples at run positions -M..-1, win[M+RUN .. M+RUN+M) = positions RUN..RUN+M-1
+    template <int W>
+    __device__ static __forceinline__ void halo(const float2 *sm, int t, float2 (&win)[W]) {
+        static_assert(W == RUN + 2 * M, "window size");
+#pragma unroll
+        for (int d = 1; d <= M; ++d) {              // position -d
+            int idx;
+            if (EDGES) {
+                idx = max(t - 1, 0) * STRIDE + 2 * M - d;
+            } else {
+                const int c = (d + RUN - 1) / RUN;
+                idx = max(t - c, 0) * STRIDE + (RUN * c - d);
+            }
+            win[M - d] = sm[idx];
+        }
+#pragma unroll
+        for (int d = 0; d < M; ++d) {               // position RUN + d
+            int idx;
+            if (EDGES) {
+                idx = min(t + 1, FIR_NT - 1) * STRIDE + d;
+            } else {
+                const int c = d / RUN;
+                idx = min(t + 1 + c, FIR_NT - 1) * STRIDE + (d - RUN * c);
+            }
+            win[M + RUN + d] = sm[idx];
+        }
+    }
+};
+
+// RUN/2 outputs of a decimate-by-2 symmetric FIR from a window win[-M .. RUN-1+M]
+template <int RUN, int M>
+__device__ __forceinline__ void fir_decim_regs(const float2 (&win)[RUN + 2 * M], const float *hp,
+                                               float2 (&y)[RUN / 2]) {
+    float h[M + 1];
+#pragma unroll
+    for (int j = 0; j <= M; ++j) h[j] = hp[j];
+#pragma unroll
+    for (int m = 0; m < RUN / 2; ++m) {
+        float2 acc = pk_mul(h[0], win[M + 2 * m]);
+#pragma unroll
+        for (int j = 1; j <= M; ++j) acc = pk_fma(h[j], pk_add(win[M + 2 * m - j], win[M + 2 * m + j]), acc);
+        y[m] = acc;
+    }
+}
+
+template <int RUN, int M>
+__device__ __forceinline__ void fir_same_regs(const float2 (&win)[RUN + 2 * M], const float *hp,
+                                              float2 (&y)[RUN]) {
+    float h[M + 1];
+#pragma unroll
+    for (int j = 0; j <= M; ++j) h[j] = hp[j];
+#pragma unroll
+    for (int m = 0; m < RUN; ++m) {
+        float2 acc = pk_mul(h[0], win[M + m]);
+#pragma unroll
+        for (int j = 1; j <= M; ++j) acc = pk_fma(h[j], pk_add(win[M + m - j], win[M + m + j]), acc);
+        y[m] = acc;
+    }
+}
+
+// zero the outputs whose level position lies outside [0, Llev)
+template <int RUN>
+__device__ __forceinline__ void mask_level(float2 (&y)[RUN], int pos0, int Llev) {
+#pragma unroll
+    for (int j = 0; j < RUN; ++j)
+        if (pos0 + j < 0 || pos0 + j >= Llev) y[j] = make_float2(0.f, 0.f);
+}
+
+// one stage: publish the input runs, barrier, gather the halos, filter
+template <int RUN, int M>
+__device__ __forceinline__ void run_stage(float2 *sm, int t, const float2 (&x)[RUN], const float *hp,
+                                          float2 (&y)[RUN / 2], int pos0_out, int L_out) {
+    LevelStore<RUN, M>::publish(sm, t, x);
+    __syncthreads();
+    float2 win[RUN + 2 * M];
+#pragma unroll
+    for (int j = 0; j < RUN; ++j) win[M + j] = x[j];
+    LevelStore<RUN, M>::template halo<RUN + 2 * M>(sm, t, win);
+    fir_decim_regs<RUN, M>(win, hp, y);
+    mask_level<RUN / 2>(y, pos0_out, L_out);
+}
+
+template <int NS, int M0, int M1, int M2, int MC>
+struct FirRunShape {
+    static constexpr int RUN_OUT = RUN0 >> NS;
+    static constexpr int S0 = LevelStore<RUN0, M0>::SIZE;
+    static constexpr int S1 = NS >= 2 ? LevelStore<RUN0 / 2, (M1 > 0 ? M1 : 1)>::SIZE : 0;
+    static constexpr int S2 = NS >= 3 ? LevelStore<RUN0 / 4, (M2 > 0 ? M2 : 1)>::SIZE : 0;
+    static constexpr int SC = LevelStore<RUN_OUT, MC>::SIZE;
+    static constexpr size_t SMEM = (size_t)(S0 + S1 + S2 + SC) * sizeof(float2);
+    // dependency cone of a final output, in level-0 samples
+    static constexpr int CONE = M0 + (NS >= 2 ? 2 * M1 : 0) + (NS >= 3 ? 4 * M2 : 0) + (1 << NS) * MC;
+    static constexpr int HT = (CONE + RUN0 - 1) / RUN0;
+    static constexpr int SPAN = (FIR_NT - 2 * HT) * RUN0;          // level-0 samples a tile finishes
+};
+
+template <int KIND, int NS, int M0, int M1, int M2, int MC>
+__global__ void __launch_bounds__(FIR_NT, 2) fir_run_kernel(const FirRunParams p) {
+    using SH = FirRunShape<NS, M0, M1, M2, MC>;
+    constexpr int VEC = (KIND == KIND_U8_RAW) ? 8 : 2;
+    ZFB_DYN_SMEM(smem_raw);
+    float2 *sm0 = reinterpret_cast<float2 *>(smem_raw);
+    float2 *sm1 = sm0 + SH::S0;
+    float2 *sm2 = sm1 + SH::S1;
+    float2 *smc = sm2 + SH::S2;
+    const int t = threadIdx.x;
+    const int frame = blockIdx.y;
+    const int lo0 = blockIdx.x * SH::SPAN - SH::HT * RUN0;          // level-0 position of thread 0, sample 0
+    const int pos0 = lo0 + t * RUN0;
+    const int L = p.L;
+
+    // ---------------- level 0: this thread's 32 samples ----------------
+    float2 x0[RUN0];
+    {
+        const size_t esz = (KIND == KIND_U8_RAW) ? 2 : 8;
+        const char *frame_in = (const char *)p.in + (size_t)frame * (size_t)p.in_stride * esz;
+        const bool fl = (KIND != KIND_C64_MID) && p.flip;
+        // element e of the run <-> sample index fl ? L-1-(pos0+e) : pos0+e
+        const long long i_first = fl ? (long long)L - RUN0 - pos0 : (long long)pos0;
+        const char *a = frame_in + (size_t)i_first * esz;
+        if (pos0 >= 0 && pos0 + RUN0 <= L && ((((uintptr_t)a) & 15) == 0)) {
+            constexpr int NV = RUN0 / VEC;
+            uint4 raw[NV];
+#pragma unroll
+            for (int v = 0; v < NV; ++v) raw[v] = __ldg((const uint4 *)a + v);
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                if (KIND == KIND_U8_RAW) {
+                    const unsigned int wds[4] = {raw[v].x, raw[v].y, raw[v].z, raw[v].w};
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const int idx = v * 8 + e;                 // memory order
+                        x0[fl ? RUN0 - 1 - idx : idx] = u8pair_to_iq(wds[e >> 1], e & 1);
+                    }
+                } else {
+                    const int i0 = v * 2, i1 = v * 2 + 1;
+                    x0[fl ? RUN0 - 1 - i0 : i0] = make_float2(__uint_as_float(raw[v].x), __uint_as_float(raw[v].y));
+                    x0[fl ? RUN0 - 1 - i1 : i1] = make_float2(__uint_as_float(raw[v].z), __uint_as_float(raw[v].w));
+                }
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < RUN0; ++e) {
+                const int pe = pos0 + e;
+                x0[e] = make_float2(0.f, 0.f);
+                if (pe >= 0 && pe < L) {
+                    const long long ie = fl ? (long long)L - 1 - pe : (long long)pe;
+                    if (KIND == KIND_U8_RAW) {
+                        const unsigned char *src = (const unsigned char *)frame_in;
+                        x0[e] = make_float2(u8_to_f(src[2 * ie]), u8_to_f(src[2 * ie + 1]));
+                    } else {
+                        x0[e] = __ldg((const float2 *)frame_in + ie);
+                    }
+                }
+            }
+        }
+        if (KIND != KIND_C64_MID) {
+            const float2 b0 = lo_phasor((long long)pos0, p.phase_inc);
+#pragma unroll
+            for (int e = 0; e < RUN0; ++e) x0[e] = cmul(x0[e], cmul(b0, p.lo_run[e]));
+        }
+    }
+
+    int Llev[4];
+    Llev[0] = L;
+    Llev[1] = (L + 1) >> 1;
+    Llev[2] = (Llev[1] + 1) >> 1;
+    Llev[3] = (Llev[2] + 1) >> 1;
+
+    // ---------------- decimating stages, all in registers ----------------
+    float2 yf[SH::RUN_OUT];                 // level NS run of this thread
+    {
+        float2 y1[RUN0 / 2];
+        run_stage<RUN0, M0>(sm0, t, x0, p.h0, y1, pos0 >> 1, Llev[1]);
+        if constexpr (NS == 1) {
+#pragma unroll
+            for (int j = 0; j < RUN0 / 2; ++j) yf[j] = y1[j];
+        } else {
+            float2 y2[RUN0 / 4];
+            run_stage<RUN0 / 2, M1>(sm1, t, y1, p.h1, y2, pos0 >> 2, Llev[2]);
+            if constexpr (NS == 2) {
+#pragma unroll
+                for (int j = 0; j < RUN0 / 4; ++j) yf[j] = y2[j];
+            } else {
+                run_stage<RUN0 / 4, M2>(sm2, t, y2, p.h2, yf, pos0 >> 3, Llev[3]);
+            }
+        }
+    }
+
+    // ---------------- compensator ----------------
+    constexpr int RO = SH::RUN_OUT;
+    LevelStore<RO, MC>::publish(smc, t, yf);
+    __syncthreads();
+    float2 win[RO + 2 * MC];
+#pragma unroll
+    for (int j = 0; j < RO; ++j) win[MC + j] = yf[j];
+    LevelStore<RO, MC>::template halo<RO + 2 * MC>(smc, t, win);
+    float2 out[RO];
+    fir_same_regs<RO, MC>(win, p.hc, out);
+
+    if (t >= SH::HT && t < FIR_NT - SH::HT) {
+        const int po = pos0 >> NS;
+        float2 *frame_out = p.out + (size_t)frame * (size_t)p.out_stride;
+#pragma unroll
+        for (int j = 0; j < RO; ++j)
+            if (po + j >= 0 && po + j < Llev[NS]) frame_out[po + j] = out[j];
+    }
+}
+
+}  // namespace zfb

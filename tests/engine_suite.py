@@ -241,3 +241,17 @@ def fast_strong_out_of_band(engine):
     assert engine.fast_active
     row = engine.process(x)[0].astype(np.float64)
     parity.assert_row_parity(row, want, parity.floor_db20(fs, "hamming", N, True), "fast interferers")
+
+
+def fast_generic_fir_kernel(engine):
+    """The general shared-memory FIR kernel (fallback for tap sets the
+    register-blocked kernel is not built for) meets the same parity."""
+    try:
+        engine.set_option("fir_generic", 1)
+        engine._key = None
+        for name in ("cfg1_T", "cfg2_T_f0", "zoom_R4", "zoom_R64"):
+            parity.check_case(engine, name, mode="fast")
+            assert engine.fast_active
+    finally:
+        engine.set_option("fir_generic", 0)
+        engine._key = None

@@ -99,3 +99,7 @@ def test_fast_batch_and_ema(emu_engine):
 
 def test_fast_strong_out_of_band(emu_engine):
     es.fast_strong_out_of_band(emu_engine)
+
+
+def test_fast_generic_fir_kernel(emu_engine):
+    es.fast_generic_fir_kernel(emu_engine)

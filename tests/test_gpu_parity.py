@@ -175,3 +175,7 @@ def test_fast_batch_and_ema(gpu_engine):
 
 def test_fast_strong_out_of_band(gpu_engine):
     es.fast_strong_out_of_band(gpu_engine)
+
+
+def test_fast_generic_fir_kernel(gpu_engine):
+    es.fast_generic_fir_kernel(gpu_engine)
