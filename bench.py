@@ -393,8 +393,8 @@ def run_b200(args, w):
             "kernel_share_of_step": top_ms / total_kernel_ms,
             "kernel_ms": {k: round(v[0], 4) for k, v in prof.items()},
             "step_achieved_gbs": step_bytes * args.steps / (ms * 1e-3) / 1e9 * 1.0,
-            "note": "fp32-issue bound, not HBM bound: the exact zero-phase IIR costs ~120 packed "
-                    "FMA per input sample (DESIGN.md)",
+            "note": "fp32-pipe bound, not HBM bound (DESIGN.md 4): FMA pipe ~64 % active in the FIR chain; "
+                    "60 % of HBM at 2 B/sample would leave 19 pipe-cycles per sample",
         }
         cfg = workload_config(w, F)
         cfg["l2"] = "inputs larger than L2: %.0f MB per step per GPU" % (in_bytes / 1e6)
@@ -431,7 +431,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(synth.WORKLOADS))
-    ap.add_argument("--frames", type=int, default=256, help="frames per step per GPU")
+    ap.add_argument("--frames", type=int, default=512, help="frames per step per GPU")
     ap.add_argument("--group", type=int, default=0, help="frames per launch group (0 = auto)")
     ap.add_argument("--decim-threads", type=int, default=0, help="tuning: 0 auto, 128 or 256")
     ap.add_argument("--mode", default="fast", choices=["exact", "fast"],

@@ -443,19 +443,67 @@ int setup_device_once(zfb_engine *e) {
 int raw_kind(const zfb_config &c) { return c.dtype == ZFB_DTYPE_U8 ? KIND_U8_RAW : KIND_C64_RAW; }
 size_t sample_bytes(const zfb_config &c) { return c.dtype == ZFB_DTYPE_U8 ? 2 : 8; }
 
-int choose_group(const zfb_engine *e) {
+// FAST engages when the plan fits and the chunk is long enough for the strips
+bool fast_wanted(const zfb_engine *e, int *strip_len, int *strip_q) {
+    const zfb_config &c = e->cfg;
+    const int k = e->nstages;
+    if (c.mode != ZFB_MODE_FAST || k < 2 || !e->fplan.set || e->fplan.ne != k - 1) return false;
+    // strips: i_{k-1} = 2K + D, i_s = 2 i_{s+1} + D, right strip starts at an even position
+    const int K = e->fplan.K;
+    const int D = 320;                 // >= WARM: the artificial strip edge has decayed (0.935^320 = 5e-10)
+    int need = 2 * K + D;
+    for (int s = k - 1; s >= 0; --s) {
+        int i = need;
+        if ((e->len[s] - i) & 1) i += 1;
+        strip_len[s] = i;
+        strip_q[s] = e->len[s] - i;
+        need = 2 * i + D;
+    }
+    return e->len[0] >= 4 * strip_len[0] && e->len[k] >= 4 * K;
+}
+
+// chains of FAST: sizes from the back (the last chain takes up to 3 stages)
+int fast_chain_sizes(int ne, int sizes[4]) {
+    int n = 0, done = 0;
+    while (done < ne && n < 4) {
+        int ns = (ne - done) % FIR_MAX_STAGES;
+        if (ns == 0) ns = FIR_MAX_STAGES;
+        sizes[n++] = ns;
+        done += ns;
+    }
+    return done == ne ? n : -1;
+}
+
+// capacity (samples per frame) the two ping-pong buffers need in the active mode
+void mid_lengths(const zfb_engine *e, bool fast, long long need[2]) {
+    need[0] = need[1] = 0;
+    int b = 0;
+    auto put = [&](long long len) { if (len > need[b]) need[b] = len; b ^= 1; };
+    const int k = e->nstages;
+    if (fast) {
+        int sizes[4];
+        const int n = fast_chain_sizes(k - 1, sizes);
+        int lvl = 0;
+        for (int j = 0; j < n; ++j) { lvl += sizes[j]; put(e->len[lvl]); }
+        put(e->len[k]);
+    } else {
+        for (int s = 0; s < k; ++s) put(e->len[s + 1]);
+    }
+}
+
+int choose_group(const zfb_engine *e, bool fast) {
     if (e->group_user > 0) return e->group_user;
     // enough frames per launch that the late, small stages still fill the GPU
     // (the chain is fp32-bound, not bandwidth-bound: L2 residency of the
     // intermediates is worth less than full waves); bounded to 256 MB of workspace
-    size_t per_frame = 0;
-    if (e->nstages >= 1) per_frame += (size_t)e->len[1] * 8;
-    if (e->nstages >= 2) per_frame += (size_t)e->len[2] * 8;
+    long long need[2];
+    mid_lengths(e, fast, need);
+    size_t per_frame = (size_t)(need[0] + need[1]) * 8;
     if (e->log2N > kMaxLog2Small) per_frame += (size_t)e->nseg * ((size_t)8 << e->log2N);
     if (per_frame == 0) return 2048;
     long long g = (long long)(256ull << 20) / (long long)per_frame;
     if (g < 1) g = 1;
-    if (g > 2048) g = 2048;
+    if (g > 1024) g = 1024;
     if (g > 32) g -= g % 32;              // typical batches (powers of two) split into equal groups
     return (int)g;
 }
@@ -846,28 +894,11 @@ int run_group(zfb_engine *e, const void *d_in, int gf, float *d_rows) {
 // tile sizes; decides whether the frame is long enough for the FAST interior
 int plan_fast(zfb_engine *e) {
     const zfb_config &c = e->cfg;
-    e->fast_active = false;
     e->nchains = 0;
-    if (c.mode != ZFB_MODE_FAST) return ZFB_OK;
+    if (!e->fast_active) return ZFB_OK;
     const int k = e->nstages;
-    if (k < 2) return ZFB_OK;                                  // nothing to replace
-    if (!e->fplan.set || e->fplan.ne != k - 1)
-        return fail(e, ZFB_ESTATE, "mode FAST needs zfb_set_fast_plan with %d stages (got %d)", k - 1,
-                    e->fplan.set ? e->fplan.ne : -1);
-    // strips: i_{k-1} = 2K + D, i_s = 2 i_{s+1} + D, right strip starts at an even position
-    const int K = e->fplan.K;
-    const int D = 320;                 // >= WARM: the artificial strip edge has decayed (0.935^320 = 5e-10)
-    int need = 2 * K + D;
-    for (int s = k - 1; s >= 0; --s) {
-        int i = need;
-        if ((e->len[s] - i) & 1) i += 1;
-        e->strip_len[s] = i;
-        e->strip_q[s] = e->len[s] - i;
-        need = 2 * i + D;
-    }
-    if (e->len[0] < 4 * e->strip_len[0] || e->len[k] < 4 * K) return ZFB_OK;   // too short: EXACT
     e->strip_cap = (e->strip_len[0] + 1) / 2 + 8;
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 2 && k > 4; ++i) {      // only deep zooms run strip stages through global memory
         int rc = ensure(e, e->sbuf[i], (size_t)e->group * 2 * (size_t)e->strip_cap * sizeof(float2));
         if (rc) return rc;
     }
@@ -883,7 +914,7 @@ int plan_fast(zfb_engine *e) {
         FirChainParams &p = e->chain[e->nchains];
         memset(&p, 0, sizeof p);
         // the LAST chain takes up to 3 stages (it has the specialised kernel);
-        // what is left over goes to the first chain
+        // what is left over goes to the first chain (fast_chain_sizes)
         int ns = (ne - done) % FIR_MAX_STAGES;
         if (ns == 0) ns = FIR_MAX_STAGES;
         p.ns = ns;
@@ -922,7 +953,6 @@ int plan_fast(zfb_engine *e) {
         e->chain_smem[e->nchains] = fir_chain_smem(p);
         // register-blocked kernel when the tap set is one it is built for
         e->chain_run[e->nchains] = e->fir_generic ? 0 : fir_run_variant(p);
-        if (getenv("ZFB_DEBUG_PLAN")) fprintf(stderr, "chain %d: ns %d M %d %d %d Mc %d L %d variant %d TO %d\n", e->nchains, p.ns, p.M[0], p.M[1], p.M[2], p.Mc, p.L, e->chain_run[e->nchains], p.TO);
         if (e->chain_run[e->nchains]) {
             FirRunParams &rp = e->runp[e->nchains];
             memset(&rp, 0, sizeof rp);
@@ -942,7 +972,6 @@ int plan_fast(zfb_engine *e) {
         e->chain_level_out[e->nchains] = done;
         e->nchains += 1;
     }
-    e->fast_active = true;
     return ZFB_OK;
 }
 
@@ -1172,20 +1201,25 @@ int zfb_configure(zfb_engine *e, const zfb_config *cfg) {
         for (int i = 0; i < 8; ++i) lo_entry(r, i, amp, p.lo_small[i]);
         for (int it = 0; it < 32; ++it) lo_entry(r, (long long)it * nt * vec, 1.0, p.lo_big[it]);
     }
-    e->group = choose_group(e);
+    if (cfg->mode == ZFB_MODE_FAST && g.nstages >= 2 && (!e->fplan.set || e->fplan.ne != g.nstages - 1))
+        return fail(e, ZFB_ESTATE, "mode FAST needs zfb_set_fast_plan with %d stages (got %d)", g.nstages - 1,
+                    e->fplan.set ? e->fplan.ne : -1);
+    e->fast_active = fast_wanted(e, e->strip_len, e->strip_q);
+    e->group = choose_group(e, e->fast_active);
     plan_tiles(e);
     e->nsplit_cap = 16;
     rc = plan_fast(e);
     if (rc) return rc;
 
     // workspaces
-    if (g.nstages >= 1) {
-        rc = ensure(e, e->mid[0], (size_t)e->group * (size_t)g.len[1] * sizeof(float2));
-        if (rc) return rc;
-    }
-    if (g.nstages >= 2) {
-        rc = ensure(e, e->mid[1], (size_t)e->group * (size_t)g.len[2] * sizeof(float2));
-        if (rc) return rc;
+    {
+        long long need[2];
+        mid_lengths(e, e->fast_active, need);
+        for (int i = 0; i < 2; ++i)
+            if (need[i] > 0) {
+                rc = ensure(e, e->mid[i], (size_t)e->group * (size_t)need[i] * sizeof(float2));
+                if (rc) return rc;
+            }
     }
     rc = ensure(e, e->pow, (size_t)e->group * (size_t)e->nsplit_cap * (size_t)e->W * sizeof(float));
     if (rc) return rc;
