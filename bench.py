@@ -266,13 +266,20 @@ def run_b200(args, w):
     eng.set_stream(stream.cuda_stream)
     W = eng.row_width
 
+    # BASELINE configs[3]: 64 virtual receivers over one stream, channels sharded across ranks
+    centres = None
+    if w.name == "cfg4":
+        from pypanadapter_b200 import dist as zdist
+        mine = zdist.channels_for_rank(64, rank, world)
+        centres = synth.cfg4_centres()[mine.start:mine.stop]
+    nch = 1 if centres is None else len(centres)
     host = synth.make_frames(w, F, distinct=min(F, 8))
     h_in = torch.from_numpy(host.view(np.uint8).reshape(F, -1)).pin_memory()
-    h_rows = torch.empty((F, W), dtype=torch.float32).pin_memory()
+    h_rows = torch.empty((nch * F, W), dtype=torch.float32).pin_memory()
     d_in = h_in.cuda()
     # rows are double-buffered so that the NCCL gather of step k (side stream)
     # overlaps the kernels of step k+1
-    d_rows2 = [torch.empty((F, W), dtype=torch.float32, device="cuda") for _ in range(2)]
+    d_rows2 = [torch.empty((nch * F, W), dtype=torch.float32, device="cuda") for _ in range(2)]
     d_rows = d_rows2[0]
     gather_list = [torch.empty_like(d_rows) for _ in range(world)] if (world > 1 and rank == 0) else None
     comm_stream = torch.cuda.Stream() if world > 1 else None
@@ -295,7 +302,10 @@ def run_b200(args, w):
         step_no[0] += 1
         if world > 1:
             stream.wait_event(gathered[b])          # the gather that last read this buffer
-        eng.process_device(d_in.data_ptr(), F, d_rows2[b].data_ptr())
+        if centres is None:
+            eng.process_device(d_in.data_ptr(), F, d_rows2[b].data_ptr())
+        else:
+            eng.process_channels_device(d_in.data_ptr(), F, centres, d_rows2[b].data_ptr())
         if world > 1:
             gather_async(b)
 
@@ -303,7 +313,10 @@ def run_b200(args, w):
     h_rows_np = h_rows.numpy()
 
     def step_e2e():
-        eng.process(h_in_np, out=h_rows_np)          # H2D + kernels + D2H, returns when rows are on the host
+        if centres is None:                          # H2D + kernels + D2H, returns when rows are on the host
+            eng.process(h_in_np, out=h_rows_np)
+        else:
+            eng.process_channels(h_in_np, centres, out=h_rows_np.reshape(nch, F, W))
         if world > 1:
             b = step_no[0] & 1
             step_no[0] += 1
@@ -362,7 +375,7 @@ def run_b200(args, w):
         tsum = t.clone()
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
         ms, ms_e2e, launches = float(tmax[0]), float(tmax[1]), int(tsum[2])
-    samples_step = world * F * w.frame_len
+    samples_step = world * F * w.frame_len * nch      # cfg4: channel-samples (every channel consumes the stream)
     value = samples_step * args.steps / (ms * 1e-3) / 1e6
     e2e_value = samples_step * e2e_steps / (ms_e2e * 1e-3) / 1e6
 
@@ -374,7 +387,7 @@ def run_b200(args, w):
         top_ms, top_n = prof[top]
         # algorithmic bytes: every input sample read once; the row
         # bytes (4*W, x3 with EMA) belong to the finalize kernel
-        b_in = w.bytes_per_sample
+        b_in = w.bytes_per_sample / nch               # algorithmic: the stream is read once, not once per channel
         if top.startswith("decimate_stage0") or (top == "welch" and w.fft_ratio == 1):
             algo_bytes_total = args.steps * F * w.frame_len * b_in
         elif top.startswith("decimate_stage"):
@@ -401,15 +414,18 @@ def run_b200(args, w):
         cfg["parallelism"] = "frames sharded, %d rank(s), rows gathered to rank 0 over NCCL" % world
         cfg["group_frames"] = args.group or "auto"
         cfg["decim_threads"] = args.decim_threads or "auto"
+        if centres is not None:
+            cfg["channels_per_gpu"] = nch
+            cfg["value_counts"] = "channel-samples: every virtual receiver consumes the whole stream"
         cfg["decimator_mode"] = "fast" if eng.fast_active else "exact"
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": cfg, "rows_per_s": world * F * args.steps / (ms * 1e-3),
+            "config": cfg, "rows_per_s": world * nch * F * args.steps / (ms * 1e-3),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": world * in_bytes,
-                    "d2h_bytes_per_step": world * F * W * 4, "steps": e2e_steps,
+                    "d2h_bytes_per_step": world * nch * F * W * 4, "steps": e2e_steps,
                     "ms_per_step": ms_e2e / e2e_steps},
             "gpu_launches": launches,
             "roofline": roofline,
@@ -431,7 +447,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(synth.WORKLOADS))
-    ap.add_argument("--frames", type=int, default=512, help="frames per step per GPU")
+    ap.add_argument("--frames", type=int, default=None,
+                    help="frames per step per GPU (default: 512 for cfg1/cfg2, 64 for cfg3, 8 for cfg4)")
     ap.add_argument("--group", type=int, default=0, help="frames per launch group (0 = auto)")
     ap.add_argument("--decim-threads", type=int, default=0, help="tuning: 0 auto, 128 or 256")
     ap.add_argument("--mode", default="fast", choices=["exact", "fast"],
@@ -443,6 +460,8 @@ def main():
     if args.warmup < 3:
         args.warmup = 3
     w = synth.WORKLOADS[args.workload]
+    if args.frames is None:
+        args.frames = {"cfg3": 64, "cfg4": 8}.get(w.name, 512)
     if args.impl == "reference":
         return run_reference(args, w)
     return run_b200(args, w)

@@ -151,6 +151,17 @@ int  zfb_process_device(zfb_engine *e, const void *d_in, int nframes,
  */
 int  zfb_process_host(zfb_engine *e, const void *h_in, int nframes,
                       float *h_rows);
+/*
+ * Several virtual receivers over the SAME chunks (BASELINE configs[3]: distinct
+ * zoom centres over one wide stream): channel c runs the configured chain with
+ * the software LO (S:2090) at f_demod[c] Hz instead of cfg.f_demod.  The input
+ * is uploaded / read once per group, rows come back as [nch][nframes][row_width].
+ * Needs fft_ratio >= 2 and ema_alpha < 0 (the EMA state is per engine).
+ */
+int  zfb_process_channels_device(zfb_engine *e, const void *d_in, int nframes,
+                                 const double *f_demod, int nch, float *d_rows);
+int  zfb_process_channels_host(zfb_engine *e, const void *h_in, int nframes,
+                               const double *f_demod, int nch, float *h_rows);
 int  zfb_synchronize(zfb_engine *e);
 
 /* mixed + decimated chunk of the last processed frame group's FIRST frame

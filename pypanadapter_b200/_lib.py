@@ -82,6 +82,8 @@ SYMBOLS = {
     "zfb_set_option": (C.c_int, [_P, C.c_char_p, C.c_longlong]),
     "zfb_process_device": (C.c_int, [_P, _P, C.c_int, _P]),
     "zfb_process_host": (C.c_int, [_P, _P, C.c_int, _P]),
+    "zfb_process_channels_device": (C.c_int, [_P, _P, C.c_int, C.POINTER(C.c_double), C.c_int, _P]),
+    "zfb_process_channels_host": (C.c_int, [_P, _P, C.c_int, C.POINTER(C.c_double), C.c_int, _P]),
     "zfb_synchronize": (C.c_int, [_P]),
     "zfb_debug_read_decimated": (C.c_int, [_P, _P, C.c_int]),
     "zfb_ring_configure": (C.c_int, [_P, C.c_int]),

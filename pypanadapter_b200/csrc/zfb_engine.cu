@@ -975,6 +975,40 @@ int plan_fast(zfb_engine *e) {
     return ZFB_OK;
 }
 
+// point every LO table of the current plan at software-LO frequency f_demod
+// (zfb_process_channels_*: one configuration, many zoom centres)
+void apply_lo(zfb_engine *e, double f_demod) {
+    const zfb_config &c = e->cfg;
+    const bool no_lo = (c.flags & ZFB_FLAG_NO_LO) != 0;
+    double r = no_lo ? 0.0 : f_demod / c.fs;
+    r -= floor(r);
+    if (r >= 1.0) r = 0.0;
+    const double scaled = ldexp(r, 64);
+    const unsigned long long inc = (scaled >= 18446744073709551615.0) ? 0ull : (unsigned long long)scaled;
+    const int vec = (c.dtype == ZFB_DTYPE_U8) ? 8 : 2;
+    DecimConst dc;
+    build_decim_const(dc);
+    const double amp0 = no_lo ? 1.0 : sqrt(2.0);
+    for (int v = 0; v < 2; ++v) {
+        const int nt = v == 0 ? NTHR_BIG : NTHR_SMALL;
+        StageParams &p = e->sp0[v];
+        p.phase_inc = inc;
+        for (int i = 0; i < 8; ++i) lo_entry(r, i, amp0 * (double)dc.g, p.lo_small[i]);
+        for (int it = 0; it < 32; ++it) lo_entry(r, (long long)it * nt * vec, 1.0, p.lo_big[it]);
+    }
+    if (e->fast_active && e->nchains > 0) {
+        FirChainParams &p = e->chain[0];
+        p.phase_inc = inc;
+        for (int i = 0; i < 8; ++i) lo_entry(r, i, amp0, p.lo_small[i]);
+        for (int it = 0; it < 32; ++it) lo_entry(r, (long long)it * FIR_NT * vec, 1.0, p.lo_big[it]);
+        if (e->chain_run[0]) {
+            FirRunParams &rp = e->runp[0];
+            rp.phase_inc = inc;
+            for (int i = 0; i < RUN0; ++i) lo_entry(r, i, amp0, rp.lo_run[i]);
+        }
+    }
+}
+
 bool is_pinned(const void *p) {
     cudaPointerAttributes a;
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
@@ -1327,36 +1361,68 @@ int zfb_reset_ema(zfb_engine *e) {
     return ZFB_OK;
 }
 
-int zfb_process_device(zfb_engine *e, const void *d_in, int nframes, float *d_rows) {
-    if (!e) return ZFB_EINVAL;
-    std::lock_guard<std::mutex> lk(e->mu);
-    if (!e->configured) return fail(e, ZFB_ESTATE, "process: engine is not configured");
-    if (!d_in || nframes < 0) return fail(e, ZFB_EINVAL, "process: bad arguments");
-    CK(e, cudaSetDevice(e->device));
-    const size_t fbytes = (size_t)e->cfg.frame_len * sample_bytes(e->cfg);
-    for (int g0 = 0; g0 < nframes; g0 += e->group) {
-        const int gf = (nframes - g0 < e->group) ? nframes - g0 : e->group;
-        int rc = run_group(e, (const char *)d_in + (size_t)g0 * fbytes, gf,
-                           d_rows ? d_rows + (size_t)g0 * e->W : nullptr);
-        if (rc) return rc;
-    }
+static int check_channels(zfb_engine *e, const double *f_demod, int nch) {
+    if (nch < 0 || (nch > 0 && !f_demod)) return fail(e, ZFB_EINVAL, "channels: bad arguments");
+    if (nch > 0 && e->cfg.ema_alpha >= 0.0)
+        return fail(e, ZFB_EINVAL, "channels: EMA state is per engine; configure with ema_alpha < 0");
+    if (nch > 0 && e->nstages == 0)
+        return fail(e, ZFB_EINVAL, "channels: fft_ratio 1 has no software LO");
     return ZFB_OK;
 }
 
-int zfb_process_host(zfb_engine *e, const void *h_in, int nframes, float *h_rows) {
+// nch == 0: the configured f_demod; rows [nframes][W].  nch > 0: rows [nch][nframes][W]
+static int process_device_impl(zfb_engine *e, const void *d_in, int nframes, const double *f_demod, int nch,
+                               float *d_rows) {
+    if (!e->configured) return fail(e, ZFB_ESTATE, "process: engine is not configured");
+    if (!d_in || nframes < 0) return fail(e, ZFB_EINVAL, "process: bad arguments");
+    int rc = check_channels(e, f_demod, nch);
+    if (rc) return rc;
+    CK(e, cudaSetDevice(e->device));
+    const size_t fbytes = (size_t)e->cfg.frame_len * sample_bytes(e->cfg);
+    const int loops = nch > 0 ? nch : 1;
+    for (int g0 = 0; g0 < nframes; g0 += e->group) {
+        const int gf = (nframes - g0 < e->group) ? nframes - g0 : e->group;
+        for (int ch = 0; ch < loops; ++ch) {          // channels innermost: the group's input stays in L2
+            if (nch > 0) apply_lo(e, f_demod[ch]);
+            rc = run_group(e, (const char *)d_in + (size_t)g0 * fbytes, gf,
+                           d_rows ? d_rows + ((size_t)ch * nframes + g0) * e->W : nullptr);
+            if (rc) break;
+        }
+        if (rc) break;
+    }
+    if (nch > 0) apply_lo(e, e->cfg.f_demod);
+    return rc;
+}
+
+int zfb_process_device(zfb_engine *e, const void *d_in, int nframes, float *d_rows) {
     if (!e) return ZFB_EINVAL;
     std::lock_guard<std::mutex> lk(e->mu);
+    return process_device_impl(e, d_in, nframes, nullptr, 0, d_rows);
+}
+
+int zfb_process_channels_device(zfb_engine *e, const void *d_in, int nframes, const double *f_demod, int nch,
+                                float *d_rows) {
+    if (!e) return ZFB_EINVAL;
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (nch < 1) return fail(e, ZFB_EINVAL, "channels: nch must be >= 1");
+    return process_device_impl(e, d_in, nframes, f_demod, nch, d_rows);
+}
+
+static int process_host_impl(zfb_engine *e, const void *h_in, int nframes, const double *f_demod, int nch,
+                             float *h_rows) {
     if (!e->configured) return fail(e, ZFB_ESTATE, "process: engine is not configured");
     if (!h_in || !h_rows || nframes < 0) return fail(e, ZFB_EINVAL, "process: bad arguments");
+    int rc = check_channels(e, f_demod, nch);
+    if (rc) return rc;
     if (nframes == 0) return ZFB_OK;
     CK(e, cudaSetDevice(e->device));
+    const int loops = nch > 0 ? nch : 1;
     const size_t fbytes = (size_t)e->cfg.frame_len * sample_bytes(e->cfg);
     // host path pipelines in sub-groups so that copies overlap compute
     int hg = e->group;
     if (nframes > 1 && hg > (nframes + 3) / 4) hg = (nframes + 3) / 4;
     if (hg < 1) hg = 1;
     const bool pinned_src = is_pinned(h_in);
-    int rc;
     for (int i = 0; i < 2; ++i) {
         rc = ensure(e, e->stage_in[i], (size_t)hg * fbytes);
         if (rc) return rc;
@@ -1368,7 +1434,7 @@ int zfb_process_host(zfb_engine *e, const void *h_in, int nframes, float *h_rows
             e->h_stage_cap[i] = (size_t)hg * fbytes;
         }
     }
-    const size_t rows_bytes = (size_t)nframes * e->W * sizeof(float);
+    const size_t rows_bytes = (size_t)loops * nframes * e->W * sizeof(float);
     rc = ensure(e, e->rows_tmp, rows_bytes);
     if (rc) return rc;
     const bool pinned_dst = is_pinned(h_rows);
@@ -1381,7 +1447,7 @@ int zfb_process_host(zfb_engine *e, const void *h_in, int nframes, float *h_rows
     }
 
     int it = 0;
-    for (int g0 = 0; g0 < nframes; g0 += hg, ++it) {
+    for (int g0 = 0; g0 < nframes && rc == ZFB_OK; g0 += hg, ++it) {
         const int gf = (nframes - g0 < hg) ? nframes - g0 : hg;
         const int slot = it & 1;
         const char *src = (const char *)h_in + (size_t)g0 * fbytes;
@@ -1400,15 +1466,19 @@ int zfb_process_host(zfb_engine *e, const void *h_in, int nframes, float *h_rows
         CK(e, cudaEventRecord(e->ev_h2d[slot], e->copy_stream));
         CK(e, cudaStreamWaitEvent(e->stream, e->ev_h2d[slot], 0));
         e->counters[3] += bytes;
-        for (int q0 = 0; q0 < gf; q0 += e->group) {
+        for (int q0 = 0; q0 < gf && rc == ZFB_OK; q0 += e->group) {
             const int qf = (gf - q0 < e->group) ? gf - q0 : e->group;
-            rc = run_group(e, (const char *)e->stage_in[slot].p + (size_t)q0 * fbytes, qf,
-                           (float *)e->rows_tmp.p + (size_t)(g0 + q0) * e->W);
-            if (rc) return rc;
+            for (int ch = 0; ch < loops && rc == ZFB_OK; ++ch) {
+                if (nch > 0) apply_lo(e, f_demod[ch]);
+                rc = run_group(e, (const char *)e->stage_in[slot].p + (size_t)q0 * fbytes, qf,
+                               (float *)e->rows_tmp.p + ((size_t)ch * nframes + g0 + q0) * e->W);
+            }
         }
         CK(e, cudaEventRecord(e->ev_free[slot], e->stream));
         e->slot_busy[slot] = true;
     }
+    if (nch > 0) apply_lo(e, e->cfg.f_demod);
+    if (rc) return rc;
     float *dst = pinned_dst ? h_rows : e->h_rows;
     CK(e, cudaMemcpyAsync(dst, e->rows_tmp.p, rows_bytes, cudaMemcpyDeviceToHost, e->stream));
     CK(e, cudaStreamSynchronize(e->stream));
@@ -1416,6 +1486,20 @@ int zfb_process_host(zfb_engine *e, const void *h_in, int nframes, float *h_rows
     e->counters[4] += rows_bytes;
     e->slot_busy[0] = e->slot_busy[1] = false;
     return ZFB_OK;
+}
+
+int zfb_process_host(zfb_engine *e, const void *h_in, int nframes, float *h_rows) {
+    if (!e) return ZFB_EINVAL;
+    std::lock_guard<std::mutex> lk(e->mu);
+    return process_host_impl(e, h_in, nframes, nullptr, 0, h_rows);
+}
+
+int zfb_process_channels_host(zfb_engine *e, const void *h_in, int nframes, const double *f_demod, int nch,
+                              float *h_rows) {
+    if (!e) return ZFB_EINVAL;
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (nch < 1) return fail(e, ZFB_EINVAL, "channels: nch must be >= 1");
+    return process_host_impl(e, h_in, nframes, f_demod, nch, h_rows);
 }
 
 int zfb_synchronize(zfb_engine *e) {

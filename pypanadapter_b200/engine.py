@@ -251,6 +251,30 @@ class ZoomPSD:
                                                C.c_void_p(out.ctypes.data)), "zfb_process_host")
         return out
 
+    def process_channels(self, frames, f_demod, out=None) -> np.ndarray:
+        """Several virtual receivers (zoom centres ``f_demod[c]`` Hz) over the
+        same frames, uploaded once: rows (nch, nframes, W) float32."""
+        if self._key is None:
+            raise ZoomFFTError(_lib.ZFB_ESTATE, "process: engine is not configured")
+        a = self._as_wire(frames)
+        f = np.ascontiguousarray(f_demod, dtype=np.float64).ravel()
+        n = a.shape[0]
+        shape = (len(f), n, self.row_width)
+        if out is None:
+            out = np.empty(shape, dtype=np.float32)
+        elif out.dtype != np.float32 or out.shape != shape or not out.flags.c_contiguous:
+            raise ValueError("out must be C-contiguous float32 of shape %r" % (shape,))
+        self._check(self._lib.zfb_process_channels_host(
+            self._h, C.c_void_p(a.ctypes.data), n, f.ctypes.data_as(C.POINTER(C.c_double)), len(f),
+            C.c_void_p(out.ctypes.data)), "zfb_process_channels_host")
+        return out
+
+    def process_channels_device(self, d_in_ptr: int, nframes: int, f_demod, d_rows_ptr: int):
+        f = np.ascontiguousarray(f_demod, dtype=np.float64).ravel()
+        self._check(self._lib.zfb_process_channels_device(
+            self._h, C.c_void_p(d_in_ptr), int(nframes), f.ctypes.data_as(C.POINTER(C.c_double)), len(f),
+            C.c_void_p(d_rows_ptr)), "zfb_process_channels_device")
+
     def process_device(self, d_in_ptr: int, nframes: int, d_rows_ptr: int | None = None):
         """DEVICE pointers in/out (asynchronous; rows also land in the ring)."""
         self._check(self._lib.zfb_process_device(self._h, C.c_void_p(d_in_ptr), int(nframes),

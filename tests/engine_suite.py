@@ -255,3 +255,33 @@ def fast_generic_fir_kernel(engine):
     finally:
         engine.set_option("fir_generic", 0)
         engine._key = None
+
+
+def multi_channel(engine):
+    """BASELINE configs[3] in small: virtual receivers with distinct zoom centres
+    over the same frames (process_channels) == one configure+process per centre,
+    bit for bit, and each meets parity against the oracle."""
+    fs, N, R = 20e6, 1024, 16
+    n = N * R * 6
+    centres = np.array([-9.5e6, -3.1e6, 1.0, 4.44e6, 9.5e6])
+    k = np.arange(n)
+    rng = np.random.default_rng(21)
+    x = 1e-3 * (rng.standard_normal((2, n)) + 1j * rng.standard_normal((2, n)))
+    for fc in centres:
+        x = x + 0.1 * np.exp(2j * np.pi * ((fc + 7000.0) / fs) * k)
+    x = x.astype(np.complex64)
+    for mode in ("fast", "exact"):
+        engine.configure(fs, N, R, n, "hamming", crop="thread", mode=mode)
+        rows = engine.process_channels(x, centres)
+        assert rows.shape == (len(centres), 2, engine.row_width)
+        floor = parity.floor_db20(fs, "hamming", N, True)
+        for c, fc in enumerate(centres):
+            engine.configure(fs, N, R, n, "hamming", f_demod=float(fc), crop="thread", mode=mode)
+            one = engine.process(x)
+            assert np.array_equal(one, rows[c]), (mode, c)
+            want = zo.zoom_psd(x[1], fs, N, R, "hamming", f_demod=float(fc), crop="thread")
+            parity.assert_row_parity(rows[c, 1], want, floor, "channel %d %s" % (c, mode))
+            engine.configure(fs, N, R, n, "hamming", crop="thread", mode=mode)
+    engine.configure(fs, N, R, n, "hamming", crop="thread", ema_alpha=0.3)
+    with pytest.raises(ZoomFFTError):
+        engine.process_channels(x, centres)

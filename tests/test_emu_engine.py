@@ -103,3 +103,7 @@ def test_fast_strong_out_of_band(emu_engine):
 
 def test_fast_generic_fir_kernel(emu_engine):
     es.fast_generic_fir_kernel(emu_engine)
+
+
+def test_multi_channel(emu_engine):
+    es.multi_channel(emu_engine)

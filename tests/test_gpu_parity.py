@@ -179,3 +179,7 @@ def test_fast_strong_out_of_band(gpu_engine):
 
 def test_fast_generic_fir_kernel(gpu_engine):
     es.fast_generic_fir_kernel(gpu_engine)
+
+
+def test_multi_channel(gpu_engine):
+    es.multi_channel(gpu_engine)
