@@ -285,3 +285,40 @@ def multi_channel(engine):
     engine.configure(fs, N, R, n, "hamming", crop="thread", ema_alpha=0.3)
     with pytest.raises(ZoomFFTError):
         engine.process_channels(x, centres)
+
+
+def random_configs(engine, seed, count):
+    """Seeded sweep over frame length (ragged/odd), N, R, window, wire dtype, flip,
+    crop, f_demod and decimator mode against the oracle."""
+    rng = np.random.default_rng(seed)
+    windows = ["hamming", "hann", "boxcar", "blackmanharris", ("kaiser", 8.6), ("tukey", 0.5), "flattop"]
+    for it in range(count):
+        N = int(2 ** rng.integers(5, 12))
+        R = int(2 ** rng.integers(0, 6))
+        segs = int(rng.integers(2, 9))
+        n = int(N * R * (segs + 1) // 2 + rng.integers(0, 2 * R + 3))
+        if R > 1:
+            n = max(n, 28 * R + 5)
+        dtype = "u8" if rng.random() < 0.3 else "c64"
+        flip = bool(rng.random() < 0.4)
+        window = windows[int(rng.integers(len(windows)))]
+        crop = [None, "thread", int(2 * rng.integers(1, N // 2 + 1))][int(rng.integers(3))]
+        if crop == "thread" and N < 2 * R:
+            crop = None                     # the reference's slice would be empty (W = 0): rejected here
+        f_demod = 1.0 if rng.random() < 0.5 else float(rng.uniform(-0.5, 0.5) * 1e6)
+        mode = "fast" if rng.random() < 0.6 else "exact"
+        fs = 1e6
+        k = np.arange(n)
+        ftone = f_demod + rng.uniform(-0.3, 0.3) * fs / R / max(1, R if crop == "thread" else 1)
+        x = 0.45 * np.exp(2j * np.pi * ftone / fs * k) + 0.2 * np.exp(2j * np.pi * rng.uniform(-0.5, 0.5) * k)
+        x = x + 5e-3 * (rng.standard_normal(n) + 1j * rng.standard_normal(n))
+        wire = synth.quantise_u8(x * 0.9) if dtype == "u8" else x.astype(np.complex64)
+        what = "case %d: N=%d R=%d n=%d %s flip=%s win=%s crop=%s f=%g %s" % (
+            it, N, R, n, dtype, flip, window, crop, f_demod, mode)
+        engine.configure(fs, N, R, n, window, dtype=dtype, flip=flip, f_demod=f_demod, crop=crop, mode=mode)
+        row = engine.process(wire)[0].astype(np.float64)
+        want = zo.zoom_psd(wire, fs, N, R, window, f_demod=f_demod, crop=crop, flip=flip)
+        floor = parity.floor_db20(fs, window, engine.geometry["nperseg"], R > 1)
+        # single- and few-segment rows: fp32 holds 0.01 dB20 only within ~85 dB of the row's peak (DESIGN 4)
+        floor = max(floor, want.max() - 170.0)
+        parity.assert_row_parity(row, want, floor, what)

@@ -107,3 +107,8 @@ def test_fast_generic_fir_kernel(emu_engine):
 
 def test_multi_channel(emu_engine):
     es.multi_channel(emu_engine)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_random_configs(emu_engine, seed):
+    es.random_configs(emu_engine, seed, 12)

@@ -183,3 +183,8 @@ def test_fast_generic_fir_kernel(gpu_engine):
 
 def test_multi_channel(gpu_engine):
     es.multi_channel(gpu_engine)
+
+
+@pytest.mark.parametrize("seed", [11, 12, 13, 14])
+def test_random_configs(gpu_engine, seed):
+    es.random_configs(gpu_engine, seed, 25)
