@@ -39,6 +39,7 @@ struct BigParams {
     const float2 *winfft;      // N entries FFT(window)
     float2       *scratch;     // [frames][nseg][N]  (k1-major)
     float2       *partial;     // [frames][nseg][ntiles_col] raw sums
+    float2       *means;       // [frames][nseg] segment means
     int           W;
     float        *pow_out;     // [frames][nsplit][W]
 };
@@ -113,15 +114,24 @@ __global__ void __launch_bounds__(BIG_THREADS) bigfft_col_kernel(const BigParams
     }
 }
 
+// segment means from the column pass's per-tile raw sums (fixed summation order)
+__global__ void bigfft_mean_kernel(const BigParams p, int nsegs_total) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nsegs_total) return;
+    const float2 *src = p.partial + (size_t)i * p.ntiles_col;
+    float2 s = make_float2(0.f, 0.f);
+    for (int t = 0; t < p.ntiles_col; ++t) s = cadd(s, src[t]);
+    const float inv_n = 1.0f / (float)(1 << p.log2N);
+    p.means[i] = make_float2(s.x * inv_n, s.y * inv_n);
+}
+
 template <int LM>
-__global__ void __launch_bounds__(BIG_THREADS) bigfft_row_kernel(const BigParams p) {
+__global__ void __launch_bounds__(BIG_THREADS, 2) bigfft_row_kernel(const BigParams p) {
     constexpr int M = 1 << LM;            // N2
     constexpr int RR = BIG_TILE / M;      // rows (k1 values) per tile
     constexpr int S = big_stride(M);
     ZFB_DYN_SMEM(smem_raw);
     float2 *sm = reinterpret_cast<float2 *>(smem_raw);
-    __shared__ float2 red[33];
-
     const int t = threadIdx.x;
     const int r = t / (M / 8), j = t % (M / 8);
     const int tile = blockIdx.x, split = blockIdx.y, frame = blockIdx.z;
@@ -136,7 +146,6 @@ __global__ void __launch_bounds__(BIG_THREADS) bigfft_row_kernel(const BigParams
         wf[q] = __ldg(p.winfft + k1 + ((j + q * (M / 8)) << log2N1));
         acc[q] = 0.f;
     }
-    const float inv_n = 1.0f / (float)N;
     const int s_begin = split * p.seg_per_split;
     const int s_end = min(p.nseg, s_begin + p.seg_per_split);
     for (int s = s_begin; s < s_end; ++s) {
@@ -145,9 +154,7 @@ __global__ void __launch_bounds__(BIG_THREADS) bigfft_row_kernel(const BigParams
         float2 v[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) v[q] = y[j + q * (M / 8)];
-        float2 ps = (t < p.ntiles_col) ? p.partial[seg * p.ntiles_col + t] : make_float2(0.f, 0.f);
-        ps = block_sum<BIG_THREADS>(ps, t, red);
-        const float2 mean = make_float2(ps.x * inv_n, ps.y * inv_n);
+        const float2 mean = __ldg(p.means + seg);
         sub_fft<LM>(v, j, sm + r * S, p.twiddle, p.log2N);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
@@ -186,7 +193,7 @@ inline int big_ntiles_col(int log2N) {
 }
 
 inline size_t big_scratch_bytes(int log2N, int nseg, int frames) {
-    return (size_t)frames * (size_t)nseg * (((size_t)1 << log2N) + (size_t)big_ntiles_col(log2N)) * sizeof(float2);
+    return (size_t)frames * (size_t)nseg * (((size_t)1 << log2N) + (size_t)big_ntiles_col(log2N) + 1) * sizeof(float2);
 }
 
 template <int LM1>
@@ -217,6 +224,8 @@ inline void big_run_col(const BigParams &p, int kind, int frames, cudaStream_t s
 inline void big_run_row(const BigParams &p, int frames, cudaStream_t st) {
     int lm1, lm2;
     big_split(p.log2N, lm1, lm2);
+    const int nsegs_total = frames * p.nseg;
+    ZFB_LAUNCH(bigfft_mean_kernel, dim3((unsigned)((nsegs_total + 127) / 128)), dim3(128), 0, st, p, nsegs_total);
     const int rr = BIG_TILE >> lm2;
     dim3 grow((unsigned)((1 << lm1) / rr), (unsigned)p.nsplit, (unsigned)frames);
     switch (lm2) {

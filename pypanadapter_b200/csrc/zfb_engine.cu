@@ -499,9 +499,13 @@ int choose_group(const zfb_engine *e, bool fast) {
     long long need[2];
     mid_lengths(e, fast, need);
     size_t per_frame = (size_t)(need[0] + need[1]) * 8;
-    if (e->log2N > kMaxLog2Small) per_frame += (size_t)e->nseg * ((size_t)8 << e->log2N);
+    size_t budget = 256ull << 20;
+    if (e->log2N > kMaxLog2Small) {
+        per_frame += (size_t)e->nseg * ((size_t)8 << e->log2N);       // four-step scratch
+        budget = 512ull << 20;
+    }
     if (per_frame == 0) return 2048;
-    long long g = (long long)(256ull << 20) / (long long)per_frame;
+    long long g = (long long)budget / (long long)per_frame;
     if (g < 1) g = 1;
     if (g > 1024) g = 1024;
     if (g > 32) g -= g % 32;              // typical batches (powers of two) split into equal groups
@@ -846,6 +850,7 @@ int run_group(zfb_engine *e, const void *d_in, int gf, float *d_rows) {
         b.winfft = (const float2 *)e->winfft.p;
         b.scratch = (float2 *)e->big.p;
         b.partial = b.scratch + ((size_t)e->group * (size_t)e->nseg << e->log2N);
+        b.means = b.partial + (size_t)e->group * (size_t)e->nseg * (size_t)b.ntiles_col;
         b.W = e->W;
         b.pow_out = (float *)e->pow.p;
         const int pr = prof_begin(e, 16);
@@ -854,7 +859,7 @@ int run_group(zfb_engine *e, const void *d_in, int gf, float *d_rows) {
         const int pr2 = prof_begin(e, 17);
         big_run_row(b, gf, st);
         prof_end(e, pr2);
-        e->counters[2] += 2;
+        e->counters[2] += 3;
     }
 
     FinalizeParams f{};
