@@ -39,6 +39,15 @@ struct DecimConst {
     float Mp[JTERMS][NSTATE][NSTATE];    // Mp[j] = (state transition over BLK)^j
 };
 
+// per-channel software-LO tables of the channel-batched launches
+// (zfb_process_channels_*: many zoom centres over the same frames in one grid)
+struct ChannelLo {
+    unsigned long long phase_inc;   // frac(f_demod/fs) * 2^64
+    float2 run[32];                 // fir_run_kernel: sqrt(2) * exp(-2 pi i f/fs j)
+    float2 dec_small[8];            // exact stage 0 / strips: sqrt(2) g^2 exp(-2 pi i f/fs v)
+    float2 dec_big[32];             // exp(-2 pi i f/fs * it*128*VEC)
+};
+
 // packed fp32x2 arithmetic (Blackwell FFMA2/FADD2/FMUL2): re and im of a
 // sample share every real filter coefficient, so one issue slot does both.
 __device__ __forceinline__ float2 pk_fma(float a, float2 x, float2 y) {

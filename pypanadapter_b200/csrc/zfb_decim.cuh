@@ -50,6 +50,8 @@ struct StageParams {
     int         pos_off;       // raw kinds: absolute position of side 1's sample 0 (LO phase, flip)
     int         Lfull;         // raw kinds: length of the whole frame (flip index); L otherwise
     int         w_lo[2], w_hi[2];   // outputs [w_lo, w_hi) of a side are written
+    const ChannelLo *chan;     // channel-batched launches: LO tables per channel, else null
+    int         chan_frames;   // frames per channel in this launch (batch b = ch*chan_frames + frame)
     float2      lo_small[8];   // sqrt(2)*g*exp(-2pi i f/fs v), v = 0..7
     float2      lo_big[32];    // exp(-2pi i f/fs * it*NT*VEC)
 };
@@ -271,17 +273,19 @@ __device__ __forceinline__ float2 u8pair_to_iq(unsigned int word, int hi) {
     return __ffma2_rn(f, make_float2(1.0f / 127.5f, 1.0f / 127.5f), make_float2(-1.0f, -1.0f));
 }
 
-template <int KIND, int NT>
+template <int KIND, int NT, bool CHAN = false>
 __device__ __forceinline__ void load_region(float2 *buf, const StageParams &p,
-                                            const char *frame_in, int rs, int tid, int posoff) {
+                                            const char *frame_in, int rs, int tid, int posoff, int ch = 0) {
     constexpr int VEC = (KIND == KIND_U8_RAW) ? 8 : 2;
     constexpr int ITERS = BLK / VEC;
     constexpr int CH = 8;
     const int L = p.L;
     const bool fl = (KIND != KIND_C64_MID) && p.flip;
     float2 b0 = make_float2(1.f, 0.f);
+    const ChannelLo *cl = CHAN ? p.chan + ch : nullptr;
     if (KIND != KIND_C64_MID)
-        b0 = lo_phasor((long long)rs + (long long)posoff + (long long)tid * VEC, p.phase_inc);
+        b0 = lo_phasor((long long)rs + (long long)posoff + (long long)tid * VEC,
+                       CHAN ? cl->phase_inc : p.phase_inc);
     const float g = c_dec.g;
     const size_t esz = (KIND == KIND_U8_RAW) ? 2 : 8;
     const int Lf = p.Lfull;               // raw kinds index the whole frame: element = posoff + pos
@@ -339,9 +343,10 @@ __device__ __forceinline__ void load_region(float2 *buf, const StageParams &p,
 #pragma unroll
                 for (int e = 0; e < VEC; ++e) v[e] = pk_mul(g, v[e]);
             } else {
-                const float2 bi = cmul(b0, p.lo_big[it]);
+                const float2 bi = cmul(b0, CHAN ? cl->dec_big[it] : p.lo_big[it]);
 #pragma unroll
-                for (int e = 0; e < VEC; ++e) v[e] = cmul(v[e], cmul(bi, p.lo_small[e]));
+                for (int e = 0; e < VEC; ++e)
+                    v[e] = cmul(v[e], cmul(bi, CHAN ? cl->dec_small[e] : p.lo_small[e]));
             }
             const int s0 = sidx(q);           // VEC consecutive samples share a block
 #pragma unroll
@@ -492,7 +497,7 @@ struct StripParams {
     int   ndec;                // decimated chunk length
 };
 
-template <int KIND>
+template <int KIND, bool CHAN = false>
 __global__ void __launch_bounds__(NTHR_SMALL, 3) strip_cascade_kernel(const StripParams sp) {
     constexpr int NT = NTHR_SMALL;
     ZFB_DYN_SMEM(smem_raw);
@@ -500,14 +505,16 @@ __global__ void __launch_bounds__(NTHR_SMALL, 3) strip_cascade_kernel(const Stri
     float2 *zbuf = buf + NT * BLK_PAD;
     const int tid = threadIdx.x;
     const int side = blockIdx.x;
-    const int frame = blockIdx.y;
+    const int frame = blockIdx.y;                      // output (batch) index
     const StageParams &p = sp.st;
+    const int ch = CHAN ? frame / p.chan_frames : 0;
+    const int in_frame = CHAN ? frame % p.chan_frames : frame;
     const size_t esz = (KIND == KIND_U8_RAW) ? 2 : 8;
     const char *frame_in = (const char *)p.in +
-                           ((size_t)frame * (size_t)p.in_stride + (size_t)side * (size_t)p.side_in_off) * esz;
+                           ((size_t)in_frame * (size_t)p.in_stride + (size_t)side * (size_t)p.side_in_off) * esz;
     const int rs = -WARM;
 
-    load_region<KIND, NT>(buf, p, frame_in, rs, tid, (KIND != KIND_C64_MID && side) ? p.pos_off : 0);
+    load_region<KIND, NT, CHAN>(buf, p, frame_in, rs, tid, (KIND != KIND_C64_MID && side) ? p.pos_off : 0, ch);
     __syncthreads();
     const float g = c_dec.g;
     for (int s = 0; s < sp.nstages; ++s) {

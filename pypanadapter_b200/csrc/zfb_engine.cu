@@ -101,6 +101,11 @@ struct zfb_engine {
     int strip_cap = 0;
     DevBuf sbuf[2];
     int final_buf = 0;                 // mid[] index holding the decimated chunk of the last group
+    // channel-batched launch in flight (zfb_process_channels_*): 0 = off
+    int cur_nch = 0, cur_chan_frames = 0;
+    long long cur_row_stride = 0;
+    DevBuf chan_dev;
+    std::vector<ChannelLo> chan_host;
 
     // pinned sample ring + double-buffered device mirror
     void   *sr_host = nullptr;
@@ -432,6 +437,10 @@ int setup_device_once(zfb_engine *e) {
                                (int)decim_smem(NTHR_SMALL)));
     CK(e, cudaFuncSetAttribute(strip_cascade_kernel<KIND_C64_MID>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)decim_smem(NTHR_SMALL)));
+    CK(e, cudaFuncSetAttribute((strip_cascade_kernel<KIND_U8_RAW, true>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)decim_smem(NTHR_SMALL)));
+    CK(e, cudaFuncSetAttribute((strip_cascade_kernel<KIND_C64_RAW, true>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)decim_smem(NTHR_SMALL)));
     for (int kind = 0; kind < 3; ++kind)
         CK(e, cudaFuncSetAttribute(chain_lookup_fn(kind), cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     int rc = fir_run_setup_kind<KIND_C64_RAW>(e);
@@ -561,7 +570,12 @@ void launch_fir_run_kind(int variant, const FirRunParams &rp, int L_out, int gf,
         using SH = FirRunShape<NS, A, B, C, D>;                                                   \
         const int per_tile = SH::SPAN >> NS;                                                      \
         const unsigned tiles = (unsigned)((L_out + per_tile - 1) / per_tile);                     \
-        ZFB_LAUNCH((fir_run_kernel<K, NS, A, B, C, D>), dim3(tiles, (unsigned)gf), dim3(FIR_NT), SH::SMEM, st, rp); \
+        if (K != KIND_C64_MID && rp.chan) {                                                       \
+            ZFB_LAUNCH((fir_run_kernel<K, NS, A, B, C, D, (K != KIND_C64_MID)>), dim3(tiles, (unsigned)gf), \
+                       dim3(FIR_NT), SH::SMEM, st, rp);                                           \
+        } else {                                                                                  \
+            ZFB_LAUNCH((fir_run_kernel<K, NS, A, B, C, D>), dim3(tiles, (unsigned)gf), dim3(FIR_NT), SH::SMEM, st, rp); \
+        }                                                                                         \
         return;                                                                                   \
     }
     ZFB_RUN_COMBOS(ZFB_X, KIND)
@@ -587,7 +601,10 @@ template <int KIND>
 int fir_run_setup_kind(zfb_engine *e) {
 #define ZFB_X(ID, K, NS, A, B, C, D)                                                              \
     CK(e, cudaFuncSetAttribute((fir_run_kernel<K, NS, A, B, C, D>), cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                               (int)FirRunShape<NS, A, B, C, D>::SMEM));
+                               (int)FirRunShape<NS, A, B, C, D>::SMEM));                          \
+    if (K != KIND_C64_MID)                                                                        \
+        CK(e, cudaFuncSetAttribute((fir_run_kernel<K, NS, A, B, C, D, (K != KIND_C64_MID)>),      \
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FirRunShape<NS, A, B, C, D>::SMEM));
     ZFB_RUN_COMBOS(ZFB_X, KIND)
 #undef ZFB_X
     return ZFB_OK;
@@ -635,6 +652,10 @@ void run_decimation_fast(zfb_engine *e, const void *d_in, int gf, int *out_buf) 
             rp.in_stride = p.in_stride;
             rp.out = p.out;
             rp.out_stride = p.out_stride;
+            if (j == 0 && e->cur_nch > 0) {
+                rp.chan = (const ChannelLo *)e->chan_dev.p;
+                rp.chan_frames = e->cur_chan_frames;
+            }
             launch_fir_run(e->chain_run[j], kind, rp, e->len[lvl], gf, st);
         } else {
             const unsigned tiles = (unsigned)((e->len[lvl] + p.TO - 1) / p.TO);
@@ -736,7 +757,15 @@ void run_decimation_fast(zfb_engine *e, const void *d_in, int gf, int *out_buf) 
         sp.ndec = e->len[k];
         const int pr = prof_begin(e, 15);
         const dim3 grid(2, (unsigned)gf);
-        if (skind == KIND_U8_RAW) {
+        if (e->cur_nch > 0 && s0 == 0) {
+            sp.st.chan = (const ChannelLo *)e->chan_dev.p;
+            sp.st.chan_frames = e->cur_chan_frames;
+            if (skind == KIND_U8_RAW) {
+                ZFB_LAUNCH((strip_cascade_kernel<KIND_U8_RAW, true>), grid, dim3(NTHR_SMALL), decim_smem(NTHR_SMALL), st, sp);
+            } else {
+                ZFB_LAUNCH((strip_cascade_kernel<KIND_C64_RAW, true>), grid, dim3(NTHR_SMALL), decim_smem(NTHR_SMALL), st, sp);
+            }
+        } else if (skind == KIND_U8_RAW) {
             ZFB_LAUNCH(strip_cascade_kernel<KIND_U8_RAW>, grid, dim3(NTHR_SMALL), decim_smem(NTHR_SMALL), st, sp);
         } else if (skind == KIND_C64_RAW) {
             ZFB_LAUNCH(strip_cascade_kernel<KIND_C64_RAW>, grid, dim3(NTHR_SMALL), decim_smem(NTHR_SMALL), st, sp);
@@ -876,6 +905,8 @@ int run_group(zfb_engine *e, const void *d_in, int gf, float *d_rows) {
     f.ring = (float *)e->ring.p;
     f.ring_pos = (long long)(e->ring_written % e->ring_rows);
     f.ring_rows = e->ring_rows;
+    f.chan_frames = e->cur_nch > 0 ? e->cur_chan_frames : 0;
+    f.chan_row_stride = e->cur_row_stride;
     const int prf = prof_begin(e, 18);
     const long long cells = (long long)gf * e->W;
     ZFB_LAUNCH(reduce_rows_kernel, dim3((unsigned)((cells + 255) / 256)), dim3(256), 0, st, f);
@@ -1105,6 +1136,7 @@ void zfb_destroy(zfb_engine *e) {
     release(e->sr_dev[1]);
     release(e->sbuf[0]);
     release(e->sbuf[1]);
+    release(e->chan_dev);
     if (e->sr_copied) cudaEventDestroy(e->sr_copied);
     for (int i = 0; i < 2; ++i) if (e->sr_free[i]) cudaEventDestroy(e->sr_free[i]);
     if (e->h_rows) cudaFreeHost(e->h_rows);
@@ -1366,6 +1398,81 @@ int zfb_reset_ema(zfb_engine *e) {
     return ZFB_OK;
 }
 
+// channel-batched launches exist for the FAST path with one register-blocked
+// chain and fused strips (fft_ratio 4, 8, 16 on raw input); everything else
+// loops over the channels
+static bool channels_batchable(const zfb_engine *e) {
+    return e->fast_active && e->nchains == 1 && e->chain_run[0] != 0 && e->nstages <= 4;
+}
+
+static int upload_channels(zfb_engine *e, const double *f_demod, int nch) {
+    const zfb_config &c = e->cfg;
+    const bool no_lo = (c.flags & ZFB_FLAG_NO_LO) != 0;
+    const int vec = (c.dtype == ZFB_DTYPE_U8) ? 8 : 2;
+    DecimConst dc;
+    build_decim_const(dc);
+    const double amp0 = no_lo ? 1.0 : sqrt(2.0);
+    e->chan_host.resize((size_t)nch);
+    for (int ch = 0; ch < nch; ++ch) {
+        ChannelLo &t = e->chan_host[(size_t)ch];
+        double r = no_lo ? 0.0 : f_demod[ch] / c.fs;
+        r -= floor(r);
+        if (r >= 1.0) r = 0.0;
+        const double scaled = ldexp(r, 64);
+        t.phase_inc = (scaled >= 18446744073709551615.0) ? 0ull : (unsigned long long)scaled;
+        for (int i = 0; i < 32; ++i) lo_entry(r, i, amp0, t.run[i]);
+        for (int i = 0; i < 8; ++i) lo_entry(r, i, amp0 * (double)dc.g, t.dec_small[i]);
+        for (int it = 0; it < 32; ++it) lo_entry(r, (long long)it * NTHR_SMALL * vec, 1.0, t.dec_big[it]);
+    }
+    int rc = ensure(e, e->chan_dev, (size_t)nch * sizeof(ChannelLo));
+    if (rc) return rc;
+    // pageable source: the runtime stages it before returning, chan_host may be reused afterwards
+    CK(e, cudaMemcpyAsync(e->chan_dev.p, e->chan_host.data(), (size_t)nch * sizeof(ChannelLo),
+                          cudaMemcpyHostToDevice, e->stream));
+    return ZFB_OK;
+}
+
+// `gf` frames starting at d_in for all `nch` channels; rows at d_rows[ch*nframes*W + f*W]
+static int run_channels(zfb_engine *e, const void *d_in, int gf, const double *f_demod, int nch, int nframes,
+                        float *d_rows, bool batched) {
+    const size_t fbytes = (size_t)e->cfg.frame_len * sample_bytes(e->cfg);
+    int rc = ZFB_OK;
+    if (batched) {
+        int per = e->group / nch;
+        if (per < 1) per = 1;
+        for (int q0 = 0; q0 < gf && rc == ZFB_OK; q0 += per) {
+            const int qf = (gf - q0 < per) ? gf - q0 : per;
+            // more channels than the workspace holds at once: slices of channels
+            const int chmax = e->group < nch ? e->group : nch;
+            for (int c0 = 0; c0 < nch && rc == ZFB_OK; c0 += chmax) {
+                const int cn = (nch - c0 < chmax) ? nch - c0 : chmax;
+                e->cur_nch = cn;
+                e->cur_chan_frames = qf;
+                e->cur_row_stride = (long long)nframes * e->W;
+                const ChannelLo *base = (const ChannelLo *)e->chan_dev.p;
+                void *saved = e->chan_dev.p;
+                e->chan_dev.p = (void *)(base + c0);
+                rc = run_group(e, (const char *)d_in + (size_t)q0 * fbytes, qf * cn,
+                               d_rows ? d_rows + ((size_t)c0 * nframes + q0) * e->W : nullptr);
+                e->chan_dev.p = saved;
+            }
+        }
+        e->cur_nch = 0;
+        e->cur_chan_frames = 0;
+    } else {
+        for (int q0 = 0; q0 < gf && rc == ZFB_OK; q0 += e->group) {
+            const int qf = (gf - q0 < e->group) ? gf - q0 : e->group;
+            for (int ch = 0; ch < nch && rc == ZFB_OK; ++ch) {      // channels innermost: input stays in L2
+                apply_lo(e, f_demod[ch]);
+                rc = run_group(e, (const char *)d_in + (size_t)q0 * fbytes, qf,
+                               d_rows ? d_rows + ((size_t)ch * nframes + q0) * e->W : nullptr);
+            }
+        }
+        apply_lo(e, e->cfg.f_demod);
+    }
+    return rc;
+}
+
 static int check_channels(zfb_engine *e, const double *f_demod, int nch) {
     if (nch < 0 || (nch > 0 && !f_demod)) return fail(e, ZFB_EINVAL, "channels: bad arguments");
     if (nch > 0 && e->cfg.ema_alpha >= 0.0)
@@ -1384,18 +1491,21 @@ static int process_device_impl(zfb_engine *e, const void *d_in, int nframes, con
     if (rc) return rc;
     CK(e, cudaSetDevice(e->device));
     const size_t fbytes = (size_t)e->cfg.frame_len * sample_bytes(e->cfg);
-    const int loops = nch > 0 ? nch : 1;
+    if (nch > 0) {
+        const bool batched = channels_batchable(e);
+        if (batched) {
+            rc = upload_channels(e, f_demod, nch);
+            if (rc) return rc;
+        }
+        // the counters count frames per channel pass; rows [nch][nframes][W]
+        return run_channels(e, d_in, nframes, f_demod, nch, nframes, d_rows, batched);
+    }
     for (int g0 = 0; g0 < nframes; g0 += e->group) {
         const int gf = (nframes - g0 < e->group) ? nframes - g0 : e->group;
-        for (int ch = 0; ch < loops; ++ch) {          // channels innermost: the group's input stays in L2
-            if (nch > 0) apply_lo(e, f_demod[ch]);
-            rc = run_group(e, (const char *)d_in + (size_t)g0 * fbytes, gf,
-                           d_rows ? d_rows + ((size_t)ch * nframes + g0) * e->W : nullptr);
-            if (rc) break;
-        }
+        rc = run_group(e, (const char *)d_in + (size_t)g0 * fbytes, gf,
+                       d_rows ? d_rows + (size_t)g0 * e->W : nullptr);
         if (rc) break;
     }
-    if (nch > 0) apply_lo(e, e->cfg.f_demod);
     return rc;
 }
 
@@ -1423,6 +1533,11 @@ static int process_host_impl(zfb_engine *e, const void *h_in, int nframes, const
     CK(e, cudaSetDevice(e->device));
     const int loops = nch > 0 ? nch : 1;
     const size_t fbytes = (size_t)e->cfg.frame_len * sample_bytes(e->cfg);
+    const bool batched = nch > 0 && channels_batchable(e);
+    if (batched) {
+        rc = upload_channels(e, f_demod, nch);
+        if (rc) return rc;
+    }
     // host path pipelines in sub-groups so that copies overlap compute
     int hg = e->group;
     if (nframes > 1 && hg > (nframes + 3) / 4) hg = (nframes + 3) / 4;
@@ -1471,18 +1586,19 @@ static int process_host_impl(zfb_engine *e, const void *h_in, int nframes, const
         CK(e, cudaEventRecord(e->ev_h2d[slot], e->copy_stream));
         CK(e, cudaStreamWaitEvent(e->stream, e->ev_h2d[slot], 0));
         e->counters[3] += bytes;
-        for (int q0 = 0; q0 < gf && rc == ZFB_OK; q0 += e->group) {
-            const int qf = (gf - q0 < e->group) ? gf - q0 : e->group;
-            for (int ch = 0; ch < loops && rc == ZFB_OK; ++ch) {
-                if (nch > 0) apply_lo(e, f_demod[ch]);
+        if (nch > 0) {
+            rc = run_channels(e, e->stage_in[slot].p, gf, f_demod, nch, nframes,
+                              (float *)e->rows_tmp.p + (size_t)g0 * e->W, batched);
+        } else {
+            for (int q0 = 0; q0 < gf && rc == ZFB_OK; q0 += e->group) {
+                const int qf = (gf - q0 < e->group) ? gf - q0 : e->group;
                 rc = run_group(e, (const char *)e->stage_in[slot].p + (size_t)q0 * fbytes, qf,
-                               (float *)e->rows_tmp.p + ((size_t)ch * nframes + g0 + q0) * e->W);
+                               (float *)e->rows_tmp.p + (size_t)(g0 + q0) * e->W);
             }
         }
         CK(e, cudaEventRecord(e->ev_free[slot], e->stream));
         e->slot_busy[slot] = true;
     }
-    if (nch > 0) apply_lo(e, e->cfg.f_demod);
     if (rc) return rc;
     float *dst = pinned_dst ? h_rows : e->h_rows;
     CK(e, cudaMemcpyAsync(dst, e->rows_tmp.p, rows_bytes, cudaMemcpyDeviceToHost, e->stream));

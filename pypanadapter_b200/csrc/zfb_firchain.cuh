@@ -330,6 +330,8 @@ struct FirRunParams {
     float2     *out;
     long long   out_stride;
     int         ht;                // halo threads per side
+    const ChannelLo *chan;         // channel-batched launches (template CH), else null
+    int         chan_frames;       // frames per channel: batch b = ch*chan_frames + frame
 };
 
 // neighbour exchange of one level: a thread publishes its run (or only the M
@@ -450,7 +452,7 @@ struct FirRunShape {
     static constexpr int SPAN = (FIR_NT - 2 * HT) * RUN0;          // level-0 samples a tile finishes
 };
 
-template <int KIND, int NS, int M0, int M1, int M2, int MC>
+template <int KIND, int NS, int M0, int M1, int M2, int MC, bool CH = false>
 __global__ void __launch_bounds__(FIR_NT, 2) fir_run_kernel(const FirRunParams p) {
     using SH = FirRunShape<NS, M0, M1, M2, MC>;
     constexpr int VEC = (KIND == KIND_U8_RAW) ? 8 : 2;
@@ -460,7 +462,9 @@ __global__ void __launch_bounds__(FIR_NT, 2) fir_run_kernel(const FirRunParams p
     float2 *sm2 = sm1 + SH::S1;
     float2 *smc = sm2 + SH::S2;
     const int t = threadIdx.x;
-    const int frame = blockIdx.y;
+    const int frame = blockIdx.y;                                   // output (batch) index
+    const int ch = CH ? frame / p.chan_frames : 0;
+    const int in_frame = CH ? frame % p.chan_frames : frame;
     const int lo0 = blockIdx.x * SH::SPAN - SH::HT * RUN0;          // level-0 position of thread 0, sample 0
     const int pos0 = lo0 + t * RUN0;
     const int L = p.L;
@@ -469,7 +473,7 @@ __global__ void __launch_bounds__(FIR_NT, 2) fir_run_kernel(const FirRunParams p
     float2 x0[RUN0];
     {
         const size_t esz = (KIND == KIND_U8_RAW) ? 2 : 8;
-        const char *frame_in = (const char *)p.in + (size_t)frame * (size_t)p.in_stride * esz;
+        const char *frame_in = (const char *)p.in + (size_t)in_frame * (size_t)p.in_stride * esz;
         const bool fl = (KIND != KIND_C64_MID) && p.flip;
         // element e of the run <-> sample index fl ? L-1-(pos0+e) : pos0+e
         const long long i_first = fl ? (long long)L - RUN0 - pos0 : (long long)pos0;
@@ -511,9 +515,10 @@ __global__ void __launch_bounds__(FIR_NT, 2) fir_run_kernel(const FirRunParams p
             }
         }
         if (KIND != KIND_C64_MID) {
-            const float2 b0 = lo_phasor((long long)pos0, p.phase_inc);
+            const ChannelLo *cl = CH ? p.chan + ch : nullptr;
+            const float2 b0 = lo_phasor((long long)pos0, CH ? cl->phase_inc : p.phase_inc);
 #pragma unroll
-            for (int e = 0; e < RUN0; ++e) x0[e] = cmul(x0[e], cmul(b0, p.lo_run[e]));
+            for (int e = 0; e < RUN0; ++e) x0[e] = cmul(x0[e], cmul(b0, CH ? cl->run[e] : p.lo_run[e]));
         }
     }
 

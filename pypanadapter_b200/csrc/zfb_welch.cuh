@@ -293,11 +293,20 @@ struct FinalizeParams {
     float *ring;              // [ring_rows][W] or null
     long long ring_pos;       // ring slot of frame 0
     int    ring_rows;
+    // channel-batched launches: frame index b = ch*chan_frames + f lands at
+    // rows[ch*chan_row_stride + f*W]; chan_frames == 0: rows[b*W]
+    int    chan_frames;
+    long long chan_row_stride;
 };
 
 __device__ __forceinline__ void emit_row_value(const FinalizeParams &p, int f, int col, float v) {
     const float out = p.linear ? v : 20.0f * log10f(fabsf(v));
-    if (p.rows) p.rows[(size_t)f * p.W + col] = out;
+    if (p.rows) {
+        const size_t at = p.chan_frames ? (size_t)(f / p.chan_frames) * (size_t)p.chan_row_stride +
+                                              (size_t)(f % p.chan_frames) * p.W
+                                        : (size_t)f * p.W;
+        p.rows[at + col] = out;
+    }
     if (p.ring) p.ring[(size_t)((p.ring_pos + f) % p.ring_rows) * p.W + col] = out;
 }
 
