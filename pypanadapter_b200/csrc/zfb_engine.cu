@@ -362,7 +362,11 @@ struct WelchEntry { WelchFn fn; int threads; size_t smem; };
 
 template <int LOG2N, int KIND>
 WelchEntry welch_entry() {
-    constexpr int PPT = (LOG2N >= 13) ? 16 : 8;
+#ifndef ZFB_WELCH_PPT16_FROM
+#define ZFB_WELCH_PPT16_FROM 11
+#endif
+    // 16 points per thread from N = 2048 up: half the threads per barrier, twice the ILP
+    constexpr int PPT = (LOG2N >= ZFB_WELCH_PPT16_FROM) ? 16 : 8;
     using S = WelchShape<LOG2N, PPT>;
     return WelchEntry{welch_kernel<LOG2N, PPT, KIND>, S::NTHREADS, S::SMEM};
 }
@@ -430,6 +434,8 @@ int setup_device_once(zfb_engine *e) {
             WelchEntry w = welch_lookup(l, kind);
             if (w.smem > 48 * 1024)
                 CK(e, cudaFuncSetAttribute(w.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.smem));
+            if (l >= 11)   // N >= 2048: room for several CTAs' exchange buffers; small N keeps its L1
+                CK(e, cudaFuncSetAttribute(w.fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         }
     CK(e, cudaFuncSetAttribute(strip_cascade_kernel<KIND_U8_RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)decim_smem(NTHR_SMALL)));

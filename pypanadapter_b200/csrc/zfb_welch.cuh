@@ -203,11 +203,12 @@ struct WelchShape {
     static constexpr int N = 1 << LOG2N;
     static constexpr int NT = N / PPT;                       // working threads
     static constexpr int NTHREADS = NT < 32 ? 32 : NT;       // launched threads
+    static constexpr int MINB = NTHREADS <= 256 ? 2 : 1;     // >= 2 CTAs/SM: the passes are barrier-bound
     static constexpr size_t SMEM = (size_t)(N + (N >> 4) + 1) * sizeof(float2);
 };
 
 template <int LOG2N, int PPT, int KIND>
-__global__ void __launch_bounds__((WelchShape<LOG2N, PPT>::NTHREADS))
+__global__ void __launch_bounds__((WelchShape<LOG2N, PPT>::NTHREADS), (WelchShape<LOG2N, PPT>::MINB))
 welch_kernel(const WelchParams p) {
     using S = WelchShape<LOG2N, PPT>;
     constexpr int N = S::N;
