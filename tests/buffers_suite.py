@@ -220,3 +220,58 @@ def dropin_on_reference_modules(engine):
 def buffers_Data():
     from pypanadapter_b200.buffers import Data as D
     return D
+
+
+def producer_consumer_threads(engine):
+    """DataReader-style producer thread (T:2187-2195) and PSD.run-style consumer
+    thread (T:1498-1511) hammering one Data/PSD pair: no deadlock, no torn
+    state, every published row is a finite full-width row."""
+    import threading
+    import time
+    w = synth.CFG1
+    state = types.SimpleNamespace(fft_size=w.fft_size, fft_ratio=w.fft_ratio, fft_tapering=w.window,
+                                  panadapter=types.SimpleNamespace(SampleRate=w.fs))
+    d = Data(engine=engine).new_complex()
+    psd = PSD(d, state)
+    frame = synth.make_frame(w, 0)
+    stop = threading.Event()
+    errors = []
+
+    def producer():
+        i = 0
+        try:
+            while not stop.is_set():
+                a = (i * d.chunk_size) % (len(frame) - d.chunk_size)
+                d.add(frame[a:a + d.chunk_size])
+                i += 1
+        except Exception as exc:                      # pragma: no cover
+            errors.append(exc)
+
+    rows = []
+
+    def consumer():
+        try:
+            while not stop.is_set():
+                psd.update()
+                psd.lock.lock()
+                r = psd.psd
+                psd.lock.unlock()
+                if len(r) == 2 * int(.5 * w.fft_size / w.fft_ratio):
+                    rows.append(np.array(r, copy=True))
+                time.sleep(0.002)
+        except Exception as exc:                      # pragma: no cover
+            errors.append(exc)
+
+    ts = [threading.Thread(target=producer), threading.Thread(target=consumer)]
+    for t in ts:
+        t.start()
+    time.sleep(1.0)
+    stop.set()
+    for t in ts:
+        t.join(timeout=20)
+        assert not t.is_alive(), "thread did not finish (deadlock?)"
+    assert not errors, errors
+    assert len(rows) >= 3
+    for r in rows:
+        assert r.shape == (256,) and np.all(np.isfinite(r)) and r.max() > -120.0
+    assert 0 <= d.size <= d.max_size and d.real_size <= d.max_size

@@ -112,3 +112,7 @@ def test_multi_channel(emu_engine):
 @pytest.mark.parametrize("seed", [1, 2, 3])
 def test_random_configs(emu_engine, seed):
     es.random_configs(emu_engine, seed, 12)
+
+
+def test_producer_consumer_threads(emu_engine):
+    bs.producer_consumer_threads(emu_engine)

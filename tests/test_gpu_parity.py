@@ -188,3 +188,7 @@ def test_multi_channel(gpu_engine):
 @pytest.mark.parametrize("seed", [11, 12, 13, 14])
 def test_random_configs(gpu_engine, seed):
     es.random_configs(gpu_engine, seed, 25)
+
+
+def test_producer_consumer_threads(gpu_engine):
+    bs.producer_consumer_threads(gpu_engine)
