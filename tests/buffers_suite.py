@@ -275,3 +275,47 @@ def producer_consumer_threads(engine):
     for r in rows:
         assert r.shape == (256,) and np.all(np.isfinite(r)) and r.max() > -120.0
     assert 0 <= d.size <= d.max_size and d.real_size <= d.max_size
+
+
+def replay_source_through_plugin_api(engine):
+    """cfg2 through the reference's own plug-in surface: ReplayPan.Read ->
+    Data.add -> PSD.update (complex path, flipped per chunk like RTLSDR.Read),
+    and ReplayPan.ReadRaw -> Data.new_u8 (wire format, device conversion)."""
+    from pypanadapter_b200.replay import ReplayPan
+    w = synth.CFG2
+    n = w.fft_size * 40
+    raw = synth.make_frame(w, 0, n=n)
+    state = types.SimpleNamespace(fft_size=w.fft_size, fft_ratio=w.fft_ratio, fft_tapering=w.window,
+                                  panadapter=types.SimpleNamespace(SampleRate=w.fs))
+    floor = parity.floor_db20(w.fs, w.window, w.fft_size, True)
+    # complex path: DataReader.run's loop (T:2187-2191)
+    pan = ReplayPan(raw, w.fs)
+    assert pan.Mode == "Block" and pan.SampleRate == w.fs and pan.driver
+    d = Data(engine=engine).new_complex()
+    psd = PSD(d, state)
+    chunks = []
+    for _ in range(n // d.chunk_size):
+        c = pan.Read(d.chunk_size)
+        chunks.append(c)
+        d.add(c)
+    psd.update()
+    want = zo.zoom_psd(np.concatenate(chunks), w.fs, w.fft_size, w.fft_ratio, w.window)
+    parity.assert_row_parity(psd.psd, want, floor, "replay complex path")
+    # wire-format path
+    pan = ReplayPan(raw, w.fs)
+    d = Data(engine=engine).new_u8()
+    psd = PSD(d, state, flip=True)
+    got_raw = []
+    for _ in range(n // d.chunk_size):
+        c = pan.ReadRaw(d.chunk_size)
+        got_raw.append(c)
+        d.add(c)
+    psd.update()
+    want = zo.zoom_psd(np.concatenate(got_raw), w.fs, w.fft_size, w.fft_ratio, w.window, flip=True)
+    parity.assert_row_parity(psd.psd, want, floor, "replay u8 path")
+    # looping and EOF
+    small = ReplayPan(raw[:20], w.fs, loop=True)
+    assert len(small.ReadRaw(25)) == 50
+    import pytest
+    with pytest.raises(EOFError):
+        ReplayPan(raw[:20], w.fs, loop=False).ReadRaw(25)

@@ -322,3 +322,46 @@ def random_configs(engine, seed, count):
         # single- and few-segment rows: fp32 holds 0.01 dB20 only within ~85 dB of the row's peak
         floor = max(floor, want.max() - 170.0)
         parity.assert_row_parity(row, want, floor, what)
+
+
+def reconfigure_stress(engine, rounds=4):
+    """The reference lets N, R, window and frame length change between any two
+    frames (S:1753-1757, S:2079-2086): cycling through very different plans on
+    ONE engine must reproduce each plan's first-run rows bit for bit (no stale
+    workspace, LO table, FIR plan or EMA state leaks between configurations)."""
+    rng = np.random.default_rng(5)
+    plans = [
+        dict(fs=2.4e6, N=2048, R=8, n=2048 * 20, window="hamming", dtype="c64", mode="fast", crop="thread"),
+        dict(fs=3.2e6, N=4096, R=16, n=4096 * 20, window="hann", dtype="u8", flip=True, mode="fast", crop="thread"),
+        dict(fs=1e6, N=256, R=1, n=256 * 9 + 17, window=("kaiser", 9.0), dtype="c64", mode="exact", crop=None),
+        dict(fs=2.4e6, N=1024, R=4, n=1024 * 12 + 1, window="hamming", dtype="c64", mode="exact", crop=512),
+        dict(fs=2.4e6, N=16384, R=2, n=16384 * 6, window="hann", dtype="c64", mode="fast", crop="thread"),
+        dict(fs=20e6, N=512, R=32, n=512 * 32 * 12, window="blackmanharris", dtype="c64", mode="fast",
+             crop="thread", f_demod=-3.3e6),
+        dict(fs=2.4e6, N=2048, R=8, n=2048 * 20, window="hamming", dtype="c64", mode="fast", crop="thread",
+             ema_alpha=0.5),
+    ]
+    data, first = [], []
+    for p in plans:
+        n = p["n"]
+        x = 0.3 * np.exp(2j * np.pi * rng.uniform(-0.02, 0.02) * np.arange(n)) \
+            + 1e-2 * (rng.standard_normal(n) + 1j * rng.standard_normal(n))
+        data.append(synth.quantise_u8(x) if p["dtype"] == "u8" else x.astype(np.complex64))
+
+    def run(i):
+        p = plans[i]
+        engine.configure(p["fs"], p["N"], p["R"], p["n"], p["window"], dtype=p["dtype"],
+                         flip=p.get("flip", False), f_demod=p.get("f_demod", 1.0), crop=p["crop"],
+                         ema_alpha=p.get("ema_alpha"), mode=p["mode"])
+        if p.get("ema_alpha") is not None:
+            engine.reset_ema()
+        return engine.process(np.stack([data[i], data[i]]))
+
+    for i in range(len(plans)):
+        first.append(run(i))
+        assert np.all(np.isfinite(first[i]))
+    order = list(range(len(plans)))
+    for _ in range(rounds):
+        rng.shuffle(order)
+        for i in order:
+            assert np.array_equal(run(i), first[i]), "plan %d changed after reconfiguration" % i

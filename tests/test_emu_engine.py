@@ -116,3 +116,11 @@ def test_random_configs(emu_engine, seed):
 
 def test_producer_consumer_threads(emu_engine):
     bs.producer_consumer_threads(emu_engine)
+
+
+def test_reconfigure_stress(emu_engine):
+    es.reconfigure_stress(emu_engine)
+
+
+def test_replay_source(emu_engine):
+    bs.replay_source_through_plugin_api(emu_engine)

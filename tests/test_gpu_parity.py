@@ -192,3 +192,11 @@ def test_random_configs(gpu_engine, seed):
 
 def test_producer_consumer_threads(gpu_engine):
     bs.producer_consumer_threads(gpu_engine)
+
+
+def test_reconfigure_stress(gpu_engine):
+    es.reconfigure_stress(gpu_engine)
+
+
+def test_replay_source(gpu_engine):
+    bs.replay_source_through_plugin_api(gpu_engine)
