@@ -564,10 +564,15 @@ void prof_end(zfb_engine *e, int idx) {
 }
 
 // the tap sets fastdesign.py produces for the last chain of R = 4 / 8 / >= 16
+// ... and, without compensator (D = -1), for the light first chains of deeper
+// zooms (every stage there has <= 7 taps; shorter ones are zero-padded)
 #define ZFB_RUN_COMBOS(X, KIND) \
     X(1, KIND, 1, 13, 0, 0, 15)  \
     X(2, KIND, 2, 5, 13, 0, 16)  \
-    X(3, KIND, 3, 4, 5, 13, 16)
+    X(3, KIND, 3, 4, 5, 13, 16)  \
+    X(4, KIND, 1, 3, 0, 0, -1)   \
+    X(5, KIND, 2, 3, 3, 0, -1)   \
+    X(6, KIND, 3, 3, 3, 3, -1)
 
 template <int KIND>
 void launch_fir_run_kind(int variant, const FirRunParams &rp, int L_out, int gf, cudaStream_t st) {
@@ -596,8 +601,12 @@ void launch_fir_run(int variant, int kind, const FirRunParams &rp, int L_out, in
 
 // which specialised variant (0 = none) handles this chain
 int fir_run_variant(const FirChainParams &p) {
+    // exact tap sets with a compensator; "<=" (zero-padded taps) for the chains without
 #define ZFB_X(ID, K, NS, A, B, C, D)                                                             \
-    if (p.ns == NS && p.Mc == D && p.M[0] == A && (NS < 2 || p.M[1] == B) && (NS < 3 || p.M[2] == C)) return ID;
+    if (D >= 0 && p.ns == NS && p.Mc == D && p.M[0] == A && (NS < 2 || p.M[1] == B) && (NS < 3 || p.M[2] == C)) \
+        return ID;                                                                               \
+    if (D < 0 && p.ns == NS && p.Mc < 0 && p.M[0] <= A && (NS < 2 || p.M[1] <= B) && (NS < 3 || p.M[2] <= C)) \
+        return ID;
     ZFB_RUN_COMBOS(ZFB_X, 0)
 #undef ZFB_X
     return 0;

@@ -444,10 +444,10 @@ struct FirRunShape {
     static constexpr int S0 = LevelStore<RUN0, M0>::SIZE;
     static constexpr int S1 = NS >= 2 ? LevelStore<RUN0 / 2, (M1 > 0 ? M1 : 1)>::SIZE : 0;
     static constexpr int S2 = NS >= 3 ? LevelStore<RUN0 / 4, (M2 > 0 ? M2 : 1)>::SIZE : 0;
-    static constexpr int SC = LevelStore<RUN_OUT, MC>::SIZE;
+    static constexpr int SC = MC >= 0 ? LevelStore<RUN_OUT, (MC > 0 ? MC : 1)>::SIZE : 0;   // MC < 0: no compensator
     static constexpr size_t SMEM = (size_t)(S0 + S1 + S2 + SC) * sizeof(float2);
     // dependency cone of a final output, in level-0 samples
-    static constexpr int CONE = M0 + (NS >= 2 ? 2 * M1 : 0) + (NS >= 3 ? 4 * M2 : 0) + (1 << NS) * MC;
+    static constexpr int CONE = M0 + (NS >= 2 ? 2 * M1 : 0) + (NS >= 3 ? 4 * M2 : 0) + (MC > 0 ? (1 << NS) * MC : 0);
     static constexpr int HT = (CONE + RUN0 - 1) / RUN0;
     static constexpr int SPAN = (FIR_NT - 2 * HT) * RUN0;          // level-0 samples a tile finishes
 };
@@ -548,16 +548,22 @@ __global__ void __launch_bounds__(FIR_NT, 2) fir_run_kernel(const FirRunParams p
         }
     }
 
-    // ---------------- compensator ----------------
+    // ---------------- compensator (last chain only) ----------------
     constexpr int RO = SH::RUN_OUT;
-    LevelStore<RO, MC>::publish(smc, t, yf);
-    __syncthreads();
-    float2 win[RO + 2 * MC];
-#pragma unroll
-    for (int j = 0; j < RO; ++j) win[MC + j] = yf[j];
-    LevelStore<RO, MC>::template halo<RO + 2 * MC>(smc, t, win);
     float2 out[RO];
-    fir_same_regs<RO, MC>(win, p.hc, out);
+    if constexpr (MC > 0) {
+        LevelStore<RO, MC>::publish(smc, t, yf);
+        __syncthreads();
+        float2 win[RO + 2 * MC];
+#pragma unroll
+        for (int j = 0; j < RO; ++j) win[MC + j] = yf[j];
+        LevelStore<RO, MC>::template halo<RO + 2 * MC>(smc, t, win);
+        fir_same_regs<RO, MC>(win, p.hc, out);
+    } else {
+        (void)smc;
+#pragma unroll
+        for (int j = 0; j < RO; ++j) out[j] = yf[j];
+    }
 
     if (t >= SH::HT && t < FIR_NT - SH::HT) {
         const int po = pos0 >> NS;
