@@ -12,7 +12,7 @@ namespace zfb {
 // T <= TMAX samples; WARM samples on either side absorb the start-up
 // transient of regions that do not begin/end at a true chunk edge (the slow
 // pole pair of cheby1(8,.05,.4) has radius 0.935: 0.935^320 = 5e-10 in state,
-// 4.9e-8 worst-case in output -- below fp32 resolution).
+// below fp32 resolution in the outputs).
 constexpr int BLK      = 64;                 // samples per thread
 constexpr int WARM     = 320;                // warm-up halo each side
 // threads per CTA is a kernel template parameter NT (256 or 128):
@@ -34,8 +34,8 @@ constexpr int KIND_C64_MID = 2;  // complex64 intermediate (already mixed)
 
 struct DecimConst {
     float na1[NSEC], na2[NSEC];          // -a1, -a2 of each section
-    float g;                             // b0 of section 0 (overall gain)
-    float zi[NSEC];                      // DF2 steady state per unit scaled input
+    float g;                             // (b0 of section 0)^2: gain of the forward + backward pass
+    float zi[NSEC];                      // steady state of the all-pole cascade per unit scaled input
     float Mp[JTERMS][NSTATE][NSTATE];    // Mp[j] = (state transition over BLK)^j
 };
 

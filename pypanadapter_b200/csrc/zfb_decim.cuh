@@ -10,16 +10,23 @@
 // S:543), the np.flip (S:460,543; T:460) and the LO mix (S:2090-2094).
 //
 // Parallel scheme (one CTA = one REGION of one frame, resident in smem):
+//   * the pass H(z) = g (1+z^-1)^8 / prod A_k(z) is split: the sweeps run the
+//     all-pole cascade only, the binomial numerator is one FIR pass per
+//     direction afterwards, g^2 is folded into the load (see `pole` below);
 //   * thread t owns samples [64t, 64t+64) of the region;
-//   * sweep 1: every thread runs the 4-biquad cascade over its run from a zero
+//   * sweep 1: every thread runs the all-pole cascade over its run from a zero
 //     state and publishes the 8-value final state z_t;
 //   * hand-off: the true incoming state is s_t = sum_j M^(j-1) z_(t-j) (M = the
-//     cascade's state transition over 64 samples; |M^5| < 4e-8 so 5 terms);
+//     cascade's state transition over 64 samples; |M^5| = 2e-9, so 5 terms);
 //     the run that contains the chunk's first extended sample starts instead
 //     from the exact steady state zi*ext[0] and ends the sum ("anchor");
-//   * sweep 2: rerun from s_t, now storing.  Same again backwards.
+//   * sweep 2: rerun from s_t, now storing, software-pipelined across the four
+//     sections.  Same again backwards.
 //   A region that starts/ends inside the chunk anchors on a steady-state guess
 //   WARM=320 samples outside its outputs; true chunk edges are exact.
+// The same stage body (exact_stage_inplace) serves the tiled kernel
+// (decim2_exact_kernel: mode exact, and the last stage of mode fast) and the
+// fused edge-strip cascade of mode fast (strip_cascade_kernel).
 #pragma once
 #include "zfb_common.cuh"
 
