@@ -25,7 +25,8 @@ constexpr int BLK_PAD  = BLK + 1;            // +1 complex: conflict-free LDS.64
 constexpr int PADLEN   = 27;                 // scipy sosfiltfilt odd extension
 constexpr int NSEC     = 4;                  // biquads in cheby1 order 8
 constexpr int NSTATE   = 2 * NSEC;
-constexpr int JTERMS   = 5;                  // blocks of history in hand-off
+constexpr int JTERMS   = 5;                  // blocks of history in hand-off (64-sample runs)
+constexpr int JTERMS32 = 10;                 // same for the 32-sample runs of the strip kernel
 
 // input kinds of a decimation stage / of the Welch kernel
 constexpr int KIND_C64_RAW = 0;  // complex64 chunk: flip + LO mix on load
@@ -37,6 +38,7 @@ struct DecimConst {
     float g;                             // (b0 of section 0)^2: gain of the forward + backward pass
     float zi[NSEC];                      // steady state of the all-pole cascade per unit scaled input
     float Mp[JTERMS][NSTATE][NSTATE];    // Mp[j] = (state transition over BLK)^j
+    float Mp32[JTERMS32][NSTATE][NSTATE];// same over 32 samples (|M32^10| = 3e-9)
 };
 
 // per-channel software-LO tables of the channel-batched launches
@@ -45,7 +47,7 @@ struct ChannelLo {
     unsigned long long phase_inc;   // frac(f_demod/fs) * 2^64
     float2 run[32];                 // fir_run_kernel: sqrt(2) * exp(-2 pi i f/fs j)
     float2 dec_small[8];            // exact stage 0 / strips: sqrt(2) g^2 exp(-2 pi i f/fs v)
-    float2 dec_big[32];             // exp(-2 pi i f/fs * it*128*VEC)
+    float2 dec_big[32];             // exp(-2 pi i f/fs * it*STRIP_NT*VEC)  (strip kernel)
 };
 
 // packed fp32x2 arithmetic (Blackwell FFMA2/FADD2/FMUL2): re and im of a

@@ -104,10 +104,10 @@ __device__ __forceinline__ float2 pole(float2 v, float2 &w1, float2 &w2, float n
 // Full BLK-sample run, software-pipelined across the cascade: in step i
 // section k works on sample i-k, so the four recurrences are independent
 // instruction streams (the serial form leaves the FMA pipe idle ~60 %).
-template <bool BWD, bool STORE>
+template <bool BWD, bool STORE, int B = BLK>
 __device__ __forceinline__ void sweep_full(float2 *blk, Sec4 &s, const float (&na1)[NSEC],
                                            const float (&na2)[NSEC]) {
-#define ZFB_POS(i) (BWD ? (BLK - 1 - (i)) : (i))
+#define ZFB_POS(i) (BWD ? (B - 1 - (i)) : (i))
     float2 p0, p1, p2;
     p0 = pole(blk[ZFB_POS(0)], s.w1[0], s.w2[0], na1[0], na2[0]);
     {
@@ -122,7 +122,7 @@ __device__ __forceinline__ void sweep_full(float2 *blk, Sec4 &s, const float (&n
         p2 = n2;
         p1 = n1;
     }
-    // steady part: BLK - 3 = 61 steps = 1 + 60, the 60 unrolled by ZFB_SWEEP_UNROLL
+    // steady part: B - 3 steps (61 = 1 + 60 for B = 64), unrolled by ZFB_SWEEP_UNROLL
 #define ZFB_SWEEP_STEP(i)                                                         \
     {                                                                             \
         float2 y = pole(p2, s.w1[3], s.w2[3], na1[3], na2[3]);                    \
@@ -136,34 +136,34 @@ __device__ __forceinline__ void sweep_full(float2 *blk, Sec4 &s, const float (&n
     }
     ZFB_SWEEP_STEP(3)
 #pragma unroll SWEEP_UNROLL
-    for (int i = 4; i < BLK; ++i) ZFB_SWEEP_STEP(i)
+    for (int i = 4; i < B; ++i) ZFB_SWEEP_STEP(i)
 #undef ZFB_SWEEP_STEP
     {
         float2 y = pole(p2, s.w1[3], s.w2[3], na1[3], na2[3]);
         float2 n2 = pole(p1, s.w1[2], s.w2[2], na1[2], na2[2]);
         float2 n1 = pole(p0, s.w1[1], s.w2[1], na1[1], na2[1]);
-        if (STORE) blk[ZFB_POS(BLK - 3)] = y;
+        if (STORE) blk[ZFB_POS(B - 3)] = y;
         p2 = n2;
         p1 = n1;
     }
     {
         float2 y = pole(p2, s.w1[3], s.w2[3], na1[3], na2[3]);
         float2 n2 = pole(p1, s.w1[2], s.w2[2], na1[2], na2[2]);
-        if (STORE) blk[ZFB_POS(BLK - 2)] = y;
+        if (STORE) blk[ZFB_POS(B - 2)] = y;
         p2 = n2;
     }
     {
         float2 y = pole(p2, s.w1[3], s.w2[3], na1[3], na2[3]);
-        if (STORE) blk[ZFB_POS(BLK - 1)] = y;
+        if (STORE) blk[ZFB_POS(B - 1)] = y;
     }
 #undef ZFB_POS
 }
 
-template <bool BWD, bool STORE>
+template <bool BWD, bool STORE, int B = BLK>
 __device__ __forceinline__ void sweep(float2 *blk, int lo, int hi, Sec4 &s,
                                       const float (&na1)[NSEC], const float (&na2)[NSEC]) {
-    if (lo == 0 && hi == BLK) {
-        sweep_full<BWD, STORE>(blk, s, na1, na2);
+    if (lo == 0 && hi == B) {
+        sweep_full<BWD, STORE, B>(blk, s, na1, na2);
     } else {
         for (int i = lo; i < hi; ++i) {
             const int q = BWD ? (hi - 1 - (i - lo)) : i;
@@ -189,12 +189,13 @@ __device__ __forceinline__ float2 binom9(const float2 *w) {
 }
 
 // y[n] = sum_j C(8,j) x[n-j] over one thread's run, in place; hist = x[-8..-1]
+template <int B = BLK>
 __device__ __forceinline__ void fir_causal(float2 *blk, const float2 (&hist)[8]) {
     float2 win[16];
 #pragma unroll
     for (int j = 0; j < 8; ++j) win[j] = hist[j];
 #pragma unroll 2
-    for (int b = 0; b < BLK; b += 8) {
+    for (int b = 0; b < B; b += 8) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) win[8 + j] = blk[b + j];
 #pragma unroll
@@ -206,13 +207,14 @@ __device__ __forceinline__ void fir_causal(float2 *blk, const float2 (&hist)[8])
 
 // y[n] = sum_j C(8,j) x[n+j] at the even n of one thread's run, in place
 // (odd positions keep x); ahead = x[BLK .. BLK+7]
+template <int B = BLK>
 __device__ __forceinline__ void fir_anticausal_even(float2 *blk, const float2 (&ahead)[8]) {
     float2 win[16];
 #pragma unroll
     for (int j = 0; j < 8; ++j) win[j] = blk[j];
 #pragma unroll 2
-    for (int b = 0; b < BLK; b += 8) {
-        if (b + 8 < BLK) {
+    for (int b = 0; b < B; b += 8) {
+        if (b + 8 < B) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) win[8 + j] = blk[b + 8 + j];
         } else {
@@ -235,8 +237,8 @@ __device__ __forceinline__ void publish(float2 *zbuf, int t, const Sec4 &s) {
     }
 }
 
-// s = sum_{j=1..jmax} Mp[j-1] * z_{t -/+ j}
-template <bool BWD, int NT>
+// s = sum_{j=1..jmax} M^(j-1) * z_{t -/+ j}, M = state transition over one B-sample run
+template <bool BWD, int NT, int B = BLK>
 __device__ __forceinline__ void handoff(const float2 *zbuf, int t, int jmax, Sec4 &s) {
     float2 acc[NSTATE];
 #pragma unroll
@@ -254,7 +256,7 @@ __device__ __forceinline__ void handoff(const float2 *zbuf, int t, int jmax, Sec
             for (int r = 0; r < NSTATE; ++r) {
 #pragma unroll
                 for (int c = 0; c < 2 * (r / 2 + 1); ++c)    // block lower triangular
-                    acc[r] = pk_fma(c_dec.Mp[j - 1][r][c], z[c], acc[r]);
+                    acc[r] = pk_fma(B == BLK ? c_dec.Mp[j - 1][r][c] : c_dec.Mp32[j - 1][r][c], z[c], acc[r]);
             }
         }
     }
@@ -265,7 +267,12 @@ __device__ __forceinline__ void handoff(const float2 *zbuf, int t, int jmax, Sec
     }
 }
 
-__device__ __forceinline__ int sidx(int q) { return q + (q >> 6); }   // BLK_PAD layout
+// run-padded layout: one spare complex after every B-sample run
+template <int B = BLK>
+__device__ __forceinline__ int sidx(int q) {
+    return q + (q >> (B == 64 ? 6 : 5));
+}
+static_assert(BLK == 64, "sidx assumes runs of 64 (default) or 32 samples");
 
 // ---- region load: convert / flip / mix / gain, zero outside [0, L) -------
 // 128-bit coalesced loads, CH of them in flight per thread before the first
@@ -280,12 +287,12 @@ __device__ __forceinline__ float2 u8pair_to_iq(unsigned int word, int hi) {
     return __ffma2_rn(f, make_float2(1.0f / 127.5f, 1.0f / 127.5f), make_float2(-1.0f, -1.0f));
 }
 
-template <int KIND, int NT, bool CHAN = false>
+template <int KIND, int NT, bool CHAN = false, int B = BLK>
 __device__ __forceinline__ void load_region(float2 *buf, const StageParams &p,
                                             const char *frame_in, int rs, int tid, int posoff, int ch = 0) {
     constexpr int VEC = (KIND == KIND_U8_RAW) ? 8 : 2;
-    constexpr int ITERS = BLK / VEC;
-    constexpr int CH = 8;
+    constexpr int ITERS = B / VEC;
+    constexpr int CH = ITERS < 8 ? ITERS : 8;     // loads in flight per thread
     const int L = p.L;
     const bool fl = (KIND != KIND_C64_MID) && p.flip;
     float2 b0 = make_float2(1.f, 0.f);
@@ -355,7 +362,7 @@ __device__ __forceinline__ void load_region(float2 *buf, const StageParams &p,
                 for (int e = 0; e < VEC; ++e)
                     v[e] = cmul(v[e], cmul(bi, CHAN ? cl->dec_small[e] : p.lo_small[e]));
             }
-            const int s0 = sidx(q);           // VEC consecutive samples share a block
+            const int s0 = sidx<B>(q);        // VEC consecutive samples share a run
 #pragma unroll
             for (int e = 0; e < VEC; ++e) buf[s0 + e] = v[e];
         }
@@ -366,23 +373,25 @@ __device__ __forceinline__ void load_region(float2 *buf, const StageParams &p,
 // (stage input of length L at region coordinate q = pos - rs, g^2-scaled).
 // On return (after a barrier) the filtered samples are at the EVEN positions:
 // output m of the stage = buf[sidx(2m - rs)].
-template <int NT>
+template <int NT, int B = BLK>
 __device__ __forceinline__ void exact_stage_inplace(float2 *buf, float2 *zbuf, int L, int rs, int tid) {
-    constexpr int REGION = region_of(NT);
+    constexpr int REGION = B * NT;
+    constexpr int LB = (B == 64) ? 6 : 5;
+    constexpr int JT = (B == BLK) ? JTERMS : JTERMS32;
     // odd extension (scipy odd_ext, 27 samples each side) where it falls in the region
     if (tid < PADLEN) {
         const int pos = -1 - tid;                 // 2*x[0] - x[-pos]
         const int q = pos - rs;
         if (q >= 0) {
-            float2 x0 = buf[sidx(-rs)], xm = buf[sidx(-pos - rs)];
-            buf[sidx(q)] = make_float2(2.f * x0.x - xm.x, 2.f * x0.y - xm.y);
+            float2 x0 = buf[sidx<B>(-rs)], xm = buf[sidx<B>(-pos - rs)];
+            buf[sidx<B>(q)] = make_float2(2.f * x0.x - xm.x, 2.f * x0.y - xm.y);
         }
     } else if (tid >= 32 && tid < 32 + PADLEN) {
         const int pos = L + (tid - 32);           // 2*x[L-1] - x[2(L-1)-pos]
         const int q = pos - rs;
         if (q < REGION) {
-            float2 x1 = buf[sidx(L - 1 - rs)], xm = buf[sidx(2 * (L - 1) - pos - rs)];
-            buf[sidx(q)] = make_float2(2.f * x1.x - xm.x, 2.f * x1.y - xm.y);
+            float2 x1 = buf[sidx<B>(L - 1 - rs)], xm = buf[sidx<B>(2 * (L - 1) - pos - rs)];
+            buf[sidx<B>(q)] = make_float2(2.f * x1.x - xm.x, 2.f * x1.y - xm.y);
         }
     }
     __syncthreads();
@@ -390,12 +399,12 @@ __device__ __forceinline__ void exact_stage_inplace(float2 *buf, float2 *zbuf, i
     // valid part of the region in region coordinates
     const int vlo = max(0, -PADLEN - rs);
     const int vhi = min(REGION, L + PADLEN - rs);
-    const int a_f = vlo >> 6;                     // run holding the first valid sample
-    const int a_b = (vhi - 1) >> 6;               // run holding the last valid sample
+    const int a_f = vlo >> LB;                     // run holding the first valid sample
+    const int a_b = (vhi - 1) >> LB;               // run holding the last valid sample
     const bool active = (tid >= a_f) && (tid <= a_b);
-    const int lo = max(vlo - tid * BLK, 0);
-    const int hi = min(vhi - tid * BLK, BLK);
-    float2 *blk = buf + tid * BLK_PAD;
+    const int lo = max(vlo - tid * B, 0);
+    const int hi = min(vhi - tid * B, B);
+    float2 *blk = buf + tid * (B + 1);
 
     float na1[NSEC], na2[NSEC];
 #pragma unroll
@@ -408,14 +417,14 @@ __device__ __forceinline__ void exact_stage_inplace(float2 *buf, float2 *zbuf, i
     // ---------------- forward ----------------
     if (active) {
         if (tid == a_f) sec_steady(s, blk[lo]); else sec_zero(s);
-        sweep<false, false>(blk, lo, hi, s, na1, na2);
+        sweep<false, false, B>(blk, lo, hi, s, na1, na2);
         publish<NT>(zbuf, tid, s);
     }
     __syncthreads();
     if (active) {
         if (tid == a_f) sec_steady(s, blk[lo]);
-        else handoff<false, NT>(zbuf, tid, min(JTERMS, tid - a_f), s);
-        sweep<false, true>(blk, lo, hi, s, na1, na2);
+        else handoff<false, NT, B>(zbuf, tid, min(JT, tid - a_f), s);
+        sweep<false, true, B>(blk, lo, hi, s, na1, na2);
     }
     __syncthreads();
     // numerator of the forward pass: (1+z^-1)^8 over the whole region.  The 8
@@ -424,22 +433,22 @@ __device__ __forceinline__ void exact_stage_inplace(float2 *buf, float2 *zbuf, i
         float2 hist[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-            hist[j] = (tid > 0) ? buf[sidx(tid * BLK - 8 + j)] : make_float2(0.f, 0.f);
+            hist[j] = (tid > 0) ? buf[sidx<B>(tid * B - 8 + j)] : make_float2(0.f, 0.f);
         __syncthreads();
-        if (active) fir_causal(blk, hist);        // runs without valid samples are never read
+        if (active) fir_causal<B>(blk, hist);        // runs without valid samples are never read
     }
     __syncthreads();
     // ---------------- backward ----------------
     if (active) {
         if (tid == a_b) sec_steady(s, blk[hi - 1]); else sec_zero(s);
-        sweep<true, false>(blk, lo, hi, s, na1, na2);
+        sweep<true, false, B>(blk, lo, hi, s, na1, na2);
         publish<NT>(zbuf, tid, s);
     }
     __syncthreads();
     if (active) {
         if (tid == a_b) sec_steady(s, blk[hi - 1]);
-        else handoff<true, NT>(zbuf, tid, min(JTERMS, a_b - tid), s);
-        sweep<true, true>(blk, lo, hi, s, na1, na2);
+        else handoff<true, NT, B>(zbuf, tid, min(JT, a_b - tid), s);
+        sweep<true, true, B>(blk, lo, hi, s, na1, na2);
     }
     __syncthreads();
     // numerator of the backward pass, (1+z)^8, only where a sample is kept
@@ -447,9 +456,9 @@ __device__ __forceinline__ void exact_stage_inplace(float2 *buf, float2 *zbuf, i
         float2 ahead[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-            ahead[j] = (tid < NT - 1) ? buf[sidx((tid + 1) * BLK + j)] : make_float2(0.f, 0.f);
+            ahead[j] = (tid < NT - 1) ? buf[sidx<B>((tid + 1) * B + j)] : make_float2(0.f, 0.f);
         __syncthreads();
-        if (active) fir_anticausal_even(blk, ahead);
+        if (active) fir_anticausal_even<B>(blk, ahead);
     }
     __syncthreads();
 }
@@ -494,6 +503,13 @@ __global__ void __launch_bounds__(NT, (NT == NTHR_BIG ? 1 : 3)) decim2_exact_ker
 // outputs in shared memory, the part the next stage needs is compacted to the
 // front of the region, and only the last stage's `keep` outputs reach global
 // memory (they overwrite the FIR interior's values at the chunk edge).
+// (measured: 256 threads x 32-sample runs -- half the serial chain per thread, but twice
+// the hand-off terms and 2 CTAs/SM -- is 36 % SLOWER than 128 x 64; the run length stays
+// a template parameter of the stage body)
+constexpr int STRIP_NT = 128;
+constexpr int STRIP_BLK = 64;
+constexpr size_t strip_smem() { return (size_t)(STRIP_NT * (STRIP_BLK + 1) + NSTATE * STRIP_NT) * sizeof(float2); }
+
 struct StripParams {
     StageParams st;            // stage 0 load: in, in_stride, L = len[0], flip, Lfull, pos_off, LO tables
     int   nstages;
@@ -505,11 +521,12 @@ struct StripParams {
 };
 
 template <int KIND, bool CHAN = false>
-__global__ void __launch_bounds__(NTHR_SMALL, 3) strip_cascade_kernel(const StripParams sp) {
-    constexpr int NT = NTHR_SMALL;
+__global__ void __launch_bounds__(STRIP_NT, 3) strip_cascade_kernel(const StripParams sp) {
+    constexpr int NT = STRIP_NT;
+    constexpr int B = STRIP_BLK;
     ZFB_DYN_SMEM(smem_raw);
     float2 *buf  = reinterpret_cast<float2 *>(smem_raw);
-    float2 *zbuf = buf + NT * BLK_PAD;
+    float2 *zbuf = buf + NT * (B + 1);
     const int tid = threadIdx.x;
     const int side = blockIdx.x;
     const int frame = blockIdx.y;                      // output (batch) index
@@ -521,18 +538,18 @@ __global__ void __launch_bounds__(NTHR_SMALL, 3) strip_cascade_kernel(const Stri
                            ((size_t)in_frame * (size_t)p.in_stride + (size_t)side * (size_t)p.side_in_off) * esz;
     const int rs = -WARM;
 
-    load_region<KIND, NT, CHAN>(buf, p, frame_in, rs, tid, (KIND != KIND_C64_MID && side) ? p.pos_off : 0, ch);
+    load_region<KIND, NT, CHAN, B>(buf, p, frame_in, rs, tid, (KIND != KIND_C64_MID && side) ? p.pos_off : 0, ch);
     __syncthreads();
     const float g = c_dec.g;
     for (int s = 0; s < sp.nstages; ++s) {
         const int L = sp.len[s];
-        exact_stage_inplace<NT>(buf, zbuf, L, rs, tid);
+        exact_stage_inplace<NT, B>(buf, zbuf, L, rs, tid);
         const int nout = (L + 1) >> 1;
         if (s == sp.nstages - 1) {
             float2 *out = sp.out + (size_t)frame * (size_t)sp.out_stride;
             const int m0 = side ? nout - sp.keep : 0;
             const int d0 = side ? sp.ndec - sp.keep : 0;
-            for (int i = tid; i < sp.keep; i += NT) out[d0 + i] = buf[sidx(WARM + 2 * (m0 + i))];
+            for (int i = tid; i < sp.keep; i += NT) out[d0 + i] = buf[sidx<B>(WARM + 2 * (m0 + i))];
         } else {
             // the next stage works on the first (side 0) / last (side 1) len[s+1] outputs:
             // move them, gain-scaled, to region positions WARM + j.  dst <= src, so
@@ -545,13 +562,13 @@ __global__ void __launch_bounds__(NTHR_SMALL, 3) strip_cascade_kernel(const Stri
 #pragma unroll
                 for (int c = 0; c < CH; ++c) {
                     const int j = j0 + c * NT + tid;
-                    v[c] = (j < Ln) ? buf[sidx(WARM + 2 * (off + j))] : make_float2(0.f, 0.f);
+                    v[c] = (j < Ln) ? buf[sidx<B>(WARM + 2 * (off + j))] : make_float2(0.f, 0.f);
                 }
                 __syncthreads();
 #pragma unroll
                 for (int c = 0; c < CH; ++c) {
                     const int j = j0 + c * NT + tid;
-                    if (j < Ln) buf[sidx(WARM + j)] = pk_mul(g, v[c]);
+                    if (j < Ln) buf[sidx<B>(WARM + j)] = pk_mul(g, v[c]);
                 }
                 __syncthreads();
             }

@@ -276,16 +276,21 @@ void build_decim_const(DecimConst &dc) {
             A[2 * k + 1][j] = w2[k];
         }
     }
-    double M[NSTATE][NSTATE];
-    memcpy(M, A, sizeof M);
-    for (int i = 1; i < BLK; i <<= 1) mat_mul(M, M, M);   // BLK is a power of two
-    double P[NSTATE][NSTATE];
-    for (int i = 0; i < NSTATE; ++i)
-        for (int j = 0; j < NSTATE; ++j) P[i][j] = (i == j) ? 1.0 : 0.0;
-    for (int j = 0; j < JTERMS; ++j) {
-        for (int r = 0; r < NSTATE; ++r)
-            for (int cc = 0; cc < NSTATE; ++cc) dc.Mp[j][r][cc] = (float)P[r][cc];
-        mat_mul(M, P, P);
+    for (int variant = 0; variant < 2; ++variant) {
+        const int run = variant == 0 ? BLK : 32;
+        const int terms = variant == 0 ? JTERMS : JTERMS32;
+        double M[NSTATE][NSTATE];
+        memcpy(M, A, sizeof M);
+        for (int i = 1; i < run; i <<= 1) mat_mul(M, M, M);   // run lengths are powers of two
+        double P[NSTATE][NSTATE];
+        for (int i = 0; i < NSTATE; ++i)
+            for (int j = 0; j < NSTATE; ++j) P[i][j] = (i == j) ? 1.0 : 0.0;
+        for (int j = 0; j < terms; ++j) {
+            for (int r = 0; r < NSTATE; ++r)
+                for (int cc = 0; cc < NSTATE; ++cc)
+                    (variant == 0 ? dc.Mp[j][r][cc] : dc.Mp32[j][r][cc]) = (float)P[r][cc];
+            mat_mul(M, P, P);
+        }
     }
 }
 
@@ -438,15 +443,15 @@ int setup_device_once(zfb_engine *e) {
                 CK(e, cudaFuncSetAttribute(w.fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         }
     CK(e, cudaFuncSetAttribute(strip_cascade_kernel<KIND_U8_RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)decim_smem(NTHR_SMALL)));
+                               (int)strip_smem()));
     CK(e, cudaFuncSetAttribute(strip_cascade_kernel<KIND_C64_RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)decim_smem(NTHR_SMALL)));
+                               (int)strip_smem()));
     CK(e, cudaFuncSetAttribute(strip_cascade_kernel<KIND_C64_MID>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)decim_smem(NTHR_SMALL)));
+                               (int)strip_smem()));
     CK(e, cudaFuncSetAttribute((strip_cascade_kernel<KIND_U8_RAW, true>), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)decim_smem(NTHR_SMALL)));
+                               (int)strip_smem()));
     CK(e, cudaFuncSetAttribute((strip_cascade_kernel<KIND_C64_RAW, true>), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)decim_smem(NTHR_SMALL)));
+                               (int)strip_smem()));
     for (int kind = 0; kind < 3; ++kind)
         CK(e, cudaFuncSetAttribute(chain_lookup_fn(kind), cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     int rc = fir_run_setup_kind<KIND_C64_RAW>(e);
@@ -742,7 +747,7 @@ void run_decimation_fast(zfb_engine *e, const void *d_in, int gf, int *out_buf) 
     }
     {
         StripParams sp{};
-        sp.st = e->sp0[1];                       // NT = 128 LO tables
+        sp.st = e->sp0[STRIP_NT == NTHR_BIG ? 0 : 1];   // LO tables for STRIP_NT threads per CTA
         sp.st.L = e->strip_len[s0];
         sp.st.T = 0;
         sp.st.strips = 1;
@@ -776,16 +781,16 @@ void run_decimation_fast(zfb_engine *e, const void *d_in, int gf, int *out_buf) 
             sp.st.chan = (const ChannelLo *)e->chan_dev.p;
             sp.st.chan_frames = e->cur_chan_frames;
             if (skind == KIND_U8_RAW) {
-                ZFB_LAUNCH((strip_cascade_kernel<KIND_U8_RAW, true>), grid, dim3(NTHR_SMALL), decim_smem(NTHR_SMALL), st, sp);
+                ZFB_LAUNCH((strip_cascade_kernel<KIND_U8_RAW, true>), grid, dim3(STRIP_NT), strip_smem(), st, sp);
             } else {
-                ZFB_LAUNCH((strip_cascade_kernel<KIND_C64_RAW, true>), grid, dim3(NTHR_SMALL), decim_smem(NTHR_SMALL), st, sp);
+                ZFB_LAUNCH((strip_cascade_kernel<KIND_C64_RAW, true>), grid, dim3(STRIP_NT), strip_smem(), st, sp);
             }
         } else if (skind == KIND_U8_RAW) {
-            ZFB_LAUNCH(strip_cascade_kernel<KIND_U8_RAW>, grid, dim3(NTHR_SMALL), decim_smem(NTHR_SMALL), st, sp);
+            ZFB_LAUNCH(strip_cascade_kernel<KIND_U8_RAW>, grid, dim3(STRIP_NT), strip_smem(), st, sp);
         } else if (skind == KIND_C64_RAW) {
-            ZFB_LAUNCH(strip_cascade_kernel<KIND_C64_RAW>, grid, dim3(NTHR_SMALL), decim_smem(NTHR_SMALL), st, sp);
+            ZFB_LAUNCH(strip_cascade_kernel<KIND_C64_RAW>, grid, dim3(STRIP_NT), strip_smem(), st, sp);
         } else {
-            ZFB_LAUNCH(strip_cascade_kernel<KIND_C64_MID>, grid, dim3(NTHR_SMALL), decim_smem(NTHR_SMALL), st, sp);
+            ZFB_LAUNCH(strip_cascade_kernel<KIND_C64_MID>, grid, dim3(STRIP_NT), strip_smem(), st, sp);
         }
         prof_end(e, pr);
         e->counters[2] += 1;
@@ -1437,7 +1442,7 @@ static int upload_channels(zfb_engine *e, const double *f_demod, int nch) {
         t.phase_inc = (scaled >= 18446744073709551615.0) ? 0ull : (unsigned long long)scaled;
         for (int i = 0; i < 32; ++i) lo_entry(r, i, amp0, t.run[i]);
         for (int i = 0; i < 8; ++i) lo_entry(r, i, amp0 * (double)dc.g, t.dec_small[i]);
-        for (int it = 0; it < 32; ++it) lo_entry(r, (long long)it * NTHR_SMALL * vec, 1.0, t.dec_big[it]);
+        for (int it = 0; it < 32; ++it) lo_entry(r, (long long)it * STRIP_NT * vec, 1.0, t.dec_big[it]);
     }
     int rc = ensure(e, e->chan_dev, (size_t)nch * sizeof(ChannelLo));
     if (rc) return rc;

@@ -314,6 +314,10 @@ inline size_t fir_chain_smem(const FirChainParams &p) {
 // memory traffic than fir_chain_kernel (which stays as the general fallback:
 // ncu showed it at 83 % of the LSU/shared-memory wavefront peak).
 // ===========================================================================
+#ifndef ZFB_FIR_MINB
+#define ZFB_FIR_MINB 2
+#endif
+
 namespace zfb {
 
 constexpr int RUN0 = 32;
@@ -453,7 +457,7 @@ struct FirRunShape {
 };
 
 template <int KIND, int NS, int M0, int M1, int M2, int MC, bool CH = false>
-__global__ void __launch_bounds__(FIR_NT, 2) fir_run_kernel(const FirRunParams p) {
+__global__ void __launch_bounds__(FIR_NT, ZFB_FIR_MINB) fir_run_kernel(const FirRunParams p) {
     using SH = FirRunShape<NS, M0, M1, M2, MC>;
     constexpr int VEC = (KIND == KIND_U8_RAW) ? 8 : 2;
     ZFB_DYN_SMEM(smem_raw);
