@@ -256,6 +256,8 @@ def run_b200(args, w):
         eng.set_group(args.group)
     if args.decim_threads:
         eng.set_option("decim_threads", args.decim_threads)
+    if args.strips_async is not None:
+        eng.set_option("strips_async", args.strips_async)
     eng.configure(w.fs, w.fft_size, w.fft_ratio, w.frame_len, w.window, dtype=w.dtype, flip=w.flip,
                   f_demod=w.f_demod, crop=w.crop, ema_alpha=w.ema_alpha, mode=args.mode)
     # a real (non-default) stream: the engine launches on it, NCCL enqueues on
@@ -382,8 +384,10 @@ def run_b200(args, w):
     if rank == 0:
         peak, peak_src = measured_hbm_peak()
         # dominant kernel = largest share of device time in the timed region
-        total_kernel_ms = sum(v[0] for v in prof.values()) or 1.0
-        top = max(prof, key=lambda k: prof[k][0])
+        # (the edge strips of mode fast run on a side stream beside the FIR interior: their
+        # event interval is not exclusive, so they are left out of the ranking)
+        exclusive = {k: v for k, v in prof.items() if k != "decimate_stage15"} or prof
+        top = max(exclusive, key=lambda k: exclusive[k][0])
         top_ms, top_n = prof[top]
         # algorithmic bytes: every input sample read once; the row
         # bytes (4*W, x3 with EMA) belong to the finalize kernel
@@ -403,8 +407,9 @@ def run_b200(args, w):
             "traffic": ncu_traffic(w.name, top, args.steps * F / max(1, top_n)), "peak_source": peak_src,
             "launches": top_n, "avg_launch_ms": top_ms / max(1, top_n),
             "algorithmic_bytes_per_launch": algo_bytes_total / max(1, top_n),
-            "kernel_share_of_step": top_ms / total_kernel_ms,
-            "kernel_ms": {k: round(v[0], 4) for k, v in prof.items()},
+            "kernel_share_of_step": top_ms / ms,
+            "kernel_ms": {("edge_strips(concurrent)" if k == "decimate_stage15" else k): round(v[0], 4)
+                          for k, v in prof.items()},
             "step_achieved_gbs": step_bytes * args.steps / (ms * 1e-3) / 1e9 * 1.0,
             "note": "fp32-pipe bound, not HBM bound (DESIGN.md 4): FMA pipe ~64 % active in the FIR chain; "
                     "60 % of HBM at 2 B/sample would leave 19 pipe-cycles per sample",
@@ -453,6 +458,7 @@ def main():
     ap.add_argument("--decim-threads", type=int, default=0, help="tuning: 0 auto, 128 or 256")
     ap.add_argument("--mode", default="fast", choices=["exact", "fast"],
                     help="decimator: exact zero-phase IIR everywhere, or polyphase-FIR interior + exact edges")
+    ap.add_argument("--strips-async", type=int, default=None, help="tuning: 0 = edge strips on the main stream")
     ap.add_argument("--lib", default=None, help="tuning: path of an alternative sm_100a build")
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")

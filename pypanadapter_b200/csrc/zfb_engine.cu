@@ -52,6 +52,9 @@ struct zfb_engine {
     std::string err;
 
     cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
+    cudaStream_t aux_stream = nullptr;           // edge strips of mode fast run beside the FIR interior
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    int strips_async = 1;                        // zfb_set_option("strips_async")
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
     bool slot_busy[2] = {false, false};
 
@@ -549,7 +552,7 @@ void plan_tiles(zfb_engine *e) {
 constexpr size_t kMaxProfRecs = 1 << 16;
 
 // returns the index of the open record, or -1 when profiling is off
-int prof_begin(zfb_engine *e, int cls) {
+int prof_begin(zfb_engine *e, int cls, cudaStream_t on = nullptr) {
     if (!e->profiling || e->prof_used.size() >= kMaxProfRecs) return -1;
     zfb_engine::ProfRec r;
     if (!e->prof_free.empty()) {
@@ -559,13 +562,13 @@ int prof_begin(zfb_engine *e, int cls) {
         if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return -1;
     }
     r.cls = cls;
-    cudaEventRecord(r.a, e->stream);
+    cudaEventRecord(r.a, on ? on : e->stream);
     e->prof_used.push_back(r);
     return (int)e->prof_used.size() - 1;
 }
 
-void prof_end(zfb_engine *e, int idx) {
-    if (idx >= 0) cudaEventRecord(e->prof_used[(size_t)idx].b, e->stream);
+void prof_end(zfb_engine *e, int idx, cudaStream_t on = nullptr) {
+    if (idx >= 0) cudaEventRecord(e->prof_used[(size_t)idx].b, on ? on : e->stream);
 }
 
 // the tap sets fastdesign.py produces for the last chain of R = 4 / 8 / >= 16
@@ -650,10 +653,87 @@ void launch_stage(zfb_engine *e, int kind, int v, const StageParams &p, unsigned
 // ZFB_MODE_FAST: FIR chains + exact last stage over the whole frames, then the
 // exact cascade on the two end strips of every frame; leaves the decimated
 // chunks in mid[*out_buf]
-void run_decimation_fast(zfb_engine *e, const void *d_in, int gf, int *out_buf) {
+// the fused tail (up to 4 stages) of the exact edge strips, one CTA per strip,
+// writing the first / last K samples of the decimated chunks in `final_out`
+void launch_fused_strips(zfb_engine *e, const void *d_in, int gf, float2 *final_out, cudaStream_t st) {
+    const zfb_config &c = e->cfg;
+    const int k = e->nstages;
+    const int kf = k < 4 ? k : 4;
+    const int s0 = k - kf;
+    const long long cap = e->strip_cap;
+    StripParams sp{};
+    sp.st = e->sp0[STRIP_NT == NTHR_BIG ? 0 : 1];   // LO tables for STRIP_NT threads per CTA
+    sp.st.L = e->strip_len[s0];
+    sp.st.T = 0;
+    sp.st.strips = 1;
+    int skind;
+    if (s0 == 0) {
+        skind = raw_kind(c);
+        sp.st.in = d_in;
+        sp.st.in_stride = c.frame_len;
+        sp.st.side_in_off = 0;
+        sp.st.flip = c.flip;
+        sp.st.pos_off = e->strip_q[0];
+        sp.st.Lfull = c.frame_len;
+    } else {
+        skind = KIND_C64_MID;
+        sp.st.in = e->sbuf[(s0 - 1) & 1].p;
+        sp.st.in_stride = 2 * cap;
+        sp.st.side_in_off = cap + (e->strip_q[s0] - e->strip_q[s0 - 1] / 2);
+        sp.st.flip = 0;
+        sp.st.pos_off = 0;
+        sp.st.Lfull = sp.st.L;
+    }
+    sp.nstages = kf;
+    for (int s = 0; s < kf; ++s) sp.len[s] = e->strip_len[s0 + s];
+    sp.keep = e->fplan.K;
+    sp.out = final_out;
+    sp.out_stride = e->len[k];
+    sp.ndec = e->len[k];
+    const int pr = prof_begin(e, 15, st);
+    const dim3 grid(2, (unsigned)gf);
+    if (e->cur_nch > 0 && s0 == 0) {
+        sp.st.chan = (const ChannelLo *)e->chan_dev.p;
+        sp.st.chan_frames = e->cur_chan_frames;
+        if (skind == KIND_U8_RAW) {
+            ZFB_LAUNCH((strip_cascade_kernel<KIND_U8_RAW, true>), grid, dim3(STRIP_NT), strip_smem(), st, sp);
+        } else {
+            ZFB_LAUNCH((strip_cascade_kernel<KIND_C64_RAW, true>), grid, dim3(STRIP_NT), strip_smem(), st, sp);
+        }
+    } else if (skind == KIND_U8_RAW) {
+        ZFB_LAUNCH(strip_cascade_kernel<KIND_U8_RAW>, grid, dim3(STRIP_NT), strip_smem(), st, sp);
+    } else if (skind == KIND_C64_RAW) {
+        ZFB_LAUNCH(strip_cascade_kernel<KIND_C64_RAW>, grid, dim3(STRIP_NT), strip_smem(), st, sp);
+    } else {
+        ZFB_LAUNCH(strip_cascade_kernel<KIND_C64_MID>, grid, dim3(STRIP_NT), strip_smem(), st, sp);
+    }
+    prof_end(e, pr, st);
+    e->counters[2] += 1;
+}
+
+// ZFB_MODE_FAST: FIR chains + exact last stage over the whole frames, and the
+// exact cascade on the two end strips of every frame; leaves the decimated
+// chunks in mid[*out_buf].  Returns a CUDA status.
+cudaError_t run_decimation_fast(zfb_engine *e, const void *d_in, int gf, int *out_buf) {
     const zfb_config &c = e->cfg;
     cudaStream_t st = e->stream;
     const int k = e->nstages;
+    const int kf = k < 4 ? k : 4;
+    const int s0 = k - kf;
+    const int b_final = e->nchains & 1;             // every chain flips the ping-pong buffer once
+    float2 *final_out = (float2 *)e->mid[b_final].p;
+    const int K = e->fplan.K;
+    // Strips read only the raw input and own the first / last K decimated samples; the
+    // interior owns the rest, so the two need no order between them: with k <= 4 the
+    // strips go to a side stream and fill the SMs beside the FIR interior.
+    const bool async_strips = e->strips_async && s0 == 0;
+    cudaError_t err = cudaSuccess;
+    if (async_strips) {
+        if ((err = cudaEventRecord(e->ev_fork, st)) != cudaSuccess) return err;      // input ready, buffers free
+        if ((err = cudaStreamWaitEvent(e->aux_stream, e->ev_fork, 0)) != cudaSuccess) return err;
+        launch_fused_strips(e, d_in, gf, final_out, e->aux_stream);
+        if ((err = cudaEventRecord(e->ev_join, e->aux_stream)) != cudaSuccess) return err;
+    }
     const void *src = d_in;
     long long src_stride = c.frame_len;
     int kind = raw_kind(c);
@@ -689,28 +769,28 @@ void run_decimation_fast(zfb_engine *e, const void *d_in, int gf, int *out_buf) 
         b ^= 1;
     }
     const int v = (e->decim_threads == NTHR_BIG) ? 0 : 1;
-    {   // the last decimate call, exact, over the whole (FIR-filtered) chunk
+    {   // the last decimate call, exact, over the whole (FIR-filtered) chunk; it leaves the
+        // K samples at either end to the strips
         const int s = k - 1;
         StageParams p = e->sp0[v];
         p.in = src;
         p.in_stride = src_stride;
-        p.out = (float2 *)e->mid[b].p;
+        p.out = final_out;
         p.out_stride = e->len[k];
         p.L = e->len[s];
         p.T = e->T[s][v];
         p.flip = 0;
         p.strips = 0;
         p.Lfull = p.L;
-        p.w_lo[0] = p.w_lo[1] = 0;
-        p.w_hi[0] = p.w_hi[1] = INT_MAX;
+        p.w_lo[0] = p.w_lo[1] = K;
+        p.w_hi[0] = p.w_hi[1] = e->len[k] - K;
         launch_stage(e, KIND_C64_MID, v, p, (unsigned)e->tiles[s][v], (unsigned)gf, k - 1);
     }
-    *out_buf = b;
-    // exact edge strips.  The last (up to) 4 stages of a strip fit one 8192-sample
-    // region and run fused in ONE CTA per strip (strip_cascade_kernel); for deeper
-    // zooms the first stages' strips are longer and go through the tiled kernel.
-    const int kf = k < 4 ? k : 4;
-    const int s0 = k - kf;
+    *out_buf = b_final;
+    if (async_strips) return cudaStreamWaitEvent(st, e->ev_join, 0);
+
+    // deeper zooms: the first stages' strips are longer than one region and go through the
+    // tiled kernel (on the main stream), then the fused tail
     const int tmax = tmax_of(v == 0 ? NTHR_BIG : NTHR_SMALL);
     const long long cap = e->strip_cap;
     for (int s = 0; s < s0; ++s) {
@@ -745,56 +825,8 @@ void run_decimation_fast(zfb_engine *e, const void *d_in, int gf, int *out_buf) 
         launch_stage(e, s == 0 ? raw_kind(c) : KIND_C64_MID, v, p, (unsigned)((L + T - 1) / T),
                      (unsigned)(2 * gf), 15);
     }
-    {
-        StripParams sp{};
-        sp.st = e->sp0[STRIP_NT == NTHR_BIG ? 0 : 1];   // LO tables for STRIP_NT threads per CTA
-        sp.st.L = e->strip_len[s0];
-        sp.st.T = 0;
-        sp.st.strips = 1;
-        int skind;
-        if (s0 == 0) {
-            skind = raw_kind(c);
-            sp.st.in = d_in;
-            sp.st.in_stride = c.frame_len;
-            sp.st.side_in_off = 0;
-            sp.st.flip = c.flip;
-            sp.st.pos_off = e->strip_q[0];
-            sp.st.Lfull = c.frame_len;
-        } else {
-            skind = KIND_C64_MID;
-            sp.st.in = e->sbuf[(s0 - 1) & 1].p;
-            sp.st.in_stride = 2 * cap;
-            sp.st.side_in_off = cap + (e->strip_q[s0] - e->strip_q[s0 - 1] / 2);
-            sp.st.flip = 0;
-            sp.st.pos_off = 0;
-            sp.st.Lfull = sp.st.L;
-        }
-        sp.nstages = kf;
-        for (int s = 0; s < kf; ++s) sp.len[s] = e->strip_len[s0 + s];
-        sp.keep = e->fplan.K;
-        sp.out = (float2 *)e->mid[b].p;
-        sp.out_stride = e->len[k];
-        sp.ndec = e->len[k];
-        const int pr = prof_begin(e, 15);
-        const dim3 grid(2, (unsigned)gf);
-        if (e->cur_nch > 0 && s0 == 0) {
-            sp.st.chan = (const ChannelLo *)e->chan_dev.p;
-            sp.st.chan_frames = e->cur_chan_frames;
-            if (skind == KIND_U8_RAW) {
-                ZFB_LAUNCH((strip_cascade_kernel<KIND_U8_RAW, true>), grid, dim3(STRIP_NT), strip_smem(), st, sp);
-            } else {
-                ZFB_LAUNCH((strip_cascade_kernel<KIND_C64_RAW, true>), grid, dim3(STRIP_NT), strip_smem(), st, sp);
-            }
-        } else if (skind == KIND_U8_RAW) {
-            ZFB_LAUNCH(strip_cascade_kernel<KIND_U8_RAW>, grid, dim3(STRIP_NT), strip_smem(), st, sp);
-        } else if (skind == KIND_C64_RAW) {
-            ZFB_LAUNCH(strip_cascade_kernel<KIND_C64_RAW>, grid, dim3(STRIP_NT), strip_smem(), st, sp);
-        } else {
-            ZFB_LAUNCH(strip_cascade_kernel<KIND_C64_MID>, grid, dim3(STRIP_NT), strip_smem(), st, sp);
-        }
-        prof_end(e, pr);
-        e->counters[2] += 1;
-    }
+    launch_fused_strips(e, d_in, gf, final_out, st);
+    return cudaSuccess;
 }
 
 // one group of frames, all resident on the device, through the whole chain
@@ -807,7 +839,7 @@ int run_group(zfb_engine *e, const void *d_in, int gf, float *d_rows) {
 
     if (e->fast_active) {
         int ob = 0;
-        run_decimation_fast(e, d_in, gf, &ob);
+        CK(e, run_decimation_fast(e, d_in, gf, &ob));
         e->final_buf = ob;
         src = e->mid[ob].p;
         src_stride = e->len[e->nstages];
@@ -1109,7 +1141,10 @@ int zfb_create(int device, zfb_engine **out) {
         cudaDeviceProp prop;
         if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) e->sm_count = prop.multiProcessorCount;
         if (cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
-            cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
+            cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&e->aux_stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming) != cudaSuccess) {
             rc = fail(nullptr, ZFB_ECUDA, "stream creation failed: %s", cudaGetErrorString(cudaGetLastError()));
             break;
         }
@@ -1141,6 +1176,7 @@ void zfb_destroy(zfb_engine *e) {
     cudaSetDevice(e->device);
     if (e->own_stream) cudaStreamSynchronize(e->own_stream);
     if (e->copy_stream) cudaStreamSynchronize(e->copy_stream);
+    if (e->aux_stream) cudaStreamSynchronize(e->aux_stream);
     DevBuf *bufs[] = {&e->window, &e->winfft, &e->twiddle, &e->mid[0], &e->mid[1], &e->pow, &e->rows_tmp, &e->ema,
                       &e->ema_valid, &e->ring, &e->stage_in[0], &e->stage_in[1], &e->big};
     for (DevBuf *b : bufs) release(*b);
@@ -1162,6 +1198,9 @@ void zfb_destroy(zfb_engine *e) {
     if (e->h_rows) cudaFreeHost(e->h_rows);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+    if (e->aux_stream) cudaStreamDestroy(e->aux_stream);
+    if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+    if (e->ev_join) cudaEventDestroy(e->ev_join);
     delete e;
 }
 
@@ -1400,6 +1439,10 @@ int zfb_set_option(zfb_engine *e, const char *name, long long value) {
     if (strcmp(name, "welch_splits") == 0) {
         if (value < 0 || value > 16) return fail(e, ZFB_EINVAL, "welch_splits must be in [0, 16]");
         e->welch_splits = (int)value;
+        return ZFB_OK;
+    }
+    if (strcmp(name, "strips_async") == 0) {
+        e->strips_async = value ? 1 : 0;
         return ZFB_OK;
     }
     if (strcmp(name, "fir_generic") == 0) {
