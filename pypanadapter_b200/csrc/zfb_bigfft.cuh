@@ -180,6 +180,115 @@ __global__ void __launch_bounds__(BIG_THREADS, 2) bigfft_row_kernel(const BigPar
     }
 }
 
+// ===========================================================================
+// N = 2^14 .. 2^17: decimation in frequency by 16 in front of the one-CTA FFT.
+//   X[16k + r] = FFT_S( Z_r )[k],  S = N/16,
+//   Z_r[n] = W_N^(r n) * sum_q x[n + S q] W_16^(q r),   x = window * (segment - mean)
+// big_halfsum_kernel : sums of the half-segment blocks (segment mean = two of them / N),
+// big_r16_kernel     : detrend + window + 16-point DFT across the 16 blocks + twiddle,
+//                      coalesced in and out -> scratch [frame][r][segment][S],
+// then welch_kernel (prepared = 1) runs its shared-memory FFT on every S-point block
+// and accumulates |X|^2 over the segments; big_gather_kernel puts bin 16k + r of
+// residue r back in place (fftshift + crop).  Exact detrend (no post-FFT correction)
+// and ~half the instructions of the generic four-step kernels above.
+// ===========================================================================
+struct BigR16Params {
+    const void   *in;
+    long long     in_stride;
+    int           len, flip, log2N, hop, nseg;
+    const float  *window;      // N taps
+    const float2 *twiddle;     // N entries exp(-2 pi i k / N)
+    float2       *halfsum;     // [frames][nseg + 1]
+    float2       *scratch;     // [frames][16][nseg][S]
+};
+
+template <int KIND>
+__global__ void __launch_bounds__(256) big_halfsum_kernel(const BigR16Params p) {
+    __shared__ float2 red[33];
+    const int h = blockIdx.x, frame = blockIdx.y, t = threadIdx.x;
+    const size_t esz = (KIND == KIND_U8_RAW) ? 2 : 8;
+    const char *frame_in = (const char *)p.in + (size_t)frame * (size_t)p.in_stride * esz;
+    const int base = h * p.hop;
+    float2 sum = make_float2(0.f, 0.f);
+    for (int i = t; i < p.hop; i += 256) sum = cadd(sum, welch_fetch<KIND>(frame_in, base + i, p.len, p.flip));
+    sum = block_sum<256>(sum, t, red);
+    if (t == 0) p.halfsum[(size_t)frame * (p.nseg + 1) + h] = sum;
+}
+
+// 16-point forward DFT, natural order in and out: X[r] = sum_q v[q] W16^(q r)
+__device__ __forceinline__ void dft16(float2 (&v)[16]) {
+    // q = 4 q1 + q0, r = r1 + 4 r0:  4-point DFTs over q1, twiddle W16^(q0 r1), 4-point DFTs over q0
+    const float c1 = 0.92387953251128673848f, s1 = 0.38268343236508978178f;   // cos, sin(pi/8)
+    const float h = 0.70710678118654752440f;
+    float2 t[4][4];                       // t[q0][r1]
+#pragma unroll
+    for (int q0 = 0; q0 < 4; ++q0) {
+        float2 a0 = v[q0], a1 = v[4 + q0], a2 = v[8 + q0], a3 = v[12 + q0];
+        dft4(a0, a1, a2, a3);
+        t[q0][0] = a0; t[q0][1] = a1; t[q0][2] = a2; t[q0][3] = a3;
+    }
+    // W16^m = exp(-2 pi i m / 16), m = q0 * r1
+    const float2 w1 = make_float2(c1, -s1), w2 = make_float2(h, -h), w3 = make_float2(s1, -c1);
+    const float2 w6 = make_float2(-h, -h), w9 = make_float2(-c1, s1);
+    t[1][1] = cmul(t[1][1], w1); t[1][2] = cmul(t[1][2], w2); t[1][3] = cmul(t[1][3], w3);
+    t[2][1] = cmul(t[2][1], w2); t[2][2] = mul_mi(t[2][2]);   t[2][3] = cmul(t[2][3], w6);
+    t[3][1] = cmul(t[3][1], w3); t[3][2] = cmul(t[3][2], w6); t[3][3] = cmul(t[3][3], w9);
+#pragma unroll
+    for (int r1 = 0; r1 < 4; ++r1) {
+        float2 a0 = t[0][r1], a1 = t[1][r1], a2 = t[2][r1], a3 = t[3][r1];
+        dft4(a0, a1, a2, a3);
+        v[r1] = a0; v[r1 + 4] = a1; v[r1 + 8] = a2; v[r1 + 12] = a3;
+    }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(256) big_r16_kernel(const BigR16Params p) {
+    const int N = 1 << p.log2N, S = N >> 4;
+    const int n = blockIdx.x * 256 + threadIdx.x;          // < S
+    const int s = blockIdx.y, frame = blockIdx.z;
+    const size_t esz = (KIND == KIND_U8_RAW) ? 2 : 8;
+    const char *frame_in = (const char *)p.in + (size_t)frame * (size_t)p.in_stride * esz;
+    const int base = s * p.hop;
+    const float2 *hs = p.halfsum + (size_t)frame * (p.nseg + 1) + s;
+    const float inv_n = 1.0f / (float)N;
+    const float2 mean = make_float2((hs[0].x + hs[1].x) * inv_n, (hs[0].y + hs[1].y) * inv_n);
+    float2 v[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+        const int idx = n + S * q;
+        const float2 x = welch_fetch<KIND>(frame_in, base + idx, p.len, p.flip);
+        const float w = __ldg(p.window + idx);
+        v[q] = make_float2((x.x - mean.x) * w, (x.y - mean.y) * w);
+    }
+    dft16(v);
+    float2 *out = p.scratch + (((size_t)frame * 16) * p.nseg + s) * (size_t)S + n;
+    const size_t rstride = (size_t)p.nseg * S;
+    out[0] = v[0];
+#pragma unroll
+    for (int r = 1; r < 16; ++r) out[r * rstride] = cmul(v[r], __ldg(p.twiddle + ((r * n) & (N - 1))));
+}
+
+// pow16 [frames*16][nsplit][S] (fftshifted sub-spectra) -> pow [frames][1][W]
+struct BigGatherParams {
+    const float *pow16;
+    float       *pow_out;
+    int          log2N, nsplit, W, frames;
+};
+
+__global__ void big_gather_kernel(const BigGatherParams p) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)p.frames * p.W) return;
+    const int f = (int)(i / p.W), col = (int)(i % p.W);
+    const int N = 1 << p.log2N, S = N >> 4;
+    const int bin = (col - p.W / 2 + N) & (N - 1);          // undo fftshift + centre crop
+    const int r = bin & 15, k = bin >> 4;
+    const int sub = (k + S / 2) & (S - 1);                  // welch_kernel stored its block fftshifted
+    const float *src = p.pow16 + ((size_t)(f * 16 + r) * p.nsplit) * S + sub;
+    float acc = 0.f;
+    for (int sp = 0; sp < p.nsplit; ++sp) acc += src[(size_t)sp * S];
+    p.pow_out[(size_t)f * p.W + col] = acc;
+}
+
 // N = N1*N2 split used for a given log2N
 inline void big_split(int log2N, int &lm1, int &lm2) {
     lm1 = (log2N + 1) / 2;

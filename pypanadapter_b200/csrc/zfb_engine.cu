@@ -34,6 +34,8 @@ constexpr int kMaxStages = 16;
 constexpr int kMinLog2N = 5;          // 32
 constexpr int kMaxLog2Small = 13;     // 8192: one CTA per segment
 constexpr int kMaxLog2N = 18;         // 262144: four-step path
+constexpr int kMinLog2R16 = 16;       // 65536 and 131072: radix-16 front pass + one-CTA FFT of N/16
+constexpr int kMaxLog2R16 = 17;       // (measured: 16384 is faster on the generic four-step kernels)
 constexpr double kPi = 3.14159265358979323846264338327950288;
 
 thread_local std::string g_create_error;
@@ -73,7 +75,7 @@ struct zfb_engine {
     int nsplit_cap = 1;
     StageParams sp0[2]{};              // LO tables of stage 0 for NT = 256 / 128
 
-    DevBuf window, winfft, twiddle, mid[2], pow, rows_tmp, ema, ema_valid, ring, stage_in[2], big;
+    DevBuf window, winfft, twiddle, twiddle_sub, pow16, mid[2], pow, rows_tmp, ema, ema_valid, ring, stage_in[2], big;
     void  *h_stage[2] = {nullptr, nullptr};
     size_t h_stage_cap[2] = {0, 0};
     float *h_rows = nullptr;
@@ -525,7 +527,7 @@ int choose_group(const zfb_engine *e, bool fast) {
     size_t budget = 256ull << 20;
     if (e->log2N > kMaxLog2Small) {
         per_frame += (size_t)e->nseg * ((size_t)8 << e->log2N);       // four-step scratch
-        budget = 512ull << 20;
+        budget = (e->log2N >= kMinLog2R16 && e->log2N <= kMaxLog2R16) ? (1100ull << 20) : (512ull << 20);
     }
     if (per_frame == 0) return 2048;
     long long g = (long long)budget / (long long)per_frame;
@@ -908,6 +910,71 @@ int run_group(zfb_engine *e, const void *d_in, int gf, float *d_rows) {
         ZFB_LAUNCH(we.fn, dim3((unsigned)nsplit, (unsigned)gf), dim3((unsigned)we.threads), we.smem, st, w);
         prof_end(e, pr);
         e->counters[2] += 1;
+    } else if (e->log2N >= kMinLog2R16 && e->log2N <= kMaxLog2R16) {
+        // radix-16 decimation in frequency, then the one-CTA FFT on every block of N/16
+        const int lS = e->log2N - 4, S = 1 << lS;
+        int want = e->welch_splits > 0 ? e->welch_splits : 4;
+        if (want > 4) want = 4;                          // pow16 is sized for 4 splits
+        if (want > e->nseg) want = e->nseg;
+        if (want < 1) want = 1;
+        const int per = (e->nseg + want - 1) / want;
+        const int ns16 = (e->nseg + per - 1) / per;
+        BigR16Params r{};
+        r.in = src;
+        r.in_stride = src_stride;
+        r.len = e->len[e->nstages];
+        r.flip = (e->nstages == 0) ? c.flip : 0;
+        r.log2N = e->log2N;
+        r.hop = e->hop;
+        r.nseg = e->nseg;
+        r.window = (const float *)e->window.p;
+        r.twiddle = (const float2 *)e->twiddle.p;
+        r.scratch = (float2 *)e->big.p;
+        r.halfsum = r.scratch + ((size_t)e->group * (size_t)e->nseg << e->log2N);
+        const int pr = prof_begin(e, 16);
+        const dim3 gh((unsigned)(e->nseg + 1), (unsigned)gf), gr((unsigned)(S / 256), (unsigned)e->nseg, (unsigned)gf);
+        if (kind == KIND_C64_RAW) {
+            ZFB_LAUNCH(big_halfsum_kernel<KIND_C64_RAW>, gh, dim3(256), 0, st, r);
+            ZFB_LAUNCH(big_r16_kernel<KIND_C64_RAW>, gr, dim3(256), 0, st, r);
+        } else if (kind == KIND_U8_RAW) {
+            ZFB_LAUNCH(big_halfsum_kernel<KIND_U8_RAW>, gh, dim3(256), 0, st, r);
+            ZFB_LAUNCH(big_r16_kernel<KIND_U8_RAW>, gr, dim3(256), 0, st, r);
+        } else {
+            ZFB_LAUNCH(big_halfsum_kernel<KIND_C64_MID>, gh, dim3(256), 0, st, r);
+            ZFB_LAUNCH(big_r16_kernel<KIND_C64_MID>, gr, dim3(256), 0, st, r);
+        }
+        prof_end(e, pr);
+        WelchParams w{};
+        w.in = r.scratch;
+        w.in_stride = (long long)e->nseg * S;
+        w.len = e->nseg * S;
+        w.flip = 0;
+        w.nperseg = S;
+        w.hop = S;
+        w.nseg = e->nseg;
+        w.seg_per_split = per;
+        w.nsplit = ns16;
+        w.reuse = 0;
+        w.prepared = 1;
+        w.window = nullptr;
+        w.twiddle = (const float2 *)e->twiddle_sub.p;
+        w.W = S;
+        w.pow_out = (float *)e->pow16.p;
+        WelchEntry we = welch_lookup(lS, KIND_C64_MID);
+        const int pr2 = prof_begin(e, 17);
+        ZFB_LAUNCH(we.fn, dim3((unsigned)ns16, (unsigned)(gf * 16)), dim3((unsigned)we.threads), we.smem, st, w);
+        BigGatherParams g{};
+        g.pow16 = (const float *)e->pow16.p;
+        g.pow_out = (float *)e->pow.p;
+        g.log2N = e->log2N;
+        g.nsplit = ns16;
+        g.W = e->W;
+        g.frames = gf;
+        const long long cellsg = (long long)gf * e->W;
+        ZFB_LAUNCH(big_gather_kernel, dim3((unsigned)((cellsg + 255) / 256)), dim3(256), 0, st, g);
+        prof_end(e, pr2);
+        e->counters[2] += 4;
+        nsplit = 1;
     } else {
         int want = e->welch_splits > 0 ? e->welch_splits : 4;
         if (want > e->nseg) want = e->nseg;
@@ -1177,7 +1244,7 @@ void zfb_destroy(zfb_engine *e) {
     if (e->own_stream) cudaStreamSynchronize(e->own_stream);
     if (e->copy_stream) cudaStreamSynchronize(e->copy_stream);
     if (e->aux_stream) cudaStreamSynchronize(e->aux_stream);
-    DevBuf *bufs[] = {&e->window, &e->winfft, &e->twiddle, &e->mid[0], &e->mid[1], &e->pow, &e->rows_tmp, &e->ema,
+    DevBuf *bufs[] = {&e->window, &e->winfft, &e->twiddle, &e->twiddle_sub, &e->pow16, &e->mid[0], &e->mid[1], &e->pow, &e->rows_tmp, &e->ema,
                       &e->ema_valid, &e->ring, &e->stage_in[0], &e->stage_in[1], &e->big};
     for (DevBuf *b : bufs) release(*b);
     for (int i = 0; i < 2; ++i) {
@@ -1355,6 +1422,20 @@ int zfb_configure(zfb_engine *e, const zfb_config *cfg) {
     if (rc) return rc;
     if (l2 > kMaxLog2Small) {
         rc = ensure(e, e->big, big_scratch_bytes(l2, g.nseg, e->group));
+        if (rc) return rc;
+    }
+    if (l2 >= kMinLog2R16 && l2 <= kMaxLog2R16) {
+        const int S = N >> 4;
+        std::vector<float2> tws((size_t)S);
+        for (int k = 0; k < S; ++k) {
+            const double a = -2.0 * kPi * (double)k / (double)S;
+            tws[(size_t)k] = make_float2((float)cos(a), (float)sin(a));
+        }
+        rc = ensure(e, e->twiddle_sub, tws.size() * sizeof(float2));
+        if (rc) return rc;
+        CK(e, cudaMemcpyAsync(e->twiddle_sub.p, tws.data(), tws.size() * sizeof(float2), cudaMemcpyHostToDevice, e->stream));
+        CK(e, cudaStreamSynchronize(e->stream));
+        rc = ensure(e, e->pow16, (size_t)e->group * 4 * (size_t)N * sizeof(float));   // <= 4 splits
         if (rc) return rc;
     }
     rc = ensure(e, e->ema, (size_t)e->W * sizeof(float));

@@ -33,6 +33,7 @@ struct WelchParams {
     int          seg_per_split;   // segments handled by one CTA
     int          nsplit;          // CTAs per frame (gridDim.x)
     int          reuse;           // hop == N/2 && nperseg == N: register reuse
+    int          prepared;        // 1: blocks are already detrended + windowed (radix-16 front pass)
     const float *window;      // nperseg taps
     const float2*twiddle;     // N entries exp(-2 pi i k / N)
     int          W;           // row width
@@ -248,19 +249,24 @@ welch_kernel(const WelchParams p) {
                              : make_float2(0.f, 0.f);
             }
         }
-        float2 sum = make_float2(0.f, 0.f);
-#pragma unroll
-        for (int m = 0; m < PPT; ++m) sum = cadd(sum, raw[m]);
-        // detrend='constant': subtract the segment's complex mean
-        sum = block_sum<S::NTHREADS>(sum, tid, red);
-        const float2 mean = make_float2(sum.x * inv_n, sum.y * inv_n);
         float2 v[PPT];
+        if (p.prepared) {
 #pragma unroll
-        for (int m = 0; m < PPT; ++m) {
-            const int idx = tid + m * NT;
-            const float w = (active && idx < p.nperseg) ? __ldg(p.window + idx) : 0.f;
-            v[m].x = (raw[m].x - mean.x) * w;
-            v[m].y = (raw[m].y - mean.y) * w;
+            for (int m = 0; m < PPT; ++m) v[m] = raw[m];
+        } else {
+            float2 sum = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int m = 0; m < PPT; ++m) sum = cadd(sum, raw[m]);
+            // detrend='constant': subtract the segment's complex mean
+            sum = block_sum<S::NTHREADS>(sum, tid, red);
+            const float2 mean = make_float2(sum.x * inv_n, sum.y * inv_n);
+#pragma unroll
+            for (int m = 0; m < PPT; ++m) {
+                const int idx = tid + m * NT;
+                const float w = (active && idx < p.nperseg) ? __ldg(p.window + idx) : 0.f;
+                v[m].x = (raw[m].x - mean.x) * w;
+                v[m].y = (raw[m].y - mean.y) * w;
+            }
         }
         fft_block<LOG2N, PPT>(v, tid, p.twiddle, sm);
 #pragma unroll
