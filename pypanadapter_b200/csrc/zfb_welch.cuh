@@ -108,10 +108,26 @@ __device__ __forceinline__ void fft_pass(float2 (&v)[PPT], int tid, int nt, int 
 #pragma unroll
         for (int r = 0; r < RADIX; ++r) a[r] = v[c + NB * r];
         if (log2Ns > 0 && active) {
-            // twiddle exp(-2 pi i r k / (Ns*RADIX)) = tw[r * k * 2^log2tw/(Ns*RADIX)]
+            // twiddle w^r, w = exp(-2 pi i k / (Ns*RADIX)) = tw[k * 2^log2tw/(Ns*RADIX)].
+            // The table lookups of a warp are scattered (k differs per lane): ncu showed
+            // the LSU/L1 pipe at 74 % with one lookup per r, so only w, w^2, w^4 are
+            // loaded and the other powers are one complex product each.
             const int step = k << (log2tw - log2Ns - LR);
-#pragma unroll
-            for (int r = 1; r < RADIX; ++r) a[r] = cmul(a[r], __ldg(tw + r * step));
+            const float2 w1 = __ldg(tw + step);
+            a[1] = cmul(a[1], w1);
+            if (RADIX >= 4) {
+                const float2 w2 = __ldg(tw + 2 * step);
+                const float2 w3 = cmul(w1, w2);
+                a[2] = cmul(a[2], w2);
+                a[3] = cmul(a[3], w3);
+                if (RADIX == 8) {
+                    const float2 w4 = __ldg(tw + 4 * step);
+                    a[4] = cmul(a[4], w4);
+                    a[5] = cmul(a[5], cmul(w1, w4));
+                    a[6] = cmul(a[6], cmul(w2, w4));
+                    a[7] = cmul(a[7], cmul(w3, w4));
+                }
+            }
         }
         if (RADIX == 8) dft8(a);
         else if (RADIX == 4) dft4(a[0], a[1], a[2], a[3]);
