@@ -263,9 +263,21 @@ __global__ void __launch_bounds__(256) big_r16_kernel(const BigR16Params p) {
     dft16(v);
     float2 *out = p.scratch + (((size_t)frame * 16) * p.nseg + s) * (size_t)S + n;
     const size_t rstride = (size_t)p.nseg * S;
+    // W_N^(r n), r = 1..15, from four table lookups (n, 2n, 4n, 8n) and products
+    float2 w[16];
+    w[1] = __ldg(p.twiddle + n);
+    w[2] = __ldg(p.twiddle + ((2 * n) & (N - 1)));
+    w[4] = __ldg(p.twiddle + ((4 * n) & (N - 1)));
+    w[8] = __ldg(p.twiddle + ((8 * n) & (N - 1)));
+    w[3] = cmul(w[1], w[2]);
+    w[5] = cmul(w[1], w[4]);
+    w[6] = cmul(w[2], w[4]);
+    w[7] = cmul(w[3], w[4]);
+#pragma unroll
+    for (int r = 9; r < 16; ++r) w[r] = cmul(w[r - 8], w[8]);
     out[0] = v[0];
 #pragma unroll
-    for (int r = 1; r < 16; ++r) out[r * rstride] = cmul(v[r], __ldg(p.twiddle + ((r * n) & (N - 1))));
+    for (int r = 1; r < 16; ++r) out[r * rstride] = cmul(v[r], w[r]);
 }
 
 // pow16 [frames*16][nsplit][S] (fftshifted sub-spectra) -> pow [frames][1][W]
