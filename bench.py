@@ -256,6 +256,8 @@ def run_b200(args, w):
         eng.set_group(args.group)
     if args.decim_threads:
         eng.set_option("decim_threads", args.decim_threads)
+    if args.welch_splits:
+        eng.set_option("welch_splits", args.welch_splits)
     if args.strips_async is not None:
         eng.set_option("strips_async", args.strips_async)
     eng.configure(w.fs, w.fft_size, w.fft_ratio, w.frame_len, w.window, dtype=w.dtype, flip=w.flip,
@@ -458,6 +460,7 @@ def main():
     ap.add_argument("--decim-threads", type=int, default=0, help="tuning: 0 auto, 128 or 256")
     ap.add_argument("--mode", default="fast", choices=["exact", "fast"],
                     help="decimator: exact zero-phase IIR everywhere, or polyphase-FIR interior + exact edges")
+    ap.add_argument("--welch-splits", type=int, default=0, help="tuning: CTAs per frame in the Welch kernel")
     ap.add_argument("--strips-async", type=int, default=None, help="tuning: 0 = edge strips on the main stream")
     ap.add_argument("--lib", default=None, help="tuning: path of an alternative sm_100a build")
     ap.add_argument("--e2e-steps", type=int, default=20)

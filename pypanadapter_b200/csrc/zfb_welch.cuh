@@ -354,7 +354,7 @@ __global__ void ema_rows_kernel(const FinalizeParams p) {
     if (col >= p.W) return;
     bool have = (*p.ema_valid != 0);
     float a = have ? p.ema_state[col] : 0.f;
-    constexpr int CH = 16;
+    constexpr int CH = 64;                // loads in flight: the walk is load-latency bound
     const size_t stride = (size_t)p.nsplit * p.W;
     for (int f0 = 0; f0 < p.nframes; f0 += CH) {
         float pw[CH];
