@@ -7,7 +7,7 @@ near-Gaussian noise) plus a tone, reproducible on the host in numpy; a
 deterministic subset of rows is regenerated on the host and checked against
 the oracle (0.01 dB20 above the floor, peak bin exact).
 
-    python tools/cfg3_job.py [--samples 1e10] [--batch 64] [--check 6]
+    python tests/tools/cfg3_job.py [--samples 1e10] [--batch 64] [--check 6]
 
 torch is used only to fill device buffers; every row comes from the engine.
 """
@@ -21,7 +21,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 FS = 2.4e6

@@ -2,7 +2,7 @@
 """Single-frame latency of the drop-in surface (the live use case: 10 rows/s
 of ~0.24 M samples): wall time of one call, host to host.
 
-    python tools/latency.py
+    python tests/tools/latency.py
 """
 from __future__ import annotations
 
@@ -14,7 +14,7 @@ import types
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 

@@ -3,7 +3,7 @@
 avg = max(R, 16), complex64, Hamming) -- device-resident throughput of the
 engine next to the CPU oracle port (one core, one frame) on the same box.
 
-    python tools/sweep.py [--out profiles/sweep.jsonl] [--budget-mb 256] [--no-cpu]
+    python tests/tools/sweep.py [--out profiles/sweep.jsonl] [--budget-mb 256] [--no-cpu]
 
 Prints one JSON line per grid point and a markdown table at the end.
 """
@@ -17,7 +17,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 
