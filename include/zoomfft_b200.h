@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define ZFB_ABI_VERSION 1
+#define ZFB_ABI_VERSION 2
 
 /* status codes */
 #define ZFB_OK            0
@@ -183,6 +183,33 @@ int  zfb_read_rows(zfb_engine *e, int age, int nrows, float *h_out);
  * that was computed elsewhere, S:1638-1652). */
 int  zfb_ring_push_rows(zfb_engine *e, const float *h_rows, int nrows);
 
+/* ---- waterfall image and autolevel on the device -----------
+ * Replaces Waterfall.init_image / image_update's img_array bookkeeping
+ * (S:1625-1662: -500 fill, grid columns, np.roll of the whole image per row,
+ * tick marks) and the level -> colour-table mapping pyqtgraph applies to it
+ * (S:1592-1594 setLevels, S:1612-1623 lookuptable, S:1664 setImage): the
+ * [height][row_width] image the reference would hold after `rows_seen`
+ * image_update calls with AppState.scroll = `scroll` is produced from the ring
+ * by one kernel when it is displayed.
+ *   kind ZFB_IMAGE_F32 : float32 img_array itself
+ *   kind ZFB_IMAGE_U8  : colour indices clip(trunc((v-minlev)*256/(maxlev-minlev)),0,255)
+ *   kind ZFB_IMAGE_RGBA: lut_rgba[index] (256 x 4 bytes, R G B A in memory order)
+ * `out` is a host buffer (blocks until it is filled) or, with out_on_device
+ * != 0, a device buffer (asynchronous on the engine's stream). */
+#define ZFB_IMAGE_F32  0
+#define ZFB_IMAGE_U8   1
+#define ZFB_IMAGE_RGBA 2
+int  zfb_ring_image(zfb_engine *e, int height, int scroll, int64_t rows_seen,
+                    int kind, double minlev, double maxlev,
+                    const uint8_t *lut_rgba, void *out, int out_on_device);
+/* Replaces Waterfall.autolevel's np.percentile(img_array[img_array < 0],
+ * [2, 98]) (S:1676): out_values[i] = the q[i]-quantile (0..1, numpy's default
+ * linear interpolation between exact order statistics) of the image pixels
+ * below zero; *out_count = how many there are (0: values are NaN). */
+int  zfb_ring_quantiles(zfb_engine *e, int height, int scroll, int64_t rows_seen,
+                        const double *q, int nq, double *out_values,
+                        int64_t *out_count);
+
 /* ---- pinned sample ring with double-buffered device mirror -------------
  * Replaces Data.data (T:1415-1421) and the copy-in of Data.add (T:1447): the
  * producer thread writes chunks into pinned host memory and each chunk is sent
@@ -224,8 +251,9 @@ int  zfb_get_counters(const zfb_engine *e, uint64_t out5[5]);
 /* kernel classes: 0..15 = decimate-by-2 stage s (replaces scipy.signal.
  * decimate call s of the loop at S:2097-2098), 16 = Welch kernel / four-step
  * column pass, 17 = four-step row pass (both: scipy.signal.welch, S:2111),
- * 18 = row finalisation (S:2114-2119 + EMA). */
-#define ZFB_PROF_CLASSES 19
+ * 18 = row finalisation (S:2114-2119 + EMA), 19 = waterfall image
+ * (S:1625-1664), 20 = autolevel selection sweep (S:1676). */
+#define ZFB_PROF_CLASSES 21
 /* on != 0: bracket every kernel launch with CUDA events on the engine's
  * stream (no host synchronisation is added). */
 int  zfb_set_profiling(zfb_engine *e, int on);

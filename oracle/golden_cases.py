@@ -150,3 +150,17 @@ def case_by_name(name):
         if c["name"] == name:
             return c
     raise KeyError(name)
+
+
+def waterfall_rows_ramp():
+    """70 rows of width 256 (wraps the 64-row image): row i = -100 - i + 0.01 x."""
+    return [np.full(256, -100.0 - i) + np.arange(256) * 0.01 for i in range(70)]
+
+
+def waterfall_rows_noise(n=40, width=256, seed=20260202):
+    """n < 64 rows of float32-representable dB values around -150 (the -500
+    fill is still part of the image): device rows equal the reference's."""
+    rng = np.random.default_rng(seed)
+    return [(-150.0 + 10.0 * rng.standard_normal(width)).astype(np.float32).astype(np.float64)
+            for _ in range(n)]
+

@@ -75,19 +75,27 @@ def main():
                         trace=trace, tail=tail, max_size=max_size)
 
     # Waterfall image after 70 rows of width 256 (wraps the 64-row image)
-    rows_wf = [np.full(256, -100.0 - i) + np.arange(256) * 0.01
-               for i in range(70)]
+    rows_wf = gc.waterfall_rows_ramp()
     img_pos = rh.waterfall_rows(rows_wf, scroll=1)
     img_neg = rh.waterfall_rows(rows_wf, scroll=-1)
-    np.savez_compressed(os.path.join(OUT, "waterfall.npz"), img_pos=img_pos,
-                        img_neg=img_neg)
+    # the reference's own autolevel (S:1668-1680) on those images and on a
+    # partly filled image of noise rows
+    wf = dict(img_pos=img_pos, img_neg=img_neg)
+    for key, rows_a, scroll in (("ramp_pos", rows_wf, 1), ("ramp_neg", rows_wf, -1),
+                                ("noise_pos", gc.waterfall_rows_noise(), 1),
+                                ("noise_neg", gc.waterfall_rows_noise(), -1)):
+        levels, ret = rh.waterfall_autolevel(rows_a, scroll)
+        wf["auto_" + key] = levels
+        wf["autoret_" + key] = ret
+    wf["img_noise_pos"] = rh.waterfall_rows(gc.waterfall_rows_noise(), scroll=1)
+    np.savez_compressed(os.path.join(OUT, "waterfall.npz"), **wf)
 
     with open(os.path.join(OUT, "MANIFEST.json"), "w") as f:
         json.dump({"numpy": np.__version__, "scipy": scipy.__version__,
                    "generator": "python -m oracle.make_golden",
                    "source": "reference methods ApplicationDisplay.update/"
                              "zoomfft, PSD.update, Data.add, "
-                             "Waterfall.image_update run under Qt stubs "
+                             "Waterfall.image_update, Waterfall.autolevel run under Qt stubs "
                              "(oracle/ref_harness.py)",
                    "cases": [c["name"] for c in gc.CASES + gc.ZOOMFFT_CASES]},
                   f, indent=1)

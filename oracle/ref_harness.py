@@ -237,3 +237,26 @@ def waterfall_rows(rows, scroll=1):
     for r in rows:
         wf.image_update(np.array(r, dtype=np.float64, copy=True))
     return np.array(wf.img_array, copy=True)
+
+
+def waterfall_autolevel(rows, scroll=1):
+    """The reference's own Waterfall.autolevel (S:1668-1680) after image_update
+    for each row: returns (minlevel, maxlevel) -- the attributes its
+    np.percentile(img_array[img_array<0], [2, 98]) lands in (S:1676) -- and the
+    (minlev, maxlev) pair it returns (unchanged defaults: the attribute-name
+    slip at S:1676-1677)."""
+    mod = load("spectrum")
+    mod.AppState.scroll = scroll
+    _set_state(mod, 2.4e6, 2048, 8, 1, "hamming")
+    wf = mod.Waterfall.__new__(mod.Waterfall)
+    wf.fftwidth = 0
+    wf.minlev = -220                      # S:1592-1593 (set in __init__, which needs Qt)
+    wf.maxlev = -120
+    wf.scale = lambda *a, **k: None
+    wf.setImage = lambda *a, **k: None
+    wf.setLevels = lambda *a, **k: None
+    for r in rows:
+        wf.image_update(np.array(r, dtype=np.float64, copy=True))
+    ret = wf.autolevel()
+    return np.array([wf.minlevel, wf.maxlevel]), np.array(ret, dtype=np.float64)
+

@@ -371,6 +371,51 @@ def waterfall_update(img: np.ndarray, psd: np.ndarray, scroll: int = 1):
     return img
 
 
+def waterfall_autolevel(img: np.ndarray):
+    """Waterfall.autolevel (S:1676): the 2nd / 98th percentile of the image
+    pixels below zero (the -500 fill counts, grid and tick zeros do not)."""
+    lo, hi = np.percentile(img[img < 0], [2, 98])
+    return float(lo), float(hi)
+
+
+def waterfall_indices(img: np.ndarray, minlev: float = -220, maxlev: float = -120,
+                      ncolors: int = 256) -> np.ndarray:
+    """Colour-table index pyqtgraph's ImageItem computes for every pixel of
+    the image the reference hands it (S:1664 setImage(..., autoLevels=False)
+    after S:1594 setLevels([minlev, maxlev]) and S:1623 setLookupTable(256
+    entries)).  PARITY UNPINNED: pyqtgraph is a third-party dependency of the
+    reference (README.md:7 `pip3 install pyqtgraph`, no version), not vendored
+    and not installed here; this restates its published algorithm
+    (pyqtgraph/graphicsItems/ImageItem.py `_try_rescale_float` ->
+    functions.rescaleData): scale = ncolors / (max - min); d = (img - min) *
+    scale; clip to [0, ncolors-1]; truncate to an unsigned integer."""
+    d = (np.asarray(img, dtype=np.float64) - float(minlev)) * (ncolors / (float(maxlev) - float(minlev)))
+    d = np.clip(d, 0, ncolors - 1)
+    return d.astype(np.uint8)
+
+
+def waterfall_rgba(indices: np.ndarray, lut: np.ndarray) -> np.ndarray:
+    """lut[index]: the table lookup of pyqtgraph's makeARGB / ImageItem
+    render step (same caveat as waterfall_indices)."""
+    return np.asarray(lut, dtype=np.uint8)[indices]
+
+
+def colormap_lut(pos, color, npts: int = 256) -> np.ndarray:
+    """ColorMap(pos, color).getLookupTable(0.0, 1.0, 256) as called at
+    S:1622-1623 (pyqtgraph/colormap.py, published algorithm, unpinned): RGB(A)
+    linearly interpolated between the stops over linspace(0, 1, npts), returned
+    as uint8 with alpha 255.  Colour stops are taken modulo 256 like numpy < 2
+    did for the reference's out-of-range 'Default' stop 2020 (S:1581; numpy >=
+    2 raises OverflowError there)."""
+    pos = np.asarray(pos, dtype=np.float64)
+    col = (np.asarray(color, dtype=np.int64) % 256).astype(np.float64)
+    x = np.linspace(0.0, 1.0, npts)
+    out = np.empty((npts, 4), dtype=np.uint8)
+    for c in range(4):
+        out[:, c] = (np.interp(x, pos, col[:, c]) + 0.5).astype(np.uint8)
+    return out
+
+
 # --------------------------------------------------------------------------
 # closed forms used as known-answer tests (SURVEY §8a "dB20 note")
 # --------------------------------------------------------------------------

@@ -30,8 +30,11 @@ FAST_MAX_STAGES = 12
 ZFB_FLAG_NO_LO = 1
 ZFB_FLAG_LINEAR = 2
 
-ABI_VERSION = 1
-PROF_CLASSES = 19
+ABI_VERSION = 2
+PROF_CLASSES = 21
+ZFB_IMAGE_F32 = 0
+ZFB_IMAGE_U8 = 1
+ZFB_IMAGE_RGBA = 2
 
 
 class ZfbConfig(C.Structure):
@@ -90,6 +93,9 @@ SYMBOLS = {
     "zfb_ring_rows_written": (C.c_int64, [_P]),
     "zfb_read_rows": (C.c_int, [_P, C.c_int, C.c_int, _P]),
     "zfb_ring_push_rows": (C.c_int, [_P, _P, C.c_int]),
+    "zfb_ring_image": (C.c_int, [_P, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_double, C.c_double, _P, _P, C.c_int]),
+    "zfb_ring_quantiles": (C.c_int, [_P, C.c_int, C.c_int, C.c_int64, C.POINTER(C.c_double), C.c_int,
+                                     C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "zfb_samples_create": (C.c_int, [_P, C.c_int64, C.c_int]),
     "zfb_samples_host_ptr": (_P, [_P]),
     "zfb_samples_begin_write": (C.c_int, [_P, C.c_int64, C.c_int64]),

@@ -245,49 +245,44 @@ class Waterfall:
         if self.on_image is not None:
             self.on_image(self.img_array.T)                    # S:1664
 
+    # reference defaults (S:1592-1594)
+    minlev = -220
+    maxlev = -120
+
     @property
     def img_array(self) -> np.ndarray:
-        """The reference's ``img_array`` after the same sequence of updates."""
+        """The reference's ``img_array`` after the same sequence of updates
+        (-500 fill, grid columns, scroll order, tick marks: S:1625-1662),
+        assembled on the device from the ring when it is displayed."""
         w = self.fftwidth
-        h = w // 4
-        img = -500 * np.ones((h, w))
-        img[:, 0] = 0
-        img[:, w - 1] = 0
-        have = min(self.rows_seen, h, self.engine.rows_written)
-        ticks = tick_columns(w)
-        if have:
-            rows = self.engine.read_rows(have).astype(np.float64)      # oldest .. newest
-            for x in (0, w // 2, w - 1):
-                rows[:, x] = 0
-            newest_first = rows[::-1]
-            if self.scroll > 0:
-                # newest sits at h-2, older rows above it; the row that wrapped from 0 is at h-1
-                for j in range(have):
-                    img[(h - 2 - j) % h] = newest_first[j]
-            else:
-                for j in range(have):
-                    img[j] = newest_first[j]
-        if self.rows_seen:
-            # tick marks are redrawn on every update and scroll with the image:
-            # every row that has passed through the marked band keeps them
-            if self.scroll > 0:
-                marked = list(range(0, 15)) + ([h - 1] if self.rows_seen >= 1 else [])
-                first_band = range(5, 15)
-            else:
-                marked = list(range(h - 10, h))
-                first_band = range(h - 10, h - 2)
-            n = self.rows_seen
-            for y in marked:
-                if y in first_band:
-                    hit = True
-                elif self.scroll > 0:
-                    # rows at 0..4 came from the band after 1..5 more updates; h-1 wrapped from 0
-                    age_needed = (5 - y) if y < 5 else 6
-                    hit = n > age_needed
-                else:
-                    age_needed = y - (h - 3)
-                    hit = n > age_needed
-                if hit:
-                    for x in ticks:
-                        img[y, x] = 0
-        return img
+        return self.engine.ring_image(w // 4, self.scroll, self.rows_seen, "f32").astype(np.float64)
+
+    def image_indices(self, levels=None) -> np.ndarray:
+        """8-bit colour indices pyqtgraph's ImageItem would look up for
+        ``img_array`` with ``setLevels(levels)`` and a 256-entry table
+        (S:1594, S:1623, S:1664): the only thing read back for display."""
+        lo, hi = levels if levels is not None else (self.minlev, self.maxlev)
+        return self.engine.ring_image(self.fftwidth // 4, self.scroll, self.rows_seen, "u8", levels=(lo, hi))
+
+    def image_rgba(self, lut, levels=None) -> np.ndarray:
+        """``lut[image_indices]``: (h, w, 4) uint8, lut = the (256, 4) table of
+        ``ColorMap.getLookupTable(0.0, 1.0, 256)`` (S:1623) with alpha."""
+        lo, hi = levels if levels is not None else (self.minlev, self.maxlev)
+        return self.engine.ring_image(self.fftwidth // 4, self.scroll, self.rows_seen, "rgba",
+                                      levels=(lo, hi), lut=lut)
+
+    def autolevel(self, fix: bool = False):
+        """Waterfall.autolevel (S:1668-1680): the 2nd and 98th percentile of the
+        image pixels below zero, selected on the device.  Like the reference
+        the result lands in ``minlevel`` / ``maxlevel`` and the levels in use
+        (``minlev`` / ``maxlev``) are returned unchanged -- the reference's
+        attribute-name slip (S:1676-1677); ``fix=True`` applies them."""
+        (lo, hi), _ = self.engine.ring_quantiles(self.fftwidth // 4, self.scroll, self.rows_seen, [0.02, 0.98])
+        self.minlevel, self.maxlevel = lo, hi
+        if fix:
+            self.minlev, self.maxlev = lo, hi
+        return self.minlev, self.maxlev
+
+    def newlevel(self, low, high):                             # S:1682-1686
+        self.minlev, self.maxlev = low, high
+        return low, high

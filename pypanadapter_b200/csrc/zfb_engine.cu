@@ -25,6 +25,7 @@
 #include "zfb_welch.cuh"
 #include "zfb_bigfft.cuh"
 #include "zfb_firchain.cuh"
+#include "zfb_image.cuh"
 
 using namespace zfb;
 
@@ -75,7 +76,7 @@ struct zfb_engine {
     int nsplit_cap = 1;
     StageParams sp0[2]{};              // LO tables of stage 0 for NT = 256 / 128
 
-    DevBuf window, winfft, twiddle, twiddle_sub, pow16, mid[2], pow, rows_tmp, ema, ema_valid, ring, stage_in[2], big;
+    DevBuf window, winfft, twiddle, twiddle_sub, pow16, mid[2], pow, rows_tmp, ema, ring, stage_in[2], big, img_out, img_lut, sel_hist;
     void  *h_stage[2] = {nullptr, nullptr};
     size_t h_stage_cap[2] = {0, 0};
     float *h_rows = nullptr;
@@ -83,6 +84,7 @@ struct zfb_engine {
     int ring_rows = 256, ring_rows_req = 256, ring_W = 0;
     int64_t ring_written = 0;
     int last_group_frames = 0;
+    bool ema_have = false;             // the EMA state holds a row (host side; launch order = stream order)
 
     // ZFB_MODE_FAST
     struct FastPlan {
@@ -1019,7 +1021,7 @@ int run_group(zfb_engine *e, const void *d_in, int gf, float *d_rows) {
     f.alpha = (c.ema_alpha >= 0.0) ? (float)c.ema_alpha : -1.f;
     f.linear = (c.flags & ZFB_FLAG_LINEAR) ? 1 : 0;
     f.ema_state = (float *)e->ema.p;
-    f.ema_valid = (int *)e->ema_valid.p;
+    f.ema_have = e->ema_have ? 1 : 0;
     f.rows = d_rows;
     f.ring = (float *)e->ring.p;
     f.ring_pos = (long long)(e->ring_written % e->ring_rows);
@@ -1028,14 +1030,13 @@ int run_group(zfb_engine *e, const void *d_in, int gf, float *d_rows) {
     f.chan_row_stride = e->cur_row_stride;
     const int prf = prof_begin(e, 18);
     const long long cells = (long long)gf * e->W;
-    ZFB_LAUNCH(reduce_rows_kernel, dim3((unsigned)((cells + 255) / 256)), dim3(256), 0, st, f);
-    e->counters[2] += 1;
     if (f.alpha >= 0.f) {
-        ZFB_LAUNCH(ema_rows_kernel, dim3((unsigned)((e->W + 31) / 32)), dim3(32), 0, st, f);
-        ZFB_LAUNCH(set_flag_kernel, dim3(1), dim3(1), 0, st, (int *)e->ema_valid.p, 1);
-        ZFB_LAUNCH(emit_rows_kernel, dim3((unsigned)((cells + 255) / 256)), dim3(256), 0, st, f);
-        e->counters[2] += 3;
+        ZFB_LAUNCH(ema_rows_kernel, dim3((unsigned)((e->W + EMA_COLS - 1) / EMA_COLS)), dim3(EMA_NT), 0, st, f);
+        e->ema_have = true;
+    } else {
+        ZFB_LAUNCH(reduce_rows_kernel, dim3((unsigned)((cells + 255) / 256)), dim3(256), 0, st, f);
     }
+    e->counters[2] += 1;
     prof_end(e, prf);
     CK(e, cudaGetLastError());
     e->ring_written += gf;
@@ -1226,9 +1227,6 @@ int zfb_create(int device, zfb_engine **out) {
         if (rc != ZFB_OK) break;
         rc = setup_device_once(e);
         if (rc != ZFB_OK) { g_create_error = e->err; break; }
-        rc = ensure(e, e->ema_valid, sizeof(int));
-        if (rc != ZFB_OK) { g_create_error = e->err; break; }
-        if (cudaMemset(e->ema_valid.p, 0, sizeof(int)) != cudaSuccess) { rc = fail(nullptr, ZFB_ECUDA, "memset failed"); break; }
     } while (0);
     if (rc != ZFB_OK) {
         zfb_destroy(e);
@@ -1245,7 +1243,7 @@ void zfb_destroy(zfb_engine *e) {
     if (e->copy_stream) cudaStreamSynchronize(e->copy_stream);
     if (e->aux_stream) cudaStreamSynchronize(e->aux_stream);
     DevBuf *bufs[] = {&e->window, &e->winfft, &e->twiddle, &e->twiddle_sub, &e->pow16, &e->mid[0], &e->mid[1], &e->pow, &e->rows_tmp, &e->ema,
-                      &e->ema_valid, &e->ring, &e->stage_in[0], &e->stage_in[1], &e->big};
+                      &e->img_out, &e->img_lut, &e->sel_hist, &e->ring, &e->stage_in[0], &e->stage_in[1], &e->big};
     for (DevBuf *b : bufs) release(*b);
     for (int i = 0; i < 2; ++i) {
         if (e->h_stage[i]) cudaFreeHost(e->h_stage[i]);
@@ -1446,7 +1444,7 @@ int zfb_configure(zfb_engine *e, const zfb_config *cfg) {
         if (rc) return rc;
         e->ring_W = e->W;
         e->ring_written = 0;
-        CK(e, cudaMemsetAsync(e->ema_valid.p, 0, sizeof(int), e->stream));
+        e->ema_have = false;
     }
     e->configured = true;
     return ZFB_OK;
@@ -1537,8 +1535,7 @@ int zfb_set_option(zfb_engine *e, const char *name, long long value) {
 int zfb_reset_ema(zfb_engine *e) {
     if (!e) return ZFB_EINVAL;
     std::lock_guard<std::mutex> lk(e->mu);
-    CK(e, cudaSetDevice(e->device));
-    CK(e, cudaMemsetAsync(e->ema_valid.p, 0, sizeof(int), e->stream));
+    e->ema_have = false;     // launch order is stream order: the next EMA group starts afresh
     return ZFB_OK;
 }
 
@@ -1854,6 +1851,190 @@ int zfb_ring_push_rows(zfb_engine *e, const float *h_rows, int nrows) {
     }
     CK(e, cudaStreamSynchronize(e->stream));      // caller's buffer may be pageable / reused
     e->counters[3] += (size_t)nrows * rb;
+    return ZFB_OK;
+}
+
+// ---- waterfall image and autolevel on the device (zfb_image.cuh) -----------
+static int image_params(zfb_engine *e, int height, int scroll, int64_t rows_seen, ImageParams &p) {
+    if (!e->configured) return fail(e, ZFB_ESTATE, "engine is not configured");
+    if (height < 1 || rows_seen < 0) return fail(e, ZFB_EINVAL, "waterfall image: bad height / rows_seen");
+    int64_t have = rows_seen;
+    if (have > height) have = height;
+    if (have > e->ring_written) have = e->ring_written;
+    if (have > e->ring_rows) have = e->ring_rows;
+    p.ring = (const float *)e->ring.p;
+    p.ring_rows = e->ring_rows;
+    p.written = e->ring_written;
+    p.W = e->W;
+    p.H = height;
+    p.have = (int)have;
+    p.nseen = (int)(rows_seen > (1 << 20) ? (1 << 20) : rows_seen);
+    p.scroll = scroll;
+    p.tick_step = e->W / 10;
+    p.minlev = 0.0;
+    p.scale = 1.0;
+    p.lut = nullptr;
+    p.out = nullptr;
+    return ZFB_OK;
+}
+
+int zfb_ring_image(zfb_engine *e, int height, int scroll, int64_t rows_seen, int kind, double minlev, double maxlev,
+                   const uint8_t *lut_rgba, void *out, int out_on_device) {
+    if (!e) return ZFB_EINVAL;
+    std::lock_guard<std::mutex> lk(e->mu);
+    ImageParams p{};
+    int rc = image_params(e, height, scroll, rows_seen, p);
+    if (rc) return rc;
+    if (!out) return fail(e, ZFB_EINVAL, "waterfall image: out is NULL");
+    if (kind != ZFB_IMAGE_F32 && kind != ZFB_IMAGE_U8 && kind != ZFB_IMAGE_RGBA)
+        return fail(e, ZFB_EINVAL, "waterfall image: unknown kind %d", kind);
+    if (kind != ZFB_IMAGE_F32 && !(maxlev > minlev)) return fail(e, ZFB_EINVAL, "waterfall image: maxlev must exceed minlev");
+    if (kind == ZFB_IMAGE_RGBA && !lut_rgba) return fail(e, ZFB_EINVAL, "waterfall image: RGBA needs a 256-entry table");
+    CK(e, cudaSetDevice(e->device));
+    cudaStream_t st = e->stream;
+    const size_t px = (size_t)height * (size_t)e->W;
+    const size_t bytes = px * (kind == ZFB_IMAGE_U8 ? 1 : 4);
+    if (kind != ZFB_IMAGE_F32) {
+        p.minlev = minlev;
+        p.scale = 256.0 / (maxlev - minlev);
+    }
+    if (kind == ZFB_IMAGE_RGBA) {
+        rc = ensure(e, e->img_lut, 256 * sizeof(unsigned int));
+        if (rc) return rc;
+        CK(e, cudaMemcpyAsync(e->img_lut.p, lut_rgba, 256 * sizeof(unsigned int), cudaMemcpyHostToDevice, st));
+        e->counters[3] += 256 * sizeof(unsigned int);
+        p.lut = (const unsigned int *)e->img_lut.p;
+    }
+    if (out_on_device) {
+        p.out = out;
+    } else {
+        if (e->img_out.cap < bytes) CK(e, cudaStreamSynchronize(st));
+        rc = ensure(e, e->img_out, bytes);
+        if (rc) return rc;
+        p.out = e->img_out.p;
+    }
+    const dim3 grid((unsigned)((e->W + 1023) / 1024), (unsigned)height);
+    const int pr = prof_begin(e, 19);
+    if (kind == ZFB_IMAGE_F32) ZFB_LAUNCH(wf_image_kernel<IMG_F32>, grid, dim3(256), 0, st, p);
+    else if (kind == ZFB_IMAGE_U8) ZFB_LAUNCH(wf_image_kernel<IMG_U8>, grid, dim3(256), 0, st, p);
+    else ZFB_LAUNCH(wf_image_kernel<IMG_RGBA>, grid, dim3(256), 0, st, p);
+    prof_end(e, pr);
+    CK(e, cudaGetLastError());
+    e->counters[2] += 1;
+    if (!out_on_device) {
+        CK(e, cudaMemcpyAsync(out, p.out, bytes, cudaMemcpyDeviceToHost, st));
+        CK(e, cudaStreamSynchronize(st));
+        e->counters[4] += bytes;
+    }
+    return ZFB_OK;
+}
+
+// numpy's _lerp (numpy/lib/_function_base_impl.py), as np.percentile's default
+// 'linear' method applies it between the two neighbouring order statistics
+static double np_lerp(double a, double b, double t) {
+    const double d = b - a;
+    double r = a + d * t;
+    if (t >= 0.5) r = b - d * (1.0 - t);
+    if (d == 0.0) r = a;
+    return r;
+}
+
+int zfb_ring_quantiles(zfb_engine *e, int height, int scroll, int64_t rows_seen, const double *q, int nq,
+                       double *out_values, int64_t *out_count) {
+    if (!e) return ZFB_EINVAL;
+    std::lock_guard<std::mutex> lk(e->mu);
+    SelectParams s{};
+    int rc = image_params(e, height, scroll, rows_seen, s.img);
+    if (rc) return rc;
+    if (!q || !out_values || nq < 1 || nq > 64) return fail(e, ZFB_EINVAL, "quantiles: bad arguments");
+    for (int i = 0; i < nq; ++i)
+        if (!(q[i] >= 0.0 && q[i] <= 1.0)) return fail(e, ZFB_EINVAL, "quantiles: q[%d] outside [0, 1]", i);
+    CK(e, cudaSetDevice(e->device));
+    cudaStream_t st = e->stream;
+    const size_t hbytes = (size_t)SEL_TARGETS * SEL_BINS * sizeof(unsigned int);
+    rc = ensure(e, e->sel_hist, hbytes);
+    if (rc) return rc;
+    s.hist = (unsigned int *)e->sel_hist.p;
+    // enough CTAs to fill the GPU, whole rows per CTA
+    int ctas = e->sm_count * 8;
+    if (ctas > height) ctas = height;
+    s.rows_per_cta = (height + ctas - 1) / ctas;
+    ctas = (height + s.rows_per_cta - 1) / s.rows_per_cta;
+    std::vector<unsigned int> hist((size_t)SEL_TARGETS * SEL_BINS);
+    auto sweep = [&](int pass, int nt) -> int {
+        s.pass = pass;
+        s.ntargets = nt;
+        CK(e, cudaMemsetAsync(s.hist, 0, hbytes, st));
+        const int pr = prof_begin(e, 20);
+        ZFB_LAUNCH(wf_select_kernel, dim3((unsigned)ctas), dim3(256), 0, st, s);
+        prof_end(e, pr);
+        CK(e, cudaGetLastError());
+        e->counters[2] += 1;
+        CK(e, cudaMemcpyAsync(hist.data(), s.hist, hbytes, cudaMemcpyDeviceToHost, st));
+        CK(e, cudaStreamSynchronize(st));
+        e->counters[4] += hbytes;
+        return ZFB_OK;
+    };
+    // pass 0 is shared by every rank: 11 leading key bits
+    rc = sweep(0, 1);
+    if (rc) return rc;
+    std::vector<unsigned long long> cum0(SEL_BINS + 1, 0);
+    for (int b = 0; b < SEL_BINS; ++b) cum0[b + 1] = cum0[b] + hist[b];
+    const long long n = (long long)cum0[SEL_BINS];
+    if (out_count) *out_count = n;
+    if (n == 0) {
+        for (int i = 0; i < nq; ++i) out_values[i] = NAN;     // np.percentile of an empty selection
+        return ZFB_OK;
+    }
+    // ranks np.percentile(method='linear') needs: floor and floor+1 of (n-1)*q
+    std::vector<long long> ranks;
+    std::vector<double> gamma(nq);
+    std::vector<int> lo_at(nq), hi_at(nq);
+    auto rank_slot = [&](long long r) {
+        for (size_t i = 0; i < ranks.size(); ++i) if (ranks[i] == r) return (int)i;
+        ranks.push_back(r);
+        return (int)ranks.size() - 1;
+    };
+    for (int i = 0; i < nq; ++i) {
+        const double virt = (double)(n - 1) * q[i];
+        long long k = (long long)floor(virt);
+        if (k > n - 1) k = n - 1;
+        if (k < 0) k = 0;
+        gamma[i] = virt - (double)k;
+        lo_at[i] = rank_slot(k);
+        hi_at[i] = rank_slot(k + 1 < n ? k + 1 : n - 1);
+    }
+    std::vector<float> value(ranks.size());
+    for (size_t base = 0; base < ranks.size(); base += SEL_TARGETS) {
+        const int nt = (int)std::min<size_t>(SEL_TARGETS, ranks.size() - base);
+        long long resid[SEL_TARGETS];
+        unsigned int key[SEL_TARGETS];
+        for (int t = 0; t < nt; ++t) {
+            const long long r = ranks[base + t];
+            int b = 0;
+            while (cum0[b + 1] <= (unsigned long long)r) ++b;
+            key[t] = (unsigned int)b;
+            resid[t] = r - (long long)cum0[b];
+            s.prefix[t] = key[t];
+        }
+        for (int pass = 1; pass <= 2; ++pass) {
+            rc = sweep(pass, nt);
+            if (rc) return rc;
+            const int bins = pass == 1 ? 2048 : 1024;
+            for (int t = 0; t < nt; ++t) {
+                const unsigned int *ht = hist.data() + (size_t)t * SEL_BINS;
+                long long acc = 0;
+                int b = 0;
+                while (b < bins - 1 && acc + ht[b] <= resid[t]) acc += ht[b++];
+                resid[t] -= acc;
+                key[t] = (key[t] << (pass == 1 ? 11 : 10)) | (unsigned int)b;
+                s.prefix[t] = key[t];
+            }
+        }
+        for (int t = 0; t < nt; ++t) value[base + t] = wf_unkey(key[t]);
+    }
+    for (int i = 0; i < nq; ++i)
+        out_values[i] = np_lerp((double)value[(size_t)lo_at[i]], (double)value[(size_t)hi_at[i]], gamma[i]);
     return ZFB_OK;
 }
 

@@ -311,7 +311,7 @@ struct FinalizeParams {
     float  alpha;             // < 0: EMA off
     int    linear;            // 1: emit linear power instead of dB20
     float *ema_state;         // [W]
-    int   *ema_valid;         // device flag: state holds a row
+    int    ema_have;          // the state holds a row (host-side knowledge, launch order)
     float *rows;              // [nframes][W] or null
     float *ring;              // [ring_rows][W] or null
     long long ring_pos;       // ring slot of frame 0
@@ -333,7 +333,7 @@ __device__ __forceinline__ void emit_row_value(const FinalizeParams &p, int f, i
     if (p.ring) p.ring[(size_t)((p.ring_pos + f) % p.ring_rows) * p.W + col] = out;
 }
 
-// one thread per (frame, column): fully parallel part
+// without EMA: one thread per (frame, column)
 __global__ void reduce_rows_kernel(const FinalizeParams p) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long long)p.nframes * p.W) return;
@@ -342,45 +342,66 @@ __global__ void reduce_rows_kernel(const FinalizeParams p) {
     float pw = 0.f;
     for (int s = 0; s < p.nsplit; ++s) pw += src[(size_t)s * p.W];
     pw *= p.scale;
-    if (p.alpha >= 0.f) src[0] = pw;          // the EMA kernel walks the frames in order
-    else emit_row_value(p, f, col, pw);
+    emit_row_value(p, f, col, pw);
 }
 
-// EMA is order dependent: one thread per column walks the frames (loads of CH
-// frames in flight together), doing nothing but the recurrence; the averaged
-// power goes back to slot 0 and emit_rows_kernel turns it into rows in parallel
-__global__ void ema_rows_kernel(const FinalizeParams p) {
-    const int col = blockIdx.x * blockDim.x + threadIdx.x;
-    if (col >= p.W) return;
-    bool have = (*p.ema_valid != 0);
-    float a = have ? p.ema_state[col] : 0.f;
-    constexpr int CH = 64;                // loads in flight: the walk is load-latency bound
+// EMA is order dependent (a_i needs a_(i-1)) but only along the frames: one CTA
+// owns EMA_COLS columns.  All warps reduce the per-split sums of EMA_FR frames
+// into a shared-memory tile (32-byte sectors, EMA_CH independent loads in
+// flight per thread), the first EMA_COLS threads walk the recurrence over the
+// tile (nothing but LDS + 2 dependent ops per frame), all warps turn the
+// averaged power into rows.  Same operations in the same order per (frame,
+// column) as a serial walk: a row does not depend on the batch it is in.
+constexpr int EMA_COLS = 8;
+constexpr int EMA_NT = 512;
+constexpr int EMA_CH = 4;
+constexpr int EMA_FPP = EMA_NT / EMA_COLS;          // frames per pass of the CTA
+constexpr int EMA_FR = EMA_FPP * EMA_CH;            // frames per tile
+
+__global__ void __launch_bounds__(EMA_NT) ema_rows_kernel(const FinalizeParams p) {
+    __shared__ float tile[EMA_FR * EMA_COLS];
+    const int c = threadIdx.x % EMA_COLS, fs = threadIdx.x / EMA_COLS;
+    const int col = blockIdx.x * EMA_COLS + c;
+    const bool ok = col < p.W;
+    const bool walker = threadIdx.x < EMA_COLS;
+    bool have = p.ema_have != 0;
+    float a = (walker && have && ok) ? p.ema_state[col] : 0.f;
     const size_t stride = (size_t)p.nsplit * p.W;
-    for (int f0 = 0; f0 < p.nframes; f0 += CH) {
-        float pw[CH];
+    for (int f0 = 0; f0 < p.nframes; f0 += EMA_FR) {
+        const int n = min(EMA_FR, p.nframes - f0);
+        {
+            float pw[EMA_CH];
 #pragma unroll
-        for (int i = 0; i < CH; ++i)
-            pw[i] = (f0 + i < p.nframes) ? p.pow_io[(size_t)(f0 + i) * stride + col] : 0.f;
+            for (int k = 0; k < EMA_CH; ++k) pw[k] = 0.f;
+            for (int s = 0; s < p.nsplit; ++s) {
 #pragma unroll
-        for (int i = 0; i < CH; ++i) {
-            if (f0 + i < p.nframes) {
-                a = have ? fmaf(p.alpha, pw[i] - a, a) : pw[i];
+                for (int k = 0; k < EMA_CH; ++k) {
+                    const int i = fs + k * EMA_FPP;
+                    if (ok && i < n) pw[k] += p.pow_io[(size_t)(f0 + i) * stride + (size_t)s * p.W + col];
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < EMA_CH; ++k) tile[(fs + k * EMA_FPP) * EMA_COLS + c] = pw[k] * p.scale;
+        }
+        __syncthreads();
+        if (walker) {
+#pragma unroll 8
+            for (int i = 0; i < n; ++i) {
+                const float pw = tile[i * EMA_COLS + c];
+                a = have ? fmaf(p.alpha, pw - a, a) : pw;
                 have = true;
-                p.pow_io[(size_t)(f0 + i) * stride + col] = a;
+                tile[i * EMA_COLS + c] = a;
             }
         }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < EMA_CH; ++k) {
+            const int i = fs + k * EMA_FPP;
+            if (ok && i < n) emit_row_value(p, f0 + i, col, tile[i * EMA_COLS + c]);
+        }
+        __syncthreads();
     }
-    p.ema_state[col] = a;       // ema_valid is raised by set_flag_kernel afterwards (other
-                                // CTAs of this launch may not have read it yet)
+    if (walker && ok && p.nframes > 0) p.ema_state[col] = a;
 }
-
-__global__ void emit_rows_kernel(const FinalizeParams p) {
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (long long)p.nframes * p.W) return;
-    const int f = (int)(idx / p.W), col = (int)(idx % p.W);
-    emit_row_value(p, f, col, p.pow_io[(size_t)f * p.nsplit * p.W + col]);
-}
-
-__global__ void set_flag_kernel(int *flag, int v) { *flag = v; }
 
 }  // namespace zfb

@@ -323,6 +323,53 @@ class ZoomPSD:
         self._check(self._lib.zfb_ring_push_rows(self._h, C.c_void_p(r.ctypes.data), r.shape[0]),
                     "zfb_ring_push_rows")
 
+    # -- waterfall image / autolevel on the device (S:1625-1676) ---------------
+    def ring_image(self, height: int, scroll: int, rows_seen: int, kind: str = "f32", *,
+                   levels=None, lut=None) -> np.ndarray:
+        """The (height, row_width) image the reference's Waterfall would hold
+        after ``rows_seen`` image_update calls, assembled on the device from the
+        ring: ``kind`` 'f32' = img_array, 'u8' = colour indices for ``levels``
+        (minlev, maxlev), 'rgba' = ``lut[index]`` (lut: (256, 4) uint8)."""
+        code = {"f32": _lib.ZFB_IMAGE_F32, "u8": _lib.ZFB_IMAGE_U8, "rgba": _lib.ZFB_IMAGE_RGBA}[kind]
+        h, w = int(height), self.row_width
+        lo, hi = (0.0, 1.0) if levels is None else (float(levels[0]), float(levels[1]))
+        if kind != "f32" and levels is None:
+            raise ValueError("kind %r needs levels=(minlev, maxlev)" % kind)
+        lut_p = None
+        if kind == "rgba":
+            lut = np.ascontiguousarray(lut, dtype=np.uint8)
+            if lut.shape != (256, 4):
+                raise ValueError("lut must be (256, 4) uint8")
+            lut_p = C.c_void_p(lut.ctypes.data)
+        out = np.empty((h, w) if kind != "rgba" else (h, w, 4), dtype=np.float32 if kind == "f32" else np.uint8)
+        self._check(self._lib.zfb_ring_image(self._h, h, int(scroll), int(rows_seen), code, lo, hi, lut_p,
+                                             C.c_void_p(out.ctypes.data), 0), "zfb_ring_image")
+        return out
+
+    def ring_image_device(self, d_out_ptr: int, height: int, scroll: int, rows_seen: int, kind: str = "u8", *,
+                          levels=(-220.0, -120.0), lut=None):
+        """Same, into a caller-owned device buffer (asynchronous)."""
+        code = {"f32": _lib.ZFB_IMAGE_F32, "u8": _lib.ZFB_IMAGE_U8, "rgba": _lib.ZFB_IMAGE_RGBA}[kind]
+        lut_p = None
+        if kind == "rgba":
+            lut = np.ascontiguousarray(lut, dtype=np.uint8)
+            lut_p = C.c_void_p(lut.ctypes.data)
+        self._check(self._lib.zfb_ring_image(self._h, int(height), int(scroll), int(rows_seen), code,
+                                             float(levels[0]), float(levels[1]), lut_p, C.c_void_p(d_out_ptr), 1),
+                    "zfb_ring_image")
+
+    def ring_quantiles(self, height: int, scroll: int, rows_seen: int, q) -> tuple[np.ndarray, int]:
+        """np.quantile(img[img < 0], q) of that image (exact order statistics,
+        numpy's linear interpolation) and the number of pixels below zero."""
+        qq = np.ascontiguousarray(q, dtype=np.float64).ravel()
+        out = np.empty(qq.size, dtype=np.float64)
+        n = C.c_int64(0)
+        self._check(self._lib.zfb_ring_quantiles(self._h, int(height), int(scroll), int(rows_seen),
+                                                 qq.ctypes.data_as(C.POINTER(C.c_double)), qq.size,
+                                                 out.ctypes.data_as(C.POINTER(C.c_double)), C.byref(n)),
+                    "zfb_ring_quantiles")
+        return out, int(n.value)
+
     # -- pinned sample ring (storage of buffers.Data) ------------------------
     def samples_create(self, capacity: int, dtype: str = "c64") -> np.ndarray:
         """Allocate the pinned sample ring + device mirrors; returns a numpy
@@ -356,7 +403,7 @@ class ZoomPSD:
 def _prof_name(c: int) -> str:
     if c < 16:
         return "decimate_stage%d" % c
-    return {16: "welch", 17: "welch_rowpass", 18: "finalize"}[c]
+    return {16: "welch", 17: "welch_rowpass", 18: "finalize", 19: "waterfall_image", 20: "autolevel_select"}[c]
 
 
 def decim_sos(lib=None) -> np.ndarray:

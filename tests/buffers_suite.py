@@ -108,6 +108,58 @@ def waterfall_image(engine):
         assert np.abs(wf.img_array - g[key]).max() < 1e-4
 
 
+def waterfall_display(engine):
+    """Device-side display path: colour indices / RGBA of the
+    image and the autolevel percentiles, against the oracle's restatement of
+    pyqtgraph's level mapping and the reference's own autolevel (golden)."""
+    g = np.load(os.path.join(parity.GOLDEN_DIR, "waterfall.npz"))
+    engine.configure(2.4e6, 2048, 8, 2048 * 10, "hamming", crop="thread")      # row_width 256
+    lut = zo.colormap_lut([0., 0.5, 1.], [[0, 0, 0, 255], [0, 255, 0, 255], [255, 0, 0, 255]])   # 'Red Green' S:1583
+    for name, rows in (("noise", gc.waterfall_rows_noise()), ("ramp", gc.waterfall_rows_ramp())):
+        for scroll, tag in ((1, "pos"), (-1, "neg")):
+            wf = Waterfall(engine, scroll=scroll)
+            ref = None
+            for n, r in enumerate(rows, 1):
+                wf.image_update(r.copy())
+                ref = zo.waterfall_update(ref, r.copy(), scroll)
+                if n not in (1, 3, 7, len(rows)):
+                    continue
+                img = wf.img_array                                   # float32 rows on the device
+                assert np.abs(img - ref).max() < 1e-4
+                # bit-exact against the oracle on the pixels the device holds
+                for levels in ((-220, -120), (-180.5, -99.25)):
+                    idx = wf.image_indices(levels)
+                    assert idx.dtype == np.uint8 and idx.shape == img.shape
+                    assert np.array_equal(idx, zo.waterfall_indices(img, *levels)), (name, tag, n, levels)
+                rgba = wf.image_rgba(lut)
+                assert np.array_equal(rgba, zo.waterfall_rgba(zo.waterfall_indices(img), lut))
+                wf.autolevel()
+                want = zo.waterfall_autolevel(img)
+                assert (wf.minlevel, wf.maxlevel) == want, (name, tag, n, wf.minlevel, wf.maxlevel, want)
+            ret = wf.autolevel()
+            assert ret == (-220, -120)                               # S:1676-1677: levels in use are untouched
+            gold = g["auto_%s_%s" % (name, tag)]
+            if name == "noise":                                      # float32-representable rows: exact
+                assert (wf.minlevel, wf.maxlevel) == (gold[0], gold[1])
+            else:
+                assert abs(wf.minlevel - gold[0]) < 1e-4 and abs(wf.maxlevel - gold[1]) < 1e-4
+            assert wf.autolevel(fix=True) == (wf.minlevel, wf.maxlevel)
+    # quantile edge cases: nothing below zero yet / every requested rank
+    wf = Waterfall(engine)
+    wf.fftwidth = 256
+    wf.init_image()
+    q, n = engine.ring_quantiles(64, 1, 0, [0.0, 0.5, 1.0])
+    assert n == 64 * 254 and list(q) == [-500.0, -500.0, -500.0]
+    row = np.linspace(-90.0, -10.0, 256).astype(np.float32)
+    wf.image_update(row.astype(np.float64))
+    img = wf.img_array
+    qs = [0.0, 0.001, 0.25, 0.5, 0.75, 0.98, 0.9999, 1.0]
+    got, n = engine.ring_quantiles(64, 1, 1, qs)
+    sel = img[img < 0]
+    assert n == sel.size
+    assert np.array_equal(got, np.quantile(sel, qs))
+
+
 def waterfall_from_engine_rows(engine):
     """Rows the engine produced itself are not pushed twice."""
     w = synth.CFG1

@@ -158,6 +158,11 @@ static inline unsigned int __byte_perm(unsigned int x, unsigned int y, unsigned 
 }
 static inline float __uint_as_float(unsigned int u) { float f; memcpy(&f, &u, 4); return f; }
 static inline unsigned int __float_as_uint(float f) { unsigned int u; memcpy(&u, &f, 4); return u; }
+// CTAs run on several OS threads: global atomics must be real ones (shared
+// memory of a CTA is only touched by its own fibers, one OS thread)
+static inline unsigned int atomicAdd(unsigned int *p, unsigned int v) {
+    return __atomic_fetch_add(p, v, __ATOMIC_RELAXED);
+}
 static inline int min(int a, int b) { return a < b ? a : b; }
 static inline int max(int a, int b) { return a > b ? a : b; }
 

@@ -67,6 +67,10 @@ def test_waterfall_image(emu_engine):
     bs.waterfall_image(emu_engine)
 
 
+def test_waterfall_display(emu_engine):
+    bs.waterfall_display(emu_engine)
+
+
 def test_waterfall_engine_rows(emu_engine):
     bs.waterfall_from_engine_rows(emu_engine)
 

@@ -143,6 +143,10 @@ def test_waterfall_image(gpu_engine):
     bs.waterfall_image(gpu_engine)
 
 
+def test_waterfall_display(gpu_engine):
+    bs.waterfall_display(gpu_engine)
+
+
 def test_waterfall_engine_rows(gpu_engine):
     bs.waterfall_from_engine_rows(gpu_engine)
 

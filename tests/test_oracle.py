@@ -156,3 +156,34 @@ def test_oracle_matches_live_reference(name):
     case = gc.case_by_name(name)
     ref = mg.reference_row(case)
     assert _tight(parity.oracle_row(case), np.asarray(ref, dtype=np.float64)) <= 1e-10
+
+
+def test_waterfall_autolevel_golden():
+    """oracle autolevel == the reference's own Waterfall.autolevel (recorded by
+    make_golden under Qt stubs), which also pins its minlevel/minlev slip."""
+    g = np.load(os.path.join(GOLD, "waterfall.npz"))
+    for name, rows in (("ramp", gc.waterfall_rows_ramp()), ("noise", gc.waterfall_rows_noise())):
+        for scroll, tag in ((1, "pos"), (-1, "neg")):
+            img = None
+            for r in rows:
+                img = zo.waterfall_update(img, r.copy(), scroll)
+            lo, hi = zo.waterfall_autolevel(img)
+            want = g["auto_%s_%s" % (name, tag)]
+            assert lo == want[0] and hi == want[1], (name, tag, lo, hi, want)
+            assert list(g["autoret_%s_%s" % (name, tag)]) == [-220.0, -120.0]
+    img = None
+    for r in gc.waterfall_rows_noise():
+        img = zo.waterfall_update(img, r.copy(), 1)
+    assert np.array_equal(img, g["img_noise_pos"])
+
+
+def test_waterfall_indices_properties():
+    """level mapping restatement: monotone, clipped, -500 fill and -inf -> 0,
+    grid zeros -> 255, bin edges at minlev + k (max - min)/256."""
+    v = np.array([-np.inf, -500.0, -220.0, -219.7, -170.0, -120.4, -120.0, 0.0])
+    idx = zo.waterfall_indices(v, -220, -120)
+    assert list(idx) == [0, 0, 0, 0, 128, 254, 255, 255]
+    lut = zo.colormap_lut([0., 1.], [[0, 0, 0, 255], [0, 255, 0, 255]])      # 'Matrix' (S:1582)
+    assert lut.shape == (256, 4) and list(lut[0]) == [0, 0, 0, 255] and list(lut[255]) == [0, 255, 0, 255]
+    assert np.all(np.diff(lut[:, 1].astype(int)) >= 0)
+
