@@ -76,7 +76,7 @@ struct zfb_engine {
     int nsplit_cap = 1;
     StageParams sp0[2]{};              // LO tables of stage 0 for NT = 256 / 128
 
-    DevBuf window, winfft, twiddle, twiddle_sub, pow16, mid[2], pow, rows_tmp, ema, ring, stage_in[2], big, img_out, img_lut, sel_hist;
+    DevBuf window, winfft, twiddle, twiddle_sub, pow16, mid[2], pow, rows_tmp, ema, ring, stage_in[2], big, img_out, img_lut, img_thr, sel_hist;
     void  *h_stage[2] = {nullptr, nullptr};
     size_t h_stage_cap[2] = {0, 0};
     float *h_rows = nullptr;
@@ -84,6 +84,8 @@ struct zfb_engine {
     int ring_rows = 256, ring_rows_req = 256, ring_W = 0;
     int64_t ring_written = 0;
     int last_group_frames = 0;
+    bool thr_valid = false;            // img_thr holds the level thresholds of thr_levels
+    double thr_levels[2] = {0.0, 0.0};
     bool ema_have = false;             // the EMA state holds a row (host side; launch order = stream order)
 
     // ZFB_MODE_FAST
@@ -1243,7 +1245,7 @@ void zfb_destroy(zfb_engine *e) {
     if (e->copy_stream) cudaStreamSynchronize(e->copy_stream);
     if (e->aux_stream) cudaStreamSynchronize(e->aux_stream);
     DevBuf *bufs[] = {&e->window, &e->winfft, &e->twiddle, &e->twiddle_sub, &e->pow16, &e->mid[0], &e->mid[1], &e->pow, &e->rows_tmp, &e->ema,
-                      &e->img_out, &e->img_lut, &e->sel_hist, &e->ring, &e->stage_in[0], &e->stage_in[1], &e->big};
+                      &e->img_out, &e->img_lut, &e->img_thr, &e->sel_hist, &e->ring, &e->stage_in[0], &e->stage_in[1], &e->big};
     for (DevBuf *b : bufs) release(*b);
     for (int i = 0; i < 2; ++i) {
         if (e->h_stage[i]) cudaFreeHost(e->h_stage[i]);
@@ -1871,11 +1873,48 @@ static int image_params(zfb_engine *e, int height, int scroll, int64_t rows_seen
     p.nseen = (int)(rows_seen > (1 << 20) ? (1 << 20) : rows_seen);
     p.scroll = scroll;
     p.tick_step = e->W / 10;
-    p.minlev = 0.0;
-    p.scale = 1.0;
+    p.newest_slot = (int)((e->ring_written + (int64_t)e->ring_rows - 1) % e->ring_rows);
+    p.thr = nullptr;
+    p.fscale = 1.f;
+    p.foff = 0.f;
     p.lut = nullptr;
     p.out = nullptr;
     return ZFB_OK;
+}
+
+// pyqtgraph's level mapping in its own double arithmetic, and the float
+// thresholds at which its result steps (zfb_image.cuh: wf_level)
+static int level_index(double v, double minlev, double scale) {
+    double d = (v - minlev) * scale;
+    if (!(d > 0.0)) d = 0.0;
+    if (d > 255.0) d = 255.0;
+    return (int)d;
+}
+static uint32_t float_ord(float f) {
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+static float ord_float(uint32_t o) {
+    const uint32_t u = (o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o;
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+}
+static void level_thresholds(double minlev, double maxlev, float thr[257]) {
+    const double scale = 256.0 / (maxlev - minlev);
+    thr[0] = -INFINITY;
+    thr[256] = INFINITY;
+    uint32_t lo = float_ord(-INFINITY);                   // index(lo) = 0 < k
+    for (int k = 1; k <= 255; ++k) {
+        uint32_t a = lo, b = float_ord(INFINITY);         // index(a) < k <= index(b)
+        while (b - a > 1) {
+            const uint32_t m = a + (b - a) / 2;
+            if (level_index((double)ord_float(m), minlev, scale) >= k) b = m; else a = m;
+        }
+        thr[k] = ord_float(b);
+        lo = a;
+    }
 }
 
 int zfb_ring_image(zfb_engine *e, int height, int scroll, int64_t rows_seen, int kind, double minlev, double maxlev,
@@ -1895,8 +1934,22 @@ int zfb_ring_image(zfb_engine *e, int height, int scroll, int64_t rows_seen, int
     const size_t px = (size_t)height * (size_t)e->W;
     const size_t bytes = px * (kind == ZFB_IMAGE_U8 ? 1 : 4);
     if (kind != ZFB_IMAGE_F32) {
-        p.minlev = minlev;
-        p.scale = 256.0 / (maxlev - minlev);
+        if (!e->thr_valid || e->thr_levels[0] != minlev || e->thr_levels[1] != maxlev) {
+            float thr[257];
+            level_thresholds(minlev, maxlev, thr);
+            rc = ensure(e, e->img_thr, sizeof thr);
+            if (rc) return rc;
+            CK(e, cudaMemcpyAsync(e->img_thr.p, thr, sizeof thr, cudaMemcpyHostToDevice, st));
+            CK(e, cudaStreamSynchronize(st));             // thr lives on this stack frame
+            e->counters[3] += sizeof thr;
+            e->thr_levels[0] = minlev;
+            e->thr_levels[1] = maxlev;
+            e->thr_valid = true;
+        }
+        p.thr = (const float *)e->img_thr.p;
+        const double scale = 256.0 / (maxlev - minlev);
+        p.fscale = (float)scale;
+        p.foff = (float)(-minlev * scale);
     }
     if (kind == ZFB_IMAGE_RGBA) {
         rc = ensure(e, e->img_lut, 256 * sizeof(unsigned int));
@@ -1913,7 +1966,8 @@ int zfb_ring_image(zfb_engine *e, int height, int scroll, int64_t rows_seen, int
         if (rc) return rc;
         p.out = e->img_out.p;
     }
-    const dim3 grid((unsigned)((e->W + 1023) / 1024), (unsigned)height);
+    const int per_cta = IMG_NT * IMG_U * 4;
+    const dim3 grid((unsigned)((e->W + per_cta - 1) / per_cta), (unsigned)height);
     const int pr = prof_begin(e, 19);
     if (kind == ZFB_IMAGE_F32) ZFB_LAUNCH(wf_image_kernel<IMG_F32>, grid, dim3(256), 0, st, p);
     else if (kind == ZFB_IMAGE_U8) ZFB_LAUNCH(wf_image_kernel<IMG_U8>, grid, dim3(256), 0, st, p);
@@ -2015,20 +2069,26 @@ int zfb_ring_quantiles(zfb_engine *e, int height, int scroll, int64_t rows_seen,
             while (cum0[b + 1] <= (unsigned long long)r) ++b;
             key[t] = (unsigned int)b;
             resid[t] = r - (long long)cum0[b];
-            s.prefix[t] = key[t];
         }
         for (int pass = 1; pass <= 2; ++pass) {
-            rc = sweep(pass, nt);
+            // neighbouring ranks usually share a prefix: one histogram per distinct prefix
+            int slot_of[SEL_TARGETS], nu = 0;
+            for (int t = 0; t < nt; ++t) {
+                int u = 0;
+                while (u < nu && s.prefix[u] != key[t]) ++u;
+                if (u == nu) s.prefix[nu++] = key[t];
+                slot_of[t] = u;
+            }
+            rc = sweep(pass, nu);
             if (rc) return rc;
             const int bins = pass == 1 ? 2048 : 1024;
             for (int t = 0; t < nt; ++t) {
-                const unsigned int *ht = hist.data() + (size_t)t * SEL_BINS;
+                const unsigned int *ht = hist.data() + (size_t)slot_of[t] * SEL_BINS;
                 long long acc = 0;
                 int b = 0;
                 while (b < bins - 1 && acc + ht[b] <= resid[t]) acc += ht[b++];
                 resid[t] -= acc;
                 key[t] = (key[t] << (pass == 1 ? 11 : 10)) | (unsigned int)b;
-                s.prefix[t] = key[t];
             }
         }
         for (int t = 0; t < nt; ++t) value[base + t] = wf_unkey(key[t]);

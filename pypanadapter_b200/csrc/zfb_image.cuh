@@ -28,7 +28,14 @@ struct ImageParams {
     int    nseen;             // image_update calls since init_image, saturated at 1<<20
     int    scroll;            // AppState.scroll: > 0 newest row near the bottom, else at the top
     int    tick_step;         // W // 10
-    double minlev, scale;     // level mapping: (v - minlev) * scale, scale = 256 / (maxlev - minlev)
+    int    newest_slot;       // ring slot of the newest row: (written - 1) mod ring_rows
+    // level mapping: index = clip(trunc((double(v) - minlev) * 256 / (maxlev - minlev)), 0, 255).
+    // thr[k], k = 1..255 = the smallest float whose index is >= k (found on the host with
+    // exactly that double arithmetic): the device makes an fp32 guess v * fscale + foff
+    // (within 1 of the index for any sane level pair) and settles it by comparing with the
+    // neighbouring thresholds, bit-exact with the double formula, no FP64 or F2I instructions.
+    const float *thr;         // [257]
+    float  fscale, foff;
     const unsigned int *lut;  // 256 packed RGBA entries (IMG_RGBA)
     void  *out;
 };
@@ -64,7 +71,8 @@ __device__ __forceinline__ const float *wf_row(const ImageParams &p, int y) {
         j = y;
     }
     if (j >= p.have) return nullptr;
-    long long slot = (p.written - 1 - j) % p.ring_rows;
+    int slot = p.newest_slot - j;                    // j < have <= ring_rows
+    if (slot < 0) slot += p.ring_rows;
     return p.ring + (size_t)slot * p.W;
 }
 
@@ -79,52 +87,72 @@ __device__ __forceinline__ float wf_fix(const ImageParams &p, bool from_ring, bo
     return v;
 }
 
-__device__ __forceinline__ unsigned int wf_level(const ImageParams &p, float v) {
-    double d = ((double)v - p.minlev) * p.scale;
-    if (!(d > 0.0)) d = 0.0;                         // also NaN
-    if (d > 255.0) d = 255.0;
-    return (unsigned int)d;                          // truncation, like astype after clip
+__device__ __forceinline__ unsigned int wf_level(const ImageParams &p, const float *thr, float v) {
+    float x = fmaf(v, p.fscale, p.foff);
+    x = (x > 0.f) ? fminf(x, 255.f) : 0.f;           // NaN -> 0
+    int g = (int)(__float_as_uint(x + 8388608.0f) - 0x4B000000u);    // round to nearest, 0..255
+    while (g < 255 && v >= thr[g + 1]) ++g;          // 0 or 1 trips for any sane level pair
+    while (g > 0 && v < thr[g]) --g;
+    return (unsigned int)g;
 }
 
+constexpr int IMG_NT = 256;
+constexpr int IMG_U = 4;                  // float4 loads in flight per thread
+
 template <int KIND>
-__global__ void __launch_bounds__(256) wf_image_kernel(const ImageParams p) {
+__global__ void __launch_bounds__(IMG_NT) wf_image_kernel(const ImageParams p) {
+    __shared__ float thr[260];
+    __shared__ unsigned int lut[256];
+    if (KIND != IMG_F32) {
+        for (int i = threadIdx.x; i < 257; i += IMG_NT) thr[i] = p.thr[i];
+        if (KIND == IMG_RGBA)
+            for (int i = threadIdx.x; i < 256; i += IMG_NT) lut[i] = p.lut[i];
+        __syncthreads();
+    }
     const int y = blockIdx.y;
     const float *row = wf_row(p, y);
     const bool tick_row = wf_tick_row(p, y);
-    const bool vec = (p.W & 3) == 0;
-    if (vec) {
-        const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-        if (x0 >= p.W) return;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (row) v = __ldg((const float4 *)(row + x0));
-        float q[4] = {v.x, v.y, v.z, v.w};
+    const int xb = (int)blockIdx.x * (IMG_NT * IMG_U * 4);
+    if ((p.W & 3) == 0) {
+        float4 v[IMG_U];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) q[e] = wf_fix(p, row != nullptr, tick_row, x0 + e, q[e]);
-        const size_t at = (size_t)y * p.W + x0;
-        if (KIND == IMG_F32) {
-            *(float4 *)((float *)p.out + at) = make_float4(q[0], q[1], q[2], q[3]);
-        } else if (KIND == IMG_U8) {
-            unsigned int pk = 0;
+        for (int u = 0; u < IMG_U; ++u) {
+            const int x0 = xb + (u * IMG_NT + (int)threadIdx.x) * 4;
+            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row && x0 < p.W) v[u] = __ldg((const float4 *)(row + x0));
+        }
 #pragma unroll
-            for (int e = 0; e < 4; ++e) pk |= wf_level(p, q[e]) << (8 * e);
-            *(unsigned int *)((unsigned char *)p.out + at) = pk;
-        } else {
-            uint4 c;
-            c.x = p.lut[wf_level(p, q[0])];
-            c.y = p.lut[wf_level(p, q[1])];
-            c.z = p.lut[wf_level(p, q[2])];
-            c.w = p.lut[wf_level(p, q[3])];
-            *(uint4 *)((unsigned int *)p.out + at) = c;
+        for (int u = 0; u < IMG_U; ++u) {
+            const int x0 = xb + (u * IMG_NT + (int)threadIdx.x) * 4;
+            if (x0 >= p.W) break;
+            float q[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) q[e] = wf_fix(p, row != nullptr, tick_row, x0 + e, q[e]);
+            const size_t at = (size_t)y * p.W + x0;
+            if (KIND == IMG_F32) {
+                *(float4 *)((float *)p.out + at) = make_float4(q[0], q[1], q[2], q[3]);
+            } else if (KIND == IMG_U8) {
+                unsigned int pk = 0;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) pk |= wf_level(p, thr, q[e]) << (8 * e);
+                *(unsigned int *)((unsigned char *)p.out + at) = pk;
+            } else {
+                uint4 c;
+                c.x = lut[wf_level(p, thr, q[0])];
+                c.y = lut[wf_level(p, thr, q[1])];
+                c.z = lut[wf_level(p, thr, q[2])];
+                c.w = lut[wf_level(p, thr, q[3])];
+                *(uint4 *)((unsigned int *)p.out + at) = c;
+            }
         }
     } else {
-        const int xb = (int)blockIdx.x * 1024;
-        const int xe = min(p.W, xb + 1024);
-        for (int x = xb + (int)threadIdx.x; x < xe; x += 256) {
+        const int xe = min(p.W, xb + IMG_NT * IMG_U * 4);
+        for (int x = xb + (int)threadIdx.x; x < xe; x += IMG_NT) {
             const float v = wf_fix(p, row != nullptr, tick_row, x, row ? row[x] : 0.f);
             const size_t at = (size_t)y * p.W + x;
             if (KIND == IMG_F32) ((float *)p.out)[at] = v;
-            else if (KIND == IMG_U8) ((unsigned char *)p.out)[at] = (unsigned char)wf_level(p, v);
-            else ((unsigned int *)p.out)[at] = p.lut[wf_level(p, v)];
+            else if (KIND == IMG_U8) ((unsigned char *)p.out)[at] = (unsigned char)wf_level(p, thr, v);
+            else ((unsigned int *)p.out)[at] = lut[wf_level(p, thr, v)];
         }
     }
 }
@@ -151,46 +179,65 @@ __host__ inline float wf_unkey(unsigned int k) {
     return f;
 }
 
+// one histogram slot per pixel (prefixes are distinct), warp-aggregated: the
+// lanes that hit the same slot elect a leader which adds their count with ONE
+// shared-memory atomic (dB rows crowd a handful of leading-bit bins: unaggregated,
+// every warp would serialise 32 same-address atomics)
+constexpr unsigned int SEL_NONE = 0xFFFFFFFFu;
+
+__device__ __forceinline__ unsigned int wf_slot(const SelectParams &s, float v) {
+    if (!(v < 0.f)) return SEL_NONE;
+    const unsigned int k = wf_key(v);
+    if (s.pass == 0) return k >> 21;
+    const unsigned int pre = (s.pass == 1) ? (k >> 21) : (k >> 10);
+    const unsigned int sub = (s.pass == 1) ? ((k >> 10) & 0x7FFu) : (k & 0x3FFu);
+    unsigned int at = SEL_NONE;
+#pragma unroll
+    for (int t = 0; t < SEL_TARGETS; ++t)
+        if (t < s.ntargets && pre == s.prefix[t]) at = (unsigned int)t * SEL_BINS + sub;
+    return at;
+}
+
+__device__ __forceinline__ void wf_count(unsigned int *h, unsigned int at, int lane) {
+    const unsigned int peers = __match_any_sync(0xFFFFFFFFu, at);
+    if (at != SEL_NONE && lane == __ffs((int)peers) - 1) atomicAdd(&h[at], (unsigned int)__popc(peers));
+}
+
 __global__ void __launch_bounds__(256) wf_select_kernel(const SelectParams s) {
     __shared__ unsigned int h[SEL_TARGETS * SEL_BINS];
     const ImageParams &p = s.img;
     const int nh = (s.pass == 0) ? 1 : s.ntargets;
+    const int lane = threadIdx.x & 31;
     for (int i = threadIdx.x; i < nh * SEL_BINS; i += blockDim.x) h[i] = 0u;
     __syncthreads();
     const int y0 = blockIdx.x * s.rows_per_cta;
     const int y1 = min(p.H, y0 + s.rows_per_cta);
-    // runs of equal bins (the -500 fill, flat floors) cost one atomic per run and thread
-    int run_at = -1;
-    unsigned int run_n = 0;
+    const bool vec = (p.W & 3) == 0;
     for (int y = y0; y < y1; ++y) {
         const float *row = wf_row(p, y);
         const bool tick_row = wf_tick_row(p, y);
-        for (int x = threadIdx.x; x < p.W; x += blockDim.x) {
-            const float v = wf_fix(p, row != nullptr, tick_row, x, row ? __ldg(row + x) : 0.f);
-            if (!(v < 0.f)) continue;
-            const unsigned int k = wf_key(v);
-            if (s.pass == 0) {
-                const int at = (int)(k >> 21);
-                if (at == run_at) { ++run_n; } else {
-                    if (run_n) atomicAdd(&h[run_at], run_n);
-                    run_at = at;
-                    run_n = 1;
+        if (vec) {
+            for (int xb = 0; xb < p.W; xb += 1024) {          // uniform trip count: warp collectives inside
+                const int x0 = xb + (int)threadIdx.x * 4;
+                const bool in = x0 < p.W;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (row && in) v = __ldg((const float4 *)(row + x0));
+                const float q[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const unsigned int at = in ? wf_slot(s, wf_fix(p, row != nullptr, tick_row, x0 + e, q[e])) : SEL_NONE;
+                    wf_count(h, at, lane);
                 }
-            } else {
-                for (int t = 0; t < s.ntargets; ++t) {
-                    const bool hit = (s.pass == 1) ? ((k >> 21) == s.prefix[t]) : ((k >> 10) == s.prefix[t]);
-                    if (!hit) continue;
-                    const int at = t * SEL_BINS + (int)((s.pass == 1) ? ((k >> 10) & 0x7FFu) : (k & 0x3FFu));
-                    if (at == run_at) { ++run_n; } else {
-                        if (run_n) atomicAdd(&h[run_at], run_n);
-                        run_at = at;
-                        run_n = 1;
-                    }
-                }
+            }
+        } else {
+            for (int xb = 0; xb < p.W; xb += 256) {
+                const int x = xb + (int)threadIdx.x;
+                const bool in = x < p.W;
+                const float v = wf_fix(p, row != nullptr, tick_row, x, (row && in) ? __ldg(row + x) : 0.f);
+                wf_count(h, in ? wf_slot(s, v) : SEL_NONE, lane);
             }
         }
     }
-    if (run_n) atomicAdd(&h[run_at], run_n);
     __syncthreads();
     for (int i = threadIdx.x; i < nh * SEL_BINS; i += blockDim.x)
         if (h[i]) atomicAdd(&s.hist[i], h[i]);

@@ -127,7 +127,7 @@ def waterfall_display(engine):
                 img = wf.img_array                                   # float32 rows on the device
                 assert np.abs(img - ref).max() < 1e-4
                 # bit-exact against the oracle on the pixels the device holds
-                for levels in ((-220, -120), (-180.5, -99.25)):
+                for levels in ((-220, -120), (-180.5, -99.25), (-150.001, -149.999), (-1e6, 1e6)):
                     idx = wf.image_indices(levels)
                     assert idx.dtype == np.uint8 and idx.shape == img.shape
                     assert np.array_equal(idx, zo.waterfall_indices(img, *levels)), (name, tag, n, levels)

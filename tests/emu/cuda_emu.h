@@ -134,6 +134,25 @@ static inline T __shfl_xor_sync(unsigned, T v, int lane_mask) {
     return out;
 }
 
+// every lane of the warp posts its value; the result is the mask of lanes that
+// posted the same one (all lanes of the warp must take part, as with shuffles)
+static inline unsigned int __match_any_sync(unsigned, unsigned int v) {
+    cuemu::Cta *c = cuemu::t_cta;
+    const int t = c->cur, lane = t & 31;
+    cuemu::Warp &w = c->warps[t >> 5];
+    const int wsize = (c->nthreads - (t & ~31)) < 32 ? (c->nthreads - (t & ~31)) : 32;
+    const long g = ++w.gen[lane];
+    w.slot[g & 1][lane] = v;
+    w.arrived += 1;
+    cuemu::yield_until(&w.arrived, g * (long)wsize);
+    unsigned int m = 0;
+    for (int l = 0; l < wsize; ++l)
+        if ((unsigned int)w.slot[g & 1][l] == v) m |= 1u << l;
+    return m;
+}
+static inline int __popc(unsigned int x) { return __builtin_popcount(x); }
+static inline int __ffs(int x) { return __builtin_ffs(x); }
+
 template <typename T>
 static inline T __ldg(const T *p) { return *p; }
 
