@@ -1877,6 +1877,7 @@ static int image_params(zfb_engine *e, int height, int scroll, int64_t rows_seen
     p.thr = nullptr;
     p.fscale = 1.f;
     p.foff = 0.f;
+    p.wide_guess = 0;
     p.lut = nullptr;
     p.out = nullptr;
     return ZFB_OK;
@@ -1950,6 +1951,8 @@ int zfb_ring_image(zfb_engine *e, int height, int scroll, int64_t rows_seen, int
         const double scale = 256.0 / (maxlev - minlev);
         p.fscale = (float)scale;
         p.foff = (float)(-minlev * scale);
+        // fp32 guess error <= (256 + 2|foff|) * 2^-23: stays below 1/4 for |foff| < 1e6
+        p.wide_guess = (fabs(minlev * scale) < 1.0e6 && scale < 1.0e30) ? 0 : 1;
     }
     if (kind == ZFB_IMAGE_RGBA) {
         rc = ensure(e, e->img_lut, 256 * sizeof(unsigned int));
@@ -2020,7 +2023,8 @@ int zfb_ring_quantiles(zfb_engine *e, int height, int scroll, int64_t rows_seen,
         s.ntargets = nt;
         CK(e, cudaMemsetAsync(s.hist, 0, hbytes, st));
         const int pr = prof_begin(e, 20);
-        ZFB_LAUNCH(wf_select_kernel, dim3((unsigned)ctas), dim3(256), 0, st, s);
+        ZFB_LAUNCH(wf_select_kernel, dim3((unsigned)ctas), dim3(256),
+                   (size_t)(pass == 0 ? 1 : nt) * SEL_BINS * sizeof(unsigned int), st, s);
         prof_end(e, pr);
         CK(e, cudaGetLastError());
         e->counters[2] += 1;
@@ -2029,7 +2033,7 @@ int zfb_ring_quantiles(zfb_engine *e, int height, int scroll, int64_t rows_seen,
         e->counters[4] += hbytes;
         return ZFB_OK;
     };
-    // pass 0 is shared by every rank: 11 leading key bits
+    // pass 0 is shared by every rank: key bits 30..20 (bit 31 is clear for every value below zero)
     rc = sweep(0, 1);
     if (rc) return rc;
     std::vector<unsigned long long> cum0(SEL_BINS + 1, 0);
@@ -2081,14 +2085,14 @@ int zfb_ring_quantiles(zfb_engine *e, int height, int scroll, int64_t rows_seen,
             }
             rc = sweep(pass, nu);
             if (rc) return rc;
-            const int bins = pass == 1 ? 2048 : 1024;
+            const int bins = pass == 1 ? 2048 : 512;
             for (int t = 0; t < nt; ++t) {
                 const unsigned int *ht = hist.data() + (size_t)slot_of[t] * SEL_BINS;
                 long long acc = 0;
                 int b = 0;
                 while (b < bins - 1 && acc + ht[b] <= resid[t]) acc += ht[b++];
                 resid[t] -= acc;
-                key[t] = (key[t] << (pass == 1 ? 11 : 10)) | (unsigned int)b;
+                key[t] = (key[t] << (pass == 1 ? 11 : 9)) | (unsigned int)b;
             }
         }
         for (int t = 0; t < nt; ++t) value[base + t] = wf_unkey(key[t]);

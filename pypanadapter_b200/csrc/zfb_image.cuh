@@ -11,7 +11,7 @@
 // is produced by one streaming pass only when it is displayed, and only the
 // 8-bit image crosses PCIe.  Waterfall.autolevel's np.percentile(img_array[
 // img_array < 0], [2, 98]) (S:1676) is an exact order-statistic selection by
-// three 11/11/10-bit radix histograms over the same pixel function.
+// three 11/11/9-bit radix histograms over the same pixel function.
 #pragma once
 #include "zfb_common.cuh"
 
@@ -36,6 +36,7 @@ struct ImageParams {
     // neighbouring thresholds, bit-exact with the double formula, no FP64 or F2I instructions.
     const float *thr;         // [257]
     float  fscale, foff;
+    int    wide_guess;        // the fp32 guess may be off by more than 1 (degenerate level pair)
     const unsigned int *lut;  // 256 packed RGBA entries (IMG_RGBA)
     void  *out;
 };
@@ -87,12 +88,34 @@ __device__ __forceinline__ float wf_fix(const ImageParams &p, bool from_ring, bo
     return v;
 }
 
-__device__ __forceinline__ unsigned int wf_level(const ImageParams &p, const float *thr, float v) {
+// four consecutive pixels starting at x0 (x0 % 4 == 0): only the quads that
+// hold a grid column, and the few tick rows, take the per-pixel path
+__device__ __forceinline__ void wf_fix4(const ImageParams &p, bool from_ring, bool tick_row, int x0, float (&q)[4]) {
+    const int mid = p.W >> 1;
+    const bool special = tick_row || x0 == 0 || x0 + 4 >= p.W || (unsigned)(mid - x0) < 4u;
+    if (special) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) q[e] = wf_fix(p, from_ring, tick_row, x0 + e, q[e]);
+    } else if (!from_ring) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) q[e] = -500.f;
+    }
+}
+
+// thr2[g] = (thr[g], thr[g + 1]) with thr[0] = -inf and thr[256] = NaN (never reached)
+__device__ __forceinline__ unsigned int wf_level(const ImageParams &p, const float2 *thr2, float v) {
     float x = fmaf(v, p.fscale, p.foff);
-    x = (x > 0.f) ? fminf(x, 255.f) : 0.f;           // NaN -> 0
+    x = fminf(fmaxf(x, 0.f), 255.f);                 // NaN -> 0
     int g = (int)(__float_as_uint(x + 8388608.0f) - 0x4B000000u);    // round to nearest, 0..255
-    while (g < 255 && v >= thr[g + 1]) ++g;          // 0 or 1 trips for any sane level pair
-    while (g > 0 && v < thr[g]) --g;
+    if (!p.wide_guess) {
+        // |guess - index| <= 1 (the host checked the level pair): one LDS.64, two compares
+        const float2 t = thr2[g];
+        g += (v >= t.y) ? 1 : 0;
+        g -= (v < t.x) ? 1 : 0;
+    } else {
+        while (g < 255 && v >= thr2[g].y) ++g;       // degenerate level pairs: walk to the index
+        while (g > 0 && v < thr2[g].x) --g;
+    }
     return (unsigned int)g;
 }
 
@@ -101,10 +124,11 @@ constexpr int IMG_U = 4;                  // float4 loads in flight per thread
 
 template <int KIND>
 __global__ void __launch_bounds__(IMG_NT) wf_image_kernel(const ImageParams p) {
-    __shared__ float thr[260];
+    __shared__ float2 thr[256];
     __shared__ unsigned int lut[256];
     if (KIND != IMG_F32) {
-        for (int i = threadIdx.x; i < 257; i += IMG_NT) thr[i] = p.thr[i];
+        for (int i = threadIdx.x; i < 256; i += IMG_NT)
+            thr[i] = make_float2(p.thr[i], i < 255 ? p.thr[i + 1] : __uint_as_float(0x7FC00000u));
         if (KIND == IMG_RGBA)
             for (int i = threadIdx.x; i < 256; i += IMG_NT) lut[i] = p.lut[i];
         __syncthreads();
@@ -126,8 +150,7 @@ __global__ void __launch_bounds__(IMG_NT) wf_image_kernel(const ImageParams p) {
             const int x0 = xb + (u * IMG_NT + (int)threadIdx.x) * 4;
             if (x0 >= p.W) break;
             float q[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) q[e] = wf_fix(p, row != nullptr, tick_row, x0 + e, q[e]);
+            wf_fix4(p, row != nullptr, tick_row, x0, q);
             const size_t at = (size_t)y * p.W + x0;
             if (KIND == IMG_F32) {
                 *(float4 *)((float *)p.out + at) = make_float4(q[0], q[1], q[2], q[3]);
@@ -163,9 +186,9 @@ constexpr int SEL_BINS = 2048;
 
 struct SelectParams {
     ImageParams img;
-    int pass;                             // 0: key bits 31..21, 1: bits 20..10, 2: bits 9..0
+    int pass;                             // 0: key bits 30..20, 1: bits 19..9, 2: bits 8..0
     int ntargets;
-    unsigned int prefix[SEL_TARGETS];     // pass 1: key >> 21, pass 2: key >> 10 of each target
+    unsigned int prefix[SEL_TARGETS];     // pass 1: key >> 20, pass 2: key >> 9 (distinct values)
     unsigned int *hist;                   // [SEL_TARGETS][SEL_BINS] (pass 0 uses histogram 0 only)
     int rows_per_cta;
 };
@@ -188,9 +211,10 @@ constexpr unsigned int SEL_NONE = 0xFFFFFFFFu;
 __device__ __forceinline__ unsigned int wf_slot(const SelectParams &s, float v) {
     if (!(v < 0.f)) return SEL_NONE;
     const unsigned int k = wf_key(v);
-    if (s.pass == 0) return k >> 21;
-    const unsigned int pre = (s.pass == 1) ? (k >> 21) : (k >> 10);
-    const unsigned int sub = (s.pass == 1) ? ((k >> 10) & 0x7FFu) : (k & 0x3FFu);
+    // keys of negative floats have bit 31 clear: digits are bits 30..20, 19..9, 8..0
+    if (s.pass == 0) return k >> 20;
+    const unsigned int pre = (s.pass == 1) ? (k >> 20) : (k >> 9);
+    const unsigned int sub = (s.pass == 1) ? ((k >> 9) & 0x7FFu) : (k & 0x1FFu);
     unsigned int at = SEL_NONE;
 #pragma unroll
     for (int t = 0; t < SEL_TARGETS; ++t)
@@ -204,7 +228,8 @@ __device__ __forceinline__ void wf_count(unsigned int *h, unsigned int at, int l
 }
 
 __global__ void __launch_bounds__(256) wf_select_kernel(const SelectParams s) {
-    __shared__ unsigned int h[SEL_TARGETS * SEL_BINS];
+    ZFB_DYN_SMEM(smem_raw);                                  // nh * SEL_BINS counters
+    unsigned int *h = reinterpret_cast<unsigned int *>(smem_raw);
     const ImageParams &p = s.img;
     const int nh = (s.pass == 0) ? 1 : s.ntargets;
     const int lane = threadIdx.x & 31;
@@ -222,12 +247,10 @@ __global__ void __launch_bounds__(256) wf_select_kernel(const SelectParams s) {
                 const bool in = x0 < p.W;
                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (row && in) v = __ldg((const float4 *)(row + x0));
-                const float q[4] = {v.x, v.y, v.z, v.w};
+                float q[4] = {v.x, v.y, v.z, v.w};
+                wf_fix4(p, row != nullptr, tick_row, x0, q);
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const unsigned int at = in ? wf_slot(s, wf_fix(p, row != nullptr, tick_row, x0 + e, q[e])) : SEL_NONE;
-                    wf_count(h, at, lane);
-                }
+                for (int e = 0; e < 4; ++e) wf_count(h, in ? wf_slot(s, q[e]) : SEL_NONE, lane);
             }
         } else {
             for (int xb = 0; xb < p.W; xb += 256) {
