@@ -215,32 +215,6 @@ __global__ void __launch_bounds__(256) big_halfsum_kernel(const BigR16Params p) 
     if (t == 0) p.halfsum[(size_t)frame * (p.nseg + 1) + h] = sum;
 }
 
-// 16-point forward DFT, natural order in and out: X[r] = sum_q v[q] W16^(q r)
-__device__ __forceinline__ void dft16(float2 (&v)[16]) {
-    // q = 4 q1 + q0, r = r1 + 4 r0:  4-point DFTs over q1, twiddle W16^(q0 r1), 4-point DFTs over q0
-    const float c1 = 0.92387953251128673848f, s1 = 0.38268343236508978178f;   // cos, sin(pi/8)
-    const float h = 0.70710678118654752440f;
-    float2 t[4][4];                       // t[q0][r1]
-#pragma unroll
-    for (int q0 = 0; q0 < 4; ++q0) {
-        float2 a0 = v[q0], a1 = v[4 + q0], a2 = v[8 + q0], a3 = v[12 + q0];
-        dft4(a0, a1, a2, a3);
-        t[q0][0] = a0; t[q0][1] = a1; t[q0][2] = a2; t[q0][3] = a3;
-    }
-    // W16^m = exp(-2 pi i m / 16), m = q0 * r1
-    const float2 w1 = make_float2(c1, -s1), w2 = make_float2(h, -h), w3 = make_float2(s1, -c1);
-    const float2 w6 = make_float2(-h, -h), w9 = make_float2(-c1, s1);
-    t[1][1] = cmul(t[1][1], w1); t[1][2] = cmul(t[1][2], w2); t[1][3] = cmul(t[1][3], w3);
-    t[2][1] = cmul(t[2][1], w2); t[2][2] = mul_mi(t[2][2]);   t[2][3] = cmul(t[2][3], w6);
-    t[3][1] = cmul(t[3][1], w3); t[3][2] = cmul(t[3][2], w6); t[3][3] = cmul(t[3][3], w9);
-#pragma unroll
-    for (int r1 = 0; r1 < 4; ++r1) {
-        float2 a0 = t[0][r1], a1 = t[1][r1], a2 = t[2][r1], a3 = t[3][r1];
-        dft4(a0, a1, a2, a3);
-        v[r1] = a0; v[r1 + 4] = a1; v[r1 + 8] = a2; v[r1 + 12] = a3;
-    }
-}
-
 template <int KIND>
 __global__ void __launch_bounds__(256) big_r16_kernel(const BigR16Params p) {
     const int N = 1 << p.log2N, S = N >> 4;

@@ -81,10 +81,37 @@ __device__ __forceinline__ void dft8(float2 *v) {
     t = v[3]; v[3] = v[6]; v[6] = t;
 }
 
+// 16-point forward DFT, natural order in and out: X[r] = sum_q v[q] W16^(q r)
+__device__ __forceinline__ void dft16(float2 (&v)[16]) {
+    // q = 4 q1 + q0, r = r1 + 4 r0:  4-point DFTs over q1, twiddle W16^(q0 r1), 4-point DFTs over q0
+    const float c1 = 0.92387953251128673848f, s1 = 0.38268343236508978178f;   // cos, sin(pi/8)
+    const float h = 0.70710678118654752440f;
+    float2 t[4][4];                       // t[q0][r1]
+#pragma unroll
+    for (int q0 = 0; q0 < 4; ++q0) {
+        float2 a0 = v[q0], a1 = v[4 + q0], a2 = v[8 + q0], a3 = v[12 + q0];
+        dft4(a0, a1, a2, a3);
+        t[q0][0] = a0; t[q0][1] = a1; t[q0][2] = a2; t[q0][3] = a3;
+    }
+    // W16^m = exp(-2 pi i m / 16), m = q0 * r1
+    const float2 w1 = make_float2(c1, -s1), w2 = make_float2(h, -h), w3 = make_float2(s1, -c1);
+    const float2 w6 = make_float2(-h, -h), w9 = make_float2(-c1, s1);
+    t[1][1] = cmul(t[1][1], w1); t[1][2] = cmul(t[1][2], w2); t[1][3] = cmul(t[1][3], w3);
+    t[2][1] = cmul(t[2][1], w2); t[2][2] = mul_mi(t[2][2]);   t[2][3] = cmul(t[2][3], w6);
+    t[3][1] = cmul(t[3][1], w3); t[3][2] = cmul(t[3][2], w6); t[3][3] = cmul(t[3][3], w9);
+#pragma unroll
+    for (int r1 = 0; r1 < 4; ++r1) {
+        float2 a0 = t[0][r1], a1 = t[1][r1], a2 = t[2][r1], a3 = t[3][r1];
+        dft4(a0, a1, a2, a3);
+        v[r1] = a0; v[r1 + 4] = a1; v[r1 + 8] = a2; v[r1 + 12] = a3;
+    }
+}
+
 template <int RADIX> struct Log2R;
 template <> struct Log2R<2> { static constexpr int v = 1; };
 template <> struct Log2R<4> { static constexpr int v = 2; };
 template <> struct Log2R<8> { static constexpr int v = 3; };
+template <> struct Log2R<16> { static constexpr int v = 4; };
 
 // One Stockham pass of radix RADIX over the PPT values a thread holds.
 // Thread `tid` of nt = N/PPT holds v[m] = data[tid + m*nt].  A thread does
@@ -115,22 +142,35 @@ __device__ __forceinline__ void fft_pass(float2 (&v)[PPT], int tid, int nt, int 
             const int step = k << (log2tw - log2Ns - LR);
             const float2 w1 = __ldg(tw + step);
             a[1] = cmul(a[1], w1);
-            if (RADIX >= 4) {
+            if constexpr (RADIX >= 4) {
                 const float2 w2 = __ldg(tw + 2 * step);
                 const float2 w3 = cmul(w1, w2);
                 a[2] = cmul(a[2], w2);
                 a[3] = cmul(a[3], w3);
-                if (RADIX == 8) {
+                if constexpr (RADIX >= 8) {
                     const float2 w4 = __ldg(tw + 4 * step);
+                    const float2 w5 = cmul(w1, w4), w6 = cmul(w2, w4), w7 = cmul(w3, w4);
                     a[4] = cmul(a[4], w4);
-                    a[5] = cmul(a[5], cmul(w1, w4));
-                    a[6] = cmul(a[6], cmul(w2, w4));
-                    a[7] = cmul(a[7], cmul(w3, w4));
+                    a[5] = cmul(a[5], w5);
+                    a[6] = cmul(a[6], w6);
+                    a[7] = cmul(a[7], w7);
+                    if constexpr (RADIX == 16) {
+                        const float2 w8 = __ldg(tw + 8 * step);
+                        a[8] = cmul(a[8], w8);
+                        a[9] = cmul(a[9], cmul(w1, w8));
+                        a[10] = cmul(a[10], cmul(w2, w8));
+                        a[11] = cmul(a[11], cmul(w3, w8));
+                        a[12] = cmul(a[12], cmul(w4, w8));
+                        a[13] = cmul(a[13], cmul(w5, w8));
+                        a[14] = cmul(a[14], cmul(w6, w8));
+                        a[15] = cmul(a[15], cmul(w7, w8));
+                    }
                 }
             }
         }
-        if (RADIX == 8) dft8(a);
-        else if (RADIX == 4) dft4(a[0], a[1], a[2], a[3]);
+        if constexpr (RADIX == 16) dft16(a);
+        else if constexpr (RADIX == 8) dft8(a);
+        else if constexpr (RADIX == 4) dft4(a[0], a[1], a[2], a[3]);
         else bfly2(a[0], a[1]);
         if (last) {
 #pragma unroll
@@ -156,10 +196,30 @@ __device__ __forceinline__ void fft_pass(float2 (&v)[PPT], int tid, int nt, int 
 template <int LOG2N, int PPT>
 __device__ __forceinline__ void fft_block(float2 (&v)[PPT], int tid, const float2 *tw, float2 *sm) {
     constexpr int NT = (1 << LOG2N) / PPT;
-    constexpr int R8 = (LOG2N % 3 == 1) ? (LOG2N / 3 - 1) : (LOG2N / 3);   // radix-8 passes
-    constexpr int REM = LOG2N - 3 * R8;                                   // 0, 2 or 4 bits
     const bool active = tid < NT;
     int log2Ns = 0;
+#ifndef ZFB_WELCH_NO_R16
+    if constexpr (PPT == 16) {
+        // 16 points per thread = one radix-16 butterfly per pass: 2048 = 16.16.8,
+        // 4096 = 16.16.16, 8192 = 16.16.8.4 -- one exchange through shared memory
+        // (and two barriers) fewer than the radix-8 schedule, 4 table lookups per
+        // thread and pass instead of 6
+        static_assert(LOG2N >= 11 && LOG2N <= 13, "radix-16 schedule covers 2048..8192");
+        fft_pass<16, PPT>(v, tid, NT, LOG2N, 0, tw, sm, false, active);
+        fft_pass<16, PPT>(v, tid, NT, LOG2N, 4, tw, sm, false, active);
+        if constexpr (LOG2N == 11) {
+            fft_pass<8, PPT>(v, tid, NT, LOG2N, 8, tw, sm, true, active);
+        } else if constexpr (LOG2N == 12) {
+            fft_pass<16, PPT>(v, tid, NT, LOG2N, 8, tw, sm, true, active);
+        } else {
+            fft_pass<8, PPT>(v, tid, NT, LOG2N, 8, tw, sm, false, active);
+            fft_pass<4, PPT>(v, tid, NT, LOG2N, 11, tw, sm, true, active);
+        }
+        return;
+    }
+#endif
+    constexpr int R8 = (LOG2N % 3 == 1) ? (LOG2N / 3 - 1) : (LOG2N / 3);   // radix-8 passes
+    constexpr int REM = LOG2N - 3 * R8;                                   // 0, 2 or 4 bits
 #pragma unroll
     for (int p = 0; p < R8; ++p) {
         const bool last = (REM == 0) && (p == R8 - 1);
