@@ -57,6 +57,13 @@ extern "C" {
                                   -- the call S:2098 / T:1534 makes -- plus welch   */
 #define ZFB_FLAG_LINEAR  2     /* rows hold the linear PSD (welch's Pxx, S:2111)
                                   instead of 20*log10(abs(.)) (S:2117-2119)         */
+#define ZFB_FLAG_ONESIDED 4    /* the chunk is REAL (imaginary parts zero: AudioPan,
+                                 S:712-714, Data.new_real T:1413-1417) and fft_ratio is 1:
+                                 scipy.signal.welch then returns the one-sided density
+                                 (N/2+1 bins, doubled except DC and Nyquist) and the
+                                 reference fftshifts and crops THAT array (T:1538-1543,
+                                 S:2111-2114).  Rows are row_width/2 + 1 bins wide:
+                                 shifted[N/2 - row_width/2 : N/2 + 1].  N <= 8192.      */
 
 typedef struct zfb_engine zfb_engine;
 

@@ -22,6 +22,16 @@ def tone_noise(n, fs, tones, sigma, seed, dtype=np.complex128):
     return x.astype(dtype)
 
 
+def real_tone_noise(n, fs, tones, sigma, seed, dtype=np.float64):
+    """Real samples, as AudioPan's callback delivers them (S:712-714)."""
+    k = np.arange(n, dtype=np.float64)
+    x = np.zeros(n, dtype=np.float64)
+    for f, a in tones:
+        x += a * np.cos(2 * np.pi * (f / fs) * k + 0.3)
+    x += sigma * np.random.default_rng(seed).standard_normal(n)
+    return x.astype(dtype)
+
+
 def ref_sine(size, cycles=10.0):
     """The reference's own Waveform.Sine test signal (S:992-994)."""
     a = np.linspace(0, 2 * np.pi * cycles, size)
@@ -47,6 +57,9 @@ def make_input(case: dict) -> np.ndarray:
         return tone_noise(case["n"], case["fs"], case["tones"], case["sigma"],
                           case["seed"],
                           np.complex64 if case.get("c64") else np.complex128)
+    if kind == "real_tone_noise":
+        return real_tone_noise(case["n"], case["fs"], case["tones"], case["sigma"], case["seed"],
+                               np.float32 if case.get("f32") else np.float64)
     if kind == "ref_sine":
         return ref_sine(case["n"], case.get("cycles", 10.0))
     if kind == "ref_random":
@@ -132,6 +145,22 @@ CASES = [
          R=1, window="hann"),
     dict(name="n32_T", path="T", input="tone_noise", n=32 * 64, fs=48e3,
          tones=[(700.0, 0.5)], sigma=1e-3, seed=73, N=32, R=2,
+         window="hamming"),
+    # --- real samples (AudioPan, S:712-714; Data.new_real T:1413-1417): without
+    #     zoom welch is one-sided and the reference fftshifts/crops N/2+1 bins
+    #     (S path; T path only with Data.new_real -- its own set-up stores
+    #     everything in the complex buffer, T:1807, hence two-sided rows)
+    dict(name="audio_R1_T", path="T", input="real_tone_noise", n=2048 * 12,
+         fs=48e3, tones=[(5000.0, 0.5), (11250.0, 0.02)], sigma=1e-3, seed=90,
+         N=2048, R=1, window="hamming"),
+    dict(name="audio_R1_Treal", path="T", data_real=True, input="real_tone_noise",
+         n=2048 * 12, fs=48e3, tones=[(5000.0, 0.5), (11250.0, 0.02)], sigma=1e-3,
+         seed=90, N=2048, R=1, window="hamming"),
+    dict(name="audio_R1_S", path="S", n_win=1024, input="real_tone_noise",
+         f32=True, n=2048 * 12, fs=48e3, tones=[(3000.0, 0.5)], sigma=1e-3,
+         seed=91, N=2048, R=1, window="hann"),
+    dict(name="audio_R4_T", path="T", input="real_tone_noise", n=1024 * 24,
+         fs=48e3, tones=[(900.0, 0.4)], sigma=1e-3, seed=92, N=1024, R=4,
          window="hamming"),
 ]
 

@@ -43,7 +43,7 @@ def reference_row(case):
         x = np.flip(x)                    # what RTLSDR.Read hands on (T:460)
     if case["path"] == "T":
         return rh.thread_update(x, case["fs"], case["N"], case["R"],
-                                case["window"])
+                                case["window"], real=bool(case.get("data_real")))
     return rh.spectrum_update(x, case["fs"], case["N"], case["R"],
                               case["window"], case["n_win"])
 

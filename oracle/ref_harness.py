@@ -187,16 +187,21 @@ def _quiet_data(mod, chunk_size=None):
     return d
 
 
-def thread_update(chunk, fs, fft_size, fft_ratio, window):
+def thread_update(chunk, fs, fft_size, fft_ratio, window, real=False):
     """Data.add(chunk) + PSD.update() (T:1433-1468, T:1513-1549) -> psd row.
-    The chunk must fit the fold-back buffer (max_size = 16*chunk_size)."""
+    The chunk must fit the fold-back buffer (max_size = 16*chunk_size).
+    ``real``: allocate with Data.new_real (T:1413-1417) instead of the
+    new_complex the reference's own set-up calls (T:1807)."""
     import contextlib
     import io
     import warnings
     mod = load("thread")
     _set_state(mod, fs, fft_size, fft_ratio, 1, window)
     d = _quiet_data(mod, max(8196 * 2, -(-len(chunk) // 16)))
-    d.new_complex()
+    if real:
+        d.new_real()
+    else:
+        d.new_complex()
     d.delay_time = 0.
     d.add(chunk)
     d.delay_time = 0.

@@ -29,6 +29,7 @@ ZFB_MODE_FAST = 1
 FAST_MAX_STAGES = 12
 ZFB_FLAG_NO_LO = 1
 ZFB_FLAG_LINEAR = 2
+ZFB_FLAG_ONESIDED = 4
 
 ABI_VERSION = 2
 PROF_CLASSES = 21

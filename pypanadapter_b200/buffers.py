@@ -179,14 +179,13 @@ class PSD:
         row = None
         try:
             if size >= st.fft_size:                            # T:1522
-                if d.real and not st.fft_ratio > 1:
-                    raise NotImplementedError("real samples without zoom (one-sided welch) are not supported")
                 # enqueue under the lock: the kernels read the device mirror the
                 # producer has just finished filling; afterwards it moves on to
                 # the other mirror, so nothing is overwritten under the kernels
                 self.engine.configure(st.panadapter.SampleRate, st.fft_size, st.fft_ratio, size,
                                       st.fft_tapering, dtype=d.wire, flip=self.flip,
-                                      crop="thread", ema_alpha=self.ema_alpha)
+                                      crop="thread", ema_alpha=self.ema_alpha,
+                                      onesided=d.real and not st.fft_ratio > 1)    # T:1538: welch of real samples
                 row = self.engine.samples_process()
         finally:
             d.get_data_end()

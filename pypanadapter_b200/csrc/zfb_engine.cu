@@ -71,6 +71,8 @@ struct zfb_engine {
     int welch_splits = 0;              // 0 = automatic
     int fir_generic = 0;               // 1: never use the register-blocked FIR kernel (tests)
     int nperseg = 0, hop = 0, nseg = 0, W = 0, log2N = 0;
+    int Wp = 0;                        // width of a pow row: W, or N for one-sided rows
+    bool onesided = false;             // ZFB_FLAG_ONESIDED
     double sum_w2 = 0.0;
     int group = 1, group_user = 0;
     int nsplit_cap = 1;
@@ -907,7 +909,7 @@ int run_group(zfb_engine *e, const void *d_in, int gf, float *d_rows) {
         w.reuse = (e->nperseg == (1 << e->log2N) && e->hop * 2 == e->nperseg) ? 1 : 0;
         w.window = (const float *)e->window.p;
         w.twiddle = (const float2 *)e->twiddle.p;
-        w.W = e->W;
+        w.W = e->Wp;
         w.pow_out = (float *)e->pow.p;
         WelchEntry we = welch_lookup(e->log2N, kind);
         const int pr = prof_begin(e, 16);
@@ -1019,6 +1021,10 @@ int run_group(zfb_engine *e, const void *d_in, int gf, float *d_rows) {
     f.nframes = gf;
     f.nsplit = nsplit;
     f.W = e->W;
+    f.Wp = e->Wp;
+    f.onesided = e->onesided ? 1 : 0;
+    f.os_lo = (1 << e->log2N) / 2 - c.row_width / 2;
+    f.os_N = 1 << e->log2N;
     f.scale = (float)(1.0 / (c.fs * e->sum_w2) / (double)e->nseg);
     f.alpha = (c.ema_alpha >= 0.0) ? (float)c.ema_alpha : -1.f;
     f.linear = (c.flags & ZFB_FLAG_LINEAR) ? 1 : 0;
@@ -1310,6 +1316,11 @@ int zfb_configure(zfb_engine *e, const zfb_config *cfg) {
         return fail(e, ZFB_EINVAL, "unknown mode %d", cfg->mode);
     if (cfg->row_width < 2 || cfg->row_width > N || (cfg->row_width & 1))
         return fail(e, ZFB_EINVAL, "row_width %d: must be even and in [2, fft_size]", cfg->row_width);
+    const bool onesided = (cfg->flags & ZFB_FLAG_ONESIDED) != 0;
+    if (onesided && (cfg->fft_ratio != 1 || cfg->dtype != ZFB_DTYPE_C64 || l2 > kMaxLog2Small))
+        return fail(e, ZFB_EINVAL, "one-sided rows need fft_ratio 1, complex64 storage of the real samples and "
+                    "fft_size <= %d", 1 << kMaxLog2Small);
+    const int row_w = onesided ? cfg->row_width / 2 + 1 : cfg->row_width;
     if (!cfg->window) return fail(e, ZFB_EINVAL, "window is NULL");
     Geometry g;
     int rc = geometry(cfg->frame_len, N, cfg->fft_ratio, g);
@@ -1325,8 +1336,8 @@ int zfb_configure(zfb_engine *e, const zfb_config *cfg) {
         return fail(e, ZFB_EINVAL, "fft_size %d needs a decimated chunk of at least fft_size samples (got %d)",
                     N, g.ndec);
 
-    const bool geom_changed = !e->configured || e->W != cfg->row_width || e->cfg.fft_size != N ||
-                              e->cfg.fft_ratio != cfg->fft_ratio;
+    const bool geom_changed = !e->configured || e->W != row_w || e->onesided != onesided ||
+                              e->cfg.fft_size != N || e->cfg.fft_ratio != cfg->fft_ratio;
     // everything below may replace buffers still in use
     CK(e, cudaStreamSynchronize(e->stream));
 
@@ -1377,7 +1388,9 @@ int zfb_configure(zfb_engine *e, const zfb_config *cfg) {
     e->nperseg = g.nperseg;
     e->hop = g.hop;
     e->nseg = g.nseg;
-    e->W = cfg->row_width;
+    e->W = row_w;
+    e->Wp = onesided ? N : row_w;
+    e->onesided = onesided;
     e->log2N = l2;
     e->sum_w2 = s2;
     // stage-0 LO tables (one per tile geometry)
@@ -1418,7 +1431,7 @@ int zfb_configure(zfb_engine *e, const zfb_config *cfg) {
                 if (rc) return rc;
             }
     }
-    rc = ensure(e, e->pow, (size_t)e->group * (size_t)e->nsplit_cap * (size_t)e->W * sizeof(float));
+    rc = ensure(e, e->pow, (size_t)e->group * (size_t)e->nsplit_cap * (size_t)e->Wp * sizeof(float));
     if (rc) return rc;
     if (l2 > kMaxLog2Small) {
         rc = ensure(e, e->big, big_scratch_bytes(l2, g.nseg, e->group));

@@ -365,8 +365,13 @@ welch_kernel(const WelchParams p) {
 // across consecutive frames on linear power, then dB20.
 //   a_0 = p_0 (when the state is empty), a_i = alpha p_i + (1-alpha) a_(i-1)
 struct FinalizeParams {
-    float *pow_io;            // [nframes][nsplit][W]; slot 0 of a frame receives its reduced row
-    int    nframes, nsplit, W;
+    float *pow_io;            // [nframes][nsplit][Wp] partial sums from the Welch kernels
+    int    nframes, nsplit, W;   // W: row width
+    int    Wp;                // width of a pow row (== W except one-sided rows)
+    // one-sided rows (real input, R = 1): row column c is bin k = (c + os_lo + (M+1)/2) mod M
+    // of the M = N/2+1 one-sided bins (np.fft.fftshift of an odd-length array), doubled
+    // except DC and Nyquist; pow holds the full two-sided, fftshifted N-bin row
+    int    onesided, os_lo, os_N;
     float  scale;             // 1 / (fs * sum w^2) / nseg
     float  alpha;             // < 0: EMA off
     int    linear;            // 1: emit linear power instead of dB20
@@ -393,15 +398,27 @@ __device__ __forceinline__ void emit_row_value(const FinalizeParams &p, int f, i
     if (p.ring) p.ring[(size_t)((p.ring_pos + f) % p.ring_rows) * p.W + col] = out;
 }
 
+// column of the pow row that feeds row column `col`, and the one-sided factor
+__device__ __forceinline__ int pow_col(const FinalizeParams &p, int col, float &factor) {
+    factor = 1.f;
+    if (!p.onesided) return col;
+    const int M = p.os_N / 2 + 1;
+    int k = col + p.os_lo + (M + 1) / 2;
+    if (k >= M) k -= M;
+    factor = (k == 0 || k == p.os_N / 2) ? 1.f : 2.f;
+    return (k + p.os_N / 2) & (p.os_N - 1);
+}
+
 // without EMA: one thread per (frame, column)
 __global__ void reduce_rows_kernel(const FinalizeParams p) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long long)p.nframes * p.W) return;
     const int f = (int)(idx / p.W), col = (int)(idx % p.W);
-    float *src = p.pow_io + (size_t)f * p.nsplit * p.W + col;
+    float factor;
+    const float *src = p.pow_io + (size_t)f * p.nsplit * p.Wp + pow_col(p, col, factor);
     float pw = 0.f;
-    for (int s = 0; s < p.nsplit; ++s) pw += src[(size_t)s * p.W];
-    pw *= p.scale;
+    for (int s = 0; s < p.nsplit; ++s) pw += src[(size_t)s * p.Wp];
+    pw *= p.scale * factor;
     emit_row_value(p, f, col, pw);
 }
 
@@ -426,7 +443,10 @@ __global__ void __launch_bounds__(EMA_NT) ema_rows_kernel(const FinalizeParams p
     const bool walker = threadIdx.x < EMA_COLS;
     bool have = p.ema_have != 0;
     float a = (walker && have && ok) ? p.ema_state[col] : 0.f;
-    const size_t stride = (size_t)p.nsplit * p.W;
+    const size_t stride = (size_t)p.nsplit * p.Wp;
+    float factor = 1.f;
+    const int scol = ok ? pow_col(p, col, factor) : 0;
+    const float scale = p.scale * factor;
     for (int f0 = 0; f0 < p.nframes; f0 += EMA_FR) {
         const int n = min(EMA_FR, p.nframes - f0);
         {
@@ -437,11 +457,11 @@ __global__ void __launch_bounds__(EMA_NT) ema_rows_kernel(const FinalizeParams p
 #pragma unroll
                 for (int k = 0; k < EMA_CH; ++k) {
                     const int i = fs + k * EMA_FPP;
-                    if (ok && i < n) pw[k] += p.pow_io[(size_t)(f0 + i) * stride + (size_t)s * p.W + col];
+                    if (ok && i < n) pw[k] += p.pow_io[(size_t)(f0 + i) * stride + (size_t)s * p.Wp + scol];
                 }
             }
 #pragma unroll
-            for (int k = 0; k < EMA_CH; ++k) tile[(fs + k * EMA_FPP) * EMA_COLS + c] = pw[k] * p.scale;
+            for (int k = 0; k < EMA_CH; ++k) tile[(fs + k * EMA_FPP) * EMA_COLS + c] = pw[k] * scale;
         }
         __syncthreads();
         if (walker) {

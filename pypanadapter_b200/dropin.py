@@ -44,7 +44,10 @@ def _spectrum_methods(module, engine_of):
         self.win.setWindowTitle('PEPYSCOPE - IS0KYB - N_FFT: %d, BW: %.1f kHz'
                                 % (st.fft_size, bw_hz / 1000. / st.fft_ratio))
         chunk = np.asarray(chunk)
-        eng.configure(fs, st.fft_size, st.fft_ratio, len(chunk), st.fft_tapering, crop=self.N_WIN)
+        # real chunks (AudioPan, S:712-714) without zoom: welch is one-sided (S:2111)
+        onesided = np.isrealobj(chunk) and chunk.dtype != np.uint8 and not st.fft_ratio > 1
+        eng.configure(fs, st.fft_size, st.fft_ratio, len(chunk), st.fft_tapering, crop=self.N_WIN,
+                      onesided=onesided)
         psd = eng.process(chunk)[0].astype(np.float64)
         self.waterfall.image_update(psd)
         hz = fs / 4
@@ -65,12 +68,14 @@ def _thread_psd_update(module, engine_of):
             if size >= st.fft_size:
                 if isinstance(d, buffers.Data):
                     eng.configure(st.panadapter.SampleRate, st.fft_size, st.fft_ratio, size,
-                                  st.fft_tapering, dtype=d.wire, crop="thread")
+                                  st.fft_tapering, dtype=d.wire, crop="thread",
+                                  onesided=d.real and not st.fft_ratio > 1)
                     row = eng.samples_process()
                 else:               # the reference's own Data: snapshot under the lock
+                    real = np.isrealobj(d.data)                 # Data.new_real (T:1413-1417)
                     chunk = np.array(d.data[:size], dtype=np.complex64)
                     eng.configure(st.panadapter.SampleRate, st.fft_size, st.fft_ratio, size,
-                                  st.fft_tapering, crop="thread")
+                                  st.fft_tapering, crop="thread", onesided=real and not st.fft_ratio > 1)
                     row = eng.process(chunk)[0]
         finally:
             d.get_data_end()

@@ -131,18 +131,23 @@ class ZoomPSD:
     # -- configuration ---------------------------------------------------
     def configure(self, fs, fft_size, fft_ratio, frame_len, window="hamming", *,
                   dtype="c64", flip=False, f_demod=1.0, crop="thread",
-                  ema_alpha=None, no_lo=False, linear=False, mode="fast"):
+                  ema_alpha=None, no_lo=False, linear=False, mode="fast", onesided=False):
         """Plan for a frame shape (cheap if nothing changed).  Mirrors the
         AppState the reference reads per frame (S:1492-1497).
 
         ``mode``: ``"exact"`` -- every decimate call by the zero-phase IIR
         kernels; ``"fast"`` -- polyphase-FIR interior + exact last stage +
         exact chunk edges (same parity bar; falls back to exact for
-        fft_ratio < 4 or short chunks, see ``fast_active``)."""
+        fft_ratio < 4 or short chunks, see ``fast_active``).
+
+        ``onesided``: the samples are REAL (AudioPan S:712-714; stored as
+        complex64 with zero imaginary part) and ``fft_ratio`` is 1: rows are what
+        the reference gets from welch's one-sided spectrum (N/2+1 bins) after
+        its fftshift and crop (T:1538-1543), ``crop_width/2 + 1`` bins wide."""
         fft_ratio_i = int(fft_ratio)
         wkey = window if isinstance(window, (str, tuple)) else ("array", np.asarray(window).tobytes())
         key = (float(fs), int(fft_size), float(fft_ratio), int(frame_len), wkey, dtype, bool(flip),
-               float(f_demod), crop, ema_alpha, bool(no_lo), bool(linear), mode)
+               float(f_demod), crop, ema_alpha, bool(no_lo), bool(linear), mode, bool(onesided))
         if key == self._key:
             return self
         geo = plan_geometry(frame_len, fft_size, fft_ratio_i, self._lib)
@@ -163,13 +168,16 @@ class ZoomPSD:
         if mode == "fast" and geo["nstages"] >= 2:
             self._set_fast_plan(1 << geo["nstages"])
             cfg.mode = _lib.ZFB_MODE_FAST
-        cfg.flags = (_lib.ZFB_FLAG_NO_LO if no_lo else 0) | (_lib.ZFB_FLAG_LINEAR if linear else 0)
+        cfg.flags = (_lib.ZFB_FLAG_NO_LO if no_lo else 0) | (_lib.ZFB_FLAG_LINEAR if linear else 0) | \
+                    (_lib.ZFB_FLAG_ONESIDED if onesided else 0)
+        if onesided and (fft_ratio_i != 1 or dtype != "c64"):
+            raise ValueError("onesided rows are the real-input, fft_ratio == 1 case")
         cfg.f_demod = float(f_demod)
         cfg.ema_alpha = -1.0 if ema_alpha is None else float(ema_alpha)
         cfg.window = w.ctypes.data_as(C.POINTER(C.c_double))
         self._check(self._lib.zfb_configure(self._h, C.byref(cfg)), "zfb_configure")
         self._key = key
-        self.row_width = int(W)
+        self.row_width = int(W) // 2 + 1 if onesided else int(W)
         self.frame_len = int(frame_len)
         self.dtype = dtype
         self.geometry = geo
@@ -433,7 +441,9 @@ def zoom_psd(chunk, fs, fft_size, fft_ratio, window, *, f_demod=1.0, crop="threa
              flip=False, ema_alpha=None, mode="fast", engine: ZoomPSD | None = None) -> np.ndarray:
     """One dB20 waterfall row of one chunk (float64 ndarray[W]).
 
-    ``chunk``: 1-D complex64/complex128, or interleaved uint8 I,Q (RTL-SDR).
+    ``chunk``: 1-D complex64/complex128, interleaved uint8 I,Q (RTL-SDR), or
+    real floats (AudioPan, S:712-714; without zoom the row is then the
+    reference's fftshifted one-sided spectrum, T:1538-1543).
     ``crop``: ``'thread'`` reproduces PSD.update (T:1542-1543); an int N_WIN
     reproduces ApplicationDisplay.update (S:2114); None keeps all N bins.
     """
@@ -447,6 +457,7 @@ def zoom_psd(chunk, fs, fft_size, fft_ratio, window, *, f_demod=1.0, crop="threa
         dtype, n = "u8", chunk.size // 2
     else:
         dtype, n = "c64", chunk.size
+    onesided = dtype == "c64" and np.isrealobj(chunk) and not fft_ratio > 1
     eng.configure(fs, fft_size, fft_ratio, n, window, dtype=dtype, flip=flip,
-                  f_demod=f_demod, crop=crop, ema_alpha=ema_alpha, mode=mode)
+                  f_demod=f_demod, crop=crop, ema_alpha=ema_alpha, mode=mode, onesided=onesided)
     return eng.process(chunk)[0].astype(np.float64)

@@ -51,14 +51,16 @@ def decimate(x, q, n=None, ftype="iir", axis=-1, zero_phase=True, *, engine: Zoo
 def welch(x, fs=1.0, window="hann", nperseg=None, noverlap=None, nfft=None, detrend="constant",
           return_onesided=True, scaling="density", axis=-1, average="mean", *,
           engine: ZoomPSD | None = None):
-    """``scipy.signal.welch(x, fs, window=w, nperseg=N, nfft=N)`` for complex
-    input: two-sided density in natural FFT order (scipy:_spectral_py.py:515)."""
+    """``scipy.signal.welch(x, fs, window=w, nperseg=N, nfft=N)``: two-sided
+    density in natural FFT order for complex input, one-sided (N/2+1 bins)
+    for real input (scipy:_spectral_py.py:515, :915-916)."""
     if noverlap is not None or detrend != "constant" or scaling != "density" or axis != -1 \
             or average != "mean":
         raise NotImplementedError("only the welch defaults the reference relies on are accelerated")
+    real = np.isrealobj(np.asarray(x))
+    if real and not return_onesided:
+        raise NotImplementedError("two-sided spectra of real input are not accelerated")
     x = _as_complex_1d(x)
-    if np.isrealobj(x):
-        raise NotImplementedError("real input (one-sided spectrum) is not accelerated")
     if nperseg is None:
         nperseg = 256
     if nfft is None:
@@ -66,6 +68,11 @@ def welch(x, fs=1.0, window="hann", nperseg=None, noverlap=None, nfft=None, detr
     if nfft != nperseg:
         raise NotImplementedError("nfft must equal nperseg (S:2111)")
     eng = engine or default_engine()
+    if real:
+        eng.configure(fs, nfft, 1, len(x), window, crop=None, linear=True, onesided=True)
+        p = eng.process(x)[0]                       # fftshifted one-sided bins, as the reference crops them
+        out_dtype = np.float32 if np.asarray(x).dtype == np.float32 else np.float64
+        return np.fft.rfftfreq(nfft, 1.0 / fs), np.fft.ifftshift(p).astype(out_dtype)
     eng.configure(fs, nfft, 1, len(x), window, crop=None, linear=True)
     p = eng.process(x)[0]
     pxx = np.fft.ifftshift(p)

@@ -84,6 +84,33 @@ def psd_update_u8(engine):
     parity.assert_row_parity(psd.psd, want, parity.floor_db20(w.fs, w.window, w.fft_size, True), "u8 PSD.update")
 
 
+def psd_update_real(engine):
+    """Data.new_real (T:1413-1417) + PSD.update without zoom: welch of real
+    samples is one-sided and the reference fftshifts / crops those N/2+1 bins
+    (golden audio_R1_Treal, recorded from the reference's own methods)."""
+    case = gc.case_by_name("audio_R1_Treal")
+    x = gc.make_input(case)
+    state = types.SimpleNamespace(fft_size=case["N"], fft_ratio=case["R"], fft_tapering=case["window"],
+                                  panadapter=types.SimpleNamespace(SampleRate=case["fs"]))
+    d = Data(engine=engine).new_real()
+    psd = PSD(d, state)
+    for i in range(0, len(x), 4096):
+        d.add(x[i:i + 4096])
+    psd.update()
+    want = parity.golden_rows()["audio_R1_Treal"]
+    assert psd.psd.shape == want.shape == (case["N"] // 2 + 1,)
+    parity.assert_row_parity(psd.psd, want, parity.floor_db20(case["fs"], case["window"], case["N"], False),
+                             "real PSD.update")
+    # zoomed: the mix makes the chunk complex, rows are two-sided again (T:1525-1536)
+    state.fft_ratio = 4
+    for i in range(0, len(x), 4096):
+        d.add(x[i:i + 4096])
+    psd.update()
+    want = zo.zoom_psd(x, case["fs"], case["N"], 4, case["window"])
+    parity.assert_row_parity(psd.psd, want, parity.floor_db20(case["fs"], case["window"], case["N"], True),
+                             "real PSD.update R=4")
+
+
 def waterfall_image(engine):
     """Waterfall.img_array assembled from the device ring == the reference's
     img_array after the same image_update calls (golden waterfall.npz)."""
@@ -202,8 +229,16 @@ def scipy_shaped_calls(engine):
     import pytest
     with pytest.raises(NotImplementedError):
         zsig.decimate(x, 3, engine=engine)
+    # real input: one-sided density, natural order (scipy:_spectral_py.py:915-916)
+    xr = np.ascontiguousarray(x.real)
+    f1, p1 = zsig.welch(xr, 48e3, window="hann", nperseg=512, nfft=512, engine=engine)
+    f1r, p1r = scipy.signal.welch(xr, 48e3, window="hann", nperseg=512, nfft=512)
+    assert np.array_equal(f1, f1r) and p1.shape == (257,) and p1.dtype == np.float64
+    assert np.abs(10 * np.log10(p1 / p1r)).max() < 0.005
+    p32 = zsig.welch(xr.astype(np.float32), 48e3, nperseg=256, nfft=256, engine=engine)[1]
+    assert p32.dtype == np.float32 and p32.shape == (129,)
     with pytest.raises(NotImplementedError):
-        zsig.welch(x.real, 48e3, nperseg=512, engine=engine)
+        zsig.welch(xr, 48e3, nperseg=512, return_onesided=False, engine=engine)
     with pytest.raises(ValueError):
         zsig.decimate(x[:27], 2, engine=engine)          # scipy: padlen
 

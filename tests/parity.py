@@ -64,8 +64,11 @@ def run_case(engine, case, x=None, mode="exact"):
         x = gc.make_input(case)
     crop, dtype = case_config(case)
     n = len(x) // 2 if dtype == "u8" else len(x)
+    # welch of real samples is one-sided (S:2111; T:1538 only when Data holds reals)
+    onesided = dtype == "c64" and np.isrealobj(x) and case["R"] == 1 and \
+        (case["path"] == "S" or bool(case.get("data_real")))
     engine.configure(case["fs"], case["N"], case["R"], n, case["window"], dtype=dtype,
-                     flip=bool(case.get("flip")), crop=crop, mode=mode)
+                     flip=bool(case.get("flip")), crop=crop, mode=mode, onesided=onesided)
     return engine.process(x)[0].astype(np.float64)
 
 
@@ -80,5 +83,7 @@ def oracle_row(case, x=None):
     if x is None:
         x = gc.make_input(case)
     crop, _ = case_config(case)
+    if np.isrealobj(x) and x.dtype != np.uint8 and case["path"] == "T" and not case.get("data_real"):
+        x = x.astype(np.complex128)              # the reference's Data buffer is complex (T:1807)
     return zo.zoom_psd(x, case["fs"], case["N"], case["R"], case["window"], crop=crop,
                        flip=bool(case.get("flip")))

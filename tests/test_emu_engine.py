@@ -63,6 +63,10 @@ def test_psd_update_u8(emu_engine):
     bs.psd_update_u8(emu_engine)
 
 
+def test_psd_update_real(emu_engine):
+    bs.psd_update_real(emu_engine)
+
+
 def test_waterfall_image(emu_engine):
     bs.waterfall_image(emu_engine)
 
