@@ -134,7 +134,10 @@ int  zfb_set_group(zfb_engine *e, int frames_per_group);
 int  zfb_reset_ema(zfb_engine *e);
 /* tuning knobs (no effect on results): "decim_threads" = 0 (auto) | 128 | 256
  * threads per decimator CTA (8192- / 16384-sample shared-memory region);
- * "welch_splits" = CTAs per frame in the Welch kernel, 0 = auto. */
+ * "welch_splits" = CTAs per frame in the Welch kernel, 0 = auto.
+ * "ring_append" = 1 (default): every processed row also enters the waterfall
+ * ring; 0: only zfb_ring_push_rows does (display loops that show a subset of
+ * the rows, like the threaded variant's GUI timer, T:2140-2148). */
 int  zfb_set_option(zfb_engine *e, const char *name, long long value);
 
 /* ---- the hot path ----------------------------------------------------- */

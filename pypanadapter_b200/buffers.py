@@ -220,6 +220,7 @@ class Waterfall:
 
     def init_image(self):                                      # S:1625-1635
         self.rows_seen = 0
+        self._pending_engine_rows = 0    # a resized ring starts empty: the row in hand is pushed
         self.engine.ring_configure(max(4, self.fftwidth // 4))
 
     def note_engine_rows(self, n=1):

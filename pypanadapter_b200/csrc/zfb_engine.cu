@@ -58,6 +58,7 @@ struct zfb_engine {
     cudaStream_t aux_stream = nullptr;           // edge strips of mode fast run beside the FIR interior
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int strips_async = 1;                        // zfb_set_option("strips_async")
+    int ring_append = 1;                         // zfb_set_option("ring_append"): processed rows enter the ring
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
     bool slot_busy[2] = {false, false};
 
@@ -1031,7 +1032,7 @@ int run_group(zfb_engine *e, const void *d_in, int gf, float *d_rows) {
     f.ema_state = (float *)e->ema.p;
     f.ema_have = e->ema_have ? 1 : 0;
     f.rows = d_rows;
-    f.ring = (float *)e->ring.p;
+    f.ring = e->ring_append ? (float *)e->ring.p : nullptr;
     f.ring_pos = (long long)(e->ring_written % e->ring_rows);
     f.ring_rows = e->ring_rows;
     f.chan_frames = e->cur_nch > 0 ? e->cur_chan_frames : 0;
@@ -1047,7 +1048,7 @@ int run_group(zfb_engine *e, const void *d_in, int gf, float *d_rows) {
     e->counters[2] += 1;
     prof_end(e, prf);
     CK(e, cudaGetLastError());
-    e->ring_written += gf;
+    if (e->ring_append) e->ring_written += gf;
     e->last_group_frames = gf;
     e->counters[0] += (uint64_t)gf;
     e->counters[1] += (uint64_t)gf * (uint64_t)c.frame_len;
@@ -1537,6 +1538,10 @@ int zfb_set_option(zfb_engine *e, const char *name, long long value) {
     }
     if (strcmp(name, "strips_async") == 0) {
         e->strips_async = value ? 1 : 0;
+        return ZFB_OK;
+    }
+    if (strcmp(name, "ring_append") == 0) {
+        e->ring_append = value ? 1 : 0;
         return ZFB_OK;
     }
     if (strcmp(name, "fir_generic") == 0) {

@@ -10,6 +10,9 @@ the AppState object stay the reference's own:
 * ``ApplicationDisplay.zoomfft`` / ``.update(chunk)``  (S:2088-2130)
 * ``PSD.update``                                      (T:1513-1549)
 * ``Data``'s storage and ``add`` / ``get_data_*``      (T:1400-1483)
+* ``Waterfall.init_image`` / ``image_update`` / ``autolevel`` / ``newlevel``
+  and ``img_array``                                   (S:1625-1686): rows stay
+  in the device ring, ``setImage`` receives 8-bit colour indices
 
 ``install`` returns a dict of the originals so that ``uninstall`` can put
 them back.
@@ -49,6 +52,9 @@ def _spectrum_methods(module, engine_of):
         eng.configure(fs, st.fft_size, st.fft_ratio, len(chunk), st.fft_tapering, crop=self.N_WIN,
                       onesided=onesided)
         psd = eng.process(chunk)[0].astype(np.float64)
+        wf = getattr(self.waterfall, "__dict__", {}).get("_zfb_wf")
+        if isinstance(wf, buffers.Waterfall) and wf.engine is eng:
+            wf.note_engine_rows(1)                                  # the row is in the device ring already
         self.waterfall.image_update(psd)
         hz = fs / 4
         self.spectrum_plot.setData(np.linspace(-hz, hz, psd.shape[0]), psd, pen="g")
@@ -88,7 +94,62 @@ def _thread_psd_update(module, engine_of):
     return update
 
 
-def install(module, *, engine: ZoomPSD | None = None, replace_data: bool = True) -> dict:
+_ABSENT = object()
+
+
+def _waterfall_methods(module, engine_of):
+    """Waterfall.init_image / image_update / autolevel / newlevel (S:1625-1686)
+    on the device ring: nothing is rolled or redrawn on the host, the item is
+    handed the 8-bit colour indices (with levels [0, 256] the table lookup
+    pyqtgraph then does is the identity on them)."""
+
+    def mirror(self) -> buffers.Waterfall:
+        wf = self.__dict__.get("_zfb_wf")             # (not getattr: Qt base classes may answer anything)
+        if wf is None:
+            wf = self.__dict__["_zfb_wf"] = buffers.Waterfall(engine_of(), scroll=module.AppState.scroll)
+        wf.scroll = module.AppState.scroll
+        return wf
+
+    def levels(self):
+        return self.__dict__.get("_zfb_levels", (self.minlev, self.maxlev))
+
+    def init_image(self):                                           # S:1625-1635
+        st = module.AppState
+        bw_hz = st.panadapter.SampleRate / st.fft_size * self.fftwidth / 1.e6 / st.fft_ratio
+        self.scale(bw_hz, 1)
+        wf = mirror(self)
+        wf.fftwidth = self.fftwidth
+        wf.init_image()
+
+    def image_update(self, psd):                                    # S:1638-1664
+        wf = mirror(self)
+        fftwidth = np.size(psd)
+        if fftwidth != self.fftwidth:
+            self.fftwidth = fftwidth
+            self.init_image()
+        wf.image_update(psd)                                        # grid bins zeroed in place, row -> ring
+        self.setImage(wf.image_indices(levels(self)).T, autoLevels=False, levels=[0, 256],
+                      opacity=1.0, autoDownsample=True)
+
+    def autolevel(self):                                            # S:1668-1680
+        wf = mirror(self)
+        wf.minlev, wf.maxlev = self.minlev, self.maxlev
+        wf.autolevel()
+        self.minlevel, self.maxlevel = wf.minlevel, wf.maxlevel     # S:1676 (sic)
+        self._zfb_levels = (self.minlev, self.maxlev)               # S:1677 setLevels([minlev, maxlev])
+        return self.minlev, self.maxlev
+
+    def newlevel(self, low, high):                                  # S:1682-1686
+        self._zfb_levels = (low, high)
+        return low, high
+
+    img_array = property(lambda self: mirror(self).img_array)
+    return dict(init_image=init_image, image_update=image_update, autolevel=autolevel,
+                newlevel=newlevel, img_array=img_array)
+
+
+def install(module, *, engine: ZoomPSD | None = None, replace_data: bool = True,
+            replace_waterfall: bool = True) -> dict:
     """Patch ``module`` (a loaded pypanadapter_spectrum / pypanadapter_thread)
     in place; returns the originals."""
     engine_of = (lambda: engine) if engine is not None else default_engine
@@ -128,12 +189,27 @@ def install(module, *, engine: ZoomPSD | None = None, replace_data: bool = True)
             module.Data = Data
     if not saved:
         raise ValueError("module has neither ApplicationDisplay.zoomfft nor PSD: not a pypanadapter module")
+    wfc = getattr(module, "Waterfall", None)
+    if replace_waterfall and wfc is not None:
+        for name, fn in _waterfall_methods(module, engine_of).items():
+            saved["Waterfall." + name] = wfc.__dict__.get(name, _ABSENT)
+            setattr(wfc, name, fn)
+        if psd is not None:
+            # threaded variant: the GUI timer shows whatever row is current (T:2140-2148), not
+            # every row PSD.update computes -- only displayed rows enter the ring
+            engine_of().set_option("ring_append", 0)
+            saved["option.ring_append"] = engine_of()
     return saved
 
 
 def uninstall(module, saved: dict) -> None:
     for key, val in saved.items():
-        if "." in key:
+        if key == "option.ring_append":
+            val.set_option("ring_append", 1)
+        elif val is _ABSENT:
+            cls, attr = key.split(".")
+            delattr(getattr(module, cls), attr)
+        elif "." in key:
             cls, attr = key.split(".")
             setattr(getattr(module, cls), attr, val)
         else:

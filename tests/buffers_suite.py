@@ -274,9 +274,56 @@ def dropin_on_reference_modules(engine):
         z = mod.ApplicationDisplay.zoomfft(types.SimpleNamespace(), x, case["R"])
         ref = np.load(os.path.join(parity.GOLDEN_DIR, "zoomfft.npz"))[case["name"]]
         assert np.abs(z - ref).max() < 2e-5 * np.abs(ref).max()
+        # ---- Waterfall: the reference's own class, its methods on the device ring ----
+        g = np.load(os.path.join(parity.GOLDEN_DIR, "waterfall.npz"))
+        engine.configure(2.4e6, 2048, 8, 2048 * 10, "hamming", crop="thread")      # row_width 256
+        for scroll, tag in ((1, "pos"), (-1, "neg")):
+            mod.AppState.scroll = scroll
+            wf = mod.Waterfall.__new__(mod.Waterfall)
+            wf.fftwidth, wf.minlev, wf.maxlev = 0, -220, -120                      # S:1590-1593
+            shown = {}
+            wf.scale = lambda *a, **k: None
+            wf.setImage = lambda img, **k: shown.update(img=np.array(img), kw=k)
+            ref = None
+            for r in gc.waterfall_rows_noise():
+                psd = r.copy()
+                wf.image_update(psd)
+                assert psd[0] == 0 and psd[128] == 0 and psd[255] == 0             # S:1647-1648
+                ref = zo.waterfall_update(ref, r.copy(), scroll)
+            assert shown["kw"]["levels"] == [0, 256] and shown["kw"]["autoLevels"] is False
+            assert np.array_equal(shown["img"], zo.waterfall_indices(ref, -220, -120).T)
+            assert np.abs(wf.img_array - ref).max() < 1e-4
+            assert wf.autolevel() == (-220, -120)
+            gold = g["auto_noise_" + tag]
+            assert (wf.minlevel, wf.maxlevel) == (gold[0], gold[1])                # the reference's own autolevel
+            assert wf.newlevel(-180.0, -100.0) == (-180.0, -100.0)
+            last = gc.waterfall_rows_noise()[-1].copy()
+            wf.image_update(last)
+            ref = zo.waterfall_update(ref, gc.waterfall_rows_noise()[-1].copy(), scroll)
+            assert np.array_equal(shown["img"], zo.waterfall_indices(ref, -180.0, -100.0).T)
+        mod.AppState.scroll = 1
+        # ---- update(chunk) -> image_update(psd): each row enters the ring once, in order ----
+        case = gc.case_by_name("cfg1_S256")
+        wf = mod.Waterfall.__new__(mod.Waterfall)
+        wf.fftwidth, wf.minlev, wf.maxlev = 0, -220, -120
+        wf.scale = lambda *a, **k: None
+        wf.setImage = lambda img, **k: None
+        fake = types.SimpleNamespace(N_WIN=256, win=rh._Anything(), spectrum_plot=rh._Anything(), waterfall=wf)
+        rows = []
+        for i in range(4):
+            x = synth.make_frame(synth.CFG1, i)
+            rh._set_state(mod, case["fs"], case["N"], case["R"], len(x) // case["N"], case["window"])
+            mod.ApplicationDisplay.update(fake, x)
+            rows.append(engine.read_rows(1)[0].astype(np.float64))
+        img = wf.img_array
+        for j, r in enumerate(reversed(rows)):
+            r = r.copy()
+            r[[0, 128, 255]] = 0
+            assert np.array_equal(img[64 - 2 - j], r), j
     finally:
         dropin.uninstall(mod, saved)
     assert mod.ApplicationDisplay.update is saved["ApplicationDisplay.update"]
+    assert "img_array" not in mod.Waterfall.__dict__
     # ---- thread variant: Data + PSD.update ----
     mod = rh.load("thread")
     saved = dropin.install(mod, engine=engine)
