@@ -57,6 +57,11 @@ class Data:
         self.real = False
         self.data = None
         self.size = self.real_size = self.total_size = 0
+        # event-driven hand-off for a GPU consumer: add() raises the flag when
+        # `ready_size` samples have arrived since the last take, PSD.run(event_driven=True)
+        # waits on it instead of sleeping out a fixed frame time (T:1498-1511)
+        self._ready = threading.Condition()
+        self.ready_size = 0
 
     # -- allocation (T:1413-1431) -------------------------------------------
     def _new(self, wire, real):
@@ -112,8 +117,12 @@ class Data:
             self.size = new_size
             self.real_size = max(self.real_size, self.size)
             self.total_size += length
+            ready = self.ready_size > 0 and self.real_size >= self.ready_size
         finally:
             self.lock.unlock()
+        if ready:
+            with self._ready:
+                self._ready.notify_all()
         if self.delay_time:
             time.sleep(abs(self.delay_time))                   # T:1457
 
@@ -128,6 +137,13 @@ class Data:
         self.real_size = 0
         self.total_size = 0
         self.lock.unlock()
+
+    def wait_ready(self, nsamples: int, timeout: float | None = None) -> bool:
+        """Block until at least ``nsamples`` samples have arrived since the last
+        take (or ``timeout`` seconds pass); True when they are there."""
+        self.ready_size = int(nsamples)
+        with self._ready:
+            return self._ready.wait_for(lambda: self.real_size >= self.ready_size, timeout)
 
     @property
     def target(self):
@@ -163,8 +179,21 @@ class PSD:
         self.flip = flip
         self.ema_alpha = ema_alpha
 
-    def run(self):                                             # T:1498-1511 without NewtRap
+    def run(self, event_driven: bool = False, frame_samples: int | None = None):
+        """T:1498-1511 without NewtRap: one row per .95 FRAME_TIME.  With
+        ``event_driven`` the loop instead wakes when ``frame_samples`` (default
+        ``fft_size * fft_ratio``-ish: one full Welch segment after decimation)
+        new samples are in the ring -- the GPU needs microseconds per row, so
+        the row rate is set by the sample source, not by a sleep."""
         while self.loop:
+            if event_driven:
+                st = self.state
+                need = frame_samples or int(st.fft_size * max(1, st.fft_ratio))
+                need = min(need, self.dataclass.max_size)
+                if not self.dataclass.wait_ready(need, timeout=self.FRAME_TIME):
+                    continue
+                self.update()
+                continue
             target = time.monotonic() + .95 * self.FRAME_TIME
             self.update()
             end = time.monotonic()

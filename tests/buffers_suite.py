@@ -351,6 +351,47 @@ def dropin_on_reference_modules(engine):
         dropin.uninstall(mod, saved)
 
 
+def event_driven_run(engine):
+    """PSD.run(event_driven=True): rows appear when enough samples have arrived,
+    not on a timer: a producer delivering one frame's worth every
+    ~100 ms yields ~one row per delivery, and nothing while it is silent."""
+    import threading
+    import time
+    w = synth.CFG1
+    state = types.SimpleNamespace(fft_size=w.fft_size, fft_ratio=w.fft_ratio, fft_tapering=w.window,
+                                  panadapter=types.SimpleNamespace(SampleRate=w.fs))
+    d = Data(engine=engine).new_complex()
+    psd = PSD(d, state)
+    psd.FRAME_TIME = 0.05
+    frame = synth.make_frame(w, 0)
+    need = 4 * d.chunk_size                                   # 65568 samples per row
+    count = [0]
+    orig = psd.update
+
+    def counted():
+        orig()
+        count[0] += 1
+    psd.update = counted
+    t = threading.Thread(target=psd.run, kwargs=dict(event_driven=True, frame_samples=need))
+    t.start()
+    try:
+        time.sleep(0.15)
+        assert count[0] == 0                                   # silent source: no rows
+        for _ in range(5):
+            for k in range(4):
+                d.add(frame[k * d.chunk_size:(k + 1) * d.chunk_size])
+            time.sleep(0.1)
+        deadline = time.time() + 5
+        while count[0] < 5 and time.time() < deadline:
+            time.sleep(0.01)
+        assert 3 <= count[0] <= 6, count[0]              # (a slow consumer may merge deliveries)
+        assert psd.psd.shape == (2 * int(.5 * w.fft_size / w.fft_ratio),) and np.all(np.isfinite(psd.psd))
+    finally:
+        psd.loop = False
+        t.join(timeout=10)
+    assert not t.is_alive()
+
+
 def buffers_Data():
     from pypanadapter_b200.buffers import Data as D
     return D
