@@ -187,6 +187,38 @@ def waterfall_display(engine):
     assert np.array_equal(got, np.quantile(sel, qs))
 
 
+def waterfall_random_shapes(engine, seeds=range(6)):
+    """Image / indices / percentiles against the oracle for random row widths
+    (incl. widths that are not a multiple of 4: the scalar pixel path), scroll
+    directions, row counts around the wrap and level pairs."""
+    for seed in seeds:
+        rng = np.random.default_rng(1000 + seed)
+        w = int(rng.choice([60, 62, 100, 130, 250, 256, 510, 1000]))
+        h = w // 4
+        scroll = int(rng.choice([1, -1]))
+        nrows = int(rng.choice([1, 4, 6, 7, h - 1, h, h + 1, h + 9]))
+        # any configuration with that row width: no zoom, crop = w
+        engine.configure(1e6, 1024, 1, 4096, "hann", crop=w)
+        assert engine.row_width == w
+        wf = Waterfall(engine, scroll=scroll)
+        ref = None
+        for i in range(nrows):
+            r = (-160.0 + 25.0 * rng.standard_normal(w)).astype(np.float32).astype(np.float64)
+            if i % 3 == 0:
+                r[rng.integers(0, w, 3)] = [np.float32(3.5), -np.inf, 0.0]      # above zero, -inf, zero
+            wf.image_update(r.copy())
+            ref = zo.waterfall_update(ref, r.copy(), scroll)
+        img = wf.img_array
+        assert img.shape == (h, w) and np.array_equal(img, ref), (seed, w, scroll, nrows)
+        lo = float(rng.uniform(-300, -100))
+        levels = (lo, lo + float(rng.uniform(0.5, 200)))
+        assert np.array_equal(wf.image_indices(levels), zo.waterfall_indices(ref, *levels)), (seed, w, levels)
+        qs = np.sort(rng.uniform(0, 1, 3))
+        got, n = engine.ring_quantiles(h, scroll, wf.rows_seen, qs)
+        sel = ref[ref < 0]
+        assert n == sel.size and np.array_equal(got, np.quantile(sel, qs)), (seed, w, qs)
+
+
 def waterfall_from_engine_rows(engine):
     """Rows the engine produced itself are not pushed twice."""
     w = synth.CFG1

@@ -155,6 +155,10 @@ def test_waterfall_display(gpu_engine):
     bs.waterfall_display(gpu_engine)
 
 
+def test_waterfall_random_shapes(gpu_engine):
+    bs.waterfall_random_shapes(gpu_engine, range(40))
+
+
 def test_waterfall_engine_rows(gpu_engine):
     bs.waterfall_from_engine_rows(gpu_engine)
 
