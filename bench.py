@@ -260,6 +260,8 @@ def run_b200(args, w):
         eng.set_option("welch_splits", args.welch_splits)
     if args.strips_async is not None:
         eng.set_option("strips_async", args.strips_async)
+    if args.late_mix is not None:
+        eng.set_option("late_mix", args.late_mix)
     eng.configure(w.fs, w.fft_size, w.fft_ratio, w.frame_len, w.window, dtype=w.dtype, flip=w.flip,
                   f_demod=w.f_demod, crop=w.crop, ema_alpha=w.ema_alpha, mode=args.mode)
     # a real (non-default) stream: the engine launches on it, NCCL enqueues on
@@ -462,6 +464,7 @@ def main():
                     help="decimator: exact zero-phase IIR everywhere, or polyphase-FIR interior + exact edges")
     ap.add_argument("--welch-splits", type=int, default=0, help="tuning: CTAs per frame in the Welch kernel")
     ap.add_argument("--strips-async", type=int, default=None, help="tuning: 0 = edge strips on the main stream")
+    ap.add_argument("--late-mix", type=int, default=None, help="tuning: 0 = always mix before the FIR chain")
     ap.add_argument("--lib", default=None, help="tuning: path of an alternative sm_100a build")
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")

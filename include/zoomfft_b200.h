@@ -132,9 +132,13 @@ int  zfb_set_stream(zfb_engine *e, void *cuda_stream);
  * stay L2-resident).  0 = automatic. */
 int  zfb_set_group(zfb_engine *e, int frames_per_group);
 int  zfb_reset_ema(zfb_engine *e);
-/* tuning knobs (no effect on results): "decim_threads" = 0 (auto) | 128 | 256
+/* tuning knobs: "decim_threads" = 0 (auto) | 128 | 256
  * threads per decimator CTA (8192- / 16384-sample shared-memory region);
  * "welch_splits" = CTAs per frame in the Welch kernel, 0 = auto.
+ * "late_mix" = 1 (default): mode FAST may apply the software LO at the output
+ * of the first FIR chain instead of its input when |f_demod| * fft_ratio / fs
+ * <= 1e-3 (the reference's LO sits at 1 Hz, S:2090; the chain's gain then moves
+ * by < 1e-3 dB); 0: always mix first.
  * "ring_append" = 1 (default): every processed row also enters the waterfall
  * ring; 0: only zfb_ring_push_rows does (display loops that show a subset of
  * the rows, like the threaded variant's GUI timer, T:2140-2148). */

@@ -48,6 +48,9 @@ struct ChannelLo {
     float2 run[32];                 // fir_run_kernel: sqrt(2) * exp(-2 pi i f/fs j)
     float2 dec_small[8];            // exact stage 0 / strips: sqrt(2) g^2 exp(-2 pi i f/fs v)
     float2 dec_big[32];             // exp(-2 pi i f/fs * it*STRIP_NT*VEC)  (strip kernel)
+    int    late;                    // fir_run_kernel: mix at the chain's output (FirRunParams::late)
+    int    pad_;
+    float2 out[16];                 // sqrt(2) * exp(-2 pi i f/fs * (j << NS))
 };
 
 // packed fp32x2 arithmetic (Blackwell FFMA2/FADD2/FMUL2): re and im of a

@@ -59,6 +59,7 @@ struct zfb_engine {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int strips_async = 1;                        // zfb_set_option("strips_async")
     int ring_append = 1;                         // zfb_set_option("ring_append"): processed rows enter the ring
+    int late_mix = 1;                            // zfb_set_option("late_mix"): FIR chain may mix at its output
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
     bool slot_busy[2] = {false, false};
 
@@ -1055,6 +1056,15 @@ int run_group(zfb_engine *e, const void *d_in, int gf, float *d_rows) {
     return ZFB_OK;
 }
 
+// late mix of the first register-blocked chain (zfb_firchain.cuh): allowed when the LO
+// offset r (cycles per input sample, folded to [0,1)) times the zoom ratio is <= 1e-3
+void set_late_mix(zfb_engine *e, FirRunParams &rp, double r, double amp, int ns) {
+    const double off = r < 0.5 ? r : 1.0 - r;
+    const bool no_lo = (e->cfg.flags & ZFB_FLAG_NO_LO) != 0;
+    rp.late = (e->late_mix && !no_lo && off * (double)e->cfg.fft_ratio <= 1.0e-3) ? 1 : 0;
+    for (int j = 0; j < (RUN0 >> ns); ++j) lo_entry(r, (long long)j << ns, amp, rp.lo_out[j]);
+}
+
 // ZFB_MODE_FAST planning: strip geometry, FIR chains (<= 3 stages per launch),
 // tile sizes; decides whether the frame is long enough for the FAST interior
 int plan_fast(zfb_engine *e) {
@@ -1127,6 +1137,7 @@ int plan_fast(zfb_engine *e) {
             if (done == 0) {
                 const double amp = no_lo ? 1.0 : sqrt(2.0);
                 for (int i = 0; i < RUN0; ++i) lo_entry(r, i, amp, rp.lo_run[i]);
+                set_late_mix(e, rp, r, amp, ns);
             }
             memcpy(rp.h0, p.h[0], sizeof rp.h0);
             memcpy(rp.h1, p.h[1], sizeof rp.h1);
@@ -1170,6 +1181,7 @@ void apply_lo(zfb_engine *e, double f_demod) {
             FirRunParams &rp = e->runp[0];
             rp.phase_inc = inc;
             for (int i = 0; i < RUN0; ++i) lo_entry(r, i, amp0, rp.lo_run[i]);
+            set_late_mix(e, rp, r, amp0, e->chain[0].ns);
         }
     }
 }
@@ -1540,6 +1552,11 @@ int zfb_set_option(zfb_engine *e, const char *name, long long value) {
         e->strips_async = value ? 1 : 0;
         return ZFB_OK;
     }
+    if (strcmp(name, "late_mix") == 0) {
+        e->late_mix = value ? 1 : 0;
+        e->configured = false;                   // replanned by the next zfb_configure
+        return ZFB_OK;
+    }
     if (strcmp(name, "ring_append") == 0) {
         e->ring_append = value ? 1 : 0;
         return ZFB_OK;
@@ -1584,6 +1601,17 @@ static int upload_channels(zfb_engine *e, const double *f_demod, int nch) {
         for (int i = 0; i < 32; ++i) lo_entry(r, i, amp0, t.run[i]);
         for (int i = 0; i < 8; ++i) lo_entry(r, i, amp0 * (double)dc.g, t.dec_small[i]);
         for (int it = 0; it < 32; ++it) lo_entry(r, (long long)it * STRIP_NT * vec, 1.0, t.dec_big[it]);
+        // same late-mix decision and table as a single-channel configuration at this f_demod
+        // (batched == per-channel, bit for bit)
+        t.late = 0;
+        t.pad_ = 0;
+        for (int j = 0; j < 16; ++j) t.out[j] = make_float2(0.f, 0.f);
+        if (e->fast_active && e->nchains > 0 && e->chain_run[0]) {
+            FirRunParams tmp{};
+            set_late_mix(e, tmp, r, amp0, e->chain[0].ns);
+            t.late = tmp.late;
+            for (int j = 0; j < RUN0 / 2; ++j) t.out[j] = tmp.lo_out[j];
+        }
     }
     int rc = ensure(e, e->chan_dev, (size_t)nch * sizeof(ChannelLo));
     if (rc) return rc;

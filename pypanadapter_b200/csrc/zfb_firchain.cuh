@@ -336,6 +336,13 @@ struct FirRunParams {
     int         ht;                // halo threads per side
     const ChannelLo *chan;         // channel-batched launches (template CH), else null
     int         chan_frames;       // frames per channel: batch b = ch*chan_frames + frame
+    // Late mix.  Mixing then filtering with h equals filtering with h[n] e^{+i theta n} and
+    // mixing afterwards; when the LO offset is negligible against every filter bandwidth of the
+    // chain (|f_demod| R / fs <= 1e-3: the chain's gain, smooth over 0.7 fs/R, moves by < 1e-3 dB
+    // -- the reference's own LO sits at 1 Hz, S:2090) the modulation of the taps is dropped and
+    // the LO is applied to the chain's OUTPUT, 2^NS times fewer complex products.
+    int         late;
+    float2      lo_out[RUN0 / 2];  // amp * exp(-2 pi i f/fs * (j << NS)), j = 0 .. (RUN0 >> NS) - 1
 };
 
 // neighbour exchange of one level: a thread publishes its run (or only the M
@@ -518,7 +525,7 @@ __global__ void __launch_bounds__(FIR_NT, ZFB_FIR_MINB) fir_run_kernel(const Fir
                 }
             }
         }
-        if (KIND != KIND_C64_MID) {
+        if (KIND != KIND_C64_MID && !(CH ? p.chan[ch].late : p.late)) {
             const ChannelLo *cl = CH ? p.chan + ch : nullptr;
             const float2 b0 = lo_phasor((long long)pos0, CH ? cl->phase_inc : p.phase_inc);
 #pragma unroll
@@ -567,6 +574,14 @@ __global__ void __launch_bounds__(FIR_NT, ZFB_FIR_MINB) fir_run_kernel(const Fir
         (void)smc;
 #pragma unroll
         for (int j = 0; j < RO; ++j) out[j] = yf[j];
+    }
+
+    if (KIND != KIND_C64_MID && (CH ? p.chan[ch].late : p.late)) {
+        // output j of this thread sits at input position (pos0 >> NS << NS) + (j << NS)
+        const ChannelLo *cl = CH ? p.chan + ch : nullptr;
+        const float2 b0 = lo_phasor((long long)(pos0 >> NS) << NS, CH ? cl->phase_inc : p.phase_inc);
+#pragma unroll
+        for (int j = 0; j < RO; ++j) out[j] = cmul(out[j], cmul(b0, CH ? cl->out[j] : p.lo_out[j]));
     }
 
     if (t >= SH::HT && t < FIR_NT - SH::HT) {

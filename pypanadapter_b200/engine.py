@@ -211,8 +211,9 @@ class ZoomPSD:
         self._check(self._lib.zfb_set_stream(self._h, C.c_void_p(cuda_stream_ptr or 0)), "zfb_set_stream")
 
     def set_option(self, name: str, value: int):
-        """Tuning knobs that never change results (zfb_set_option)."""
+        """Tuning knobs (zfb_set_option); the next configure() replans."""
         self._check(self._lib.zfb_set_option(self._h, name.encode(), int(value)), "zfb_set_option")
+        self._key = None
 
     def reset_ema(self):
         self._check(self._lib.zfb_reset_ema(self._h), "zfb_reset_ema")
