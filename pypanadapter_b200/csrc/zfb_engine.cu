@@ -738,11 +738,16 @@ cudaError_t run_decimation_fast(zfb_engine *e, const void *d_in, int gf, int *ou
     // strips go to a side stream and fill the SMs beside the FIR interior.
     const bool async_strips = e->strips_async && s0 == 0;
     cudaError_t err = cudaSuccess;
+    // strips_async 1: strips are submitted before the FIR chain (their CTAs are dispatched
+    // first), 2: after it (they fill its tail and run beside the exact last stage)
+    const bool strips_first = e->strips_async != 2;
     if (async_strips) {
         if ((err = cudaEventRecord(e->ev_fork, st)) != cudaSuccess) return err;      // input ready, buffers free
         if ((err = cudaStreamWaitEvent(e->aux_stream, e->ev_fork, 0)) != cudaSuccess) return err;
-        launch_fused_strips(e, d_in, gf, final_out, e->aux_stream);
-        if ((err = cudaEventRecord(e->ev_join, e->aux_stream)) != cudaSuccess) return err;
+        if (strips_first) {
+            launch_fused_strips(e, d_in, gf, final_out, e->aux_stream);
+            if ((err = cudaEventRecord(e->ev_join, e->aux_stream)) != cudaSuccess) return err;
+        }
     }
     const void *src = d_in;
     long long src_stride = c.frame_len;
@@ -777,6 +782,10 @@ cudaError_t run_decimation_fast(zfb_engine *e, const void *d_in, int gf, int *ou
         src_stride = p.out_stride;
         kind = KIND_C64_MID;
         b ^= 1;
+    }
+    if (async_strips && !strips_first) {
+        launch_fused_strips(e, d_in, gf, final_out, e->aux_stream);
+        if ((err = cudaEventRecord(e->ev_join, e->aux_stream)) != cudaSuccess) return err;
     }
     const int v = (e->decim_threads == NTHR_BIG) ? 0 : 1;
     {   // the last decimate call, exact, over the whole (FIR-filtered) chunk; it leaves the
@@ -1549,7 +1558,7 @@ int zfb_set_option(zfb_engine *e, const char *name, long long value) {
         return ZFB_OK;
     }
     if (strcmp(name, "strips_async") == 0) {
-        e->strips_async = value ? 1 : 0;
+        e->strips_async = (value == 2) ? 2 : (value ? 1 : 0);
         return ZFB_OK;
     }
     if (strcmp(name, "late_mix") == 0) {
