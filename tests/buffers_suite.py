@@ -379,8 +379,29 @@ def dropin_on_reference_modules(engine):
         assert d.target == 100000
         d.target = 10             # below fft_size: ignored (T:1476)
         assert d.target == 100000
+        # GUI timer side (T:2140-2148): only the rows it displays enter the ring
+        before = engine.rows_written
+        for i in range(0, len(x), d.chunk_size):
+            d.add(x[i:i + d.chunk_size])
+            d.delay_time = 0.
+        mod.PSD.update(psd)                                   # a second row nobody displays
+        assert engine.rows_written == before
+        wf = mod.Waterfall.__new__(mod.Waterfall)
+        wf.fftwidth, wf.minlev, wf.maxlev = 0, -220, -120
+        wf.scale = lambda *a, **k: None
+        shown = {}
+        wf.setImage = lambda img, **k: shown.update(img=np.array(img))
+        row = np.array(psd.psd, copy=True)
+        wf.image_update(row)
+        assert engine.rows_written == 1 and shown["img"].shape == (256, 64)
+        ref = zo.waterfall_update(None, np.array(psd.psd, dtype=np.float32).astype(np.float64), 1)
+        assert np.array_equal(shown["img"], zo.waterfall_indices(ref, -220, -120).T)
     finally:
         dropin.uninstall(mod, saved)
+    engine.configure(2.4e6, 2048, 8, 2048 * 10, "hamming", crop="thread")
+    n0 = engine.rows_written
+    engine.process(synth.make_frame(synth.CFG1, 0, 2048 * 10))
+    assert engine.rows_written == n0 + 1                      # uninstall restored ring_append
 
 
 def event_driven_run(engine):
