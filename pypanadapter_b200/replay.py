@@ -72,3 +72,103 @@ class ReplayPan:
 
     def Close(self):
         self.driver = None
+
+
+class RtlTcpPan:
+    """rtl_tcp client behind the reference's ``PanStreamClass`` surface
+    (pypanadapter_spectrum.py:271-297: ``Mode == 'Stream'``, ``Stream(cb,
+    chunk_size)``, ``stream_open/stream_close``, ``SetFrequency``, ``Close``).
+
+    rtl_tcp's wire protocol (osmocom rtl-sdr, ``rtl_tcp.c``): the server greets
+    with 12 bytes -- magic ``RTL0``, tuner type and gain count as big-endian
+    uint32 -- and then sends the dongle's interleaved uint8 I,Q without any
+    framing; the client sends 5-byte commands (1 byte id, big-endian uint32
+    argument: 0x01 centre frequency, 0x02 sample rate, 0x09 direct sampling).
+    The callback receives RAW BYTES (``chunk_size`` samples = 2*chunk_size
+    uint8), ready for ``buffers.Data.new_u8().add`` -- conversion (S:543) and
+    flip happen on the device.  ``complex_callback=True`` instead hands over
+    what ``RTLSDRstream.read_callback`` emits (S:459-460): flipped complex128.
+    """
+    Mode = "Stream"
+    _name = "rtl_tcp"
+
+    def __init__(self, host="127.0.0.1", port=1234, sample_rate=2.56e6, complex_callback=False, timeout=5.0):
+        import socket
+        self.SampleRate = float(sample_rate)          # S:407
+        self.complex_callback = complex_callback
+        self.stream = None
+        self.chunk_size = 0
+        self.update_signal = None
+        self._sock = socket.create_connection((host, port), timeout=timeout)
+        hdr = self._recv_exact(12)
+        if hdr[:4] != b"RTL0":
+            self._sock.close()
+            raise ConnectionError("not an rtl_tcp server (greeting %r)" % hdr[:4])
+        self.tuner_type = int.from_bytes(hdr[4:8], "big")
+        self.gain_count = int.from_bytes(hdr[8:12], "big")
+        self.driver = self
+        self._name = "rtl_tcp @%s:%d" % (host, port)
+        self._command(0x02, int(self.SampleRate))
+
+    @property
+    def name(self):
+        return self._name
+
+    def _recv_exact(self, n):
+        buf = bytearray()
+        while len(buf) < n:
+            part = self._sock.recv(n - len(buf))
+            if not part:
+                raise EOFError("rtl_tcp server closed the connection")
+            buf += part
+        return bytes(buf)
+
+    def _command(self, cmd, arg):
+        self._sock.sendall(bytes([cmd]) + int(arg).to_bytes(4, "big"))
+
+    # -- PanStreamClass surface ------------------------------------------------
+    def SetFrequency(self, IF):                       # S:462-476
+        self._command(0x09, 2 if IF < 30.e6 else 0)   # direct sampling below 30 MHz (S:531-537)
+        self._command(0x01, int(IF))
+        self.center_freq = IF
+
+    def Stream(self, update_signal, chunk_size):      # S:290-297
+        self.update_signal = update_signal
+        self.chunk_size = int(chunk_size)
+        if self.stream:
+            self.stream_close()
+        self.stream = self.stream_open()
+
+    def stream_open(self):
+        import threading
+        self._run = True
+        emit = getattr(self.update_signal, "emit", self.update_signal)
+
+        def pump():
+            try:
+                while self._run:
+                    raw = np.frombuffer(self._recv_exact(2 * self.chunk_size), dtype=np.uint8)
+                    if self.complex_callback:
+                        iq = raw.astype(np.float64).view(np.complex128) / 127.5 - (1 + 1j)
+                        emit(np.flip(iq))
+                    else:
+                        emit(raw)
+            except (EOFError, OSError):
+                pass
+        t = threading.Thread(target=pump, daemon=True)
+        t.start()
+        return t
+
+    def stream_close(self):
+        self._run = False
+        t, self.stream = self.stream, None
+        if t is not None and t.is_alive():
+            t.join(timeout=2.0)
+
+    def Close(self):
+        self.stream_close()
+        try:
+            self._sock.close()
+        except OSError:
+            pass
+        self.driver = None

@@ -445,6 +445,73 @@ def event_driven_run(engine):
     assert not t.is_alive()
 
 
+def rtl_tcp_source(engine):
+    """RtlTcpPan against a fake rtl_tcp server on localhost: greeting parsed,
+    commands framed as rtl_tcp expects, raw bytes streamed into Data.new_u8()
+    and PSD.update's row equals the oracle's for the same bytes (cfg2 shape)."""
+    import socket
+    import threading
+    import time
+    from pypanadapter_b200.replay import RtlTcpPan
+    w = synth.CFG2
+    raw = synth.make_frame(w, 0)                               # uint8 IQ, 2*frame_len bytes
+    assert raw.dtype == np.uint8
+    srv = socket.socket()
+    srv.bind(("127.0.0.1", 0))
+    srv.listen(1)
+    port = srv.getsockname()[1]
+    got_cmds = []
+
+    def serve():
+        conn, _ = srv.accept()
+        conn.sendall(b"RTL0" + (5).to_bytes(4, "big") + (29).to_bytes(4, "big"))
+        conn.settimeout(0.5)
+        try:
+            for _ in range(3):                                   # sample rate, direct sampling, frequency
+                got_cmds.append(conn.recv(5, socket.MSG_WAITALL))
+        except OSError:
+            pass
+        try:
+            conn.sendall(raw.tobytes())
+            time.sleep(0.5)
+        finally:
+            conn.close()
+    th = threading.Thread(target=serve, daemon=True)
+    th.start()
+    pan = RtlTcpPan("127.0.0.1", port, sample_rate=w.fs)
+    assert (pan.tuner_type, pan.gain_count, pan.Mode) == (5, 29, "Stream")
+    pan.SetFrequency(8.8315e6)                                   # TS-180S IF (S:106): direct sampling
+    d = Data(engine=engine).new_u8()
+    chunk = 16384
+    nchunks = 15                                                 # 245760 samples: below Data's fold-back (T:1440)
+    seen = []
+    done = threading.Event()
+
+    def on_chunk(b):
+        if len(seen) >= nchunks:                                 # the pump keeps reading until Close()
+            return
+        d.add(b)
+        seen.append(len(b))
+        if len(seen) == nchunks:
+            done.set()
+    pan.Stream(on_chunk, chunk)
+    assert done.wait(10), "stream stalled after %d chunks" % len(seen)
+    pan.Close()
+    th.join(timeout=5)
+    srv.close()
+    assert got_cmds[0] == bytes([0x02]) + int(w.fs).to_bytes(4, "big")
+    assert got_cmds[1] == bytes([0x09]) + (2).to_bytes(4, "big")
+    assert got_cmds[2] == bytes([0x01]) + int(8.8315e6).to_bytes(4, "big")
+    assert all(n == 2 * chunk for n in seen[:nchunks])
+    state = types.SimpleNamespace(fft_size=w.fft_size, fft_ratio=w.fft_ratio, fft_tapering=w.window,
+                                  panadapter=types.SimpleNamespace(SampleRate=w.fs))
+    psd = PSD(d, state, flip=True)
+    psd.update()
+    n = nchunks * chunk
+    want = zo.zoom_psd(raw[:2 * n], w.fs, w.fft_size, w.fft_ratio, w.window, flip=True)
+    parity.assert_row_parity(psd.psd, want, parity.floor_db20(w.fs, w.window, w.fft_size, True), "rtl_tcp row")
+
+
 def buffers_Data():
     from pypanadapter_b200.buffers import Data as D
     return D

@@ -63,6 +63,10 @@ def test_psd_update_u8(emu_engine):
     bs.psd_update_u8(emu_engine)
 
 
+def test_rtl_tcp_source(emu_engine):
+    bs.rtl_tcp_source(emu_engine)
+
+
 def test_event_driven_run(emu_engine):
     bs.event_driven_run(emu_engine)
 

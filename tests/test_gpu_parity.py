@@ -139,6 +139,10 @@ def test_psd_update_u8(gpu_engine):
     bs.psd_update_u8(gpu_engine)
 
 
+def test_rtl_tcp_source(gpu_engine):
+    bs.rtl_tcp_source(gpu_engine)
+
+
 def test_event_driven_run(gpu_engine):
     bs.event_driven_run(gpu_engine)
 
