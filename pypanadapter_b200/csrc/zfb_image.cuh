@@ -1,17 +1,18 @@
-// Waterfall image on the device: the reference keeps a float64
+// Waterfall image on the device.  The reference keeps a float64
 // img_array of (w//4, w) on the host, rolls the WHOLE image by one row per
 // update (np.roll, pypanadapter_spectrum.py:1651-1652), redraws grid and tick
 // marks (S:1647-1648, S:1655-1662) and hands it to pyqtgraph, which maps
 // [minlev, maxlev] onto a 256-entry colour table (S:1592-1594, S:1612-1623;
 // pyqtgraph ImageItem: index = clip(trunc((v - min) * 256 / (max - min)), 0,
-// 255)).  Here the rows stay in the device ring; a pixel of the image the
-// reference would hold after the same sequence of updates is a pure function
-// of (y, x), the ring and three counters (wf_pixel), so the image -- as
-// float32 img_array, as 8-bit colour indices or as RGBA through the table --
-// is produced by one streaming pass only when it is displayed, and only the
-// 8-bit image crosses PCIe.  Waterfall.autolevel's np.percentile(img_array[
-// img_array < 0], [2, 98]) (S:1676) is an exact order-statistic selection by
-// three 11/11/9-bit radix histograms over the same pixel function.
+// 255), reproduced bit for bit in fp32 by wf_level).
+// Here the rows stay in the device ring.  A pixel of the image the reference
+// would hold after the same sequence of updates is a pure function of (y, x),
+// the ring and three counters (wf_row, wf_tick_row, wf_fix), so the image --
+// as float32 img_array, as 8-bit colour indices or as RGBA through the table
+// -- is produced by one streaming pass only when it is displayed, and only
+// the 8-bit image crosses PCIe.  Waterfall.autolevel's np.percentile(
+// img_array[img_array < 0], [2, 98]) (S:1676) is an exact order-statistic
+// selection by three 11/11/9-bit radix histograms over the same pixel function.
 #pragma once
 #include "zfb_common.cuh"
 
