@@ -219,6 +219,31 @@ def waterfall_random_shapes(engine, seeds=range(6)):
         assert n == sel.size and np.array_equal(got, np.quantile(sel, qs)), (seed, w, qs)
 
 
+def level_mapping_edges(engine):
+    """Colour index at, just below and just above every one of the 255 index
+    steps, for several level pairs: the device's fp32 guess + threshold
+    compares must land on the double-precision formula's index everywhere."""
+    w = 768
+    engine.configure(1e6, 1024, 1, 4096, "hann", crop=w)
+    pairs = [(-220.0, -120.0), (-180.5, -99.25), (-300.0, 0.0), (-100.0, 100.0), (-153.7, -151.2),
+             (-1e4, 1e4), (-130.0, -129.0), (3.0, 40.0)]
+    for lo, hi in pairs:
+        scale = 256.0 / (hi - lo)
+        # float32 values around the exact step positions lo + k / scale
+        steps = (lo + np.arange(1, 256) / scale).astype(np.float32)
+        vals = np.concatenate([steps, np.nextafter(steps, np.float32(-np.inf)), np.nextafter(steps, np.float32(np.inf))])
+        assert vals.size == 765
+        row = np.concatenate([vals, np.float32([lo, hi, -np.inf])]).astype(np.float32)
+        wf = Waterfall(engine)
+        wf.image_update(row.astype(np.float64))
+        img = wf.img_array
+        idx = wf.image_indices((lo, hi))
+        assert np.array_equal(idx, zo.waterfall_indices(img, lo, hi)), (lo, hi)
+        # and the steps really are exercised: the three rows of values straddle index changes
+        got = idx[idx.shape[0] - 2, 1:255]
+        assert len(np.unique(got)) > 200
+
+
 def waterfall_from_engine_rows(engine):
     """Rows the engine produced itself are not pushed twice."""
     w = synth.CFG1

@@ -87,6 +87,10 @@ def test_waterfall_random_shapes(emu_engine):
     bs.waterfall_random_shapes(emu_engine, range(4))
 
 
+def test_level_mapping_edges(emu_engine):
+    bs.level_mapping_edges(emu_engine)
+
+
 def test_waterfall_engine_rows(emu_engine):
     bs.waterfall_from_engine_rows(emu_engine)
 

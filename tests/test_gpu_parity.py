@@ -163,6 +163,10 @@ def test_waterfall_random_shapes(gpu_engine):
     bs.waterfall_random_shapes(gpu_engine, range(40))
 
 
+def test_level_mapping_edges(gpu_engine):
+    bs.level_mapping_edges(gpu_engine)
+
+
 def test_waterfall_engine_rows(gpu_engine):
     bs.waterfall_from_engine_rows(gpu_engine)
 
