@@ -34,6 +34,42 @@ def data_foldback(engine):
     assert np.array_equal(tail, g["tail"].astype(np.complex64))
 
 
+def data_random_sequences(engine, seeds=range(8)):
+    """Random chunk-length sequences (incl. lengths that force the fold-back,
+    takes in between, and raw uint8 storage): counters and contents of
+    buffers.Data equal the oracle's restatement of T:1433-1468 at every step."""
+    for seed in seeds:
+        rng = np.random.default_rng(500 + seed)
+        cs = int(rng.choice([512, 1000, 4096]))
+        u8 = bool(seed % 2)
+        d = Data(cs, engine=engine)
+        d = d.new_u8() if u8 else d.new_complex()
+        o = zo.DataOracle(cs).new_complex()
+        assert d.max_size == o.max_size
+        for step in range(60):
+            if rng.random() < 0.15:
+                d.get_data_start()
+                got = np.array(d.data[:(2 if u8 else 1) * d.real_size], copy=True)
+                d.get_data_end()
+                want = o.take()
+                if u8:
+                    assert np.array_equal(got.astype(np.float64).view(np.complex128), want)
+                else:
+                    assert np.array_equal(got, want.astype(np.complex64))
+                assert (d.size, d.real_size, d.total_size) == (0, 0, 0)
+                continue
+            n = int(rng.integers(1, 3 * cs))
+            if u8:
+                b = rng.integers(0, 256, 2 * n, dtype=np.uint8)
+                d.add(b)
+                o.add(b.astype(np.float64).view(np.complex128))       # the bytes as (I, Q) pairs
+            else:
+                c = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
+                d.add(c)
+                o.add(c)
+            assert (d.size, d.real_size, d.total_size) == (o.size, o.real_size, o.total_size), (seed, step)
+
+
 def psd_update_matches_reference(engine):
     """PSD.update on Data fed chunk by chunk == the golden row the reference's
     own PSD.update produced for the same samples (cfg1_T)."""

@@ -55,6 +55,10 @@ def test_data_foldback(emu_engine):
     bs.data_foldback(emu_engine)
 
 
+def test_data_random_sequences(emu_engine):
+    bs.data_random_sequences(emu_engine, range(8))
+
+
 def test_psd_update(emu_engine):
     bs.psd_update_matches_reference(emu_engine)
 

@@ -131,6 +131,10 @@ def test_data_foldback(gpu_engine):
     bs.data_foldback(gpu_engine)
 
 
+def test_data_random_sequences(gpu_engine):
+    bs.data_random_sequences(gpu_engine, range(8))
+
+
 def test_psd_update(gpu_engine):
     bs.psd_update_matches_reference(gpu_engine)
 
