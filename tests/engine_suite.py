@@ -123,6 +123,26 @@ def error_paths(engine):
         engine.process(np.zeros(512, dtype=np.uint8))              # wrong wire dtype
     row = engine.process(np.zeros(256, dtype=np.complex64))[0]
     assert np.all(np.isneginf(row))                                # zero power -> -inf like numpy
+    # display path arguments
+    with pytest.raises(ZoomFFTError):
+        engine.ring_image(16, 1, 1, "u8", levels=(-120.0, -120.0))   # empty level range
+    with pytest.raises(ValueError):
+        engine.ring_image(16, 1, 1, "u8")                            # levels missing
+    with pytest.raises(ValueError):
+        engine.ring_image(16, 1, 1, "rgba", levels=(-220, -120), lut=np.zeros((255, 4), np.uint8))
+    with pytest.raises(ZoomFFTError):
+        engine.ring_image(0, 1, 1, "f32")                            # height
+    with pytest.raises(ZoomFFTError):
+        engine.ring_quantiles(16, 1, 1, [1.5])                       # quantile outside [0, 1]
+    with pytest.raises(ZoomFFTError):
+        engine.set_option("no_such_knob", 1)
+    # one-sided rows are the real-input, no-zoom case only
+    with pytest.raises(ValueError):
+        engine.configure(48e3, 64, 2, 256, "hamming", onesided=True)
+    with pytest.raises(ZoomFFTError):
+        engine.configure(48e3, 16384, 1, 65536, "hamming", onesided=True)   # beyond the one-CTA FFT
+    engine.configure(48e3, 64, 1, 256, "hamming", crop=32, onesided=True)
+    assert engine.row_width == 17 and engine.process(np.ones(256, np.float32)).shape == (1, 17)
 
 
 def f_demod_extension(engine):
