@@ -2078,8 +2078,10 @@ int zfb_ring_quantiles(zfb_engine *e, int height, int scroll, int64_t rows_seen,
         s.ntargets = nt;
         CK(e, cudaMemsetAsync(s.hist, 0, hbytes, st));
         const int pr = prof_begin(e, 20);
-        ZFB_LAUNCH(wf_select_kernel, dim3((unsigned)ctas), dim3(256),
-                   (size_t)(pass == 0 ? 1 : nt) * SEL_BINS * sizeof(unsigned int), st, s);
+        const size_t hb = (size_t)(pass == 0 ? 1 : nt) * SEL_BINS * sizeof(unsigned int);
+        if (pass == 0) ZFB_LAUNCH(wf_select_kernel<0>, dim3((unsigned)ctas), dim3(256), hb, st, s);
+        else if (pass == 1) ZFB_LAUNCH(wf_select_kernel<1>, dim3((unsigned)ctas), dim3(256), hb, st, s);
+        else ZFB_LAUNCH(wf_select_kernel<2>, dim3((unsigned)ctas), dim3(256), hb, st, s);
         prof_end(e, pr);
         CK(e, cudaGetLastError());
         e->counters[2] += 1;

@@ -209,13 +209,14 @@ __host__ inline float wf_unkey(unsigned int k) {
 // every warp would serialise 32 same-address atomics)
 constexpr unsigned int SEL_NONE = 0xFFFFFFFFu;
 
+template <int PASS>
 __device__ __forceinline__ unsigned int wf_slot(const SelectParams &s, float v) {
     if (!(v < 0.f)) return SEL_NONE;
     const unsigned int k = wf_key(v);
     // keys of negative floats have bit 31 clear: digits are bits 30..20, 19..9, 8..0
-    if (s.pass == 0) return k >> 20;
-    const unsigned int pre = (s.pass == 1) ? (k >> 20) : (k >> 9);
-    const unsigned int sub = (s.pass == 1) ? ((k >> 9) & 0x7FFu) : (k & 0x1FFu);
+    if (PASS == 0) return k >> 20;
+    const unsigned int pre = (PASS == 1) ? (k >> 20) : (k >> 9);
+    const unsigned int sub = (PASS == 1) ? ((k >> 9) & 0x7FFu) : (k & 0x1FFu);
     unsigned int at = SEL_NONE;
 #pragma unroll
     for (int t = 0; t < SEL_TARGETS; ++t)
@@ -228,11 +229,12 @@ __device__ __forceinline__ void wf_count(unsigned int *h, unsigned int at, int l
     if (at != SEL_NONE && lane == __ffs((int)peers) - 1) atomicAdd(&h[at], (unsigned int)__popc(peers));
 }
 
+template <int PASS>
 __global__ void __launch_bounds__(256) wf_select_kernel(const SelectParams s) {
     ZFB_DYN_SMEM(smem_raw);                                  // nh * SEL_BINS counters
     unsigned int *h = reinterpret_cast<unsigned int *>(smem_raw);
     const ImageParams &p = s.img;
-    const int nh = (s.pass == 0) ? 1 : s.ntargets;
+    const int nh = (PASS == 0) ? 1 : s.ntargets;
     const int lane = threadIdx.x & 31;
     for (int i = threadIdx.x; i < nh * SEL_BINS; i += blockDim.x) h[i] = 0u;
     __syncthreads();
@@ -251,14 +253,14 @@ __global__ void __launch_bounds__(256) wf_select_kernel(const SelectParams s) {
                 float q[4] = {v.x, v.y, v.z, v.w};
                 wf_fix4(p, row != nullptr, tick_row, x0, q);
 #pragma unroll
-                for (int e = 0; e < 4; ++e) wf_count(h, in ? wf_slot(s, q[e]) : SEL_NONE, lane);
+                for (int e = 0; e < 4; ++e) wf_count(h, in ? wf_slot<PASS>(s, q[e]) : SEL_NONE, lane);
             }
         } else {
             for (int xb = 0; xb < p.W; xb += 256) {
                 const int x = xb + (int)threadIdx.x;
                 const bool in = x < p.W;
                 const float v = wf_fix(p, row != nullptr, tick_row, x, (row && in) ? __ldg(row + x) : 0.f);
-                wf_count(h, in ? wf_slot(s, v) : SEL_NONE, lane);
+                wf_count(h, in ? wf_slot<PASS>(s, v) : SEL_NONE, lane);
             }
         }
     }
