@@ -635,12 +635,17 @@ __device__ __forceinline__ void stage_wait_all() {
 #endif
 }
 
+// `counter` (zeroed before the launch) hands out tiles gridDim.x, gridDim.x + 1, ... on demand:
+// the edge strips run beside this kernel on a side stream and hold SM slots of their own for
+// a while, so CTAs of this grid start at different times and a static split leaves a tail.
+// counter == nullptr: static round robin i += gridDim.x.
 template <int NS, int M0, int M1, int M2, int MC>
 __global__ void __launch_bounds__(FIR_NT, ZFB_FIR_MINB)
-fir_run_persist_kernel(const FirRunParams p, int tiles_x, int ntiles) {
+fir_run_persist_kernel(const FirRunParams p, int tiles_x, int ntiles, unsigned int *counter) {
     using SH = FirRunShape<NS, M0, M1, M2, MC>;
     ZFB_DYN_SMEM(smem_raw);
     uint4 *stage = reinterpret_cast<uint4 *>(smem_raw + SH::SMEM);        // [2][FIR_STAGE_VECS][FIR_NT]
+    __shared__ int s_next;
     const int t = threadIdx.x;
 
     // stage this thread's run of tile i (same fast-path test as fir_run_tile)
@@ -659,16 +664,29 @@ fir_run_persist_kernel(const FirRunParams p, int tiles_x, int ntiles) {
         }
         stage_commit();
     };
+    const int G = (int)gridDim.x;
+    auto claim = [&]() -> int { return G + (int)atomicAdd(counter, 1u); };   // thread 0 only
 
-    int slot = 0;
-    prefetch((int)blockIdx.x, 0);
-    for (int i = blockIdx.x; i < ntiles; i += gridDim.x, slot ^= 1) {
-        stage_wait_all();                              // tile i is in `slot` (own copies only)
-        prefetch(i + (int)gridDim.x, slot ^ 1);        // in flight during the whole of tile i
-        const int frame = i / tiles_x, bx = i - frame * tiles_x;
+    int cur = (int)blockIdx.x, nxt = cur + G;
+    prefetch(cur, 0);
+    if (counter) {
+        if (t == 0) s_next = claim();
+        __syncthreads();
+        nxt = s_next;
+    }
+    for (int slot = 0; cur < ntiles; slot ^= 1) {
+        stage_wait_all();                              // tile cur is in `slot` (own copies only)
+        prefetch(nxt, slot ^ 1);                       // in flight during the whole of tile cur
+        int after = nxt + G;
+        if (counter && t == 0) after = claim();        // its latency hides behind the tile
+        const int frame = cur / tiles_x, bx = cur - frame * tiles_x;
         fir_run_tile<KIND_U8_RAW, NS, M0, M1, M2, MC, false, true>(
             p, smem_raw, frame, bx, stage + (size_t)slot * FIR_STAGE_VECS * FIR_NT);
+        // (every tile has a barrier of its own between the readers of s_next and this write)
+        if (counter && t == 0) s_next = after;
         __syncthreads();                               // the exchange buffers are reused by the next tile
+        cur = nxt;
+        nxt = counter ? s_next : after;
     }
 }
 

@@ -295,17 +295,19 @@ def fast_persistent_fir(engine):
             got = {}
             # (CTAs per SM, grid size outright): 2 per SM as it would run; 5 or 3 CTAs in all, so
             # that every CTA walks over many tiles and the last round is ragged
-            variants = ((0, 0), (2, 0), (1, 5), (1, 3))
-            for persist, ctas in variants:
+            # the last one with tiles dealt round robin instead of claimed from the counter
+            variants = ((0, 0, 0), (2, 0, 0), (1, 5, 0), (1, 3, 1))
+            for persist, ctas, static in variants:
                 engine.set_option("fir_persist", persist)
                 engine.set_option("fir_persist_ctas", ctas)
+                engine.set_option("fir_persist_static", static)
                 engine.configure(3.2e6, N, R, n, "hamming", dtype="u8", flip=flip, crop="thread", mode="fast")
                 assert engine.fast_active
                 rows = engine.process(wire)
-                got[persist, ctas] = (rows.copy(), engine.read_decimated().copy())
+                got[persist, ctas, static] = (rows.copy(), engine.read_decimated().copy())
             for v in variants[1:]:
-                assert np.array_equal(got[v][0], got[0, 0][0]), (n, N, R, flip, v)
-                assert np.array_equal(got[v][1], got[0, 0][1]), (n, N, R, flip, v)
+                assert np.array_equal(got[v][0], got[0, 0, 0][0]), (n, N, R, flip, v)
+                assert np.array_equal(got[v][1], got[0, 0, 0][1]), (n, N, R, flip, v)
         # golden rows through the persistent kernel, and complex64 input is untouched by the option
         engine.set_option("fir_persist", 2)
         engine.set_option("fir_persist_ctas", 7)
@@ -314,6 +316,7 @@ def fast_persistent_fir(engine):
     finally:
         engine.set_option("fir_persist", 0)
         engine.set_option("fir_persist_ctas", 0)
+        engine.set_option("fir_persist_static", 0)
         engine._key = None
     with pytest.raises(ZoomFFTError):
         engine.set_option("fir_persist", 9)

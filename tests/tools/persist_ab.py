@@ -24,9 +24,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--frames", type=int, default=512)
     ap.add_argument("--rounds", type=int, default=2)
-    ap.add_argument("--variants", default="0,2,1,3")
+    ap.add_argument("--variants", default="0,2,2s,1",
+                    help="CTAs per SM of the persistent kernel (0 = off); suffix s = static round robin")
     ap.add_argument("--skip-check", action="store_true")
-    ap.add_argument("--strips-async", type=int, default=None, help="0: edge strips on the main stream")
+    ap.add_argument("--strips-async", default="1", help="comma list; 0: edge strips on the main stream")
     args = ap.parse_args()
 
     import torch
@@ -46,14 +47,15 @@ def main():
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     eng.set_stream(stream.cuda_stream)
-    variants = [int(v) for v in args.variants.split(",")]
-    if args.strips_async is not None:
-        eng.set_option("strips_async", args.strips_async)
+    variants = [(int(v.rstrip("s")), v.endswith("s"), int(sa))
+                for sa in args.strips_async.split(",") for v in args.variants.split(",")]
     rows = {}
     best = {v: None for v in variants}
     for rnd in range(args.rounds):
         for v in variants:
-            eng.set_option("fir_persist", v)
+            eng.set_option("strips_async", v[2])
+            eng.set_option("fir_persist", v[0])
+            eng.set_option("fir_persist_static", int(v[1]))
             eng.configure(w.fs, w.fft_size, w.fft_ratio, w.frame_len, w.window, dtype=w.dtype, flip=w.flip,
                           f_demod=w.f_demod, crop=w.crop, ema_alpha=w.ema_alpha, mode="fast")
             d_rows = torch.empty((F, eng.row_width), dtype=torch.float32, device="cuda")
@@ -77,7 +79,7 @@ def main():
             eng.process_device(d_in.data_ptr(), F, d_rows.data_ptr())
             torch.cuda.synchronize()
             rows[v] = d_rows.cpu().numpy()
-            rec = {"fir_persist": v, "strips_async": args.strips_async, "round": rnd, "ms_per_step": ms,
+            rec = {"fir_persist": v[0], "static": v[1], "strips_async": v[2], "round": rnd, "ms_per_step": ms,
                    "gsamples_per_s": F * w.frame_len / ms / 1e6,
                    "fir_chain_ms_per_launch": fir_ms / max(fir_n, 1),
                    "rows_equal_to_variant0": bool(np.array_equal(rows[v], rows[variants[0]]))}
