@@ -72,10 +72,6 @@ struct zfb_engine {
     int decim_threads = 0;             // 0 = automatic per launch
     int welch_splits = 0;              // 0 = automatic
     int fir_generic = 0;               // 1: never use the register-blocked FIR kernel (tests)
-    int fir_persist = 0;               // > 0: persistent FIR chain for uint8 IQ, that many CTAs per SM
-    int fir_persist_ctas = 0;          // > 0: its grid size outright (tests: few CTAs, many tiles each)
-    int fir_persist_static = 0;        // 1: tiles dealt round robin instead of claimed from a counter
-    DevBuf tile_counter;
     int nperseg = 0, hop = 0, nseg = 0, W = 0, log2N = 0;
     int Wp = 0;                        // width of a pow row: W, or N for one-sided rows
     bool onesided = false;             // ZFB_FLAG_ONESIDED
@@ -596,26 +592,13 @@ void prof_end(zfb_engine *e, int idx, cudaStream_t on = nullptr) {
     X(5, KIND, 2, 3, 3, 0, -1)   \
     X(6, KIND, 3, 3, 3, 3, -1)
 
-// persist_ctas > 0 (zfb_set_option "fir_persist", uint8 IQ, no channel batching): that many
-// CTAs walk over all tiles of the launch and stage their next tile with cp.async
 template <int KIND>
-void launch_fir_run_kind(int variant, const FirRunParams &rp, int L_out, int gf, cudaStream_t st, int persist_ctas,
-                         unsigned int *tile_counter) {
+void launch_fir_run_kind(int variant, const FirRunParams &rp, int L_out, int gf, cudaStream_t st) {
 #define ZFB_X(ID, K, NS, A, B, C, D)                                                              \
     if (variant == ID) {                                                                          \
         using SH = FirRunShape<NS, A, B, C, D>;                                                   \
         const int per_tile = SH::SPAN >> NS;                                                      \
         const unsigned tiles = (unsigned)((L_out + per_tile - 1) / per_tile);                     \
-        if (K == KIND_U8_RAW && !rp.chan && persist_ctas > 0) {                                   \
-            const long long nt = (long long)tiles * gf;                                           \
-            const unsigned ctas = (unsigned)(nt < persist_ctas ? nt : persist_ctas);              \
-            if (ctas > 0 && nt <= INT_MAX / 2) {                                                  \
-                if (tile_counter) cudaMemsetAsync(tile_counter, 0, sizeof(unsigned int), st);     \
-                ZFB_LAUNCH((fir_run_persist_kernel<NS, A, B, C, D>), dim3(ctas), dim3(FIR_NT),    \
-                           SH::SMEM + FIR_STAGE_BYTES, st, rp, (int)tiles, (int)nt, tile_counter); \
-                return;                                                                           \
-            }                                                                                     \
-        }                                                                                         \
         if (K != KIND_C64_MID && rp.chan) {                                                       \
             ZFB_LAUNCH((fir_run_kernel<K, NS, A, B, C, D, (K != KIND_C64_MID)>), dim3(tiles, (unsigned)gf), \
                        dim3(FIR_NT), SH::SMEM, st, rp);                                           \
@@ -628,11 +611,10 @@ void launch_fir_run_kind(int variant, const FirRunParams &rp, int L_out, int gf,
 #undef ZFB_X
 }
 
-void launch_fir_run(int variant, int kind, const FirRunParams &rp, int L_out, int gf, cudaStream_t st,
-                    int persist_ctas, unsigned int *tile_counter) {
-    if (kind == KIND_U8_RAW) launch_fir_run_kind<KIND_U8_RAW>(variant, rp, L_out, gf, st, persist_ctas, tile_counter);
-    else if (kind == KIND_C64_RAW) launch_fir_run_kind<KIND_C64_RAW>(variant, rp, L_out, gf, st, 0, nullptr);
-    else launch_fir_run_kind<KIND_C64_MID>(variant, rp, L_out, gf, st, 0, nullptr);
+void launch_fir_run(int variant, int kind, const FirRunParams &rp, int L_out, int gf, cudaStream_t st) {
+    if (kind == KIND_U8_RAW) launch_fir_run_kind<KIND_U8_RAW>(variant, rp, L_out, gf, st);
+    else if (kind == KIND_C64_RAW) launch_fir_run_kind<KIND_C64_RAW>(variant, rp, L_out, gf, st);
+    else launch_fir_run_kind<KIND_C64_MID>(variant, rp, L_out, gf, st);
 }
 
 // which specialised variant (0 = none) handles this chain
@@ -658,13 +640,6 @@ int fir_run_setup_kind(zfb_engine *e) {
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FirRunShape<NS, A, B, C, D>::SMEM));
     ZFB_RUN_COMBOS(ZFB_X, KIND)
 #undef ZFB_X
-    if (KIND == KIND_U8_RAW) {
-#define ZFB_X(ID, K, NS, A, B, C, D)                                                              \
-    CK(e, cudaFuncSetAttribute((fir_run_persist_kernel<NS, A, B, C, D>), cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                               (int)(FirRunShape<NS, A, B, C, D>::SMEM + FIR_STAGE_BYTES)));
-        ZFB_RUN_COMBOS(ZFB_X, KIND)
-#undef ZFB_X
-    }
     return ZFB_OK;
 }
 
@@ -796,12 +771,7 @@ cudaError_t run_decimation_fast(zfb_engine *e, const void *d_in, int gf, int *ou
                 rp.chan = (const ChannelLo *)e->chan_dev.p;
                 rp.chan_frames = e->cur_chan_frames;
             }
-            const int pctas = e->fir_persist_ctas ? e->fir_persist_ctas : e->fir_persist * e->sm_count;
-            unsigned int *tile_counter = nullptr;
-            if (pctas > 0 && kind == KIND_U8_RAW && !e->fir_persist_static &&
-                ensure(e, e->tile_counter, 256) == ZFB_OK)
-                tile_counter = (unsigned int *)e->tile_counter.p;
-            launch_fir_run(e->chain_run[j], kind, rp, e->len[lvl], gf, st, pctas, tile_counter);
+            launch_fir_run(e->chain_run[j], kind, rp, e->len[lvl], gf, st);
         } else {
             const unsigned tiles = (unsigned)((e->len[lvl] + p.TO - 1) / p.TO);
             ZFB_LAUNCH(chain_lookup(kind), dim3(tiles, (unsigned)gf), dim3(FIR_NT), e->chain_smem[j], st, p);
@@ -1318,7 +1288,6 @@ void zfb_destroy(zfb_engine *e) {
     release(e->sbuf[0]);
     release(e->sbuf[1]);
     release(e->chan_dev);
-    release(e->tile_counter);
     if (e->sr_copied) cudaEventDestroy(e->sr_copied);
     for (int i = 0; i < 2; ++i) if (e->sr_free[i]) cudaEventDestroy(e->sr_free[i]);
     if (e->h_rows) cudaFreeHost(e->h_rows);
@@ -1599,20 +1568,6 @@ int zfb_set_option(zfb_engine *e, const char *name, long long value) {
     }
     if (strcmp(name, "ring_append") == 0) {
         e->ring_append = value ? 1 : 0;
-        return ZFB_OK;
-    }
-    if (strcmp(name, "fir_persist") == 0) {
-        if (value < 0 || value > 4) return fail(e, ZFB_EINVAL, "fir_persist must be in [0, 4] (CTAs per SM)");
-        e->fir_persist = (int)value;
-        return ZFB_OK;
-    }
-    if (strcmp(name, "fir_persist_static") == 0) {
-        e->fir_persist_static = value ? 1 : 0;
-        return ZFB_OK;
-    }
-    if (strcmp(name, "fir_persist_ctas") == 0) {
-        if (value < 0 || value > 65535) return fail(e, ZFB_EINVAL, "fir_persist_ctas must be in [0, 65535]");
-        e->fir_persist_ctas = (int)value;
         return ZFB_OK;
     }
     if (strcmp(name, "fir_generic") == 0) {

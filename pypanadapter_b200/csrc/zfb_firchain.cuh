@@ -463,21 +463,20 @@ struct FirRunShape {
     static constexpr int SPAN = (FIR_NT - 2 * HT) * RUN0;          // level-0 samples a tile finishes
 };
 
-// One tile of one frame.  `staged` (PREF only): this thread's RUN0 raw samples, brought into
-// shared memory ahead of time by fir_run_persist_kernel ([RUN0 / VEC][FIR_NT] uint4).
-template <int KIND, int NS, int M0, int M1, int M2, int MC, bool CH, bool PREF>
-__device__ __forceinline__ void fir_run_tile(const FirRunParams &p, unsigned char *smem_raw, int frame, int bx,
-                                             const uint4 *staged) {
+template <int KIND, int NS, int M0, int M1, int M2, int MC, bool CH = false>
+__global__ void __launch_bounds__(FIR_NT, ZFB_FIR_MINB) fir_run_kernel(const FirRunParams p) {
     using SH = FirRunShape<NS, M0, M1, M2, MC>;
     constexpr int VEC = (KIND == KIND_U8_RAW) ? 8 : 2;
+    ZFB_DYN_SMEM(smem_raw);
     float2 *sm0 = reinterpret_cast<float2 *>(smem_raw);
     float2 *sm1 = sm0 + SH::S0;
     float2 *sm2 = sm1 + SH::S1;
     float2 *smc = sm2 + SH::S2;
     const int t = threadIdx.x;
-    const int ch = CH ? frame / p.chan_frames : 0;                  // frame: output (batch) index
+    const int frame = blockIdx.y;                                   // output (batch) index
+    const int ch = CH ? frame / p.chan_frames : 0;
     const int in_frame = CH ? frame % p.chan_frames : frame;
-    const int lo0 = bx * SH::SPAN - SH::HT * RUN0;                  // level-0 position of thread 0, sample 0
+    const int lo0 = blockIdx.x * SH::SPAN - SH::HT * RUN0;          // level-0 position of thread 0, sample 0
     const int pos0 = lo0 + t * RUN0;
     const int L = p.L;
 
@@ -494,7 +493,7 @@ __device__ __forceinline__ void fir_run_tile(const FirRunParams &p, unsigned cha
             constexpr int NV = RUN0 / VEC;
             uint4 raw[NV];
 #pragma unroll
-            for (int v = 0; v < NV; ++v) raw[v] = PREF ? staged[v * FIR_NT + t] : __ldg((const uint4 *)a + v);
+            for (int v = 0; v < NV; ++v) raw[v] = __ldg((const uint4 *)a + v);
 #pragma unroll
             for (int v = 0; v < NV; ++v) {
                 if (KIND == KIND_U8_RAW) {
@@ -591,102 +590,6 @@ __device__ __forceinline__ void fir_run_tile(const FirRunParams &p, unsigned cha
 #pragma unroll
         for (int j = 0; j < RO; ++j)
             if (po + j >= 0 && po + j < Llev[NS]) frame_out[po + j] = out[j];
-    }
-}
-
-template <int KIND, int NS, int M0, int M1, int M2, int MC, bool CH = false>
-__global__ void __launch_bounds__(FIR_NT, ZFB_FIR_MINB) fir_run_kernel(const FirRunParams p) {
-    ZFB_DYN_SMEM(smem_raw);
-    fir_run_tile<KIND, NS, M0, M1, M2, MC, CH, false>(p, smem_raw, blockIdx.y, blockIdx.x, nullptr);
-}
-
-// ---------------------------------------------------------------------------
-// Persistent variant for uint8 IQ (zfb_set_option "fir_persist"; off by default until it
-// has been measured).  ncu of fir_run_kernel: issue slots 56 % busy, the largest stall is the
-// long scoreboard -- every CTA starts by waiting out its own global loads, and with 124
-// registers only two CTAs share an SM to cover for each other.  Here a CTA walks over tiles
-// i = blockIdx.x, blockIdx.x + gridDim.x, ... and, before it starts on tile i, has the raw
-// bytes of its NEXT tile copied by cp.async (LDGSTS: no registers, no issue slots while in
-// flight) into a thread-private shared-memory slot: 4 x 16 B per thread, double-buffered,
-// 32 KB per CTA.  Each thread later reads only what it copied itself, so cp.async.wait_group
-// is the only synchronisation the staging needs.  Threads whose run is not a whole aligned
-// 64 B piece of the frame (chunk edges) stage nothing and take fir_run_tile's scalar path.
-// Arithmetic and its order are those of fir_run_kernel: rows are bit-identical.
-// ---------------------------------------------------------------------------
-constexpr int FIR_STAGE_VECS = RUN0 / 8;                                   // uint4 per thread (uint8 IQ)
-constexpr size_t FIR_STAGE_BYTES = 2 * (size_t)FIR_STAGE_VECS * FIR_NT * sizeof(uint4);
-
-__device__ __forceinline__ void stage_copy16(uint4 *dst_smem, const void *src_gmem) {
-#ifdef ZFB_EMULATE
-    *dst_smem = *reinterpret_cast<const uint4 *>(src_gmem);
-#else
-    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src_gmem) : "memory");
-#endif
-}
-__device__ __forceinline__ void stage_commit() {
-#ifndef ZFB_EMULATE
-    asm volatile("cp.async.commit_group;" ::: "memory");
-#endif
-}
-__device__ __forceinline__ void stage_wait_all() {
-#ifndef ZFB_EMULATE
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-#endif
-}
-
-// `counter` (zeroed before the launch) hands out tiles gridDim.x, gridDim.x + 1, ... on demand:
-// the edge strips run beside this kernel on a side stream and hold SM slots of their own for
-// a while, so CTAs of this grid start at different times and a static split leaves a tail.
-// counter == nullptr: static round robin i += gridDim.x.
-template <int NS, int M0, int M1, int M2, int MC>
-__global__ void __launch_bounds__(FIR_NT, ZFB_FIR_MINB)
-fir_run_persist_kernel(const FirRunParams p, int tiles_x, int ntiles, unsigned int *counter) {
-    using SH = FirRunShape<NS, M0, M1, M2, MC>;
-    ZFB_DYN_SMEM(smem_raw);
-    uint4 *stage = reinterpret_cast<uint4 *>(smem_raw + SH::SMEM);        // [2][FIR_STAGE_VECS][FIR_NT]
-    __shared__ int s_next;
-    const int t = threadIdx.x;
-
-    // stage this thread's run of tile i (same fast-path test as fir_run_tile)
-    auto prefetch = [&](int i, int slot) {
-        if (i < ntiles) {
-            const int frame = i / tiles_x, bx = i - frame * tiles_x;
-            const int pos0 = bx * SH::SPAN - SH::HT * RUN0 + t * RUN0;
-            const char *frame_in = (const char *)p.in + (size_t)frame * (size_t)p.in_stride * 2;
-            const long long i_first = p.flip ? (long long)p.L - RUN0 - pos0 : (long long)pos0;
-            const char *a = frame_in + (size_t)i_first * 2;
-            if (pos0 >= 0 && pos0 + RUN0 <= p.L && ((((uintptr_t)a) & 15) == 0)) {
-                uint4 *dst = stage + (size_t)slot * FIR_STAGE_VECS * FIR_NT + t;
-#pragma unroll
-                for (int v = 0; v < FIR_STAGE_VECS; ++v) stage_copy16(dst + v * FIR_NT, a + 16 * v);
-            }
-        }
-        stage_commit();
-    };
-    const int G = (int)gridDim.x;
-    auto claim = [&]() -> int { return G + (int)atomicAdd(counter, 1u); };   // thread 0 only
-
-    int cur = (int)blockIdx.x, nxt = cur + G;
-    prefetch(cur, 0);
-    if (counter) {
-        if (t == 0) s_next = claim();
-        __syncthreads();
-        nxt = s_next;
-    }
-    for (int slot = 0; cur < ntiles; slot ^= 1) {
-        stage_wait_all();                              // tile cur is in `slot` (own copies only)
-        prefetch(nxt, slot ^ 1);                       // in flight during the whole of tile cur
-        int after = nxt + G;
-        if (counter && t == 0) after = claim();        // its latency hides behind the tile
-        const int frame = cur / tiles_x, bx = cur - frame * tiles_x;
-        fir_run_tile<KIND_U8_RAW, NS, M0, M1, M2, MC, false, true>(
-            p, smem_raw, frame, bx, stage + (size_t)slot * FIR_STAGE_VECS * FIR_NT);
-        // (every tile has a barrier of its own between the readers of s_next and this write)
-        if (counter && t == 0) s_next = after;
-        __syncthreads();                               // the exchange buffers are reused by the next tile
-        cur = nxt;
-        nxt = counter ? s_next : after;
     }
 }
 

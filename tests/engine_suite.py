@@ -277,51 +277,6 @@ def fast_generic_fir_kernel(engine):
         engine._key = None
 
 
-def fast_persistent_fir(engine):
-    """zfb_set_option("fir_persist", n): the persistent FIR chain (next tile staged with
-    cp.async) does the arithmetic of the one-tile-per-CTA kernel in the same order, so rows
-    and the decimated chunk are bit-identical -- uint8 IQ, with and without flip, odd chunk
-    lengths (unaligned runs take the scalar path), R = 4 / 8 / 16 / 64, batches whose tile
-    count is not a multiple of the CTA count; it leaves complex64 input alone."""
-    rng = np.random.default_rng(314)
-    cases = ((4096 * 20, 4096, 16, True, 3), (319488, 4096, 16, True, 2), (100003, 1024, 8, False, 5),
-             (77777, 512, 4, True, 1), (262144 + 6, 1024, 64, False, 2), (50000, 256, 16, False, 7))
-    try:
-        for n, N, R, flip, nframes in cases:
-            k = np.arange(n)
-            x = 0.4 * np.exp(2j * np.pi * 0.0031 / R * k) + 0.2 * np.exp(-2j * np.pi * 0.37 * k)
-            x = x[None, :] + 0.02 * (rng.standard_normal((nframes, n)) + 1j * rng.standard_normal((nframes, n)))
-            wire = np.stack([synth.quantise_u8(f) for f in x])
-            got = {}
-            # (CTAs per SM, grid size outright): 2 per SM as it would run; 5 or 3 CTAs in all, so
-            # that every CTA walks over many tiles and the last round is ragged
-            # the last one with tiles dealt round robin instead of claimed from the counter
-            variants = ((0, 0, 0), (2, 0, 0), (1, 5, 0), (1, 3, 1))
-            for persist, ctas, static in variants:
-                engine.set_option("fir_persist", persist)
-                engine.set_option("fir_persist_ctas", ctas)
-                engine.set_option("fir_persist_static", static)
-                engine.configure(3.2e6, N, R, n, "hamming", dtype="u8", flip=flip, crop="thread", mode="fast")
-                assert engine.fast_active
-                rows = engine.process(wire)
-                got[persist, ctas, static] = (rows.copy(), engine.read_decimated().copy())
-            for v in variants[1:]:
-                assert np.array_equal(got[v][0], got[0, 0, 0][0]), (n, N, R, flip, v)
-                assert np.array_equal(got[v][1], got[0, 0, 0][1]), (n, N, R, flip, v)
-        # golden rows through the persistent kernel, and complex64 input is untouched by the option
-        engine.set_option("fir_persist", 2)
-        engine.set_option("fir_persist_ctas", 7)
-        for name in ("cfg2_T_f0", "cfg1_T", "zoom_R64"):
-            parity.check_case(engine, name, mode="fast")
-    finally:
-        engine.set_option("fir_persist", 0)
-        engine.set_option("fir_persist_ctas", 0)
-        engine.set_option("fir_persist_static", 0)
-        engine._key = None
-    with pytest.raises(ZoomFFTError):
-        engine.set_option("fir_persist", 9)
-
-
 def multi_channel(engine):
     """BASELINE configs[3] in small: virtual receivers with distinct zoom centres
     over the same frames (process_channels) == one configure+process per centre,

@@ -133,10 +133,6 @@ def test_fast_generic_fir_kernel(emu_engine):
     es.fast_generic_fir_kernel(emu_engine)
 
 
-def test_fast_persistent_fir(emu_engine):
-    es.fast_persistent_fir(emu_engine)
-
-
 def test_multi_channel(emu_engine):
     es.multi_channel(emu_engine)
 

@@ -209,10 +209,6 @@ def test_fast_generic_fir_kernel(gpu_engine):
     es.fast_generic_fir_kernel(gpu_engine)
 
 
-def test_fast_persistent_fir(gpu_engine):
-    es.fast_persistent_fir(gpu_engine)
-
-
 def test_multi_channel(gpu_engine):
     es.multi_channel(gpu_engine)
 
