@@ -145,6 +145,12 @@ class ZoomPSD:
         the reference gets from welch's one-sided spectrum (N/2+1 bins) after
         its fftshift and crop (T:1538-1543), ``crop_width/2 + 1`` bins wide."""
         fft_ratio_i = int(fft_ratio)
+        if dtype not in ("c64", "u8"):
+            raise ValueError("dtype must be 'c64' or 'u8', got %r" % (dtype,))
+        if mode not in ("exact", "fast"):
+            raise ValueError("mode must be 'exact' or 'fast'")
+        if onesided and (fft_ratio_i != 1 or dtype != "c64"):
+            raise ValueError("onesided rows are the real-input, fft_ratio == 1 case")
         wkey = window if isinstance(window, (str, tuple)) else ("array", np.asarray(window).tobytes())
         key = (float(fs), int(fft_size), float(fft_ratio), int(frame_len), wkey, dtype, bool(flip),
                float(f_demod), crop, ema_alpha, bool(no_lo), bool(linear), mode, bool(onesided))
@@ -162,16 +168,12 @@ class ZoomPSD:
         cfg.nperseg = geo["nperseg"]
         cfg.dtype = {"c64": _lib.ZFB_DTYPE_C64, "u8": _lib.ZFB_DTYPE_U8}[dtype]
         cfg.flip = 1 if flip else 0
-        if mode not in ("exact", "fast"):
-            raise ValueError("mode must be 'exact' or 'fast'")
         cfg.mode = _lib.ZFB_MODE_EXACT
         if mode == "fast" and geo["nstages"] >= 2:
             self._set_fast_plan(1 << geo["nstages"])
             cfg.mode = _lib.ZFB_MODE_FAST
         cfg.flags = (_lib.ZFB_FLAG_NO_LO if no_lo else 0) | (_lib.ZFB_FLAG_LINEAR if linear else 0) | \
                     (_lib.ZFB_FLAG_ONESIDED if onesided else 0)
-        if onesided and (fft_ratio_i != 1 or dtype != "c64"):
-            raise ValueError("onesided rows are the real-input, fft_ratio == 1 case")
         cfg.f_demod = float(f_demod)
         cfg.ema_alpha = -1.0 if ema_alpha is None else float(ema_alpha)
         cfg.window = w.ctypes.data_as(C.POINTER(C.c_double))
@@ -362,6 +364,8 @@ class ZoomPSD:
         lut_p = None
         if kind == "rgba":
             lut = np.ascontiguousarray(lut, dtype=np.uint8)
+            if lut.shape != (256, 4):
+                raise ValueError("lut must be (256, 4) uint8")
             lut_p = C.c_void_p(lut.ctypes.data)
         self._check(self._lib.zfb_ring_image(self._h, int(height), int(scroll), int(rows_seen), code,
                                              float(levels[0]), float(levels[1]), lut_p, C.c_void_p(d_out_ptr), 1),

@@ -136,9 +136,18 @@ def error_paths(engine):
         engine.ring_quantiles(16, 1, 1, [1.5])                       # quantile outside [0, 1]
     with pytest.raises(ZoomFFTError):
         engine.set_option("no_such_knob", 1)
+    # unknown wire format / decimator mode: rejected before anything is planned
+    with pytest.raises(ValueError):
+        engine.configure(2.4e6, 64, 2, 256, "hamming", dtype="cs16")
+    with pytest.raises(ValueError):
+        engine.configure(2.4e6, 64, 4, 4096, "hamming", mode="turbo")
+    with pytest.raises(ValueError):
+        engine.ring_image_device(0, 16, 1, 1, "rgba", lut=np.zeros((16, 4), np.uint8))
     # one-sided rows are the real-input, no-zoom case only
     with pytest.raises(ValueError):
         engine.configure(48e3, 64, 2, 256, "hamming", onesided=True)
+    with pytest.raises(ValueError):
+        engine.configure(48e3, 64, 1, 256, "hamming", dtype="u8", onesided=True)
     with pytest.raises(ZoomFFTError):
         engine.configure(48e3, 16384, 1, 65536, "hamming", onesided=True)   # beyond the one-CTA FFT
     engine.configure(48e3, 64, 1, 256, "hamming", crop=32, onesided=True)
