@@ -236,6 +236,18 @@ def run_b200(args, w):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl b200 needs a CUDA device (there is no CPU fallback)")
     torch.cuda.set_device(local_rank)
+    host_affinity = None
+    if world > 1 and not args.no_numa_bind:
+        # one process per GPU: sit on the CPUs (hence the memory) of this GPU's NUMA node before
+        # any pinned staging buffer is allocated
+        from pypanadapter_b200 import dist as zdist0
+        pr = torch.cuda.get_device_properties(local_rank)
+        try:
+            bus = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+            host_affinity = zdist0.bind_host_to_gpu(bus)
+            host_affinity["gpu"] = bus
+        except Exception as exc:                      # never let placement stop a run
+            host_affinity = {"bound": False, "why": repr(exc)}
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -427,6 +439,8 @@ def run_b200(args, w):
             cfg["channels_per_gpu"] = nch
             cfg["value_counts"] = "channel-samples: every virtual receiver consumes the whole stream"
         cfg["decimator_mode"] = "fast" if eng.fast_active else "exact"
+        if host_affinity is not None:
+            cfg["host_affinity_rank0"] = host_affinity
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -468,6 +482,8 @@ def main():
     ap.add_argument("--lib", default=None, help="tuning: path of an alternative sm_100a build")
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-numa-bind", action="store_true",
+                    help="N > 1: do not bind each rank to the CPUs of its GPU's NUMA node")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
