@@ -41,6 +41,11 @@ extern "C" {
 #define ZFB_DTYPE_C64   0      /* interleaved float32 I,Q  (SoapySDR CF32, S:602) */
 #define ZFB_DTYPE_U8    1      /* interleaved uint8 offset-binary I,Q (RTL-SDR;
                                   converted as pyrtlsdr does: u/127.5 - 1, S:543) */
+#define ZFB_DTYPE_CS16  2      /* interleaved int16 I,Q (SoapySDR CS16 -- the native format of
+                                  most Soapy devices; the reference asks for CF32, S:602, and
+                                  lets SoapySDR convert on the host): (I + jQ) / 32768, by one
+                                  streaming pass on the device in front of the complex64 path
+                                  (no reference code to match: unpinned) */
 
 /* decimator implementations (zfb_config.mode) */
 #define ZFB_MODE_EXACT  0      /* per-chunk zero-phase cheby1 IIR, scipy semantics */

@@ -68,6 +68,20 @@ def rtlsdr_bytes_to_iq(raw: np.ndarray) -> np.ndarray:
     return iq
 
 
+def cs16_to_iq(raw: np.ndarray) -> np.ndarray:
+    """int16 interleaved I,Q (SoapySDR ``SOAPY_SDR_CS16``) -> complex128.
+
+    The reference asks SoapySDR for ``SOAPY_SDR_CF32`` (S:602) and lets the
+    library convert the device's native int16 on the host; SoapySDR's
+    CS16 -> CF32 converter scales by 1/32768.  SoapySDR is not installed and not
+    vendored: PARITY UNPINNED for this one function.
+    """
+    raw = np.ascontiguousarray(raw, dtype=np.int16)
+    if raw.size % 2:
+        raise ValueError("int16 IQ stream must hold an even number of values")
+    return raw.astype(np.float64).view(np.complex128) / 32768.0
+
+
 def flip_chunk(x: np.ndarray) -> np.ndarray:
     """``np.flip`` of the chunk: the reference's "IQ inversion" (S:460, S:543,
     T:460) is a time reversal of the whole chunk."""
@@ -251,13 +265,16 @@ def zoom_psd_power(chunk, fs, fft_size, fft_ratio, window, *, f_demod=1.0,
                    crop="thread", flip=False, explicit=False):
     """Linear (pre-dB) cropped PSD row of one chunk.
 
-    chunk: complex ndarray, or uint8 interleaved I,Q (converted as pyrtlsdr).
+    chunk: complex ndarray, uint8 interleaved I,Q (converted as pyrtlsdr) or
+    int16 interleaved I,Q (SoapySDR CS16).
     Mirrors ApplicationDisplay.update (S:2102-2114) for ``crop=N_WIN`` and
     PSD.update (T:1513-1543) for ``crop='thread'``.
     """
     chunk = np.asarray(chunk)
     if chunk.dtype == np.uint8:
         chunk = rtlsdr_bytes_to_iq(chunk)
+    elif chunk.dtype == np.int16:
+        chunk = cs16_to_iq(chunk)
     if flip:
         chunk = flip_chunk(chunk)
     if fft_ratio > 1:                                # S:2108, T:1525

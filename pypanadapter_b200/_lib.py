@@ -24,6 +24,7 @@ ZFB_ETOOSHORT = -34
 
 ZFB_DTYPE_C64 = 0
 ZFB_DTYPE_U8 = 1
+ZFB_DTYPE_CS16 = 2
 ZFB_MODE_EXACT = 0
 ZFB_MODE_FAST = 1
 FAST_MAX_STAGES = 12

@@ -83,6 +83,11 @@ class Data:
         conversion (S:543) then happens on the device."""
         return self._new("u8", False)
 
+    def new_cs16(self):
+        """SoapySDR CS16 wire format: interleaved int16 I,Q (2*max_size values),
+        widened to complex64 (/32768) on the device."""
+        return self._new("cs16", False)
+
     def new_common(self):
         self.size = 0            # position of the next entry
         self.real_size = 0       # high-water mark since the last take
@@ -94,11 +99,13 @@ class Data:
     # -- producer (T:1433-1457) ------------------------------------------------
     def add(self, chunk):
         chunk = np.asarray(chunk)
-        per = 2 if self.wire == "u8" else 1
+        per = 1 if self.wire == "c64" else 2
         if self.wire == "u8" and chunk.dtype != np.uint8:
             raise TypeError("this Data holds raw uint8 IQ")
+        if self.wire == "cs16" and chunk.dtype != np.int16:
+            raise TypeError("this Data holds raw int16 IQ")
         if len(chunk) % per:
-            raise ValueError("uint8 IQ chunk must hold an even number of bytes")
+            raise ValueError("interleaved IQ chunk must hold an even number of values")
         length = len(chunk) // per
         self.lock.lock()
         try:

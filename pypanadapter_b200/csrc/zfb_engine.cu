@@ -80,6 +80,7 @@ struct zfb_engine {
     int nsplit_cap = 1;
     StageParams sp0[2]{};              // LO tables of stage 0 for NT = 256 / 128
 
+    DevBuf cvt;                        // complex64 copy of an int16 IQ launch group (ZFB_DTYPE_CS16)
     DevBuf window, winfft, twiddle, twiddle_sub, pow16, mid[2], pow, rows_tmp, ema, ring, stage_in[2], big, img_out, img_lut, img_thr, sel_hist;
     void  *h_stage[2] = {nullptr, nullptr};
     size_t h_stage_cap[2] = {0, 0};
@@ -473,8 +474,22 @@ int setup_device_once(zfb_engine *e) {
     return rc;
 }
 
+// kind of the samples the kernels see (int16 IQ has been widened to complex64 by then)
 int raw_kind(const zfb_config &c) { return c.dtype == ZFB_DTYPE_U8 ? KIND_U8_RAW : KIND_C64_RAW; }
-size_t sample_bytes(const zfb_config &c) { return c.dtype == ZFB_DTYPE_U8 ? 2 : 8; }
+size_t dtype_bytes(int dtype) { return dtype == ZFB_DTYPE_U8 ? 2 : dtype == ZFB_DTYPE_CS16 ? 4 : 8; }
+// bytes per sample on the wire (caller's buffers, staging, sample ring)
+size_t sample_bytes(const zfb_config &c) { return dtype_bytes(c.dtype); }
+
+// SoapySDR CS16 -> complex64, (I + jQ) / 32768: one coalesced streaming pass (4 B in, 8 B out
+// per sample) in front of the complex64 path
+__global__ void __launch_bounds__(256) cs16_to_c64_kernel(const unsigned int *in, float2 *out, long long n) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const unsigned int w = in[i];                       // little endian: I in the low half
+        const float fi = (float)(short)(w & 0xffffu), fq = (float)(short)(w >> 16);
+        out[i] = make_float2(fi * (1.0f / 32768.0f), fq * (1.0f / 32768.0f));
+    }
+}
 
 // FAST engages when the plan fits and the chunk is long enough for the strips
 bool fast_wanted(const zfb_engine *e, int *strip_len, int *strip_q) {
@@ -852,6 +867,22 @@ cudaError_t run_decimation_fast(zfb_engine *e, const void *d_in, int gf, int *ou
 int run_group(zfb_engine *e, const void *d_in, int gf, float *d_rows) {
     const zfb_config &c = e->cfg;
     cudaStream_t st = e->stream;
+    if (c.dtype == ZFB_DTYPE_CS16) {
+        // channel-batched launches read cur_chan_frames input frames for gf = frames * channels rows
+        const long long in_frames = e->cur_nch > 0 ? e->cur_chan_frames : gf;
+        const long long n = in_frames * (long long)c.frame_len;
+        int rc = ensure(e, e->cvt, (size_t)n * sizeof(float2));
+        if (rc) return rc;
+        if (n > 0) {
+            long long blocks = (n + 255) / 256;
+            const long long cap = (long long)e->sm_count * 16;
+            if (blocks > cap) blocks = cap;
+            ZFB_LAUNCH(cs16_to_c64_kernel, dim3((unsigned)blocks), dim3(256), 0, st, (const unsigned int *)d_in,
+                       (float2 *)e->cvt.p, n);
+            e->counters[2] += 1;
+        }
+        d_in = e->cvt.p;
+    }
     const void *src = d_in;
     long long src_stride = c.frame_len;
     int kind = raw_kind(c);
@@ -1288,6 +1319,7 @@ void zfb_destroy(zfb_engine *e) {
     release(e->sbuf[0]);
     release(e->sbuf[1]);
     release(e->chan_dev);
+    release(e->cvt);
     if (e->sr_copied) cudaEventDestroy(e->sr_copied);
     for (int i = 0; i < 2; ++i) if (e->sr_free[i]) cudaEventDestroy(e->sr_free[i]);
     if (e->h_rows) cudaFreeHost(e->h_rows);
@@ -1332,7 +1364,7 @@ int zfb_configure(zfb_engine *e, const zfb_config *cfg) {
                     1 << kMaxLog2N);
     if (!(cfg->fs > 0.0)) return fail(e, ZFB_EINVAL, "fs must be positive");
     if (cfg->fft_ratio < 1) return fail(e, ZFB_EINVAL, "fft_ratio %d: must be >= 1", cfg->fft_ratio);
-    if (cfg->dtype != ZFB_DTYPE_C64 && cfg->dtype != ZFB_DTYPE_U8)
+    if (cfg->dtype != ZFB_DTYPE_C64 && cfg->dtype != ZFB_DTYPE_U8 && cfg->dtype != ZFB_DTYPE_CS16)
         return fail(e, ZFB_EINVAL, "unknown dtype %d", cfg->dtype);
     if (cfg->mode != ZFB_MODE_EXACT && cfg->mode != ZFB_MODE_FAST)
         return fail(e, ZFB_EINVAL, "unknown mode %d", cfg->mode);
@@ -2164,11 +2196,12 @@ int zfb_samples_create(zfb_engine *e, int64_t capacity_samples, int dtype) {
     std::lock_guard<std::mutex> lk(e->mu);
     if (capacity_samples < 1 || capacity_samples > (1ll << 31))
         return fail(e, ZFB_EINVAL, "sample ring capacity out of range");
-    if (dtype != ZFB_DTYPE_C64 && dtype != ZFB_DTYPE_U8) return fail(e, ZFB_EINVAL, "unknown dtype %d", dtype);
+    if (dtype != ZFB_DTYPE_C64 && dtype != ZFB_DTYPE_U8 && dtype != ZFB_DTYPE_CS16)
+        return fail(e, ZFB_EINVAL, "unknown dtype %d", dtype);
     CK(e, cudaSetDevice(e->device));
     CK(e, cudaStreamSynchronize(e->stream));
     CK(e, cudaStreamSynchronize(e->copy_stream));
-    const size_t bytes = (size_t)capacity_samples * (dtype == ZFB_DTYPE_U8 ? 2 : 8);
+    const size_t bytes = (size_t)capacity_samples * dtype_bytes(dtype);
     if (e->sr_host) { CK(e, cudaFreeHost(e->sr_host)); e->sr_host = nullptr; }
     CK(e, cudaMallocHost(&e->sr_host, bytes));
     memset(e->sr_host, 0, bytes);
@@ -2211,7 +2244,7 @@ int zfb_samples_commit(zfb_engine *e, int64_t offset, int64_t n) {
     if (offset < 0 || n < 0 || offset + n > e->sr_cap) return fail(e, ZFB_EINVAL, "sample span out of range");
     if (n == 0) return ZFB_OK;
     CK(e, cudaSetDevice(e->device));
-    const size_t esz = e->sr_dtype == ZFB_DTYPE_U8 ? 2 : 8;
+    const size_t esz = dtype_bytes(e->sr_dtype);
     const int m = e->sr_active;
     if (e->sr_free_pending[m]) {       // a kernel may still be reading this mirror
         CK(e, cudaStreamWaitEvent(e->copy_stream, e->sr_free[m], 0));

@@ -35,6 +35,14 @@ class ZoomFFTError(RuntimeError):
         self.code = code
 
 
+# wire formats: name -> (ZFB_DTYPE_*, numpy dtype of the interleaved stream or None for complex64,
+#                        stream elements per sample)
+_DTYPES = {
+    "c64": (_lib.ZFB_DTYPE_C64, None, 1),
+    "u8": (_lib.ZFB_DTYPE_U8, np.uint8, 2),        # RTL-SDR offset binary
+    "cs16": (_lib.ZFB_DTYPE_CS16, np.int16, 2),    # SoapySDR CS16
+}
+
 _window_cache: dict = {}
 _window_lock = threading.Lock()
 
@@ -145,8 +153,8 @@ class ZoomPSD:
         the reference gets from welch's one-sided spectrum (N/2+1 bins) after
         its fftshift and crop (T:1538-1543), ``crop_width/2 + 1`` bins wide."""
         fft_ratio_i = int(fft_ratio)
-        if dtype not in ("c64", "u8"):
-            raise ValueError("dtype must be 'c64' or 'u8', got %r" % (dtype,))
+        if dtype not in _DTYPES:
+            raise ValueError("dtype must be one of %s, got %r" % (", ".join(map(repr, _DTYPES)), dtype))
         if mode not in ("exact", "fast"):
             raise ValueError("mode must be 'exact' or 'fast'")
         if onesided and (fft_ratio_i != 1 or dtype != "c64"):
@@ -166,7 +174,7 @@ class ZoomPSD:
         cfg.frame_len = int(frame_len)
         cfg.row_width = int(W)
         cfg.nperseg = geo["nperseg"]
-        cfg.dtype = {"c64": _lib.ZFB_DTYPE_C64, "u8": _lib.ZFB_DTYPE_U8}[dtype]
+        cfg.dtype = _DTYPES[dtype][0]
         cfg.flip = 1 if flip else 0
         cfg.mode = _lib.ZFB_MODE_EXACT
         if mode == "fast" and geo["nstages"] >= 2:
@@ -229,14 +237,15 @@ class ZoomPSD:
         complex128 (what pyrtlsdr / the reference's Data hand over) is cast to
         complex64 here -- the device computes in fp32."""
         a = np.asarray(frames)
-        if self.dtype == "u8":
-            if a.dtype != np.uint8:
-                raise TypeError("engine is configured for uint8 IQ, got %s" % a.dtype)
-            per = 2 * self.frame_len
+        _code, raw, per_sample = _DTYPES[self.dtype]
+        if raw is not None:
+            if a.dtype != raw:
+                raise TypeError("engine is configured for %s IQ, got %s" % (np.dtype(raw).name, a.dtype))
+            per = per_sample * self.frame_len
         else:
             if a.dtype != np.complex64:
-                if a.dtype == np.uint8:
-                    raise TypeError("engine is configured for complex samples, got raw uint8 IQ")
+                if a.dtype in (np.uint8, np.int16):
+                    raise TypeError("engine is configured for complex samples, got raw %s IQ" % a.dtype)
                 if not np.issubdtype(a.dtype, np.number):
                     raise TypeError("unsupported sample dtype %s" % a.dtype)
                 a = a.astype(np.complex64)
@@ -386,14 +395,15 @@ class ZoomPSD:
     # -- pinned sample ring (storage of buffers.Data) ------------------------
     def samples_create(self, capacity: int, dtype: str = "c64") -> np.ndarray:
         """Allocate the pinned sample ring + device mirrors; returns a numpy
-        view of the pinned host storage (complex64[capacity] or uint8[2*capacity])."""
-        code = {"c64": _lib.ZFB_DTYPE_C64, "u8": _lib.ZFB_DTYPE_U8}[dtype]
+        view of the pinned host storage (complex64[capacity], uint8[2*capacity]
+        or int16[2*capacity])."""
+        code, raw_dtype, per = _DTYPES[dtype]
         self._check(self._lib.zfb_samples_create(self._h, int(capacity), code), "zfb_samples_create")
         ptr = self._lib.zfb_samples_host_ptr(self._h)
-        nbytes = int(capacity) * (2 if dtype == "u8" else 8)
+        view = np.dtype(np.complex64 if raw_dtype is None else raw_dtype)
+        nbytes = int(capacity) * per * view.itemsize
         raw = (C.c_ubyte * nbytes).from_address(ptr)
-        a = np.frombuffer(raw, dtype=np.uint8)
-        return a if dtype == "u8" else a.view(np.complex64)
+        return np.frombuffer(raw, dtype=np.uint8).view(view)
 
     def samples_begin_write(self, offset: int, n: int):
         self._check(self._lib.zfb_samples_begin_write(self._h, int(offset), int(n)), "zfb_samples_begin_write")
@@ -446,7 +456,8 @@ def zoom_psd(chunk, fs, fft_size, fft_ratio, window, *, f_demod=1.0, crop="threa
              flip=False, ema_alpha=None, mode="fast", engine: ZoomPSD | None = None) -> np.ndarray:
     """One dB20 waterfall row of one chunk (float64 ndarray[W]).
 
-    ``chunk``: 1-D complex64/complex128, interleaved uint8 I,Q (RTL-SDR), or
+    ``chunk``: 1-D complex64/complex128, interleaved uint8 I,Q (RTL-SDR),
+    interleaved int16 I,Q (SoapySDR CS16), or
     real floats (AudioPan, S:712-714; without zoom the row is then the
     reference's fftshifted one-sided spectrum, T:1538-1543).
     ``crop``: ``'thread'`` reproduces PSD.update (T:1542-1543); an int N_WIN
@@ -456,10 +467,10 @@ def zoom_psd(chunk, fs, fft_size, fft_ratio, window, *, f_demod=1.0, crop="threa
     if chunk.ndim != 1:
         raise ValueError("chunk must be 1-D")
     eng = engine or default_engine()
-    if chunk.dtype == np.uint8:
+    if chunk.dtype == np.uint8 or chunk.dtype == np.int16:
         if chunk.size % 2:
-            raise ValueError("uint8 IQ stream must hold an even number of bytes")
-        dtype, n = "u8", chunk.size // 2
+            raise ValueError("interleaved IQ stream must hold an even number of values")
+        dtype, n = ("u8" if chunk.dtype == np.uint8 else "cs16"), chunk.size // 2
     else:
         dtype, n = "c64", chunk.size
     onesided = dtype == "c64" and np.isrealobj(chunk) and not fft_ratio > 1

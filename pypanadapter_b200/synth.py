@@ -104,6 +104,14 @@ def quantise_u8(x: np.ndarray) -> np.ndarray:
     return np.clip(np.rint(127.5 * (1.0 + iq)), 0, 255).astype(np.uint8)
 
 
+def quantise_cs16(x: np.ndarray) -> np.ndarray:
+    """complex -> interleaved int16 I,Q (SoapySDR CS16): clip(rint(32768*s))."""
+    iq = np.empty(2 * len(x), dtype=np.float64)
+    iq[0::2] = x.real
+    iq[1::2] = x.imag
+    return np.clip(np.rint(32768.0 * iq), -32768, 32767).astype(np.int16)
+
+
 def make_frame(w: Workload, frame_index: int = 0, n: int | None = None
                ) -> np.ndarray:
     """One frame in the workload's wire dtype (complex64 or interleaved u8)."""

@@ -6,6 +6,7 @@ import os
 import types
 
 import numpy as np
+import pytest
 
 from oracle import golden_cases as gc
 from oracle import make_golden as mg
@@ -118,6 +119,32 @@ def psd_update_u8(engine):
     psd.update()
     want = zo.zoom_psd(raw, w.fs, w.fft_size, w.fft_ratio, w.window, flip=True)
     parity.assert_row_parity(psd.psd, want, parity.floor_db20(w.fs, w.window, w.fft_size, True), "u8 PSD.update")
+
+
+def psd_update_cs16(engine):
+    """SoapySDR CS16 through Data.new_cs16 (pinned int16 ring, widened on the
+    device), fold-back included: the row equals the oracle's on the samples the
+    ring holds."""
+    fs, N, R = 2.4e6, 1024, 8
+    n = N * R * 5
+    k = np.arange(n)
+    rng = np.random.default_rng(5)
+    x = 0.4 * np.exp(2j * np.pi * 1700.0 / fs * k) + 3e-3 * (rng.standard_normal(n) + 1j * rng.standard_normal(n))
+    raw = synth.quantise_cs16(x)
+    state = types.SimpleNamespace(fft_size=N, fft_ratio=R, fft_tapering="hamming",
+                                  panadapter=types.SimpleNamespace(SampleRate=fs))
+    d = Data(chunk_size=4096, engine=engine).new_cs16()
+    assert d.data.dtype == np.int16 and d.data.shape == (2 * d.max_size,)
+    psd = PSD(d, state)
+    step = 2 * 4096
+    for i in range(0, len(raw), step):
+        d.add(raw[i:i + step])
+    assert d.real_size == n
+    psd.update()
+    want = zo.zoom_psd(raw, fs, N, R, "hamming")
+    parity.assert_row_parity(psd.psd, want, parity.floor_db20(fs, "hamming", N, True), "cs16 PSD.update")
+    with pytest.raises(TypeError):
+        d.add(np.zeros(64, dtype=np.uint8))
 
 
 def psd_update_real(engine):

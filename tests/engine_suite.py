@@ -138,7 +138,7 @@ def error_paths(engine):
         engine.set_option("no_such_knob", 1)
     # unknown wire format / decimator mode: rejected before anything is planned
     with pytest.raises(ValueError):
-        engine.configure(2.4e6, 64, 2, 256, "hamming", dtype="cs16")
+        engine.configure(2.4e6, 64, 2, 256, "hamming", dtype="cf64")
     with pytest.raises(ValueError):
         engine.configure(2.4e6, 64, 4, 4096, "hamming", mode="turbo")
     with pytest.raises(ValueError):
@@ -284,6 +284,57 @@ def fast_generic_fir_kernel(engine):
     finally:
         engine.set_option("fir_generic", 0)
         engine._key = None
+
+
+def cs16_wire_format(engine):
+    """SoapySDR CS16 (interleaved int16 I,Q): widened on the device,
+    (I + jQ) / 32768.  Every int16 is exact in fp32, so rows are BIT-IDENTICAL to
+    those of the same samples handed over as complex64 -- both decimator modes, no
+    zoom, flip, batches, odd lengths, virtual receivers -- and meet parity against
+    the oracle's own conversion."""
+    rng = np.random.default_rng(1616)
+    cases = ((2.4e6, 2048, 8, 2048 * 8 * 6, "hamming", False, 3), (3.2e6, 1024, 16, 100003, "hann", True, 2),
+             (1e6, 512, 1, 512 * 9 + 5, "hamming", False, 2), (2.4e6, 256, 4, 77777, "blackman", True, 1))
+    for fs, N, R, n, win, flip, nframes in cases:
+        k = np.arange(n)
+        x = 0.45 * np.exp(2j * np.pi * 0.011 / R * k) + 0.05 * np.exp(-2j * np.pi * 0.023 / R * k)
+        x = x[None, :] + 3e-3 * (rng.standard_normal((nframes, n)) + 1j * rng.standard_normal((nframes, n)))
+        wire = np.stack([synth.quantise_cs16(f) for f in x])
+        as_c64 = np.stack([zo.cs16_to_iq(f).astype(np.complex64) for f in wire])
+        assert np.array_equal(as_c64.astype(np.complex128), np.stack([zo.cs16_to_iq(f) for f in wire]))
+        for mode in ("fast", "exact"):
+            engine.configure(fs, N, R, n, win, dtype="cs16", flip=flip, crop="thread", mode=mode)
+            rows = engine.process(wire)
+            dec = engine.read_decimated().copy() if R > 1 else None
+            single = np.stack([engine.process(wire[i])[0] for i in range(nframes)])
+            assert np.array_equal(rows, single), (fs, N, R, mode)
+            engine.configure(fs, N, R, n, win, dtype="c64", flip=flip, crop="thread", mode=mode)
+            assert np.array_equal(rows, engine.process(as_c64)), (fs, N, R, mode)
+            if R > 1:
+                assert np.array_equal(dec, engine.read_decimated())
+            floor = parity.floor_db20(fs, win, engine.geometry["nperseg"], R > 1)
+            for i in range(nframes):
+                want = zo.zoom_psd(wire[i], fs, N, R, win, crop="thread", flip=flip)
+                parity.assert_row_parity(rows[i].astype(np.float64), want, floor, "cs16 %s R=%d" % (mode, R))
+    # the fused frame call infers the format from the dtype; virtual receivers over int16 frames
+    fs, N, R, n = 2.4e6, 1024, 8, 1024 * 8 * 4
+    x = 0.3 * np.exp(2j * np.pi * (250e3 + 900.0) / fs * np.arange(n))
+    wire = synth.quantise_cs16(x)
+    from pypanadapter_b200.engine import zoom_psd
+    got = zoom_psd(wire, fs, N, R, "hamming", f_demod=250e3, engine=engine)
+    want = zo.zoom_psd(wire, fs, N, R, "hamming", f_demod=250e3)
+    parity.assert_row_parity(got, want, parity.floor_db20(fs, "hamming", N, True), "cs16 zoom_psd")
+    centres = np.array([250e3, -1.0e6, 1.0])
+    engine.configure(fs, N, R, n, "hamming", dtype="cs16", crop="thread")
+    rows = engine.process_channels(np.stack([wire, wire]), centres)
+    engine.configure(fs, N, R, n, "hamming", dtype="c64", crop="thread")
+    ref = engine.process_channels(np.stack([zo.cs16_to_iq(wire).astype(np.complex64)] * 2), centres)
+    assert np.array_equal(rows, ref)
+    with pytest.raises(TypeError):
+        engine.configure(fs, N, R, n, "hamming", dtype="cs16")
+        engine.process(np.zeros(2 * n, dtype=np.uint8))
+    with pytest.raises(ValueError):
+        zoom_psd(np.zeros(2 * n + 1, dtype=np.int16), fs, N, R, "hamming", engine=engine)
 
 
 def multi_channel(engine):

@@ -67,6 +67,10 @@ def test_psd_update_u8(emu_engine):
     bs.psd_update_u8(emu_engine)
 
 
+def test_psd_update_cs16(emu_engine):
+    bs.psd_update_cs16(emu_engine)
+
+
 def test_rtl_tcp_source(emu_engine):
     bs.rtl_tcp_source(emu_engine)
 
@@ -131,6 +135,10 @@ def test_fast_strong_out_of_band(emu_engine):
 
 def test_fast_generic_fir_kernel(emu_engine):
     es.fast_generic_fir_kernel(emu_engine)
+
+
+def test_cs16_wire_format(emu_engine):
+    es.cs16_wire_format(emu_engine)
 
 
 def test_multi_channel(emu_engine):

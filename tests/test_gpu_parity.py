@@ -143,6 +143,10 @@ def test_psd_update_u8(gpu_engine):
     bs.psd_update_u8(gpu_engine)
 
 
+def test_psd_update_cs16(gpu_engine):
+    bs.psd_update_cs16(gpu_engine)
+
+
 def test_rtl_tcp_source(gpu_engine):
     bs.rtl_tcp_source(gpu_engine)
 
@@ -207,6 +211,10 @@ def test_fast_strong_out_of_band(gpu_engine):
 
 def test_fast_generic_fir_kernel(gpu_engine):
     es.fast_generic_fir_kernel(gpu_engine)
+
+
+def test_cs16_wire_format(gpu_engine):
+    es.cs16_wire_format(gpu_engine)
 
 
 def test_multi_channel(gpu_engine):
