@@ -10,8 +10,10 @@ Citations: ``S:`` = /root/reference/pypanadapter_spectrum.py,
 
 Pinned by tests/golden/*.npz, which were produced by the reference's own
 methods (oracle/ref_harness.py + oracle/make_golden.py) with numpy 2.3.5 /
-scipy 1.18.1.  ``rtlsdr_bytes_to_iq`` restates pyrtlsdr (not installed, not
-vendored): parity unpinned for that one function.
+scipy 1.18.1.  PARITY UNPINNED for the functions that restate libraries which are
+neither installed nor vendored: ``rtlsdr_bytes_to_iq`` (pyrtlsdr), ``cs16_to_iq``
+(SoapySDR's CS16 -> CF32 converter) and ``waterfall_indices`` / ``colormap_lut``
+(pyqtgraph's level -> colour-index mapping and ColorMap table).
 
 Two levels are provided for every stage:
 * ``*_ref``      -- the same scipy call the reference makes (fast; used for
