@@ -109,6 +109,22 @@ def test_u8_conversion_and_flip():
         zo.rtlsdr_bytes_to_iq(raw[:5])
 
 
+def test_cs16_conversion():
+    """SoapySDR CS16 -> complex: (I + jQ) / 32768, exact in fp32 (the device path
+    relies on that for bit-identical rows)."""
+    raw = np.array([-32768, 32767, 0, 16384, -1, 1], dtype=np.int16)
+    iq = zo.cs16_to_iq(raw)
+    assert np.array_equal(iq, [-1 + (32767 / 32768) * 1j, 0.5j, (-1 + 1j) / 32768])
+    assert np.array_equal(iq.astype(np.complex64).astype(np.complex128), iq)
+    every = np.arange(-32768, 32768, dtype=np.int64).astype(np.int16)
+    assert np.array_equal((every.astype(np.float32) * np.float32(1 / 32768)).astype(np.float64), every / 32768.0)
+    with pytest.raises(ValueError):
+        zo.cs16_to_iq(raw[:5])
+    from pypanadapter_b200 import synth
+    x = np.array([0.5 - 0.25j, 1.0 + 1.0j, -1.0 - 1.0j])
+    assert np.array_equal(synth.quantise_cs16(x), [16384, -8192, 32767, 32767, -32768, -32768])
+
+
 def test_ema_definition():
     p = np.array([[1.0, 4.0], [3.0, 0.0], [1.0, 1.0]])
     out = zo.ema_rows_db20(p, 0.3)
