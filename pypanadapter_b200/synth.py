@@ -5,7 +5,7 @@ configs.  Nothing here touches the GPU or the oracle.
 """
 from __future__ import annotations
 
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 
 import numpy as np
 
