@@ -47,10 +47,19 @@ def _spectrum_methods(module, engine_of):
         self.win.setWindowTitle('PEPYSCOPE - IS0KYB - N_FFT: %d, BW: %.1f kHz'
                                 % (st.fft_size, bw_hz / 1000. / st.fft_ratio))
         chunk = np.asarray(chunk)
+        # raw wire formats from a source that skips the host conversion (replay.RtlTcpPan's byte
+        # callback, a Soapy CS16 stream): converted on the device; RTL bytes are also flipped there,
+        # as RTLSDRstream.read_callback flips what it emits (S:459-460)
+        if chunk.dtype == np.uint8:
+            dtype, n, flip = "u8", len(chunk) // 2, True
+        elif chunk.dtype == np.int16:
+            dtype, n, flip = "cs16", len(chunk) // 2, False
+        else:
+            dtype, n, flip = "c64", len(chunk), False
         # real chunks (AudioPan, S:712-714) without zoom: welch is one-sided (S:2111)
-        onesided = np.isrealobj(chunk) and chunk.dtype != np.uint8 and not st.fft_ratio > 1
-        eng.configure(fs, st.fft_size, st.fft_ratio, len(chunk), st.fft_tapering, crop=self.N_WIN,
-                      onesided=onesided)
+        onesided = dtype == "c64" and np.isrealobj(chunk) and not st.fft_ratio > 1
+        eng.configure(fs, st.fft_size, st.fft_ratio, n, st.fft_tapering, dtype=dtype, flip=flip,
+                      crop=self.N_WIN, onesided=onesided)
         psd = eng.process(chunk)[0].astype(np.float64)
         wf = getattr(self.waterfall, "__dict__", {}).get("_zfb_wf")
         if isinstance(wf, buffers.Waterfall) and wf.engine is eng:

@@ -388,6 +388,19 @@ def dropin_on_reference_modules(engine):
             mod.ApplicationDisplay.update(fake, x)
             floor = parity.floor_db20(case["fs"], case["window"], case["N"], case["R"] > 1)
             parity.assert_row_parity(got["psd"], parity.golden_rows()[name], floor, "dropin " + name)
+        # raw RTL bytes (rtl_tcp byte callback): converted and flipped on the device == the
+        # reference's update on what RTLSDRstream.read_callback would have emitted (S:459-460)
+        case = gc.case_by_name("cfg1_S256")
+        raw = synth.quantise_u8(0.8 * gc.make_input(case))
+        rh._set_state(mod, case["fs"], case["N"], case["R"], len(raw) // 2 // case["N"], case["window"])
+        got = {}
+        fake = types.SimpleNamespace(N_WIN=case["n_win"], win=rh._Anything(), spectrum_plot=rh._Anything(),
+                                     waterfall=types.SimpleNamespace(
+                                         image_update=lambda psd: got.__setitem__("psd", psd.copy())))
+        mod.ApplicationDisplay.update(fake, raw)
+        want = zo.zoom_psd(raw, case["fs"], case["N"], case["R"], case["window"], crop=case["n_win"], flip=True)
+        parity.assert_row_parity(got["psd"], want, parity.floor_db20(case["fs"], case["window"], case["N"], True),
+                                 "dropin raw u8")
         case = gc.ZOOMFFT_CASES[0]
         x = gc.make_input(case)
         rh._set_state(mod, case["fs"], case["N"], case["R"], len(x) // case["N"], "hamming")
