@@ -39,6 +39,7 @@ struct DecimConst {
     float zi[NSEC];                      // steady state of the all-pole cascade per unit scaled input
     float Mp[JTERMS][NSTATE][NSTATE];    // Mp[j] = (state transition over BLK)^j
     float Mp32[JTERMS32][NSTATE][NSTATE];// same over 32 samples (|M32^10| = 3e-9)
+    float bc[9];                         // numerator of the causal half G(z) of H(z)H(1/z) (zfb_iirstream.cuh)
 };
 
 // per-channel software-LO tables of the channel-batched launches

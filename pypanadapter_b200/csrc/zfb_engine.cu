@@ -25,6 +25,7 @@
 #include "zfb_welch.cuh"
 #include "zfb_bigfft.cuh"
 #include "zfb_firchain.cuh"
+#include "zfb_iirstream.cuh"
 #include "zfb_image.cuh"
 
 using namespace zfb;
@@ -60,6 +61,8 @@ struct zfb_engine {
     int strips_async = 1;                        // zfb_set_option("strips_async")
     int ring_append = 1;                         // zfb_set_option("ring_append"): processed rows enter the ring
     int late_mix = 1;                            // zfb_set_option("late_mix"): FIR chain may mix at its output
+    int iir_stream = 1;                          // zfb_set_option("iir_stream"): streaming last stage of mode fast
+    int iir_S = 1024, iir_Wm = 256;              // zfb_set_option("iir_stream_len" / "iir_stream_warm")
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
     bool slot_busy[2] = {false, false};
 
@@ -306,6 +309,50 @@ void build_decim_const(DecimConst &dc) {
             mat_mul(M, P, P);
         }
     }
+    // Partial fractions of the zero-phase response (zfb_iirstream.cuh):
+    // H(z)H(1/z) = G(z) + G(1/z), G(z) = Bc(z) / prod A_k(z).  G's impulse response is the
+    // autocorrelation of H's (halved at lag 0); multiplying by the denominator leaves Bc.
+    {
+        const int n = 8192;                               // 0.935^8192: far below double precision
+        std::vector<double> h((size_t)n, 0.0);
+        {
+            double w1[NSEC] = {0}, w2[NSEC] = {0};
+            for (int i = 0; i < n; ++i) {
+                double v = (i == 0) ? 1.0 : 0.0;
+                for (int k = 0; k < NSEC; ++k) {          // direct form II section of the sos
+                    const double w = v - sos[k][4] * w1[k] - sos[k][5] * w2[k];
+                    v = sos[k][0] * w + sos[k][1] * w1[k] + sos[k][2] * w2[k];
+                    w2[k] = w1[k];
+                    w1[k] = w;
+                }
+                h[(size_t)i] = v;
+            }
+        }
+        double gimp[9];
+        for (int lag = 0; lag < 9; ++lag) {
+            double acc = 0.0;
+            for (int i = 0; i + lag < n; ++i) acc += h[(size_t)i] * h[(size_t)(i + lag)];
+            gimp[lag] = acc;
+        }
+        gimp[0] *= 0.5;
+        double A[2 * NSEC + 1] = {1.0};
+        int deg = 0;
+        for (int k = 0; k < NSEC; ++k) {
+            double nxt[2 * NSEC + 1] = {0};
+            for (int i = 0; i <= deg; ++i) {
+                nxt[i] += A[i];
+                nxt[i + 1] += A[i] * a1[k];
+                nxt[i + 2] += A[i] * a2[k];
+            }
+            deg += 2;
+            memcpy(A, nxt, sizeof A);
+        }
+        for (int i = 0; i < 9; ++i) {
+            double acc = 0.0;
+            for (int k = 0; k <= i; ++k) acc += gimp[k] * A[i - k];
+            dc.bc[i] = (float)acc;
+        }
+    }
 }
 
 // in-place radix-2 FFT in double (host; window spectra only)
@@ -331,6 +378,9 @@ void host_fft(std::vector<double> &re, std::vector<double> &im) {
         }
     }
 }
+
+// engine-owned intermediates: frames start on 32-byte boundaries (bulk copies need 16)
+long long stride4(long long n) { return (n + 3) & ~3LL; }
 
 int ilog2_floor(long long v) {
     int l = -1;
@@ -439,6 +489,7 @@ ChainFn0 chain_lookup_fn(int kind) {
 }
 
 template <int KIND> int fir_run_setup_kind(zfb_engine *e);
+constexpr int kIirNS = 3, kIirNO = 3;      // x pieces / output rows in flight per lane (zfb_iirstream.cuh)
 
 int setup_device_once(zfb_engine *e) {
     DecimConst dc;
@@ -468,6 +519,8 @@ int setup_device_once(zfb_engine *e) {
                                (int)strip_smem()));
     for (int kind = 0; kind < 3; ++kind)
         CK(e, cudaFuncSetAttribute(chain_lookup_fn(kind), cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    CK(e, cudaFuncSetAttribute((iir_stream_kernel<kIirNS, kIirNO>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)IirStreamShape<kIirNS, kIirNO>::SMEM));
     int rc = fir_run_setup_kind<KIND_C64_RAW>(e);
     if (rc == ZFB_OK) rc = fir_run_setup_kind<KIND_U8_RAW>(e);
     if (rc == ZFB_OK) rc = fir_run_setup_kind<KIND_C64_MID>(e);
@@ -526,7 +579,7 @@ int fast_chain_sizes(int ne, int sizes[4]) {
 void mid_lengths(const zfb_engine *e, bool fast, long long need[2]) {
     need[0] = need[1] = 0;
     int b = 0;
-    auto put = [&](long long len) { if (len > need[b]) need[b] = len; b ^= 1; };
+    auto put = [&](long long len) { len = stride4(len); if (len > need[b]) need[b] = len; b ^= 1; };
     const int k = e->nstages;
     if (fast) {
         int sizes[4];
@@ -667,6 +720,12 @@ ChainFn chain_lookup(int kind) {
     }
 }
 
+// streaming IIR stage: one warp per CTA, 32 streams per warp
+void launch_iir_stream(zfb_engine *, const IirStreamParams &q, cudaStream_t st) {
+    const unsigned ctas = (unsigned)((q.nstreams + 31) / 32);
+    ZFB_LAUNCH((iir_stream_kernel<kIirNS, kIirNO>), dim3(ctas), dim3(32), (IirStreamShape<kIirNS, kIirNO>::SMEM), st, q);
+}
+
 void launch_stage(zfb_engine *e, int kind, int v, const StageParams &p, unsigned tiles, unsigned ny, int cls) {
     const int nt = v == 0 ? NTHR_BIG : NTHR_SMALL;
     const int pr = prof_begin(e, cls);
@@ -713,7 +772,7 @@ void launch_fused_strips(zfb_engine *e, const void *d_in, int gf, float2 *final_
     for (int s = 0; s < kf; ++s) sp.len[s] = e->strip_len[s0 + s];
     sp.keep = e->fplan.K;
     sp.out = final_out;
-    sp.out_stride = e->len[k];
+    sp.out_stride = stride4(e->len[k]);
     sp.ndec = e->len[k];
     const int pr = prof_begin(e, 15, st);
     const dim3 grid(2, (unsigned)gf);
@@ -774,7 +833,7 @@ cudaError_t run_decimation_fast(zfb_engine *e, const void *d_in, int gf, int *ou
         p.in = src;
         p.in_stride = src_stride;
         p.out = (float2 *)e->mid[b].p;
-        p.out_stride = e->len[lvl];
+        p.out_stride = stride4(e->len[lvl]);
         const int pr = prof_begin(e, j == 0 ? 0 : 1);
         if (e->chain_run[j]) {
             FirRunParams rp = e->runp[j];
@@ -810,7 +869,7 @@ cudaError_t run_decimation_fast(zfb_engine *e, const void *d_in, int gf, int *ou
         p.in = src;
         p.in_stride = src_stride;
         p.out = final_out;
-        p.out_stride = e->len[k];
+        p.out_stride = stride4(e->len[k]);
         p.L = e->len[s];
         p.T = e->T[s][v];
         p.flip = 0;
@@ -818,7 +877,29 @@ cudaError_t run_decimation_fast(zfb_engine *e, const void *d_in, int gf, int *ou
         p.Lfull = p.L;
         p.w_lo[0] = p.w_lo[1] = K;
         p.w_hi[0] = p.w_hi[1] = e->len[k] - K;
-        launch_stage(e, KIND_C64_MID, v, p, (unsigned)e->tiles[s][v], (unsigned)gf, k - 1);
+        if (e->iir_stream) {
+            // streaming form (zfb_iirstream.cuh): LTI interior only -- the K outputs at either
+            // end, the only ones the chunk-edge rules of this stage reach, belong to the strips
+            IirStreamParams q{};
+            q.in = (const float2 *)src;
+            q.in_stride = src_stride;
+            q.L = p.L;
+            q.out = final_out;
+            q.out_stride = p.out_stride;
+            q.S = e->iir_S;
+            q.Wm = e->iir_Wm;
+            q.nspf = (p.L + q.S - 1) / q.S;
+            q.n0 = 0;
+            q.m_lo = K;
+            q.m_hi = e->len[k] - K;
+            q.nstreams = (long long)gf * q.nspf;
+            const int pr = prof_begin(e, k - 1);
+            launch_iir_stream(e, q, st);
+            prof_end(e, pr);
+            e->counters[2] += 1;
+        } else {
+            launch_stage(e, KIND_C64_MID, v, p, (unsigned)e->tiles[s][v], (unsigned)gf, k - 1);
+        }
     }
     *out_buf = b_final;
     if (async_strips) return cudaStreamWaitEvent(st, e->ev_join, 0);
@@ -892,7 +973,7 @@ int run_group(zfb_engine *e, const void *d_in, int gf, float *d_rows) {
         CK(e, run_decimation_fast(e, d_in, gf, &ob));
         e->final_buf = ob;
         src = e->mid[ob].p;
-        src_stride = e->len[e->nstages];
+        src_stride = stride4(e->len[e->nstages]);
         kind = KIND_C64_MID;
     } else
     for (int s = 0; s < e->nstages; ++s) {
@@ -904,7 +985,7 @@ int run_group(zfb_engine *e, const void *d_in, int gf, float *d_rows) {
         const int nt = v == 0 ? NTHR_BIG : NTHR_SMALL;
         StageParams p = e->sp0[v];        // LO tables only matter for stage 0
         float2 *out = (float2 *)e->mid[s & 1].p;
-        const long long out_stride = e->len[s + 1];
+        const long long out_stride = stride4(e->len[s + 1]);
         p.in = src;
         p.out = out;
         p.in_stride = src_stride;
@@ -1596,6 +1677,22 @@ int zfb_set_option(zfb_engine *e, const char *name, long long value) {
     if (strcmp(name, "late_mix") == 0) {
         e->late_mix = value ? 1 : 0;
         e->configured = false;                   // replanned by the next zfb_configure
+        return ZFB_OK;
+    }
+    if (strcmp(name, "iir_stream") == 0) {
+        e->iir_stream = value ? 1 : 0;
+        return ZFB_OK;
+    }
+    if (strcmp(name, "iir_stream_len") == 0) {
+        if (value < IS_CH || value > (1 << 20) || value % IS_CH)
+            return fail(e, ZFB_EINVAL, "iir_stream_len must be a positive multiple of %d", IS_CH);
+        e->iir_S = (int)value;
+        return ZFB_OK;
+    }
+    if (strcmp(name, "iir_stream_warm") == 0) {
+        if (value < IS_CH || value > 4096 || value % IS_CH)
+            return fail(e, ZFB_EINVAL, "iir_stream_warm must be a multiple of %d in [%d, 4096]", IS_CH, IS_CH);
+        e->iir_Wm = (int)value;
         return ZFB_OK;
     }
     if (strcmp(name, "ring_append") == 0) {
