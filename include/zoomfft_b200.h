@@ -191,7 +191,17 @@ int  zfb_debug_read_decimated(zfb_engine *e, float *h_out_iq, int max_samples);
 
 /* ---- device-resident waterfall ring (replaces Waterfall.img_array,
  *      S:1631,1651-1652: rows stay on the device until displayed) -------- */
-int  zfb_ring_configure(zfb_engine *e, int rows);      /* default 256 rows  */
+int  zfb_ring_configure(zfb_engine *e, int rows);      /* default 256 rows; the ring's width
+                                                         * follows the configured row_width */
+/* A ring with a width of its own, independent of what is configured (usable before
+ * the first zfb_configure): the reference's Waterfall takes rows of ANY width and
+ * re-initialises its image when the width changes (S:1638-1643) -- e.g. the blank
+ * np.zeros(fft_size) row PSD publishes before the first real one (T:1490, T:2140-2148),
+ * or the stale-width row right after a zoom click.  The ring starts empty.  Rows the
+ * engine computes enter such a ring only while row_width == width; zfb_ring_push_rows,
+ * zfb_read_rows, zfb_ring_image and zfb_ring_quantiles work on `width` columns. */
+int  zfb_ring_configure_width(zfb_engine *e, int rows, int width);
+int  zfb_ring_width(const zfb_engine *e);              /* columns of the ring, 0: none yet */
 int64_t zfb_ring_rows_written(const zfb_engine *e);    /* monotone counter  */
 /* copy `nrows` rows ending `age` rows before the newest one to host
  * (age 0 = newest); blocks only until those rows are complete. */

@@ -92,6 +92,8 @@ SYMBOLS = {
     "zfb_synchronize": (C.c_int, [_P]),
     "zfb_debug_read_decimated": (C.c_int, [_P, _P, C.c_int]),
     "zfb_ring_configure": (C.c_int, [_P, C.c_int]),
+    "zfb_ring_configure_width": (C.c_int, [_P, C.c_int, C.c_int]),
+    "zfb_ring_width": (C.c_int, [_P]),
     "zfb_ring_rows_written": (C.c_int64, [_P]),
     "zfb_read_rows": (C.c_int, [_P, C.c_int, C.c_int, _P]),
     "zfb_ring_push_rows": (C.c_int, [_P, _P, C.c_int]),

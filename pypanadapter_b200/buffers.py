@@ -22,6 +22,7 @@ from __future__ import annotations
 
 import threading
 import time
+import weakref
 
 import numpy as np
 
@@ -56,6 +57,7 @@ class Data:
         self.wire = None
         self.real = False
         self.data = None
+        self._detached = False           # True once another Data has taken over the engine's ring
         self.size = self.real_size = self.total_size = 0
         # event-driven hand-off for a GPU consumer: add() raises the flag when
         # `ready_size` samples have arrived since the last take, PSD.run(event_driven=True)
@@ -65,11 +67,30 @@ class Data:
 
     # -- allocation (T:1413-1431) -------------------------------------------
     def _new(self, wire, real):
+        # An engine owns ONE pinned sample ring; creating it again frees the previous one
+        # (the reference re-creates Data when its main loop restarts ApplicationDisplay,
+        # T:2509-2543).  The previous owner is detached first: its `data` becomes a private
+        # array, so a late add() from an old reader thread never writes freed pinned memory.
+        prev_ref = getattr(self.engine, "_samples_owner", None)
+        prev = prev_ref() if prev_ref is not None else None
+        if prev is not None and prev is not self:
+            prev._detach()
         self.lock.lock()
         self.wire = wire
         self.real = real
         self.data = self.engine.samples_create(self.max_size, wire)   # zero-filled, pinned
+        self._detached = False
+        self.engine._samples_owner = weakref.ref(self)
         return self.new_common()
+
+    def _detach(self):
+        self.lock.lock()
+        try:
+            if self.data is not None and not self._detached:
+                self.data = np.array(self.data)                # private copy, ordinary memory
+            self._detached = True
+        finally:
+            self.lock.unlock()
 
     def new_real(self):
         """Real samples (AudioPan) are stored as complex64 with zero imaginary part."""
@@ -118,9 +139,11 @@ class Data:
                 # the reference fails here too (broadcast error at T:1447)
                 raise ValueError("could not broadcast input array from shape (%d,) into shape (%d,)"
                                  % (length, self.max_size - self.size))
-            self.engine.samples_begin_write(self.size, length)
+            if not self._detached:
+                self.engine.samples_begin_write(self.size, length)
             np.copyto(self.data[self.size * per:new_size * per], chunk, casting="unsafe")
-            self.engine.samples_commit(self.size, length)      # async H2D of this chunk
+            if not self._detached:
+                self.engine.samples_commit(self.size, length)  # async H2D of this chunk
             self.size = new_size
             self.real_size = max(self.real_size, self.size)
             self.total_size += length
@@ -214,7 +237,7 @@ class PSD:
         size = d.real_size
         row = None
         try:
-            if size >= st.fft_size:                            # T:1522
+            if size >= st.fft_size and not getattr(d, "_detached", False):   # T:1522
                 # enqueue under the lock: the kernels read the device mirror the
                 # producer has just finished filling; afterwards it moves on to
                 # the other mirror, so nothing is overwritten under the kernels
@@ -257,7 +280,10 @@ class Waterfall:
     def init_image(self):                                      # S:1625-1635
         self.rows_seen = 0
         self._pending_engine_rows = 0    # a resized ring starts empty: the row in hand is pushed
-        self.engine.ring_configure(max(4, self.fftwidth // 4))
+        # the ring is the waterfall's own, `fftwidth` wide whatever the engine computes next
+        # (the reference takes rows of any width: the blank np.zeros(fft_size) of T:1490 before
+        # the first real row, the stale width right after a zoom click)
+        self.engine.ring_configure(max(4, self.fftwidth // 4), self.fftwidth)
 
     def note_engine_rows(self, n=1):
         """The engine has just appended ``n`` rows to its ring itself (PSD.update
@@ -266,11 +292,9 @@ class Waterfall:
 
     def image_update(self, psd):                               # S:1638-1664
         fftwidth = np.size(psd)
-        if fftwidth != self.fftwidth:
-            self.fftwidth = fftwidth
+        if fftwidth != self.fftwidth or self.engine.ring_width != fftwidth:
+            self.fftwidth = fftwidth                           # S:1641-1643
             self.init_image()
-        if fftwidth != self.engine.row_width:
-            raise ValueError("row width %d does not match the engine's %d" % (fftwidth, self.engine.row_width))
         for x in (0, fftwidth // 2, fftwidth - 1):             # grid, in place like the reference
             psd[x] = 0
         if self._pending_engine_rows > 0:

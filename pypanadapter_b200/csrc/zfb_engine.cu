@@ -90,6 +90,10 @@ struct zfb_engine {
     float *h_rows = nullptr;
     size_t h_rows_cap = 0;
     int ring_rows = 256, ring_rows_req = 256, ring_W = 0;
+    int ring_user_W = 0;               // zfb_ring_configure_width: the ring keeps this width whatever is configured
+    // geometry of the last successful configure (ring / EMA validity): W, N, R, onesided
+    bool geom_valid = false;
+    int geom[4] = {0, 0, 0, 0};
     int64_t ring_written = 0;
     int last_group_frames = 0;
     bool thr_valid = false;            // img_thr holds the level thresholds of thr_levels
@@ -1154,7 +1158,10 @@ int run_group(zfb_engine *e, const void *d_in, int gf, float *d_rows) {
     f.ema_state = (float *)e->ema.p;
     f.ema_have = e->ema_have ? 1 : 0;
     f.rows = d_rows;
-    f.ring = e->ring_append ? (float *)e->ring.p : nullptr;
+    // rows enter the ring when it has their width; channel-batched launches (rows of different
+    // receivers) never do
+    const bool to_ring = e->ring_append && e->ring.p && e->ring_W == e->W && e->cur_nch == 0;
+    f.ring = to_ring ? (float *)e->ring.p : nullptr;
     f.ring_pos = (long long)(e->ring_written % e->ring_rows);
     f.ring_rows = e->ring_rows;
     f.chan_frames = e->cur_nch > 0 ? e->cur_chan_frames : 0;
@@ -1170,7 +1177,7 @@ int run_group(zfb_engine *e, const void *d_in, int gf, float *d_rows) {
     e->counters[2] += 1;
     prof_end(e, prf);
     CK(e, cudaGetLastError());
-    if (e->ring_append) e->ring_written += gf;
+    if (to_ring) e->ring_written += gf;
     e->last_group_frames = gf;
     e->counters[0] += (uint64_t)gf;
     e->counters[1] += (uint64_t)gf * (uint64_t)c.frame_len;
@@ -1471,10 +1478,14 @@ int zfb_configure(zfb_engine *e, const zfb_config *cfg) {
         return fail(e, ZFB_EINVAL, "fft_size %d needs a decimated chunk of at least fft_size samples (got %d)",
                     N, g.ndec);
 
-    const bool geom_changed = !e->configured || e->W != row_w || e->onesided != onesided ||
-                              e->cfg.fft_size != N || e->cfg.fft_ratio != cfg->fft_ratio;
+    // (re-planning after zfb_set_fast_plan / zfb_set_group / an option does not change the
+    // geometry: the ring and the EMA state survive a change of frame_len alone)
+    const int geom_now[4] = {row_w, N, cfg->fft_ratio, onesided ? 1 : 0};
+    const bool geom_changed = !e->geom_valid || memcmp(geom_now, e->geom, sizeof geom_now) != 0;
     // everything below may replace buffers still in use
     CK(e, cudaStreamSynchronize(e->stream));
+    // the live plan is taken apart from here on: a failure must not leave it half updated
+    e->configured = false;
 
     // window -> float, sum w^2 in double (scale = 1/(fs*sum w^2), scipy:_spectral_py.py 'density')
     std::vector<float> wf((size_t)g.nperseg);
@@ -1588,14 +1599,19 @@ int zfb_configure(zfb_engine *e, const zfb_config *cfg) {
     }
     rc = ensure(e, e->ema, (size_t)e->W * sizeof(float));
     if (rc) return rc;
-    if (geom_changed || e->ring_W != e->W || e->ring_rows != e->ring_rows_req) {
+    if (geom_changed) e->ema_have = false;
+    if (e->ring_user_W == 0 &&
+        (geom_changed || e->ring_W != e->W || e->ring_rows != e->ring_rows_req || !e->ring.p)) {
+        // the ring follows the configured row width (Waterfall.init_image on a new width, S:1641-1643)
+        e->ring_W = 0;
         e->ring_rows = e->ring_rows_req;
         rc = ensure(e, e->ring, (size_t)e->ring_rows * (size_t)e->W * sizeof(float));
         if (rc) return rc;
         e->ring_W = e->W;
         e->ring_written = 0;
-        e->ema_have = false;
     }
+    memcpy(e->geom, geom_now, sizeof geom_now);
+    e->geom_valid = true;
     e->configured = true;
     return ZFB_OK;
 }
@@ -1627,8 +1643,14 @@ int zfb_set_fast_plan(zfb_engine *e, const zfb_fast_plan *plan) {
     for (int j = 0; j <= f.Mc; ++j) f.hc[j] = (float)plan->comp_taps[j];
     f.K = plan->strip;
     f.set = true;
+    {
+        const zfb_engine::FastPlan &o = e->fplan;
+        if (o.set && o.ne == f.ne && o.Mc == f.Mc && o.K == f.K && memcmp(o.M, f.M, sizeof f.M) == 0 &&
+            memcmp(o.h, f.h, sizeof f.h) == 0 && memcmp(o.hc, f.hc, sizeof f.hc) == 0)
+            return ZFB_OK;                                    // same plan again: nothing to re-plan
+    }
     e->fplan = f;
-    e->configured = false;
+    e->configured = false;       // re-plan on the next configure (ring and EMA state are kept)
     return ZFB_OK;
 }
 
@@ -1974,20 +1996,42 @@ int zfb_debug_read_decimated(zfb_engine *e, float *h_out_iq, int max_samples) {
     return n;
 }
 
+static int ring_realloc(zfb_engine *e, int rows, int width) {
+    CK(e, cudaSetDevice(e->device));
+    CK(e, cudaStreamSynchronize(e->stream));
+    e->ring_W = 0;                                  // no valid ring while it is replaced
+    int rc = ensure(e, e->ring, (size_t)rows * (size_t)width * sizeof(float));
+    if (rc) return rc;
+    e->ring_rows = rows;
+    e->ring_W = width;
+    e->ring_written = 0;
+    return ZFB_OK;
+}
+
 int zfb_ring_configure(zfb_engine *e, int rows) {
     if (!e) return ZFB_EINVAL;
     std::lock_guard<std::mutex> lk(e->mu);
     if (rows < 1) return fail(e, ZFB_EINVAL, "ring rows must be >= 1");
     e->ring_rows_req = rows;
-    if (e->configured && rows != e->ring_rows) {
-        CK(e, cudaSetDevice(e->device));
-        CK(e, cudaStreamSynchronize(e->stream));
-        e->ring_rows = rows;
-        int rc = ensure(e, e->ring, (size_t)rows * (size_t)e->W * sizeof(float));
-        if (rc) return rc;
-        e->ring_written = 0;
-    }
+    e->ring_user_W = 0;                             // back to following the configured row width
+    if (e->configured && (rows != e->ring_rows || e->ring_W != e->W)) return ring_realloc(e, rows, e->W);
     return ZFB_OK;
+}
+
+int zfb_ring_configure_width(zfb_engine *e, int rows, int width) {
+    if (!e) return ZFB_EINVAL;
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (rows < 1) return fail(e, ZFB_EINVAL, "ring rows must be >= 1");
+    if (width < 1 || width > (1 << 24)) return fail(e, ZFB_EINVAL, "ring width %d out of range", width);
+    e->ring_rows_req = rows;
+    e->ring_user_W = width;
+    return ring_realloc(e, rows, width);            // a (re)configured ring starts empty (S:1625-1635)
+}
+
+int zfb_ring_width(const zfb_engine *e) {
+    if (!e) return ZFB_EINVAL;
+    std::lock_guard<std::mutex> lk(e->mu);
+    return e->ring.p ? e->ring_W : 0;
 }
 
 int64_t zfb_ring_rows_written(const zfb_engine *e) {
@@ -1999,7 +2043,7 @@ int64_t zfb_ring_rows_written(const zfb_engine *e) {
 int zfb_read_rows(zfb_engine *e, int age, int nrows, float *h_out) {
     if (!e) return ZFB_EINVAL;
     std::lock_guard<std::mutex> lk(e->mu);
-    if (!e->configured) return fail(e, ZFB_ESTATE, "engine is not configured");
+    if (!e->ring.p || e->ring_W < 1) return fail(e, ZFB_ESTATE, "no ring (configure the engine or the ring first)");
     if (age < 0 || nrows < 1 || !h_out) return fail(e, ZFB_EINVAL, "read_rows: bad arguments");
     const int64_t have = e->ring_written < e->ring_rows ? e->ring_written : e->ring_rows;
     if ((int64_t)age + nrows > have)
@@ -2007,7 +2051,7 @@ int zfb_read_rows(zfb_engine *e, int age, int nrows, float *h_out) {
                     age + nrows - 1, (long long)have);
     CK(e, cudaSetDevice(e->device));
     const int64_t first = e->ring_written - age - nrows;          // chronological index
-    const size_t rb = (size_t)e->W * sizeof(float);
+    const size_t rb = (size_t)e->ring_W * sizeof(float);
     int done = 0;
     while (done < nrows) {
         const int64_t slot = (first + done) % e->ring_rows;
@@ -2025,10 +2069,10 @@ int zfb_read_rows(zfb_engine *e, int age, int nrows, float *h_out) {
 int zfb_ring_push_rows(zfb_engine *e, const float *h_rows, int nrows) {
     if (!e) return ZFB_EINVAL;
     std::lock_guard<std::mutex> lk(e->mu);
-    if (!e->configured) return fail(e, ZFB_ESTATE, "engine is not configured");
+    if (!e->ring.p || e->ring_W < 1) return fail(e, ZFB_ESTATE, "no ring (configure the engine or the ring first)");
     if (!h_rows || nrows < 0) return fail(e, ZFB_EINVAL, "push_rows: bad arguments");
     CK(e, cudaSetDevice(e->device));
-    const size_t rb = (size_t)e->W * sizeof(float);
+    const size_t rb = (size_t)e->ring_W * sizeof(float);
     for (int i = 0; i < nrows; ++i) {
         const int64_t slot = e->ring_written % e->ring_rows;
         CK(e, cudaMemcpyAsync((char *)e->ring.p + (size_t)slot * rb, (const char *)h_rows + (size_t)i * rb, rb,
@@ -2042,7 +2086,7 @@ int zfb_ring_push_rows(zfb_engine *e, const float *h_rows, int nrows) {
 
 // ---- waterfall image and autolevel on the device (zfb_image.cuh) -----------
 static int image_params(zfb_engine *e, int height, int scroll, int64_t rows_seen, ImageParams &p) {
-    if (!e->configured) return fail(e, ZFB_ESTATE, "engine is not configured");
+    if (!e->ring.p || e->ring_W < 1) return fail(e, ZFB_ESTATE, "no ring (configure the engine or the ring first)");
     if (height < 1 || rows_seen < 0) return fail(e, ZFB_EINVAL, "waterfall image: bad height / rows_seen");
     int64_t have = rows_seen;
     if (have > height) have = height;
@@ -2051,12 +2095,12 @@ static int image_params(zfb_engine *e, int height, int scroll, int64_t rows_seen
     p.ring = (const float *)e->ring.p;
     p.ring_rows = e->ring_rows;
     p.written = e->ring_written;
-    p.W = e->W;
+    p.W = e->ring_W;
     p.H = height;
     p.have = (int)have;
     p.nseen = (int)(rows_seen > (1 << 20) ? (1 << 20) : rows_seen);
     p.scroll = scroll;
-    p.tick_step = e->W / 10;
+    p.tick_step = e->ring_W / 10;
     p.newest_slot = (int)((e->ring_written + (int64_t)e->ring_rows - 1) % e->ring_rows);
     p.thr = nullptr;
     p.fscale = 1.f;
@@ -2116,7 +2160,7 @@ int zfb_ring_image(zfb_engine *e, int height, int scroll, int64_t rows_seen, int
     if (kind == ZFB_IMAGE_RGBA && !lut_rgba) return fail(e, ZFB_EINVAL, "waterfall image: RGBA needs a 256-entry table");
     CK(e, cudaSetDevice(e->device));
     cudaStream_t st = e->stream;
-    const size_t px = (size_t)height * (size_t)e->W;
+    const size_t px = (size_t)height * (size_t)e->ring_W;
     const size_t bytes = px * (kind == ZFB_IMAGE_U8 ? 1 : 4);
     if (kind != ZFB_IMAGE_F32) {
         if (!e->thr_valid || e->thr_levels[0] != minlev || e->thr_levels[1] != maxlev) {
@@ -2154,7 +2198,7 @@ int zfb_ring_image(zfb_engine *e, int height, int scroll, int64_t rows_seen, int
         p.out = e->img_out.p;
     }
     const int per_cta = IMG_NT * IMG_U * 4;
-    const dim3 grid((unsigned)((e->W + per_cta - 1) / per_cta), (unsigned)height);
+    const dim3 grid((unsigned)((e->ring_W + per_cta - 1) / per_cta), (unsigned)height);
     const int pr = prof_begin(e, 19);
     if (kind == ZFB_IMAGE_F32) ZFB_LAUNCH(wf_image_kernel<IMG_F32>, grid, dim3(256), 0, st, p);
     else if (kind == ZFB_IMAGE_U8) ZFB_LAUNCH(wf_image_kernel<IMG_U8>, grid, dim3(256), 0, st, p);

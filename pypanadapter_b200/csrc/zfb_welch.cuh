@@ -395,7 +395,10 @@ __device__ __forceinline__ void emit_row_value(const FinalizeParams &p, int f, i
                                         : (size_t)f * p.W;
         p.rows[at + col] = out;
     }
-    if (p.ring) p.ring[(size_t)((p.ring_pos + f) % p.ring_rows) * p.W + col] = out;
+    // only the newest ring_rows frames of a launch enter the ring: older ones would share
+    // a slot with them (unordered writes from different threads)
+    if (p.ring && f >= p.nframes - p.ring_rows)
+        p.ring[(size_t)((p.ring_pos + f) % p.ring_rows) * p.W + col] = out;
 }
 
 // column of the pow row that feeds row column `col`, and the one-sided factor

@@ -80,7 +80,7 @@ def _thread_psd_update(module, engine_of):
         size = d.real_size
         row = None
         try:
-            if size >= st.fft_size:
+            if size >= st.fft_size and not getattr(d, "_detached", False):
                 if isinstance(d, buffers.Data):
                     eng.configure(st.panadapter.SampleRate, st.fft_size, st.fft_ratio, size,
                                   st.fft_tapering, dtype=d.wire, crop="thread",

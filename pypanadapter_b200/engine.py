@@ -185,6 +185,7 @@ class ZoomPSD:
         cfg.f_demod = float(f_demod)
         cfg.ema_alpha = -1.0 if ema_alpha is None else float(ema_alpha)
         cfg.window = w.ctypes.data_as(C.POINTER(C.c_double))
+        self._key = None               # a failed zfb_configure leaves the engine unconfigured
         self._check(self._lib.zfb_configure(self._h, C.byref(cfg)), "zfb_configure")
         self._key = key
         self.row_width = int(W) // 2 + 1 if onesided else int(W)
@@ -194,6 +195,10 @@ class ZoomPSD:
         return self
 
     def _set_fast_plan(self, ratio: int):
+        # one plan per zoom ratio: a change of frame_len alone (PSD.update hands over whatever
+        # the ring holds, T:1516-1520) must not touch the engine's plan, ring or EMA state
+        if getattr(self, "_fast_ratio", None) == ratio:
+            return
         from . import fastdesign
         plan = fastdesign.design(ratio, decim_sos(self._lib))
         fp = _lib.ZfbFastPlan()
@@ -208,6 +213,7 @@ class ZoomPSD:
         fp.strip = plan["strip"]
         self._check(self._lib.zfb_set_fast_plan(self._h, C.byref(fp)), "zfb_set_fast_plan")
         self.fast_plan = plan
+        self._fast_ratio = ratio
 
     @property
     def fast_active(self) -> bool:
@@ -228,8 +234,20 @@ class ZoomPSD:
     def reset_ema(self):
         self._check(self._lib.zfb_reset_ema(self._h), "zfb_reset_ema")
 
-    def ring_configure(self, rows: int):
-        self._check(self._lib.zfb_ring_configure(self._h, int(rows)), "zfb_ring_configure")
+    def ring_configure(self, rows: int, width: int | None = None):
+        """``width=None``: the ring follows the configured row width.  With a
+        ``width`` the ring is the waterfall's own (S:1638-1643: any row width is
+        taken, a new width re-initialises the image) and works before the
+        first ``configure``."""
+        if width is None:
+            self._check(self._lib.zfb_ring_configure(self._h, int(rows)), "zfb_ring_configure")
+        else:
+            self._check(self._lib.zfb_ring_configure_width(self._h, int(rows), int(width)),
+                        "zfb_ring_configure_width")
+
+    @property
+    def ring_width(self) -> int:
+        return int(self._lib.zfb_ring_width(self._h))
 
     # -- hot path --------------------------------------------------------
     def _as_wire(self, frames):
@@ -318,7 +336,7 @@ class ZoomPSD:
         return int(self._lib.zfb_ring_rows_written(self._h))
 
     def read_rows(self, nrows: int = 1, age: int = 0) -> np.ndarray:
-        out = np.empty((int(nrows), self.row_width), dtype=np.float32)
+        out = np.empty((int(nrows), self.ring_width or self.row_width), dtype=np.float32)
         self._check(self._lib.zfb_read_rows(self._h, int(age), int(nrows), C.c_void_p(out.ctypes.data)),
                     "zfb_read_rows")
         return out
@@ -338,8 +356,8 @@ class ZoomPSD:
         r = np.ascontiguousarray(rows, dtype=np.float32)
         if r.ndim == 1:
             r = r.reshape(1, -1)
-        if r.shape[1] != self.row_width:
-            raise ValueError("rows must be %d wide" % self.row_width)
+        if r.shape[1] != (self.ring_width or self.row_width):
+            raise ValueError("rows must be %d wide" % (self.ring_width or self.row_width))
         self._check(self._lib.zfb_ring_push_rows(self._h, C.c_void_p(r.ctypes.data), r.shape[0]),
                     "zfb_ring_push_rows")
 
@@ -351,7 +369,7 @@ class ZoomPSD:
         ring: ``kind`` 'f32' = img_array, 'u8' = colour indices for ``levels``
         (minlev, maxlev), 'rgba' = ``lut[index]`` (lut: (256, 4) uint8)."""
         code = {"f32": _lib.ZFB_IMAGE_F32, "u8": _lib.ZFB_IMAGE_U8, "rgba": _lib.ZFB_IMAGE_RGBA}[kind]
-        h, w = int(height), self.row_width
+        h, w = int(height), (self.ring_width or self.row_width)
         lo, hi = (0.0, 1.0) if levels is None else (float(levels[0]), float(levels[1]))
         if kind != "f32" and levels is None:
             raise ValueError("kind %r needs levels=(minlev, maxlev)" % kind)

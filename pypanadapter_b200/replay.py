@@ -109,6 +109,10 @@ class RtlTcpPan:
         self.driver = self
         self._name = "rtl_tcp @%s:%d" % (host, port)
         self._command(0x02, int(self.SampleRate))
+        # the connect / greeting timeout must not apply to the sample stream: a source that
+        # pauses longer than it would end the pump silently
+        self._sock.settimeout(None)
+        self.stream_error = None
 
     @property
     def name(self):
@@ -141,29 +145,44 @@ class RtlTcpPan:
 
     def stream_open(self):
         import threading
-        self._run = True
+        stop = threading.Event()                      # one per pump: a late pump never restarts
+        self._stop = stop
         emit = getattr(self.update_signal, "emit", self.update_signal)
+        chunk_bytes = 2 * self.chunk_size
 
         def pump():
             try:
-                while self._run:
-                    raw = np.frombuffer(self._recv_exact(2 * self.chunk_size), dtype=np.uint8)
+                while not stop.is_set():
+                    raw = np.frombuffer(self._recv_exact(chunk_bytes), dtype=np.uint8)
+                    if stop.is_set():
+                        break
                     if self.complex_callback:
                         iq = raw.astype(np.float64).view(np.complex128) / 127.5 - (1 + 1j)
                         emit(np.flip(iq))
                     else:
                         emit(raw)
-            except (EOFError, OSError):
-                pass
+            except (EOFError, OSError) as exc:
+                if not stop.is_set():
+                    self.stream_error = exc           # the source went away: visible to the owner
         t = threading.Thread(target=pump, daemon=True)
         t.start()
         return t
 
     def stream_close(self):
-        self._run = False
+        """Stops the pump for good: the socket's read side is shut down so that a
+        pump blocked in recv returns at once -- two pumps must never read the same
+        socket (a partial chunk taken by the old one would swap I and Q for the new)."""
+        import socket
+        stop = getattr(self, "_stop", None)
+        if stop is not None:
+            stop.set()
         t, self.stream = self.stream, None
         if t is not None and t.is_alive():
-            t.join(timeout=2.0)
+            try:
+                self._sock.shutdown(socket.SHUT_RD)
+            except OSError:
+                pass
+            t.join()
 
     def Close(self):
         self.stream_close()

@@ -505,6 +505,151 @@ def dropin_on_reference_modules(engine):
     assert engine.rows_written == n0 + 1                      # uninstall restored ring_append
 
 
+def dropin_on_standin_modules(engine):
+    """dropin.install on stand-in modules with the reference's class / method
+    names and EMPTY hot-path bodies (tests/standin_pan.py) -- runs wherever the
+    library runs, the GPU box included: every row below comes out of the engine
+    and is held to the reference-recorded goldens."""
+    from pypanadapter_b200 import dropin
+    from tests import standin_pan as sp
+    # ---- spectrum variant: ApplicationDisplay.update(chunk), zoomfft, Waterfall ----
+    mod = sp.make("spectrum")
+    saved = dropin.install(mod, engine=engine)
+    try:
+        for name in ("cfg1_S1024", "cfg1_S256", "defaults_S"):
+            case = gc.case_by_name(name)
+            x = gc.make_input(case)
+            sp.set_state(mod, case["fs"], case["N"], case["R"], len(x) // case["N"], case["window"])
+            app = mod.ApplicationDisplay(case["n_win"])
+            got = {}
+            app.waterfall = types.SimpleNamespace(image_update=lambda psd: got.__setitem__("psd", psd.copy()))
+            app.update(x)
+            floor = parity.floor_db20(case["fs"], case["window"], case["N"], case["R"] > 1)
+            parity.assert_row_parity(got["psd"], parity.golden_rows()[name], floor, "stand-in dropin " + name)
+            assert "N_FFT: %d" % case["N"] in app.win.calls["setWindowTitle"][0][0]          # S:2105-2106
+            assert app.spectrum_plot.calls["setData"][0][0].shape == (case["n_win"],)        # S:2128-2130
+        case = gc.ZOOMFFT_CASES[0]
+        x = gc.make_input(case)
+        sp.set_state(mod, case["fs"], case["N"], case["R"], len(x) // case["N"], "hamming")
+        z = mod.ApplicationDisplay(256).zoomfft(x, case["R"])
+        ref = np.load(os.path.join(parity.GOLDEN_DIR, "zoomfft.npz"))[case["name"]]
+        assert np.abs(z - ref).max() < 2e-5 * np.abs(ref).max()
+        # update(chunk) -> Waterfall.image_update: the image the reference would hold
+        case = gc.case_by_name("cfg1_S256")
+        app = mod.ApplicationDisplay(256)
+        ref_img = None
+        for i in range(3):
+            x = synth.make_frame(synth.CFG1, i)
+            sp.set_state(mod, case["fs"], case["N"], case["R"], len(x) // case["N"], case["window"])
+            app.update(x)
+            row = engine.read_rows(1)[0].astype(np.float64)
+            ref_img = zo.waterfall_update(ref_img, row.copy(), 1)
+        assert np.array_equal(app.waterfall.img_array, ref_img)
+        assert np.array_equal(app.waterfall.shown["img"], zo.waterfall_indices(ref_img, -220, -120).T)
+    finally:
+        dropin.uninstall(mod, saved)
+    # ---- thread variant: Data, PSD.update, and the GUI timer (T:2140-2157) ----
+    mod = sp.make("thread")
+    saved = dropin.install(mod, engine=engine)
+    try:
+        case = gc.case_by_name("cfg1_T")
+        x = gc.make_input(case)
+        st = sp.set_state(mod, case["fs"], case["N"], case["R"], 1, case["window"])
+        d = mod.Data()
+        assert isinstance(d, buffers_Data())
+        d.new_complex()
+        psd = mod.PSD(d)
+        app = mod.ApplicationDisplay(psd)
+        # the timer fires before any row exists: the blank np.zeros(fft_size) row (T:1490) is shown
+        app.update()
+        assert app.waterfall.fftwidth == case["N"] and app.waterfall.shown["img"].shape == (case["N"], case["N"] // 4)
+        blank = zo.waterfall_update(None, np.zeros(case["N"]), 1)
+        assert np.array_equal(app.waterfall.img_array, blank)
+
+        def feed():
+            for i in range(0, len(x), d.chunk_size):
+                d.add(x[i:i + d.chunk_size])
+        feed()
+        psd.update()
+        floor = parity.floor_db20(case["fs"], case["window"], case["N"], True)
+        parity.assert_row_parity(psd.psd, parity.golden_rows()["cfg1_T"], floor, "stand-in PSD.update")
+        app.update()                                          # new width: the image starts over (S:1641-1643)
+        W = 2 * int(.5 * case["N"] / case["R"])
+        assert app.waterfall.fftwidth == W and app.waterfall.shown["img"].shape == (W, W // 4)
+        img = zo.waterfall_update(None, np.array(psd.psd, dtype=np.float32).astype(np.float64), 1)
+        assert np.array_equal(app.waterfall.img_array, img)
+        # a zoom click (S:2079-2086 makes fft_ratio a float): PSD.update has re-planned for the new
+        # width while the timer still shows the row of the old one -- then the new row arrives
+        st.fft_ratio = case["R"] * 2.0
+        feed()
+        stale = np.array(psd.psd, copy=True)
+        engine.configure(case["fs"], case["N"], st.fft_ratio, len(x), case["window"], crop="thread")
+        app.update()                                          # stale 256-wide row, engine now at 128
+        img = zo.waterfall_update(img, np.array(stale, dtype=np.float32).astype(np.float64), 1)
+        assert np.array_equal(app.waterfall.img_array, img)
+        psd.update()
+        assert psd.psd.shape == (W // 2,)
+        app.update()
+        assert app.waterfall.fftwidth == W // 2
+        assert np.array_equal(app.waterfall.img_array,
+                              zo.waterfall_update(None, np.array(psd.psd, dtype=np.float32).astype(np.float64), 1))
+        # a second Data on the same engine takes the pinned ring over; the first one goes on
+        # working on private memory (late add() of an old reader thread)
+        d2 = mod.Data()
+        d2.new_complex()
+        assert d._detached and not d2._detached
+        d.add(x[:d.chunk_size])
+        for i in range(0, len(x), d2.chunk_size):
+            d2.add(x[i:i + d2.chunk_size])
+        st.fft_ratio = case["R"]
+        psd2 = mod.PSD(d2)
+        psd2.update()
+        parity.assert_row_parity(psd2.psd, parity.golden_rows()["cfg1_T"], floor, "stand-in PSD.update (2nd Data)")
+    finally:
+        dropin.uninstall(mod, saved)
+
+
+def fast_mode_state_survives_frame_len(engine):
+    """A live stream hands PSD.update a different number of samples every take
+    (T:1516-1520).  In mode fast that must neither restart the EMA nor empty the
+    waterfall ring (zfb_configure keeps both unless W, N, R change)."""
+    fs, N, R = 2.4e6, 1024, 8
+    rows = []
+    engine.ring_configure(16)
+    for i, n in enumerate((N * 24, N * 24 + 512, N * 25, N * 24)):
+        x = gc.tone_noise(n, fs, [(3000.0 + 500 * i, 0.4)], 3e-3, 40 + i, np.complex64)
+        engine.configure(fs, N, R, n, "hamming", crop="thread", ema_alpha=0.3, mode="fast")
+        assert engine.fast_active
+        rows.append(engine.process(x)[0].astype(np.float64))
+    assert engine.rows_written == 4
+    assert np.array_equal(engine.read_rows(4).astype(np.float64), np.array(rows))
+    # the oracle's EMA over the same four frames
+    lin = []
+    for i, n in enumerate((N * 24, N * 24 + 512, N * 25, N * 24)):
+        x = gc.tone_noise(n, fs, [(3000.0 + 500 * i, 0.4)], 3e-3, 40 + i, np.complex64)
+        lin.append(zo.zoom_psd_power(x, fs, N, R, "hamming", crop="thread"))
+    want = zo.ema_rows_db20(np.array(lin), 0.3)
+    floor = parity.floor_db20(fs, "hamming", N, True)
+    for r, w in zip(rows, want):
+        parity.assert_row_parity(r, w, floor, "EMA across frame_len changes")
+    engine.ring_configure(256)
+
+
+def ring_wrap_within_one_launch(engine):
+    """More frames in one launch than the ring has rows: the ring ends up with
+    the NEWEST rows, each row whole (no per-column mix of frames sharing a slot)."""
+    fs, N = 2.4e6, 256
+    n = N * 4
+    frames = np.stack([gc.tone_noise(n, fs, [(1.0e5 * (1 + i % 7), 0.3)], 3e-3, 100 + i, np.complex64)
+                       for i in range(40)])
+    engine.ring_configure(8)
+    engine.configure(fs, N, 1, n, "hann", crop=None)
+    rows = engine.process(frames)
+    assert engine.rows_written == 40
+    assert np.array_equal(engine.read_rows(8), rows[-8:])
+    engine.ring_configure(256)
+
+
 def event_driven_run(engine):
     """PSD.run(event_driven=True): rows appear when enough samples have arrived,
     not on a timer: a producer delivering one frame's worth every

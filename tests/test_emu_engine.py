@@ -160,3 +160,15 @@ def test_reconfigure_stress(emu_engine):
 
 def test_replay_source(emu_engine):
     bs.replay_source_through_plugin_api(emu_engine)
+
+
+def test_dropin_on_standin_modules(emu_engine):
+    bs.dropin_on_standin_modules(emu_engine)
+
+
+def test_fast_state_survives_frame_len(emu_engine):
+    bs.fast_mode_state_survives_frame_len(emu_engine)
+
+
+def test_ring_wrap_within_one_launch(emu_engine):
+    bs.ring_wrap_within_one_launch(emu_engine)

@@ -236,3 +236,15 @@ def test_reconfigure_stress(gpu_engine):
 
 def test_replay_source(gpu_engine):
     bs.replay_source_through_plugin_api(gpu_engine)
+
+
+def test_dropin_on_standin_modules(gpu_engine):
+    bs.dropin_on_standin_modules(gpu_engine)
+
+
+def test_fast_state_survives_frame_len(gpu_engine):
+    bs.fast_mode_state_survives_frame_len(gpu_engine)
+
+
+def test_ring_wrap_within_one_launch(gpu_engine):
+    bs.ring_wrap_within_one_launch(gpu_engine)
