@@ -62,7 +62,16 @@ struct zfb_engine {
     int ring_append = 1;                         // zfb_set_option("ring_append"): processed rows enter the ring
     int late_mix = 1;                            // zfb_set_option("late_mix"): FIR chain may mix at its output
     int iir_stream = 1;                          // zfb_set_option("iir_stream"): streaming last stage of mode fast
-    int iir_S = 1024, iir_Wm = 256;              // zfb_set_option("iir_stream_len" / "iir_stream_warm")
+    int iir_S = 640, iir_Wm = 256;               // zfb_set_option("iir_stream_len" (target) / "iir_stream_warm")
+    // plan of the streaming last stage (zfb_iirstream.cuh), valid while iis.active
+    struct IirStreamPlan {
+        bool active = false;
+        IirStreamParams q{};
+        long long in_stride = 0, out_stride = 0;     // frame strides of its input / output buffers (samples)
+        int tail = 0;                                // samples [L, nspf*S) of every input frame kept at zero
+        TensorMap tm_in, tm_out;
+    } iis;
+    DevBuf strip_out;                            // [group][2][K] edge samples of the strips, patched in afterwards
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
     bool slot_busy[2] = {false, false};
 
@@ -146,6 +155,56 @@ struct zfb_engine {
     bool profiling = false;
     std::vector<ProfRec> prof_used, prof_free;
 };
+
+namespace {
+
+}  // namespace
+
+namespace zfb {
+#ifdef ZFB_EMULATE
+int make_tensor_map(const TensorMapSpec &spec, TensorMap *out) {
+    out->base = (unsigned char *)spec.base;
+    for (int i = 0; i < 4; ++i) {
+        out->dim[i] = spec.dim[i];
+        out->stride[i] = spec.stride[i];
+        out->box[i] = spec.box[i];
+    }
+    out->stride[0] = 8;
+    out->swizzle = spec.swizzle;
+    return 0;
+}
+#else
+int make_tensor_map(const TensorMapSpec &spec, TensorMap *out) {
+    typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                 const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                 CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess || !fn) {
+            cudaGetLastError();
+            return -1;
+        }
+        encode = (EncodeFn)fn;
+    }
+    cuuint64_t dim[4], stride[3];
+    cuuint32_t box[4], estr[4] = {1, 1, 1, 1};
+    for (int i = 0; i < 4; ++i) {
+        dim[i] = spec.dim[i];
+        box[i] = spec.box[i];
+    }
+    for (int i = 0; i < 3; ++i) stride[i] = spec.stride[i + 1];
+    const CUtensorMapSwizzle sw = spec.swizzle == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                  : spec.swizzle == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE;
+    const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, spec.base, dim, stride, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : -1;
+}
+#endif
+}  // namespace zfb
 
 namespace {
 
@@ -579,6 +638,17 @@ int fast_chain_sizes(int ne, int sizes[4]) {
     return done == ne ? n : -1;
 }
 
+// frame strides of mode fast's intermediates: the streaming last stage reads whole streams
+// (its input frames span nspf*S >= L samples) and stores whole streams of results
+long long fast_level_stride(const zfb_engine *e, int lvl) {
+    if (e->iis.active && lvl == e->nstages - 1) return e->iis.in_stride;
+    return stride4(e->len[lvl]);
+}
+long long final_stride(const zfb_engine *e) {
+    if (e->fast_active && e->iis.active) return e->iis.out_stride;
+    return stride4(e->len[e->nstages]);
+}
+
 // capacity (samples per frame) the two ping-pong buffers need in the active mode
 void mid_lengths(const zfb_engine *e, bool fast, long long need[2]) {
     need[0] = need[1] = 0;
@@ -589,8 +659,8 @@ void mid_lengths(const zfb_engine *e, bool fast, long long need[2]) {
         int sizes[4];
         const int n = fast_chain_sizes(k - 1, sizes);
         int lvl = 0;
-        for (int j = 0; j < n; ++j) { lvl += sizes[j]; put(e->len[lvl]); }
-        put(e->len[k]);
+        for (int j = 0; j < n; ++j) { lvl += sizes[j]; put(fast_level_stride(e, lvl)); }
+        put(final_stride(e));
     } else {
         for (int s = 0; s < k; ++s) put(e->len[s + 1]);
     }
@@ -725,9 +795,23 @@ ChainFn chain_lookup(int kind) {
 }
 
 // streaming IIR stage: one warp per CTA, 32 streams per warp
-void launch_iir_stream(zfb_engine *, const IirStreamParams &q, cudaStream_t st) {
-    const unsigned ctas = (unsigned)((q.nstreams + 31) / 32);
-    ZFB_LAUNCH((iir_stream_kernel<kIirNS, kIirNO>), dim3(ctas), dim3(32), (IirStreamShape<kIirNS, kIirNO>::SMEM), st, q);
+void launch_iir_stream(zfb_engine *e, int gf, cudaStream_t st) {
+    const zfb_engine::IirStreamPlan &pl = e->iis;
+    const unsigned ctas = (unsigned)(gf * pl.q.groups);
+    ZFB_LAUNCH((iir_stream_kernel<kIirNS, kIirNO>), dim3(ctas), dim3(32), (IirStreamShape<kIirNS, kIirNO>::SMEM), st,
+               pl.tm_in, pl.tm_out, pl.q);
+}
+
+// the K samples at either end of every decimated chunk, computed by the exact edge strips into
+// strip_out[frame][side][K], overwrite what the streaming last stage left there
+__global__ void __launch_bounds__(256) strip_patch_kernel(const float2 *strip_out, float2 *out, long long out_stride,
+                                                          int ndec, int K, long long total) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int j = (int)(i % (2 * K));
+    const long long f = i / (2 * K);
+    const int m = j < K ? j : ndec - 2 * K + j;
+    out[f * out_stride + m] = strip_out[i];
 }
 
 void launch_stage(zfb_engine *e, int kind, int v, const StageParams &p, unsigned tiles, unsigned ny, int cls) {
@@ -775,9 +859,16 @@ void launch_fused_strips(zfb_engine *e, const void *d_in, int gf, float2 *final_
     sp.nstages = kf;
     for (int s = 0; s < kf; ++s) sp.len[s] = e->strip_len[s0 + s];
     sp.keep = e->fplan.K;
-    sp.out = final_out;
-    sp.out_stride = stride4(e->len[k]);
-    sp.ndec = e->len[k];
+    if (e->iis.active) {
+        // compact [frame][side][K]: patched into the chunks once the streaming last stage is done
+        sp.out = (float2 *)e->strip_out.p;
+        sp.out_stride = 2 * e->fplan.K;
+        sp.ndec = 2 * e->fplan.K;
+    } else {
+        sp.out = final_out;
+        sp.out_stride = final_stride(e);
+        sp.ndec = e->len[k];
+    }
     const int pr = prof_begin(e, 15, st);
     const dim3 grid(2, (unsigned)gf);
     if (e->cur_nch > 0 && s0 == 0) {
@@ -837,7 +928,7 @@ cudaError_t run_decimation_fast(zfb_engine *e, const void *d_in, int gf, int *ou
         p.in = src;
         p.in_stride = src_stride;
         p.out = (float2 *)e->mid[b].p;
-        p.out_stride = stride4(e->len[lvl]);
+        p.out_stride = fast_level_stride(e, lvl);
         const int pr = prof_begin(e, j == 0 ? 0 : 1);
         if (e->chain_run[j]) {
             FirRunParams rp = e->runp[j];
@@ -873,7 +964,7 @@ cudaError_t run_decimation_fast(zfb_engine *e, const void *d_in, int gf, int *ou
         p.in = src;
         p.in_stride = src_stride;
         p.out = final_out;
-        p.out_stride = stride4(e->len[k]);
+        p.out_stride = final_stride(e);
         p.L = e->len[s];
         p.T = e->T[s][v];
         p.flip = 0;
@@ -881,24 +972,17 @@ cudaError_t run_decimation_fast(zfb_engine *e, const void *d_in, int gf, int *ou
         p.Lfull = p.L;
         p.w_lo[0] = p.w_lo[1] = K;
         p.w_hi[0] = p.w_hi[1] = e->len[k] - K;
-        if (e->iir_stream) {
-            // streaming form (zfb_iirstream.cuh): LTI interior only -- the K outputs at either
-            // end, the only ones the chunk-edge rules of this stage reach, belong to the strips
-            IirStreamParams q{};
-            q.in = (const float2 *)src;
-            q.in_stride = src_stride;
-            q.L = p.L;
-            q.out = final_out;
-            q.out_stride = p.out_stride;
-            q.S = e->iir_S;
-            q.Wm = e->iir_Wm;
-            q.nspf = (p.L + q.S - 1) / q.S;
-            q.n0 = 0;
-            q.m_lo = K;
-            q.m_hi = e->len[k] - K;
-            q.nstreams = (long long)gf * q.nspf;
+        if (e->iis.active) {
+            // streaming form (zfb_iirstream.cuh): LTI interior; the K outputs at either end, the
+            // only ones the chunk-edge rules of this stage reach, are patched in from the strips.
+            // The copy engine reads whole streams: keep [L, nspf*S) of every frame at zero.
+            if (e->iis.tail > 0) {
+                cudaError_t me = cudaMemset2DAsync((float2 *)const_cast<void *>(src) + p.L, (size_t)src_stride * sizeof(float2),
+                                                   0, (size_t)e->iis.tail * sizeof(float2), (size_t)gf, st);
+                if (me != cudaSuccess) return me;
+            }
             const int pr = prof_begin(e, k - 1);
-            launch_iir_stream(e, q, st);
+            launch_iir_stream(e, gf, st);
             prof_end(e, pr);
             e->counters[2] += 1;
         } else {
@@ -906,7 +990,18 @@ cudaError_t run_decimation_fast(zfb_engine *e, const void *d_in, int gf, int *ou
         }
     }
     *out_buf = b_final;
-    if (async_strips) return cudaStreamWaitEvent(st, e->ev_join, 0);
+    auto patch = [&]() {
+        if (!e->iis.active) return;
+        const long long total = (long long)gf * 2 * K;
+        ZFB_LAUNCH(strip_patch_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st,
+                   (const float2 *)e->strip_out.p, final_out, final_stride(e), e->len[k], K, total);
+        e->counters[2] += 1;
+    };
+    if (async_strips) {
+        err = cudaStreamWaitEvent(st, e->ev_join, 0);
+        patch();
+        return err;
+    }
 
     // deeper zooms: the first stages' strips are longer than one region and go through the
     // tiled kernel (on the main stream), then the fused tail
@@ -945,6 +1040,7 @@ cudaError_t run_decimation_fast(zfb_engine *e, const void *d_in, int gf, int *ou
                      (unsigned)(2 * gf), 15);
     }
     launch_fused_strips(e, d_in, gf, final_out, st);
+    patch();
     return cudaSuccess;
 }
 
@@ -977,7 +1073,7 @@ int run_group(zfb_engine *e, const void *d_in, int gf, float *d_rows) {
         CK(e, run_decimation_fast(e, d_in, gf, &ob));
         e->final_buf = ob;
         src = e->mid[ob].p;
-        src_stride = stride4(e->len[e->nstages]);
+        src_stride = final_stride(e);
         kind = KIND_C64_MID;
     } else
     for (int s = 0; s < e->nstages; ++s) {
@@ -1279,6 +1375,63 @@ int plan_fast(zfb_engine *e) {
     return ZFB_OK;
 }
 
+// Streaming last stage of mode fast (zfb_iirstream.cuh): every frame's stage input is cut into
+// nspf streams of S samples, 32 consecutive streams per warp.  S and nspf depend on the stage
+// length only -- never on how many frames share a launch -- so a frame's row stays
+// bit-identical whatever batch it is in.
+void plan_iir_stream(zfb_engine *e) {
+    zfb_engine::IirStreamPlan &pl = e->iis;
+    pl.active = false;
+    if (!e->fast_active || !e->iir_stream) return;
+    const int k = e->nstages;
+    const int L = e->len[k - 1];
+    const int Wb = e->iir_Wm / IS_BLK;
+    // whole warps: nspf a multiple of 32 whose streams come closest to the target length
+    int g = (int)((double)L / (32.0 * (double)e->iir_S) + 0.5);
+    if (g < 1) g = 1;
+    int nspf = 32 * g;
+    int S16 = (L + nspf * IS_BLK - 1) / (nspf * IS_BLK);
+    // the warm-up (and the lag block) must fit into the neighbouring stream
+    if (S16 < Wb + 1) return;                 // short frames keep the shared-memory kernel
+    const int S = S16 * IS_BLK;
+    nspf = (L + S - 1) / S;                   // streams actually holding samples
+    pl.q.S16 = S16;
+    pl.q.Wb = Wb;
+    pl.q.nspf = nspf;
+    pl.q.groups = (nspf + 31) / 32;
+    pl.in_stride = stride4((long long)nspf * S);
+    pl.out_stride = stride4((long long)nspf * (S / 2));
+    pl.tail = nspf * S - L;
+    pl.active = true;
+}
+
+// tensor maps over the (now allocated) intermediates, and the strips' patch buffer
+int finish_iir_stream(zfb_engine *e) {
+    zfb_engine::IirStreamPlan &pl = e->iis;
+    const int k = e->nstages;
+    const int b_final = e->nchains & 1;
+    void *in = e->mid[b_final ^ 1].p, *out = e->mid[b_final].p;
+    const unsigned long long S = (unsigned long long)pl.q.S16 * IS_BLK;
+    TensorMapSpec si{};
+    si.base = in;
+    si.dim[0] = IS_BLK; si.dim[1] = (unsigned long long)pl.q.S16; si.dim[2] = (unsigned long long)pl.q.nspf;
+    si.dim[3] = (unsigned long long)e->group;
+    si.stride[0] = 8; si.stride[1] = IS_BLK * 8; si.stride[2] = S * 8; si.stride[3] = (unsigned long long)pl.in_stride * 8;
+    si.box[0] = IS_BLK; si.box[1] = 1; si.box[2] = 32; si.box[3] = 1;
+    si.swizzle = 128;
+    TensorMapSpec so{};
+    so.base = out;
+    so.dim[0] = IS_BLK / 2; so.dim[1] = (unsigned long long)pl.q.S16; so.dim[2] = (unsigned long long)pl.q.nspf;
+    so.dim[3] = (unsigned long long)e->group;
+    so.stride[0] = 8; so.stride[1] = IS_BLK * 4; so.stride[2] = S * 4; so.stride[3] = (unsigned long long)pl.out_stride * 8;
+    so.box[0] = IS_BLK / 2; so.box[1] = 1; so.box[2] = 32; so.box[3] = 1;
+    so.swizzle = 64;
+    if (make_tensor_map(si, &pl.tm_in) != 0 || make_tensor_map(so, &pl.tm_out) != 0)
+        return fail(e, ZFB_ECUDA, "cuTensorMapEncodeTiled failed for the streaming last stage (stage length %d)",
+                    e->len[k - 1]);
+    return ensure(e, e->strip_out, (size_t)e->group * 2 * (size_t)e->fplan.K * sizeof(float2));
+}
+
 // point every LO table of the current plan at software-LO frequency f_demod
 // (zfb_process_channels_*: one configuration, many zoom centres)
 void apply_lo(zfb_engine *e, double f_demod) {
@@ -1408,6 +1561,7 @@ void zfb_destroy(zfb_engine *e) {
     release(e->sbuf[1]);
     release(e->chan_dev);
     release(e->cvt);
+    release(e->strip_out);
     if (e->sr_copied) cudaEventDestroy(e->sr_copied);
     for (int i = 0; i < 2; ++i) if (e->sr_free[i]) cudaEventDestroy(e->sr_free[i]);
     if (e->h_rows) cudaFreeHost(e->h_rows);
@@ -1561,6 +1715,7 @@ int zfb_configure(zfb_engine *e, const zfb_config *cfg) {
         return fail(e, ZFB_ESTATE, "mode FAST needs zfb_set_fast_plan with %d stages (got %d)", g.nstages - 1,
                     e->fplan.set ? e->fplan.ne : -1);
     e->fast_active = fast_wanted(e, e->strip_len, e->strip_q);
+    plan_iir_stream(e);                          // (frame strides of the intermediates depend on it)
     e->group = choose_group(e, e->fast_active);
     plan_tiles(e);
     e->nsplit_cap = 16;
@@ -1576,6 +1731,10 @@ int zfb_configure(zfb_engine *e, const zfb_config *cfg) {
                 rc = ensure(e, e->mid[i], (size_t)e->group * (size_t)need[i] * sizeof(float2));
                 if (rc) return rc;
             }
+    }
+    if (e->iis.active) {
+        rc = finish_iir_stream(e);
+        if (rc) return rc;
     }
     rc = ensure(e, e->pow, (size_t)e->group * (size_t)e->nsplit_cap * (size_t)e->Wp * sizeof(float));
     if (rc) return rc;
@@ -1703,18 +1862,21 @@ int zfb_set_option(zfb_engine *e, const char *name, long long value) {
     }
     if (strcmp(name, "iir_stream") == 0) {
         e->iir_stream = value ? 1 : 0;
+        e->configured = false;
         return ZFB_OK;
     }
     if (strcmp(name, "iir_stream_len") == 0) {
-        if (value < IS_CH || value > (1 << 20) || value % IS_CH)
-            return fail(e, ZFB_EINVAL, "iir_stream_len must be a positive multiple of %d", IS_CH);
+        if (value < 256 || value > (1 << 20))
+            return fail(e, ZFB_EINVAL, "iir_stream_len (target samples per stream) must be in [256, 2^20]");
         e->iir_S = (int)value;
+        e->configured = false;
         return ZFB_OK;
     }
     if (strcmp(name, "iir_stream_warm") == 0) {
-        if (value < IS_CH || value > 4096 || value % IS_CH)
-            return fail(e, ZFB_EINVAL, "iir_stream_warm must be a multiple of %d in [%d, 4096]", IS_CH, IS_CH);
+        if (value < 2 * IS_BLK || value > 4096 || value % IS_BLK)
+            return fail(e, ZFB_EINVAL, "iir_stream_warm must be a multiple of %d in [%d, 4096]", IS_BLK, 2 * IS_BLK);
         e->iir_Wm = (int)value;
+        e->configured = false;
         return ZFB_OK;
     }
     if (strcmp(name, "ring_append") == 0) {

@@ -21,50 +21,49 @@
 // transposed form, four partial sums per lane).  No barriers, no hand-off, no
 // idle lanes; a warp of 32 streams keeps the FMA pipe busy on its own.
 //
-// Data movement is all 1-D TMA (cp.async.bulk, zfb_tma.cuh): every lane pulls
-// 256-byte pieces of ITS stream into a padded shared-memory row (row pitch 272 B:
-// the lanes' LDS.128 hit distinct banks), NS pieces in flight behind per-lane
-// mbarriers, and pushes 128-byte pieces of results back the same way.  The
-// forward pass writes its half of the sum to the output; the backward pass of
-// the same lane pulls it back (L2), adds its own half and stores the result.
-// A per-lane LDG/STG.128 here would touch 32 cache lines per warp instruction
-// (32 L1 wavefronts); the bulk copies bypass that path.
+// Data movement is tiled TMA (cp.async.bulk.tensor, zfb_tma.cuh): the frames are
+// described to the copy engine as a 4-D tensor [frame][stream][16-sample block][16
+// samples], so ONE request brings the next 16 samples of all 32 streams of a warp
+// (a [32 rows][128 B] box, SWIZZLE_128B: the lanes' LDS.128 of their own rows hit
+// distinct banks) and one request takes 8 results of every stream back ([32][64 B],
+// SWIZZLE_64B).  A warm-up block that lies before (after) a stream is the tail
+// (head) of the neighbouring stream -- the same box one stream over; rows that
+// fall outside the frame are zero-filled / dropped by the engine itself, which is
+// the zero extension this kernel assumes: there is not one bounds check, fallback
+// path or per-lane address in it.  (The first version issued one 256-byte
+// cp.async.bulk per LANE; UBLKCP is a uniform-datapath instruction, the compiler
+// serialises it over the lanes and the copy engine needs ~46 cycles per request:
+// 4000 cycles per 32 samples, 326 us for the cfg2 last stage, profiles/r02a_*.)
+// The forward pass writes its half of the sum to the output; the backward pass of
+// the same warp pulls it back (L2), adds its own half and stores the result.
 //
-// Outside [0, L) the input is held constant (x[0], x[L-1]); the reference's own
-// edge rules (odd extension, steady-state zi at every pass) differ from that
-// only within ~256 samples of a chunk end, which mode FAST recomputes exactly on
-// its edge strips (zfb_engine.cu).
+// Outside [0, L) the input is zero; the reference's own edge rules (odd
+// extension, steady-state zi at every pass) differ from that only within ~256
+// samples of a chunk end, which mode FAST recomputes exactly on its edge strips
+// and patches in afterwards (zfb_engine.cu).
 #pragma once
 #include "zfb_decim.cuh"
 #include "zfb_tma.cuh"
 
 namespace zfb {
 
-constexpr int IS_CH = 32;                          // samples per piece and lane
-constexpr int IS_XPITCH = IS_CH * 8 + 16;          // 272 B rows: conflict-free LDS.128
-constexpr int IS_OPITCH = (IS_CH / 2) * 8 + 16;    // 144 B rows of 16 outputs
+constexpr int IS_BLK = 16;                         // samples per block (one 128-byte row of a tile)
 constexpr int IS_LAG = 6;                          // samples between a section-0 input and the cascade's output
+constexpr int IS_XTILE = 32 * IS_BLK * 8;          // 4096 B: [32 streams][16 samples]
+constexpr int IS_OTILE = 32 * (IS_BLK / 2) * 8;    // 2048 B: [32 streams][8 results]
 
 struct IirStreamParams {
-    const float2 *in;          // [frames][in_stride] complex64, 16-byte aligned rows
-    long long     in_stride;
-    int           L;           // stage input length per frame
-    float2       *out;         // [frames][out_stride]
-    long long     out_stride;
-    int           S;           // samples per stream (multiple of IS_CH)
-    int           Wm;          // warm-up samples (multiple of IS_CH)
-    int           nspf;        // streams per frame
-    int           n0;          // input position of stream 0's first sample (multiple of 4)
-    int           m_lo, m_hi;  // outputs [m_lo, m_hi) of a frame are written
-    long long     nstreams;    // frames * nspf
+    int S16;              // blocks per stream (stream length S = 16 * S16)
+    int Wb;               // warm-up blocks (Wb + 1 <= S16)
+    int nspf;             // streams per frame (rows beyond it are out of bounds for the copy engine)
+    int groups;           // warps per frame: ceil(nspf / 32)
 };
 
 template <int NS, int NO>
 struct IirStreamShape {
-    static constexpr int XBYTES = NS * 32 * IS_XPITCH;
-    static constexpr int OBYTES = NO * 32 * IS_OPITCH;
-    static constexpr int BARS = (NS + NO) * 32;
-    static constexpr size_t SMEM = (size_t)XBYTES + OBYTES + BARS * sizeof(uint64_t);
+    static constexpr int XBYTES = NS * IS_XTILE;
+    static constexpr int OBYTES = NO * IS_OTILE;
+    static constexpr size_t SMEM = 1024 + (size_t)XBYTES + OBYTES + (NS + NO) * sizeof(uint64_t);
 };
 
 struct IirState {
@@ -73,11 +72,9 @@ struct IirState {
     float2 A1, A2, A3, A4;                   // partial sums of the next four kept outputs
 };
 
-__device__ __forceinline__ void iir_init(IirState &st, float2 c) {
-    sec_steady(st.s, c);
-    st.q1a = st.q1b = st.s.w1[0];
-    st.q2a = st.q2b = st.s.w1[1];
-    st.q3a = st.q3b = st.s.w1[2];
+__device__ __forceinline__ void iir_zero(IirState &st) {
+    sec_zero(st.s);
+    st.q1a = st.q1b = st.q2a = st.q2b = st.q3a = st.q3b = make_float2(0.f, 0.f);
     st.A1 = st.A2 = st.A3 = st.A4 = make_float2(0.f, 0.f);
 }
 
@@ -110,28 +107,32 @@ __device__ __forceinline__ void iir_step(IirState &st, float2 xa, float2 xb, con
     }
 }
 
-// 32 samples of one lane from its shared-memory row.  MODE 0: warm-up (recursion only),
-// 1: numerator running, nothing kept, 2: the 16 kept outputs go to `orow` (forward: stored;
-// backward: added to what the row holds -- the forward half, or zeros).
+// One block (16 cascade outputs) of one lane.  The inputs lead the outputs by IS_LAG = 6
+// samples in processing order: 10 come from the lane's row of tile `ta`, 6 from tile `tb`
+// (the next one in processing order).  `xsw` / `osw` are the lane's swizzle masks.
+// MODE 0: warm-up (recursion only); 1: numerator running, nothing kept; 2: the 8 kept outputs
+// go to the lane's row of `orow` (forward: stored; backward: added to what the row holds).
 template <bool BWD, int MODE>
-__device__ __forceinline__ void iir_piece(const unsigned char *xrow, unsigned char *orow, IirState &st,
+__device__ __forceinline__ void iir_block(const unsigned char *ta, const unsigned char *tb, unsigned xsw,
+                                          unsigned char *orow, unsigned osw, IirState &st,
                                           const float (&na1)[NSEC], const float (&na2)[NSEC],
                                           const float (&bc)[9]) {
     float2 held = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int t = 0; t < IS_CH / 2; ++t) {
-        const int xi = BWD ? (IS_CH / 2 - 1 - t) : t;
-        const float4 x = *reinterpret_cast<const float4 *>(xrow + xi * 16);
+    for (int t = 0; t < IS_BLK / 2; ++t) {
+        // 16-byte chunk (two samples) of this step
+        const unsigned char *tile = (t < 5) ? ta : tb;
+        const int chunk = BWD ? ((t < 5) ? 4 - t : 12 - t) : ((t < 5) ? 3 + t : t - 5);
+        const float4 x = *reinterpret_cast<const float4 *>(tile + (((unsigned)chunk << 4) ^ xsw));
         const float2 lo = make_float2(x.x, x.y), hi = make_float2(x.z, x.w);
         float2 o;
         iir_step<BWD, (MODE >= 1)>(st, BWD ? hi : lo, BWD ? lo : hi, na1, na2, bc, o);
         if (MODE == 2) {
-            // output index within the piece: forward t, backward 15 - t; two share a 16-byte slot
             if ((t & 1) == 0) {
                 held = o;
             } else {
-                const int slot = BWD ? (IS_CH / 2 - 1 - t) / 2 : t / 2;
-                float4 *dst = reinterpret_cast<float4 *>(orow + slot * 16);
+                const int oc = BWD ? (IS_BLK / 2 - 1 - t) / 2 : t / 2;       // result chunk (two outputs)
+                float4 *dst = reinterpret_cast<float4 *>(orow + (((unsigned)oc << 4) ^ osw));
                 if (!BWD) {
                     *dst = make_float4(held.x, held.y, o.x, o.y);
                 } else {
@@ -144,33 +145,31 @@ __device__ __forceinline__ void iir_piece(const unsigned char *xrow, unsigned ch
 }
 
 template <int NS, int NO>
-__global__ void __launch_bounds__(32) iir_stream_kernel(const IirStreamParams p) {
+__global__ void __launch_bounds__(32) iir_stream_kernel(ZFB_TMAP_PARAM tm_in, ZFB_TMAP_PARAM tm_out,
+                                                        const IirStreamParams p) {
     using SH = IirStreamShape<NS, NO>;
     ZFB_DYN_SMEM(smem_raw);
     const int lane = threadIdx.x;
-    unsigned char *xbuf = smem_raw;                               // [NS][32][IS_XPITCH]
-    unsigned char *obuf = smem_raw + SH::XBYTES;                  // [NO][32][IS_OPITCH]
-    uint64_t *xbar = reinterpret_cast<uint64_t *>(smem_raw + SH::XBYTES + SH::OBYTES);   // [NS][32]
-    uint64_t *pbar = xbar + NS * 32;                              // [NO][32]
-
+    // tiles want 1024-byte alignment (the swizzle pattern is a function of the address)
+    unsigned char *base = smem_raw + smem_align_pad(smem_raw, 1024);
+    unsigned char *xbuf = base;                                   // [NS] tiles of [32][128 B]
+    unsigned char *obuf = base + SH::XBYTES;                      // [NO] tiles of [32][64 B]
+    uint64_t *xbar = reinterpret_cast<uint64_t *>(base + SH::XBYTES + SH::OBYTES);   // [NS]
+    uint64_t *pbar = xbar + NS;                                   // [NO]
+    if (lane == 0) {
 #pragma unroll
-    for (int i = 0; i < NS; ++i) mbar_init(xbar + i * 32 + lane, 1);
+        for (int i = 0; i < NS; ++i) mbar_init(xbar + i, 1);
 #pragma unroll
-    for (int i = 0; i < NO; ++i) mbar_init(pbar + i * 32 + lane, 1);
-    mbar_fence_init();
+        for (int i = 0; i < NO; ++i) mbar_init(pbar + i, 1);
+        mbar_fence_init();
+    }
     __syncwarp();
 
-    long long g = (long long)blockIdx.x * 32 + lane;
-    const bool live = g < p.nstreams;
-    if (!live) g = p.nstreams - 1;                 // same work, nothing stored
-    const int frame = (int)(g / p.nspf);
-    const int a = p.n0 + (int)(g % p.nspf) * p.S;  // first sample of the stream
-    const float2 *in_row = p.in + (size_t)frame * (size_t)p.in_stride;
-    float2 *out_row = p.out + (size_t)frame * (size_t)p.out_stride;
-    const int L = p.L;
-    const int m_lo = live ? p.m_lo : 0, m_hi = live ? p.m_hi : 0;
-    const int jw = p.Wm / IS_CH;                   // warm-up pieces
-    const int npieces = jw + p.S / IS_CH;
+    const int frame = blockIdx.x / p.groups;
+    const int s0 = (blockIdx.x % p.groups) * 32;       // first stream of this warp
+    const int S16 = p.S16, Wb = p.Wb;
+    const unsigned xrow = (unsigned)lane * (IS_BLK * 8), xsw = (unsigned)(lane & 7) << 4;
+    const unsigned orow_off = (unsigned)lane * (IS_BLK * 4), osw = (unsigned)((lane >> 1) & 3) << 4;
 
     float na1[NSEC], na2[NSEC], bc[9];
 #pragma unroll
@@ -181,118 +180,82 @@ __global__ void __launch_bounds__(32) iir_stream_kernel(const IirStreamParams p)
 #pragma unroll
     for (int j = 0; j < 9; ++j) bc[j] = c_dec.bc[j];
 
-    long long gx = 0;        // x pieces consumed so far (both directions): slot gx % NS, parity (gx / NS) & 1
-    long long gp = 0;        // forward halves pulled back so far (backward direction only)
-
-    // input piece j of a direction: positions [cin, cin + 32) of the frame into slot `slot`
-    auto issue_x = [&](int cin, int slot) {
-        unsigned char *row = xbuf + ((size_t)slot * 32 + lane) * IS_XPITCH;
-        uint64_t *bar = xbar + slot * 32 + lane;
-        const float2 *src = in_row + cin;
-        if (cin >= 0 && cin + IS_CH <= L && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
-            mbar_arrive_expect_tx(bar, IS_CH * 8);
-            bulk_g2s(row, src, IS_CH * 8, bar);
-        } else {
-            float2 *r = reinterpret_cast<float2 *>(row);
-            for (int i = 0; i < IS_CH; ++i) {
-                int q = cin + i;
-                q = q < 0 ? 0 : (q >= L ? L - 1 : q);
-                r[i] = in_row[q];
-            }
-            mbar_arrive(bar);
-        }
-    };
-    auto out_bulk_ok = [&](int mc) {
-        return mc >= m_lo && mc + IS_CH / 2 <= m_hi && ((reinterpret_cast<uintptr_t>(out_row + mc) & 15) == 0);
-    };
+    unsigned gx = 0;          // x tiles consumed so far (both directions): slot gx % NS, parity (gx / NS) & 1
+    const int npieces = Wb + S16;
 
 #pragma unroll 1
     for (int dir = 0; dir < 2; ++dir) {
         const bool bwd = dir == 1;
-        // output-side position of piece j: forward a - Wm + 32 j, backward a + S + Wm - 32 (j + 1);
-        // the input piece runs IS_LAG samples ahead of it in processing order
-        const int top = a + p.S + p.Wm;
-        auto piece_po = [&](int j) { return bwd ? top - IS_CH * (j + 1) : a - p.Wm + IS_CH * j; };
-        auto piece_cin = [&](int j) { return bwd ? piece_po(j) - IS_LAG : piece_po(j) + IS_LAG; };
-
-        // initial state: steady state for the constant the first warm-up sample would hold for ever
+        // piece k works on output block jb(k) of the stream; x tile q is block jx(q)
+        //   forward : jb = k - Wb,            jx(q) = q - Wb            (tiles k, k+1)
+        //   backward: jb = S16 + Wb - 1 - k,  jx(q) = S16 + Wb - 1 - q  (tiles k, k+1)
+        auto issue_x = [&](int q) {
+            const int jx = bwd ? S16 + Wb - 1 - q : q - Wb;
+            int c1 = jx, c2 = s0;
+            if (jx < 0) { c1 += S16; c2 -= 1; }
+            else if (jx >= S16) { c1 -= S16; c2 += 1; }
+            const unsigned slot = (gx + (unsigned)q) % NS;
+            mbar_arrive_expect_tx(xbar + slot, IS_XTILE);
+            tma_load_4d(xbuf + slot * IS_XTILE, &tm_in, 0, c1, c2, frame, xbar + slot);
+        };
         IirState st;
-        {
-            int q0 = bwd ? piece_cin(0) + IS_CH - 1 : piece_cin(0);
-            q0 = q0 < 0 ? 0 : (q0 >= L ? L - 1 : q0);
-            iir_init(st, in_row[q0]);
-        }
-        for (int j = 0; j < NS - 1 && j < npieces; ++j) issue_x(piece_cin(j), (int)((gx + j) % NS));
+        iir_zero(st);
+        if (lane == 0)
+            for (int q = 0; q < NS - 1 && q <= npieces; ++q) issue_x(q);
+        mbar_wait(xbar + gx % NS, (gx / NS) & 1);                 // tile 0
 
 #pragma unroll 1
-        for (int j = 0; j < npieces; ++j) {
-            if (j + NS - 1 < npieces) issue_x(piece_cin(j + NS - 1), (int)((gx + NS - 1) % NS));
-            const int e = j - jw;                             // kept piece number (>= 0: outputs are kept)
-            const int mc = piece_po(j) >> 1;                  // first output of the piece
-            if (bwd) {
-                // pull the forward half of the NEXT kept piece into its row (or zeros where the
-                // piece is not written whole); its row was last read by the store of piece e+1-NO
-                const int en = e + 1;
-                if (en >= 0 && en < p.S / IS_CH) {
-                    bulk_wait_read<(NO >= 2 ? NO - 2 : 0)>();
-                    const int slot = (int)((gp + en) % NO);
-                    unsigned char *row = obuf + ((size_t)slot * 32 + lane) * IS_OPITCH;
-                    uint64_t *bar = pbar + slot * 32 + lane;
-                    const int mcn = piece_po(j + 1) >> 1;
-                    if (out_bulk_ok(mcn)) {
-                        mbar_arrive_expect_tx(bar, IS_CH * 4);
-                        bulk_g2s(row, out_row + mcn, IS_CH * 4, bar);
-                    } else {
-                        float4 *r = reinterpret_cast<float4 *>(row);
-#pragma unroll
-                        for (int i = 0; i < IS_CH / 4; ++i) r[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        mbar_arrive(bar);
-                    }
-                }
-            } else if (e >= 0) {
-                bulk_wait_read<NO - 1>();                     // the row's previous store has left it
-            }
-            const int xs = (int)(gx % NS);
-            mbar_wait(xbar + xs * 32 + lane, (uint32_t)((gx / NS) & 1));
-            const unsigned char *xrow = xbuf + ((size_t)xs * 32 + lane) * IS_XPITCH;
-            if (e < -1) {
-                if (bwd) iir_piece<true, 0>(xrow, nullptr, st, na1, na2, bc);
-                else iir_piece<false, 0>(xrow, nullptr, st, na1, na2, bc);
-            } else if (e == -1) {
-                if (bwd) iir_piece<true, 1>(xrow, nullptr, st, na1, na2, bc);
-                else iir_piece<false, 1>(xrow, nullptr, st, na1, na2, bc);
-            } else {
-                const int os = (int)(((bwd ? gp : 0) + e) % NO);
-                unsigned char *orow = obuf + ((size_t)os * 32 + lane) * IS_OPITCH;
+        for (int k = 0; k < npieces; ++k) {
+            const int jb = bwd ? S16 + Wb - 1 - k : k - Wb;
+            const int e = bwd ? (jb < S16 ? S16 - 1 - jb : -(jb - S16 + 1)) : jb;   // kept piece number, < 0: warm-up
+            // everybody has left tile k-1: its slot takes tile k + NS - 1
+            __syncwarp();
+            if (lane == 0) {
+                if (k + NS - 1 <= npieces) issue_x(k + NS - 1);
                 if (bwd) {
-                    mbar_wait(pbar + os * 32 + lane, (uint32_t)((((gp + e) / NO)) & 1));
-                    iir_piece<true, 2>(xrow, orow, st, na1, na2, bc);
-                } else {
-                    iir_piece<false, 2>(xrow, orow, st, na1, na2, bc);
-                }
-                if (out_bulk_ok(mc)) {
-                    fence_proxy_async();
-                    bulk_s2g(out_row + mc, orow, IS_CH * 4);
-                } else {
-                    const float2 *r = reinterpret_cast<const float2 *>(orow);
-                    for (int i = 0; i < IS_CH / 2; ++i) {
-                        const int m = mc + i;
-                        if (m >= m_lo && m < m_hi) {
-                            float2 v = r[i];
-                            if (bwd) {
-                                const float2 f = out_row[m];
-                                v = make_float2(v.x + f.x, v.y + f.y);
-                            }
-                            out_row[m] = v;
-                        }
+                    // forward half of the NEXT kept piece into its row tile (last read by the store of
+                    // kept piece en - NO)
+                    const int en = e + 1;
+                    if (en >= 0 && en < S16) {
+                        bulk_wait_read<(NO >= 2 ? NO - 2 : 0)>();
+                        const unsigned slot = (unsigned)en % NO;
+                        mbar_arrive_expect_tx(pbar + slot, IS_OTILE);
+                        tma_load_4d(obuf + slot * IS_OTILE, &tm_out, 0, S16 - 1 - en, s0, frame, pbar + slot);
                     }
+                } else if (e >= 0) {
+                    bulk_wait_read<NO - 1>();                     // the row tile's previous store has left it
                 }
-                bulk_commit();
             }
-            gx += 1;
+            __syncwarp();
+            const unsigned sa = (gx + (unsigned)k) % NS, sb = (gx + (unsigned)k + 1) % NS;
+            mbar_wait(xbar + sb, ((gx + (unsigned)k + 1) / NS) & 1);                  // tile k + 1
+            const unsigned char *ta = xbuf + sa * IS_XTILE + xrow, *tb = xbuf + sb * IS_XTILE + xrow;
+            if (e < -1) {
+                if (bwd) iir_block<true, 0>(ta, tb, xsw, nullptr, 0, st, na1, na2, bc);
+                else iir_block<false, 0>(ta, tb, xsw, nullptr, 0, st, na1, na2, bc);
+            } else if (e == -1) {
+                if (bwd) iir_block<true, 1>(ta, tb, xsw, nullptr, 0, st, na1, na2, bc);
+                else iir_block<false, 1>(ta, tb, xsw, nullptr, 0, st, na1, na2, bc);
+            } else {
+                const unsigned os = (unsigned)e % NO;
+                unsigned char *orow = obuf + os * IS_OTILE + orow_off;
+                if (bwd) {
+                    mbar_wait(pbar + os, ((unsigned)e / NO) & 1);
+                    iir_block<true, 2>(ta, tb, xsw, orow, osw, st, na1, na2, bc);
+                } else {
+                    iir_block<false, 2>(ta, tb, xsw, orow, osw, st, na1, na2, bc);
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_4d(&tm_out, 0, jb, s0, frame, obuf + os * IS_OTILE);
+                    bulk_commit();
+                }
+            }
         }
-        if (bwd) gp += p.S / IS_CH;
-        bulk_wait<0>();          // forward halves are in place before the backward pass pulls them back
+        gx += (unsigned)npieces + 1;
+        if (lane == 0) bulk_wait<0>();   // forward halves are in place before the backward pass pulls them back
+        __syncwarp();
     }
 }
 

@@ -11,6 +11,9 @@
 #include <stdint.h>
 
 #include "zfb_platform.h"
+#ifndef ZFB_EMULATE
+#include <cuda.h>
+#endif
 
 namespace zfb {
 
@@ -18,6 +21,11 @@ namespace zfb {
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
     return (uint32_t)__cvta_generic_to_shared(p);
+}
+// bytes to skip so that a shared-memory pointer becomes `align`-aligned (keeps the pointer's
+// address space visible to the compiler: LDS/STS, not generic LD/ST)
+__device__ __forceinline__ unsigned smem_align_pad(const void *p, unsigned align) {
+    return (align - (smem_u32(p) & (align - 1))) & (align - 1);
 }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -72,8 +80,29 @@ __device__ __forceinline__ void bulk_wait() {
 // generic-proxy writes to shared memory -> visible to the bulk-copy engine
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// ---- tiled TMA over a 4-D tensor map (one request moves a whole [rows][bytes] box) ----
+typedef CUtensorMap TensorMap;
+#define ZFB_TMAP_PARAM const __grid_constant__ ::zfb::TensorMap
+__device__ __forceinline__ void tma_load_4d(void *dst_smem, const TensorMap *map, int c0, int c1, int c2, int c3,
+                                            uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::
+            "r"(smem_u32(dst_smem)),
+        "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const TensorMap *map, int c0, int c1, int c2, int c3,
+                                             const void *src_smem) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3, %4}], [%5];" ::"l"(map),
+                 "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(src_smem))
+                 : "memory");
+}
+
 #else  // ---------------------------------------------------------------- emulation
 
+inline unsigned smem_align_pad(const void *p, unsigned align) {
+    return (unsigned)((align - ((uintptr_t)p & (align - 1))) & (align - 1));
+}
 inline void mbar_init(uint64_t *, int) {}
 inline void mbar_fence_init() {}
 inline void mbar_arrive(uint64_t *) {}
@@ -86,6 +115,62 @@ template <int N> inline void bulk_wait_read() {}
 template <int N> inline void bulk_wait() {}
 inline void fence_proxy_async() {}
 
+// tensor map stand-in: the fields cuTensorMapEncodeTiled takes, interpreted by the two
+// functions below exactly as the hardware does (out-of-bounds elements read as zero and are
+// not written; SWIZZLE_128B / SWIZZLE_64B XOR the 16-byte chunk index with the row's bits)
+struct TensorMap {
+    unsigned char *base;
+    unsigned long long dim[4], stride[4];      // elements, bytes (stride[0] = element size)
+    unsigned int box[4];
+    int swizzle;                               // bytes: 0, 64 or 128
+};
+#define ZFB_TMAP_PARAM const ::zfb::TensorMap
+template <bool STORE>
+inline void tma_emu_4d(unsigned char *smem, const TensorMap *m, int c0, int c1, int c2, int c3) {
+    const size_t es = (size_t)m->stride[0];
+    const size_t row_bytes = (size_t)m->box[0] * es;
+    size_t row = 0;
+    for (unsigned i3 = 0; i3 < m->box[3]; ++i3)
+        for (unsigned i2 = 0; i2 < m->box[2]; ++i2)
+            for (unsigned i1 = 0; i1 < m->box[1]; ++i1, ++row) {
+                const long long g3 = (long long)c3 + i3, g2 = (long long)c2 + i2, g1 = (long long)c1 + i1;
+                const bool row_ok = g3 >= 0 && g3 < (long long)m->dim[3] && g2 >= 0 && g2 < (long long)m->dim[2] &&
+                                    g1 >= 0 && g1 < (long long)m->dim[1];
+                for (unsigned i0 = 0; i0 < m->box[0]; ++i0) {
+                    const long long g0 = (long long)c0 + i0;
+                    const bool ok = row_ok && g0 >= 0 && g0 < (long long)m->dim[0];
+                    size_t off = row * row_bytes + (size_t)i0 * es;          // dense box offset
+                    if (m->swizzle) {
+                        const size_t chunk = off >> 4, within = off & 15;
+                        const size_t mask = m->swizzle == 128 ? ((off >> 7) & 7) : ((off >> 7) & 3);
+                        off = ((chunk ^ mask) << 4) | within;
+                    }
+                    unsigned char *g = m->base + (size_t)g3 * m->stride[3] + (size_t)g2 * m->stride[2] +
+                                       (size_t)g1 * m->stride[1] + (size_t)g0 * es;
+                    if (STORE) { if (ok) memcpy(g, smem + off, es); }
+                    else if (ok) memcpy(smem + off, g, es);
+                    else memset(smem + off, 0, es);
+                }
+            }
+}
+inline void tma_load_4d(void *dst, const TensorMap *m, int c0, int c1, int c2, int c3, uint64_t *) {
+    tma_emu_4d<false>((unsigned char *)dst, m, c0, c1, c2, c3);
+}
+inline void tma_store_4d(const TensorMap *m, int c0, int c1, int c2, int c3, const void *src) {
+    tma_emu_4d<true>((unsigned char *)src, m, c0, c1, c2, c3);
+}
+
 #endif
+
+// host side: rank-4 map over 8-byte elements; dims in elements, strides in bytes (dim 0 is dense)
+struct TensorMapSpec {
+    void *base;
+    unsigned long long dim[4];
+    unsigned long long stride[4];          // stride[0] ignored (8)
+    unsigned int box[4];
+    int swizzle;                           // 0, 64, 128
+};
+// returns 0 on success (the sm_100a build resolves cuTensorMapEncodeTiled through the runtime)
+int make_tensor_map(const TensorMapSpec &spec, TensorMap *out);
 
 }  // namespace zfb

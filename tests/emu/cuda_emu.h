@@ -112,7 +112,16 @@ static inline void __syncthreads() {
     c->bar_gen[t] += 1;
     cuemu::yield_until(&c->bar_arrived, c->bar_gen[t] * (long)c->nthreads);
 }
-static inline void __syncwarp(unsigned = 0xffffffffu) {}
+// warp barrier: a fiber yield point like the shuffles (all lanes of the warp must take part)
+static inline void __syncwarp(unsigned = 0xffffffffu) {
+    cuemu::Cta *c = cuemu::t_cta;
+    const int t = c->cur, lane = t & 31;
+    cuemu::Warp &w = c->warps[t >> 5];
+    const int wsize = (c->nthreads - (t & ~31)) < 32 ? (c->nthreads - (t & ~31)) : 32;
+    const long g = ++w.gen[lane];
+    w.arrived += 1;
+    cuemu::yield_until(&w.arrived, g * (long)wsize);
+}
 
 template <typename T>
 static inline T __shfl_xor_sync(unsigned, T v, int lane_mask) {
@@ -223,6 +232,10 @@ static inline cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcp
 static inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t = nullptr) { memcpy(d, s, n); return cudaSuccess; }
 static inline cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t = nullptr) { memset(d, v, n); return cudaSuccess; }
 static inline cudaError_t cudaMemset(void *d, int v, size_t n) { memset(d, v, n); return cudaSuccess; }
+static inline cudaError_t cudaMemset2DAsync(void *d, size_t pitch, int v, size_t width, size_t height, cudaStream_t = nullptr) {
+    for (size_t r = 0; r < height; ++r) memset((char *)d + r * pitch, v, width);
+    return cudaSuccess;
+}
 static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) { *s = (void *)1; return cudaSuccess; }
 static inline cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
