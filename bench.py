@@ -195,6 +195,39 @@ def measured_hbm_peak():
         return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
 
 
+def algorithmic_flops(w, eng, nch=1):
+    """Algorithmic fp32 FLOP per INPUT sample of the chain as planned:
+    conversion, LO mix, the decimator structure actually run (FIR taps as designed, the
+    zero-phase IIR in the form the kernels evaluate), Welch (FFT 10*log2(N)/R at 50 %
+    overlap, detrend + window + |.|^2 + accumulate 24/R).  A real coefficient times a
+    complex sample is 2 multiply-adds = 4 FLOP.  Returned per part; with ``nch`` virtual
+    receivers everything but the conversion is per channel."""
+    R = max(1, int(w.fft_ratio))
+    k = int(np.log2(R))
+    parts = {"convert_u8": 2.0 if w.dtype == "u8" else 0.0}
+    parts["lo_mix"] = 0.0 if k == 0 else 8.0
+    dec = {}
+    if k > 0 and eng.fast_active:
+        plan = eng.fast_plan
+        for s_, taps in enumerate(plan["stages"]):
+            ntaps = 2 * (len(taps) - 1) + 1
+            dec["fir_stage%d(%d taps)" % (s_, ntaps)] = 4.0 * ntaps / 2 ** (s_ + 1)
+        ne = len(plan["stages"])
+        dec["compensator(%d taps)" % (2 * (len(plan["comp"]) - 1) + 1)] = 4.0 * (2 * (len(plan["comp"]) - 1) + 1) / 2 ** ne
+        # causal + anti-causal order-8 recursion (2 x 8 packed FMAs) + 9-tap numerators at the kept samples
+        dec["iir_last_stage"] = 4.0 * 25.0 / 2 ** ne
+        parts["lo_mix"] = 8.0 / 2 ** ne if getattr(eng, "late_mix_active", True) and abs(w.f_demod) * R / w.fs <= 1e-3 else 8.0
+    elif k > 0:
+        for s_ in range(k):                       # all-pole sweeps twice (hand-off) + binomial numerators
+            dec["iir_stage%d" % s_] = 4.0 * 44.5 / 2 ** s_
+    parts.update(dec)
+    parts["welch_fft"] = 10.0 * np.log2(w.fft_size) / R
+    parts["welch_other"] = 24.0 / R
+    per_channel = sum(v for n_, v in parts.items() if n_ != "convert_u8")
+    total = parts["convert_u8"] + nch * per_channel
+    return total, parts
+
+
 def ncu_traffic(workload, kernel, frames_per_launch):
     """Per-launch DRAM bytes (read + write) of the dominant kernel, from the
     committed ncu --set full capture (profiles/roofline_traffic.json holds it
@@ -330,8 +363,21 @@ def run_b200(args, w):
     h_in_np = h_in.numpy().view(frame_wire.dtype).reshape(frame_wire.shape)
     h_rows_np = h_rows.numpy()
 
+    # cfg4 on several GPUs: every rank needs the SAME stream.  It crosses PCIe once (rank 0) and
+    # reaches the other GPUs over NVLink (ncclBroadcast); only the rows come back per rank.
+    bcast_feed = centres is not None and world > 1 and args.cfg4_feed == "broadcast"
+    d_feed = torch.empty_like(d_in) if bcast_feed else None
+    d_rows_e2e = torch.empty((nch * F, W), dtype=torch.float32, device="cuda") if bcast_feed else None
+
     def step_e2e():
-        if centres is None:                          # H2D + kernels + D2H, returns when rows are on the host
+        if bcast_feed:
+            if rank == 0:
+                d_feed.copy_(h_in, non_blocking=True)
+            dist.broadcast(d_feed, src=0)            # on `stream` (the current stream)
+            eng.process_channels_device(d_feed.data_ptr(), F, centres, d_rows_e2e.data_ptr())
+            h_rows.copy_(d_rows_e2e, non_blocking=True)
+            stream.synchronize()                     # rows are on the host, like eng.process()
+        elif centres is None:                        # H2D + kernels + D2H, returns when rows are on the host
             eng.process(h_in_np, out=h_rows_np)
         else:
             eng.process_channels(h_in_np, centres, out=h_rows_np.reshape(nch, F, W))
@@ -384,51 +430,170 @@ def run_b200(args, w):
     ev3.record(stream)
     barrier()
     ms_e2e = ev2.elapsed_time(ev3)
+
+    # ---------------- copy-only ceiling of the end-to-end leg ----------------
+    # the same pinned buffers over the same PCIe link, no kernels: what e2e could reach at best
+    copy_feeds = (rank == 0) if bcast_feed else True
+    d_copy = torch.empty_like(d_in)
+    d_rows_c = d_rows2[0]
+    for _ in range(2):
+        if copy_feeds:
+            d_copy.copy_(h_in, non_blocking=True)
+        h_rows.copy_(d_rows_c, non_blocking=True)
+    barrier()
+    ev4, ev5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev4.record(stream)
+    for _ in range(e2e_steps):
+        if copy_feeds:
+            d_copy.copy_(h_in, non_blocking=True)
+        if bcast_feed:
+            dist.broadcast(d_copy, src=0)
+        h_rows.copy_(d_rows_c, non_blocking=True)
+    ev5.record(stream)
+    barrier()
+    ms_copy = ev4.elapsed_time(ev5)
+    del d_copy
+
+    # ---------------- sustained leg: >= args.sustain_s seconds of back-to-back steps ----------------
+    sustained = None
+    if args.sustain_s > 0:
+        n_sus = max(args.steps, int(np.ceil(args.sustain_s * 1e3 / max(ms / args.steps, 1e-3))))
+        barrier()
+        ev6, ev7 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ts0 = time.perf_counter()
+        ev6.record(stream)
+        for i in range(n_sus):
+            step_device()
+            if (i & 63) == 63:
+                stream.synchronize()                 # bound the launch queue; negligible against 64 steps
+        if world > 1:
+            stream.wait_event(gathered[(step_no[0] - 1) & 1])
+        ev7.record(stream)
+        barrier()
+        ts1 = time.perf_counter()
+        sustained = {"ms": ev6.elapsed_time(ev7), "steps": n_sus, "clocks": sampler.summary(ts0, ts1)}
     sampler.stop()
 
-    t = torch.tensor([ms, ms_e2e, float(launches)], dtype=torch.float64, device="cuda")
+    # ---------------- per-kernel times with nothing overlapped (strips on the main stream) ----------
+    serial_prof = None
+    if world == 1 and eng.fast_active:
+        eng.set_option("strips_async", 0)
+        eng.configure(w.fs, w.fft_size, w.fft_ratio, w.frame_len, w.window, dtype=w.dtype, flip=w.flip,
+                      f_demod=w.f_demod, crop=w.crop, ema_alpha=w.ema_alpha, mode=args.mode)
+        for _ in range(2):
+            step_device()
+        barrier()
+        eng.profile()
+        eng.set_profiling(True)
+        for _ in range(5):
+            step_device()
+        barrier()
+        eng.set_profiling(False)
+        serial_prof = {k: v[0] / max(1, v[1]) for k, v in eng.profile().items()}
+        eng.set_option("strips_async", 1 if args.strips_async is None else args.strips_async)
+
+    # ---------------- N > 1: the gathered rows ARE the single-GPU rows, bit for bit ----------------
+    # frames are independent (LO phase, filter state and Welch mean restart per chunk: S:2092, 2098,
+    # 2111): rank r computes frames [r*Fv, (r+1)*Fv) of one list, rank 0 also computes all of them
+    verify = None
+    if world > 1 and centres is None:
+        Fv = min(F, 48)
+        allf = synth.make_frames(w, world * Fv, distinct=world * Fv)
+        eng.configure(w.fs, w.fft_size, w.fft_ratio, w.frame_len, w.window, dtype=w.dtype, flip=w.flip,
+                      f_demod=w.f_demod, crop=w.crop, ema_alpha=None, mode=args.mode)
+        mine = torch.from_numpy(allf[rank * Fv:(rank + 1) * Fv].view(np.uint8).reshape(Fv, -1)).cuda()
+        rows_mine = torch.empty((Fv, W), dtype=torch.float32, device="cuda")
+        eng.process_device(mine.data_ptr(), Fv, rows_mine.data_ptr())
+        glist = [torch.empty_like(rows_mine) for _ in range(world)] if rank == 0 else None
+        dist.gather(rows_mine, glist, dst=0)
+        stream.synchronize()
+        if rank == 0:
+            everything = torch.from_numpy(allf.view(np.uint8).reshape(world * Fv, -1)).cuda()
+            rows_all = torch.empty((world * Fv, W), dtype=torch.float32, device="cuda")
+            eng.process_device(everything.data_ptr(), world * Fv, rows_all.data_ptr())
+            stream.synchronize()
+            got = torch.cat(glist, 0).cpu().numpy()
+            want = rows_all.cpu().numpy()
+            verify = {"frames": world * Fv, "rows_equal_single_gpu": bool(np.array_equal(got, want)),
+                      "max_abs_diff": float(np.max(np.abs(got - want)))}
+
+    ms_sus = sustained["ms"] if sustained else 0.0
+    t = torch.tensor([ms, ms_e2e, float(launches), ms_copy, ms_sus], dtype=torch.float64, device="cuda")
     if world > 1:
         tmax = t.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = t.clone()
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        ms, ms_e2e, launches = float(tmax[0]), float(tmax[1]), int(tsum[2])
+        ms, ms_e2e, launches, ms_copy, ms_sus = (float(tmax[0]), float(tmax[1]), int(tsum[2]), float(tmax[3]),
+                                                 float(tmax[4]))
     samples_step = world * F * w.frame_len * nch      # cfg4: channel-samples (every channel consumes the stream)
     value = samples_step * args.steps / (ms * 1e-3) / 1e6
     e2e_value = samples_step * e2e_steps / (ms_e2e * 1e-3) / 1e6
+    copy_value = samples_step * e2e_steps / (ms_copy * 1e-3) / 1e6
+    burst_value, value_source, steps_counted, ms_counted = value, "timed K steps", args.steps, ms
+    if sustained:
+        sus_value = samples_step * sustained["steps"] / (ms_sus * 1e-3) / 1e6
+        sustained.update(value=sus_value, unit=UNIT, seconds=ms_sus * 1e-3,
+                         ratio_to_burst=sus_value / burst_value)
+        if abs(sus_value / burst_value - 1.0) > 0.03:
+            # a burst of K steps at boost clocks is not what a long job sees: report the long run
+            value, value_source = sus_value, "sustained leg (differs from the K-step burst by > 3 %)"
+            steps_counted, ms_counted = sustained["steps"], ms_sus
 
     if rank == 0:
         peak, peak_src = measured_hbm_peak()
-        # dominant kernel = largest share of device time in the timed region
-        # (the edge strips of mode fast run on a side stream beside the FIR interior: their
-        # event interval is not exclusive, so they are left out of the ranking)
+        # Dominant kernel: largest share of device time in the timed region.  The edge strips of
+        # mode fast run on a side stream beside the other kernels, so their event interval is not
+        # exclusive; they are ranked by their time in the serialised pass below (kernel_ms_serial).
+        names = {"decimate_stage15": "edge_strips"}
         exclusive = {k: v for k, v in prof.items() if k != "decimate_stage15"} or prof
-        top = max(exclusive, key=lambda k: exclusive[k][0])
-        top_ms, top_n = prof[top]
-        # algorithmic bytes: every input sample read once; the row
-        # bytes (4*W, x3 with EMA) belong to the finalize kernel
-        b_in = w.bytes_per_sample / nch               # algorithmic: the stream is read once, not once per channel
-        if top.startswith("decimate_stage0") or (top == "welch" and w.fft_ratio == 1):
-            algo_bytes_total = args.steps * F * w.frame_len * b_in
-        elif top.startswith("decimate_stage"):
-            s = int(top[len("decimate_stage"):])
-            algo_bytes_total = args.steps * F * (w.frame_len >> s) * 8
+        if serial_prof:
+            top = max(serial_prof, key=lambda k: serial_prof[k] if k in exclusive else -1.0)
         else:
-            algo_bytes_total = args.steps * F * w.frame_len * b_in
-        achieved = algo_bytes_total / (top_ms * 1e-3) / 1e9
-        step_bytes = F * (w.frame_len * b_in + 4 * W * (3 if w.ema_alpha is not None else 1))
+            # N > 1: the same kernel as at N = 1 (the FIR chain / stage 0 / the R = 1 Welch), whose
+            # interval holds no wait on another stream
+            top = "decimate_stage0" if "decimate_stage0" in exclusive else max(exclusive, key=lambda k: exclusive[k][0])
+        top_ms, top_n = prof[top]
+        # algorithmic bytes: every input sample read ONCE -- not once per virtual receiver,
+        # not per overlap re-read, not per stage; rows 4*W (x3 with EMA: read-modify-write of the state)
+        row_bytes = 4 * W * (3 if w.ema_alpha is not None else 1)
+        frame_bytes = w.frame_len * w.bytes_per_sample + nch * row_bytes
+        if top.startswith("decimate_stage") and top not in ("decimate_stage0",):
+            s_ = int(top[len("decimate_stage"):])
+            algo_launch = F * nch * (w.frame_len >> s_) * 8 / max(1, top_n // args.steps)
+        else:
+            algo_launch = F * w.frame_len * w.bytes_per_sample / max(1, top_n // args.steps)
+        avg_launch_ms = top_ms / max(1, top_n)
+        achieved = algo_launch / (avg_launch_ms * 1e-3) / 1e9
+        step_ms = ms_counted / steps_counted
         roofline = {
-            "bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "bound": "hbm", "kernel": names.get(top, top), "achieved": achieved, "peak": peak, "unit": "GB/s",
             "frac": achieved / peak,
-            "traffic": ncu_traffic(w.name, top, args.steps * F / max(1, top_n)), "peak_source": peak_src,
-            "launches": top_n, "avg_launch_ms": top_ms / max(1, top_n),
-            "algorithmic_bytes_per_launch": algo_bytes_total / max(1, top_n),
+            "traffic": ncu_traffic(w.name, top, F / max(1, top_n // args.steps)), "peak_source": peak_src,
+            "launches": top_n, "avg_launch_ms": avg_launch_ms,
+            "algorithmic_bytes_per_launch": algo_launch,
             "kernel_share_of_step": top_ms / ms,
-            "kernel_ms": {("edge_strips(concurrent)" if k == "decimate_stage15" else k): round(v[0], 4)
+            "kernel_ms": {names.get(k, k) + ("(concurrent)" if k == "decimate_stage15" else ""): round(v[0], 4)
                           for k, v in prof.items()},
-            "step_achieved_gbs": step_bytes * args.steps / (ms * 1e-3) / 1e9 * 1.0,
-            "note": "fp32-pipe bound, not HBM bound (DESIGN.md 4): FMA pipe ~64 % active in the FIR chain; "
-                    "60 % of HBM at 2 B/sample would leave 19 pipe-cycles per sample",
+            "kernel_ms_serial_per_launch": None if serial_prof is None else
+                {names.get(k, k): round(v, 5) for k, v in serial_prof.items()},
+            "step_algorithmic_bytes": F * frame_bytes,
+            "step_achieved_gbs": world * F * frame_bytes / (step_ms * 1e-3) / 1e9,
+            "step_frac": F * frame_bytes / (step_ms * 1e-3) / 1e9 / peak,
+        }
+        # the binding roofline: fp32 FMA pipe (SURVEY 8d "report both")
+        flops_sample, flop_parts = algorithmic_flops(w, eng, nch)
+        sm_mhz = (sustained["clocks"]["sm_mhz"] if (sustained and value_source.startswith("sustained")) else
+                  clocks["sm_mhz"]) or clocks.get("sm_max_mhz") or 1965.0
+        sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
+        peak_tf = sms * 128 * 2 * sm_mhz * 1e6 / 1e12
+        ach_tf = flops_sample * (F * w.frame_len) / (step_ms * 1e-3) / 1e12
+        roofline_fp32 = {
+            "bound": "fp32", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf,
+            "peak_source": "%d SMs x 128 lanes x 2 FLOP x %.0f MHz (SM clock sampled during the run)" % (sms, sm_mhz),
+            "algorithmic_flop_per_input_sample": flops_sample,
+            "flop_parts_per_input_sample%s" % ("_per_channel" if nch > 1 else ""): {k: round(v, 3) for k, v in flop_parts.items()},
+            "scope": "whole step, one GPU",
         }
         cfg = workload_config(w, F)
         cfg["l2"] = "inputs larger than L2: %.0f MB per step per GPU" % (in_bytes / 1e6)
@@ -436,23 +601,39 @@ def run_b200(args, w):
         cfg["group_frames"] = args.group or "auto"
         cfg["decim_threads"] = args.decim_threads or "auto"
         if centres is not None:
+            cfg["stream_feed"] = ("rank 0 H2D + NCCL broadcast over NVLink" if bcast_feed else "H2D on every rank")
             cfg["channels_per_gpu"] = nch
             cfg["value_counts"] = "channel-samples: every virtual receiver consumes the whole stream"
         cfg["decimator_mode"] = "fast" if eng.fast_active else "exact"
         if host_affinity is not None:
             cfg["host_affinity_rank0"] = host_affinity
+        h2d_step = in_bytes if bcast_feed else world * in_bytes
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "warmup": args.warmup, "ms_per_step": ms_counted / steps_counted, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": cfg, "rows_per_s": world * nch * F * args.steps / (ms * 1e-3),
-            "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": world * in_bytes,
+            "config": cfg, "rows_per_s": world * nch * F * steps_counted / (ms_counted * 1e-3),
+            "value_source": value_source,
+            "burst": {"value": burst_value, "unit": UNIT, "steps": args.steps, "ms_per_step": ms / args.steps,
+                      "clocks": clocks},
+            "sustained": sustained,
+            "clocks": sustained["clocks"] if (sustained and value_source.startswith("sustained")) else clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_step,
                     "d2h_bytes_per_step": world * nch * F * W * 4, "steps": e2e_steps,
-                    "ms_per_step": ms_e2e / e2e_steps},
+                    "ms_per_step": ms_e2e / e2e_steps,
+                    "copy_only": {"value": copy_value, "unit": UNIT, "ms_per_step": ms_copy / e2e_steps,
+                                  "h2d_gbs": h2d_step / (ms_copy / e2e_steps * 1e-3) / 1e9,
+                                  "what": "the same pinned buffers over PCIe%s, no kernels"
+                                          % (" + the NCCL broadcast" if bcast_feed else "")},
+                    "e2e_over_copy_only": e2e_value / copy_value},
             "gpu_launches": launches,
             "roofline": roofline,
+            "roofline_fp32": roofline_fp32,
+            "reference_arm_note": "bench.py --impl reference runs the scipy port without the EMA (one "
+                                  "multiply-add per row bin: negligible)",
         }
+        if verify is not None:
+            line["multi_gpu_check"] = verify
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
         print(json.dumps(line), flush=True)
@@ -481,6 +662,10 @@ def main():
     ap.add_argument("--late-mix", type=int, default=None, help="tuning: 0 = always mix before the FIR chain")
     ap.add_argument("--lib", default=None, help="tuning: path of an alternative sm_100a build")
     ap.add_argument("--e2e-steps", type=int, default=20)
+    ap.add_argument("--sustain-s", type=float, default=3.0,
+                    help="seconds of back-to-back steps for the sustained leg (0 = skip)")
+    ap.add_argument("--cfg4-feed", default="broadcast", choices=["broadcast", "replicate"],
+                    help="cfg4, N > 1: H2D on rank 0 + NCCL broadcast over NVLink, or H2D on every rank")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-numa-bind", action="store_true",
                     help="N > 1: do not bind each rank to the CPUs of its GPU's NUMA node")

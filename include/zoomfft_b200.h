@@ -96,6 +96,9 @@ typedef struct zfb_config {
 int  zfb_abi_version(void);
 /* "sm_100a" for the product library. */
 const char *zfb_build_kind(void);
+/* sha256 of the sources and compiler flags this library was built from
+ * (pypanadapter_b200/build.py compares it with the tree before reusing a build). */
+const char *zfb_source_hash(void);
 /* create an engine on CUDA device `device`; fails with ZFB_ENODEV when there
  * is no GPU (no CPU fallback exists). */
 int  zfb_create(int device, zfb_engine **out);

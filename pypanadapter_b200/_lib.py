@@ -75,6 +75,7 @@ _P = C.c_void_p
 SYMBOLS = {
     "zfb_abi_version": (C.c_int, []),
     "zfb_build_kind": (C.c_char_p, []),
+    "zfb_source_hash": (C.c_char_p, []),
     "zfb_create": (C.c_int, [C.c_int, C.POINTER(_P)]),
     "zfb_destroy": (None, [_P]),
     "zfb_last_error": (C.c_char_p, [_P]),

@@ -33,18 +33,42 @@ def find_nvcc() -> str:
     return nvcc
 
 
-def up_to_date() -> bool:
+def source_hash() -> str:
+    """sha256 over every source file's name and bytes and the compiler flags: the
+    library carries it (zfb_source_hash), so "is this .so built from these
+    sources" is a comparison, not a guess from mtimes."""
+    import hashlib
+    h = hashlib.sha256()
+    h.update(" ".join(NVCC_FLAGS).encode())
+    for d in DEPS:
+        h.update(os.path.basename(d).encode() + b"\0")
+        with open(d, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
+def built_hash() -> str | None:
     if not os.path.isfile(OUT):
-        return False
-    t = os.path.getmtime(OUT)
-    return all(os.path.getmtime(d) <= t for d in DEPS)
+        return None
+    import ctypes
+    try:
+        lib = ctypes.CDLL(OUT, mode=ctypes.RTLD_LOCAL)
+        fn = lib.zfb_source_hash
+        fn.restype = ctypes.c_char_p
+        return fn().decode()
+    except (OSError, AttributeError):
+        return None
+
+
+def up_to_date() -> bool:
+    return built_hash() == source_hash()
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and up_to_date():
         return OUT
-    cmd = [find_nvcc(), *NVCC_FLAGS, "-I", os.path.join(ROOT, "include"), "-I", CSRC,
-           *SOURCES, "-o", OUT]
+    cmd = [find_nvcc(), *NVCC_FLAGS, '-DZFB_SOURCE_HASH="%s"' % source_hash(),
+           "-I", os.path.join(ROOT, "include"), "-I", CSRC, *SOURCES, "-o", OUT]
     if verbose:
         cmd += ["-Xptxas", "-v"]
         print(" ".join(cmd))

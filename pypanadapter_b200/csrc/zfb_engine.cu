@@ -1485,6 +1485,11 @@ int zfb_abi_version(void) { return ZFB_ABI_VERSION; }
 
 const char *zfb_build_kind(void) { return ZFB_BUILD_KIND; }
 
+#ifndef ZFB_SOURCE_HASH
+#define ZFB_SOURCE_HASH "unknown"
+#endif
+const char *zfb_source_hash(void) { return ZFB_SOURCE_HASH; }
+
 const char *zfb_last_error(const zfb_engine *e) {
     return e ? e->err.c_str() : g_create_error.c_str();
 }
