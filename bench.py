@@ -127,63 +127,72 @@ def run_reference(args, w):
 # --------------------------------------------------------------------------
 # clocks
 # --------------------------------------------------------------------------
-class ClockSampler(threading.Thread):
-    """Samples SM clock + throttle reasons of one GPU through NVML while the
-    timed region runs."""
+class ClockSampler:
+    """SM clock + clock-event reasons of one GPU while the timed regions run, sampled by
+    `nvidia-smi -lms` in its OWN process (B200_PROFILING.md's clocks line): an NVML thread
+    inside this process gets one sample per region -- its queries queue behind the kernel
+    launches on the driver's locks."""
     REASONS = {
         0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
         0x4: "sw_power_cap", 0x80: "hw_power_brake_slowdown",
     }
 
-    def __init__(self, uuid, index, period=0.02):
-        super().__init__(daemon=True)
-        self.period = period
-        self.samples = []        # (t, sm_mhz, reasons_mask)
+    def __init__(self, uuid, index, period_ms=50):
+        import subprocess
+        self.samples = []        # (unix time, sm_mhz, reasons_mask, power_w)
         self.max_mhz = None
-        self._halt = threading.Event()
-        self.ok = False
+        self.proc = None
+        self.err = None
+        self._lines = []
+        sel = uuid if (isinstance(uuid, str) and len(uuid) > 8) else str(index)
+        cmd = ["nvidia-smi", "-i", sel,
+               "--query-gpu=timestamp,clocks.sm,clocks.max.sm,clocks_event_reasons.active,power.draw",
+               "--format=csv,noheader,nounits", "-lms", str(int(period_ms))]
         try:
-            import pynvml
-            pynvml.nvmlInit()
-            self.nv = pynvml
-            try:
-                self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode() if isinstance(uuid, str) else uuid)
-            except Exception:
-                self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
-            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
-            self.ok = True
+            self.proc = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception as exc:          # pragma: no cover
             self.err = repr(exc)
+        self._thread = threading.Thread(target=self._pump, daemon=True)
 
-    def run(self):
-        if not self.ok:
-            return
-        nv = self.nv
-        while not self._halt.is_set():
+    def start(self):
+        if self.proc is not None:
+            self._thread.start()
+
+    def _pump(self):
+        import datetime
+        for ln in self.proc.stdout:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 5:
+                continue
             try:
-                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
-                try:
-                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
-                except Exception:
-                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                self.samples.append((time.perf_counter(), float(mhz), int(mask)))
-            except Exception:
-                pass
-            time.sleep(self.period)
+                t = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                mask = int(f[3], 16) if f[3].lower().startswith("0x") else 0
+                self.samples.append((t, float(f[1]), mask, float(f[4]) if f[4][:1].isdigit() else 0.0))
+                self.max_mhz = float(f[2])
+            except ValueError:
+                continue
 
     def stop(self):
-        self._halt.set()
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
 
     def summary(self, t0, t1):
-        inside = [s for s in self.samples if t0 <= s[0] <= t1] or self.samples
+        """t0, t1: time.time() bounds of the region"""
+        inside = [x for x in list(self.samples) if t0 <= x[0] <= t1]
         if not inside:
-            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0,
+                    "note": self.err or "no nvidia-smi sample fell inside the region"}
         mask = 0
-        for s in inside:
-            mask |= s[2]
+        for x in inside:
+            mask |= x[2]
         reasons = [name for bit, name in self.REASONS.items() if mask & bit]
-        return {"sm_mhz": float(np.median([s[1] for s in inside])), "sm_max_mhz": self.max_mhz,
-                "reasons": reasons, "samples": len(inside)}
+        return {"sm_mhz": float(np.median([x[1] for x in inside])), "sm_max_mhz": self.max_mhz,
+                "reasons": reasons, "samples": len(inside),
+                "power_w_max": max(x[3] for x in inside)}
 
 
 def measured_hbm_peak():
@@ -283,7 +292,10 @@ def run_b200(args, w):
             host_affinity = {"bound": False, "why": repr(exc)}
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        import datetime
+        # a mismatch between ranks must end the run in minutes, not hold the GPUs for the default 10
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank),
+                                timeout=datetime.timedelta(seconds=180))
 
     def barrier():
         if world > 1:
@@ -401,7 +413,7 @@ def run_b200(args, w):
     eng.profile()
     eng.set_profiling(True)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0 = time.perf_counter()
+    t0 = time.time()
     ev0.record(stream)
     for _ in range(args.steps):
         step_device()
@@ -409,12 +421,12 @@ def run_b200(args, w):
         stream.wait_event(gathered[(step_no[0] - 1) & 1])
     ev1.record(stream)
     barrier()
-    t1 = time.perf_counter()
+    t1 = time.time()
     ms = ev0.elapsed_time(ev1)
     eng.set_profiling(False)
     prof = eng.profile()
     launches = eng.counters()["kernels"] - k0
-    clocks = sampler.summary(t0, t1)
+    clocks = sampler.summary(t0 - 0.06, t1 + 0.06)     # K steps take milliseconds: the samples around them
 
     # ---------------- end to end (host buffers) ----------------
     for _ in range(max(1, min(args.warmup, 3))):
@@ -458,9 +470,14 @@ def run_b200(args, w):
     sustained = None
     if args.sustain_s > 0:
         n_sus = max(args.steps, int(np.ceil(args.sustain_s * 1e3 / max(ms / args.steps, 1e-3))))
+        if world > 1:
+            # every rank must issue the same number of gathers: take rank 0's count
+            nt = torch.tensor([n_sus], dtype=torch.int64, device="cuda")
+            dist.broadcast(nt, src=0)
+            n_sus = int(nt.item())
         barrier()
         ev6, ev7 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ts0 = time.perf_counter()
+        ts0 = time.time()
         ev6.record(stream)
         for i in range(n_sus):
             step_device()
@@ -470,7 +487,7 @@ def run_b200(args, w):
             stream.wait_event(gathered[(step_no[0] - 1) & 1])
         ev7.record(stream)
         barrier()
-        ts1 = time.perf_counter()
+        ts1 = time.time()
         sustained = {"ms": ev6.elapsed_time(ev7), "steps": n_sus, "clocks": sampler.summary(ts0, ts1)}
     sampler.stop()
 
@@ -583,8 +600,8 @@ def run_b200(args, w):
         }
         # the binding roofline: fp32 FMA pipe (SURVEY 8d "report both")
         flops_sample, flop_parts = algorithmic_flops(w, eng, nch)
-        sm_mhz = (sustained["clocks"]["sm_mhz"] if (sustained and value_source.startswith("sustained")) else
-                  clocks["sm_mhz"]) or clocks.get("sm_max_mhz") or 1965.0
+        sm_mhz = ((sustained["clocks"]["sm_mhz"] if sustained else None) or clocks["sm_mhz"] or
+                  clocks.get("sm_max_mhz") or 1965.0)
         sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
         peak_tf = sms * 128 * 2 * sm_mhz * 1e6 / 1e12
         ach_tf = flops_sample * (F * w.frame_len) / (step_ms * 1e-3) / 1e12
@@ -617,7 +634,8 @@ def run_b200(args, w):
             "burst": {"value": burst_value, "unit": UNIT, "steps": args.steps, "ms_per_step": ms / args.steps,
                       "clocks": clocks},
             "sustained": sustained,
-            "clocks": sustained["clocks"] if (sustained and value_source.startswith("sustained")) else clocks,
+            # the long leg holds >= 50 samples; the K-step burst lasts milliseconds (see burst.clocks)
+            "clocks": sustained["clocks"] if (sustained and sustained["clocks"].get("samples", 0) > clocks.get("samples", 0)) else clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_step,
                     "d2h_bytes_per_step": world * nch * F * W * 4, "steps": e2e_steps,
                     "ms_per_step": ms_e2e / e2e_steps,

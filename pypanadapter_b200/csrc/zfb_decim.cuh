@@ -379,19 +379,22 @@ __device__ __forceinline__ void exact_stage_inplace(float2 *buf, float2 *zbuf, i
     constexpr int LB = (B == 64) ? 6 : 5;
     constexpr int JT = (B == BLK) ? JTERMS : JTERMS32;
     // odd extension (scipy odd_ext, 27 samples each side) where it falls in the region
-    if (tid < PADLEN) {
-        const int pos = -1 - tid;                 // 2*x[0] - x[-pos]
-        const int q = pos - rs;
-        if (q >= 0) {
-            float2 x0 = buf[sidx<B>(-rs)], xm = buf[sidx<B>(-pos - rs)];
-            buf[sidx<B>(q)] = make_float2(2.f * x0.x - xm.x, 2.f * x0.y - xm.y);
-        }
-    } else if (tid >= 32 && tid < 32 + PADLEN) {
-        const int pos = L + (tid - 32);           // 2*x[L-1] - x[2(L-1)-pos]
-        const int q = pos - rs;
-        if (q < REGION) {
-            float2 x1 = buf[sidx<B>(L - 1 - rs)], xm = buf[sidx<B>(2 * (L - 1) - pos - rs)];
-            buf[sidx<B>(q)] = make_float2(2.f * x1.x - xm.x, 2.f * x1.y - xm.y);
+    // (slots 0..26: left pad, 32..58: right pad; one-warp CTAs take two turns)
+    for (int slot = tid; slot < 32 + PADLEN; slot += NT) {
+        if (slot < PADLEN) {
+            const int pos = -1 - slot;                // 2*x[0] - x[-pos]
+            const int q = pos - rs;
+            if (q >= 0) {
+                float2 x0 = buf[sidx<B>(-rs)], xm = buf[sidx<B>(-pos - rs)];
+                buf[sidx<B>(q)] = make_float2(2.f * x0.x - xm.x, 2.f * x0.y - xm.y);
+            }
+        } else if (slot >= 32) {
+            const int pos = L + (slot - 32);          // 2*x[L-1] - x[2(L-1)-pos]
+            const int q = pos - rs;
+            if (q < REGION) {
+                float2 x1 = buf[sidx<B>(L - 1 - rs)], xm = buf[sidx<B>(2 * (L - 1) - pos - rs)];
+                buf[sidx<B>(q)] = make_float2(2.f * x1.x - xm.x, 2.f * x1.y - xm.y);
+            }
         }
     }
     __syncthreads();
@@ -498,31 +501,43 @@ __global__ void __launch_bounds__(NT, (NT == NTHR_BIG ? 1 : 3)) decim2_exact_ker
         if (i >= wlo && i < whi) out[i] = buf[sidx(WARM + 2 * i)];
 }
 
-// ZFB_MODE_FAST edge strips: the whole exact cascade on one short chunk cut from
-// a frame's left (side 0) or right (side 1) end, in ONE CTA: stage s leaves its
-// outputs in shared memory, the part the next stage needs is compacted to the
-// front of the region, and only the last stage's `keep` outputs reach global
-// memory (they overwrite the FIR interior's values at the chunk edge).
-// (measured: 256 threads x 32-sample runs -- half the serial chain per thread, but twice
-// the hand-off terms and 2 CTAs/SM -- is 36 % SLOWER than 128 x 64; the run length stays
-// a template parameter of the stage body)
-constexpr int STRIP_NT = 128;
+// ZFB_MODE_FAST edge strips: the exact cascade on one short chunk cut from a frame's left
+// (side 0) or right (side 1) end.  A launch runs `nstages` consecutive stages of every strip
+// in ONE CTA (stage s leaves its outputs in shared memory, the part the next stage needs is
+// compacted to the front of the region) with NT = region / 64 threads; the strip halves in
+// length from stage to stage, so the cascade is cut into launches whose regions fit the
+// strip -- 8192 samples (128 threads) for the first stage of R = 16, 2048 (one warp) for the
+// last two -- instead of dragging 128 threads, of which 9 to 23 hold samples, and 75 KB of
+// shared memory through the late stages (round 1: 26 % of the cfg2 step).  Between launches
+// the strips live in a small global buffer [frame][side][cap]; the last launch writes the
+// `keep` outputs at the chunk's end.
+// (measured in round 1: 256 threads x 32-sample runs -- half the serial chain per thread, but
+// twice the hand-off terms -- is 36 % SLOWER than 64-sample runs; the run length stays a
+// template parameter of the stage body)
+constexpr int STRIP_NT = 128;          // widest region (stage 0 of the fused cascades; LO tables are built for it)
 constexpr int STRIP_BLK = 64;
-constexpr size_t strip_smem() { return (size_t)(STRIP_NT * (STRIP_BLK + 1) + NSTATE * STRIP_NT) * sizeof(float2); }
+constexpr size_t strip_smem(int nt = STRIP_NT) { return (size_t)(nt * (STRIP_BLK + 1) + NSTATE * nt) * sizeof(float2); }
+// threads a stage of `len` input samples needs: lead-in WARM, the samples, the odd extension
+__host__ __device__ constexpr int strip_threads_for(int len) {
+    return (WARM + len + PADLEN + STRIP_BLK) / STRIP_BLK <= 32 ? 32 : ((WARM + len + PADLEN + STRIP_BLK) / STRIP_BLK <= 64 ? 64 : 128);
+}
 
 struct StripParams {
-    StageParams st;            // stage 0 load: in, in_stride, L = len[0], flip, Lfull, pos_off, LO tables
-    int   nstages;
-    int   len[16];             // strip length at the input of stage s
+    StageParams st;            // first stage's load: in, in_stride, side_in_off, L = len[0], flip, Lfull, pos_off, LO tables
+    int   nstages;             // stages fused in this launch
+    int   len[16];             // strip length at the input of stage s of this launch
+    int   last;                // 1: the launch ends the cascade and writes `keep` outputs to out
     int   keep;                // outputs of the last stage that are written (K)
     float2 *out;               // decimated chunks [frames][out_stride]
     long long out_stride;
     int   ndec;                // decimated chunk length
+    float2 *mid_out;           // !last: [frames][2][mid_cap] first / last next_len outputs of the launch's last stage
+    long long mid_cap;
+    int   next_len;
 };
 
-template <int KIND, bool CHAN = false>
-__global__ void __launch_bounds__(STRIP_NT, 3) strip_cascade_kernel(const StripParams sp) {
-    constexpr int NT = STRIP_NT;
+template <int KIND, bool CHAN = false, int NT = STRIP_NT>
+__global__ void __launch_bounds__(NT, (NT == 128 ? 3 : (NT == 64 ? 6 : 12))) strip_cascade_kernel(const StripParams sp) {
     constexpr int B = STRIP_BLK;
     ZFB_DYN_SMEM(smem_raw);
     float2 *buf  = reinterpret_cast<float2 *>(smem_raw);
@@ -546,10 +561,17 @@ __global__ void __launch_bounds__(STRIP_NT, 3) strip_cascade_kernel(const StripP
         exact_stage_inplace<NT, B>(buf, zbuf, L, rs, tid);
         const int nout = (L + 1) >> 1;
         if (s == sp.nstages - 1) {
-            float2 *out = sp.out + (size_t)frame * (size_t)sp.out_stride;
-            const int m0 = side ? nout - sp.keep : 0;
-            const int d0 = side ? sp.ndec - sp.keep : 0;
-            for (int i = tid; i < sp.keep; i += NT) out[d0 + i] = buf[sidx<B>(WARM + 2 * (m0 + i))];
+            if (sp.last) {
+                float2 *out = sp.out + (size_t)frame * (size_t)sp.out_stride;
+                const int m0 = side ? nout - sp.keep : 0;
+                const int d0 = side ? sp.ndec - sp.keep : 0;
+                for (int i = tid; i < sp.keep; i += NT) out[d0 + i] = buf[sidx<B>(WARM + 2 * (m0 + i))];
+            } else {
+                // hand the next launch its input: the first (side 0) / last (side 1) next_len outputs
+                float2 *out = sp.mid_out + ((size_t)frame * 2 + (size_t)side) * (size_t)sp.mid_cap;
+                const int off = side ? nout - sp.next_len : 0;
+                for (int j = tid; j < sp.next_len; j += NT) out[j] = buf[sidx<B>(WARM + 2 * (off + j))];
+            }
         } else {
             // the next stage works on the first (side 0) / last (side 1) len[s+1] outputs:
             // move them, gain-scaled, to region positions WARM + j.  dst <= src, so

@@ -59,6 +59,7 @@ struct zfb_engine {
     cudaStream_t aux_stream = nullptr;           // edge strips of mode fast run beside the FIR interior
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int strips_async = 1;                        // zfb_set_option("strips_async")
+    int strip_split = 1;                         // zfb_set_option("strip_split"): narrower regions for the late strip stages
     int ring_append = 1;                         // zfb_set_option("ring_append"): processed rows enter the ring
     int late_mix = 1;                            // zfb_set_option("late_mix"): FIR chain may mix at its output
     int iir_stream = 1;                          // zfb_set_option("iir_stream"): streaming last stage of mode fast
@@ -576,6 +577,10 @@ int setup_device_once(zfb_engine *e) {
                                (int)strip_smem()));
     CK(e, cudaFuncSetAttribute(strip_cascade_kernel<KIND_C64_MID>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)strip_smem()));
+    CK(e, cudaFuncSetAttribute((strip_cascade_kernel<KIND_C64_MID, false, 64>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)strip_smem(64)));
+    CK(e, cudaFuncSetAttribute((strip_cascade_kernel<KIND_C64_MID, false, 32>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)strip_smem(32)));
     CK(e, cudaFuncSetAttribute((strip_cascade_kernel<KIND_U8_RAW, true>), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)strip_smem()));
     CK(e, cudaFuncSetAttribute((strip_cascade_kernel<KIND_C64_RAW, true>), cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -827,67 +832,92 @@ void launch_stage(zfb_engine *e, int kind, int v, const StageParams &p, unsigned
 // chunks in mid[*out_buf]
 // the fused tail (up to 4 stages) of the exact edge strips, one CTA per strip,
 // writing the first / last K samples of the decimated chunks in `final_out`
+template <int NT>
+void launch_strip_mid(const StripParams &sp, dim3 grid, cudaStream_t st) {
+    ZFB_LAUNCH((strip_cascade_kernel<KIND_C64_MID, false, NT>), grid, dim3(NT), strip_smem(NT), st, sp);
+}
+
 void launch_fused_strips(zfb_engine *e, const void *d_in, int gf, float2 *final_out, cudaStream_t st) {
     const zfb_config &c = e->cfg;
     const int k = e->nstages;
     const int kf = k < 4 ? k : 4;
     const int s0 = k - kf;
     const long long cap = e->strip_cap;
-    StripParams sp{};
-    sp.st = e->sp0[STRIP_NT == NTHR_BIG ? 0 : 1];   // LO tables for STRIP_NT threads per CTA
-    sp.st.L = e->strip_len[s0];
-    sp.st.T = 0;
-    sp.st.strips = 1;
-    int skind;
-    if (s0 == 0) {
-        skind = raw_kind(c);
-        sp.st.in = d_in;
-        sp.st.in_stride = c.frame_len;
-        sp.st.side_in_off = 0;
-        sp.st.flip = c.flip;
-        sp.st.pos_off = e->strip_q[0];
-        sp.st.Lfull = c.frame_len;
-    } else {
-        skind = KIND_C64_MID;
-        sp.st.in = e->sbuf[(s0 - 1) & 1].p;
-        sp.st.in_stride = 2 * cap;
-        sp.st.side_in_off = cap + (e->strip_q[s0] - e->strip_q[s0 - 1] / 2);
-        sp.st.flip = 0;
-        sp.st.pos_off = 0;
-        sp.st.Lfull = sp.st.L;
-    }
-    sp.nstages = kf;
-    for (int s = 0; s < kf; ++s) sp.len[s] = e->strip_len[s0 + s];
-    sp.keep = e->fplan.K;
-    if (e->iis.active) {
-        // compact [frame][side][K]: patched into the chunks once the streaming last stage is done
-        sp.out = (float2 *)e->strip_out.p;
-        sp.out_stride = 2 * e->fplan.K;
-        sp.ndec = 2 * e->fplan.K;
-    } else {
-        sp.out = final_out;
-        sp.out_stride = final_stride(e);
-        sp.ndec = e->len[k];
-    }
-    const int pr = prof_begin(e, 15, st);
     const dim3 grid(2, (unsigned)gf);
-    if (e->cur_nch > 0 && s0 == 0) {
-        sp.st.chan = (const ChannelLo *)e->chan_dev.p;
-        sp.st.chan_frames = e->cur_chan_frames;
-        if (skind == KIND_U8_RAW) {
-            ZFB_LAUNCH((strip_cascade_kernel<KIND_U8_RAW, true>), grid, dim3(STRIP_NT), strip_smem(), st, sp);
+    const int pr = prof_begin(e, 15, st);
+    // the strips halve from stage to stage: consecutive stages that fit the same region size
+    // share a launch, a narrower region starts a new one (strip_cascade_kernel)
+    bool from_fused = false;            // the input was left by a fused launch (exactly the samples needed)
+    for (int a = s0; a < k;) {
+        int nt = (a == 0 || !e->strip_split) ? STRIP_NT : strip_threads_for(e->strip_len[a]);
+        int b = a + 1;
+        while (b < k && (!e->strip_split || strip_threads_for(e->strip_len[b]) == nt)) ++b;
+        StripParams sp{};
+        sp.st = e->sp0[STRIP_NT == NTHR_BIG ? 0 : 1];   // LO tables for STRIP_NT threads per CTA
+        sp.st.L = e->strip_len[a];
+        sp.st.T = 0;
+        sp.st.strips = 1;
+        int skind;
+        if (a == 0) {
+            skind = raw_kind(c);
+            sp.st.in = d_in;
+            sp.st.in_stride = c.frame_len;
+            sp.st.side_in_off = 0;
+            sp.st.flip = c.flip;
+            sp.st.pos_off = e->strip_q[0];
+            sp.st.Lfull = c.frame_len;
         } else {
-            ZFB_LAUNCH((strip_cascade_kernel<KIND_C64_RAW, true>), grid, dim3(STRIP_NT), strip_smem(), st, sp);
+            skind = KIND_C64_MID;
+            sp.st.in = e->sbuf[(a - 1) & 1].p;
+            sp.st.in_stride = 2 * cap;
+            sp.st.side_in_off = from_fused ? cap : cap + (e->strip_q[a] - e->strip_q[a - 1] / 2);
+            sp.st.flip = 0;
+            sp.st.pos_off = 0;
+            sp.st.Lfull = sp.st.L;
         }
-    } else if (skind == KIND_U8_RAW) {
-        ZFB_LAUNCH(strip_cascade_kernel<KIND_U8_RAW>, grid, dim3(STRIP_NT), strip_smem(), st, sp);
-    } else if (skind == KIND_C64_RAW) {
-        ZFB_LAUNCH(strip_cascade_kernel<KIND_C64_RAW>, grid, dim3(STRIP_NT), strip_smem(), st, sp);
-    } else {
-        ZFB_LAUNCH(strip_cascade_kernel<KIND_C64_MID>, grid, dim3(STRIP_NT), strip_smem(), st, sp);
+        sp.nstages = b - a;
+        for (int s = a; s < b; ++s) sp.len[s - a] = e->strip_len[s];
+        sp.last = (b == k) ? 1 : 0;
+        sp.keep = e->fplan.K;
+        if (e->iis.active) {
+            // compact [frame][side][K]: patched into the chunks once the streaming last stage is done
+            sp.out = (float2 *)e->strip_out.p;
+            sp.out_stride = 2 * e->fplan.K;
+            sp.ndec = 2 * e->fplan.K;
+        } else {
+            sp.out = final_out;
+            sp.out_stride = final_stride(e);
+            sp.ndec = e->len[k];
+        }
+        if (!sp.last) {
+            sp.mid_out = (float2 *)e->sbuf[(b - 1) & 1].p;
+            sp.mid_cap = cap;
+            sp.next_len = e->strip_len[b];
+        }
+        if (e->cur_nch > 0 && a == 0) {
+            sp.st.chan = (const ChannelLo *)e->chan_dev.p;
+            sp.st.chan_frames = e->cur_chan_frames;
+            if (skind == KIND_U8_RAW) {
+                ZFB_LAUNCH((strip_cascade_kernel<KIND_U8_RAW, true>), grid, dim3(STRIP_NT), strip_smem(), st, sp);
+            } else {
+                ZFB_LAUNCH((strip_cascade_kernel<KIND_C64_RAW, true>), grid, dim3(STRIP_NT), strip_smem(), st, sp);
+            }
+        } else if (skind == KIND_U8_RAW) {
+            ZFB_LAUNCH(strip_cascade_kernel<KIND_U8_RAW>, grid, dim3(STRIP_NT), strip_smem(), st, sp);
+        } else if (skind == KIND_C64_RAW) {
+            ZFB_LAUNCH(strip_cascade_kernel<KIND_C64_RAW>, grid, dim3(STRIP_NT), strip_smem(), st, sp);
+        } else if (nt == 32) {
+            launch_strip_mid<32>(sp, grid, st);
+        } else if (nt == 64) {
+            launch_strip_mid<64>(sp, grid, st);
+        } else {
+            launch_strip_mid<128>(sp, grid, st);
+        }
+        e->counters[2] += 1;
+        from_fused = true;
+        a = b;
     }
     prof_end(e, pr, st);
-    e->counters[2] += 1;
 }
 
 // ZFB_MODE_FAST: FIR chains + exact last stage over the whole frames, and the
@@ -1297,7 +1327,7 @@ int plan_fast(zfb_engine *e) {
     if (!e->fast_active) return ZFB_OK;
     const int k = e->nstages;
     e->strip_cap = (e->strip_len[0] + 1) / 2 + 8;
-    for (int i = 0; i < 2 && k > 4; ++i) {      // only deep zooms run strip stages through global memory
+    for (int i = 0; i < 2; ++i) {               // the strips' hand-off between launches
         int rc = ensure(e, e->sbuf[i], (size_t)e->group * 2 * (size_t)e->strip_cap * sizeof(float2));
         if (rc) return rc;
     }
@@ -1858,6 +1888,10 @@ int zfb_set_option(zfb_engine *e, const char *name, long long value) {
     }
     if (strcmp(name, "strips_async") == 0) {
         e->strips_async = (value == 2) ? 2 : (value ? 1 : 0);
+        return ZFB_OK;
+    }
+    if (strcmp(name, "strip_split") == 0) {
+        e->strip_split = value ? 1 : 0;
         return ZFB_OK;
     }
     if (strcmp(name, "late_mix") == 0) {
