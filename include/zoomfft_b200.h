@@ -242,6 +242,23 @@ int  zfb_ring_quantiles(zfb_engine *e, int height, int scroll, int64_t rows_seen
                         const double *q, int nq, double *out_values,
                         int64_t *out_count);
 
+/* ---- taper design and preview on the device ----------------
+ * The taper dialog's live preview (FFTTaperingControl.ShowCurve, S:1354-1379):
+ * zfb_taper_design replaces scipy.signal.get_window(AppState.fft_tapering, 51)
+ * (S:1366) for the closed-form families of its taper_list (S:1222-1243), in
+ * fp64 on the device; `periodic` = get_window's fftbins=True.  kind:
+ *   0 boxcar 1 triang 2 bartlett 3 hann 4 hamming 5 blackman 6 nuttall
+ *   7 blackmanharris 8 flattop 9 bohman 10 barthann 11 parzen 12 kaiser(p0=beta)
+ *   13 gaussian(p0=std) 14 general gaussian(p0=power, p1=std)
+ *   15 exponential(p0=center, p1=tau) 16 tukey(p0=taper fraction)
+ * (chebwin / dpss / slepian need a polynomial design or an eigenproblem: host.)
+ * zfb_taper_preview replaces S:1374-1376: h_db_out[k] = 20*log10(|FFT(taper
+ * zero-padded to nfft)[k]| / max_k |.|), nfft float32 values. */
+int  zfb_taper_design(zfb_engine *e, int kind, double p0, double p1, int n,
+                      int periodic, double *h_out);
+int  zfb_taper_preview(zfb_engine *e, const double *taper, int ntaps, int nfft,
+                       float *h_db_out);
+
 /* ---- pinned sample ring with double-buffered device mirror -------------
  * Replaces Data.data (T:1415-1421) and the copy-in of Data.add (T:1447): the
  * producer thread writes chunks into pinned host memory and each chunk is sent

@@ -101,6 +101,8 @@ SYMBOLS = {
     "zfb_ring_image": (C.c_int, [_P, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_double, C.c_double, _P, _P, C.c_int]),
     "zfb_ring_quantiles": (C.c_int, [_P, C.c_int, C.c_int, C.c_int64, C.POINTER(C.c_double), C.c_int,
                                      C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
+    "zfb_taper_design": (C.c_int, [_P, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, C.POINTER(C.c_double)]),
+    "zfb_taper_preview": (C.c_int, [_P, C.POINTER(C.c_double), C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "zfb_samples_create": (C.c_int, [_P, C.c_int64, C.c_int]),
     "zfb_samples_host_ptr": (_P, [_P]),
     "zfb_samples_begin_write": (C.c_int, [_P, C.c_int64, C.c_int64]),

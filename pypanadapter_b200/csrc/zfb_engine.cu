@@ -27,6 +27,7 @@
 #include "zfb_firchain.cuh"
 #include "zfb_iirstream.cuh"
 #include "zfb_image.cuh"
+#include "zfb_taper.cuh"
 
 using namespace zfb;
 
@@ -60,10 +61,12 @@ struct zfb_engine {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int strips_async = 1;                        // zfb_set_option("strips_async")
     int strip_split = 1;                         // zfb_set_option("strip_split"): narrower regions for the late strip stages
+    int strip_decay = 320;                       // zfb_set_option("strip_decay"): samples between a strip's cut and its outputs
     int ring_append = 1;                         // zfb_set_option("ring_append"): processed rows enter the ring
     int late_mix = 1;                            // zfb_set_option("late_mix"): FIR chain may mix at its output
     int iir_stream = 1;                          // zfb_set_option("iir_stream"): streaming last stage of mode fast
     int iir_S = 640, iir_Wm = 256;               // zfb_set_option("iir_stream_len" (target) / "iir_stream_warm")
+    int iir_l2_keep = 70;                        // zfb_set_option("iir_l2_keep"): % of a stream's blocks kept in L2
     // plan of the streaming last stage (zfb_iirstream.cuh), valid while iis.active
     struct IirStreamPlan {
         bool active = false;
@@ -72,6 +75,7 @@ struct zfb_engine {
         int tail = 0;                                // samples [L, nspf*S) of every input frame kept at zero
         TensorMap tm_in, tm_out;
     } iis;
+    DevBuf taper_buf;                            // window design / preview scratch (zfb_taper.cuh)
     DevBuf strip_out;                            // [group][2][K] edge samples of the strips, patched in afterwards
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
     bool slot_busy[2] = {false, false};
@@ -85,6 +89,7 @@ struct zfb_engine {
     int decim_threads = 0;             // 0 = automatic per launch
     int welch_splits = 0;              // 0 = automatic
     int fir_generic = 0;               // 1: never use the register-blocked FIR kernel (tests)
+    int fir_threads = FIR_NT;          // zfb_set_option("fir_threads"): 256 or 128 threads per CTA of fir_run_kernel
     int nperseg = 0, hop = 0, nseg = 0, W = 0, log2N = 0;
     int Wp = 0;                        // width of a pow row: W, or N for one-sided rows
     bool onesided = false;             // ZFB_FLAG_ONESIDED
@@ -619,7 +624,9 @@ bool fast_wanted(const zfb_engine *e, int *strip_len, int *strip_q) {
     if (c.mode != ZFB_MODE_FAST || k < 2 || !e->fplan.set || e->fplan.ne != k - 1) return false;
     // strips: i_{k-1} = 2K + D, i_s = 2 i_{s+1} + D, right strip starts at an even position
     const int K = e->fplan.K;
-    const int D = 320;                 // >= WARM: the artificial strip edge has decayed (0.935^320 = 5e-10)
+    // decay distance of a strip's artificial inner edge: 0.935^D of that edge's transient is left
+    // where the strip's outputs are used (320: 5e-10, 256: 3e-8, 192: 2.5e-6 = 2e-5 dB)
+    const int D = e->strip_decay;
     int need = 2 * K + D;
     for (int s = k - 1; s >= 0; --s) {
         int i = need;
@@ -739,18 +746,18 @@ void prof_end(zfb_engine *e, int idx, cudaStream_t on = nullptr) {
     X(5, KIND, 2, 3, 3, 0, -1)   \
     X(6, KIND, 3, 3, 3, 3, -1)
 
-template <int KIND>
+template <int KIND, int NT>
 void launch_fir_run_kind(int variant, const FirRunParams &rp, int L_out, int gf, cudaStream_t st) {
 #define ZFB_X(ID, K, NS, A, B, C, D)                                                              \
     if (variant == ID) {                                                                          \
-        using SH = FirRunShape<NS, A, B, C, D>;                                                   \
+        using SH = FirRunShape<NS, A, B, C, D, NT>;                                               \
         const int per_tile = SH::SPAN >> NS;                                                      \
         const unsigned tiles = (unsigned)((L_out + per_tile - 1) / per_tile);                     \
         if (K != KIND_C64_MID && rp.chan) {                                                       \
-            ZFB_LAUNCH((fir_run_kernel<K, NS, A, B, C, D, (K != KIND_C64_MID)>), dim3(tiles, (unsigned)gf), \
-                       dim3(FIR_NT), SH::SMEM, st, rp);                                           \
+            ZFB_LAUNCH((fir_run_kernel<K, NS, A, B, C, D, (K != KIND_C64_MID), NT>), dim3(tiles, (unsigned)gf), \
+                       dim3(NT), SH::SMEM, st, rp);                                               \
         } else {                                                                                  \
-            ZFB_LAUNCH((fir_run_kernel<K, NS, A, B, C, D>), dim3(tiles, (unsigned)gf), dim3(FIR_NT), SH::SMEM, st, rp); \
+            ZFB_LAUNCH((fir_run_kernel<K, NS, A, B, C, D, false, NT>), dim3(tiles, (unsigned)gf), dim3(NT), SH::SMEM, st, rp); \
         }                                                                                         \
         return;                                                                                   \
     }
@@ -758,10 +765,16 @@ void launch_fir_run_kind(int variant, const FirRunParams &rp, int L_out, int gf,
 #undef ZFB_X
 }
 
-void launch_fir_run(int variant, int kind, const FirRunParams &rp, int L_out, int gf, cudaStream_t st) {
-    if (kind == KIND_U8_RAW) launch_fir_run_kind<KIND_U8_RAW>(variant, rp, L_out, gf, st);
-    else if (kind == KIND_C64_RAW) launch_fir_run_kind<KIND_C64_RAW>(variant, rp, L_out, gf, st);
-    else launch_fir_run_kind<KIND_C64_MID>(variant, rp, L_out, gf, st);
+void launch_fir_run(int variant, int kind, const FirRunParams &rp, int L_out, int gf, cudaStream_t st, int nt) {
+    if (nt == 128) {
+        if (kind == KIND_U8_RAW) launch_fir_run_kind<KIND_U8_RAW, 128>(variant, rp, L_out, gf, st);
+        else if (kind == KIND_C64_RAW) launch_fir_run_kind<KIND_C64_RAW, 128>(variant, rp, L_out, gf, st);
+        else launch_fir_run_kind<KIND_C64_MID, 128>(variant, rp, L_out, gf, st);
+        return;
+    }
+    if (kind == KIND_U8_RAW) launch_fir_run_kind<KIND_U8_RAW, FIR_NT>(variant, rp, L_out, gf, st);
+    else if (kind == KIND_C64_RAW) launch_fir_run_kind<KIND_C64_RAW, FIR_NT>(variant, rp, L_out, gf, st);
+    else launch_fir_run_kind<KIND_C64_MID, FIR_NT>(variant, rp, L_out, gf, st);
 }
 
 // which specialised variant (0 = none) handles this chain
@@ -782,9 +795,14 @@ int fir_run_setup_kind(zfb_engine *e) {
 #define ZFB_X(ID, K, NS, A, B, C, D)                                                              \
     CK(e, cudaFuncSetAttribute((fir_run_kernel<K, NS, A, B, C, D>), cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                (int)FirRunShape<NS, A, B, C, D>::SMEM));                          \
-    if (K != KIND_C64_MID)                                                                        \
+    CK(e, cudaFuncSetAttribute((fir_run_kernel<K, NS, A, B, C, D, false, 128>), cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                               (int)FirRunShape<NS, A, B, C, D, 128>::SMEM));                     \
+    if (K != KIND_C64_MID) {                                                                      \
         CK(e, cudaFuncSetAttribute((fir_run_kernel<K, NS, A, B, C, D, (K != KIND_C64_MID)>),      \
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FirRunShape<NS, A, B, C, D>::SMEM));
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FirRunShape<NS, A, B, C, D>::SMEM)); \
+        CK(e, cudaFuncSetAttribute((fir_run_kernel<K, NS, A, B, C, D, (K != KIND_C64_MID), 128>), \
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FirRunShape<NS, A, B, C, D, 128>::SMEM)); \
+    }
     ZFB_RUN_COMBOS(ZFB_X, KIND)
 #undef ZFB_X
     return ZFB_OK;
@@ -970,7 +988,7 @@ cudaError_t run_decimation_fast(zfb_engine *e, const void *d_in, int gf, int *ou
                 rp.chan = (const ChannelLo *)e->chan_dev.p;
                 rp.chan_frames = e->cur_chan_frames;
             }
-            launch_fir_run(e->chain_run[j], kind, rp, e->len[lvl], gf, st);
+            launch_fir_run(e->chain_run[j], kind, rp, e->len[lvl], gf, st, e->fir_threads);
         } else {
             const unsigned tiles = (unsigned)((e->len[lvl] + p.TO - 1) / p.TO);
             ZFB_LAUNCH(chain_lookup(kind), dim3(tiles, (unsigned)gf), dim3(FIR_NT), e->chain_smem[j], st, p);
@@ -1429,6 +1447,7 @@ void plan_iir_stream(zfb_engine *e) {
     pl.q.Wb = Wb;
     pl.q.nspf = nspf;
     pl.q.groups = (nspf + 31) / 32;
+    pl.q.keep_from = S16 - (int)((long long)S16 * e->iir_l2_keep / 100);
     pl.in_stride = stride4((long long)nspf * S);
     pl.out_stride = stride4((long long)nspf * (S / 2));
     pl.tail = nspf * S - L;
@@ -1597,6 +1616,7 @@ void zfb_destroy(zfb_engine *e) {
     release(e->chan_dev);
     release(e->cvt);
     release(e->strip_out);
+    release(e->taper_buf);
     if (e->sr_copied) cudaEventDestroy(e->sr_copied);
     for (int i = 0; i < 2; ++i) if (e->sr_free[i]) cudaEventDestroy(e->sr_free[i]);
     if (e->h_rows) cudaFreeHost(e->h_rows);
@@ -1890,6 +1910,12 @@ int zfb_set_option(zfb_engine *e, const char *name, long long value) {
         e->strips_async = (value == 2) ? 2 : (value ? 1 : 0);
         return ZFB_OK;
     }
+    if (strcmp(name, "strip_decay") == 0) {
+        if (value < 64 || value > 1024 || (value & 1)) return fail(e, ZFB_EINVAL, "strip_decay must be even and in [64, 1024]");
+        e->strip_decay = (int)value;
+        e->configured = false;
+        return ZFB_OK;
+    }
     if (strcmp(name, "strip_split") == 0) {
         e->strip_split = value ? 1 : 0;
         return ZFB_OK;
@@ -1911,6 +1937,12 @@ int zfb_set_option(zfb_engine *e, const char *name, long long value) {
         e->configured = false;
         return ZFB_OK;
     }
+    if (strcmp(name, "iir_l2_keep") == 0) {
+        if (value < 0 || value > 100) return fail(e, ZFB_EINVAL, "iir_l2_keep is a percentage");
+        e->iir_l2_keep = (int)value;
+        e->configured = false;
+        return ZFB_OK;
+    }
     if (strcmp(name, "iir_stream_warm") == 0) {
         if (value < 2 * IS_BLK || value > 4096 || value % IS_BLK)
             return fail(e, ZFB_EINVAL, "iir_stream_warm must be a multiple of %d in [%d, 4096]", IS_BLK, 2 * IS_BLK);
@@ -1920,6 +1952,11 @@ int zfb_set_option(zfb_engine *e, const char *name, long long value) {
     }
     if (strcmp(name, "ring_append") == 0) {
         e->ring_append = value ? 1 : 0;
+        return ZFB_OK;
+    }
+    if (strcmp(name, "fir_threads") == 0) {
+        if (value != 128 && value != FIR_NT) return fail(e, ZFB_EINVAL, "fir_threads must be 128 or %d", FIR_NT);
+        e->fir_threads = (int)value;
         return ZFB_OK;
     }
     if (strcmp(name, "fir_generic") == 0) {
@@ -2628,6 +2665,60 @@ int zfb_samples_process(zfb_engine *e, float *h_row) {
     CK(e, cudaStreamSynchronize(e->stream));
     memcpy(h_row, e->h_rows, (size_t)e->W * sizeof(float));
     e->counters[4] += (size_t)e->W * sizeof(float);
+    return ZFB_OK;
+}
+
+// ---- taper design and preview on the device (zfb_taper.cuh) -------------------
+int zfb_taper_design(zfb_engine *e, int kind, double p0, double p1, int n, int periodic, double *h_out) {
+    if (!e) return ZFB_EINVAL;
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (kind < 0 || kind >= TAPER_COUNT) return fail(e, ZFB_EINVAL, "taper kind %d is not designed on the device", kind);
+    if (n < 1 || n > (1 << 24) || !h_out) return fail(e, ZFB_EINVAL, "taper design: bad arguments");
+    if ((kind == TAPER_GAUSSIAN && !(p0 > 0.0)) || (kind == TAPER_GENERAL_GAUSSIAN && !(p1 > 0.0)) ||
+        (kind == TAPER_EXPONENTIAL && !(p1 > 0.0)) || (kind == TAPER_KAISER && !(p0 == p0)))
+        return fail(e, ZFB_EINVAL, "taper design: bad shape parameter");
+    CK(e, cudaSetDevice(e->device));
+    int rc = ensure(e, e->taper_buf, (size_t)n * sizeof(double));
+    if (rc) return rc;
+    TaperParams tp{};
+    tp.kind = kind;
+    tp.n = n;
+    tp.M = periodic ? n + 1 : n;
+    tp.p0 = p0;
+    tp.p1 = p1;
+    tp.out = (double *)e->taper_buf.p;
+    ZFB_LAUNCH(taper_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, e->stream, tp);
+    CK(e, cudaGetLastError());
+    e->counters[2] += 1;
+    CK(e, cudaMemcpyAsync(h_out, e->taper_buf.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CK(e, cudaStreamSynchronize(e->stream));
+    e->counters[4] += (size_t)n * sizeof(double);
+    return ZFB_OK;
+}
+
+int zfb_taper_preview(zfb_engine *e, const double *taper, int ntaps, int nfft, float *h_db_out) {
+    if (!e) return ZFB_EINVAL;
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (!taper || !h_db_out || ntaps < 1 || ntaps > 65536 || nfft < ntaps || nfft > (1 << 20))
+        return fail(e, ZFB_EINVAL, "taper preview: bad arguments");
+    CK(e, cudaSetDevice(e->device));
+    const size_t need = (size_t)ntaps * sizeof(double) + (size_t)nfft * sizeof(double) + (size_t)nfft * sizeof(float);
+    int rc = ensure(e, e->taper_buf, need);
+    if (rc) return rc;
+    double *d_taper = (double *)e->taper_buf.p;
+    double *d_mag = d_taper + ntaps;
+    float *d_db = (float *)(d_mag + nfft);
+    CK(e, cudaMemcpyAsync(d_taper, taper, (size_t)ntaps * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    CK(e, cudaStreamSynchronize(e->stream));          // the caller's table may be pageable / short-lived
+    ZFB_LAUNCH(taper_spectrum_kernel, dim3((unsigned)((nfft + 255) / 256)), dim3(256), 0, e->stream,
+               (const double *)d_taper, ntaps, nfft, d_mag);
+    ZFB_LAUNCH(taper_db_kernel, dim3(1), dim3(256), 0, e->stream, (const double *)d_mag, nfft, d_db);
+    CK(e, cudaGetLastError());
+    e->counters[2] += 2;
+    e->counters[3] += (size_t)ntaps * sizeof(double);
+    CK(e, cudaMemcpyAsync(h_db_out, d_db, (size_t)nfft * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    CK(e, cudaStreamSynchronize(e->stream));
+    e->counters[4] += (size_t)nfft * sizeof(float);
     return ZFB_OK;
 }
 

@@ -348,11 +348,11 @@ struct FirRunParams {
 // neighbour exchange of one level: a thread publishes its run (or only the M
 // samples at either end when that is all a neighbour can need) and reads the
 // M samples left / right of its run with compile-time offsets
-template <int RUN, int M>
+template <int RUN, int M, int NT = FIR_NT>
 struct LevelStore {
     static constexpr bool EDGES = (2 * M <= RUN);
     static constexpr int STRIDE = (EDGES ? 2 * M : RUN) | 1;       // odd: conflict-free LDS.64
-    static constexpr int SIZE = FIR_NT * STRIDE;                   // float2 elements
+    static constexpr int SIZE = NT * STRIDE;                   // float2 elements
 
     __device__ static __forceinline__ void publish(float2 *sm, int t, const float2 (&x)[RUN]) {
         float2 *p = sm + t * STRIDE;
@@ -386,10 +386,10 @@ struct LevelStore {
         for (int d = 0; d < M; ++d) {               // position RUN + d
             int idx;
             if (EDGES) {
-                idx = min(t + 1, FIR_NT - 1) * STRIDE + d;
+                idx = min(t + 1, NT - 1) * STRIDE + d;
             } else {
                 const int c = d / RUN;
-                idx = min(t + 1 + c, FIR_NT - 1) * STRIDE + (d - RUN * c);
+                idx = min(t + 1 + c, NT - 1) * STRIDE + (d - RUN * c);
             }
             win[M + RUN + d] = sm[idx];
         }
@@ -436,36 +436,36 @@ __device__ __forceinline__ void mask_level(float2 (&y)[RUN], int pos0, int Llev)
 }
 
 // one stage: publish the input runs, barrier, gather the halos, filter
-template <int RUN, int M>
+template <int RUN, int M, int NT = FIR_NT>
 __device__ __forceinline__ void run_stage(float2 *sm, int t, const float2 (&x)[RUN], const float *hp,
                                           float2 (&y)[RUN / 2], int pos0_out, int L_out) {
-    LevelStore<RUN, M>::publish(sm, t, x);
+    LevelStore<RUN, M, NT>::publish(sm, t, x);
     __syncthreads();
     float2 win[RUN + 2 * M];
 #pragma unroll
     for (int j = 0; j < RUN; ++j) win[M + j] = x[j];
-    LevelStore<RUN, M>::template halo<RUN + 2 * M>(sm, t, win);
+    LevelStore<RUN, M, NT>::template halo<RUN + 2 * M>(sm, t, win);
     fir_decim_regs<RUN, M>(win, hp, y);
     mask_level<RUN / 2>(y, pos0_out, L_out);
 }
 
-template <int NS, int M0, int M1, int M2, int MC>
+template <int NS, int M0, int M1, int M2, int MC, int NT = FIR_NT>
 struct FirRunShape {
     static constexpr int RUN_OUT = RUN0 >> NS;
-    static constexpr int S0 = LevelStore<RUN0, M0>::SIZE;
-    static constexpr int S1 = NS >= 2 ? LevelStore<RUN0 / 2, (M1 > 0 ? M1 : 1)>::SIZE : 0;
-    static constexpr int S2 = NS >= 3 ? LevelStore<RUN0 / 4, (M2 > 0 ? M2 : 1)>::SIZE : 0;
-    static constexpr int SC = MC >= 0 ? LevelStore<RUN_OUT, (MC > 0 ? MC : 1)>::SIZE : 0;   // MC < 0: no compensator
+    static constexpr int S0 = LevelStore<RUN0, M0, NT>::SIZE;
+    static constexpr int S1 = NS >= 2 ? LevelStore<RUN0 / 2, (M1 > 0 ? M1 : 1), NT>::SIZE : 0;
+    static constexpr int S2 = NS >= 3 ? LevelStore<RUN0 / 4, (M2 > 0 ? M2 : 1), NT>::SIZE : 0;
+    static constexpr int SC = MC >= 0 ? LevelStore<RUN_OUT, (MC > 0 ? MC : 1), NT>::SIZE : 0;   // MC < 0: no compensator
     static constexpr size_t SMEM = (size_t)(S0 + S1 + S2 + SC) * sizeof(float2);
     // dependency cone of a final output, in level-0 samples
     static constexpr int CONE = M0 + (NS >= 2 ? 2 * M1 : 0) + (NS >= 3 ? 4 * M2 : 0) + (MC > 0 ? (1 << NS) * MC : 0);
     static constexpr int HT = (CONE + RUN0 - 1) / RUN0;
-    static constexpr int SPAN = (FIR_NT - 2 * HT) * RUN0;          // level-0 samples a tile finishes
+    static constexpr int SPAN = (NT - 2 * HT) * RUN0;          // level-0 samples a tile finishes
 };
 
-template <int KIND, int NS, int M0, int M1, int M2, int MC, bool CH = false>
-__global__ void __launch_bounds__(FIR_NT, ZFB_FIR_MINB) fir_run_kernel(const FirRunParams p) {
-    using SH = FirRunShape<NS, M0, M1, M2, MC>;
+template <int KIND, int NS, int M0, int M1, int M2, int MC, bool CH = false, int NT = FIR_NT>
+__global__ void __launch_bounds__(NT, (ZFB_FIR_MINB * FIR_NT / NT)) fir_run_kernel(const FirRunParams p) {
+    using SH = FirRunShape<NS, M0, M1, M2, MC, NT>;
     constexpr int VEC = (KIND == KIND_U8_RAW) ? 8 : 2;
     ZFB_DYN_SMEM(smem_raw);
     float2 *sm0 = reinterpret_cast<float2 *>(smem_raw);
@@ -543,18 +543,18 @@ __global__ void __launch_bounds__(FIR_NT, ZFB_FIR_MINB) fir_run_kernel(const Fir
     float2 yf[SH::RUN_OUT];                 // level NS run of this thread
     {
         float2 y1[RUN0 / 2];
-        run_stage<RUN0, M0>(sm0, t, x0, p.h0, y1, pos0 >> 1, Llev[1]);
+        run_stage<RUN0, M0, NT>(sm0, t, x0, p.h0, y1, pos0 >> 1, Llev[1]);
         if constexpr (NS == 1) {
 #pragma unroll
             for (int j = 0; j < RUN0 / 2; ++j) yf[j] = y1[j];
         } else {
             float2 y2[RUN0 / 4];
-            run_stage<RUN0 / 2, M1>(sm1, t, y1, p.h1, y2, pos0 >> 2, Llev[2]);
+            run_stage<RUN0 / 2, M1, NT>(sm1, t, y1, p.h1, y2, pos0 >> 2, Llev[2]);
             if constexpr (NS == 2) {
 #pragma unroll
                 for (int j = 0; j < RUN0 / 4; ++j) yf[j] = y2[j];
             } else {
-                run_stage<RUN0 / 4, M2>(sm2, t, y2, p.h2, yf, pos0 >> 3, Llev[3]);
+                run_stage<RUN0 / 4, M2, NT>(sm2, t, y2, p.h2, yf, pos0 >> 3, Llev[3]);
             }
         }
     }
@@ -563,12 +563,12 @@ __global__ void __launch_bounds__(FIR_NT, ZFB_FIR_MINB) fir_run_kernel(const Fir
     constexpr int RO = SH::RUN_OUT;
     float2 out[RO];
     if constexpr (MC > 0) {
-        LevelStore<RO, MC>::publish(smc, t, yf);
+        LevelStore<RO, MC, NT>::publish(smc, t, yf);
         __syncthreads();
         float2 win[RO + 2 * MC];
 #pragma unroll
         for (int j = 0; j < RO; ++j) win[MC + j] = yf[j];
-        LevelStore<RO, MC>::template halo<RO + 2 * MC>(smc, t, win);
+        LevelStore<RO, MC, NT>::template halo<RO + 2 * MC>(smc, t, win);
         fir_same_regs<RO, MC>(win, p.hc, out);
     } else {
         (void)smc;
@@ -584,7 +584,7 @@ __global__ void __launch_bounds__(FIR_NT, ZFB_FIR_MINB) fir_run_kernel(const Fir
         for (int j = 0; j < RO; ++j) out[j] = cmul(out[j], cmul(b0, CH ? cl->out[j] : p.lo_out[j]));
     }
 
-    if (t >= SH::HT && t < FIR_NT - SH::HT) {
+    if (t >= SH::HT && t < NT - SH::HT) {
         const int po = pos0 >> NS;
         float2 *frame_out = p.out + (size_t)frame * (size_t)p.out_stride;
 #pragma unroll

@@ -57,6 +57,12 @@ struct IirStreamParams {
     int Wb;               // warm-up blocks (Wb + 1 <= S16)
     int nspf;             // streams per frame (rows beyond it are out of bounds for the copy engine)
     int groups;           // warps per frame: ceil(nspf / 32)
+    // L2 residency hints (the launch moves more bytes than L2 holds: every input block is read by
+    // both passes, every result tile is written, pulled back and written again).  The backward
+    // pass starts where the forward pass ended, so the LAST blocks of a stream are the first to be
+    // wanted again: blocks >= keep_from are loaded / stored evict_last by the forward pass, the
+    // others and everything the backward pass reads evict_first.  keep_from >= S16: no hints.
+    int keep_from;
 };
 
 template <int NS, int NO>
@@ -182,6 +188,8 @@ __global__ void __launch_bounds__(32) iir_stream_kernel(ZFB_TMAP_PARAM tm_in, ZF
 
     unsigned gx = 0;          // x tiles consumed so far (both directions): slot gx % NS, parity (gx / NS) & 1
     const int npieces = Wb + S16;
+    const bool hints = p.keep_from < S16;
+    const uint64_t pol_keep = l2_policy_evict_last(), pol_drop = l2_policy_evict_first();
 
 #pragma unroll 1
     for (int dir = 0; dir < 2; ++dir) {
@@ -196,7 +204,11 @@ __global__ void __launch_bounds__(32) iir_stream_kernel(ZFB_TMAP_PARAM tm_in, ZF
             else if (jx >= S16) { c1 -= S16; c2 += 1; }
             const unsigned slot = (gx + (unsigned)q) % NS;
             mbar_arrive_expect_tx(xbar + slot, IS_XTILE);
-            tma_load_4d(xbuf + slot * IS_XTILE, &tm_in, 0, c1, c2, frame, xbar + slot);
+            if (hints)
+                tma_load_4d_hint(xbuf + slot * IS_XTILE, &tm_in, 0, c1, c2, frame, xbar + slot,
+                                 (!bwd && jx >= p.keep_from) ? pol_keep : pol_drop);
+            else
+                tma_load_4d(xbuf + slot * IS_XTILE, &tm_in, 0, c1, c2, frame, xbar + slot);
         };
         IirState st;
         iir_zero(st);
@@ -220,7 +232,11 @@ __global__ void __launch_bounds__(32) iir_stream_kernel(ZFB_TMAP_PARAM tm_in, ZF
                         bulk_wait_read<(NO >= 2 ? NO - 2 : 0)>();
                         const unsigned slot = (unsigned)en % NO;
                         mbar_arrive_expect_tx(pbar + slot, IS_OTILE);
-                        tma_load_4d(obuf + slot * IS_OTILE, &tm_out, 0, S16 - 1 - en, s0, frame, pbar + slot);
+                        if (hints)
+                            tma_load_4d_hint(obuf + slot * IS_OTILE, &tm_out, 0, S16 - 1 - en, s0, frame, pbar + slot,
+                                             pol_drop);
+                        else
+                            tma_load_4d(obuf + slot * IS_OTILE, &tm_out, 0, S16 - 1 - en, s0, frame, pbar + slot);
                     }
                 } else if (e >= 0) {
                     bulk_wait_read<NO - 1>();                     // the row tile's previous store has left it
@@ -248,7 +264,11 @@ __global__ void __launch_bounds__(32) iir_stream_kernel(ZFB_TMAP_PARAM tm_in, ZF
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) {
-                    tma_store_4d(&tm_out, 0, jb, s0, frame, obuf + os * IS_OTILE);
+                    if (hints && !bwd)
+                        tma_store_4d_hint(&tm_out, 0, jb, s0, frame, obuf + os * IS_OTILE,
+                                          jb >= p.keep_from ? pol_keep : pol_drop);
+                    else
+                        tma_store_4d(&tm_out, 0, jb, s0, frame, obuf + os * IS_OTILE);
                     bulk_commit();
                 }
             }

@@ -91,6 +91,31 @@ __device__ __forceinline__ void tma_load_4d(void *dst_smem, const TensorMap *map
         "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
         : "memory");
 }
+// the same with an L2 eviction-priority hint (createpolicy): pol != 0
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void tma_load_4d_hint(void *dst_smem, const TensorMap *map, int c0, int c1, int c2,
+                                                 int c3, uint64_t *bar, uint64_t pol) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4, %5}], [%6], %7;" ::
+            "r"(smem_u32(dst_smem)),
+        "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar)), "l"(pol)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_4d_hint(const TensorMap *map, int c0, int c1, int c2, int c3,
+                                                  const void *src_smem, uint64_t pol) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group.L2::cache_hint [%0, {%1, %2, %3, %4}], [%5], %6;" ::"l"(map),
+                 "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(src_smem)), "l"(pol)
+                 : "memory");
+}
 __device__ __forceinline__ void tma_store_4d(const TensorMap *map, int c0, int c1, int c2, int c3,
                                              const void *src_smem) {
     asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3, %4}], [%5];" ::"l"(map),
@@ -158,6 +183,14 @@ inline void tma_load_4d(void *dst, const TensorMap *m, int c0, int c1, int c2, i
 }
 inline void tma_store_4d(const TensorMap *m, int c0, int c1, int c2, int c3, const void *src) {
     tma_emu_4d<true>((unsigned char *)src, m, c0, c1, c2, c3);
+}
+inline uint64_t l2_policy_evict_last() { return 1; }
+inline uint64_t l2_policy_evict_first() { return 2; }
+inline void tma_load_4d_hint(void *dst, const TensorMap *m, int c0, int c1, int c2, int c3, uint64_t *b, uint64_t) {
+    tma_load_4d(dst, m, c0, c1, c2, c3, b);
+}
+inline void tma_store_4d_hint(const TensorMap *m, int c0, int c1, int c2, int c3, const void *src, uint64_t) {
+    tma_store_4d(m, c0, c1, c2, c3, src);
 }
 
 #endif

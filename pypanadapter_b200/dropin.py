@@ -10,6 +10,8 @@ the AppState object stay the reference's own:
 * ``ApplicationDisplay.zoomfft`` / ``.update(chunk)``  (S:2088-2130)
 * ``PSD.update``                                      (T:1513-1549)
 * ``Data``'s storage and ``add`` / ``get_data_*``      (T:1400-1483)
+* ``FFTTaperingControl.ShowCurve``                    (S:1354-1379): taper table
+  and preview spectrum from the device
 * ``Waterfall.init_image`` / ``image_update`` / ``autolevel`` / ``newlevel``
   and ``img_array``                                   (S:1625-1686): rows stay
   in the device ring, ``setImage`` receives 8-bit colour indices
@@ -157,6 +159,30 @@ def _waterfall_methods(module, engine_of):
                 newlevel=newlevel, img_array=img_array)
 
 
+def _taper_show_curve(module, engine_of):
+    """FFTTaperingControl.ShowCurve (S:1354-1379): the dialog's widgets and the
+    AppState hand-over stay as they are; the taper table and its preview
+    spectrum come from the device (pypanadapter_b200.taper)."""
+    from . import taper as _taper
+
+    def ShowCurve(self):
+        shape = type(self).taper_list[self.taper]             # [(label, default), ...]
+        values = [self.P0val.value(), self.P1val.value()][:len(shape)]
+        module.AppState.fft_tapering = (self.taper, *values) if values else self.taper
+        cls = type(self)
+        curve, spectrum = _taper.show_curve(module.AppState.fft_tapering, getattr(cls, "taper_size", 51),
+                                            getattr(cls, "fft_size", 2048), engine=engine_of())
+        pen = module.pg.mkPen(color='k', width=2) if hasattr(module, "pg") else None
+        for attr, plot, data in (("taperplot", self.plot0, curve), ("fftplot", self.plot1, spectrum)):
+            item = getattr(self, attr, None)
+            if item:
+                item.setData(data)
+            else:
+                setattr(self, attr, plot.plot(data, pen=pen))
+
+    return ShowCurve
+
+
 def install(module, *, engine: ZoomPSD | None = None, replace_data: bool = True,
             replace_waterfall: bool = True) -> dict:
     """Patch ``module`` (a loaded pypanadapter_spectrum / pypanadapter_thread)
@@ -198,6 +224,10 @@ def install(module, *, engine: ZoomPSD | None = None, replace_data: bool = True,
             module.Data = Data
     if not saved:
         raise ValueError("module has neither ApplicationDisplay.zoomfft nor PSD: not a pypanadapter module")
+    tap = getattr(module, "FFTTaperingControl", None)
+    if tap is not None and hasattr(tap, "ShowCurve"):
+        saved["FFTTaperingControl.ShowCurve"] = tap.ShowCurve
+        tap.ShowCurve = _taper_show_curve(module, engine_of)
     wfc = getattr(module, "Waterfall", None)
     if replace_waterfall and wfc is not None:
         for name, fn in _waterfall_methods(module, engine_of).items():

@@ -546,6 +546,23 @@ def dropin_on_standin_modules(engine):
             ref_img = zo.waterfall_update(ref_img, row.copy(), 1)
         assert np.array_equal(app.waterfall.img_array, ref_img)
         assert np.array_equal(app.waterfall.shown["img"], zo.waterfall_indices(ref_img, -220, -120).T)
+        # ---- the taper dialog's ShowCurve (S:1354-1379) ----
+        import scipy.signal
+        for tname, p0, p1, spec in (("hamming", 0, 0, "hamming"), ("kaiser", 9.5, 0, ("kaiser", 9.5)),
+                                    ("general gaussian", 1.5, 7.0, ("general gaussian", 1.5, 7.0))):
+            dlg = mod.FFTTaperingControl(tname, p0, p1)
+            dlg.ShowCurve()
+            assert mod.AppState.fft_tapering == spec
+            ref_t = scipy.signal.get_window(spec, 51)
+            assert np.abs(dlg.taperplot.calls["setData"][0][0] - ref_t).max() < 1e-12
+            fft = np.fft.fft(ref_t, 2048) / (len(ref_t) / 2.0)
+            ref_f = 20 * np.log10(np.abs(fft / np.max(np.abs(fft))))
+            shown = dlg.fftplot.calls["setData"][0][0]
+            vis = ref_f > -140.0
+            assert np.abs(shown[vis] - ref_f[vis]).max() < 2e-3
+            dlg.P0val.v = p0 + 1
+            dlg.ShowCurve()                                   # second call: existing curves are updated
+            assert len(dlg.plot0.items) == 1 and len(dlg.plot1.items) == 1
     finally:
         dropin.uninstall(mod, saved)
     # ---- thread variant: Data, PSD.update, and the GUI timer (T:2140-2157) ----
@@ -860,3 +877,48 @@ def replay_source_through_plugin_api(engine):
     import pytest
     with pytest.raises(EOFError):
         ReplayPan(raw[:20], w.fs, loop=False).ReadRaw(25)
+
+
+def taper_design_and_preview(engine):
+    """the taper dialog's two curves (S:1354-1379) from the device, against the
+    scipy / numpy calls the reference makes, for every entry of its taper_list (S:1222-1243)."""
+    import warnings
+    import scipy.signal
+    from pypanadapter_b200 import taper
+    dialog = {                                            # FFTTaperingControl.taper_list with its defaults
+        "barthann": (), "bartlett": (), "blackmanharris": (), "blackman": (), "bohman": (), "boxcar": (),
+        "flattop": (), "hamming": (), "hann": (), "parzen": (), "nuttall": (), "triang": (),
+        "kaiser": (14,), "gaussian": (7,), "general gaussian": (1.5, 7), "dpss": (3,), "chebwin": (100,),
+        "exponential": (3,), "tukey": (.3,),
+    }
+    ndev = 0
+    for name, par in dialog.items():
+        spec = name if not par else (name,) + par
+        for n in (51, 52, 2048, 1):
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                want = scipy.signal.get_window(spec, n)
+            got = taper.get_window(spec, n, engine=engine)
+            assert got.shape == want.shape
+            assert np.abs(got - want).max() <= 1e-12 * max(1.0, np.abs(want).max()), (name, n)
+        ndev += taper.on_device(spec)
+        taperdata, taperfft = taper.show_curve(spec, engine=engine)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            ref_t = scipy.signal.get_window(spec, 51)
+            fft = np.fft.fft(ref_t, 2048) / (len(ref_t) / 2.0)
+            ref_f = 20 * np.log10(np.abs(fft / np.max(np.abs(fft))))
+        assert np.abs(taperdata - ref_t).max() < 1e-12
+        # the dialog's plot spans 0 .. -140 dB (S:1278): compare there, nulls are bottomless
+        vis = ref_f > -140.0
+        assert np.abs(taperfft[vis] - ref_f[vis]).max() < 2e-3, name
+    assert ndev == 17
+    # symmetric designs and other parameters
+    for spec in (("kaiser", 8.6), ("tukey", 0.0), ("tukey", 1.0), ("tukey", 0.5), ("gaussian", 300.0),
+                 ("general gaussian", 0.7, 12.0), "hann", "triang", "parzen", "bohman"):
+        for n in (8, 9, 64):
+            want = scipy.signal.get_window(spec, n, fftbins=False)
+            got = taper.get_window(spec, n, fftbins=False, engine=engine)
+            assert np.abs(got - want).max() <= 1e-12, (spec, n)
+    with pytest.raises(ValueError):
+        taper.get_window("kaiser", 51, engine=engine)

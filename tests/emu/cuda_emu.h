@@ -175,6 +175,13 @@ static inline void sincospif(float x, float *s, float *c) {
     *s = (float)sin(a);
     *c = (float)cos(a);
 }
+static inline double cospi(double x) { return cos(3.14159265358979323846 * x); }
+static inline double sinpi(double x) { return sin(3.14159265358979323846 * x); }
+static inline void sincospi(double x, double *s, double *c) {
+    *s = sin(3.14159265358979323846 * x);
+    *c = cos(3.14159265358979323846 * x);
+}
+static inline double cyl_bessel_i0(double x) { return std::cyl_bessel_i(0.0, x); }
 static inline unsigned int __byte_perm(unsigned int x, unsigned int y, unsigned int sel) {
     const uint64_t src = ((uint64_t)y << 32) | x;
     unsigned int r = 0;

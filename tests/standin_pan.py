@@ -70,6 +70,39 @@ def make(which: str) -> types.ModuleType:
 
     mod.Waterfall = Waterfall
 
+    class _Spin:
+        def __init__(self, v=0.0):
+            self.v = v
+
+        def value(self):
+            return self.v
+
+    class _Plot:
+        def __init__(self):
+            self.items = []
+
+        def plot(self, data, pen=None):
+            item = _Recorder()
+            item.calls["setData"] = ((np.array(data),), {})
+            self.items.append(item)
+            return item
+
+    class FFTTaperingControl:
+        """The taper dialog (S:1220-1379) reduced to what ShowCurve touches."""
+        taper_list = {"hamming": [], "kaiser": [("beta", 14)], "general gaussian": [("power", 1.5), ("stndrd dev", 7)]}
+        taper_size = 51
+        fft_size = 2048
+
+        def __init__(self, taper, p0=0.0, p1=0.0):
+            self.taper = taper
+            self.P0val, self.P1val = _Spin(p0), _Spin(p1)
+            self.plot0, self.plot1 = _Plot(), _Plot()
+            self.taperplot = self.fftplot = None
+
+        ShowCurve = _not_replaced
+
+    mod.FFTTaperingControl = FFTTaperingControl
+
     if which == "spectrum":
         class ApplicationDisplay:
             """S:1687-2139: read() hands a chunk of fft_size*fft_avg samples to update()."""

@@ -172,3 +172,7 @@ def test_fast_state_survives_frame_len(emu_engine):
 
 def test_ring_wrap_within_one_launch(emu_engine):
     bs.ring_wrap_within_one_launch(emu_engine)
+
+
+def test_taper_design_and_preview(emu_engine):
+    bs.taper_design_and_preview(emu_engine)

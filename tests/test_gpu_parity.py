@@ -248,3 +248,7 @@ def test_fast_state_survives_frame_len(gpu_engine):
 
 def test_ring_wrap_within_one_launch(gpu_engine):
     bs.ring_wrap_within_one_launch(gpu_engine)
+
+
+def test_taper_design_and_preview(gpu_engine):
+    bs.taper_design_and_preview(gpu_engine)
