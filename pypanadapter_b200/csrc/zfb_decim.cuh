@@ -287,6 +287,13 @@ __device__ __forceinline__ float2 u8pair_to_iq(unsigned int word, int hi) {
     return __ffma2_rn(f, make_float2(1.0f / 127.5f, 1.0f / 127.5f), make_float2(-1.0f, -1.0f));
 }
 
+// the same bytes as exact integers 0..255 (conversion folded into a later linear stage)
+__device__ __forceinline__ float2 u8pair_to_raw(unsigned int word, int hi) {
+    const unsigned int fi = __byte_perm(word, 0x4B000000u, hi ? 0x7442 : 0x7440);
+    const unsigned int fq = __byte_perm(word, 0x4B000000u, hi ? 0x7443 : 0x7441);
+    return pk_add(make_float2(__uint_as_float(fi), __uint_as_float(fq)), make_float2(-8388608.0f, -8388608.0f));
+}
+
 template <int KIND, int NT, bool CHAN = false, int B = BLK>
 __device__ __forceinline__ void load_region(float2 *buf, const StageParams &p,
                                             const char *frame_in, int rs, int tid, int posoff, int ch = 0) {
@@ -516,10 +523,11 @@ __global__ void __launch_bounds__(NT, (NT == NTHR_BIG ? 1 : 3)) decim2_exact_ker
 // template parameter of the stage body)
 constexpr int STRIP_NT = 128;          // widest region (stage 0 of the fused cascades; LO tables are built for it)
 constexpr int STRIP_BLK = 64;
+constexpr int STRIP_LEAD = 32;         // region position 0 sits this far before the strip (>= PADLEN, even)
 constexpr size_t strip_smem(int nt = STRIP_NT) { return (size_t)(nt * (STRIP_BLK + 1) + NSTATE * nt) * sizeof(float2); }
-// threads a stage of `len` input samples needs: lead-in WARM, the samples, the odd extension
+// threads a stage of `len` input samples needs: lead-in, the samples, the odd extension
 __host__ __device__ constexpr int strip_threads_for(int len) {
-    return (WARM + len + PADLEN + STRIP_BLK) / STRIP_BLK <= 32 ? 32 : ((WARM + len + PADLEN + STRIP_BLK) / STRIP_BLK <= 64 ? 64 : 128);
+    return (STRIP_LEAD + len + PADLEN + STRIP_BLK) / STRIP_BLK <= 32 ? 32 : ((STRIP_LEAD + len + PADLEN + STRIP_BLK) / STRIP_BLK <= 64 ? 64 : 128);
 }
 
 struct StripParams {
@@ -551,7 +559,7 @@ __global__ void __launch_bounds__(NT, (NT == 128 ? 3 : (NT == 64 ? 6 : 12))) str
     const size_t esz = (KIND == KIND_U8_RAW) ? 2 : 8;
     const char *frame_in = (const char *)p.in +
                            ((size_t)in_frame * (size_t)p.in_stride + (size_t)side * (size_t)p.side_in_off) * esz;
-    const int rs = -WARM;
+    const int rs = -STRIP_LEAD;
 
     load_region<KIND, NT, CHAN, B>(buf, p, frame_in, rs, tid, (KIND != KIND_C64_MID && side) ? p.pos_off : 0, ch);
     __syncthreads();
@@ -565,16 +573,16 @@ __global__ void __launch_bounds__(NT, (NT == 128 ? 3 : (NT == 64 ? 6 : 12))) str
                 float2 *out = sp.out + (size_t)frame * (size_t)sp.out_stride;
                 const int m0 = side ? nout - sp.keep : 0;
                 const int d0 = side ? sp.ndec - sp.keep : 0;
-                for (int i = tid; i < sp.keep; i += NT) out[d0 + i] = buf[sidx<B>(WARM + 2 * (m0 + i))];
+                for (int i = tid; i < sp.keep; i += NT) out[d0 + i] = buf[sidx<B>(STRIP_LEAD + 2 * (m0 + i))];
             } else {
                 // hand the next launch its input: the first (side 0) / last (side 1) next_len outputs
                 float2 *out = sp.mid_out + ((size_t)frame * 2 + (size_t)side) * (size_t)sp.mid_cap;
                 const int off = side ? nout - sp.next_len : 0;
-                for (int j = tid; j < sp.next_len; j += NT) out[j] = buf[sidx<B>(WARM + 2 * (off + j))];
+                for (int j = tid; j < sp.next_len; j += NT) out[j] = buf[sidx<B>(STRIP_LEAD + 2 * (off + j))];
             }
         } else {
             // the next stage works on the first (side 0) / last (side 1) len[s+1] outputs:
-            // move them, gain-scaled, to region positions WARM + j.  dst <= src, so
+            // move them, gain-scaled, to region positions STRIP_LEAD + j.  dst <= src, so
             // ascending chunks are safe once a chunk's reads precede its writes.
             const int Ln = sp.len[s + 1];
             const int off = side ? nout - Ln : 0;
@@ -584,13 +592,13 @@ __global__ void __launch_bounds__(NT, (NT == 128 ? 3 : (NT == 64 ? 6 : 12))) str
 #pragma unroll
                 for (int c = 0; c < CH; ++c) {
                     const int j = j0 + c * NT + tid;
-                    v[c] = (j < Ln) ? buf[sidx<B>(WARM + 2 * (off + j))] : make_float2(0.f, 0.f);
+                    v[c] = (j < Ln) ? buf[sidx<B>(STRIP_LEAD + 2 * (off + j))] : make_float2(0.f, 0.f);
                 }
                 __syncthreads();
 #pragma unroll
                 for (int c = 0; c < CH; ++c) {
                     const int j = j0 + c * NT + tid;
-                    if (j < Ln) buf[sidx<B>(WARM + j)] = pk_mul(g, v[c]);
+                    if (j < Ln) buf[sidx<B>(STRIP_LEAD + j)] = pk_mul(g, v[c]);
                 }
                 __syncthreads();
             }

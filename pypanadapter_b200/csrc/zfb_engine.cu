@@ -61,7 +61,8 @@ struct zfb_engine {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int strips_async = 1;                        // zfb_set_option("strips_async")
     int strip_split = 1;                         // zfb_set_option("strip_split"): narrower regions for the late strip stages
-    int strip_decay = 320;                       // zfb_set_option("strip_decay"): samples between a strip's cut and its outputs
+    int strip_decay = 192;                       // zfb_set_option("strip_decay"): samples between the last stage's cut and its outputs
+    int strip_decay_early = 64;                  // zfb_set_option("strip_decay_early"): the same for the stages before it
     int ring_append = 1;                         // zfb_set_option("ring_append"): processed rows enter the ring
     int late_mix = 1;                            // zfb_set_option("late_mix"): FIR chain may mix at its output
     int iir_stream = 1;                          // zfb_set_option("iir_stream"): streaming last stage of mode fast
@@ -89,7 +90,7 @@ struct zfb_engine {
     int decim_threads = 0;             // 0 = automatic per launch
     int welch_splits = 0;              // 0 = automatic
     int fir_generic = 0;               // 1: never use the register-blocked FIR kernel (tests)
-    int fir_threads = FIR_NT;          // zfb_set_option("fir_threads"): 256 or 128 threads per CTA of fir_run_kernel
+    int fir_threads = 128;             // zfb_set_option("fir_threads"): 256 or 128 threads per CTA of fir_run_kernel
     int nperseg = 0, hop = 0, nseg = 0, W = 0, log2N = 0;
     int Wp = 0;                        // width of a pow row: W, or N for one-sided rows
     bool onesided = false;             // ZFB_FLAG_ONESIDED
@@ -626,14 +627,18 @@ bool fast_wanted(const zfb_engine *e, int *strip_len, int *strip_q) {
     const int K = e->fplan.K;
     // decay distance of a strip's artificial inner edge: 0.935^D of that edge's transient is left
     // where the strip's outputs are used (320: 5e-10, 256: 3e-8, 192: 2.5e-6 = 2e-5 dB)
-    const int D = e->strip_decay;
+    // The transient of stage s's cut reaches the K outputs only through the decay zones of ALL the
+    // later stages (it sits at the inner end of stage s+1's strip, D_(s+1) samples from what that
+    // stage must get right, and so on): what counts is the sum of the distances from s on.  The
+    // last stage carries the full distance, the earlier ones a short one.
+    const int D = e->strip_decay, De = e->strip_decay_early < D ? e->strip_decay_early : D;
     int need = 2 * K + D;
     for (int s = k - 1; s >= 0; --s) {
         int i = need;
         if ((e->len[s] - i) & 1) i += 1;
         strip_len[s] = i;
         strip_q[s] = e->len[s] - i;
-        need = 2 * i + D;
+        need = 2 * i + De;
     }
     return e->len[0] >= 4 * strip_len[0] && e->len[k] >= 4 * K;
 }
@@ -1412,6 +1417,14 @@ int plan_fast(zfb_engine *e) {
                 set_late_mix(e, rp, r, amp, ns);
             }
             memcpy(rp.h0, p.h[0], sizeof rp.h0);
+            {   // first stage on raw uint8 values (zfb_firchain.cuh: FirRunParams::h0s)
+                double sum = 0.0;
+                for (int j = 0; j <= FIR_MAX_HALF; ++j) {
+                    rp.h0s[j] = (float)((double)p.h[0][j] / 127.5);
+                    sum += (j == 0 ? 1.0 : 2.0) * (double)rp.h0s[j];
+                }
+                rp.bias0 = (float)(127.5 * sum);
+            }
             memcpy(rp.h1, p.h[1], sizeof rp.h1);
             memcpy(rp.h2, p.h[2], sizeof rp.h2);
             memcpy(rp.hc, p.hc, sizeof rp.hc);
@@ -1913,6 +1926,12 @@ int zfb_set_option(zfb_engine *e, const char *name, long long value) {
     if (strcmp(name, "strip_decay") == 0) {
         if (value < 64 || value > 1024 || (value & 1)) return fail(e, ZFB_EINVAL, "strip_decay must be even and in [64, 1024]");
         e->strip_decay = (int)value;
+        e->configured = false;
+        return ZFB_OK;
+    }
+    if (strcmp(name, "strip_decay_early") == 0) {
+        if (value < 32 || value > 1024 || (value & 1)) return fail(e, ZFB_EINVAL, "strip_decay_early must be even and in [32, 1024]");
+        e->strip_decay_early = (int)value;
         e->configured = false;
         return ZFB_OK;
     }

@@ -331,6 +331,11 @@ struct FirRunParams {
     float2      lo_run[RUN0];      // amp * exp(-2 pi i f/fs j), j = 0..31
     float       h0[FIR_MAX_HALF + 1], h1[FIR_MAX_HALF + 1], h2[FIR_MAX_HALF + 1];
     float       hc[FIR_COMP_MAX_HALF + 1];
+    // uint8 input with the late mix: the first stage works on the RAW byte values u (the
+    // conversion's u/127.5 - 1 is folded into it: taps h0/127.5, and the unit DC gain turns the
+    // -1 into one constant per output, `bias0` = 127.5 * sum(h0s) as the fp32 taps give it)
+    float       h0s[FIR_MAX_HALF + 1];
+    float       bias0;
     float2     *out;
     long long   out_stride;
     int         ht;                // halo threads per side
@@ -399,13 +404,14 @@ struct LevelStore {
 // RUN/2 outputs of a decimate-by-2 symmetric FIR from a window win[-M .. RUN-1+M]
 template <int RUN, int M>
 __device__ __forceinline__ void fir_decim_regs(const float2 (&win)[RUN + 2 * M], const float *hp,
-                                               float2 (&y)[RUN / 2]) {
+                                               float2 (&y)[RUN / 2], float bias = 0.f) {
     float h[M + 1];
 #pragma unroll
     for (int j = 0; j <= M; ++j) h[j] = hp[j];
+    const float2 nb = make_float2(-bias, -bias);
 #pragma unroll
     for (int m = 0; m < RUN / 2; ++m) {
-        float2 acc = pk_mul(h[0], win[M + 2 * m]);
+        float2 acc = pk_fma(h[0], win[M + 2 * m], nb);
 #pragma unroll
         for (int j = 1; j <= M; ++j) acc = pk_fma(h[j], pk_add(win[M + 2 * m - j], win[M + 2 * m + j]), acc);
         y[m] = acc;
@@ -438,14 +444,14 @@ __device__ __forceinline__ void mask_level(float2 (&y)[RUN], int pos0, int Llev)
 // one stage: publish the input runs, barrier, gather the halos, filter
 template <int RUN, int M, int NT = FIR_NT>
 __device__ __forceinline__ void run_stage(float2 *sm, int t, const float2 (&x)[RUN], const float *hp,
-                                          float2 (&y)[RUN / 2], int pos0_out, int L_out) {
+                                          float2 (&y)[RUN / 2], int pos0_out, int L_out, float bias = 0.f) {
     LevelStore<RUN, M, NT>::publish(sm, t, x);
     __syncthreads();
     float2 win[RUN + 2 * M];
 #pragma unroll
     for (int j = 0; j < RUN; ++j) win[M + j] = x[j];
     LevelStore<RUN, M, NT>::template halo<RUN + 2 * M>(sm, t, win);
-    fir_decim_regs<RUN, M>(win, hp, y);
+    fir_decim_regs<RUN, M>(win, hp, y, bias);
     mask_level<RUN / 2>(y, pos0_out, L_out);
 }
 
@@ -482,6 +488,8 @@ __global__ void __launch_bounds__(NT, (ZFB_FIR_MINB * FIR_NT / NT)) fir_run_kern
 
     // ---------------- level 0: this thread's 32 samples ----------------
     float2 x0[RUN0];
+    const bool late_mix = KIND != KIND_C64_MID && (CH ? p.chan[ch].late : p.late);
+    const bool fold = KIND == KIND_U8_RAW && late_mix;       // raw byte values through the first stage
     {
         const size_t esz = (KIND == KIND_U8_RAW) ? 2 : 8;
         const char *frame_in = (const char *)p.in + (size_t)in_frame * (size_t)p.in_stride * esz;
@@ -499,9 +507,18 @@ __global__ void __launch_bounds__(NT, (ZFB_FIR_MINB * FIR_NT / NT)) fir_run_kern
                 if (KIND == KIND_U8_RAW) {
                     const unsigned int wds[4] = {raw[v].x, raw[v].y, raw[v].z, raw[v].w};
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const int idx = v * 8 + e;                 // memory order
-                        x0[fl ? RUN0 - 1 - idx : idx] = u8pair_to_iq(wds[e >> 1], e & 1);
+                    if (fold) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const int idx = v * 8 + e;
+                            x0[fl ? RUN0 - 1 - idx : idx] = u8pair_to_raw(wds[e >> 1], e & 1);
+                        }
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const int idx = v * 8 + e;             // memory order
+                            x0[fl ? RUN0 - 1 - idx : idx] = u8pair_to_iq(wds[e >> 1], e & 1);
+                        }
                     }
                 } else {
                     const int i0 = v * 2, i1 = v * 2 + 1;
@@ -513,19 +530,20 @@ __global__ void __launch_bounds__(NT, (ZFB_FIR_MINB * FIR_NT / NT)) fir_run_kern
 #pragma unroll
             for (int e = 0; e < RUN0; ++e) {
                 const int pe = pos0 + e;
-                x0[e] = make_float2(0.f, 0.f);
+                x0[e] = fold ? make_float2(127.5f, 127.5f) : make_float2(0.f, 0.f);   // zero signal
                 if (pe >= 0 && pe < L) {
                     const long long ie = fl ? (long long)L - 1 - pe : (long long)pe;
                     if (KIND == KIND_U8_RAW) {
                         const unsigned char *src = (const unsigned char *)frame_in;
-                        x0[e] = make_float2(u8_to_f(src[2 * ie]), u8_to_f(src[2 * ie + 1]));
+                        x0[e] = fold ? make_float2((float)src[2 * ie], (float)src[2 * ie + 1])
+                                     : make_float2(u8_to_f(src[2 * ie]), u8_to_f(src[2 * ie + 1]));
                     } else {
                         x0[e] = __ldg((const float2 *)frame_in + ie);
                     }
                 }
             }
         }
-        if (KIND != KIND_C64_MID && !(CH ? p.chan[ch].late : p.late)) {
+        if (KIND != KIND_C64_MID && !late_mix) {
             const ChannelLo *cl = CH ? p.chan + ch : nullptr;
             const float2 b0 = lo_phasor((long long)pos0, CH ? cl->phase_inc : p.phase_inc);
 #pragma unroll
@@ -543,7 +561,7 @@ __global__ void __launch_bounds__(NT, (ZFB_FIR_MINB * FIR_NT / NT)) fir_run_kern
     float2 yf[SH::RUN_OUT];                 // level NS run of this thread
     {
         float2 y1[RUN0 / 2];
-        run_stage<RUN0, M0, NT>(sm0, t, x0, p.h0, y1, pos0 >> 1, Llev[1]);
+        run_stage<RUN0, M0, NT>(sm0, t, x0, fold ? p.h0s : p.h0, y1, pos0 >> 1, Llev[1], fold ? p.bias0 : 0.f);
         if constexpr (NS == 1) {
 #pragma unroll
             for (int j = 0; j < RUN0 / 2; ++j) yf[j] = y1[j];
@@ -576,7 +594,7 @@ __global__ void __launch_bounds__(NT, (ZFB_FIR_MINB * FIR_NT / NT)) fir_run_kern
         for (int j = 0; j < RO; ++j) out[j] = yf[j];
     }
 
-    if (KIND != KIND_C64_MID && (CH ? p.chan[ch].late : p.late)) {
+    if (late_mix) {
         // output j of this thread sits at input position (pos0 >> NS << NS) + (j << NS)
         const ChannelLo *cl = CH ? p.chan + ch : nullptr;
         const float2 b0 = lo_phasor((long long)(pos0 >> NS) << NS, CH ? cl->phase_inc : p.phase_inc);
