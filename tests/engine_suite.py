@@ -203,7 +203,7 @@ def fast_activation(engine):
     assert engine.fast_active
     engine.configure(2.4e6, 2048, 2, 65536, "hamming", mode="fast")        # one stage: nothing to replace
     assert not engine.fast_active
-    engine.configure(2.4e6, 1024, 8, 8192, "hamming", mode="fast")         # strips would cover the chunk
+    engine.configure(2.4e6, 512, 8, 4096, "hamming", mode="fast")          # strips would cover the chunk
     assert not engine.fast_active
     engine.configure(2.4e6, 2048, 8, 239616, "hamming", mode="exact")
     assert not engine.fast_active
