@@ -165,22 +165,12 @@ __device__ __forceinline__ void sweep(float2 *blk, int lo, int hi, Sec4 &s,
     if (lo == 0 && hi == B) {
         sweep_full<BWD, STORE, B>(blk, s, na1, na2);
     } else {
-        // partial run (a chunk edge falls inside it): the same pipeline with run-time bounds --
-        // in step j section k works on sample j - k of the n the run holds.  (The plain loop,
-        // four dependent sections per sample, made the one lane with a partial run the
-        // critical path of its whole CTA: 59 samples = 2100 cycles against 600 for a full run.)
-        // Same operations per sample in the same order as the plain loop: bit-identical.
-        const int n = hi - lo;
-        float2 p0 = make_float2(0.f, 0.f), p1 = p0, p2 = p0;
-#pragma unroll 1
-        for (int j = 0; j < n + 3; ++j) {
-            if (j >= 3) {
-                const float2 y = pole(p2, s.w1[3], s.w2[3], na1[3], na2[3]);
-                if (STORE) blk[BWD ? (hi - 1 - (j - 3)) : (lo + j - 3)] = y;
-            }
-            if (j >= 2 && j - 2 < n) p2 = pole(p1, s.w1[2], s.w2[2], na1[2], na2[2]);
-            if (j >= 1 && j - 1 < n) p1 = pole(p0, s.w1[1], s.w2[1], na1[1], na2[1]);
-            if (j < n) p0 = pole(blk[BWD ? (hi - 1 - j) : (lo + j)], s.w1[0], s.w2[0], na1[0], na2[0]);
+        for (int i = lo; i < hi; ++i) {
+            const int q = BWD ? (hi - 1 - (i - lo)) : i;
+            float2 v = blk[q];
+#pragma unroll
+            for (int k = 0; k < NSEC; ++k) v = pole(v, s.w1[k], s.w2[k], na1[k], na2[k]);
+            if (STORE) blk[q] = v;
         }
     }
 }
@@ -434,17 +424,28 @@ __device__ __forceinline__ void exact_stage_inplace(float2 *buf, float2 *zbuf, i
     }
 
     Sec4 s;
+    // A run that holds a chunk edge is only partly valid.  Its lane would crawl through the
+    // un-pipelined loop (four dependent sections per sample) while the rest of the CTA waits at
+    // the next barrier: the run is made whole instead.  The samples before the first valid one
+    // are set to ITS value -- the start-up state is the steady state for exactly that constant,
+    // so sweeping over them from it changes nothing -- and, before the backward pass, the
+    // samples after the last valid one to the forward output there (sosfiltfilt's constant
+    // future).  Every active lane then runs the full pipelined sweep.
+    if (active && tid == a_f) {
+        const float2 c = blk[lo];
+        for (int i = 0; i < lo; ++i) blk[i] = c;
+    }
     // ---------------- forward ----------------
     if (active) {
-        if (tid == a_f) sec_steady(s, blk[lo]); else sec_zero(s);
-        sweep<false, false, B>(blk, lo, hi, s, na1, na2);
+        if (tid == a_f) sec_steady(s, blk[0]); else sec_zero(s);
+        sweep_full<false, false, B>(blk, s, na1, na2);
         publish<NT>(zbuf, tid, s);
     }
     __syncthreads();
     if (active) {
-        if (tid == a_f) sec_steady(s, blk[lo]);
+        if (tid == a_f) sec_steady(s, blk[0]);
         else handoff<false, NT, B>(zbuf, tid, min(JT, tid - a_f), s);
-        sweep<false, true, B>(blk, lo, hi, s, na1, na2);
+        sweep_full<false, true, B>(blk, s, na1, na2);
     }
     __syncthreads();
     // numerator of the forward pass: (1+z^-1)^8 over the whole region.  The 8
@@ -459,16 +460,20 @@ __device__ __forceinline__ void exact_stage_inplace(float2 *buf, float2 *zbuf, i
     }
     __syncthreads();
     // ---------------- backward ----------------
+    if (active && tid == a_b) {
+        const float2 c = blk[hi - 1];
+        for (int i = hi; i < B; ++i) blk[i] = c;
+    }
     if (active) {
-        if (tid == a_b) sec_steady(s, blk[hi - 1]); else sec_zero(s);
-        sweep<true, false, B>(blk, lo, hi, s, na1, na2);
+        if (tid == a_b) sec_steady(s, blk[B - 1]); else sec_zero(s);
+        sweep_full<true, false, B>(blk, s, na1, na2);
         publish<NT>(zbuf, tid, s);
     }
     __syncthreads();
     if (active) {
-        if (tid == a_b) sec_steady(s, blk[hi - 1]);
+        if (tid == a_b) sec_steady(s, blk[B - 1]);
         else handoff<true, NT, B>(zbuf, tid, min(JT, a_b - tid), s);
-        sweep<true, true, B>(blk, lo, hi, s, na1, na2);
+        sweep_full<true, true, B>(blk, s, na1, na2);
     }
     __syncthreads();
     // numerator of the backward pass, (1+z)^8, only where a sample is kept

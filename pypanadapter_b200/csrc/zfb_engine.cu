@@ -28,6 +28,7 @@
 #include "zfb_iirstream.cuh"
 #include "zfb_image.cuh"
 #include "zfb_taper.cuh"
+#include "zfb_precise.cuh"
 
 using namespace zfb;
 
@@ -76,6 +77,12 @@ struct zfb_engine {
         int tail = 0;                                // samples [L, nspf*S) of every input frame kept at zero
         TensorMap tm_in, tm_out;
     } iis;
+    // fp64 path for rows of few segments (zfb_precise.cuh)
+    int precise = -1;                            // zfb_set_option("precise"): -1 auto, 0 never, 1 always
+    bool precise_active = false;
+    int px_group = 1;
+    long long px_stride = 0;
+    DevBuf px_a, px_b, px_work, px_pow, px_win;
     DevBuf taper_buf;                            // window design / preview scratch (zfb_taper.cuh)
     DevBuf strip_out;                            // [group][2][K] edge samples of the strips, patched in afterwards
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
@@ -565,6 +572,18 @@ int setup_device_once(zfb_engine *e) {
     DecimConst dc;
     build_decim_const(dc);
     CK(e, cudaMemcpyToSymbol(c_dec, &dc, sizeof dc));
+    {   // fp64 path: scipy's sos and sosfilt_zi (steady DF2T state per unit input, cascaded gains)
+        PreciseConst pc;
+        design_cheby1_sos(pc.sos);
+        for (int k = 0; k < NSEC; ++k) {          // per unit input of the section; the kernel cascades the gains
+            const double *b = pc.sos[k], *a = pc.sos[k] + 3;
+            const double G = (b[0] + b[1] + b[2]) / (a[0] + a[1] + a[2]);
+            const double z2 = b[2] - a[2] * G;
+            pc.zi[k][0] = b[1] - a[1] * G + z2;
+            pc.zi[k][1] = z2;
+        }
+        CK(e, cudaMemcpyToSymbol(c_px, &pc, sizeof pc));
+    }
     for (int kind = 0; kind < 3; ++kind)
         for (int nt : {NTHR_BIG, NTHR_SMALL})
             CK(e, cudaFuncSetAttribute(decim_lookup(kind, nt), cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1097,6 +1116,108 @@ cudaError_t run_decimation_fast(zfb_engine *e, const void *d_in, int gf, int *ou
     return cudaSuccess;
 }
 
+// fp64 path (zfb_precise.cuh): rows of few Welch segments, `gf` frames resident on the device
+int run_group_precise(zfb_engine *e, const void *d_in, int gf, float *d_rows) {
+    const zfb_config &c = e->cfg;
+    cudaStream_t st = e->stream;
+    const int k = e->nstages;
+    const int N = 1 << e->log2N;
+    const bool no_lo = (c.flags & ZFB_FLAG_NO_LO) != 0;
+    const int kind = raw_kind(c);
+    const size_t fbytes = (size_t)c.frame_len * (kind == KIND_U8_RAW ? 2 : 8);
+    for (int g0 = 0; g0 < gf; g0 += e->px_group) {
+        const int nf = (gf - g0 < e->px_group) ? gf - g0 : e->px_group;
+        const char *in = (const char *)d_in + (size_t)g0 * fbytes;
+        double2 *A = (double2 *)e->px_a.p, *B = (double2 *)e->px_b.p;
+        if (k > 0) {
+            PxLoadParams lp{};
+            lp.in = in;
+            lp.in_stride = c.frame_len;
+            lp.n = c.frame_len;
+            lp.kind = kind;
+            lp.flip = c.flip;
+            lp.mix = no_lo ? 0 : 1;
+            lp.phase_inc = e->sp0[0].phase_inc;
+            lp.amp = sqrt(2.0);
+            lp.out = A;
+            lp.out_stride = e->px_stride;
+            lp.frames = nf;
+            long long blocks = ((long long)nf * c.frame_len + 255) / 256;
+            if (blocks > (long long)e->sm_count * 32) blocks = (long long)e->sm_count * 32;
+            const int pr = prof_begin(e, 0);
+            ZFB_LAUNCH(px_load_kernel, dim3((unsigned)blocks), dim3(256), 0, st, lp);
+            e->counters[2] += 1;
+            for (int s = 0; s < k; ++s) {
+                PxIirParams ip{};
+                ip.L = e->len[s];
+                ip.nstreams = (ip.L + 2 * PADLEN + PX_STREAM - 1) / PX_STREAM;
+                ip.frames = nf;
+                ip.x_stride = ip.y_stride = e->px_stride;
+                const unsigned blocks_i = (unsigned)((nf * ip.nstreams + 127) / 128);
+                ip.x = A; ip.y = B; ip.backward = 0;
+                ZFB_LAUNCH(px_iir_kernel, dim3(blocks_i), dim3(128), 0, st, ip);
+                ip.x = B; ip.y = A; ip.backward = 1;
+                ZFB_LAUNCH(px_iir_kernel, dim3(blocks_i), dim3(128), 0, st, ip);
+                e->counters[2] += 2;
+            }
+            prof_end(e, pr);
+            if (g0 + nf == gf) {             // zfb_debug_read_decimated: first frame of the last sub-group
+                const int nd = e->len[k];
+                ZFB_LAUNCH(px_to_c64_kernel, dim3((unsigned)((nd + 255) / 256)), dim3(256), 0, st,
+                           (const double2 *)A, (float2 *)e->mid[0].p, nd);
+                e->counters[2] += 1;
+                e->final_buf = 0;
+            }
+        }
+        PxWelchParams wp{};
+        wp.from_wire = (k == 0) ? 1 : 0;
+        wp.x = (k == 0) ? (const void *)in : (const void *)A;
+        wp.x_stride = (k == 0) ? c.frame_len : e->px_stride;
+        wp.kind = kind;
+        wp.flip = (k == 0) ? c.flip : 0;
+        wp.len = e->len[k];
+        wp.nperseg = e->nperseg;
+        wp.hop = e->hop;
+        wp.nseg = e->nseg;
+        wp.log2N = e->log2N;
+        wp.window = (const double *)e->px_win.p;
+        wp.work = (double2 *)e->px_work.p;
+        wp.pow = (double *)e->px_pow.p;
+        const int prw = prof_begin(e, 16);
+        ZFB_LAUNCH(px_welch_kernel, dim3((unsigned)e->nseg, (unsigned)nf), dim3(PX_WELCH_NT), 0, st, wp);
+        prof_end(e, prw);
+        PxRowsParams rp{};
+        rp.pow = (const double *)e->px_pow.p;
+        rp.frames = nf;
+        rp.nseg = e->nseg;
+        rp.log2N = e->log2N;
+        rp.W = e->W;
+        rp.onesided = e->onesided ? 1 : 0;
+        rp.os_lo = N / 2 - c.row_width / 2;
+        rp.scale = 1.0 / (c.fs * e->sum_w2) / (double)e->nseg;
+        rp.alpha = (c.ema_alpha >= 0.0) ? c.ema_alpha : -1.0;
+        rp.linear = (c.flags & ZFB_FLAG_LINEAR) ? 1 : 0;
+        rp.ema_state = (float *)e->ema.p;
+        rp.ema_have = e->ema_have ? 1 : 0;
+        rp.rows = d_rows ? d_rows + (size_t)g0 * e->W : nullptr;
+        const bool to_ring = e->ring_append && e->ring.p && e->ring_W == e->W && e->cur_nch == 0;
+        rp.ring = to_ring ? (float *)e->ring.p : nullptr;
+        rp.ring_pos = (long long)(e->ring_written % e->ring_rows);
+        rp.ring_rows = e->ring_rows;
+        const int prf = prof_begin(e, 18);
+        ZFB_LAUNCH(px_rows_kernel, dim3((unsigned)((e->W + 255) / 256)), dim3(256), 0, st, rp);
+        prof_end(e, prf);
+        e->counters[2] += 2;
+        if (rp.alpha >= 0.0) e->ema_have = true;
+        if (to_ring) e->ring_written += nf;
+    }
+    CK(e, cudaGetLastError());
+    e->last_group_frames = gf;
+    e->counters[0] += (uint64_t)gf;
+    e->counters[1] += (uint64_t)gf * (uint64_t)c.frame_len;
+    return ZFB_OK;
+}
+
 // one group of frames, all resident on the device, through the whole chain
 int run_group(zfb_engine *e, const void *d_in, int gf, float *d_rows) {
     const zfb_config &c = e->cfg;
@@ -1117,6 +1238,7 @@ int run_group(zfb_engine *e, const void *d_in, int gf, float *d_rows) {
         }
         d_in = e->cvt.p;
     }
+    if (e->precise_active) return run_group_precise(e, d_in, gf, d_rows);
     const void *src = d_in;
     long long src_stride = c.frame_len;
     int kind = raw_kind(c);
@@ -1630,6 +1752,7 @@ void zfb_destroy(zfb_engine *e) {
     release(e->cvt);
     release(e->strip_out);
     release(e->taper_buf);
+    for (DevBuf *b : {&e->px_a, &e->px_b, &e->px_work, &e->px_pow, &e->px_win}) release(*b);
     if (e->sr_copied) cudaEventDestroy(e->sr_copied);
     for (int i = 0; i < 2; ++i) if (e->sr_free[i]) cudaEventDestroy(e->sr_free[i]);
     if (e->h_rows) cudaFreeHost(e->h_rows);
@@ -1837,6 +1960,32 @@ int zfb_configure(zfb_engine *e, const zfb_config *cfg) {
         e->ring_W = e->W;
         e->ring_written = 0;
     }
+    // fp64 path for rows of few segments (zfb_precise.cuh): small jobs by construction
+    e->precise_active = e->precise == 1 ||
+                        (e->precise < 0 && g.nseg <= 6 && (long long)g.nseg * N <= (1 << 21) && cfg->frame_len <= (1 << 23));
+    if (e->precise_active) {
+        const size_t stride = (size_t)stride4((long long)cfg->frame_len + 2 * PADLEN + 8);
+        size_t per_frame = 2 * stride * sizeof(double2) + (size_t)g.nseg * (size_t)N * (2 * sizeof(double2) + sizeof(double));
+        long long pg = (long long)((256ull << 20) / per_frame);
+        e->px_group = (int)(pg < 1 ? 1 : (pg > 64 ? 64 : pg));
+        e->px_stride = (long long)stride;
+        if (g.nstages > 0) {
+            rc = ensure(e, e->px_a, (size_t)e->px_group * stride * sizeof(double2));
+            if (rc) return rc;
+            rc = ensure(e, e->px_b, (size_t)e->px_group * stride * sizeof(double2));
+            if (rc) return rc;
+            rc = ensure(e, e->mid[0], (size_t)(g.ndec + 8) * sizeof(float2));
+            if (rc) return rc;
+        }
+        rc = ensure(e, e->px_work, (size_t)e->px_group * g.nseg * 2 * (size_t)N * sizeof(double2));
+        if (rc) return rc;
+        rc = ensure(e, e->px_pow, (size_t)e->px_group * g.nseg * (size_t)N * sizeof(double));
+        if (rc) return rc;
+        rc = ensure(e, e->px_win, (size_t)g.nperseg * sizeof(double));
+        if (rc) return rc;
+        CK(e, cudaMemcpyAsync(e->px_win.p, cfg->window, (size_t)g.nperseg * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+        CK(e, cudaStreamSynchronize(e->stream));       // the caller's window table may go away
+    }
     memcpy(e->geom, geom_now, sizeof geom_now);
     e->geom_valid = true;
     e->configured = true;
@@ -1956,6 +2105,12 @@ int zfb_set_option(zfb_engine *e, const char *name, long long value) {
         e->configured = false;
         return ZFB_OK;
     }
+    if (strcmp(name, "precise") == 0) {
+        if (value < -1 || value > 1) return fail(e, ZFB_EINVAL, "precise must be -1 (auto), 0 or 1");
+        e->precise = (int)value;
+        e->configured = false;
+        return ZFB_OK;
+    }
     if (strcmp(name, "iir_l2_keep") == 0) {
         if (value < 0 || value > 100) return fail(e, ZFB_EINVAL, "iir_l2_keep is a percentage");
         e->iir_l2_keep = (int)value;
@@ -1997,7 +2152,7 @@ int zfb_reset_ema(zfb_engine *e) {
 // chain and fused strips (fft_ratio 4, 8, 16 on raw input); everything else
 // loops over the channels
 static bool channels_batchable(const zfb_engine *e) {
-    return e->fast_active && e->nchains == 1 && e->chain_run[0] != 0 && e->nstages <= 4;
+    return !e->precise_active && e->fast_active && e->nchains == 1 && e->chain_run[0] != 0 && e->nstages <= 4;
 }
 
 static int upload_channels(zfb_engine *e, const double *f_demod, int nch) {

@@ -45,6 +45,8 @@ struct dim3 {
     unsigned int x, y, z;
     dim3(unsigned int a = 1, unsigned int b = 1, unsigned int c = 1) : x(a), y(b), z(c) {}
 };
+struct alignas(16) double2 { double x, y; };
+static inline double2 make_double2(double x, double y) { return double2{x, y}; }
 static inline float2 make_float2(float x, float y) { return float2{x, y}; }
 static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
 static inline uint4 make_uint4(unsigned a, unsigned b, unsigned c, unsigned d) { return uint4{a, b, c, d}; }

@@ -84,9 +84,9 @@ def test_cfg4_channel_full_size(gpu_engine, channel):
 def test_sweep_corner(gpu_engine, N, R):
     """BASELINE configs[4] corners: decim 1..64 x N 1024..262144."""
     fs = 2.4e6
-    # >= 7 segments: a single-segment row cannot hold 0.01 dB20 at bins ~90 dB under a
-    # coherent tone in fp32 (FFT round-off ~ eps * peak lands on few bins; DESIGN.md)
-    avg = max(4 * R, 16)
+    # SURVEY 8d cfg5: avg = max(R, 16) -- down to ONE Welch segment at R = 64 (such rows take the
+    # engine's fp64 path, zfb_precise.cuh; round 1 dodged them with >= 7 segments)
+    avg = max(R, 16)
     n = N * avg
     x = gc.tone_noise(n, fs, [(0.013 * fs / R, 0.4), (-0.02 * fs / R, 0.03)], 2e-3, 900 + N % 97 + R,
                       np.complex64)
