@@ -48,7 +48,8 @@ struct ChannelLo {
     unsigned long long phase_inc;   // frac(f_demod/fs) * 2^64
     float2 run[32];                 // fir_run_kernel: sqrt(2) * exp(-2 pi i f/fs j)
     float2 dec_small[8];            // exact stage 0 / strips: sqrt(2) g^2 exp(-2 pi i f/fs v)
-    float2 dec_big[32];             // exp(-2 pi i f/fs * it*STRIP_NT*VEC)  (strip kernel)
+    float2 dec_big[32];             // exp(-2 pi i f/fs * it*STRIP_NT*VEC)  (strip kernel, 128 threads)
+    float2 dec_big64[32];           // the same for the 64-thread strip regions
     int    late;                    // fir_run_kernel: mix at the chain's output (FirRunParams::late)
     int    pad_;
     float2 out[16];                 // sqrt(2) * exp(-2 pi i f/fs * (j << NS))

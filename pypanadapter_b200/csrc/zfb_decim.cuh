@@ -364,7 +364,7 @@ __device__ __forceinline__ void load_region(float2 *buf, const StageParams &p,
 #pragma unroll
                 for (int e = 0; e < VEC; ++e) v[e] = pk_mul(g, v[e]);
             } else {
-                const float2 bi = cmul(b0, CHAN ? cl->dec_big[it] : p.lo_big[it]);
+                const float2 bi = cmul(b0, CHAN ? (NT == 64 ? cl->dec_big64[it] : cl->dec_big[it]) : p.lo_big[it]);
 #pragma unroll
                 for (int e = 0; e < VEC; ++e)
                     v[e] = cmul(v[e], cmul(bi, CHAN ? cl->dec_small[e] : p.lo_small[e]));

@@ -104,7 +104,7 @@ struct zfb_engine {
     double sum_w2 = 0.0;
     int group = 1, group_user = 0;
     int nsplit_cap = 1;
-    StageParams sp0[2]{};              // LO tables of stage 0 for NT = 256 / 128
+    StageParams sp0[3]{};              // LO tables of stage 0 for NT = 256 / 128 / 64 (strips)
 
     DevBuf cvt;                        // complex64 copy of an int16 IQ launch group (ZFB_DTYPE_CS16)
     DevBuf window, winfft, twiddle, twiddle_sub, pow16, mid[2], pow, rows_tmp, ema, ring, stage_in[2], big, img_out, img_lut, img_thr, sel_hist;
@@ -604,6 +604,14 @@ int setup_device_once(zfb_engine *e) {
                                (int)strip_smem()));
     CK(e, cudaFuncSetAttribute((strip_cascade_kernel<KIND_C64_MID, false, 64>), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)strip_smem(64)));
+    CK(e, cudaFuncSetAttribute((strip_cascade_kernel<KIND_U8_RAW, false, 64>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)strip_smem(64)));
+    CK(e, cudaFuncSetAttribute((strip_cascade_kernel<KIND_C64_RAW, false, 64>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)strip_smem(64)));
+    CK(e, cudaFuncSetAttribute((strip_cascade_kernel<KIND_U8_RAW, true, 64>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)strip_smem(64)));
+    CK(e, cudaFuncSetAttribute((strip_cascade_kernel<KIND_C64_RAW, true, 64>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)strip_smem(64)));
     CK(e, cudaFuncSetAttribute((strip_cascade_kernel<KIND_C64_MID, false, 32>), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)strip_smem(32)));
     CK(e, cudaFuncSetAttribute((strip_cascade_kernel<KIND_U8_RAW, true>), cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -891,11 +899,13 @@ void launch_fused_strips(zfb_engine *e, const void *d_in, int gf, float2 *final_
     // share a launch, a narrower region starts a new one (strip_cascade_kernel)
     bool from_fused = false;            // the input was left by a fused launch (exactly the samples needed)
     for (int a = s0; a < k;) {
-        int nt = (a == 0 || !e->strip_split) ? STRIP_NT : strip_threads_for(e->strip_len[a]);
+        // raw input (stage 0): LO tables exist for 128 and 64 threads; channel-batched launches keep 128
+        int nt = !e->strip_split ? STRIP_NT : strip_threads_for(e->strip_len[a]);
+        if (a == 0 && nt < 64) nt = 64;
         int b = a + 1;
         while (b < k && (!e->strip_split || strip_threads_for(e->strip_len[b]) == nt)) ++b;
         StripParams sp{};
-        sp.st = e->sp0[STRIP_NT == NTHR_BIG ? 0 : 1];   // LO tables for STRIP_NT threads per CTA
+        sp.st = e->sp0[nt == 64 ? 2 : 1];               // LO tables for this many threads per CTA
         sp.st.L = e->strip_len[a];
         sp.st.T = 0;
         sp.st.strips = 1;
@@ -940,14 +950,18 @@ void launch_fused_strips(zfb_engine *e, const void *d_in, int gf, float2 *final_
             sp.st.chan = (const ChannelLo *)e->chan_dev.p;
             sp.st.chan_frames = e->cur_chan_frames;
             if (skind == KIND_U8_RAW) {
-                ZFB_LAUNCH((strip_cascade_kernel<KIND_U8_RAW, true>), grid, dim3(STRIP_NT), strip_smem(), st, sp);
+                if (nt == 64) ZFB_LAUNCH((strip_cascade_kernel<KIND_U8_RAW, true, 64>), grid, dim3(64), strip_smem(64), st, sp);
+                else ZFB_LAUNCH((strip_cascade_kernel<KIND_U8_RAW, true>), grid, dim3(STRIP_NT), strip_smem(), st, sp);
             } else {
-                ZFB_LAUNCH((strip_cascade_kernel<KIND_C64_RAW, true>), grid, dim3(STRIP_NT), strip_smem(), st, sp);
+                if (nt == 64) ZFB_LAUNCH((strip_cascade_kernel<KIND_C64_RAW, true, 64>), grid, dim3(64), strip_smem(64), st, sp);
+                else ZFB_LAUNCH((strip_cascade_kernel<KIND_C64_RAW, true>), grid, dim3(STRIP_NT), strip_smem(), st, sp);
             }
         } else if (skind == KIND_U8_RAW) {
-            ZFB_LAUNCH(strip_cascade_kernel<KIND_U8_RAW>, grid, dim3(STRIP_NT), strip_smem(), st, sp);
+            if (nt == 64) ZFB_LAUNCH((strip_cascade_kernel<KIND_U8_RAW, false, 64>), grid, dim3(64), strip_smem(64), st, sp);
+            else ZFB_LAUNCH(strip_cascade_kernel<KIND_U8_RAW>, grid, dim3(STRIP_NT), strip_smem(), st, sp);
         } else if (skind == KIND_C64_RAW) {
-            ZFB_LAUNCH(strip_cascade_kernel<KIND_C64_RAW>, grid, dim3(STRIP_NT), strip_smem(), st, sp);
+            if (nt == 64) ZFB_LAUNCH((strip_cascade_kernel<KIND_C64_RAW, false, 64>), grid, dim3(64), strip_smem(64), st, sp);
+            else ZFB_LAUNCH(strip_cascade_kernel<KIND_C64_RAW>, grid, dim3(STRIP_NT), strip_smem(), st, sp);
         } else if (nt == 32) {
             launch_strip_mid<32>(sp, grid, st);
         } else if (nt == 64) {
@@ -1630,8 +1644,8 @@ void apply_lo(zfb_engine *e, double f_demod) {
     DecimConst dc;
     build_decim_const(dc);
     const double amp0 = no_lo ? 1.0 : sqrt(2.0);
-    for (int v = 0; v < 2; ++v) {
-        const int nt = v == 0 ? NTHR_BIG : NTHR_SMALL;
+    for (int v = 0; v < 3; ++v) {
+        const int nt = v == 0 ? NTHR_BIG : (v == 1 ? NTHR_SMALL : 64);
         StageParams &p = e->sp0[v];
         p.phase_inc = inc;
         for (int i = 0; i < 8; ++i) lo_entry(r, i, amp0 * (double)dc.g, p.lo_small[i]);
@@ -1885,8 +1899,8 @@ int zfb_configure(zfb_engine *e, const zfb_config *cfg) {
     e->log2N = l2;
     e->sum_w2 = s2;
     // stage-0 LO tables (one per tile geometry)
-    for (int v = 0; v < 2; ++v) {
-        const int nt = v == 0 ? NTHR_BIG : NTHR_SMALL;
+    for (int v = 0; v < 3; ++v) {
+        const int nt = v == 0 ? NTHR_BIG : (v == 1 ? NTHR_SMALL : 64);
         StageParams &p = e->sp0[v];
         memset(&p, 0, sizeof p);
         const bool no_lo = (cfg->flags & ZFB_FLAG_NO_LO) != 0;
@@ -2173,6 +2187,7 @@ static int upload_channels(zfb_engine *e, const double *f_demod, int nch) {
         for (int i = 0; i < 32; ++i) lo_entry(r, i, amp0, t.run[i]);
         for (int i = 0; i < 8; ++i) lo_entry(r, i, amp0 * (double)dc.g, t.dec_small[i]);
         for (int it = 0; it < 32; ++it) lo_entry(r, (long long)it * STRIP_NT * vec, 1.0, t.dec_big[it]);
+        for (int it = 0; it < 32; ++it) lo_entry(r, (long long)it * 64 * vec, 1.0, t.dec_big64[it]);
         // same late-mix decision and table as a single-channel configuration at this f_demod
         // (batched == per-channel, bit for bit)
         t.late = 0;

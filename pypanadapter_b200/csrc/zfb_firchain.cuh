@@ -506,7 +506,6 @@ __global__ void __launch_bounds__(NT, (ZFB_FIR_MINB * FIR_NT / NT)) fir_run_kern
             for (int v = 0; v < NV; ++v) {
                 if (KIND == KIND_U8_RAW) {
                     const unsigned int wds[4] = {raw[v].x, raw[v].y, raw[v].z, raw[v].w};
-#pragma unroll
                     if (fold) {
 #pragma unroll
                         for (int e = 0; e < 8; ++e) {

@@ -311,6 +311,52 @@ welch_kernel(const WelchParams p) {
     const int s_end = min(p.nseg, s_begin + p.seg_per_split);
     float2 raw[PPT];
 
+    if (p.reuse && !p.prepared) {
+        // 50 % overlap: the second half of a segment is the first half of the next, in the same
+        // thread's registers.  The halves live in two register arrays that swap roles from
+        // segment to segment; the half that has just been windowed into v[] is dead, so the NEXT
+        // segment's new half is fetched into it before this segment's FFT starts -- the global
+        // latency (ncu: long scoreboard 0.85 per issue) hides behind the butterflies without one
+        // extra register.
+        float2 ha[H], hb[H];
+#pragma unroll
+        for (int m = 0; m < H; ++m) {
+            const int idx = tid + m * NT;
+            ha[m] = active ? welch_fetch<KIND>(frame_in, s_begin * p.hop + idx, p.len, p.flip) : make_float2(0.f, 0.f);
+            hb[m] = active ? welch_fetch<KIND>(frame_in, s_begin * p.hop + idx + H * NT, p.len, p.flip)
+                           : make_float2(0.f, 0.f);
+        }
+        auto segment = [&](float2 (&first)[H], float2 (&second)[H], int s) {
+            float2 sum = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int m = 0; m < H; ++m) sum = cadd(sum, cadd(first[m], second[m]));
+            sum = block_sum<S::NTHREADS>(sum, tid, red);
+            const float2 mean = make_float2(sum.x * inv_n, sum.y * inv_n);
+            float2 v[PPT];
+#pragma unroll
+            for (int m = 0; m < PPT; ++m) {
+                const int idx = tid + m * NT;
+                const float w = active ? __ldg(p.window + idx) : 0.f;
+                const float2 x = m < H ? first[m] : second[m - H];
+                v[m].x = (x.x - mean.x) * w;
+                v[m].y = (x.y - mean.y) * w;
+            }
+            if (s + 1 < s_end) {          // `first` is dead: it takes the next segment's second half
+                const int base = (s + 1) * p.hop + H * NT;
+#pragma unroll
+                for (int m = 0; m < H; ++m)
+                    first[m] = active ? welch_fetch<KIND>(frame_in, base + tid + m * NT, p.len, p.flip)
+                                      : make_float2(0.f, 0.f);
+            }
+            fft_block<LOG2N, PPT>(v, tid, p.twiddle, sm);
+#pragma unroll
+            for (int m = 0; m < PPT; ++m) acc[m] = fmaf(v[m].x, v[m].x, fmaf(v[m].y, v[m].y, acc[m]));
+        };
+        for (int s = s_begin; s < s_end; s += 2) {
+            segment(ha, hb, s);
+            if (s + 1 < s_end) segment(hb, ha, s + 1);
+        }
+    } else
     for (int s = s_begin; s < s_end; ++s) {
         const int base = s * p.hop;
         const bool carry = p.reuse && (s > s_begin);
@@ -432,7 +478,7 @@ __global__ void reduce_rows_kernel(const FinalizeParams p) {
 // tile (nothing but LDS + 2 dependent ops per frame), all warps turn the
 // averaged power into rows.  Same operations in the same order per (frame,
 // column) as a serial walk: a row does not depend on the batch it is in.
-constexpr int EMA_COLS = 8;
+constexpr int EMA_COLS = 4;          // (8 -> 4: twice the CTAs and one 512-frame tile; the kernel is latency-, not traffic-bound)
 constexpr int EMA_NT = 512;
 constexpr int EMA_CH = 4;
 constexpr int EMA_FPP = EMA_NT / EMA_COLS;          // frames per pass of the CTA
