@@ -96,6 +96,7 @@ struct zfb_engine {
     int tiles[kMaxStages][2] = {{0}}, T[kMaxStages][2] = {{0}};   // [stage][0: NT=256, 1: NT=128]
     int decim_threads = 0;             // 0 = automatic per launch
     int welch_splits = 0;              // 0 = automatic
+    int welch_stage = 0;               // 1: cp.async staging of the next segment's new half (N >= 2048, complex64)
     int fir_generic = 0;               // 1: never use the register-blocked FIR kernel (tests)
     int fir_threads = 128;             // zfb_set_option("fir_threads"): 256 or 128 threads per CTA of fir_run_kernel
     int nperseg = 0, hop = 0, nseg = 0, W = 0, log2N = 0;
@@ -507,37 +508,40 @@ typedef void (*WelchFn)(const WelchParams);
 struct WelchEntry { WelchFn fn; int threads; size_t smem; };
 
 template <int LOG2N, int KIND>
-WelchEntry welch_entry() {
+WelchEntry welch_entry(bool stage) {
 #ifndef ZFB_WELCH_PPT16_FROM
 #define ZFB_WELCH_PPT16_FROM 11
 #endif
     // 16 points per thread from N = 2048 up: half the threads per barrier, twice the ILP
     constexpr int PPT = (LOG2N >= ZFB_WELCH_PPT16_FROM) ? 16 : 8;
     using S = WelchShape<LOG2N, PPT>;
+    if constexpr (PPT == 16 && KIND != KIND_U8_RAW) {
+        if (stage) return WelchEntry{welch_kernel<LOG2N, PPT, KIND, true>, S::NTHREADS, S::SMEM_STAGE};
+    }
     return WelchEntry{welch_kernel<LOG2N, PPT, KIND>, S::NTHREADS, S::SMEM};
 }
 
 template <int KIND>
-WelchEntry welch_lookup_kind(int log2n) {
+WelchEntry welch_lookup_kind(int log2n, bool stage) {
     switch (log2n) {
-        case 5: return welch_entry<5, KIND>();
-        case 6: return welch_entry<6, KIND>();
-        case 7: return welch_entry<7, KIND>();
-        case 8: return welch_entry<8, KIND>();
-        case 9: return welch_entry<9, KIND>();
-        case 10: return welch_entry<10, KIND>();
-        case 11: return welch_entry<11, KIND>();
-        case 12: return welch_entry<12, KIND>();
-        case 13: return welch_entry<13, KIND>();
+        case 5: return welch_entry<5, KIND>(stage);
+        case 6: return welch_entry<6, KIND>(stage);
+        case 7: return welch_entry<7, KIND>(stage);
+        case 8: return welch_entry<8, KIND>(stage);
+        case 9: return welch_entry<9, KIND>(stage);
+        case 10: return welch_entry<10, KIND>(stage);
+        case 11: return welch_entry<11, KIND>(stage);
+        case 12: return welch_entry<12, KIND>(stage);
+        case 13: return welch_entry<13, KIND>(stage);
         default: return WelchEntry{nullptr, 0, 0};
     }
 }
 
-WelchEntry welch_lookup(int log2n, int kind) {
+WelchEntry welch_lookup(int log2n, int kind, bool stage = false) {
     switch (kind) {
-        case KIND_C64_RAW: return welch_lookup_kind<KIND_C64_RAW>(log2n);
-        case KIND_U8_RAW: return welch_lookup_kind<KIND_U8_RAW>(log2n);
-        default: return welch_lookup_kind<KIND_C64_MID>(log2n);
+        case KIND_C64_RAW: return welch_lookup_kind<KIND_C64_RAW>(log2n, stage);
+        case KIND_U8_RAW: return welch_lookup_kind<KIND_U8_RAW>(log2n, stage);
+        default: return welch_lookup_kind<KIND_C64_MID>(log2n, stage);
     }
 }
 
@@ -590,11 +594,13 @@ int setup_device_once(zfb_engine *e) {
                                        (int)decim_smem(nt)));
     for (int kind = 0; kind < 3; ++kind)
         for (int l = kMinLog2N; l <= kMaxLog2Small; ++l) {
-            WelchEntry w = welch_lookup(l, kind);
-            if (w.smem > 48 * 1024)
-                CK(e, cudaFuncSetAttribute(w.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.smem));
-            if (l >= 11)   // N >= 2048: room for several CTAs' exchange buffers; small N keeps its L1
-                CK(e, cudaFuncSetAttribute(w.fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            for (int stage = 0; stage < 2; ++stage) {
+                WelchEntry w = welch_lookup(l, kind, stage != 0);
+                if (w.smem > 48 * 1024)
+                    CK(e, cudaFuncSetAttribute(w.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.smem));
+                if (l >= 11)   // N >= 2048: room for several CTAs' exchange buffers; small N keeps its L1
+                    CK(e, cudaFuncSetAttribute(w.fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            }
         }
     CK(e, cudaFuncSetAttribute(strip_cascade_kernel<KIND_U8_RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)strip_smem()));
@@ -1323,7 +1329,7 @@ int run_group(zfb_engine *e, const void *d_in, int gf, float *d_rows) {
         w.twiddle = (const float2 *)e->twiddle.p;
         w.W = e->Wp;
         w.pow_out = (float *)e->pow.p;
-        WelchEntry we = welch_lookup(e->log2N, kind);
+        WelchEntry we = welch_lookup(e->log2N, kind, e->welch_stage != 0);
         const int pr = prof_begin(e, 16);
         ZFB_LAUNCH(we.fn, dim3((unsigned)nsplit, (unsigned)gf), dim3((unsigned)we.threads), we.smem, st, w);
         prof_end(e, pr);
@@ -2080,6 +2086,10 @@ int zfb_set_option(zfb_engine *e, const char *name, long long value) {
     if (strcmp(name, "welch_splits") == 0) {
         if (value < 0 || value > 16) return fail(e, ZFB_EINVAL, "welch_splits must be in [0, 16]");
         e->welch_splits = (int)value;
+        return ZFB_OK;
+    }
+    if (strcmp(name, "welch_stage") == 0) {
+        e->welch_stage = value ? 1 : 0;
         return ZFB_OK;
     }
     if (strcmp(name, "strips_async") == 0) {

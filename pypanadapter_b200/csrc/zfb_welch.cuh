@@ -42,6 +42,20 @@ struct WelchParams {
 
 __device__ __forceinline__ int fpad(int a) { return a + (a >> 4); }
 
+// 8-byte asynchronous copy global -> shared (LDGSTS), tracked per thread
+#ifndef ZFB_EMULATE
+__device__ __forceinline__ void cp_async8(void *dst_smem, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+#else
+inline void cp_async8(void *dst, const void *src) { memcpy(dst, src, 8); }
+inline void cp_async_commit() {}
+inline void cp_async_wait_all() {}
+#endif
+
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
 // multiply by -i (forward FFT quarter turn)
@@ -282,9 +296,11 @@ struct WelchShape {
     static constexpr int NTHREADS = NT < 32 ? 32 : NT;       // launched threads
     static constexpr int MINB = NTHREADS <= 256 ? 2 : 1;     // >= 2 CTAs/SM: the passes are barrier-bound
     static constexpr size_t SMEM = (size_t)(N + (N >> 4) + 1) * sizeof(float2);
+    // staged variant: + the staging area of the next segment's new half (PPT/2 * NT = N/2 complex)
+    static constexpr size_t SMEM_STAGE = (size_t)(N + (N >> 4) + 2 + N / 2) * sizeof(float2);
 };
 
-template <int LOG2N, int PPT, int KIND>
+template <int LOG2N, int PPT, int KIND, bool STAGE = false>
 __global__ void __launch_bounds__((WelchShape<LOG2N, PPT>::NTHREADS), (WelchShape<LOG2N, PPT>::MINB))
 welch_kernel(const WelchParams p) {
     using S = WelchShape<LOG2N, PPT>;
@@ -311,52 +327,15 @@ welch_kernel(const WelchParams p) {
     const int s_end = min(p.nseg, s_begin + p.seg_per_split);
     float2 raw[PPT];
 
-    if (p.reuse && !p.prepared) {
-        // 50 % overlap: the second half of a segment is the first half of the next, in the same
-        // thread's registers.  The halves live in two register arrays that swap roles from
-        // segment to segment; the half that has just been windowed into v[] is dead, so the NEXT
-        // segment's new half is fetched into it before this segment's FFT starts -- the global
-        // latency (ncu: long scoreboard 0.85 per issue) hides behind the butterflies without one
-        // extra register.
-        float2 ha[H], hb[H];
-#pragma unroll
-        for (int m = 0; m < H; ++m) {
-            const int idx = tid + m * NT;
-            ha[m] = active ? welch_fetch<KIND>(frame_in, s_begin * p.hop + idx, p.len, p.flip) : make_float2(0.f, 0.f);
-            hb[m] = active ? welch_fetch<KIND>(frame_in, s_begin * p.hop + idx + H * NT, p.len, p.flip)
-                           : make_float2(0.f, 0.f);
-        }
-        auto segment = [&](float2 (&first)[H], float2 (&second)[H], int s) {
-            float2 sum = make_float2(0.f, 0.f);
-#pragma unroll
-            for (int m = 0; m < H; ++m) sum = cadd(sum, cadd(first[m], second[m]));
-            sum = block_sum<S::NTHREADS>(sum, tid, red);
-            const float2 mean = make_float2(sum.x * inv_n, sum.y * inv_n);
-            float2 v[PPT];
-#pragma unroll
-            for (int m = 0; m < PPT; ++m) {
-                const int idx = tid + m * NT;
-                const float w = active ? __ldg(p.window + idx) : 0.f;
-                const float2 x = m < H ? first[m] : second[m - H];
-                v[m].x = (x.x - mean.x) * w;
-                v[m].y = (x.y - mean.y) * w;
-            }
-            if (s + 1 < s_end) {          // `first` is dead: it takes the next segment's second half
-                const int base = (s + 1) * p.hop + H * NT;
-#pragma unroll
-                for (int m = 0; m < H; ++m)
-                    first[m] = active ? welch_fetch<KIND>(frame_in, base + tid + m * NT, p.len, p.flip)
-                                      : make_float2(0.f, 0.f);
-            }
-            fft_block<LOG2N, PPT>(v, tid, p.twiddle, sm);
-#pragma unroll
-            for (int m = 0; m < PPT; ++m) acc[m] = fmaf(v[m].x, v[m].x, fmaf(v[m].y, v[m].y, acc[m]));
-        };
-        for (int s = s_begin; s < s_end; s += 2) {
-            segment(ha, hb, s);
-            if (s + 1 < s_end) segment(hb, ha, s + 1);
-        }
-    } else
+    // STAGE (option welch_stage): 50 % overlap, complex64 samples: the NEXT segment's new half is
+    // copied global -> shared (cp.async, 8 bytes per element, every thread its own H slots) while
+    // this segment's FFT runs, and picked up from there afterwards, so that the global latency
+    // (ncu: long scoreboard 0.85 per issue) hides behind the butterflies without a register.
+    // (Prefetching into a second register half instead was measured: 77.8 -> 97.8 us for the cfg2
+    // launch, gpurun r02k -- the kernel sits at 127 of the 128 registers it may use at 2 CTAs/SM.)
+    constexpr bool STAGED = STAGE && (KIND != KIND_U8_RAW);
+    float2 *stage = sm + fpad(N) + 1;                     // H * NT complex behind the exchange buffer
+    const bool staged = STAGED && p.reuse && !p.prepared;
     for (int s = s_begin; s < s_end; ++s) {
         const int base = s * p.hop;
         const bool carry = p.reuse && (s > s_begin);
@@ -365,11 +344,23 @@ welch_kernel(const WelchParams p) {
             const int idx = tid + m * NT;
             if (m < H && carry) {
                 raw[m] = raw[m + H];
+            } else if (carry && staged) {
+                raw[m] = active ? stage[(m - H) * NT + tid] : make_float2(0.f, 0.f);   // own copy: no barrier
             } else {
                 raw[m] = (active && idx < p.nperseg)
                              ? welch_fetch<KIND>(frame_in, base + idx, p.len, p.flip)
                              : make_float2(0.f, 0.f);
             }
+        }
+        if (staged && s + 1 < s_end && active) {
+            const int nb = (s + 1) * p.hop + H * NT + tid;
+#pragma unroll
+            for (int m = 0; m < H; ++m) {
+                const int idx = nb + m * NT;
+                const int i = (KIND == KIND_C64_RAW && p.flip) ? (p.len - 1 - idx) : idx;
+                cp_async8(stage + m * NT + tid, (const float2 *)frame_in + i);
+            }
+            cp_async_commit();
         }
         float2 v[PPT];
         if (p.prepared) {
@@ -393,6 +384,7 @@ welch_kernel(const WelchParams p) {
         fft_block<LOG2N, PPT>(v, tid, p.twiddle, sm);
 #pragma unroll
         for (int m = 0; m < PPT; ++m) acc[m] = fmaf(v[m].x, v[m].x, fmaf(v[m].y, v[m].y, acc[m]));
+        if (staged) cp_async_wait_all();
     }
 
     // fftshift + centre crop: natural bin k sits at column (k + N/2) mod N

@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--ratios", default="1,2,4,8,16,32,64")
     ap.add_argument("--sizes", default="1024,4096,16384,65536,262144")
     ap.add_argument("--mode", default="fast")
+    ap.add_argument("--set", action="append", dest="sets", metavar="OPTION=VALUE", help="zfb_set_option before the sweep")
     args = ap.parse_args()
 
     import torch
@@ -41,6 +42,9 @@ def main():
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     eng.set_stream(stream.cuda_stream)
+    for it in args.sets or []:
+        name, _, val = it.partition("=")
+        eng.set_option(name, int(val))
     results = []
     for R in [int(v) for v in args.ratios.split(",")]:
         for N in [int(v) for v in args.sizes.split(",")]:
