@@ -96,7 +96,7 @@ struct zfb_engine {
     int tiles[kMaxStages][2] = {{0}}, T[kMaxStages][2] = {{0}};   // [stage][0: NT=256, 1: NT=128]
     int decim_threads = 0;             // 0 = automatic per launch
     int welch_splits = 0;              // 0 = automatic
-    int welch_stage = 0;               // 1: cp.async staging of the next segment's new half (N >= 2048, complex64)
+    int welch_prune = 2;               // 0: all bins accumulated; 1: only keepable ones; 2: + 3 CTAs/SM where it fits
     int fir_generic = 0;               // 1: never use the register-blocked FIR kernel (tests)
     int fir_threads = 128;             // zfb_set_option("fir_threads"): 256 or 128 threads per CTA of fir_run_kernel
     int nperseg = 0, hop = 0, nseg = 0, W = 0, log2N = 0;
@@ -507,42 +507,62 @@ void lo_entry(double r, long long m, double amp, float2 &out) {
 typedef void (*WelchFn)(const WelchParams);
 struct WelchEntry { WelchFn fn; int threads; size_t smem; };
 
+// prune: 0 = every bin accumulated; 1 = only the bins of the thread that can fall inside the kept
+// W columns (KEEP per spectrum end, welch_kernel); 2 = the same at 3 CTAs/SM where that fits
 template <int LOG2N, int KIND>
-WelchEntry welch_entry(bool stage) {
+WelchEntry welch_entry(int keep, int prune) {
 #ifndef ZFB_WELCH_PPT16_FROM
 #define ZFB_WELCH_PPT16_FROM 11
 #endif
     // 16 points per thread from N = 2048 up: half the threads per barrier, twice the ILP
     constexpr int PPT = (LOG2N >= ZFB_WELCH_PPT16_FROM) ? 16 : 8;
     using S = WelchShape<LOG2N, PPT>;
-    if constexpr (PPT == 16 && KIND != KIND_U8_RAW) {
-        if (stage) return WelchEntry{welch_kernel<LOG2N, PPT, KIND, true>, S::NTHREADS, S::SMEM_STAGE};
+    if constexpr (PPT == 16 && KIND == KIND_C64_MID) {
+        if (prune >= 1) {
+            if constexpr (S::NTHREADS <= 256) {
+                if (prune >= 2 && keep <= 1) return WelchEntry{welch_kernel<LOG2N, PPT, KIND, 1, true>, S::NTHREADS, S::SMEM};
+                if (prune >= 2 && keep <= 2) return WelchEntry{welch_kernel<LOG2N, PPT, KIND, 2, true>, S::NTHREADS, S::SMEM};
+            }
+            if (keep <= 1) return WelchEntry{welch_kernel<LOG2N, PPT, KIND, 1>, S::NTHREADS, S::SMEM};
+            if (keep <= 2) return WelchEntry{welch_kernel<LOG2N, PPT, KIND, 2>, S::NTHREADS, S::SMEM};
+            if (keep <= 4) return WelchEntry{welch_kernel<LOG2N, PPT, KIND, 4>, S::NTHREADS, S::SMEM};
+        }
     }
     return WelchEntry{welch_kernel<LOG2N, PPT, KIND>, S::NTHREADS, S::SMEM};
 }
 
 template <int KIND>
-WelchEntry welch_lookup_kind(int log2n, bool stage) {
+WelchEntry welch_lookup_kind(int log2n, int keep, int prune) {
     switch (log2n) {
-        case 5: return welch_entry<5, KIND>(stage);
-        case 6: return welch_entry<6, KIND>(stage);
-        case 7: return welch_entry<7, KIND>(stage);
-        case 8: return welch_entry<8, KIND>(stage);
-        case 9: return welch_entry<9, KIND>(stage);
-        case 10: return welch_entry<10, KIND>(stage);
-        case 11: return welch_entry<11, KIND>(stage);
-        case 12: return welch_entry<12, KIND>(stage);
-        case 13: return welch_entry<13, KIND>(stage);
+        case 5: return welch_entry<5, KIND>(keep, prune);
+        case 6: return welch_entry<6, KIND>(keep, prune);
+        case 7: return welch_entry<7, KIND>(keep, prune);
+        case 8: return welch_entry<8, KIND>(keep, prune);
+        case 9: return welch_entry<9, KIND>(keep, prune);
+        case 10: return welch_entry<10, KIND>(keep, prune);
+        case 11: return welch_entry<11, KIND>(keep, prune);
+        case 12: return welch_entry<12, KIND>(keep, prune);
+        case 13: return welch_entry<13, KIND>(keep, prune);
         default: return WelchEntry{nullptr, 0, 0};
     }
 }
 
-WelchEntry welch_lookup(int log2n, int kind, bool stage = false) {
+// keep: bins per spectrum end and thread that can be kept (16 = all); see welch_keep()
+WelchEntry welch_lookup(int log2n, int kind, int keep = 16, int prune = 0) {
     switch (kind) {
-        case KIND_C64_RAW: return welch_lookup_kind<KIND_C64_RAW>(log2n, stage);
-        case KIND_U8_RAW: return welch_lookup_kind<KIND_U8_RAW>(log2n, stage);
-        default: return welch_lookup_kind<KIND_C64_MID>(log2n, stage);
+        case KIND_C64_RAW: return welch_lookup_kind<KIND_C64_RAW>(log2n, keep, prune);
+        case KIND_U8_RAW: return welch_lookup_kind<KIND_U8_RAW>(log2n, keep, prune);
+        default: return welch_lookup_kind<KIND_C64_MID>(log2n, keep, prune);
     }
+}
+
+// bins k = tid + m*NT of a thread that can fall inside the kept columns [0, W/2) u [N - W/2, N):
+// m < keep or m >= PPT - keep
+int welch_keep(int log2n, int W) {
+    const int ppt = (log2n >= ZFB_WELCH_PPT16_FROM) ? 16 : 8;
+    const int nt = (1 << log2n) / ppt;
+    const int k = ((W + 1) / 2 + nt - 1) / nt;
+    return k < 1 ? 1 : k;
 }
 
 typedef void (*DecimFn)(const StageParams);
@@ -594,8 +614,8 @@ int setup_device_once(zfb_engine *e) {
                                        (int)decim_smem(nt)));
     for (int kind = 0; kind < 3; ++kind)
         for (int l = kMinLog2N; l <= kMaxLog2Small; ++l) {
-            for (int stage = 0; stage < 2; ++stage) {
-                WelchEntry w = welch_lookup(l, kind, stage != 0);
+            for (int variant = 0; variant < 12; ++variant) {      // every (keep, prune) the lookup can return
+                WelchEntry w = welch_lookup(l, kind, 1 << (variant & 3), variant >> 2);
                 if (w.smem > 48 * 1024)
                     CK(e, cudaFuncSetAttribute(w.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.smem));
                 if (l >= 11)   // N >= 2048: room for several CTAs' exchange buffers; small N keeps its L1
@@ -1329,7 +1349,7 @@ int run_group(zfb_engine *e, const void *d_in, int gf, float *d_rows) {
         w.twiddle = (const float2 *)e->twiddle.p;
         w.W = e->Wp;
         w.pow_out = (float *)e->pow.p;
-        WelchEntry we = welch_lookup(e->log2N, kind, e->welch_stage != 0);
+        WelchEntry we = welch_lookup(e->log2N, kind, welch_keep(e->log2N, e->Wp), e->welch_prune);
         const int pr = prof_begin(e, 16);
         ZFB_LAUNCH(we.fn, dim3((unsigned)nsplit, (unsigned)gf), dim3((unsigned)we.threads), we.smem, st, w);
         prof_end(e, pr);
@@ -2088,8 +2108,9 @@ int zfb_set_option(zfb_engine *e, const char *name, long long value) {
         e->welch_splits = (int)value;
         return ZFB_OK;
     }
-    if (strcmp(name, "welch_stage") == 0) {
-        e->welch_stage = value ? 1 : 0;
+    if (strcmp(name, "welch_prune") == 0) {
+        if (value < 0 || value > 2) return fail(e, ZFB_EINVAL, "welch_prune must be 0, 1 or 2");
+        e->welch_prune = (int)value;
         return ZFB_OK;
     }
     if (strcmp(name, "strips_async") == 0) {

@@ -42,22 +42,11 @@ struct WelchParams {
 
 __device__ __forceinline__ int fpad(int a) { return a + (a >> 4); }
 
-// 8-byte asynchronous copy global -> shared (LDGSTS), tracked per thread
-#ifndef ZFB_EMULATE
-__device__ __forceinline__ void cp_async8(void *dst_smem, const void *src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src)
-                 : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-#else
-inline void cp_async8(void *dst, const void *src) { memcpy(dst, src, 8); }
-inline void cp_async_commit() {}
-inline void cp_async_wait_all() {}
-#endif
-
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// complex add / subtract as ONE packed instruction (FADD2; the negation is an operand modifier):
+// same IEEE result per component as two FADDs, half the issue slots -- the butterflies are 56 %
+// additions (welch_kernel<12,16>: 480 FADD of 1640 SASS instructions became 208 FADD2 + 64 FADD)
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
 // multiply by -i (forward FFT quarter turn)
 __device__ __forceinline__ float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }
 
@@ -296,26 +285,36 @@ struct WelchShape {
     static constexpr int NTHREADS = NT < 32 ? 32 : NT;       // launched threads
     static constexpr int MINB = NTHREADS <= 256 ? 2 : 1;     // >= 2 CTAs/SM: the passes are barrier-bound
     static constexpr size_t SMEM = (size_t)(N + (N >> 4) + 1) * sizeof(float2);
-    // staged variant: + the staging area of the next segment's new half (PPT/2 * NT = N/2 complex)
-    static constexpr size_t SMEM_STAGE = (size_t)(N + (N >> 4) + 2 + N / 2) * sizeof(float2);
 };
 
-template <int LOG2N, int PPT, int KIND, bool STAGE = false>
-__global__ void __launch_bounds__((WelchShape<LOG2N, PPT>::NTHREADS), (WelchShape<LOG2N, PPT>::MINB))
+// KEEP: how many of a thread's PPT bins (k = tid + m*NT) at EACH end of the spectrum can fall inside
+// the kept W columns: m < KEEP or m >= PPT - KEEP.  The reference crops the decimated spectrum to its
+// centre N/R bins (S:2114, T:1543), so for R >= 2 most of the last pass's outputs are never looked
+// at: with KEEP < PPT/2 only the kept ones are accumulated (2*KEEP instead of PPT registers) and the
+// compiler prunes the last butterfly to the outputs that are used.  KEEP = PPT/2: everything.
+// DENSE (needs KEEP <= 2, <= 256 threads): 3 CTAs/SM at 80 registers.  What makes room is the pruned
+// accumulator and NOT carrying the overlapping half of a segment in registers (16 of them): it is
+// fetched again (an L1/L2 hit: the same CTA read it one segment ago).
+template <int LOG2N, int PPT, int KIND, int KEEP = PPT / 2, bool DENSE = false>
+__global__ void __launch_bounds__((WelchShape<LOG2N, PPT>::NTHREADS), (DENSE ? 3 : WelchShape<LOG2N, PPT>::MINB))
 welch_kernel(const WelchParams p) {
     using S = WelchShape<LOG2N, PPT>;
     constexpr int N = S::N;
     constexpr int NT = S::NT;
     constexpr int H = PPT / 2;
+    static_assert(KEEP >= 1 && KEEP <= H, "KEEP counts bins per spectrum end");
+    static_assert(!DENSE || (KEEP <= 2 && S::NTHREADS <= 256), "DENSE: pruned accumulator, <= 256 threads");
+#define ZFB_KEPT(m) ((m) < KEEP || (m) >= PPT - KEEP)
     ZFB_DYN_SMEM(smem_raw);
     float2 *sm = reinterpret_cast<float2 *>(smem_raw);     // fpad(N) complex
     __shared__ float2 red[33];
 
     const int tid = threadIdx.x;
-    const bool active = tid < NT;
+    const bool active = (NT == S::NTHREADS) ? true : (tid < NT);
     const int split = blockIdx.x;
     const int frame = blockIdx.y;
     const size_t esz = (KIND == KIND_U8_RAW) ? 2 : 8;
+    const bool full = p.nperseg == N;       // the usual case: no bounds test per element
     const char *frame_in = (const char *)p.in + (size_t)frame * (size_t)p.in_stride * esz;
 
     float acc[PPT];
@@ -327,40 +326,37 @@ welch_kernel(const WelchParams p) {
     const int s_end = min(p.nseg, s_begin + p.seg_per_split);
     float2 raw[PPT];
 
-    // STAGE (option welch_stage): 50 % overlap, complex64 samples: the NEXT segment's new half is
-    // copied global -> shared (cp.async, 8 bytes per element, every thread its own H slots) while
-    // this segment's FFT runs, and picked up from there afterwards, so that the global latency
-    // (ncu: long scoreboard 0.85 per issue) hides behind the butterflies without a register.
-    // (Prefetching into a second register half instead was measured: 77.8 -> 97.8 us for the cfg2
-    // launch, gpurun r02k -- the kernel sits at 127 of the 128 registers it may use at 2 CTAs/SM.)
-    constexpr bool STAGED = STAGE && (KIND != KIND_U8_RAW);
-    float2 *stage = sm + fpad(N) + 1;                     // H * NT complex behind the exchange buffer
-    const bool staged = STAGED && p.reuse && !p.prepared;
+    // p.reuse (hop == N/2, nperseg == N; every BASELINE configuration): the second half of a segment
+    // is the first half of the next in the same thread's registers, and no element needs a bounds
+    // test -- a uniform branch picks that load sequence (H shifts + H unconditional loads)
+    const bool fastload = p.reuse && !p.prepared;
+    constexpr bool CARRY = !DENSE;
+    if (CARRY && fastload && s_begin < s_end) {           // first half of the first segment, parked in the upper half
+#pragma unroll
+        for (int m = 0; m < H; ++m)
+            raw[m + H] = active ? welch_fetch<KIND>(frame_in, s_begin * p.hop + tid + m * NT, p.len, p.flip)
+                                : make_float2(0.f, 0.f);
+    }
     for (int s = s_begin; s < s_end; ++s) {
         const int base = s * p.hop;
-        const bool carry = p.reuse && (s > s_begin);
+        if (fastload && !CARRY) {
 #pragma unroll
-        for (int m = 0; m < PPT; ++m) {
-            const int idx = tid + m * NT;
-            if (m < H && carry) {
-                raw[m] = raw[m + H];
-            } else if (carry && staged) {
-                raw[m] = active ? stage[(m - H) * NT + tid] : make_float2(0.f, 0.f);   // own copy: no barrier
-            } else {
-                raw[m] = (active && idx < p.nperseg)
-                             ? welch_fetch<KIND>(frame_in, base + idx, p.len, p.flip)
-                             : make_float2(0.f, 0.f);
-            }
-        }
-        if (staged && s + 1 < s_end && active) {
-            const int nb = (s + 1) * p.hop + H * NT + tid;
+            for (int m = 0; m < PPT; ++m)
+                raw[m] = active ? welch_fetch<KIND>(frame_in, base + tid + m * NT, p.len, p.flip) : make_float2(0.f, 0.f);
+        } else if (fastload) {
 #pragma unroll
-            for (int m = 0; m < H; ++m) {
-                const int idx = nb + m * NT;
-                const int i = (KIND == KIND_C64_RAW && p.flip) ? (p.len - 1 - idx) : idx;
-                cp_async8(stage + m * NT + tid, (const float2 *)frame_in + i);
+            for (int m = 0; m < H; ++m) raw[m] = raw[m + H];
+#pragma unroll
+            for (int m = 0; m < H; ++m)
+                raw[m + H] = active ? welch_fetch<KIND>(frame_in, base + tid + (m + H) * NT, p.len, p.flip)
+                                    : make_float2(0.f, 0.f);
+        } else {
+#pragma unroll
+            for (int m = 0; m < PPT; ++m) {
+                const int idx = tid + m * NT;
+                raw[m] = (active && idx < p.nperseg) ? welch_fetch<KIND>(frame_in, base + idx, p.len, p.flip)
+                                                     : make_float2(0.f, 0.f);
             }
-            cp_async_commit();
         }
         float2 v[PPT];
         if (p.prepared) {
@@ -373,18 +369,27 @@ welch_kernel(const WelchParams p) {
             // detrend='constant': subtract the segment's complex mean
             sum = block_sum<S::NTHREADS>(sum, tid, red);
             const float2 mean = make_float2(sum.x * inv_n, sum.y * inv_n);
+            float w[PPT];
+            if (full) {
+#pragma unroll
+                for (int m = 0; m < PPT; ++m) w[m] = active ? __ldg(p.window + tid + m * NT) : 0.f;
+            } else {
+#pragma unroll
+                for (int m = 0; m < PPT; ++m) {
+                    const int idx = tid + m * NT;
+                    w[m] = (active && idx < p.nperseg) ? __ldg(p.window + idx) : 0.f;
+                }
+            }
 #pragma unroll
             for (int m = 0; m < PPT; ++m) {
-                const int idx = tid + m * NT;
-                const float w = (active && idx < p.nperseg) ? __ldg(p.window + idx) : 0.f;
-                v[m].x = (raw[m].x - mean.x) * w;
-                v[m].y = (raw[m].y - mean.y) * w;
+                v[m].x = (raw[m].x - mean.x) * w[m];
+                v[m].y = (raw[m].y - mean.y) * w[m];
             }
         }
         fft_block<LOG2N, PPT>(v, tid, p.twiddle, sm);
 #pragma unroll
-        for (int m = 0; m < PPT; ++m) acc[m] = fmaf(v[m].x, v[m].x, fmaf(v[m].y, v[m].y, acc[m]));
-        if (staged) cp_async_wait_all();
+        for (int m = 0; m < PPT; ++m)
+            if (ZFB_KEPT(m)) acc[m] = fmaf(v[m].x, v[m].x, fmaf(v[m].y, v[m].y, acc[m]));
     }
 
     // fftshift + centre crop: natural bin k sits at column (k + N/2) mod N
@@ -393,10 +398,12 @@ welch_kernel(const WelchParams p) {
     float *row = p.pow_out + ((size_t)frame * p.nsplit + split) * p.W;
 #pragma unroll
     for (int m = 0; m < PPT; ++m) {
+        if (!ZFB_KEPT(m)) continue;
         const int k = tid + m * NT;
         const int col = ((k + N / 2) & (N - 1)) - c0;
         if (col >= 0 && col < p.W) row[col] = acc[m];
     }
+#undef ZFB_KEPT
 }
 
 // rows: sum the per-split partial sums in fixed order, scale, optional EMA
