@@ -161,6 +161,20 @@ static inline unsigned int __match_any_sync(unsigned, unsigned int v) {
         if ((unsigned int)w.slot[g & 1][l] == v) m |= 1u << l;
     return m;
 }
+// vote: true if any lane of the warp posted a non-zero predicate
+static inline int __any_sync(unsigned, int pred) {
+    cuemu::Cta *c = cuemu::t_cta;
+    const int t = c->cur, lane = t & 31;
+    cuemu::Warp &w = c->warps[t >> 5];
+    const int wsize = (c->nthreads - (t & ~31)) < 32 ? (c->nthreads - (t & ~31)) : 32;
+    const long g = ++w.gen[lane];
+    w.slot[g & 1][lane] = pred ? 1u : 0u;
+    w.arrived += 1;
+    cuemu::yield_until(&w.arrived, g * (long)wsize);
+    int any = 0;
+    for (int l = 0; l < wsize; ++l) any |= (int)w.slot[g & 1][l];
+    return any;
+}
 static inline int __popc(unsigned int x) { return __builtin_popcount(x); }
 static inline int __ffs(int x) { return __builtin_ffs(x); }
 
