@@ -68,6 +68,7 @@ struct zfb_engine {
     int late_mix = 1;                            // zfb_set_option("late_mix"): FIR chain may mix at its output
     int iir_stream = 1;                          // zfb_set_option("iir_stream"): streaming last stage of mode fast
     int iir_S = 640, iir_Wm = 256;               // zfb_set_option("iir_stream_len" (target) / "iir_stream_warm")
+    int iir_depth = 0;                           // zfb_set_option("iir_depth"): 0 = 3+3 tiles in flight per warp, 1 = 4+4, 2 = 5+4
     int iir_l2_keep = 70;                        // zfb_set_option("iir_l2_keep"): % of a stream's blocks kept in L2
     // plan of the streaming last stage (zfb_iirstream.cuh), valid while iis.active
     struct IirStreamPlan {
@@ -648,6 +649,10 @@ int setup_device_once(zfb_engine *e) {
         CK(e, cudaFuncSetAttribute(chain_lookup_fn(kind), cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     CK(e, cudaFuncSetAttribute((iir_stream_kernel<kIirNS, kIirNO>), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)IirStreamShape<kIirNS, kIirNO>::SMEM));
+    CK(e, cudaFuncSetAttribute((iir_stream_kernel<4, 4>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)IirStreamShape<4, 4>::SMEM));
+    CK(e, cudaFuncSetAttribute((iir_stream_kernel<5, 4>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)IirStreamShape<5, 4>::SMEM));
     int rc = fir_run_setup_kind<KIND_C64_RAW>(e);
     if (rc == ZFB_OK) rc = fir_run_setup_kind<KIND_U8_RAW>(e);
     if (rc == ZFB_OK) rc = fir_run_setup_kind<KIND_C64_MID>(e);
@@ -879,8 +884,14 @@ ChainFn chain_lookup(int kind) {
 void launch_iir_stream(zfb_engine *e, int gf, cudaStream_t st) {
     const zfb_engine::IirStreamPlan &pl = e->iis;
     const unsigned ctas = (unsigned)(gf * pl.q.groups);
-    ZFB_LAUNCH((iir_stream_kernel<kIirNS, kIirNO>), dim3(ctas), dim3(32), (IirStreamShape<kIirNS, kIirNO>::SMEM), st,
-               pl.tm_in, pl.tm_out, pl.q);
+    // tiles in flight per warp (option iir_depth): 3 + 3 (default), 4 + 4, 5 + 4
+    if (e->iir_depth == 1)
+        ZFB_LAUNCH((iir_stream_kernel<4, 4>), dim3(ctas), dim3(32), (IirStreamShape<4, 4>::SMEM), st, pl.tm_in, pl.tm_out, pl.q);
+    else if (e->iir_depth == 2)
+        ZFB_LAUNCH((iir_stream_kernel<5, 4>), dim3(ctas), dim3(32), (IirStreamShape<5, 4>::SMEM), st, pl.tm_in, pl.tm_out, pl.q);
+    else
+        ZFB_LAUNCH((iir_stream_kernel<kIirNS, kIirNO>), dim3(ctas), dim3(32), (IirStreamShape<kIirNS, kIirNO>::SMEM), st,
+                   pl.tm_in, pl.tm_out, pl.q);
 }
 
 // the K samples at either end of every decimated chunk, computed by the exact edge strips into
@@ -1328,7 +1339,8 @@ int run_group(zfb_engine *e, const void *d_in, int gf, float *d_rows) {
     if (e->log2N <= kMaxLog2Small) {
         // CTAs per frame: fixed per configuration (not per launch) so that the
         // summation order, hence every bit of a row, is independent of batching
-        int want = e->welch_splits > 0 ? e->welch_splits : 4;
+        // auto: 4, or 8 from 24 segments per frame (cfg1, 28 segments: 60.5 -> 56.3 us per launch, r02o)
+        int want = e->welch_splits > 0 ? e->welch_splits : (e->nseg >= 24 ? 8 : 4);
         if (want > e->nseg) want = e->nseg;
         if (want > e->nsplit_cap) want = e->nsplit_cap;
         if (want < 1) want = 1;
@@ -2154,6 +2166,11 @@ int zfb_set_option(zfb_engine *e, const char *name, long long value) {
         if (value < -1 || value > 1) return fail(e, ZFB_EINVAL, "precise must be -1 (auto), 0 or 1");
         e->precise = (int)value;
         e->configured = false;
+        return ZFB_OK;
+    }
+    if (strcmp(name, "iir_depth") == 0) {
+        if (value < 0 || value > 2) return fail(e, ZFB_EINVAL, "iir_depth must be 0, 1 or 2");
+        e->iir_depth = (int)value;
         return ZFB_OK;
     }
     if (strcmp(name, "iir_l2_keep") == 0) {

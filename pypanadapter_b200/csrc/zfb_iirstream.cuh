@@ -225,11 +225,12 @@ __global__ void __launch_bounds__(32) iir_stream_kernel(ZFB_TMAP_PARAM tm_in, ZF
             if (lane == 0) {
                 if (k + NS - 1 <= npieces) issue_x(k + NS - 1);
                 if (bwd) {
-                    // forward half of the NEXT kept piece into its row tile (last read by the store of
-                    // kept piece en - NO)
-                    const int en = e + 1;
+                    // forward half of the kept piece NO - 2 ahead into its row tile (last read by the
+                    // store of kept piece en - NO: at most one later store may still be reading)
+                    static_assert(NO >= 3, "row tiles: one being filled, NO - 2 on their way, one draining");
+                    const int en = e + (NO - 2);
                     if (en >= 0 && en < S16) {
-                        bulk_wait_read<(NO >= 2 ? NO - 2 : 0)>();
+                        bulk_wait_read<1>();
                         const unsigned slot = (unsigned)en % NO;
                         mbar_arrive_expect_tx(pbar + slot, IS_OTILE);
                         if (hints)

@@ -229,29 +229,11 @@ __device__ __forceinline__ void wf_count(unsigned int *h, unsigned int at, int l
     if (at != SEL_NONE && lane == __ffs((int)peers) - 1) atomicAdd(&h[at], (unsigned int)__popc(peers));
 }
 
-// Four neighbouring pixels of one thread first: neighbours in a dB row mostly share their leading
-// digits, so a thread run-length-merges its own four slots and the warp then matches RUNS -- key =
-// (slot, run length), so a group's weight is length * popc(peers) -- instead of pixels: usually one
-// MATCH and three votes per four pixels instead of four MATCHes (ncu: the kernel was bound by
-// MATCH/ATOMS issue at 25 % of HBM).  Rounds are skipped warp-uniformly (vote), so the collectives
-// stay convergent.
-__device__ __forceinline__ void wf_count4(unsigned int *h, const unsigned int (&at)[4], int lane) {
-    const bool s01 = at[0] == at[1], s12 = at[1] == at[2], s23 = at[2] == at[3];
-    unsigned int w[4];
-    w[3] = 1u;
-    w[2] = 1u + (s23 ? w[3] : 0u);
-    w[1] = 1u + (s12 ? w[2] : 0u);
-    w[0] = 1u + (s01 ? w[1] : 0u);
-    const bool head[4] = {true, !s01, !s12, !s23};
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        const bool mine = head[e] && at[e] != SEL_NONE;
-        if (e > 0 && !__any_sync(0xFFFFFFFFu, mine)) continue;
-        const unsigned int key = mine ? (at[e] << 3) + w[e] : SEL_NONE;
-        const unsigned int peers = __match_any_sync(0xFFFFFFFFu, key);
-        if (mine && lane == __ffs((int)peers) - 1) atomicAdd(&h[at[e]], w[e] * (unsigned int)__popc(peers));
-    }
-}
+// (Measured and dropped, gpurun r02o: run-length merging a thread's four slots before the MATCH --
+// one MATCH + three votes per four pixels -- made the sweeps SLOWER, 0.648 -> 0.711 ms on the
+// 8192 x 32768 image: only the first sweep's digits repeat among neighbours; sweeps two and three
+// spread the pixels of one prefix over 2048 / 512 bins, their cost is shared-memory atomics on
+// colliding banks (ncu: 3.4 M conflicts in 5.8 M wavefronts, short scoreboard 15.9 per issue), not MATCH.)
 
 template <int PASS>
 __global__ void __launch_bounds__(256) wf_select_kernel(const SelectParams s) {
@@ -276,10 +258,8 @@ __global__ void __launch_bounds__(256) wf_select_kernel(const SelectParams s) {
                 if (row && in) v = __ldg((const float4 *)(row + x0));
                 float q[4] = {v.x, v.y, v.z, v.w};
                 wf_fix4(p, row != nullptr, tick_row, x0, q);
-                unsigned int at[4];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) at[e] = in ? wf_slot<PASS>(s, q[e]) : SEL_NONE;
-                wf_count4(h, at, lane);
+                for (int e = 0; e < 4; ++e) wf_count(h, in ? wf_slot<PASS>(s, q[e]) : SEL_NONE, lane);
             }
         } else {
             for (int xb = 0; xb < p.W; xb += 256) {
