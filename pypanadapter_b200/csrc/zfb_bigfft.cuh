@@ -184,13 +184,17 @@ __global__ void __launch_bounds__(BIG_THREADS, 2) bigfft_row_kernel(const BigPar
 // N = 2^14 .. 2^17: decimation in frequency by 16 in front of the one-CTA FFT.
 //   X[16k + r] = FFT_S( Z_r )[k],  S = N/16,
 //   Z_r[n] = W_N^(r n) * sum_q x[n + S q] W_16^(q r),   x = window * (segment - mean)
-// big_halfsum_kernel : sums of the half-segment blocks (segment mean = two of them / N),
-// big_r16_kernel     : detrend + window + 16-point DFT across the 16 blocks + twiddle,
-//                      coalesced in and out -> scratch [frame][r][segment][S],
-// then welch_kernel (prepared = 1) runs its shared-memory FFT on every S-point block
-// and accumulates |X|^2 over the segments; big_gather_kernel puts bin 16k + r of
-// residue r back in place (fftshift + crop).  Exact detrend (no post-FFT correction)
-// and ~half the instructions of the generic four-step kernels above.
+// big_r16_kernel     : window + 16-point DFT across the 16 blocks + twiddle, coalesced in and
+//                      out -> scratch [frame][r][segment][S]; also the raw sum of the CTA's 4096
+//                      samples -> partial [frame][segment][S/256],
+// big_mean16_kernel  : segment means from those partial sums (fixed order),
+// then welch_kernel (prepared = 1) runs its shared-memory FFT on every S-point block, removes
+// the mean there -- detrend='constant' is linear: FFT(w (x - m)) = FFT(w x) - m FFT(w), with
+// FFT(w) from the host in fp64, stored per residue (winfft16 [r][k] = FFT(w)[16k + r]) -- and
+// accumulates |X|^2 over the segments; big_gather_kernel puts bin 16k + r of residue r back in
+// place (fftshift + crop).  ~Half the instructions of the generic four-step kernels above.
+// (Round 1 removed the mean before the window, which took a pass of its own over the input --
+// big_halfsum_kernel, 85 us of a 950 us cfg3 step at 78 % of the DRAM peak, ncu r02o.)
 // ===========================================================================
 struct BigR16Params {
     const void   *in;
@@ -198,21 +202,21 @@ struct BigR16Params {
     int           len, flip, log2N, hop, nseg;
     const float  *window;      // N taps
     const float2 *twiddle;     // N entries exp(-2 pi i k / N)
-    float2       *halfsum;     // [frames][nseg + 1]
+    float2       *partial;     // [frames][nseg][S/256] raw sums of the CTAs
+    float2       *means;       // [frames][nseg]
     float2       *scratch;     // [frames][16][nseg][S]
 };
 
-template <int KIND>
-__global__ void __launch_bounds__(256) big_halfsum_kernel(const BigR16Params p) {
-    __shared__ float2 red[33];
-    const int h = blockIdx.x, frame = blockIdx.y, t = threadIdx.x;
-    const size_t esz = (KIND == KIND_U8_RAW) ? 2 : 8;
-    const char *frame_in = (const char *)p.in + (size_t)frame * (size_t)p.in_stride * esz;
-    const int base = h * p.hop;
-    float2 sum = make_float2(0.f, 0.f);
-    for (int i = t; i < p.hop; i += 256) sum = cadd(sum, welch_fetch<KIND>(frame_in, base + i, p.len, p.flip));
-    sum = block_sum<256>(sum, t, red);
-    if (t == 0) p.halfsum[(size_t)frame * (p.nseg + 1) + h] = sum;
+// segment means from the front pass's per-CTA raw sums (fixed summation order)
+__global__ void big_mean16_kernel(const BigR16Params p, int nsegs_total) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nsegs_total) return;
+    const int nblk = (1 << p.log2N) >> 12;                 // S / 256
+    const float2 *src = p.partial + (size_t)i * nblk;
+    float2 s = make_float2(0.f, 0.f);
+    for (int t = 0; t < nblk; ++t) s = cadd(s, src[t]);
+    const float inv_n = 1.0f / (float)(1 << p.log2N);
+    p.means[i] = make_float2(s.x * inv_n, s.y * inv_n);
 }
 
 template <int KIND>
@@ -223,17 +227,19 @@ __global__ void __launch_bounds__(256) big_r16_kernel(const BigR16Params p) {
     const size_t esz = (KIND == KIND_U8_RAW) ? 2 : 8;
     const char *frame_in = (const char *)p.in + (size_t)frame * (size_t)p.in_stride * esz;
     const int base = s * p.hop;
-    const float2 *hs = p.halfsum + (size_t)frame * (p.nseg + 1) + s;
-    const float inv_n = 1.0f / (float)N;
-    const float2 mean = make_float2((hs[0].x + hs[1].x) * inv_n, (hs[0].y + hs[1].y) * inv_n);
+    __shared__ float2 red[33];
     float2 v[16];
+    float2 raw_sum = make_float2(0.f, 0.f);
 #pragma unroll
     for (int q = 0; q < 16; ++q) {
         const int idx = n + S * q;
         const float2 x = welch_fetch<KIND>(frame_in, base + idx, p.len, p.flip);
         const float w = __ldg(p.window + idx);
-        v[q] = make_float2((x.x - mean.x) * w, (x.y - mean.y) * w);
+        raw_sum = cadd(raw_sum, x);
+        v[q] = make_float2(x.x * w, x.y * w);
     }
+    raw_sum = block_sum<256>(raw_sum, threadIdx.x, red);
+    if (threadIdx.x == 0) p.partial[((size_t)frame * p.nseg + s) * (S >> 8) + blockIdx.x] = raw_sum;
     dft16(v);
     float2 *out = p.scratch + (((size_t)frame * 16) * p.nseg + s) * (size_t)S + n;
     const size_t rstride = (size_t)p.nseg * S;

@@ -59,6 +59,8 @@ struct zfb_engine {
 
     cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
     cudaStream_t aux_stream = nullptr;           // edge strips of mode fast run beside the FIR interior
+    cudaStream_t aux_stream_hi = nullptr;        // the same at the highest stream priority (option strips_priority)
+    int strips_priority = 0;                     // 1: strip CTAs are dispatched ahead of pending interior CTAs
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int strips_async = 1;                        // zfb_set_option("strips_async")
     int strip_split = 1;                         // zfb_set_option("strip_split"): narrower regions for the late strip stages
@@ -109,7 +111,7 @@ struct zfb_engine {
     StageParams sp0[3]{};              // LO tables of stage 0 for NT = 256 / 128 / 64 (strips)
 
     DevBuf cvt;                        // complex64 copy of an int16 IQ launch group (ZFB_DTYPE_CS16)
-    DevBuf window, winfft, twiddle, twiddle_sub, pow16, mid[2], pow, rows_tmp, ema, ring, stage_in[2], big, img_out, img_lut, img_thr, sel_hist;
+    DevBuf window, winfft, winfft16, twiddle, twiddle_sub, pow16, mid[2], pow, rows_tmp, ema, ring, stage_in[2], big, img_out, img_lut, img_thr, sel_hist;
     void  *h_stage[2] = {nullptr, nullptr};
     size_t h_stage_cap[2] = {0, 0};
     float *h_rows = nullptr;
@@ -593,6 +595,13 @@ ChainFn0 chain_lookup_fn(int kind) {
 template <int KIND> int fir_run_setup_kind(zfb_engine *e);
 constexpr int kIirNS = 3, kIirNO = 3;      // x pieces / output rows in flight per lane (zfb_iirstream.cuh)
 
+cudaError_t create_high_priority_stream(cudaStream_t *st) {
+    int lo = 0, hi = 0;                                  // numerically lower = higher priority
+    cudaError_t err = cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if (err != cudaSuccess) return err;
+    return cudaStreamCreateWithPriority(st, cudaStreamNonBlocking, hi);
+}
+
 int setup_device_once(zfb_engine *e) {
     DecimConst dc;
     build_decim_const(dc);
@@ -1029,16 +1038,17 @@ cudaError_t run_decimation_fast(zfb_engine *e, const void *d_in, int gf, int *ou
     // interior owns the rest, so the two need no order between them: with k <= 4 the
     // strips go to a side stream and fill the SMs beside the FIR interior.
     const bool async_strips = e->strips_async && s0 == 0;
+    cudaStream_t aux = e->strips_priority ? e->aux_stream_hi : e->aux_stream;
     cudaError_t err = cudaSuccess;
     // strips_async 1: strips are submitted before the FIR chain (their CTAs are dispatched
     // first), 2: after it (they fill its tail and run beside the exact last stage)
     const bool strips_first = e->strips_async != 2;
     if (async_strips) {
         if ((err = cudaEventRecord(e->ev_fork, st)) != cudaSuccess) return err;      // input ready, buffers free
-        if ((err = cudaStreamWaitEvent(e->aux_stream, e->ev_fork, 0)) != cudaSuccess) return err;
+        if ((err = cudaStreamWaitEvent(aux, e->ev_fork, 0)) != cudaSuccess) return err;
         if (strips_first) {
-            launch_fused_strips(e, d_in, gf, final_out, e->aux_stream);
-            if ((err = cudaEventRecord(e->ev_join, e->aux_stream)) != cudaSuccess) return err;
+            launch_fused_strips(e, d_in, gf, final_out, aux);
+            if ((err = cudaEventRecord(e->ev_join, aux)) != cudaSuccess) return err;
         }
     }
     const void *src = d_in;
@@ -1076,8 +1086,8 @@ cudaError_t run_decimation_fast(zfb_engine *e, const void *d_in, int gf, int *ou
         b ^= 1;
     }
     if (async_strips && !strips_first) {
-        launch_fused_strips(e, d_in, gf, final_out, e->aux_stream);
-        if ((err = cudaEventRecord(e->ev_join, e->aux_stream)) != cudaSuccess) return err;
+        launch_fused_strips(e, d_in, gf, final_out, aux);
+        if ((err = cudaEventRecord(e->ev_join, aux)) != cudaSuccess) return err;
     }
     const int v = (e->decim_threads == NTHR_BIG) ? 0 : 1;
     {   // the last decimate call, exact, over the whole (FIR-filtered) chunk; it leaves the
@@ -1386,19 +1396,20 @@ int run_group(zfb_engine *e, const void *d_in, int gf, float *d_rows) {
         r.window = (const float *)e->window.p;
         r.twiddle = (const float2 *)e->twiddle.p;
         r.scratch = (float2 *)e->big.p;
-        r.halfsum = r.scratch + ((size_t)e->group * (size_t)e->nseg << e->log2N);
+        // behind the scratch: per-CTA raw sums [group][nseg][S/256], then the means [group][nseg]
+        r.partial = r.scratch + ((size_t)e->group * (size_t)e->nseg << e->log2N);
+        r.means = r.partial + (size_t)e->group * (size_t)e->nseg * (size_t)(S / 256);
         const int pr = prof_begin(e, 16);
-        const dim3 gh((unsigned)(e->nseg + 1), (unsigned)gf), gr((unsigned)(S / 256), (unsigned)e->nseg, (unsigned)gf);
+        const dim3 gr((unsigned)(S / 256), (unsigned)e->nseg, (unsigned)gf);
         if (kind == KIND_C64_RAW) {
-            ZFB_LAUNCH(big_halfsum_kernel<KIND_C64_RAW>, gh, dim3(256), 0, st, r);
             ZFB_LAUNCH(big_r16_kernel<KIND_C64_RAW>, gr, dim3(256), 0, st, r);
         } else if (kind == KIND_U8_RAW) {
-            ZFB_LAUNCH(big_halfsum_kernel<KIND_U8_RAW>, gh, dim3(256), 0, st, r);
             ZFB_LAUNCH(big_r16_kernel<KIND_U8_RAW>, gr, dim3(256), 0, st, r);
         } else {
-            ZFB_LAUNCH(big_halfsum_kernel<KIND_C64_MID>, gh, dim3(256), 0, st, r);
             ZFB_LAUNCH(big_r16_kernel<KIND_C64_MID>, gr, dim3(256), 0, st, r);
         }
+        const int nsegs_total = gf * e->nseg;
+        ZFB_LAUNCH(big_mean16_kernel, dim3((unsigned)((nsegs_total + 127) / 128)), dim3(128), 0, st, r, nsegs_total);
         prof_end(e, pr);
         WelchParams w{};
         w.in = r.scratch;
@@ -1416,6 +1427,8 @@ int run_group(zfb_engine *e, const void *d_in, int gf, float *d_rows) {
         w.twiddle = (const float2 *)e->twiddle_sub.p;
         w.W = S;
         w.pow_out = (float *)e->pow16.p;
+        w.seg_mean = r.means;
+        w.wf16 = (const float2 *)e->winfft16.p;
         WelchEntry we = welch_lookup(lS, KIND_C64_MID);
         const int pr2 = prof_begin(e, 17);
         ZFB_LAUNCH(we.fn, dim3((unsigned)ns16, (unsigned)(gf * 16)), dim3((unsigned)we.threads), we.smem, st, w);
@@ -1754,6 +1767,7 @@ int zfb_create(int device, zfb_engine **out) {
         if (cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
             cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
             cudaStreamCreateWithFlags(&e->aux_stream, cudaStreamNonBlocking) != cudaSuccess ||
+            create_high_priority_stream(&e->aux_stream_hi) != cudaSuccess ||
             cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming) != cudaSuccess) {
             rc = fail(nullptr, ZFB_ECUDA, "stream creation failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -1785,7 +1799,8 @@ void zfb_destroy(zfb_engine *e) {
     if (e->own_stream) cudaStreamSynchronize(e->own_stream);
     if (e->copy_stream) cudaStreamSynchronize(e->copy_stream);
     if (e->aux_stream) cudaStreamSynchronize(e->aux_stream);
-    DevBuf *bufs[] = {&e->window, &e->winfft, &e->twiddle, &e->twiddle_sub, &e->pow16, &e->mid[0], &e->mid[1], &e->pow, &e->rows_tmp, &e->ema,
+    if (e->aux_stream_hi) cudaStreamSynchronize(e->aux_stream_hi);
+    DevBuf *bufs[] = {&e->window, &e->winfft, &e->winfft16, &e->twiddle, &e->twiddle_sub, &e->pow16, &e->mid[0], &e->mid[1], &e->pow, &e->rows_tmp, &e->ema,
                       &e->img_out, &e->img_lut, &e->img_thr, &e->sel_hist, &e->ring, &e->stage_in[0], &e->stage_in[1], &e->big};
     for (DevBuf *b : bufs) release(*b);
     for (int i = 0; i < 2; ++i) {
@@ -1811,6 +1826,7 @@ void zfb_destroy(zfb_engine *e) {
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     if (e->aux_stream) cudaStreamDestroy(e->aux_stream);
+    if (e->aux_stream_hi) cudaStreamDestroy(e->aux_stream_hi);
     if (e->ev_fork) cudaEventDestroy(e->ev_fork);
     if (e->ev_join) cudaEventDestroy(e->ev_join);
     delete e;
@@ -1908,6 +1924,17 @@ int zfb_configure(zfb_engine *e, const zfb_config *cfg) {
         if (rc) return rc;
         CK(e, cudaMemcpyAsync(e->winfft.p, wff.data(), wff.size() * sizeof(float2), cudaMemcpyHostToDevice, e->stream));
         CK(e, cudaStreamSynchronize(e->stream));
+        if (l2 >= kMinLog2R16 && l2 <= kMaxLog2R16) {
+            // the same per residue of the radix-16 front pass: winfft16[r][k] = FFT(w)[16 k + r]
+            std::vector<float2> w16((size_t)N);
+            const int S16 = N >> 4;
+            for (int r = 0; r < 16; ++r)
+                for (int k = 0; k < S16; ++k) w16[(size_t)r * S16 + k] = wff[(size_t)16 * k + r];
+            rc = ensure(e, e->winfft16, w16.size() * sizeof(float2));
+            if (rc) return rc;
+            CK(e, cudaMemcpyAsync(e->winfft16.p, w16.data(), w16.size() * sizeof(float2), cudaMemcpyHostToDevice, e->stream));
+            CK(e, cudaStreamSynchronize(e->stream));
+        }
     }
 
     if (!e->configured || e->cfg.fft_size != N) {
@@ -2127,6 +2154,10 @@ int zfb_set_option(zfb_engine *e, const char *name, long long value) {
     }
     if (strcmp(name, "strips_async") == 0) {
         e->strips_async = (value == 2) ? 2 : (value ? 1 : 0);
+        return ZFB_OK;
+    }
+    if (strcmp(name, "strips_priority") == 0) {
+        e->strips_priority = value ? 1 : 0;
         return ZFB_OK;
     }
     if (strcmp(name, "strip_decay") == 0) {

@@ -38,6 +38,10 @@ struct WelchParams {
     const float2*twiddle;     // N entries exp(-2 pi i k / N)
     int          W;           // row width
     float       *pow_out;     // [frames][nsplit][W] sum_s |X|^2, fftshifted + cropped
+    // prepared blocks of the radix-16 front pass (frame index = 16 * frame + residue r): the
+    // segment mean is removed after the FFT, X -= mean[frame][s] * wf16[r][k]; null: nothing to remove
+    const float2*seg_mean;    // [frames / 16][nseg]
+    const float2*wf16;        // [16][N]: FFT(window)[16 k + r]
 };
 
 __device__ __forceinline__ int fpad(int a) { return a + (a >> 4); }
@@ -387,6 +391,13 @@ welch_kernel(const WelchParams p) {
             }
         }
         fft_block<LOG2N, PPT>(v, tid, p.twiddle, sm);
+        if (p.prepared && p.seg_mean != nullptr && active) {
+            const float2 mean = __ldg(p.seg_mean + (size_t)(frame >> 4) * p.nseg + s);
+            const float2 nm = make_float2(-mean.x, -mean.y);
+            const float2 *wf = p.wf16 + (size_t)(frame & 15) * N + tid;
+#pragma unroll
+            for (int m = 0; m < PPT; ++m) v[m] = cadd(v[m], cmul(nm, __ldg(wf + m * NT)));
+        }
 #pragma unroll
         for (int m = 0; m < PPT; ++m)
             if (ZFB_KEPT(m)) acc[m] = fmaf(v[m].x, v[m].x, fmaf(v[m].y, v[m].y, acc[m]));
