@@ -1042,7 +1042,7 @@ cudaError_t run_decimation_fast(zfb_engine *e, const void *d_in, int gf, int *ou
     cudaError_t err = cudaSuccess;
     // strips_async 1: strips are submitted before the FIR chain (their CTAs are dispatched
     // first), 2: after it (they fill its tail and run beside the exact last stage)
-    const bool strips_first = e->strips_async != 2;
+    const bool strips_first = e->strips_async == 1;
     if (async_strips) {
         if ((err = cudaEventRecord(e->ev_fork, st)) != cudaSuccess) return err;      // input ready, buffers free
         if ((err = cudaStreamWaitEvent(aux, e->ev_fork, 0)) != cudaSuccess) return err;
@@ -1086,6 +1086,13 @@ cudaError_t run_decimation_fast(zfb_engine *e, const void *d_in, int gf, int *ou
         b ^= 1;
     }
     if (async_strips && !strips_first) {
+        if (e->strips_async == 3) {
+            // strips beside the last stage only: they wait for the FIR interior (which leaves no
+            // registers for them on an SM anyway) and share the SMs with the streaming last stage,
+            // one warp per CTA and DRAM-latency-bound
+            if ((err = cudaEventRecord(e->ev_fork, st)) != cudaSuccess) return err;
+            if ((err = cudaStreamWaitEvent(aux, e->ev_fork, 0)) != cudaSuccess) return err;
+        }
         launch_fused_strips(e, d_in, gf, final_out, aux);
         if ((err = cudaEventRecord(e->ev_join, aux)) != cudaSuccess) return err;
     }
@@ -2153,7 +2160,7 @@ int zfb_set_option(zfb_engine *e, const char *name, long long value) {
         return ZFB_OK;
     }
     if (strcmp(name, "strips_async") == 0) {
-        e->strips_async = (value == 2) ? 2 : (value ? 1 : 0);
+        e->strips_async = (value == 2 || value == 3) ? (int)value : (value ? 1 : 0);
         return ZFB_OK;
     }
     if (strcmp(name, "strips_priority") == 0) {
