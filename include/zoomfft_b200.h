@@ -149,7 +149,16 @@ int  zfb_reset_ema(zfb_engine *e);
  * by < 1e-3 dB); 0: always mix first.
  * "ring_append" = 1 (default): every processed row also enters the waterfall
  * ring; 0: only zfb_ring_push_rows does (display loops that show a subset of
- * the rows, like the threaded variant's GUI timer, T:2140-2148). */
+ * the rows, like the threaded variant's GUI timer, T:2140-2148).
+ * "precise" = -1 (default: rows of <= 6 Welch segments take the fp64 path),
+ * 0 never, 1 always.
+ * Measurement knobs of mode FAST (defaults are the measured best; rows do not
+ * depend on them beyond 1e-3 dB): "strips_async" 0 | 1 | 2 | 3 (edge strips on
+ * the main stream | side stream, submitted first | after the FIR chain | beside
+ * the last stage only), "strips_priority" 0 | 1, "strip_split", "strip_decay",
+ * "strip_decay_early", "fir_threads" 128 | 256, "fir_generic", "iir_stream" 0 | 1
+ * (streaming last stage), "iir_stream_len", "iir_stream_warm", "iir_l2_keep",
+ * "iir_depth" 0 | 1 | 2, "welch_prune" 0 | 1 | 2.  Unknown names: ZFB_EINVAL. */
 int  zfb_set_option(zfb_engine *e, const char *name, long long value);
 
 /* ---- the hot path ----------------------------------------------------- */

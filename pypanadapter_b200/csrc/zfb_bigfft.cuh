@@ -202,12 +202,41 @@ struct BigR16Params {
     int           len, flip, log2N, hop, nseg;
     const float  *window;      // N taps
     const float2 *twiddle;     // N entries exp(-2 pi i k / N)
-    float2       *partial;     // [frames][nseg][S/256] raw sums of the CTAs
-    float2       *means;       // [frames][nseg]
+    float2       *partial;     // [frames][nseg][S/256] sums of the CTAs' samples (less the frame's DC estimate)
+    float2       *means;       // [frames][nseg] segment mean less the frame's DC estimate
+    float2       *dc;          // [frames] DC estimate of the frame (big_dc_kernel)
     float2       *scratch;     // [frames][16][nseg][S]
 };
 
-// segment means from the front pass's per-CTA raw sums (fixed summation order)
+// A frame's DC estimate from 8192 samples spread over it (32 KB of an 8 MB row).  It is removed
+// BEFORE the window, the rest of each segment's mean after the FFT: exact in exact arithmetic
+// whatever the estimate is, and in fp32 the post-FFT correction then cancels a term proportional
+// to |segment mean - estimate| instead of |segment mean| (a chunk with a DC offset of 0.4 and
+// noise at 2e-3 read 0.015 dB20 off next to the DC bin with the plain post-FFT removal).
+constexpr int BIG_DC_SAMPLES = 8192;
+template <int KIND>
+__global__ void __launch_bounds__(256) big_dc_kernel(const BigR16Params p) {
+    __shared__ float2 red[33];
+    const int frame = blockIdx.x, t = threadIdx.x;
+    const size_t esz = (KIND == KIND_U8_RAW) ? 2 : 8;
+    const char *frame_in = (const char *)p.in + (size_t)frame * (size_t)p.in_stride * esz;
+    const int used = (p.nseg + 1) * p.hop;                   // samples the segments cover
+    const int stride = used / BIG_DC_SAMPLES > 0 ? used / BIG_DC_SAMPLES : 1;
+    float2 sum = make_float2(0.f, 0.f);
+    int cnt = 0;
+    for (int j = t; j < BIG_DC_SAMPLES; j += 256) {
+        const long long idx = (long long)j * stride;
+        if (idx < used) {
+            sum = cadd(sum, welch_fetch<KIND>(frame_in, (int)idx, p.len, p.flip));
+            cnt += 1;
+        }
+    }
+    sum = block_sum<256>(sum, t, red);
+    const float2 c = block_sum<256>(make_float2((float)cnt, 0.f), t, red + 0);
+    if (t == 0) p.dc[frame] = make_float2(sum.x / fmaxf(c.x, 1.f), sum.y / fmaxf(c.x, 1.f));
+}
+
+// segment means (less the DC estimate) from the front pass's per-CTA sums (fixed summation order)
 __global__ void big_mean16_kernel(const BigR16Params p, int nsegs_total) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nsegs_total) return;
@@ -230,11 +259,13 @@ __global__ void __launch_bounds__(256) big_r16_kernel(const BigR16Params p) {
     __shared__ float2 red[33];
     float2 v[16];
     float2 raw_sum = make_float2(0.f, 0.f);
+    const float2 dc = __ldg(p.dc + frame);
 #pragma unroll
     for (int q = 0; q < 16; ++q) {
         const int idx = n + S * q;
-        const float2 x = welch_fetch<KIND>(frame_in, base + idx, p.len, p.flip);
+        float2 x = welch_fetch<KIND>(frame_in, base + idx, p.len, p.flip);
         const float w = __ldg(p.window + idx);
+        x = make_float2(x.x - dc.x, x.y - dc.y);
         raw_sum = cadd(raw_sum, x);
         v[q] = make_float2(x.x * w, x.y * w);
     }
@@ -294,7 +325,7 @@ inline int big_ntiles_col(int log2N) {
 }
 
 inline size_t big_scratch_bytes(int log2N, int nseg, int frames) {
-    return (size_t)frames * (size_t)nseg * (((size_t)1 << log2N) + (size_t)big_ntiles_col(log2N) + 1) * sizeof(float2);
+    return (size_t)frames * (size_t)nseg * (((size_t)1 << log2N) + (size_t)big_ntiles_col(log2N) + 2) * sizeof(float2);
 }
 
 template <int LM1>

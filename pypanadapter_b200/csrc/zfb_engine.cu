@@ -99,6 +99,9 @@ struct zfb_engine {
     int tiles[kMaxStages][2] = {{0}}, T[kMaxStages][2] = {{0}};   // [stage][0: NT=256, 1: NT=128]
     int decim_threads = 0;             // 0 = automatic per launch
     int welch_splits = 0;              // 0 = automatic
+    int wf_sparse_n = 0;               // non-zero bins of FFT(window) when there are few (cosine-sum windows), else 0
+    int wf_sparse_bin[WF_SPARSE_MAX] = {0};
+    float2 wf_sparse_val[WF_SPARSE_MAX] = {};
     int welch_prune = 2;               // 0: all bins accumulated; 1: only keepable ones; 2: + 3 CTAs/SM where it fits
     int fir_generic = 0;               // 1: never use the register-blocked FIR kernel (tests)
     int fir_threads = 128;             // zfb_set_option("fir_threads"): 256 or 128 threads per CTA of fir_run_kernel
@@ -1406,13 +1409,17 @@ int run_group(zfb_engine *e, const void *d_in, int gf, float *d_rows) {
         // behind the scratch: per-CTA raw sums [group][nseg][S/256], then the means [group][nseg]
         r.partial = r.scratch + ((size_t)e->group * (size_t)e->nseg << e->log2N);
         r.means = r.partial + (size_t)e->group * (size_t)e->nseg * (size_t)(S / 256);
+        r.dc = r.means + (size_t)e->group * (size_t)e->nseg;
         const int pr = prof_begin(e, 16);
         const dim3 gr((unsigned)(S / 256), (unsigned)e->nseg, (unsigned)gf);
         if (kind == KIND_C64_RAW) {
+            ZFB_LAUNCH(big_dc_kernel<KIND_C64_RAW>, dim3((unsigned)gf), dim3(256), 0, st, r);
             ZFB_LAUNCH(big_r16_kernel<KIND_C64_RAW>, gr, dim3(256), 0, st, r);
         } else if (kind == KIND_U8_RAW) {
+            ZFB_LAUNCH(big_dc_kernel<KIND_U8_RAW>, dim3((unsigned)gf), dim3(256), 0, st, r);
             ZFB_LAUNCH(big_r16_kernel<KIND_U8_RAW>, gr, dim3(256), 0, st, r);
         } else {
+            ZFB_LAUNCH(big_dc_kernel<KIND_C64_MID>, dim3((unsigned)gf), dim3(256), 0, st, r);
             ZFB_LAUNCH(big_r16_kernel<KIND_C64_MID>, gr, dim3(256), 0, st, r);
         }
         const int nsegs_total = gf * e->nseg;
@@ -1436,6 +1443,11 @@ int run_group(zfb_engine *e, const void *d_in, int gf, float *d_rows) {
         w.pow_out = (float *)e->pow16.p;
         w.seg_mean = r.means;
         w.wf16 = (const float2 *)e->winfft16.p;
+        w.wf_n = e->wf_sparse_n;
+        for (int j = 0; j < e->wf_sparse_n; ++j) {
+            w.wf_bin[j] = e->wf_sparse_bin[j];
+            w.wf_val[j] = e->wf_sparse_val[j];
+        }
         WelchEntry we = welch_lookup(lS, KIND_C64_MID);
         const int pr2 = prof_begin(e, 17);
         ZFB_LAUNCH(we.fn, dim3((unsigned)ns16, (unsigned)(gf * 16)), dim3((unsigned)we.threads), we.smem, st, w);
@@ -1449,7 +1461,7 @@ int run_group(zfb_engine *e, const void *d_in, int gf, float *d_rows) {
         const long long cellsg = (long long)gf * e->W;
         ZFB_LAUNCH(big_gather_kernel, dim3((unsigned)((cellsg + 255) / 256)), dim3(256), 0, st, g);
         prof_end(e, pr2);
-        e->counters[2] += 4;
+        e->counters[2] += 5;
         nsplit = 1;
     } else {
         int want = e->welch_splits > 0 ? e->welch_splits : 4;
@@ -1932,6 +1944,20 @@ int zfb_configure(zfb_engine *e, const zfb_config *cfg) {
         CK(e, cudaMemcpyAsync(e->winfft.p, wff.data(), wff.size() * sizeof(float2), cudaMemcpyHostToDevice, e->stream));
         CK(e, cudaStreamSynchronize(e->stream));
         if (l2 >= kMinLog2R16 && l2 <= kMaxLog2R16) {
+            // cosine-sum windows: FFT(w) is a few bins around DC (fp64 FFT noise ~1e-16 N elsewhere)
+            double peak = 0.0;
+            for (int i = 0; i < N; ++i) peak = std::max(peak, hypot(re[(size_t)i], im[(size_t)i]));
+            int nnz = 0;
+            e->wf_sparse_n = 0;
+            for (int i = 0; i < N && nnz <= WF_SPARSE_MAX; ++i)
+                if (hypot(re[(size_t)i], im[(size_t)i]) > 1e-11 * peak) {
+                    if (nnz < WF_SPARSE_MAX) {
+                        e->wf_sparse_bin[nnz] = i;
+                        e->wf_sparse_val[nnz] = wff[(size_t)i];
+                    }
+                    ++nnz;
+                }
+            if (nnz >= 1 && nnz <= WF_SPARSE_MAX) e->wf_sparse_n = nnz;
             // the same per residue of the radix-16 front pass: winfft16[r][k] = FFT(w)[16 k + r]
             std::vector<float2> w16((size_t)N);
             const int S16 = N >> 4;

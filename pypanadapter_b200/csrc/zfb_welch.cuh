@@ -22,6 +22,8 @@
 
 namespace zfb {
 
+constexpr int WF_SPARSE_MAX = 12;
+
 struct WelchParams {
     const void  *in;          // [frames][in_stride], kind per template
     long long    in_stride;
@@ -42,6 +44,11 @@ struct WelchParams {
     // segment mean is removed after the FFT, X -= mean[frame][s] * wf16[r][k]; null: nothing to remove
     const float2*seg_mean;    // [frames / 16][nseg]
     const float2*wf16;        // [16][N]: FFT(window)[16 k + r]
+    // cosine-sum windows (boxcar, hann, hamming, blackman, nuttall, flattop ...) have a handful of
+    // non-zero FFT bins: then only those are corrected (wf_n > 0) and wf16 is not read at all
+    int          wf_n;        // 0: dense table
+    int          wf_bin[WF_SPARSE_MAX];     // bin index 16 k + r of the big FFT
+    float2       wf_val[WF_SPARSE_MAX];
 };
 
 __device__ __forceinline__ int fpad(int a) { return a + (a >> 4); }
@@ -394,9 +401,23 @@ welch_kernel(const WelchParams p) {
         if (p.prepared && p.seg_mean != nullptr && active) {
             const float2 mean = __ldg(p.seg_mean + (size_t)(frame >> 4) * p.nseg + s);
             const float2 nm = make_float2(-mean.x, -mean.y);
-            const float2 *wf = p.wf16 + (size_t)(frame & 15) * N + tid;
+            if (p.wf_n > 0) {
+                const int r = frame & 15;
+                for (int j = 0; j < p.wf_n; ++j) {
+                    const int b = p.wf_bin[j];
+                    if ((b & 15) != r) continue;               // uniform: another residue's bin
+                    const int k = b >> 4;
+                    if ((k & (NT - 1)) != tid) continue;
+                    const float2 c = cmul(nm, p.wf_val[j]);
 #pragma unroll
-            for (int m = 0; m < PPT; ++m) v[m] = cadd(v[m], cmul(nm, __ldg(wf + m * NT)));
+                    for (int m = 0; m < PPT; ++m)
+                        if (m == k / NT) v[m] = cadd(v[m], c);
+                }
+            } else {
+                const float2 *wf = p.wf16 + (size_t)(frame & 15) * N + tid;
+#pragma unroll
+                for (int m = 0; m < PPT; ++m) v[m] = cadd(v[m], cmul(nm, __ldg(wf + m * NT)));
+            }
         }
 #pragma unroll
         for (int m = 0; m < PPT; ++m)

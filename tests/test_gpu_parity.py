@@ -96,6 +96,22 @@ def test_sweep_corner(gpu_engine, N, R):
     parity.assert_row_parity(row, want, parity.floor_db20(fs, "hamming", N, R > 1), "N%d R%d" % (N, R))
 
 
+@pytest.mark.parametrize("window", ["hann", "blackmanharris", "boxcar", ("kaiser", 8.6), "bartlett"])
+def test_big_fft_detrend_with_dc(gpu_engine, window):
+    """N = 65536 (radix-16 front pass): scipy.signal.welch's detrend='constant' (S:2111) is applied
+    after the FFT there, X -= mean * FFT(window) -- through the few non-zero bins of a cosine-sum
+    window or the dense table of any other -- so a chunk with a strong DC offset is the case to hold
+    against the oracle."""
+    fs, N = 2.4e6, 65536
+    n = N * 5
+    x = gc.tone_noise(n, fs, [(0.11 * fs, 0.3), (-0.23 * fs, 0.02)], 2e-3, 4242, np.complex64)
+    x = (x + np.complex64(0.35 - 0.2j)).astype(np.complex64)
+    gpu_engine.configure(fs, N, 1, n, window, crop=None)
+    row = gpu_engine.process(x)[0].astype(np.float64)
+    want = zo.zoom_psd(x, fs, N, 1, window, crop=None)
+    parity.assert_row_parity(row, want, parity.floor_db20(fs, window, N, False), "N65536 dc %s" % (window,))
+
+
 def test_device_path_equals_host_path(gpu_engine):
     """zfb_process_device on resident buffers == zfb_process_host, bit for bit,
     at a batch that spans several groups (size-independent property)."""
