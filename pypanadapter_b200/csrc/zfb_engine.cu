@@ -114,7 +114,7 @@ struct zfb_engine {
     StageParams sp0[3]{};              // LO tables of stage 0 for NT = 256 / 128 / 64 (strips)
 
     DevBuf cvt;                        // complex64 copy of an int16 IQ launch group (ZFB_DTYPE_CS16)
-    DevBuf window, winfft, winfft16, twiddle, twiddle_sub, pow16, mid[2], pow, rows_tmp, ema, ring, stage_in[2], big, img_out, img_lut, img_thr, sel_hist;
+    DevBuf window, winfft, winfft16, wf_sparse, twiddle, twiddle_sub, pow16, mid[2], pow, rows_tmp, ema, ring, stage_in[2], big, img_out, img_lut, img_thr, sel_hist;
     void  *h_stage[2] = {nullptr, nullptr};
     size_t h_stage_cap[2] = {0, 0};
     float *h_rows = nullptr;
@@ -1444,10 +1444,8 @@ int run_group(zfb_engine *e, const void *d_in, int gf, float *d_rows) {
         w.seg_mean = r.means;
         w.wf16 = (const float2 *)e->winfft16.p;
         w.wf_n = e->wf_sparse_n;
-        for (int j = 0; j < e->wf_sparse_n; ++j) {
-            w.wf_bin[j] = e->wf_sparse_bin[j];
-            w.wf_val[j] = e->wf_sparse_val[j];
-        }
+        w.wf_bin = (const int *)e->wf_sparse.p;
+        w.wf_val = (const float2 *)((const char *)e->wf_sparse.p + WF_SPARSE_MAX * sizeof(int));
         WelchEntry we = welch_lookup(lS, KIND_C64_MID);
         const int pr2 = prof_begin(e, 17);
         ZFB_LAUNCH(we.fn, dim3((unsigned)ns16, (unsigned)(gf * 16)), dim3((unsigned)we.threads), we.smem, st, w);
@@ -1819,7 +1817,7 @@ void zfb_destroy(zfb_engine *e) {
     if (e->copy_stream) cudaStreamSynchronize(e->copy_stream);
     if (e->aux_stream) cudaStreamSynchronize(e->aux_stream);
     if (e->aux_stream_hi) cudaStreamSynchronize(e->aux_stream_hi);
-    DevBuf *bufs[] = {&e->window, &e->winfft, &e->winfft16, &e->twiddle, &e->twiddle_sub, &e->pow16, &e->mid[0], &e->mid[1], &e->pow, &e->rows_tmp, &e->ema,
+    DevBuf *bufs[] = {&e->window, &e->winfft, &e->winfft16, &e->wf_sparse, &e->twiddle, &e->twiddle_sub, &e->pow16, &e->mid[0], &e->mid[1], &e->pow, &e->rows_tmp, &e->ema,
                       &e->img_out, &e->img_lut, &e->img_thr, &e->sel_hist, &e->ring, &e->stage_in[0], &e->stage_in[1], &e->big};
     for (DevBuf *b : bufs) release(*b);
     for (int i = 0; i < 2; ++i) {
@@ -1958,6 +1956,15 @@ int zfb_configure(zfb_engine *e, const zfb_config *cfg) {
                     ++nnz;
                 }
             if (nnz >= 1 && nnz <= WF_SPARSE_MAX) e->wf_sparse_n = nnz;
+            {   // [WF_SPARSE_MAX] bins, then [WF_SPARSE_MAX] values
+                unsigned char blob[WF_SPARSE_MAX * (sizeof(int) + sizeof(float2))] = {0};
+                memcpy(blob, e->wf_sparse_bin, sizeof e->wf_sparse_bin);
+                memcpy(blob + WF_SPARSE_MAX * sizeof(int), e->wf_sparse_val, sizeof e->wf_sparse_val);
+                rc = ensure(e, e->wf_sparse, sizeof blob);
+                if (rc) return rc;
+                CK(e, cudaMemcpyAsync(e->wf_sparse.p, blob, sizeof blob, cudaMemcpyHostToDevice, e->stream));
+                CK(e, cudaStreamSynchronize(e->stream));
+            }
             // the same per residue of the radix-16 front pass: winfft16[r][k] = FFT(w)[16 k + r]
             std::vector<float2> w16((size_t)N);
             const int S16 = N >> 4;

@@ -47,8 +47,8 @@ struct WelchParams {
     // cosine-sum windows (boxcar, hann, hamming, blackman, nuttall, flattop ...) have a handful of
     // non-zero FFT bins: then only those are corrected (wf_n > 0) and wf16 is not read at all
     int          wf_n;        // 0: dense table
-    int          wf_bin[WF_SPARSE_MAX];     // bin index 16 k + r of the big FFT
-    float2       wf_val[WF_SPARSE_MAX];
+    const int   *wf_bin;      // [wf_n] bin index 16 k + r of the big FFT (device memory: indexed in a loop)
+    const float2*wf_val;      // [wf_n]
 };
 
 __device__ __forceinline__ int fpad(int a) { return a + (a >> 4); }
@@ -303,11 +303,11 @@ struct WelchShape {
 // centre N/R bins (S:2114, T:1543), so for R >= 2 most of the last pass's outputs are never looked
 // at: with KEEP < PPT/2 only the kept ones are accumulated (2*KEEP instead of PPT registers) and the
 // compiler prunes the last butterfly to the outputs that are used.  KEEP = PPT/2: everything.
-// DENSE (needs KEEP <= 2, <= 256 threads): 3 CTAs/SM at 80 registers.  What makes room is the pruned
+// DENSE (needs KEEP <= 2, <= 256 threads): 768 threads per SM (3 CTAs of 256, 6 of 128) at 80 registers.  What makes room is the pruned
 // accumulator and NOT carrying the overlapping half of a segment in registers (16 of them): it is
 // fetched again (an L1/L2 hit: the same CTA read it one segment ago).
 template <int LOG2N, int PPT, int KIND, int KEEP = PPT / 2, bool DENSE = false>
-__global__ void __launch_bounds__((WelchShape<LOG2N, PPT>::NTHREADS), (DENSE ? 3 : WelchShape<LOG2N, PPT>::MINB))
+__global__ void __launch_bounds__((WelchShape<LOG2N, PPT>::NTHREADS), (DENSE ? 768 / WelchShape<LOG2N, PPT>::NTHREADS : WelchShape<LOG2N, PPT>::MINB))
 welch_kernel(const WelchParams p) {
     using S = WelchShape<LOG2N, PPT>;
     constexpr int N = S::N;
@@ -404,14 +404,18 @@ welch_kernel(const WelchParams p) {
             if (p.wf_n > 0) {
                 const int r = frame & 15;
                 for (int j = 0; j < p.wf_n; ++j) {
-                    const int b = p.wf_bin[j];
+                    const int b = __ldg(p.wf_bin + j);
                     if ((b & 15) != r) continue;               // uniform: another residue's bin
                     const int k = b >> 4;
                     if ((k & (NT - 1)) != tid) continue;
-                    const float2 c = cmul(nm, p.wf_val[j]);
+                    const float2 c = cmul(nm, __ldg(p.wf_val + j));
+                    const int mk = k / NT;
 #pragma unroll
-                    for (int m = 0; m < PPT; ++m)
-                        if (m == k / NT) v[m] = cadd(v[m], c);
+                    for (int m = 0; m < PPT; ++m) {       // blend, not v[mk]: the array stays in registers
+                        const float f = (m == mk) ? 1.f : 0.f;
+                        v[m].x = fmaf(f, c.x, v[m].x);
+                        v[m].y = fmaf(f, c.y, v[m].y);
+                    }
                 }
             } else {
                 const float2 *wf = p.wf16 + (size_t)(frame & 15) * N + tid;
