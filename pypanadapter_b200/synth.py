@@ -35,7 +35,7 @@ class Workload:
 
     @property
     def bytes_per_sample(self) -> int:
-        return 2 if self.dtype == "u8" else 8
+        return {"u8": 2, "cs16": 4}.get(self.dtype, 8)
 
     @property
     def row_width(self) -> int:
@@ -74,7 +74,15 @@ CFG4 = Workload(
     tones=tuple((-9.5e6 + i * 19e6 / 63 + 7000.0, 0.1) for i in range(64)),
     description="64 virtual receivers over one 20 MS/s stream, 8192-pt FFT")
 
-WORKLOADS = {w.name: w for w in (CFG1, CFG2, CFG3, CFG4)}
+# cfg2's geometry fed with SoapySDR CS16 (interleaved int16 IQ, 4 B/sample): the wire format
+# the reference lets SoapySDR widen to CF32 on the host (S:602) crosses PCIe as it left the device
+CFG2_CS16 = Workload(
+    name="cfg2cs16", fs=3.2e6, fft_size=4096, fft_ratio=16, fft_avg=int(3.2e6 / 4096 / 10),
+    window="hamming", dtype="cs16", flip=False, ema_alpha=0.3,
+    tones=((2300.0, 0.5), (-4100.0, 0.05)), full_scale=0.8,
+    description="cfg2's geometry with SoapySDR CS16 int16 IQ samples (4 B/sample), EMA alpha 0.3")
+
+WORKLOADS = {w.name: w for w in (CFG1, CFG2, CFG3, CFG4, CFG2_CS16)}
 
 
 def cfg4_centres() -> np.ndarray:
@@ -116,11 +124,11 @@ def make_frame(w: Workload, frame_index: int = 0, n: int | None = None
                ) -> np.ndarray:
     """One frame in the workload's wire dtype (complex64 or interleaved u8)."""
     x = make_frame_complex(w, frame_index, n)
-    if w.dtype == "u8":
+    if w.dtype in ("u8", "cs16"):
         peak = sum(a for _f, a in w.tones) + 4 * w.sigma
         if peak > w.full_scale:
             x = x * (w.full_scale / peak)
-        return quantise_u8(x)
+        return quantise_u8(x) if w.dtype == "u8" else quantise_cs16(x)
     return x.astype(np.complex64)
 
 
