@@ -757,11 +757,11 @@ int choose_group(const zfb_engine *e, bool fast) {
     if (e->group_user > 0) return e->group_user;
     // enough frames per launch that the late, small stages still fill the GPU
     // (the chain is fp32-bound, not bandwidth-bound: L2 residency of the
-    // intermediates is worth less than full waves); bounded to 256 MB of workspace
+    // intermediates is worth less than full waves); bounded to 512 MB of workspace
     long long need[2];
     mid_lengths(e, fast, need);
     size_t per_frame = (size_t)(need[0] + need[1]) * 8;
-    size_t budget = 256ull << 20;
+    size_t budget = 512ull << 20;       // (256 MB cut cfg1's 512 frames into 352 + 160: 155 -> 161 Gs/s with one group, r02s)
     if (e->log2N > kMaxLog2Small) {
         per_frame += (size_t)e->nseg * ((size_t)8 << e->log2N);       // four-step scratch
         budget = (e->log2N >= kMinLog2R16 && e->log2N <= kMaxLog2R16) ? (1100ull << 20) : (512ull << 20);
@@ -1413,13 +1413,13 @@ int run_group(zfb_engine *e, const void *d_in, int gf, float *d_rows) {
         const int pr = prof_begin(e, 16);
         const dim3 gr((unsigned)(S / 256), (unsigned)e->nseg, (unsigned)gf);
         if (kind == KIND_C64_RAW) {
-            ZFB_LAUNCH(big_dc_kernel<KIND_C64_RAW>, dim3((unsigned)gf), dim3(256), 0, st, r);
+            ZFB_LAUNCH(big_dc_kernel<KIND_C64_RAW>, dim3((unsigned)gf), dim3(1024), 0, st, r);
             ZFB_LAUNCH(big_r16_kernel<KIND_C64_RAW>, gr, dim3(256), 0, st, r);
         } else if (kind == KIND_U8_RAW) {
-            ZFB_LAUNCH(big_dc_kernel<KIND_U8_RAW>, dim3((unsigned)gf), dim3(256), 0, st, r);
+            ZFB_LAUNCH(big_dc_kernel<KIND_U8_RAW>, dim3((unsigned)gf), dim3(1024), 0, st, r);
             ZFB_LAUNCH(big_r16_kernel<KIND_U8_RAW>, gr, dim3(256), 0, st, r);
         } else {
-            ZFB_LAUNCH(big_dc_kernel<KIND_C64_MID>, dim3((unsigned)gf), dim3(256), 0, st, r);
+            ZFB_LAUNCH(big_dc_kernel<KIND_C64_MID>, dim3((unsigned)gf), dim3(1024), 0, st, r);
             ZFB_LAUNCH(big_r16_kernel<KIND_C64_MID>, gr, dim3(256), 0, st, r);
         }
         const int nsegs_total = gf * e->nseg;
@@ -1956,6 +1956,10 @@ int zfb_configure(zfb_engine *e, const zfb_config *cfg) {
                     ++nnz;
                 }
             if (nnz >= 1 && nnz <= WF_SPARSE_MAX) e->wf_sparse_n = nnz;
+            for (int a = 0; a < e->wf_sparse_n; ++a)       // one listed bin per residue, or the dense table
+                for (int b2 = a + 1; b2 < e->wf_sparse_n; ++b2)
+                    if ((e->wf_sparse_bin[a] & 15) == (e->wf_sparse_bin[b2] & 15)) nnz = WF_SPARSE_MAX + 1;
+            if (nnz > WF_SPARSE_MAX) e->wf_sparse_n = 0;
             {   // [WF_SPARSE_MAX] bins, then [WF_SPARSE_MAX] values
                 unsigned char blob[WF_SPARSE_MAX * (sizeof(int) + sizeof(float2))] = {0};
                 memcpy(blob, e->wf_sparse_bin, sizeof e->wf_sparse_bin);

@@ -340,6 +340,15 @@ welch_kernel(const WelchParams p) {
     // p.reuse (hop == N/2, nperseg == N; every BASELINE configuration): the second half of a segment
     // is the first half of the next in the same thread's registers, and no element needs a bounds
     // test -- a uniform branch picks that load sequence (H shifts + H unconditional loads)
+    // sparse post-FFT mean removal (prepared blocks): the listed bins have distinct residues (host
+    // guarantee), so a CTA holds at most one of them and one thread owns it for all segments
+    int sparse_m = -1;                 // sparse_m + PPT * (index in the list), or -1
+    if (p.prepared && p.seg_mean != nullptr && p.wf_n > 0) {
+        for (int j = 0; j < p.wf_n; ++j) {
+            const int b = __ldg(p.wf_bin + j);
+            if ((b & 15) == (frame & 15) && ((b >> 4) & (NT - 1)) == tid) sparse_m = (b >> 4) / NT + PPT * j;
+        }
+    }
     const bool fastload = p.reuse && !p.prepared;
     constexpr bool CARRY = !DENSE;
     if (CARRY && fastload && s_begin < s_end) {           // first half of the first segment, parked in the upper half
@@ -399,25 +408,21 @@ welch_kernel(const WelchParams p) {
         }
         fft_block<LOG2N, PPT>(v, tid, p.twiddle, sm);
         if (p.prepared && p.seg_mean != nullptr && active) {
-            const float2 mean = __ldg(p.seg_mean + (size_t)(frame >> 4) * p.nseg + s);
-            const float2 nm = make_float2(-mean.x, -mean.y);
             if (p.wf_n > 0) {
-                const int r = frame & 15;
-                for (int j = 0; j < p.wf_n; ++j) {
-                    const int b = __ldg(p.wf_bin + j);
-                    if ((b & 15) != r) continue;               // uniform: another residue's bin
-                    const int k = b >> 4;
-                    if ((k & (NT - 1)) != tid) continue;
-                    const float2 c = cmul(nm, __ldg(p.wf_val + j));
-                    const int mk = k / NT;
+                if (sparse_m >= 0) {                       // the one thread of the CTA that owns a listed bin
+                    const float2 mean = __ldg(p.seg_mean + (size_t)(frame >> 4) * p.nseg + s);
+                    const float2 c = cmul(make_float2(-mean.x, -mean.y), __ldg(p.wf_val + sparse_m / PPT));
+                    const int own = sparse_m % PPT;
 #pragma unroll
-                    for (int m = 0; m < PPT; ++m) {       // blend, not v[mk]: the array stays in registers
-                        const float f = (m == mk) ? 1.f : 0.f;
+                    for (int m = 0; m < PPT; ++m) {       // blend, not v[own]: the array stays in registers
+                        const float f = (m == own) ? 1.f : 0.f;
                         v[m].x = fmaf(f, c.x, v[m].x);
                         v[m].y = fmaf(f, c.y, v[m].y);
                     }
                 }
             } else {
+                const float2 mean = __ldg(p.seg_mean + (size_t)(frame >> 4) * p.nseg + s);
+                const float2 nm = make_float2(-mean.x, -mean.y);
                 const float2 *wf = p.wf16 + (size_t)(frame & 15) * N + tid;
 #pragma unroll
                 for (int m = 0; m < PPT; ++m) v[m] = cadd(v[m], cmul(nm, __ldg(wf + m * NT)));
