@@ -85,7 +85,7 @@ struct zfb_engine {
     bool precise_active = false;
     int px_group = 1;
     long long px_stride = 0;
-    DevBuf px_a, px_b, px_work, px_pow, px_win;
+    DevBuf px_a, px_b, px_work, px_pow, px_win, px_tw;
     DevBuf taper_buf;                            // window design / preview scratch (zfb_taper.cuh)
     DevBuf strip_out;                            // [group][2][K] edge samples of the strips, patched in afterwards
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
@@ -1252,6 +1252,7 @@ int run_group_precise(zfb_engine *e, const void *d_in, int gf, float *d_rows) {
         wp.nseg = e->nseg;
         wp.log2N = e->log2N;
         wp.window = (const double *)e->px_win.p;
+        wp.twiddle = (const double2 *)e->px_tw.p;
         wp.work = (double2 *)e->px_work.p;
         wp.pow = (double *)e->px_pow.p;
         const int prw = prof_begin(e, 16);
@@ -1276,7 +1277,9 @@ int run_group_precise(zfb_engine *e, const void *d_in, int gf, float *d_rows) {
         rp.ring_pos = (long long)(e->ring_written % e->ring_rows);
         rp.ring_rows = e->ring_rows;
         const int prf = prof_begin(e, 18);
-        ZFB_LAUNCH(px_rows_kernel, dim3((unsigned)((e->W + 255) / 256)), dim3(256), 0, st, rp);
+        // EMA: the recurrence runs along the frames (one row of blocks); else frames in parallel
+        const unsigned rows_y = rp.alpha >= 0.0 ? 1u : (unsigned)(nf < 64 ? nf : 64);
+        ZFB_LAUNCH(px_rows_kernel, dim3((unsigned)((e->W + 255) / 256), rows_y), dim3(256), 0, st, rp);
         prof_end(e, prf);
         e->counters[2] += 2;
         if (rp.alpha >= 0.0) e->ema_have = true;
@@ -1836,7 +1839,7 @@ void zfb_destroy(zfb_engine *e) {
     release(e->cvt);
     release(e->strip_out);
     release(e->taper_buf);
-    for (DevBuf *b : {&e->px_a, &e->px_b, &e->px_work, &e->px_pow, &e->px_win}) release(*b);
+    for (DevBuf *b : {&e->px_a, &e->px_b, &e->px_work, &e->px_pow, &e->px_win, &e->px_tw}) release(*b);
     if (e->sr_copied) cudaEventDestroy(e->sr_copied);
     for (int i = 0; i < 2; ++i) if (e->sr_free[i]) cudaEventDestroy(e->sr_free[i]);
     if (e->h_rows) cudaFreeHost(e->h_rows);
@@ -2089,8 +2092,11 @@ int zfb_configure(zfb_engine *e, const zfb_config *cfg) {
     if (e->precise_active) {
         const size_t stride = (size_t)stride4((long long)cfg->frame_len + 2 * PADLEN + 8);
         size_t per_frame = 2 * stride * sizeof(double2) + (size_t)g.nseg * (size_t)N * (2 * sizeof(double2) + sizeof(double));
-        long long pg = (long long)((256ull << 20) / per_frame);
-        e->px_group = (int)(pg < 1 ? 1 : (pg > 64 ? 64 : pg));
+        // frames per pass: these rows are small jobs, but a batch of them (BASELINE configs[4] sweeps)
+        // should still fill the GPU: up to 1024 frames / 2 GB of fp64 workspace per pass
+        long long pg = (long long)((2048ull << 20) / per_frame);
+        e->px_group = (int)(pg < 1 ? 1 : (pg > 1024 ? 1024 : pg));
+        if (e->px_group > e->group) e->px_group = e->group > 0 ? e->group : 1;
         e->px_stride = (long long)stride;
         if (g.nstages > 0) {
             rc = ensure(e, e->px_a, (size_t)e->px_group * stride * sizeof(double2));
@@ -2106,6 +2112,17 @@ int zfb_configure(zfb_engine *e, const zfb_config *cfg) {
         if (rc) return rc;
         rc = ensure(e, e->px_win, (size_t)g.nperseg * sizeof(double));
         if (rc) return rc;
+        {   // twiddles of the radix-2 passes, fp64 on the host
+            std::vector<double2> tw((size_t)(N / 2 > 0 ? N / 2 : 1));
+            for (int m = 0; m < N / 2; ++m) {
+                const double a = -kPi * (double)m / (double)(N / 2);
+                tw[(size_t)m] = make_double2(cos(a), sin(a));
+            }
+            rc = ensure(e, e->px_tw, tw.size() * sizeof(double2));
+            if (rc) return rc;
+            CK(e, cudaMemcpyAsync(e->px_tw.p, tw.data(), tw.size() * sizeof(double2), cudaMemcpyHostToDevice, e->stream));
+            CK(e, cudaStreamSynchronize(e->stream));
+        }
         CK(e, cudaMemcpyAsync(e->px_win.p, cfg->window, (size_t)g.nperseg * sizeof(double), cudaMemcpyHostToDevice, e->stream));
         CK(e, cudaStreamSynchronize(e->stream));       // the caller's window table may go away
     }

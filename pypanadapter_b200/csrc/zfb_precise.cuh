@@ -25,7 +25,7 @@
 
 namespace zfb {
 
-constexpr int PX_STREAM = 2048;
+constexpr int PX_STREAM = 1024;       // (2048 left a batch of 64 cfg5 frames with 17 CTAs per launch)
 constexpr int PX_WARM = 576;
 
 struct PreciseConst {
@@ -167,6 +167,7 @@ struct PxWelchParams {
     int           kind, flip, len;
     int           nperseg, hop, nseg, log2N;
     const double *window;     // nperseg taps
+    const double2*twiddle;    // [N/2] exp(-i pi m / (N/2)) (host, fp64): pass s uses entry k * (N/2 >> s)
     double2      *work;       // [frames][nseg][2][N] ping-pong
     double       *pow;        // [frames][nseg][N] |X|^2, natural order
 };
@@ -225,8 +226,8 @@ __global__ void __launch_bounds__(PX_WELCH_NT) px_welch_kernel(const PxWelchPara
         for (int j = tid; j < N / 2; j += PX_WELCH_NT) {
             const int k = j & (Ns - 1);
             const double2 u = A[j], v = A[j + N / 2];
-            double sn, cs;
-            sincospi(-(double)k / (double)Ns, &sn, &cs);       // exp(-2 pi i k / (2 Ns))
+            const double2 w = p.twiddle[(size_t)k << (p.log2N - 1 - s)];   // exp(-2 pi i k / (2 Ns))
+            const double cs = w.x, sn = w.y;
             const double tr = v.x * cs - v.y * sn, ti = v.x * sn + v.y * cs;
             const int j0 = ((j >> s) << (s + 1)) + k;
             B[j0] = make_double2(u.x + tr, u.y + ti);
@@ -255,7 +256,8 @@ struct PxRowsParams {
     int    ring_rows;
 };
 
-// one thread per column, frames in order (the EMA recurrence runs along them)
+// one thread per column, frames in order (the EMA recurrence runs along them); without the EMA
+// the frames are independent and gridDim.y spreads them (frame f = blockIdx.y, blockIdx.y + gridDim.y, ...)
 __global__ void __launch_bounds__(256) px_rows_kernel(const PxRowsParams p) {
     const int col = blockIdx.x * blockDim.x + threadIdx.x;
     if (col >= p.W) return;
@@ -274,7 +276,7 @@ __global__ void __launch_bounds__(256) px_rows_kernel(const PxRowsParams p) {
     }
     bool have = p.ema_have != 0;
     double a = (have && p.alpha >= 0.0) ? (double)p.ema_state[col] : 0.0;
-    for (int f = 0; f < p.frames; ++f) {
+    for (int f = (int)blockIdx.y; f < p.frames; f += (int)gridDim.y) {
         double pw = 0.0;
         for (int s = 0; s < p.nseg; ++s) pw += p.pow[((size_t)f * p.nseg + s) * (size_t)N + k];
         pw *= p.scale * factor;
@@ -288,7 +290,7 @@ __global__ void __launch_bounds__(256) px_rows_kernel(const PxRowsParams p) {
         if (p.ring && f >= p.frames - p.ring_rows)
             p.ring[(size_t)((p.ring_pos + f) % p.ring_rows) * p.W + col] = out;
     }
-    if (p.alpha >= 0.0 && p.frames > 0) p.ema_state[col] = (float)a;
+    if (p.alpha >= 0.0 && p.frames > 0 && blockIdx.y == 0) p.ema_state[col] = (float)a;
 }
 
 // decimated chunk of frame 0 as complex64 (zfb_debug_read_decimated)
