@@ -32,6 +32,7 @@ constexpr int JTERMS32 = 10;                 // same for the 32-sample runs of t
 constexpr int KIND_C64_RAW = 0;  // complex64 chunk: flip + LO mix on load
 constexpr int KIND_U8_RAW  = 1;  // uint8 IQ chunk: convert + flip + LO mix
 constexpr int KIND_C64_MID = 2;  // complex64 intermediate (already mixed)
+constexpr int KIND_CS16_RAW = 3; // int16 IQ chunk (SoapySDR CS16): fir_run_kernel only (128 threads, no channel batch)
 
 struct DecimConst {
     float na1[NSEC], na2[NSEC];          // -a1, -a2 of each section

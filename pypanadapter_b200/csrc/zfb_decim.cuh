@@ -294,6 +294,15 @@ __device__ __forceinline__ float2 u8pair_to_raw(unsigned int word, int hi) {
     return pk_add(make_float2(__uint_as_float(fi), __uint_as_float(fq)), make_float2(-8388608.0f, -8388608.0f));
 }
 
+// int16 IQ pair (I in the low half) as exact integers -32768..32767: the sign bit is flipped, the
+// 16 bits are dropped into the mantissa of 2^23 (PRMT) and 2^23 + 32768 is taken off again -- no I2F
+__device__ __forceinline__ float2 cs16pair_to_raw(unsigned int word) {
+    const unsigned int w = word ^ 0x80008000u;
+    const unsigned int fi = __byte_perm(w, 0x4B000000u, 0x7410);
+    const unsigned int fq = __byte_perm(w, 0x4B000000u, 0x7432);
+    return pk_add(make_float2(__uint_as_float(fi), __uint_as_float(fq)), make_float2(-8421376.0f, -8421376.0f));
+}
+
 template <int KIND, int NT, bool CHAN = false, int B = BLK>
 __device__ __forceinline__ void load_region(float2 *buf, const StageParams &p,
                                             const char *frame_in, int rs, int tid, int posoff, int ch = 0) {

@@ -99,6 +99,7 @@ struct zfb_engine {
     int tiles[kMaxStages][2] = {{0}}, T[kMaxStages][2] = {{0}};   // [stage][0: NT=256, 1: NT=128]
     int decim_threads = 0;             // 0 = automatic per launch
     int welch_splits = 0;              // 0 = automatic
+    int cs16_fused = 1;                // zfb_set_option("cs16_fused"): 0 = always widen int16 IQ by a pass of its own
     int wf_sparse_n = 0;               // non-zero bins of FFT(window) when there are few (cosine-sum windows), else 0
     int wf_sparse_bin[WF_SPARSE_MAX] = {0};
     float2 wf_sparse_val[WF_SPARSE_MAX] = {};
@@ -596,6 +597,7 @@ ChainFn0 chain_lookup_fn(int kind) {
 }
 
 template <int KIND> int fir_run_setup_kind(zfb_engine *e);
+int fir_run_setup_cs16(zfb_engine *e);
 constexpr int kIirNS = 3, kIirNO = 3;      // x pieces / output rows in flight per lane (zfb_iirstream.cuh)
 
 cudaError_t create_high_priority_stream(cudaStream_t *st) {
@@ -668,6 +670,7 @@ int setup_device_once(zfb_engine *e) {
     int rc = fir_run_setup_kind<KIND_C64_RAW>(e);
     if (rc == ZFB_OK) rc = fir_run_setup_kind<KIND_U8_RAW>(e);
     if (rc == ZFB_OK) rc = fir_run_setup_kind<KIND_C64_MID>(e);
+    if (rc == ZFB_OK) rc = fir_run_setup_cs16(e);
     return rc;
 }
 
@@ -686,6 +689,19 @@ __global__ void __launch_bounds__(256) cs16_to_c64_kernel(const unsigned int *in
         const float fi = (float)(short)(w & 0xffffu), fq = (float)(short)(w >> 16);
         out[i] = make_float2(fi * (1.0f / 32768.0f), fq * (1.0f / 32768.0f));
     }
+}
+
+// the same for the first and last `ends` samples of every frame only (the exact edge strips of mode
+// fast read nothing else when the FIR interior converts its own input)
+__global__ void __launch_bounds__(256) cs16_ends_to_c64_kernel(const unsigned int *in, float2 *out, int frame_len, int ends,
+                                                               long long total) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const long long f = i / (2 * ends);
+    const int j = (int)(i % (2 * ends));
+    const long long at = f * frame_len + (j < ends ? j : frame_len - 2 * ends + j);
+    const unsigned int w = in[at];
+    out[at] = make_float2((float)(short)(w & 0xffffu) * (1.0f / 32768.0f), (float)(short)(w >> 16) * (1.0f / 32768.0f));
 }
 
 // FAST engages when the plan fits and the chunk is long enough for the strips
@@ -840,7 +856,26 @@ void launch_fir_run_kind(int variant, const FirRunParams &rp, int L_out, int gf,
 #undef ZFB_X
 }
 
+// int16 IQ read by the kernel itself: 128-thread CTAs, no channel batch (fir_cs16_fused() decides)
+void launch_fir_run_cs16(int variant, const FirRunParams &rp, int L_out, int gf, cudaStream_t st) {
+#define ZFB_X(ID, K, NS, A, B, C, D)                                                              \
+    if (variant == ID) {                                                                          \
+        using SH = FirRunShape<NS, A, B, C, D, 128>;                                              \
+        const int per_tile = SH::SPAN >> NS;                                                      \
+        const unsigned tiles = (unsigned)((L_out + per_tile - 1) / per_tile);                     \
+        ZFB_LAUNCH((fir_run_kernel<KIND_CS16_RAW, NS, A, B, C, D, false, 128>), dim3(tiles, (unsigned)gf), dim3(128), \
+                   SH::SMEM, st, rp);                                                             \
+        return;                                                                                   \
+    }
+    ZFB_RUN_COMBOS(ZFB_X, KIND_CS16_RAW)
+#undef ZFB_X
+}
+
 void launch_fir_run(int variant, int kind, const FirRunParams &rp, int L_out, int gf, cudaStream_t st, int nt) {
+    if (kind == KIND_CS16_RAW) {
+        launch_fir_run_cs16(variant, rp, L_out, gf, st);
+        return;
+    }
     if (nt == 128) {
         if (kind == KIND_U8_RAW) launch_fir_run_kind<KIND_U8_RAW, 128>(variant, rp, L_out, gf, st);
         else if (kind == KIND_C64_RAW) launch_fir_run_kind<KIND_C64_RAW, 128>(variant, rp, L_out, gf, st);
@@ -879,6 +914,15 @@ int fir_run_setup_kind(zfb_engine *e) {
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FirRunShape<NS, A, B, C, D, 128>::SMEM)); \
     }
     ZFB_RUN_COMBOS(ZFB_X, KIND)
+#undef ZFB_X
+    return ZFB_OK;
+}
+
+int fir_run_setup_cs16(zfb_engine *e) {
+#define ZFB_X(ID, K, NS, A, B, C, D)                                                              \
+    CK(e, cudaFuncSetAttribute((fir_run_kernel<KIND_CS16_RAW, NS, A, B, C, D, false, 128>),        \
+                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FirRunShape<NS, A, B, C, D, 128>::SMEM));
+    ZFB_RUN_COMBOS(ZFB_X, KIND_CS16_RAW)
 #undef ZFB_X
     return ZFB_OK;
 }
@@ -1028,7 +1072,9 @@ void launch_fused_strips(zfb_engine *e, const void *d_in, int gf, float2 *final_
 // ZFB_MODE_FAST: FIR chains + exact last stage over the whole frames, and the
 // exact cascade on the two end strips of every frame; leaves the decimated
 // chunks in mid[*out_buf].  Returns a CUDA status.
-cudaError_t run_decimation_fast(zfb_engine *e, const void *d_in, int gf, int *out_buf) {
+// d_in_cs16: the caller's int16 IQ when the first FIR chain reads it itself (fir_cs16_fused), else null;
+// d_in is then a complex64 buffer that holds only the chunk ends the strips read
+cudaError_t run_decimation_fast(zfb_engine *e, const void *d_in, int gf, int *out_buf, const void *d_in_cs16 = nullptr) {
     const zfb_config &c = e->cfg;
     cudaStream_t st = e->stream;
     const int k = e->nstages;
@@ -1054,9 +1100,9 @@ cudaError_t run_decimation_fast(zfb_engine *e, const void *d_in, int gf, int *ou
             if ((err = cudaEventRecord(e->ev_join, aux)) != cudaSuccess) return err;
         }
     }
-    const void *src = d_in;
+    const void *src = d_in_cs16 ? d_in_cs16 : d_in;
     long long src_stride = c.frame_len;
-    int kind = raw_kind(c);
+    int kind = d_in_cs16 ? KIND_CS16_RAW : raw_kind(c);
     int b = 0;
     for (int j = 0; j < e->nchains; ++j) {
         FirChainParams p = e->chain[j];
@@ -1292,11 +1338,33 @@ int run_group_precise(zfb_engine *e, const void *d_in, int gf, float *d_rows) {
     return ZFB_OK;
 }
 
+// int16 IQ converted by the first FIR chain's own loads (no widening pass over the chunk)?
+bool fir_cs16_fused(const zfb_engine *e) {
+    return e->cs16_fused && e->fast_active && !e->precise_active && e->nchains >= 1 && e->chain_run[0] != 0 &&
+           e->fir_threads == 128 && e->cur_nch == 0;
+}
+
 // one group of frames, all resident on the device, through the whole chain
 int run_group(zfb_engine *e, const void *d_in, int gf, float *d_rows) {
     const zfb_config &c = e->cfg;
     cudaStream_t st = e->stream;
-    if (c.dtype == ZFB_DTYPE_CS16) {
+    const void *d_in_cs16 = nullptr;
+    if (c.dtype == ZFB_DTYPE_CS16 && fir_cs16_fused(e)) {
+        // the FIR interior converts on load (zfb_firchain.cuh, KIND_CS16_RAW); only the chunk ends the
+        // exact strips read are widened, at their own positions of the complex64 buffer
+        const long long n = (long long)gf * (long long)c.frame_len;
+        int rc = ensure(e, e->cvt, (size_t)n * sizeof(float2));
+        if (rc) return rc;
+        int ends = e->strip_len[0] + 512;
+        if (2 * ends > c.frame_len) ends = (c.frame_len + 1) / 2;
+        const long long total = (long long)gf * 2 * ends;
+        long long blocks = (total + 255) / 256;
+        ZFB_LAUNCH(cs16_ends_to_c64_kernel, dim3((unsigned)blocks), dim3(256), 0, st, (const unsigned int *)d_in,
+                   (float2 *)e->cvt.p, c.frame_len, ends, total);
+        e->counters[2] += 1;
+        d_in_cs16 = d_in;
+        d_in = e->cvt.p;
+    } else if (c.dtype == ZFB_DTYPE_CS16) {
         // channel-batched launches read cur_chan_frames input frames for gf = frames * channels rows
         const long long in_frames = e->cur_nch > 0 ? e->cur_chan_frames : gf;
         const long long n = in_frames * (long long)c.frame_len;
@@ -1319,7 +1387,7 @@ int run_group(zfb_engine *e, const void *d_in, int gf, float *d_rows) {
 
     if (e->fast_active) {
         int ob = 0;
-        CK(e, run_decimation_fast(e, d_in, gf, &ob));
+        CK(e, run_decimation_fast(e, d_in, gf, &ob, d_in_cs16));
         e->final_buf = ob;
         src = e->mid[ob].p;
         src_stride = final_stride(e);
@@ -1624,13 +1692,14 @@ int plan_fast(zfb_engine *e) {
                 set_late_mix(e, rp, r, amp, ns);
             }
             memcpy(rp.h0, p.h[0], sizeof rp.h0);
-            {   // first stage on raw uint8 values (zfb_firchain.cuh: FirRunParams::h0s)
+            {   // first stage on raw uint8 / int16 values (zfb_firchain.cuh: FirRunParams::h0s)
+                const bool s16 = c.dtype == ZFB_DTYPE_CS16;
                 double sum = 0.0;
                 for (int j = 0; j <= FIR_MAX_HALF; ++j) {
-                    rp.h0s[j] = (float)((double)p.h[0][j] / 127.5);
+                    rp.h0s[j] = (float)((double)p.h[0][j] / (s16 ? 32768.0 : 127.5));
                     sum += (j == 0 ? 1.0 : 2.0) * (double)rp.h0s[j];
                 }
-                rp.bias0 = (float)(127.5 * sum);
+                rp.bias0 = s16 ? 0.f : (float)(127.5 * sum);      // uint8 is offset binary, int16 is not
             }
             memcpy(rp.h1, p.h[1], sizeof rp.h1);
             memcpy(rp.h2, p.h[2], sizeof rp.h2);
@@ -2206,6 +2275,10 @@ int zfb_set_option(zfb_engine *e, const char *name, long long value) {
     if (strcmp(name, "welch_splits") == 0) {
         if (value < 0 || value > 16) return fail(e, ZFB_EINVAL, "welch_splits must be in [0, 16]");
         e->welch_splits = (int)value;
+        return ZFB_OK;
+    }
+    if (strcmp(name, "cs16_fused") == 0) {
+        e->cs16_fused = value ? 1 : 0;
         return ZFB_OK;
     }
     if (strcmp(name, "welch_prune") == 0) {

@@ -475,7 +475,7 @@ struct FirRunShape {
 template <int KIND, int NS, int M0, int M1, int M2, int MC, bool CH = false, int NT = FIR_NT>
 __global__ void __launch_bounds__(NT, (ZFB_FIR_MINB * FIR_NT / NT)) fir_run_kernel(const FirRunParams p) {
     using SH = FirRunShape<NS, M0, M1, M2, MC, NT>;
-    constexpr int VEC = (KIND == KIND_U8_RAW) ? 8 : 2;
+    constexpr int VEC = (KIND == KIND_U8_RAW) ? 8 : (KIND == KIND_CS16_RAW) ? 4 : 2;    // samples per 16 bytes
     ZFB_DYN_SMEM(smem_raw);
     float2 *sm0 = reinterpret_cast<float2 *>(smem_raw);
     float2 *sm1 = sm0 + SH::S0;
@@ -492,9 +492,12 @@ __global__ void __launch_bounds__(NT, (ZFB_FIR_MINB * FIR_NT / NT)) fir_run_kern
     // ---------------- level 0: this thread's 32 samples ----------------
     float2 x0[RUN0];
     const bool late_mix = KIND != KIND_C64_MID && (CH ? p.chan[ch].late : p.late);
-    const bool fold = KIND == KIND_U8_RAW && late_mix;       // raw byte values through the first stage
+    // integer wire formats with the late mix: the raw sample values go through the first stage
+    // (its taps carry 1/127.5 or 1/32768, `bias0` the uint8 offset)
+    const bool fold = (KIND == KIND_U8_RAW || KIND == KIND_CS16_RAW) && late_mix;
+    constexpr float kCs16 = 1.0f / 32768.0f;
     {
-        const size_t esz = (KIND == KIND_U8_RAW) ? 2 : 8;
+        const size_t esz = (KIND == KIND_U8_RAW) ? 2 : (KIND == KIND_CS16_RAW) ? 4 : 8;
         const char *frame_in = (const char *)p.in + (size_t)in_frame * (size_t)p.in_stride * esz;
         const bool fl = (KIND != KIND_C64_MID) && p.flip;
         // element e of the run <-> sample index fl ? L-1-(pos0+e) : pos0+e
@@ -522,6 +525,14 @@ __global__ void __launch_bounds__(NT, (ZFB_FIR_MINB * FIR_NT / NT)) fir_run_kern
                             x0[fl ? RUN0 - 1 - idx : idx] = u8pair_to_iq(wds[e >> 1], e & 1);
                         }
                     }
+                } else if (KIND == KIND_CS16_RAW) {
+                    const unsigned int wds[4] = {raw[v].x, raw[v].y, raw[v].z, raw[v].w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int idx = v * 4 + e;
+                        const float2 r = cs16pair_to_raw(wds[e]);
+                        x0[fl ? RUN0 - 1 - idx : idx] = fold ? r : pk_mul(kCs16, r);
+                    }
                 } else {
                     const int i0 = v * 2, i1 = v * 2 + 1;
                     x0[fl ? RUN0 - 1 - i0 : i0] = make_float2(__uint_as_float(raw[v].x), __uint_as_float(raw[v].y));
@@ -532,13 +543,17 @@ __global__ void __launch_bounds__(NT, (ZFB_FIR_MINB * FIR_NT / NT)) fir_run_kern
 #pragma unroll
             for (int e = 0; e < RUN0; ++e) {
                 const int pe = pos0 + e;
-                x0[e] = fold ? make_float2(127.5f, 127.5f) : make_float2(0.f, 0.f);   // zero signal
+                x0[e] = (fold && KIND == KIND_U8_RAW) ? make_float2(127.5f, 127.5f) : make_float2(0.f, 0.f);   // zero signal
                 if (pe >= 0 && pe < L) {
                     const long long ie = fl ? (long long)L - 1 - pe : (long long)pe;
                     if (KIND == KIND_U8_RAW) {
                         const unsigned char *src = (const unsigned char *)frame_in;
                         x0[e] = fold ? make_float2((float)src[2 * ie], (float)src[2 * ie + 1])
                                      : make_float2(u8_to_f(src[2 * ie]), u8_to_f(src[2 * ie + 1]));
+                    } else if (KIND == KIND_CS16_RAW) {
+                        const short *src = (const short *)frame_in;
+                        const float2 r = make_float2((float)src[2 * ie], (float)src[2 * ie + 1]);
+                        x0[e] = fold ? r : pk_mul(kCs16, r);
                     } else {
                         x0[e] = __ldg((const float2 *)frame_in + ie);
                     }
