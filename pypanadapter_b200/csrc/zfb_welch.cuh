@@ -294,7 +294,10 @@ struct WelchShape {
     static constexpr int N = 1 << LOG2N;
     static constexpr int NT = N / PPT;                       // working threads
     static constexpr int NTHREADS = NT < 32 ? 32 : NT;       // launched threads
-    static constexpr int MINB = NTHREADS <= 256 ? 2 : 1;     // >= 2 CTAs/SM: the passes are barrier-bound
+#ifndef ZFB_WELCH_MINB_BIG
+#define ZFB_WELCH_MINB_BIG 1
+#endif
+    static constexpr int MINB = NTHREADS <= 256 ? 2 : ZFB_WELCH_MINB_BIG;     // >= 2 CTAs/SM: the passes are barrier-bound
     static constexpr size_t SMEM = (size_t)(N + (N >> 4) + 1) * sizeof(float2);
 };
 

@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--sizes", default="1024,4096,16384,65536,262144")
     ap.add_argument("--mode", default="fast")
     ap.add_argument("--set", action="append", dest="sets", metavar="OPTION=VALUE", help="zfb_set_option before the sweep")
+    ap.add_argument("--lib", default=None, help="an alternative sm_100a build of the same sources (compile-time A/B)")
     args = ap.parse_args()
 
     import torch
@@ -38,7 +39,11 @@ def main():
     from pypanadapter_b200.engine import ZoomPSD
 
     fs = 2.4e6
-    eng = ZoomPSD(0)
+    if args.lib:
+        from pypanadapter_b200 import _lib
+        eng = ZoomPSD(0, lib=_lib.load_library(args.lib))
+    else:
+        eng = ZoomPSD(0)
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     eng.set_stream(stream.cuda_stream)
