@@ -377,12 +377,22 @@ def run_b200(args, w):
 
     # cfg4 on several GPUs: every rank needs the SAME stream.  It crosses PCIe once (rank 0) and
     # reaches the other GPUs over NVLink (ncclBroadcast); only the rows come back per rank.
-    bcast_feed = centres is not None and world > 1 and args.cfg4_feed == "broadcast"
+    # "allgather" (default): every rank H2Ds 1/N of the stream over its own PCIe link and the parts
+    # are all-gathered over NVLink -- N links feed instead of one; "broadcast": rank 0 H2Ds all of it
+    feed = args.cfg4_feed if (centres is not None and world > 1) else "replicate"
+    if feed == "allgather" and F % world != 0:
+        feed = "broadcast"
+    bcast_feed = feed in ("broadcast", "allgather")       # the stream crosses PCIe once in all
+    gather_feed = feed == "allgather"
     d_feed = torch.empty_like(d_in) if bcast_feed else None
     d_rows_e2e = torch.empty((nch * F, W), dtype=torch.float32, device="cuda") if bcast_feed else None
+    Fs = F // world if gather_feed else F                  # frames this rank uploads
 
     def step_e2e():
-        if bcast_feed:
+        if gather_feed:
+            d_feed[rank * Fs:(rank + 1) * Fs].copy_(h_in[rank * Fs:(rank + 1) * Fs], non_blocking=True)
+            dist.all_gather_into_tensor(d_feed, d_feed[rank * Fs:(rank + 1) * Fs])     # in place, on `stream`
+        elif bcast_feed:
             if rank == 0:
                 d_feed.copy_(h_in, non_blocking=True)
             dist.broadcast(d_feed, src=0)            # on `stream` (the current stream)
@@ -445,22 +455,28 @@ def run_b200(args, w):
 
     # ---------------- copy-only ceiling of the end-to-end leg ----------------
     # the same pinned buffers over the same PCIe link, no kernels: what e2e could reach at best
-    copy_feeds = (rank == 0) if bcast_feed else True
+    copy_feeds = (rank == 0) if (bcast_feed and not gather_feed) else True
     d_copy = torch.empty_like(d_in)
     d_rows_c = d_rows2[0]
-    for _ in range(2):
-        if copy_feeds:
-            d_copy.copy_(h_in, non_blocking=True)
+
+    def copy_step():
+        if gather_feed:
+            d_copy[rank * Fs:(rank + 1) * Fs].copy_(h_in[rank * Fs:(rank + 1) * Fs], non_blocking=True)
+            dist.all_gather_into_tensor(d_copy, d_copy[rank * Fs:(rank + 1) * Fs])
+        else:
+            if copy_feeds:
+                d_copy.copy_(h_in, non_blocking=True)
+            if bcast_feed:
+                dist.broadcast(d_copy, src=0)
         h_rows.copy_(d_rows_c, non_blocking=True)
+
+    for _ in range(2):
+        copy_step()
     barrier()
     ev4, ev5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev4.record(stream)
     for _ in range(e2e_steps):
-        if copy_feeds:
-            d_copy.copy_(h_in, non_blocking=True)
-        if bcast_feed:
-            dist.broadcast(d_copy, src=0)
-        h_rows.copy_(d_rows_c, non_blocking=True)
+        copy_step()
     ev5.record(stream)
     barrier()
     ms_copy = ev4.elapsed_time(ev5)
@@ -618,7 +634,9 @@ def run_b200(args, w):
         cfg["group_frames"] = args.group or "auto"
         cfg["decim_threads"] = args.decim_threads or "auto"
         if centres is not None:
-            cfg["stream_feed"] = ("rank 0 H2D + NCCL broadcast over NVLink" if bcast_feed else "H2D on every rank")
+            cfg["stream_feed"] = {"allgather": "every rank H2Ds 1/N of the stream, NCCL all-gather over NVLink",
+                                  "broadcast": "rank 0 H2D + NCCL broadcast over NVLink",
+                                  "replicate": "H2D on every rank"}[feed]
             cfg["channels_per_gpu"] = nch
             cfg["value_counts"] = "channel-samples: every virtual receiver consumes the whole stream"
         cfg["decimator_mode"] = "fast" if eng.fast_active else "exact"
@@ -642,7 +660,8 @@ def run_b200(args, w):
                     "copy_only": {"value": copy_value, "unit": UNIT, "ms_per_step": ms_copy / e2e_steps,
                                   "h2d_gbs": h2d_step / (ms_copy / e2e_steps * 1e-3) / 1e9,
                                   "what": "the same pinned buffers over PCIe%s, no kernels"
-                                          % (" + the NCCL broadcast" if bcast_feed else "")},
+                                          % (" + the NCCL all-gather" if gather_feed else
+                                             " + the NCCL broadcast" if bcast_feed else "")},
                     "e2e_over_copy_only": e2e_value / copy_value},
             "gpu_launches": launches,
             "roofline": roofline,
@@ -682,7 +701,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--sustain-s", type=float, default=3.0,
                     help="seconds of back-to-back steps for the sustained leg (0 = skip)")
-    ap.add_argument("--cfg4-feed", default="broadcast", choices=["broadcast", "replicate"],
+    ap.add_argument("--cfg4-feed", default="allgather", choices=["allgather", "broadcast", "replicate"],
                     help="cfg4, N > 1: H2D on rank 0 + NCCL broadcast over NVLink, or H2D on every rank")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-numa-bind", action="store_true",
