@@ -105,6 +105,7 @@ struct zfb_engine {
     float2 wf_sparse_val[WF_SPARSE_MAX] = {};
     int welch_prune = 2;               // 0: all bins accumulated; 1: only keepable ones; 2: + 3 CTAs/SM where it fits
     int fir_generic = 0;               // 1: never use the register-blocked FIR kernel (tests)
+    int fir_smem_pad = 0;              // zfb_set_option("fir_smem_pad"): bytes (measurement)
     int fir_threads = 128;             // zfb_set_option("fir_threads"): 256 or 128 threads per CTA of fir_run_kernel
     int nperseg = 0, hop = 0, nseg = 0, W = 0, log2N = 0;
     int Wp = 0;                        // width of a pow row: W, or N for one-sided rows
@@ -849,6 +850,10 @@ void prof_end(zfb_engine *e, int idx, cudaStream_t on = nullptr) {
     X(5, KIND, 2, 3, 3, 0, -1)   \
     X(6, KIND, 3, 3, 3, 3, -1)
 
+// measurement knob (zfb_set_option("fir_smem_pad")): extra dynamic shared memory per CTA of the FIR run
+// kernel, i.e. fewer of them per SM -- leaves registers for other kernels' CTAs beside it
+static thread_local size_t g_fir_smem_pad = 0;
+
 template <int KIND, int NT>
 void launch_fir_run_kind(int variant, const FirRunParams &rp, int L_out, int gf, cudaStream_t st) {
 #define ZFB_X(ID, K, NS, A, B, C, D)                                                              \
@@ -858,9 +863,9 @@ void launch_fir_run_kind(int variant, const FirRunParams &rp, int L_out, int gf,
         const unsigned tiles = (unsigned)((L_out + per_tile - 1) / per_tile);                     \
         if (K != KIND_C64_MID && rp.chan) {                                                       \
             ZFB_LAUNCH((fir_run_kernel<K, NS, A, B, C, D, (K != KIND_C64_MID), NT>), dim3(tiles, (unsigned)gf), \
-                       dim3(NT), SH::SMEM, st, rp);                                               \
+                       dim3(NT), SH::SMEM + g_fir_smem_pad, st, rp);                              \
         } else {                                                                                  \
-            ZFB_LAUNCH((fir_run_kernel<K, NS, A, B, C, D, false, NT>), dim3(tiles, (unsigned)gf), dim3(NT), SH::SMEM, st, rp); \
+            ZFB_LAUNCH((fir_run_kernel<K, NS, A, B, C, D, false, NT>), dim3(tiles, (unsigned)gf), dim3(NT), SH::SMEM + g_fir_smem_pad, st, rp); \
         }                                                                                         \
         return;                                                                                   \
     }
@@ -918,7 +923,7 @@ int fir_run_setup_kind(zfb_engine *e) {
     CK(e, cudaFuncSetAttribute((fir_run_kernel<K, NS, A, B, C, D>), cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                (int)FirRunShape<NS, A, B, C, D>::SMEM));                          \
     CK(e, cudaFuncSetAttribute((fir_run_kernel<K, NS, A, B, C, D, false, 128>), cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                               (int)FirRunShape<NS, A, B, C, D, 128>::SMEM));                     \
+                               (int)FirRunShape<NS, A, B, C, D, 128>::SMEM + 64 * 1024));         \
     if (K != KIND_C64_MID) {                                                                      \
         CK(e, cudaFuncSetAttribute((fir_run_kernel<K, NS, A, B, C, D, (K != KIND_C64_MID)>),      \
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FirRunShape<NS, A, B, C, D>::SMEM)); \
@@ -1134,7 +1139,9 @@ cudaError_t run_decimation_fast(zfb_engine *e, const void *d_in, int gf, int *ou
                 rp.chan = (const ChannelLo *)e->chan_dev.p;
                 rp.chan_frames = e->cur_chan_frames;
             }
+            g_fir_smem_pad = (size_t)e->fir_smem_pad;
             launch_fir_run(e->chain_run[j], kind, rp, e->len[lvl], gf, st, e->fir_threads);
+            g_fir_smem_pad = 0;
         } else {
             const unsigned tiles = (unsigned)((e->len[lvl] + p.TO - 1) / p.TO);
             ZFB_LAUNCH(chain_lookup(kind), dim3(tiles, (unsigned)gf), dim3(FIR_NT), e->chain_smem[j], st, p);
@@ -2365,6 +2372,11 @@ int zfb_set_option(zfb_engine *e, const char *name, long long value) {
     }
     if (strcmp(name, "ring_append") == 0) {
         e->ring_append = value ? 1 : 0;
+        return ZFB_OK;
+    }
+    if (strcmp(name, "fir_smem_pad") == 0) {
+        if (value < 0 || value > 64 * 1024) return fail(e, ZFB_EINVAL, "fir_smem_pad must be in [0, 65536]");
+        e->fir_smem_pad = (int)value;
         return ZFB_OK;
     }
     if (strcmp(name, "fir_threads") == 0) {

@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--engines", default="1,2,4")
     ap.add_argument("--priority", type=int, default=0, help="1: alternate stream priorities")
+    ap.add_argument("--set", action="append", dest="sets", metavar="OPTION=VALUE", help="zfb_set_option on every engine")
     args = ap.parse_args()
 
     import torch
@@ -40,6 +41,9 @@ def main():
             lo, hi = torch.cuda.Stream.priority_range() if hasattr(torch.cuda.Stream, "priority_range") else (0, -1)
             st = torch.cuda.Stream(priority=(-1 if (args.priority and i % 2) else 0))
             e.set_stream(st.cuda_stream)
+            for it in args.sets or []:
+                name, _, val = it.partition("=")
+                e.set_option(name, int(val))
             e.configure(w.fs, w.fft_size, w.fft_ratio, w.frame_len, w.window, dtype=w.dtype, flip=w.flip,
                         f_demod=w.f_demod, crop=w.crop, ema_alpha=w.ema_alpha, mode="fast")
             engs.append(e)
@@ -68,7 +72,8 @@ def main():
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / args.steps
         print(json.dumps({"engines": ne, "frames_per_engine": per, "ms_per_step": ms,
-                          "gsamples_per_s": F * w.frame_len / ms / 1e6, "priority": args.priority}), flush=True)
+                          "gsamples_per_s": F * w.frame_len / ms / 1e6, "priority": args.priority,
+                          "options": args.sets or []}), flush=True)
         for e in engs:
             e.close()
 
