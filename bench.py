@@ -319,6 +319,11 @@ def run_b200(args, w):
         eng.set_option("strips_async", args.strips_async)
     if args.late_mix is not None:
         eng.set_option("late_mix", args.late_mix)
+    if args.slabs is not None:
+        eng.set_option("slabs", args.slabs)
+    for it in args.sets or []:
+        name, _, val = it.partition("=")
+        eng.set_option(name, int(val))
     eng.configure(w.fs, w.fft_size, w.fft_ratio, w.frame_len, w.window, dtype=w.dtype, flip=w.flip,
                   f_demod=w.f_demod, crop=w.crop, ema_alpha=w.ema_alpha, mode=args.mode)
     # a real (non-default) stream: the engine launches on it, NCCL enqueues on
@@ -507,10 +512,12 @@ def run_b200(args, w):
         sustained = {"ms": ev6.elapsed_time(ev7), "steps": n_sus, "clocks": sampler.summary(ts0, ts1)}
     sampler.stop()
 
-    # ---------------- per-kernel times with nothing overlapped (strips on the main stream) ----------
-    serial_prof = None
+    # ---------------- per-kernel times with nothing overlapped (strips on the main stream, one lane) ----------
+    lanes = eng.slab_lanes                   # lanes the timed batches ran through (2: slab pipelining)
+    serial_prof = serial_step = None
     if world == 1 and eng.fast_active:
         eng.set_option("strips_async", 0)
+        eng.set_option("slabs", 1)
         eng.configure(w.fs, w.fft_size, w.fft_ratio, w.frame_len, w.window, dtype=w.dtype, flip=w.flip,
                       f_demod=w.f_demod, crop=w.crop, ema_alpha=w.ema_alpha, mode=args.mode)
         for _ in range(2):
@@ -522,8 +529,11 @@ def run_b200(args, w):
             step_device()
         barrier()
         eng.set_profiling(False)
-        serial_prof = {k: v[0] / max(1, v[1]) for k, v in eng.profile().items()}
+        serial_raw = eng.profile()
+        serial_prof = {k: v[0] / max(1, v[1]) for k, v in serial_raw.items()}
+        serial_step = {k: v[0] / 5.0 for k, v in serial_raw.items()}      # ms per step, all launches of the class
         eng.set_option("strips_async", 1 if args.strips_async is None else args.strips_async)
+        eng.set_option("slabs", 2 if args.slabs is None else args.slabs)
 
     # ---------------- N > 1: the gathered rows ARE the single-GPU rows, bit for bit ----------------
     # frames are independent (LO phase, filter state and Welch mean restart per chunk: S:2092, 2098,
@@ -610,10 +620,20 @@ def run_b200(args, w):
                           for k, v in prof.items()},
             "kernel_ms_serial_per_launch": None if serial_prof is None else
                 {names.get(k, k): round(v, 5) for k, v in serial_prof.items()},
+            "lanes": lanes,
             "step_algorithmic_bytes": F * frame_bytes,
             "step_achieved_gbs": world * F * frame_bytes / (step_ms * 1e-3) / 1e9,
             "step_frac": F * frame_bytes / (step_ms * 1e-3) / 1e9 / peak,
         }
+        if serial_step and top in serial_step and serial_step[top] > 0:
+            # the same kernel with the GPU to itself (one lane, strips on the main stream, 5 steps after
+            # the timed legs): with two slab lanes its interval in the timed region above is shared with
+            # the other lane's last stage / strips / Welch, so `achieved` there is a lower bound
+            ex_ms = serial_step[top]
+            step_bytes_top = algo_launch * max(1, top_n // args.steps)
+            roofline["exclusive"] = {"ms_per_step": ex_ms, "achieved": step_bytes_top / (ex_ms * 1e-3) / 1e9,
+                                     "frac": step_bytes_top / (ex_ms * 1e-3) / 1e9 / peak,
+                                     "what": "all launches of this kernel for one step, nothing else running"}
         # the binding roofline: fp32 FMA pipe (SURVEY 8d "report both")
         flops_sample, flop_parts = algorithmic_flops(w, eng, nch)
         sm_mhz = ((sustained["clocks"]["sm_mhz"] if sustained else None) or clocks["sm_mhz"] or
@@ -640,6 +660,7 @@ def run_b200(args, w):
             cfg["channels_per_gpu"] = nch
             cfg["value_counts"] = "channel-samples: every virtual receiver consumes the whole stream"
         cfg["decimator_mode"] = "fast" if eng.fast_active else "exact"
+        cfg["slab_lanes"] = lanes
         if host_affinity is not None:
             cfg["host_affinity_rank0"] = host_affinity
         h2d_step = in_bytes if bcast_feed else world * in_bytes
@@ -697,6 +718,9 @@ def main():
     ap.add_argument("--welch-splits", type=int, default=0, help="tuning: CTAs per frame in the Welch kernel")
     ap.add_argument("--strips-async", type=int, default=None, help="tuning: 0 = edge strips on the main stream")
     ap.add_argument("--late-mix", type=int, default=None, help="tuning: 0 = always mix before the FIR chain")
+    ap.add_argument("--slabs", type=int, default=None,
+                    help="tuning: 1 = one lane (no slab pipelining inside zfb_process_device), 2 = two lanes (default)")
+    ap.add_argument("--set", action="append", dest="sets", metavar="OPTION=VALUE", help="tuning: zfb_set_option")
     ap.add_argument("--lib", default=None, help="tuning: path of an alternative sm_100a build")
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--sustain-s", type=float, default=3.0,

@@ -158,8 +158,15 @@ int  zfb_reset_ema(zfb_engine *e);
  * the last stage only), "strips_priority" 0 | 1, "strip_split", "strip_decay",
  * "strip_decay_early", "fir_threads" 128 | 256, "fir_generic", "iir_stream" 0 | 1
  * (streaming last stage), "iir_stream_len", "iir_stream_warm", "iir_l2_keep",
- * "iir_depth" 0 | 1 | 2, "welch_prune" 0 | 1 | 2.  Unknown names: ZFB_EINVAL. */
+ * "iir_depth" 0 | 1 | 2, "welch_prune" 0 | 1 | 2.
+ * "slabs" = 2 (default): zfb_process_device batches of >= "slab_min" (64)
+ * frames in mode FAST are cut into slabs that run through two lane engines
+ * (own workspaces and streams) at the same time, the rows finished in frame
+ * order on the engine's stream -- bit-identical to "slabs" = 1 (one lane).
+ * Unknown names: ZFB_EINVAL. */
 int  zfb_set_option(zfb_engine *e, const char *name, long long value);
+/* Lanes the last zfb_process_device batch ran through: 2 (slabs) or 1. */
+int  zfb_slab_lanes(const zfb_engine *e);
 
 /* ---- the hot path ----------------------------------------------------- */
 /*

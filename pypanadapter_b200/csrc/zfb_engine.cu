@@ -54,6 +54,23 @@ struct DevBuf {
 struct zfb_engine {
     int device = 0;
     int sm_count = 148;
+    // Slab pipelining (zfb_set_option("slabs") = 2): a large zfb_process_device batch is cut into
+    // slabs that alternate between two LANE engines (same plan and options, own workspaces, own
+    // streams).  A lane runs a slab up to the Welch power sums; this engine turns the sums into rows
+    // on its own stream, slab after slab (EMA strictly in frame order, dB20, ring) with the one-lane
+    // path's kernel on the same operands: rows are bit-identical.  What it buys: the FIR interior
+    // of one slab runs beside the latency-bound last stage / strips / Welch of the other.
+    int slabs = 2;
+    int slab_min = 64;                           // zfb_set_option("slab_min"): smallest batch cut into slabs
+    bool is_lane = false, lanes_ready = false, lanes_stale = true;
+    std::vector<double> window_host;             // the configured window (the caller's table may go away)
+    zfb_engine *lane[2] = {nullptr, nullptr};
+    int last_lanes = 1;                          // zfb_slab_lanes
+    zfb_engine *last_front = nullptr;            // whose mid[] holds the last decimated chunks (debug read)
+    cudaEvent_t ev_slab_in = nullptr;            // the batch's input is ready (recorded on `stream`)
+    cudaEvent_t ev_lane[2] = {nullptr, nullptr}; // a lane's power sums are ready
+    cudaEvent_t ev_fin[2] = {nullptr, nullptr};  // ... and consumed: the lane may overwrite them
+    bool ev_fin_used[2] = {false, false};
     mutable std::mutex mu;
     std::string err;
 
@@ -1352,6 +1369,7 @@ int run_group_precise(zfb_engine *e, const void *d_in, int gf, float *d_rows) {
     }
     CK(e, cudaGetLastError());
     e->last_group_frames = gf;
+    e->last_front = e;
     e->counters[0] += (uint64_t)gf;
     e->counters[1] += (uint64_t)gf * (uint64_t)c.frame_len;
     return ZFB_OK;
@@ -1364,9 +1382,14 @@ bool fir_cs16_fused(const zfb_engine *e) {
 }
 
 // one group of frames, all resident on the device, through the whole chain
-int run_group(zfb_engine *e, const void *d_in, int gf, float *d_rows) {
+int finish_rows(zfb_engine *e, zfb_engine *from, int gf, int nsplit, float *d_rows);
+
+// a launch group up to the Welch power sums (e->pow, nsplit partial sums per row); finish_rows makes
+// rows of them.  *done: the fp64 path (run_group_precise) has written the rows itself
+int run_group_front(zfb_engine *e, const void *d_in, int gf, float *d_rows, int *nsplit_out, bool *done) {
     const zfb_config &c = e->cfg;
     cudaStream_t st = e->stream;
+    *done = false;
     const void *d_in_cs16 = nullptr;
     if (c.dtype == ZFB_DTYPE_CS16 && fir_cs16_fused(e)) {
         // the FIR interior converts on load (zfb_firchain.cuh, KIND_CS16_RAW); only the chunk ends the
@@ -1399,7 +1422,10 @@ int run_group(zfb_engine *e, const void *d_in, int gf, float *d_rows) {
         }
         d_in = e->cvt.p;
     }
-    if (e->precise_active) return run_group_precise(e, d_in, gf, d_rows);
+    if (e->precise_active) {
+        *done = true;
+        return run_group_precise(e, d_in, gf, d_rows);
+    }
     const void *src = d_in;
     long long src_stride = c.frame_len;
     int kind = raw_kind(c);
@@ -1586,8 +1612,18 @@ int run_group(zfb_engine *e, const void *d_in, int gf, float *d_rows) {
         e->counters[2] += 3;
     }
 
+    CK(e, cudaGetLastError());
+    *nsplit_out = nsplit;
+    return ZFB_OK;
+}
+
+// rows of one launch group from the power sums in from->pow (this engine's, or a slab lane's): scale,
+// EMA in frame order, dB20, ring -- on e->stream
+int finish_rows(zfb_engine *e, zfb_engine *from, int gf, int nsplit, float *d_rows) {
+    const zfb_config &c = e->cfg;
+    cudaStream_t st = e->stream;
     FinalizeParams f{};
-    f.pow_io = (float *)e->pow.p;
+    f.pow_io = (float *)from->pow.p;
     f.nframes = gf;
     f.nsplit = nsplit;
     f.W = e->W;
@@ -1622,9 +1658,18 @@ int run_group(zfb_engine *e, const void *d_in, int gf, float *d_rows) {
     CK(e, cudaGetLastError());
     if (to_ring) e->ring_written += gf;
     e->last_group_frames = gf;
+    e->last_front = from;
     e->counters[0] += (uint64_t)gf;
     e->counters[1] += (uint64_t)gf * (uint64_t)c.frame_len;
     return ZFB_OK;
+}
+
+int run_group(zfb_engine *e, const void *d_in, int gf, float *d_rows) {
+    int nsplit = 1;
+    bool done = false;
+    const int rc = run_group_front(e, d_in, gf, d_rows, &nsplit, &done);
+    if (rc != ZFB_OK || done) return rc;
+    return finish_rows(e, e, gf, nsplit, d_rows);
 }
 
 // late mix of the first register-blocked chain (zfb_firchain.cuh): allowed when the LO
@@ -1904,6 +1949,13 @@ int zfb_create(int device, zfb_engine **out) {
 void zfb_destroy(zfb_engine *e) {
     if (!e) return;
     cudaSetDevice(e->device);
+    for (int i = 0; i < 2; ++i) {
+        if (e->lane[i]) zfb_destroy(e->lane[i]);
+        e->lane[i] = nullptr;
+        if (e->ev_lane[i]) cudaEventDestroy(e->ev_lane[i]);
+        if (e->ev_fin[i]) cudaEventDestroy(e->ev_fin[i]);
+    }
+    if (e->ev_slab_in) cudaEventDestroy(e->ev_slab_in);
     if (e->own_stream) cudaStreamSynchronize(e->own_stream);
     if (e->copy_stream) cudaStreamSynchronize(e->copy_stream);
     if (e->aux_stream) cudaStreamSynchronize(e->aux_stream);
@@ -1961,8 +2013,23 @@ int zfb_plan_geometry(int frame_len, int fft_size, int fft_ratio, int out5[5]) {
     return ZFB_OK;
 }
 
+static int configure_impl(zfb_engine *e, const zfb_config *cfg);
+static void setup_lanes(zfb_engine *e);
+
 int zfb_configure(zfb_engine *e, const zfb_config *cfg) {
     if (!e) return ZFB_EINVAL;
+    const int rc = configure_impl(e, cfg);
+    std::lock_guard<std::mutex> lk(e->mu);
+    // the lanes are planned lazily, by the first batch large enough to be cut in two (a live
+    // front-end that hands over one chunk per call never pays for them)
+    e->lanes_ready = false;
+    e->lanes_stale = true;
+    e->window_host.clear();
+    if (rc == ZFB_OK && cfg && cfg->window && e->nperseg > 0) e->window_host.assign(cfg->window, cfg->window + e->nperseg);
+    return rc;
+}
+
+static int configure_impl(zfb_engine *e, const zfb_config *cfg) {
     std::lock_guard<std::mutex> lk(e->mu);
     if (!cfg) return fail(e, ZFB_EINVAL, "configure: cfg is NULL");
     CK(e, cudaSetDevice(e->device));
@@ -2220,6 +2287,89 @@ int zfb_configure(zfb_engine *e, const zfb_config *cfg) {
     return ZFB_OK;
 }
 
+// lanes of the slab pipeline: two engines on the same device with this engine's plan and options
+// (best effort: any failure leaves the one-lane path in charge)
+static void setup_lanes(zfb_engine *e) {          // e->mu is held by the caller
+    e->lanes_ready = false;
+    e->lanes_stale = false;
+    if (e->is_lane || e->slabs < 2 || !e->configured || !e->fast_active || e->precise_active || e->window_host.empty())
+        return;
+    zfb_config c2 = e->cfg;
+    c2.window = e->window_host.data();
+    c2.ema_alpha = -1.0;                          // rows are finished by this engine: no EMA state in a lane
+    if (!e->ev_slab_in && cudaEventCreateWithFlags(&e->ev_slab_in, cudaEventDisableTiming) != cudaSuccess) return;
+    for (int i = 0; i < 2; ++i) {
+        if (!e->lane[i]) {
+            if (zfb_create(e->device, &e->lane[i]) != ZFB_OK) { e->lane[i] = nullptr; return; }
+            e->lane[i]->is_lane = true;
+        }
+        zfb_engine *l = e->lane[i];
+        {
+            std::lock_guard<std::mutex> lk2(l->mu);
+            l->strips_priority = e->strips_priority; l->strips_async = e->strips_async; l->strip_split = e->strip_split;
+            l->strip_decay = e->strip_decay; l->strip_decay_early = e->strip_decay_early; l->ring_append = 0;
+            l->late_mix = e->late_mix; l->iir_stream = e->iir_stream; l->iir_S = e->iir_S; l->iir_Wm = e->iir_Wm;
+            l->iir_depth = e->iir_depth; l->iir_l2_keep = e->iir_l2_keep; l->precise = e->precise;
+            l->decim_threads = e->decim_threads; l->welch_splits = e->welch_splits; l->cs16_fused = e->cs16_fused;
+            l->welch_prune = e->welch_prune; l->fir_generic = e->fir_generic; l->fir_smem_pad = e->fir_smem_pad;
+            l->fir_threads = e->fir_threads; l->group_user = e->group_user;
+            l->fplan = e->fplan;
+            l->configured = false;
+        }
+        if (configure_impl(l, &c2) != ZFB_OK || !l->fast_active || l->precise_active || l->group != e->group ||
+            l->W != e->W || l->Wp != e->Wp)
+            return;
+        for (cudaEvent_t *ev : {&e->ev_lane[i], &e->ev_fin[i]})
+            if (!*ev && cudaEventCreateWithFlags(ev, cudaEventDisableTiming) != cudaSuccess) return;
+        e->ev_fin_used[i] = false;
+    }
+    cudaGetLastError();
+    e->lanes_ready = true;
+}
+
+// a batch in slabs: lane k & 1 runs slab k up to its power sums, this engine finishes the rows in order
+static int process_slabs(zfb_engine *e, const void *d_in, int nframes, float *d_rows) {
+    const size_t fbytes = (size_t)e->cfg.frame_len * sample_bytes(e->cfg);
+    // an even number of equal slabs, none above a launch group
+    const int nsl = 2 * ((nframes + 2 * e->group - 1) / (2 * e->group));
+    const int per = (nframes + nsl - 1) / nsl;
+    CK(e, cudaEventRecord(e->ev_slab_in, e->stream));
+    for (int i = 0; i < 2; ++i) {
+        zfb_engine *l = e->lane[i];
+        CK(e, cudaStreamWaitEvent(l->stream, e->ev_slab_in, 0));
+        l->profiling = e->profiling;
+    }
+    int rc = ZFB_OK;
+    for (int k = 0; k * per < nframes && rc == ZFB_OK; ++k) {
+        const int i = k & 1;
+        zfb_engine *l = e->lane[i];
+        const int f0 = k * per;
+        const int gf = (nframes - f0 < per) ? nframes - f0 : per;
+        if (e->ev_fin_used[i]) CK(e, cudaStreamWaitEvent(l->stream, e->ev_fin[i], 0));
+        int nsplit = 1;
+        bool done = false;
+        const uint64_t launches0 = l->counters[2];
+        rc = run_group_front(l, (const char *)d_in + (size_t)f0 * fbytes, gf, nullptr, &nsplit, &done);
+        e->counters[2] += l->counters[2] - launches0;
+        if (rc != ZFB_OK) {
+            e->err = l->err;
+            break;
+        }
+        CK(e, cudaEventRecord(e->ev_lane[i], l->stream));
+        CK(e, cudaStreamWaitEvent(e->stream, e->ev_lane[i], 0));
+        rc = finish_rows(e, l, gf, nsplit, d_rows ? d_rows + (size_t)f0 * e->W : nullptr);
+        if (rc != ZFB_OK) break;
+        CK(e, cudaEventRecord(e->ev_fin[i], e->stream));
+        e->ev_fin_used[i] = true;
+    }
+    if (rc != ZFB_OK) {
+        // nothing of the lanes may still be running when the caller sees the error
+        for (int i = 0; i < 2; ++i) cudaStreamSynchronize(e->lane[i]->stream);
+        cudaGetLastError();
+    }
+    return rc;
+}
+
 int zfb_set_fast_plan(zfb_engine *e, const zfb_fast_plan *plan) {
     if (!e) return ZFB_EINVAL;
     std::lock_guard<std::mutex> lk(e->mu);
@@ -2254,6 +2404,7 @@ int zfb_set_fast_plan(zfb_engine *e, const zfb_fast_plan *plan) {
             return ZFB_OK;                                    // same plan again: nothing to re-plan
     }
     e->fplan = f;
+    e->lanes_stale = true;
     e->configured = false;       // re-plan on the next configure (ring and EMA state are kept)
     return ZFB_OK;
 }
@@ -2262,6 +2413,12 @@ int zfb_fast_active(const zfb_engine *e) {
     if (!e) return ZFB_EINVAL;
     std::lock_guard<std::mutex> lk(e->mu);
     return (e->configured && e->fast_active) ? 1 : 0;
+}
+
+int zfb_slab_lanes(const zfb_engine *e) {
+    if (!e) return ZFB_EINVAL;
+    std::lock_guard<std::mutex> lk(e->mu);
+    return e->last_lanes;
 }
 
 int zfb_set_stream(zfb_engine *e, void *cuda_stream) {
@@ -2278,6 +2435,7 @@ int zfb_set_group(zfb_engine *e, int frames_per_group) {
     std::lock_guard<std::mutex> lk(e->mu);
     if (frames_per_group < 0) return fail(e, ZFB_EINVAL, "frames_per_group must be >= 0");
     e->group_user = frames_per_group;
+    e->lanes_stale = true;
     e->configured = false;      // workspaces are sized per group: re-plan on next configure
     return ZFB_OK;
 }
@@ -2285,6 +2443,17 @@ int zfb_set_group(zfb_engine *e, int frames_per_group) {
 int zfb_set_option(zfb_engine *e, const char *name, long long value) {
     if (!e || !name) return ZFB_EINVAL;
     std::lock_guard<std::mutex> lk(e->mu);
+    e->lanes_stale = true;                       // the slab lanes take this engine's options when next used
+    if (strcmp(name, "slabs") == 0) {
+        if (value < 0 || value > 2) return fail(e, ZFB_EINVAL, "slabs must be 0, 1 (one lane) or 2");
+        e->slabs = (int)value;
+        return ZFB_OK;
+    }
+    if (strcmp(name, "slab_min") == 0) {
+        if (value < 2 || value > (1 << 20)) return fail(e, ZFB_EINVAL, "slab_min (frames) must be in [2, 2^20]");
+        e->slab_min = (int)value;
+        return ZFB_OK;
+    }
     if (strcmp(name, "decim_threads") == 0) {
         if (value != 0 && value != NTHR_BIG && value != NTHR_SMALL)
             return fail(e, ZFB_EINVAL, "decim_threads must be 0 (auto), %d or %d", NTHR_SMALL, NTHR_BIG);
@@ -2513,6 +2682,14 @@ static int process_device_impl(zfb_engine *e, const void *d_in, int nframes, con
         // the counters count frames per channel pass; rows [nch][nframes][W]
         return run_channels(e, d_in, nframes, f_demod, nch, nframes, d_rows, batched);
     }
+    if (!e->is_lane && e->slabs >= 2 && nframes >= e->slab_min && nframes >= 2 && e->fast_active && !e->precise_active) {
+        if (e->lanes_stale) setup_lanes(e);
+        if (e->lanes_ready) {
+            e->last_lanes = 2;
+            return process_slabs(e, d_in, nframes, d_rows);
+        }
+    }
+    e->last_lanes = 1;
     for (int g0 = 0; g0 < nframes; g0 += e->group) {
         const int gf = (nframes - g0 < e->group) ? nframes - g0 : e->group;
         rc = run_group(e, (const char *)d_in + (size_t)g0 * fbytes, gf,
@@ -2655,7 +2832,8 @@ int zfb_debug_read_decimated(zfb_engine *e, float *h_out_iq, int max_samples) {
     int n = e->len[e->nstages];
     if (n > max_samples) n = max_samples;
     CK(e, cudaStreamSynchronize(e->stream));
-    CK(e, cudaMemcpy(h_out_iq, e->mid[e->final_buf].p, (size_t)n * sizeof(float2), cudaMemcpyDeviceToHost));
+    const zfb_engine *src = e->last_front ? e->last_front : e;     // a slab lane, after a batch in slabs
+    CK(e, cudaMemcpy(h_out_iq, src->mid[src->final_buf].p, (size_t)n * sizeof(float2), cudaMemcpyDeviceToHost));
     e->counters[4] += (size_t)n * sizeof(float2);
     return n;
 }
@@ -3177,16 +3355,21 @@ int zfb_get_profile(zfb_engine *e, double ms_out[ZFB_PROF_CLASSES], uint64_t lau
     CK(e, cudaSetDevice(e->device));
     CK(e, cudaStreamSynchronize(e->stream));
     for (int c = 0; c < ZFB_PROF_CLASSES; ++c) { ms_out[c] = 0.0; launches_out[c] = 0; }
-    for (auto &r : e->prof_used) {
-        float ms = 0.f;
-        if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess && r.cls >= 0 && r.cls < ZFB_PROF_CLASSES) {
-            ms_out[r.cls] += (double)ms;
-            launches_out[r.cls] += 1;
+    // the slab lanes' kernels belong to this engine's profile (e->stream has waited for all of them)
+    for (zfb_engine *x : {e, e->lane[0], e->lane[1]}) {
+        if (!x) continue;
+        if (x != e) cudaStreamSynchronize(x->stream);
+        for (auto &r : x->prof_used) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess && r.cls >= 0 && r.cls < ZFB_PROF_CLASSES) {
+                ms_out[r.cls] += (double)ms;
+                launches_out[r.cls] += 1;
+            }
+            x->prof_free.push_back(r);
         }
-        e->prof_free.push_back(r);
+        x->prof_used.clear();
     }
     cudaGetLastError();
-    e->prof_used.clear();
     return ZFB_OK;
 }
 

@@ -281,7 +281,9 @@ __global__ void __launch_bounds__(256) px_rows_kernel(const PxRowsParams p) {
         for (int s = 0; s < p.nseg; ++s) pw += p.pow[((size_t)f * p.nseg + s) * (size_t)N + k];
         pw *= p.scale * factor;
         if (p.alpha >= 0.0) {
-            a = have ? a + p.alpha * (pw - a) : pw;
+            // the state between launches is fp32 (shared with the fp32 path): round it after every
+            // frame, so that a row does not depend on where a launch group or a call ends
+            a = (double)(float)(have ? a + p.alpha * (pw - a) : pw);
             have = true;
             pw = a;
         }

@@ -219,6 +219,11 @@ class ZoomPSD:
     def fast_active(self) -> bool:
         return bool(self._lib.zfb_fast_active(self._h))
 
+    @property
+    def slab_lanes(self) -> int:
+        """lanes the last ``process_device`` batch ran through (2: cut into slabs)"""
+        return int(self._lib.zfb_slab_lanes(self._h))
+
     def set_group(self, frames_per_group: int):
         self._check(self._lib.zfb_set_group(self._h, int(frames_per_group)), "zfb_set_group")
         self._key = None

@@ -60,6 +60,111 @@ def batch_equals_single(engine, lib):
     engine.set_group(0)
 
 
+class HostAsDevice:
+    """Device buffers of the CPU emulation build are host memory."""
+
+    def put(self, a):
+        a = np.ascontiguousarray(a)
+        return a.ctypes.data, a
+
+    def empty(self, shape):
+        a = np.zeros(shape, dtype=np.float32)
+        return a.ctypes.data, a
+
+    def get(self, obj):
+        return np.array(obj)
+
+
+class TorchDevice:
+    def put(self, a):
+        import torch
+        t = torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(len(a), -1)).cuda()
+        return t.data_ptr(), t
+
+    def empty(self, shape):
+        import torch
+        t = torch.zeros(shape, dtype=torch.float32, device="cuda")
+        torch.cuda.synchronize()
+        return t.data_ptr(), t
+
+    def get(self, obj):
+        return obj.cpu().numpy()
+
+
+def slabs_equal_one_lane(engine, dev, nframes=7, w=None, n=None):
+    """zfb_process_device cuts large batches into slabs that run through two lane engines at the
+    same time (option ``slabs``); the rows -- EMA carried across slabs, groups and calls, ring
+    content, counters -- must equal the one-lane path's bit for bit (frames are independent:
+    S:2092, S:2098, S:2111)."""
+    w = w or synth.CFG2
+    n = n or 4096 * 16 * 4 + 1234           # 7 Welch segments: the fp32 path
+    frames = synth.make_frames(w, nframes, n=n)
+    p_in, keep = dev.put(frames)
+
+    def run(slabs, group, calls):
+        engine.set_option("slabs", slabs)
+        engine.set_option("slab_min", 2)
+        engine.set_group(group)
+        engine.ring_configure(4)
+        engine.configure(w.fs, w.fft_size, w.fft_ratio, n, w.window, dtype="u8", flip=True, crop="thread",
+                         ema_alpha=0.3)
+        assert engine.fast_active
+        engine.reset_ema()
+        k0 = engine.counters()
+        p_rows, rows = dev.empty((nframes, engine.row_width))
+        f0 = 0
+        fbytes = frames[0].nbytes
+        for cnt in calls:
+            engine.process_device(p_in + f0 * fbytes, cnt, p_rows + f0 * engine.row_width * 4)
+            f0 += cnt
+        engine.synchronize()
+        assert engine.slab_lanes == slabs
+        k1 = engine.counters()
+        return dev.get(rows), engine.read_rows(4), engine.read_decimated().shape, \
+            {k: k1[k] - k0[k] for k in ("frames", "samples")}
+
+    try:
+        want = run(1, 0, [nframes])
+        for group, calls in ((0, [nframes]), (2, [nframes]), (0, [3, nframes - 3]), (3, [nframes - 2, 2])):
+            got = run(2, group, calls)
+            assert np.array_equal(got[0], want[0]), (group, calls)
+            assert np.array_equal(got[1], want[1]), (group, calls)
+            assert got[2] == want[2] and got[3] == want[3]
+        # one engine option changed between batches reaches the lanes
+        engine.set_option("slabs", 2)
+        engine.set_option("strips_async", 0)
+        got = run(2, 0, [nframes])
+        assert np.array_equal(got[0], want[0])
+    finally:
+        engine.set_option("strips_async", 1)
+        engine.set_option("slabs", 2)
+        engine.set_option("slab_min", 64)
+        engine.set_group(0)
+        engine.ring_configure(256)
+
+
+def ema_batch_independent(engine):
+    """EMA rows do not depend on where a launch group or a call ends -- on the fp64 path of
+    few-segment rows too (its state between launches is fp32 like the fp32 path's)."""
+    w = synth.CFG2
+    for n in (4096 * 16 + 1234, 4096 * 16 * 4 + 1234):          # 1 segment (fp64 path), 7 segments
+        frames = synth.make_frames(w, 7, n=n)
+        rows = []
+        for group, calls in ((0, [7]), (2, [7]), (3, [4, 3]), (0, [1] * 7)):
+            engine.set_group(group)
+            engine.configure(w.fs, w.fft_size, w.fft_ratio, n, w.window, dtype="u8", flip=True, crop="thread",
+                             ema_alpha=0.3)
+            engine.reset_ema()
+            f0, got = 0, []
+            for cnt in calls:
+                got.append(engine.process(frames[f0:f0 + cnt]))
+                f0 += cnt
+            rows.append(np.concatenate(got))
+        engine.set_group(0)
+        for r in rows[1:]:
+            assert np.array_equal(r, rows[0])
+
+
 def ring_behaviour(engine):
     w = synth.CFG1
     n = 2048 * 10

@@ -23,6 +23,14 @@ def test_batch_equals_single(emu_engine, emu_lib):
     es.batch_equals_single(emu_engine, emu_lib)
 
 
+def test_slabs_equal_one_lane(emu_engine):
+    es.slabs_equal_one_lane(emu_engine, es.HostAsDevice())
+
+
+def test_ema_batch_independent(emu_engine):
+    es.ema_batch_independent(emu_engine)
+
+
 def test_ring(emu_engine):
     es.ring_behaviour(emu_engine)
 
