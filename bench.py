@@ -321,6 +321,12 @@ def run_b200(args, w):
         eng.set_option("late_mix", args.late_mix)
     if args.slabs is not None:
         eng.set_option("slabs", args.slabs)
+    # pipelined batches: zfb_process_device returns without making `stream` wait for the rows; the
+    # bench joins (zfb_join) where something consumes them -- the NCCL gather, the end of a timed leg
+    # (auto: on for 1- and 2-byte wire formats; complex64 input loses -- cfg1 166.7 -> 147.9 Gs/s, the two
+    # lanes' streams evict each other from L2 -- profiles/r02ac_*)
+    pipelined = (args.pipeline == 1 or (args.pipeline < 0 and w.dtype in ("u8", "cs16"))) and w.name != "cfg4"
+    eng.set_option("pipeline", 1 if pipelined else 0)
     for it in args.sets or []:
         name, _, val = it.partition("=")
         eng.set_option(name, int(val))
@@ -359,11 +365,16 @@ def run_b200(args, w):
 
     def gather_async(buf_idx):
         """rows of this step -> rank 0, on the side stream"""
-        rows_ready[buf_idx].record(stream)
-        with torch.cuda.stream(comm_stream):
+        if pipelined and joinable[0]:
+            eng.join(comm_stream.cuda_stream)        # the side stream waits for the rows, `stream` does not
+        else:
+            rows_ready[buf_idx].record(stream)
             comm_stream.wait_event(rows_ready[buf_idx])
+        with torch.cuda.stream(comm_stream):
             dist.gather(d_rows2[buf_idx], gather_list, dst=0)
             gathered[buf_idx].record(comm_stream)
+
+    joinable = [False]                               # the last engine call was a (pipelined) device batch
 
     def step_device():
         b = step_no[0] & 1
@@ -374,8 +385,14 @@ def run_b200(args, w):
             eng.process_device(d_in.data_ptr(), F, d_rows2[b].data_ptr())
         else:
             eng.process_channels_device(d_in.data_ptr(), F, centres, d_rows2[b].data_ptr())
+        joinable[0] = True
         if world > 1:
             gather_async(b)
+
+    def join_device():
+        """`stream` waits for every batch handed to the engine (no-op unless pipelined)"""
+        if pipelined:
+            eng.join()
 
     h_in_np = h_in.numpy().view(frame_wire.dtype).reshape(frame_wire.shape)
     h_rows_np = h_rows.numpy()
@@ -413,6 +430,7 @@ def run_b200(args, w):
             step_no[0] += 1
             stream.wait_event(gathered[b])
             d_rows2[b].copy_(h_rows, non_blocking=True)
+            joinable[0] = False
             gather_async(b)
 
     props = torch.cuda.get_device_properties(local_rank)
@@ -423,6 +441,7 @@ def run_b200(args, w):
     # ---------------- device-resident throughput ----------------
     for _ in range(args.warmup):
         step_device()
+    join_device()
     barrier()
     k0 = eng.counters()["kernels"]
     eng.profile()
@@ -432,7 +451,8 @@ def run_b200(args, w):
     ev0.record(stream)
     for _ in range(args.steps):
         step_device()
-    if world > 1:                                   # the last gather belongs to the timed region
+    join_device()                                   # the rows of every step belong to the timed region
+    if world > 1:                                   # ... and so does the last gather
         stream.wait_event(gathered[(step_no[0] - 1) & 1])
     ev1.record(stream)
     barrier()
@@ -503,7 +523,9 @@ def run_b200(args, w):
         for i in range(n_sus):
             step_device()
             if (i & 63) == 63:
+                join_device()
                 stream.synchronize()                 # bound the launch queue; negligible against 64 steps
+        join_device()
         if world > 1:
             stream.wait_event(gathered[(step_no[0] - 1) & 1])
         ev7.record(stream)
@@ -518,6 +540,7 @@ def run_b200(args, w):
     if world == 1 and eng.fast_active:
         eng.set_option("strips_async", 0)
         eng.set_option("slabs", 1)
+        eng.set_option("pipeline", 0)
         eng.configure(w.fs, w.fft_size, w.fft_ratio, w.frame_len, w.window, dtype=w.dtype, flip=w.flip,
                       f_demod=w.f_demod, crop=w.crop, ema_alpha=w.ema_alpha, mode=args.mode)
         for _ in range(2):
@@ -533,7 +556,8 @@ def run_b200(args, w):
         serial_prof = {k: v[0] / max(1, v[1]) for k, v in serial_raw.items()}
         serial_step = {k: v[0] / 5.0 for k, v in serial_raw.items()}      # ms per step, all launches of the class
         eng.set_option("strips_async", 1 if args.strips_async is None else args.strips_async)
-        eng.set_option("slabs", 2 if args.slabs is None else args.slabs)
+        eng.set_option("slabs", 1 if args.slabs is None else args.slabs)
+        eng.set_option("pipeline", 1 if pipelined else 0)
 
     # ---------------- N > 1: the gathered rows ARE the single-GPU rows, bit for bit ----------------
     # frames are independent (LO phase, filter state and Welch mean restart per chunk: S:2092, 2098,
@@ -547,12 +571,14 @@ def run_b200(args, w):
         mine = torch.from_numpy(allf[rank * Fv:(rank + 1) * Fv].view(np.uint8).reshape(Fv, -1)).cuda()
         rows_mine = torch.empty((Fv, W), dtype=torch.float32, device="cuda")
         eng.process_device(mine.data_ptr(), Fv, rows_mine.data_ptr())
+        eng.join()
         glist = [torch.empty_like(rows_mine) for _ in range(world)] if rank == 0 else None
         dist.gather(rows_mine, glist, dst=0)
         stream.synchronize()
         if rank == 0:
             everything = torch.from_numpy(allf.view(np.uint8).reshape(world * Fv, -1)).cuda()
             rows_all = torch.empty((world * Fv, W), dtype=torch.float32, device="cuda")
+            eng.set_option("pipeline", 0)            # the plain path on one GPU is the yardstick
             eng.process_device(everything.data_ptr(), world * Fv, rows_all.data_ptr())
             stream.synchronize()
             got = torch.cat(glist, 0).cpu().numpy()
@@ -634,6 +660,17 @@ def run_b200(args, w):
             roofline["exclusive"] = {"ms_per_step": ex_ms, "achieved": step_bytes_top / (ex_ms * 1e-3) / 1e9,
                                      "frac": step_bytes_top / (ex_ms * 1e-3) / 1e9 / peak,
                                      "what": "all launches of this kernel for one step, nothing else running"}
+            if lanes == 2:
+                # pipelined batches: the kernel's event interval in the timed region is shared with the
+                # other lane's kernels and says nothing about the kernel; the figure with the GPU to
+                # itself is the roofline entry, the shared one is kept beside it
+                roofline["timed_region_overlapped"] = {"achieved": roofline["achieved"], "frac": roofline["frac"],
+                                                       "avg_launch_ms": roofline["avg_launch_ms"]}
+                roofline["achieved"] = roofline["exclusive"]["achieved"]
+                roofline["frac"] = roofline["exclusive"]["frac"]
+                roofline["avg_launch_ms"] = ex_ms / max(1.0, serial_raw[top][1] / 5.0)
+                roofline["avg_launch_ms_source"] = ("CUDA events around the kernel, 5 steps with nothing "
+                                                    "overlapped, after the timed legs of this run")
         # the binding roofline: fp32 FMA pipe (SURVEY 8d "report both")
         flops_sample, flop_parts = algorithmic_flops(w, eng, nch)
         sm_mhz = ((sustained["clocks"]["sm_mhz"] if sustained else None) or clocks["sm_mhz"] or
@@ -661,6 +698,7 @@ def run_b200(args, w):
             cfg["value_counts"] = "channel-samples: every virtual receiver consumes the whole stream"
         cfg["decimator_mode"] = "fast" if eng.fast_active else "exact"
         cfg["slab_lanes"] = lanes
+        cfg["pipelined_batches"] = pipelined
         if host_affinity is not None:
             cfg["host_affinity_rank0"] = host_affinity
         h2d_step = in_bytes if bcast_feed else world * in_bytes
@@ -719,7 +757,11 @@ def main():
     ap.add_argument("--strips-async", type=int, default=None, help="tuning: 0 = edge strips on the main stream")
     ap.add_argument("--late-mix", type=int, default=None, help="tuning: 0 = always mix before the FIR chain")
     ap.add_argument("--slabs", type=int, default=None,
-                    help="tuning: 1 = one lane (no slab pipelining inside zfb_process_device), 2 = two lanes (default)")
+                    help="tuning: 2 = cut every batch into slabs across two lane engines (default 1: one lane)")
+    ap.add_argument("--pipeline", type=int, default=-1,
+                    help="1: batches alternate between the engine's two lanes, rows joined where they are "
+                         "consumed (zfb_join); 0: every batch ordered on the bench stream at once; "
+                         "-1 (default): 1 for uint8 / int16 IQ, 0 for complex64")
     ap.add_argument("--set", action="append", dest="sets", metavar="OPTION=VALUE", help="tuning: zfb_set_option")
     ap.add_argument("--lib", default=None, help="tuning: path of an alternative sm_100a build")
     ap.add_argument("--e2e-steps", type=int, default=20)

@@ -159,14 +159,25 @@ int  zfb_reset_ema(zfb_engine *e);
  * "strip_decay_early", "fir_threads" 128 | 256, "fir_generic", "iir_stream" 0 | 1
  * (streaming last stage), "iir_stream_len", "iir_stream_warm", "iir_l2_keep",
  * "iir_depth" 0 | 1 | 2, "welch_prune" 0 | 1 | 2.
- * "slabs" = 2 (default): zfb_process_device batches of >= "slab_min" (64)
- * frames in mode FAST are cut into slabs that run through two lane engines
- * (own workspaces and streams) at the same time, the rows finished in frame
- * order on the engine's stream -- bit-identical to "slabs" = 1 (one lane).
+ * "slabs" = 2 (default 1: measured no faster): zfb_process_device batches of
+ * >= "slab_min" (64) frames in mode FAST are cut into slabs that run through
+ * two lane engines (own workspaces and streams) at the same time, the rows
+ * finished in frame order on the engine's stream -- bit-identical to one lane.
+ * "pipeline": see zfb_join.
  * Unknown names: ZFB_EINVAL. */
 int  zfb_set_option(zfb_engine *e, const char *name, long long value);
-/* Lanes the last zfb_process_device batch ran through: 2 (slabs) or 1. */
+/* Lanes the last zfb_process_device batch ran through: 2 (slabs, pipeline) or 1. */
 int  zfb_slab_lanes(const zfb_engine *e);
+/* Pipelined batches, zfb_set_option("pipeline", 1) (default 0; mode FAST, rows
+ * on the fp32 path): zfb_process_device hands whole batches to the two lane
+ * engines in turn and finishes their rows (EMA in frame order, ring) on a
+ * stream of its own WITHOUT making the engine's stream wait: the FIR interior
+ * of batch k + 1 runs beside the last stage / strips / Welch of batch k.  The
+ * caller orders the rows (and the reuse of d_in) with zfb_join: the given
+ * stream -- NULL or the engine's own: that one -- waits for every batch handed
+ * over so far.  zfb_synchronize and every other call on the engine join
+ * implicitly.  Rows are bit-identical to "pipeline" = 0. */
+int  zfb_join(zfb_engine *e, void *cuda_stream);
 
 /* ---- the hot path ----------------------------------------------------- */
 /*

@@ -87,6 +87,7 @@ SYMBOLS = {
     "zfb_reset_ema": (C.c_int, [_P]),
     "zfb_set_option": (C.c_int, [_P, C.c_char_p, C.c_longlong]),
     "zfb_slab_lanes": (C.c_int, [_P]),
+    "zfb_join": (C.c_int, [_P, _P]),
     "zfb_process_device": (C.c_int, [_P, _P, C.c_int, _P]),
     "zfb_process_host": (C.c_int, [_P, _P, C.c_int, _P]),
     "zfb_process_channels_device": (C.c_int, [_P, _P, C.c_int, C.POINTER(C.c_double), C.c_int, _P]),

@@ -60,11 +60,20 @@ struct zfb_engine {
     // on its own stream, slab after slab (EMA strictly in frame order, dB20, ring) with the one-lane
     // path's kernel on the same operands: rows are bit-identical.  What it buys: the FIR interior
     // of one slab runs beside the latency-bound last stage / strips / Welch of the other.
-    int slabs = 2;
+    int slabs = 1;                               // measured: no faster than one lane (profiles/r02aa, r02ab)
     int slab_min = 64;                           // zfb_set_option("slab_min"): smallest batch cut into slabs
     bool is_lane = false, lanes_ready = false, lanes_stale = true;
     std::vector<double> window_host;             // the configured window (the caller's table may go away)
     zfb_engine *lane[2] = {nullptr, nullptr};
+    // Pipelined batches (zfb_set_option("pipeline") = 1): whole zfb_process_device batches alternate
+    // between the lanes and the rows are finished on fin_stream; e->stream is NOT made to wait for
+    // them until zfb_join / zfb_synchronize (or any other call on the engine): the FIR interior of
+    // batch k + 1 runs beside the last stage / strips / Welch of batch k.
+    int pipeline = 0;
+    int next_lane = 0;
+    cudaStream_t fin_stream = nullptr;
+    cudaEvent_t ev_done = nullptr;               // everything issued so far is finished (on fin_stream)
+    bool join_pending = false;
     int last_lanes = 1;                          // zfb_slab_lanes
     zfb_engine *last_front = nullptr;            // whose mid[] holds the last decimated chunks (debug read)
     cudaEvent_t ev_slab_in = nullptr;            // the batch's input is ready (recorded on `stream`)
@@ -1382,7 +1391,7 @@ bool fir_cs16_fused(const zfb_engine *e) {
 }
 
 // one group of frames, all resident on the device, through the whole chain
-int finish_rows(zfb_engine *e, zfb_engine *from, int gf, int nsplit, float *d_rows);
+int finish_rows(zfb_engine *e, zfb_engine *from, int gf, int nsplit, float *d_rows, cudaStream_t st);
 
 // a launch group up to the Welch power sums (e->pow, nsplit partial sums per row); finish_rows makes
 // rows of them.  *done: the fp64 path (run_group_precise) has written the rows itself
@@ -1618,10 +1627,9 @@ int run_group_front(zfb_engine *e, const void *d_in, int gf, float *d_rows, int 
 }
 
 // rows of one launch group from the power sums in from->pow (this engine's, or a slab lane's): scale,
-// EMA in frame order, dB20, ring -- on e->stream
-int finish_rows(zfb_engine *e, zfb_engine *from, int gf, int nsplit, float *d_rows) {
+// EMA in frame order, dB20, ring -- on stream st (e->stream, or fin_stream for pipelined batches)
+int finish_rows(zfb_engine *e, zfb_engine *from, int gf, int nsplit, float *d_rows, cudaStream_t st) {
     const zfb_config &c = e->cfg;
-    cudaStream_t st = e->stream;
     FinalizeParams f{};
     f.pow_io = (float *)from->pow.p;
     f.nframes = gf;
@@ -1645,7 +1653,7 @@ int finish_rows(zfb_engine *e, zfb_engine *from, int gf, int nsplit, float *d_ro
     f.ring_rows = e->ring_rows;
     f.chan_frames = e->cur_nch > 0 ? e->cur_chan_frames : 0;
     f.chan_row_stride = e->cur_row_stride;
-    const int prf = prof_begin(e, 18);
+    const int prf = prof_begin(e, 18, st);
     const long long cells = (long long)gf * e->W;
     if (f.alpha >= 0.f) {
         ZFB_LAUNCH(ema_rows_kernel, dim3((unsigned)((e->W + EMA_COLS - 1) / EMA_COLS)), dim3(EMA_NT), 0, st, f);
@@ -1654,7 +1662,7 @@ int finish_rows(zfb_engine *e, zfb_engine *from, int gf, int nsplit, float *d_ro
         ZFB_LAUNCH(reduce_rows_kernel, dim3((unsigned)((cells + 255) / 256)), dim3(256), 0, st, f);
     }
     e->counters[2] += 1;
-    prof_end(e, prf);
+    prof_end(e, prf, st);
     CK(e, cudaGetLastError());
     if (to_ring) e->ring_written += gf;
     e->last_group_frames = gf;
@@ -1669,7 +1677,7 @@ int run_group(zfb_engine *e, const void *d_in, int gf, float *d_rows) {
     bool done = false;
     const int rc = run_group_front(e, d_in, gf, d_rows, &nsplit, &done);
     if (rc != ZFB_OK || done) return rc;
-    return finish_rows(e, e, gf, nsplit, d_rows);
+    return finish_rows(e, e, gf, nsplit, d_rows, e->stream);
 }
 
 // late mix of the first register-blocked chain (zfb_firchain.cuh): allowed when the LO
@@ -1883,6 +1891,14 @@ bool is_pinned(const void *p) {
 // =============================================================================
 extern "C" {
 
+// pipelined batches: e->stream catches up with everything the lanes and fin_stream still hold
+static void join_pending_work(zfb_engine *e) {
+    if (!e->join_pending) return;
+    cudaSetDevice(e->device);
+    cudaStreamWaitEvent(e->stream, e->ev_done, 0);
+    e->join_pending = false;
+}
+
 int zfb_abi_version(void) { return ZFB_ABI_VERSION; }
 
 const char *zfb_build_kind(void) { return ZFB_BUILD_KIND; }
@@ -1949,6 +1965,7 @@ int zfb_create(int device, zfb_engine **out) {
 void zfb_destroy(zfb_engine *e) {
     if (!e) return;
     cudaSetDevice(e->device);
+    if (e->fin_stream) cudaStreamSynchronize(e->fin_stream);     // rows of pipelined batches read the lanes' sums
     for (int i = 0; i < 2; ++i) {
         if (e->lane[i]) zfb_destroy(e->lane[i]);
         e->lane[i] = nullptr;
@@ -1956,6 +1973,11 @@ void zfb_destroy(zfb_engine *e) {
         if (e->ev_fin[i]) cudaEventDestroy(e->ev_fin[i]);
     }
     if (e->ev_slab_in) cudaEventDestroy(e->ev_slab_in);
+    if (e->fin_stream) {
+        cudaStreamSynchronize(e->fin_stream);
+        cudaStreamDestroy(e->fin_stream);
+    }
+    if (e->ev_done) cudaEventDestroy(e->ev_done);
     if (e->own_stream) cudaStreamSynchronize(e->own_stream);
     if (e->copy_stream) cudaStreamSynchronize(e->copy_stream);
     if (e->aux_stream) cudaStreamSynchronize(e->aux_stream);
@@ -2031,6 +2053,7 @@ int zfb_configure(zfb_engine *e, const zfb_config *cfg) {
 
 static int configure_impl(zfb_engine *e, const zfb_config *cfg) {
     std::lock_guard<std::mutex> lk(e->mu);
+    join_pending_work(e);
     if (!cfg) return fail(e, ZFB_EINVAL, "configure: cfg is NULL");
     CK(e, cudaSetDevice(e->device));
     const int N = cfg->fft_size;
@@ -2292,8 +2315,11 @@ static int configure_impl(zfb_engine *e, const zfb_config *cfg) {
 static void setup_lanes(zfb_engine *e) {          // e->mu is held by the caller
     e->lanes_ready = false;
     e->lanes_stale = false;
-    if (e->is_lane || e->slabs < 2 || !e->configured || !e->fast_active || e->precise_active || e->window_host.empty())
+    if (e->is_lane || (e->slabs < 2 && !e->pipeline) || !e->configured || !e->fast_active || e->precise_active ||
+        e->window_host.empty())
         return;
+    if (!e->fin_stream && cudaStreamCreateWithFlags(&e->fin_stream, cudaStreamNonBlocking) != cudaSuccess) return;
+    if (!e->ev_done && cudaEventCreateWithFlags(&e->ev_done, cudaEventDisableTiming) != cudaSuccess) return;
     zfb_config c2 = e->cfg;
     c2.window = e->window_host.data();
     c2.ema_alpha = -1.0;                          // rows are finished by this engine: no EMA state in a lane
@@ -2357,7 +2383,7 @@ static int process_slabs(zfb_engine *e, const void *d_in, int nframes, float *d_
         }
         CK(e, cudaEventRecord(e->ev_lane[i], l->stream));
         CK(e, cudaStreamWaitEvent(e->stream, e->ev_lane[i], 0));
-        rc = finish_rows(e, l, gf, nsplit, d_rows ? d_rows + (size_t)f0 * e->W : nullptr);
+        rc = finish_rows(e, l, gf, nsplit, d_rows ? d_rows + (size_t)f0 * e->W : nullptr, e->stream);
         if (rc != ZFB_OK) break;
         CK(e, cudaEventRecord(e->ev_fin[i], e->stream));
         e->ev_fin_used[i] = true;
@@ -2368,6 +2394,48 @@ static int process_slabs(zfb_engine *e, const void *d_in, int nframes, float *d_
         cudaGetLastError();
     }
     return rc;
+}
+
+// a whole batch on the next lane, its rows finished on fin_stream; e->stream joins later (zfb_join)
+static int process_pipelined(zfb_engine *e, const void *d_in, int nframes, float *d_rows) {
+    const size_t fbytes = (size_t)e->cfg.frame_len * sample_bytes(e->cfg);
+    const int i = e->next_lane;
+    e->next_lane ^= 1;
+    zfb_engine *l = e->lane[i];
+    // the input, and whatever the caller's stream did to the EMA state / ring before this call
+    CK(e, cudaEventRecord(e->ev_slab_in, e->stream));
+    CK(e, cudaStreamWaitEvent(l->stream, e->ev_slab_in, 0));
+    CK(e, cudaStreamWaitEvent(e->fin_stream, e->ev_slab_in, 0));
+    l->profiling = e->profiling;
+    int rc = ZFB_OK;
+    for (int g0 = 0; g0 < nframes && rc == ZFB_OK; g0 += e->group) {
+        const int gf = (nframes - g0 < e->group) ? nframes - g0 : e->group;
+        if (e->ev_fin_used[i]) CK(e, cudaStreamWaitEvent(l->stream, e->ev_fin[i], 0));
+        int nsplit = 1;
+        bool done = false;
+        const uint64_t launches0 = l->counters[2];
+        rc = run_group_front(l, (const char *)d_in + (size_t)g0 * fbytes, gf, nullptr, &nsplit, &done);
+        e->counters[2] += l->counters[2] - launches0;
+        if (rc != ZFB_OK) {
+            e->err = l->err;
+            break;
+        }
+        CK(e, cudaEventRecord(e->ev_lane[i], l->stream));
+        CK(e, cudaStreamWaitEvent(e->fin_stream, e->ev_lane[i], 0));
+        rc = finish_rows(e, l, gf, nsplit, d_rows ? d_rows + (size_t)g0 * e->W : nullptr, e->fin_stream);
+        if (rc != ZFB_OK) break;
+        CK(e, cudaEventRecord(e->ev_fin[i], e->fin_stream));
+        e->ev_fin_used[i] = true;
+    }
+    if (rc != ZFB_OK) {
+        for (int k = 0; k < 2; ++k) cudaStreamSynchronize(e->lane[k]->stream);
+        cudaStreamSynchronize(e->fin_stream);
+        cudaGetLastError();
+        return rc;
+    }
+    CK(e, cudaEventRecord(e->ev_done, e->fin_stream));
+    e->join_pending = true;
+    return ZFB_OK;
 }
 
 int zfb_set_fast_plan(zfb_engine *e, const zfb_fast_plan *plan) {
@@ -2415,6 +2483,19 @@ int zfb_fast_active(const zfb_engine *e) {
     return (e->configured && e->fast_active) ? 1 : 0;
 }
 
+int zfb_join(zfb_engine *e, void *cuda_stream) {
+    if (!e) return ZFB_EINVAL;
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (!e->join_pending) return ZFB_OK;
+    CK(e, cudaSetDevice(e->device));
+    if (cuda_stream && (cudaStream_t)cuda_stream != e->stream) {
+        CK(e, cudaStreamWaitEvent((cudaStream_t)cuda_stream, e->ev_done, 0));
+        return ZFB_OK;                            // e->stream itself still has to join
+    }
+    join_pending_work(e);
+    return ZFB_OK;
+}
+
 int zfb_slab_lanes(const zfb_engine *e) {
     if (!e) return ZFB_EINVAL;
     std::lock_guard<std::mutex> lk(e->mu);
@@ -2424,6 +2505,7 @@ int zfb_slab_lanes(const zfb_engine *e) {
 int zfb_set_stream(zfb_engine *e, void *cuda_stream) {
     if (!e) return ZFB_EINVAL;
     std::lock_guard<std::mutex> lk(e->mu);
+    join_pending_work(e);
     CK(e, cudaSetDevice(e->device));
     CK(e, cudaStreamSynchronize(e->stream));
     e->stream = cuda_stream ? (cudaStream_t)cuda_stream : e->own_stream;
@@ -2447,6 +2529,11 @@ int zfb_set_option(zfb_engine *e, const char *name, long long value) {
     if (strcmp(name, "slabs") == 0) {
         if (value < 0 || value > 2) return fail(e, ZFB_EINVAL, "slabs must be 0, 1 (one lane) or 2");
         e->slabs = (int)value;
+        return ZFB_OK;
+    }
+    if (strcmp(name, "pipeline") == 0) {
+        join_pending_work(e);
+        e->pipeline = value ? 1 : 0;
         return ZFB_OK;
     }
     if (strcmp(name, "slab_min") == 0) {
@@ -2674,6 +2761,7 @@ static int process_device_impl(zfb_engine *e, const void *d_in, int nframes, con
     CK(e, cudaSetDevice(e->device));
     const size_t fbytes = (size_t)e->cfg.frame_len * sample_bytes(e->cfg);
     if (nch > 0) {
+        join_pending_work(e);
         const bool batched = channels_batchable(e);
         if (batched) {
             rc = upload_channels(e, f_demod, nch);
@@ -2682,6 +2770,14 @@ static int process_device_impl(zfb_engine *e, const void *d_in, int nframes, con
         // the counters count frames per channel pass; rows [nch][nframes][W]
         return run_channels(e, d_in, nframes, f_demod, nch, nframes, d_rows, batched);
     }
+    if (!e->is_lane && e->pipeline && nframes >= 1 && e->fast_active && !e->precise_active) {
+        if (e->lanes_stale) setup_lanes(e);
+        if (e->lanes_ready) {
+            e->last_lanes = 2;
+            return process_pipelined(e, d_in, nframes, d_rows);
+        }
+    }
+    join_pending_work(e);
     if (!e->is_lane && e->slabs >= 2 && nframes >= e->slab_min && nframes >= 2 && e->fast_active && !e->precise_active) {
         if (e->lanes_stale) setup_lanes(e);
         if (e->lanes_ready) {
@@ -2709,6 +2805,7 @@ int zfb_process_channels_device(zfb_engine *e, const void *d_in, int nframes, co
                                 float *d_rows) {
     if (!e) return ZFB_EINVAL;
     std::lock_guard<std::mutex> lk(e->mu);
+    join_pending_work(e);
     if (nch < 1) return fail(e, ZFB_EINVAL, "channels: nch must be >= 1");
     return process_device_impl(e, d_in, nframes, f_demod, nch, d_rows);
 }
@@ -2802,6 +2899,7 @@ static int process_host_impl(zfb_engine *e, const void *h_in, int nframes, const
 int zfb_process_host(zfb_engine *e, const void *h_in, int nframes, float *h_rows) {
     if (!e) return ZFB_EINVAL;
     std::lock_guard<std::mutex> lk(e->mu);
+    join_pending_work(e);
     return process_host_impl(e, h_in, nframes, nullptr, 0, h_rows);
 }
 
@@ -2809,6 +2907,7 @@ int zfb_process_channels_host(zfb_engine *e, const void *h_in, int nframes, cons
                               float *h_rows) {
     if (!e) return ZFB_EINVAL;
     std::lock_guard<std::mutex> lk(e->mu);
+    join_pending_work(e);
     if (nch < 1) return fail(e, ZFB_EINVAL, "channels: nch must be >= 1");
     return process_host_impl(e, h_in, nframes, f_demod, nch, h_rows);
 }
@@ -2816,6 +2915,7 @@ int zfb_process_channels_host(zfb_engine *e, const void *h_in, int nframes, cons
 int zfb_synchronize(zfb_engine *e) {
     if (!e) return ZFB_EINVAL;
     std::lock_guard<std::mutex> lk(e->mu);
+    join_pending_work(e);
     CK(e, cudaSetDevice(e->device));
     CK(e, cudaStreamSynchronize(e->stream));
     return ZFB_OK;
@@ -2824,6 +2924,7 @@ int zfb_synchronize(zfb_engine *e) {
 int zfb_debug_read_decimated(zfb_engine *e, float *h_out_iq, int max_samples) {
     if (!e) return ZFB_EINVAL;
     std::lock_guard<std::mutex> lk(e->mu);
+    join_pending_work(e);
     if (!e->configured) return fail(e, ZFB_ESTATE, "engine is not configured");
     if (e->nstages < 1 || e->last_group_frames < 1)
         return fail(e, ZFB_ESTATE, "no decimated chunk available (fft_ratio < 2 or nothing processed)");
@@ -2853,6 +2954,7 @@ static int ring_realloc(zfb_engine *e, int rows, int width) {
 int zfb_ring_configure(zfb_engine *e, int rows) {
     if (!e) return ZFB_EINVAL;
     std::lock_guard<std::mutex> lk(e->mu);
+    join_pending_work(e);
     if (rows < 1) return fail(e, ZFB_EINVAL, "ring rows must be >= 1");
     e->ring_rows_req = rows;
     e->ring_user_W = 0;                             // back to following the configured row width
@@ -2863,6 +2965,7 @@ int zfb_ring_configure(zfb_engine *e, int rows) {
 int zfb_ring_configure_width(zfb_engine *e, int rows, int width) {
     if (!e) return ZFB_EINVAL;
     std::lock_guard<std::mutex> lk(e->mu);
+    join_pending_work(e);
     if (rows < 1) return fail(e, ZFB_EINVAL, "ring rows must be >= 1");
     if (width < 1 || width > (1 << 24)) return fail(e, ZFB_EINVAL, "ring width %d out of range", width);
     e->ring_rows_req = rows;
@@ -2885,6 +2988,7 @@ int64_t zfb_ring_rows_written(const zfb_engine *e) {
 int zfb_read_rows(zfb_engine *e, int age, int nrows, float *h_out) {
     if (!e) return ZFB_EINVAL;
     std::lock_guard<std::mutex> lk(e->mu);
+    join_pending_work(e);
     if (!e->ring.p || e->ring_W < 1) return fail(e, ZFB_ESTATE, "no ring (configure the engine or the ring first)");
     if (age < 0 || nrows < 1 || !h_out) return fail(e, ZFB_EINVAL, "read_rows: bad arguments");
     const int64_t have = e->ring_written < e->ring_rows ? e->ring_written : e->ring_rows;
@@ -2911,6 +3015,7 @@ int zfb_read_rows(zfb_engine *e, int age, int nrows, float *h_out) {
 int zfb_ring_push_rows(zfb_engine *e, const float *h_rows, int nrows) {
     if (!e) return ZFB_EINVAL;
     std::lock_guard<std::mutex> lk(e->mu);
+    join_pending_work(e);
     if (!e->ring.p || e->ring_W < 1) return fail(e, ZFB_ESTATE, "no ring (configure the engine or the ring first)");
     if (!h_rows || nrows < 0) return fail(e, ZFB_EINVAL, "push_rows: bad arguments");
     CK(e, cudaSetDevice(e->device));
@@ -2992,6 +3097,7 @@ int zfb_ring_image(zfb_engine *e, int height, int scroll, int64_t rows_seen, int
                    const uint8_t *lut_rgba, void *out, int out_on_device) {
     if (!e) return ZFB_EINVAL;
     std::lock_guard<std::mutex> lk(e->mu);
+    join_pending_work(e);
     ImageParams p{};
     int rc = image_params(e, height, scroll, rows_seen, p);
     if (rc) return rc;
@@ -3070,6 +3176,7 @@ int zfb_ring_quantiles(zfb_engine *e, int height, int scroll, int64_t rows_seen,
                        double *out_values, int64_t *out_count) {
     if (!e) return ZFB_EINVAL;
     std::lock_guard<std::mutex> lk(e->mu);
+    join_pending_work(e);
     SelectParams s{};
     int rc = image_params(e, height, scroll, rows_seen, s.img);
     if (rc) return rc;
@@ -3244,6 +3351,7 @@ int zfb_samples_commit(zfb_engine *e, int64_t offset, int64_t n) {
 int zfb_samples_process(zfb_engine *e, float *h_row) {
     if (!e) return ZFB_EINVAL;
     std::lock_guard<std::mutex> lk(e->mu);
+    join_pending_work(e);
     if (!e->configured) return fail(e, ZFB_ESTATE, "process: engine is not configured");
     if (!e->sr_host) return fail(e, ZFB_ESTATE, "no sample ring (zfb_samples_create)");
     if (!h_row) return fail(e, ZFB_EINVAL, "process: h_row is NULL");
@@ -3276,6 +3384,7 @@ int zfb_samples_process(zfb_engine *e, float *h_row) {
 int zfb_taper_design(zfb_engine *e, int kind, double p0, double p1, int n, int periodic, double *h_out) {
     if (!e) return ZFB_EINVAL;
     std::lock_guard<std::mutex> lk(e->mu);
+    join_pending_work(e);
     if (kind < 0 || kind >= TAPER_COUNT) return fail(e, ZFB_EINVAL, "taper kind %d is not designed on the device", kind);
     if (n < 1 || n > (1 << 24) || !h_out) return fail(e, ZFB_EINVAL, "taper design: bad arguments");
     if ((kind == TAPER_GAUSSIAN && !(p0 > 0.0)) || (kind == TAPER_GENERAL_GAUSSIAN && !(p1 > 0.0)) ||
@@ -3303,6 +3412,7 @@ int zfb_taper_design(zfb_engine *e, int kind, double p0, double p1, int n, int p
 int zfb_taper_preview(zfb_engine *e, const double *taper, int ntaps, int nfft, float *h_db_out) {
     if (!e) return ZFB_EINVAL;
     std::lock_guard<std::mutex> lk(e->mu);
+    join_pending_work(e);
     if (!taper || !h_db_out || ntaps < 1 || ntaps > 65536 || nfft < ntaps || nfft > (1 << 20))
         return fail(e, ZFB_EINVAL, "taper preview: bad arguments");
     CK(e, cudaSetDevice(e->device));
@@ -3352,6 +3462,7 @@ int zfb_set_profiling(zfb_engine *e, int on) {
 int zfb_get_profile(zfb_engine *e, double ms_out[ZFB_PROF_CLASSES], uint64_t launches_out[ZFB_PROF_CLASSES]) {
     if (!e || !ms_out || !launches_out) return ZFB_EINVAL;
     std::lock_guard<std::mutex> lk(e->mu);
+    join_pending_work(e);
     CK(e, cudaSetDevice(e->device));
     CK(e, cudaStreamSynchronize(e->stream));
     for (int c = 0; c < ZFB_PROF_CLASSES; ++c) { ms_out[c] = 0.0; launches_out[c] = 0; }

@@ -224,6 +224,11 @@ class ZoomPSD:
         """lanes the last ``process_device`` batch ran through (2: cut into slabs)"""
         return int(self._lib.zfb_slab_lanes(self._h))
 
+    def join(self, cuda_stream_ptr: int | None = None):
+        """Pipelined batches (``set_option("pipeline", 1)``): make a stream -- default: the engine's --
+        wait for every ``process_device`` batch handed over so far."""
+        self._check(self._lib.zfb_join(self._h, C.c_void_p(cuda_stream_ptr or 0)), "zfb_join")
+
     def set_group(self, frames_per_group: int):
         self._check(self._lib.zfb_set_group(self._h, int(frames_per_group)), "zfb_set_group")
         self._key = None

@@ -137,7 +137,7 @@ def slabs_equal_one_lane(engine, dev, nframes=7, w=None, n=None):
         assert np.array_equal(got[0], want[0])
     finally:
         engine.set_option("strips_async", 1)
-        engine.set_option("slabs", 2)
+        engine.set_option("slabs", 1)
         engine.set_option("slab_min", 64)
         engine.set_group(0)
         engine.ring_configure(256)
@@ -163,6 +163,56 @@ def ema_batch_independent(engine):
         engine.set_group(0)
         for r in rows[1:]:
             assert np.array_equal(r, rows[0])
+
+
+def pipeline_equals_one_lane(engine, dev, nframes=9, w=None, n=None):
+    """``pipeline`` = 1: whole batches alternate between the lane engines, rows are finished on a
+    stream of the engine's own and the caller's stream joins later (zfb_join).  Rows, EMA across
+    batches, ring, counters: bit-identical to the plain path; other calls join implicitly."""
+    w = w or synth.CFG2
+    n = n or 4096 * 16 * 4 + 1234           # 7 Welch segments: the fp32 path
+    frames = synth.make_frames(w, nframes, n=n)
+    p_in, keep = dev.put(frames)
+    fbytes = frames[0].nbytes
+
+    def run(pipeline, group, calls, host_tail=0):
+        engine.set_option("pipeline", pipeline)
+        engine.set_group(group)
+        engine.ring_configure(4)
+        engine.configure(w.fs, w.fft_size, w.fft_ratio, n, w.window, dtype="u8", flip=True, crop="thread",
+                         ema_alpha=0.3)
+        assert engine.fast_active
+        engine.reset_ema()
+        k0 = engine.counters()
+        p_rows, rows = dev.empty((nframes, engine.row_width))
+        f0 = 0
+        for cnt in calls:
+            engine.process_device(p_in + f0 * fbytes, cnt, p_rows + f0 * engine.row_width * 4)
+            assert engine.slab_lanes == (2 if pipeline else 1)
+            f0 += cnt
+        tail = None
+        if host_tail:                        # a host-path call right behind pipelined batches: implicit join
+            tail = engine.process(frames[:host_tail])
+        else:
+            engine.join()
+        engine.synchronize()
+        k1 = engine.counters()
+        return dev.get(rows)[:f0], engine.read_rows(4), tail, {k: k1[k] - k0[k] for k in ("frames", "samples")}
+
+    try:
+        for host_tail in (0, 2):
+            want = run(0, 0, [nframes - host_tail], host_tail)
+            for group, calls in ((0, [nframes - host_tail]), (0, [3, 1, nframes - host_tail - 4]),
+                                 (2, [5, nframes - host_tail - 5]), (0, [1] * (nframes - host_tail))):
+                got = run(1, group, calls, host_tail)
+                assert np.array_equal(got[0], want[0]), (group, calls)
+                assert np.array_equal(got[1], want[1]), (group, calls)
+                assert (got[2] is None and want[2] is None) or np.array_equal(got[2], want[2])
+                assert got[3] == want[3]
+    finally:
+        engine.set_option("pipeline", 0)
+        engine.set_group(0)
+        engine.ring_configure(256)
 
 
 def ring_behaviour(engine):

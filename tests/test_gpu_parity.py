@@ -63,6 +63,49 @@ def test_slabs_equal_one_lane_full_size(gpu_engine):
     assert np.isfinite(rows[2]).all()
 
 
+def test_pipeline_equals_one_lane(gpu_engine):
+    es.pipeline_equals_one_lane(gpu_engine, es.TorchDevice())
+
+
+def test_pipeline_full_size_and_join_stream(gpu_engine):
+    """cfg2 at full frame length: 12 pipelined batches of 48 frames back to back (both lanes busy,
+    EMA carried on the finishing stream), a consumer on ANOTHER stream ordered by zfb_join(stream);
+    rows equal the plain path's bit for bit."""
+    import torch
+    w = synth.CFG2
+    nb, F = 12, 48
+    frames = synth.make_frames(w, nb * F, distinct=nb * F)
+    d_in = torch.from_numpy(frames).cuda()
+    fbytes = frames[0].nbytes
+    out = {}
+    side = torch.cuda.Stream()
+    for pipeline in (0, 1):
+        gpu_engine.set_option("pipeline", pipeline)
+        gpu_engine.configure(w.fs, w.fft_size, w.fft_ratio, w.frame_len, w.window, dtype="u8", flip=True,
+                             crop="thread", ema_alpha=w.ema_alpha)
+        gpu_engine.reset_ema()
+        W = gpu_engine.row_width
+        d_rows = torch.zeros((nb * F, W), dtype=torch.float32, device="cuda")
+        copies = []
+        torch.cuda.synchronize()
+        for b in range(nb):
+            gpu_engine.process_device(d_in.data_ptr() + b * F * fbytes, F, d_rows.data_ptr() + b * F * W * 4)
+            if pipeline:
+                gpu_engine.join(side.cuda_stream)            # only the side stream waits
+                with torch.cuda.stream(side):
+                    copies.append(d_rows[b * F:(b + 1) * F].clone())
+        if pipeline:
+            side.synchronize()
+            assert gpu_engine.slab_lanes == 2
+            got_side = torch.cat(copies, 0).cpu().numpy()
+        gpu_engine.synchronize()
+        out[pipeline] = d_rows.cpu().numpy()
+    gpu_engine.set_option("pipeline", 0)
+    assert np.array_equal(out[0], out[1])
+    assert np.array_equal(got_side, out[0])
+    assert np.isfinite(out[1]).all()
+
+
 def test_batch_equals_single(gpu_engine, gpu_lib):
     es.batch_equals_single(gpu_engine, gpu_lib)
 
