@@ -325,7 +325,9 @@ def run_b200(args, w):
     # bench joins (zfb_join) where something consumes them -- the NCCL gather, the end of a timed leg
     # (auto: on for 1- and 2-byte wire formats; complex64 input loses -- cfg1 166.7 -> 147.9 Gs/s, the two
     # lanes' streams evict each other from L2 -- profiles/r02ac_*)
-    pipelined = (args.pipeline == 1 or (args.pipeline < 0 and w.dtype in ("u8", "cs16"))) and w.name != "cfg4"
+    # cfg4 (64 virtual receivers: 64x the compute per byte, launches that fill the GPU): no change, 205.1 vs
+    # 204.7 G channel-samples/s (profiles/r02ae_*) -- left off
+    pipelined = args.pipeline == 1 or (args.pipeline < 0 and w.dtype in ("u8", "cs16"))
     eng.set_option("pipeline", 1 if pipelined else 0)
     for it in args.sets or []:
         name, _, val = it.partition("=")
@@ -419,6 +421,7 @@ def run_b200(args, w):
                 d_feed.copy_(h_in, non_blocking=True)
             dist.broadcast(d_feed, src=0)            # on `stream` (the current stream)
             eng.process_channels_device(d_feed.data_ptr(), F, centres, d_rows_e2e.data_ptr())
+            join_device()
             h_rows.copy_(d_rows_e2e, non_blocking=True)
             stream.synchronize()                     # rows are on the host, like eng.process()
         elif centres is None:                        # H2D + kernels + D2H, returns when rows are on the host

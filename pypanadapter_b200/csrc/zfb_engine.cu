@@ -2751,6 +2751,9 @@ static int check_channels(zfb_engine *e, const double *f_demod, int nch) {
     return ZFB_OK;
 }
 
+static int process_pipelined_channels(zfb_engine *e, const void *d_in, int nframes, const double *f_demod, int nch,
+                                      float *d_rows);
+
 // nch == 0: the configured f_demod; rows [nframes][W].  nch > 0: rows [nch][nframes][W]
 static int process_device_impl(zfb_engine *e, const void *d_in, int nframes, const double *f_demod, int nch,
                                float *d_rows) {
@@ -2761,8 +2764,15 @@ static int process_device_impl(zfb_engine *e, const void *d_in, int nframes, con
     CK(e, cudaSetDevice(e->device));
     const size_t fbytes = (size_t)e->cfg.frame_len * sample_bytes(e->cfg);
     if (nch > 0) {
-        join_pending_work(e);
         const bool batched = channels_batchable(e);
+        if (!e->is_lane && e->pipeline && batched && nframes >= 1) {
+            if (e->lanes_stale) setup_lanes(e);
+            if (e->lanes_ready) {
+                e->last_lanes = 2;
+                return process_pipelined_channels(e, d_in, nframes, f_demod, nch, d_rows);
+            }
+        }
+        join_pending_work(e);
         if (batched) {
             rc = upload_channels(e, f_demod, nch);
             if (rc) return rc;
@@ -2793,6 +2803,36 @@ static int process_device_impl(zfb_engine *e, const void *d_in, int nframes, con
         if (rc) break;
     }
     return rc;
+}
+
+// virtual receivers (channel-batched launches; no EMA, nothing appended to the ring, so the rows need
+// no ordering among batches): the whole batch, finalisation included, on the next lane's stream
+static int process_pipelined_channels(zfb_engine *e, const void *d_in, int nframes, const double *f_demod, int nch,
+                                      float *d_rows) {
+    const int i = e->next_lane;
+    e->next_lane ^= 1;
+    zfb_engine *l = e->lane[i];
+    CK(e, cudaEventRecord(e->ev_slab_in, e->stream));
+    CK(e, cudaStreamWaitEvent(l->stream, e->ev_slab_in, 0));
+    l->profiling = e->profiling;
+    uint64_t c0[5];
+    memcpy(c0, l->counters, sizeof c0);
+    const int rc = process_device_impl(l, d_in, nframes, f_demod, nch, d_rows);
+    for (int k = 0; k < 5; ++k) e->counters[k] += l->counters[k] - c0[k];
+    e->last_front = l;
+    e->last_group_frames = l->last_group_frames;
+    if (rc != ZFB_OK) {
+        e->err = l->err;
+        cudaStreamSynchronize(l->stream);
+        cudaGetLastError();
+        return rc;
+    }
+    // fin_stream collects the lanes' completions in the order of the calls: ev_done covers all of them
+    CK(e, cudaEventRecord(e->ev_lane[i], l->stream));
+    CK(e, cudaStreamWaitEvent(e->fin_stream, e->ev_lane[i], 0));
+    CK(e, cudaEventRecord(e->ev_done, e->fin_stream));
+    e->join_pending = true;
+    return ZFB_OK;
 }
 
 int zfb_process_device(zfb_engine *e, const void *d_in, int nframes, float *d_rows) {

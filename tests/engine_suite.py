@@ -535,6 +535,51 @@ def multi_channel(engine):
         engine.process_channels(x, centres)
 
 
+def pipeline_channels_equal_plain(engine, dev):
+    """Virtual receivers through pipelined batches (each batch, finalisation included, on the next
+    lane's stream; zfb_join orders the consumer) == the plain device path, bit for bit; plain
+    pipelined batches in between keep their own order."""
+    fs, N, R = 20e6, 1024, 16
+    n = N * R * 8
+    centres = np.array([-9.5e6, -3.1e6, 1.0, 4.44e6, 9.5e6])
+    k = np.arange(n)
+    rng = np.random.default_rng(22)
+    nf = 6
+    x = 1e-3 * (rng.standard_normal((nf, n)) + 1j * rng.standard_normal((nf, n)))
+    for fc in centres:
+        x = x + 0.1 * np.exp(2j * np.pi * ((fc + 7000.0) / fs) * k)
+    x = np.ascontiguousarray(x.astype(np.complex64))
+    p_in, keep = dev.put(x)
+    fbytes = x[0].nbytes
+
+    def run(pipeline):
+        engine.set_option("pipeline", pipeline)
+        engine.configure(fs, N, R, n, "hamming", crop="thread", mode="fast")
+        W = engine.row_width
+        outs = []
+        for f0, cnt in ((0, 2), (2, 1), (3, 3)):
+            p_rows, rows = dev.empty((len(centres), cnt, W))
+            engine.process_channels_device(p_in + f0 * fbytes, cnt, centres, p_rows)
+            outs.append(rows)
+            if f0 == 2:                      # a plain batch between two channel batches
+                p_one, one = dev.empty((cnt, W))
+                engine.process_device(p_in + f0 * fbytes, cnt, p_one)
+                outs.append(one)
+        assert engine.slab_lanes == (2 if pipeline else 1)
+        engine.join()
+        engine.synchronize()
+        return [dev.get(o) for o in outs]
+
+    try:
+        want = run(0)
+        got = run(1)
+        for a, b in zip(want, got):
+            assert np.array_equal(a, b)
+        assert np.isfinite(got[0]).all() and got[0].max() > np.median(got[0]) + 20.0      # the tones stand out
+    finally:
+        engine.set_option("pipeline", 0)
+
+
 def random_configs(engine, seed, count):
     """Seeded sweep over frame length (ragged/odd), N, R, window, wire dtype, flip,
     crop, f_demod and decimator mode against the oracle."""

@@ -31,6 +31,10 @@ def test_pipeline_equals_one_lane(emu_engine):
     es.pipeline_equals_one_lane(emu_engine, es.HostAsDevice())
 
 
+def test_pipeline_channels_equal_plain(emu_engine):
+    es.pipeline_channels_equal_plain(emu_engine, es.HostAsDevice())
+
+
 def test_ema_batch_independent(emu_engine):
     es.ema_batch_independent(emu_engine)
 
