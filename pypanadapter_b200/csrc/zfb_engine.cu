@@ -2318,6 +2318,8 @@ static void setup_lanes(zfb_engine *e) {          // e->mu is held by the caller
     if (e->is_lane || (e->slabs < 2 && !e->pipeline) || !e->configured || !e->fast_active || e->precise_active ||
         e->window_host.empty())
         return;
+    // re-planning a lane may free workspaces that rows of earlier batches are still read from
+    if (e->fin_stream) cudaStreamSynchronize(e->fin_stream);
     if (!e->fin_stream && cudaStreamCreateWithFlags(&e->fin_stream, cudaStreamNonBlocking) != cudaSuccess) return;
     if (!e->ev_done && cudaEventCreateWithFlags(&e->ev_done, cudaEventDisableTiming) != cudaSuccess) return;
     zfb_config c2 = e->cfg;
@@ -2347,7 +2349,7 @@ static void setup_lanes(zfb_engine *e) {          // e->mu is held by the caller
             return;
         for (cudaEvent_t *ev : {&e->ev_lane[i], &e->ev_fin[i]})
             if (!*ev && cudaEventCreateWithFlags(ev, cudaEventDisableTiming) != cudaSuccess) return;
-        e->ev_fin_used[i] = false;
+        // ev_fin_used[i] stays: rows of an earlier batch may still be read from this lane's sums
     }
     cudaGetLastError();
     e->lanes_ready = true;

@@ -580,6 +580,74 @@ def pipeline_channels_equal_plain(engine, dev):
         engine.set_option("pipeline", 0)
 
 
+def pipeline_random_ops(engine, dev, seed=0, nops=40):
+    """A seeded random sequence of calls -- device batches (pipelined or not), host batches, virtual
+    receivers, ring reads, EMA resets, group and frame-length changes -- gives the same outputs, in the
+    same order, with ``pipeline`` = 1 as with 0: every call that is not a pipelined batch joins first."""
+    w = synth.CFG2
+    lens = (4096 * 16 * 4 + 1234, 4096 * 16 * 5)
+    nf = 6
+    frames = {n: synth.make_frames(w, nf, n=n) for n in lens}
+    dptr = {n: dev.put(frames[n]) for n in lens}
+    centres = np.array([-3.1e5, 1.0, 4.44e5])
+
+    def run(pipeline):
+        rng = np.random.default_rng(seed)
+        engine.set_option("pipeline", pipeline)
+        engine.set_group(0)
+        state = {"n": lens[0], "ema": 0.3}
+
+        def conf():
+            engine.configure(w.fs, w.fft_size, w.fft_ratio, state["n"], w.window, dtype="u8", flip=True,
+                             crop="thread", ema_alpha=state["ema"])
+        conf()
+        engine.ring_configure(4)
+        engine.ring_configure(8)                         # a ring of another size starts empty
+        assert engine.rows_written == 0
+        engine.reset_ema()
+        outs, pending = [], []
+        for _ in range(nops):
+            op = int(rng.integers(0, 9))
+            n = state["n"]
+            a = int(rng.integers(0, nf - 1))
+            cnt = int(rng.integers(1, nf - a + 1))
+            if op <= 3:                                  # device batch
+                p_rows, rows = dev.empty((cnt, engine.row_width))
+                engine.process_device(dptr[n][0] + a * frames[n][0].nbytes, cnt, p_rows)
+                pending.append(rows)
+            elif op == 4:                                # host batch (joins)
+                outs.append(engine.process(frames[n][a:a + cnt]))
+            elif op == 5 and engine.rows_written >= 2:   # ring read (joins)
+                outs.append(engine.read_rows(2))
+            elif op == 6:
+                engine.reset_ema()
+            elif op == 7:                                # group / frame length / EMA on-off
+                engine.set_group(int(rng.choice([0, 2, 3])))
+                state["n"] = lens[int(rng.integers(0, 2))]
+                state["ema"] = None if rng.random() < 0.4 else 0.3
+                conf()
+            elif op == 8 and state["ema"] is None:       # virtual receivers on the device
+                p_rows, rows = dev.empty((len(centres), cnt, engine.row_width))
+                engine.process_channels_device(dptr[n][0] + a * frames[n][0].nbytes, cnt, centres, p_rows)
+                pending.append(rows)
+        engine.join()
+        engine.synchronize()
+        outs.extend(dev.get(r) for r in pending)
+        outs.append(engine.read_rows(min(8, engine.rows_written)) if engine.rows_written else np.zeros(1))
+        return outs
+
+    try:
+        want = run(0)
+        got = run(1)
+        assert len(want) == len(got)
+        for i, (a, b) in enumerate(zip(want, got)):
+            assert a.shape == b.shape and np.array_equal(a, b), i
+    finally:
+        engine.set_option("pipeline", 0)
+        engine.set_group(0)
+        engine.ring_configure(256)
+
+
 def random_configs(engine, seed, count):
     """Seeded sweep over frame length (ragged/odd), N, R, window, wire dtype, flip,
     crop, f_demod and decimator mode against the oracle."""

@@ -35,6 +35,11 @@ def test_pipeline_channels_equal_plain(emu_engine):
     es.pipeline_channels_equal_plain(emu_engine, es.HostAsDevice())
 
 
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_pipeline_random_ops(emu_engine, seed):
+    es.pipeline_random_ops(emu_engine, es.HostAsDevice(), seed=seed, nops=30)
+
+
 def test_ema_batch_independent(emu_engine):
     es.ema_batch_independent(emu_engine)
 

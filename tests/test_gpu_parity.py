@@ -71,6 +71,11 @@ def test_pipeline_channels_equal_plain(gpu_engine):
     es.pipeline_channels_equal_plain(gpu_engine, es.TorchDevice())
 
 
+@pytest.mark.parametrize("seed", range(6))
+def test_pipeline_random_ops(gpu_engine, seed):
+    es.pipeline_random_ops(gpu_engine, es.TorchDevice(), seed=seed, nops=60)
+
+
 def test_pipeline_full_size_and_join_stream(gpu_engine):
     """cfg2 at full frame length: 12 pipelined batches of 48 frames back to back (both lanes busy,
     EMA carried on the finishing stream), a consumer on ANOTHER stream ordered by zfb_join(stream);
