@@ -264,7 +264,7 @@ def run_b200(args, w):
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = host_cores()
-        per_core = 12                   # ~20 s of CPU work in all
+        per_core = 32                   # ~20 s of CPU work in all (16 cores x 1.4 s; 12 per core was 8.7 core-seconds)
         v, dt = cpu_throughput(w, cores * per_core, cores)
         cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                         "sample": "%d frames of %d samples (%d per core) through the oracle port "
