@@ -130,6 +130,8 @@ struct zfb_engine {
     int wf_sparse_bin[WF_SPARSE_MAX] = {0};
     float2 wf_sparse_val[WF_SPARSE_MAX] = {};
     int welch_prune = 2;               // 0: all bins accumulated; 1: only keepable ones; 2: + 3 CTAs/SM where it fits
+    int big_cluster = 0;               // zfb_set_option("big_cluster"): N = 65536 in one pass over a 16-CTA cluster (DSMEM)
+    int big_cluster_ok = -1;           // -1: not probed yet; 0: the device cannot hold such a cluster; 1: it can
     int fir_generic = 0;               // 1: never use the register-blocked FIR kernel (tests)
     int fir_smem_pad = 0;              // zfb_set_option("fir_smem_pad"): bytes (measurement)
     int fir_threads = 128;             // zfb_set_option("fir_threads"): 256 or 128 threads per CTA of fir_run_kernel
@@ -661,6 +663,21 @@ int setup_device_once(zfb_engine *e) {
             pc.zi[k][1] = z2;
         }
         CK(e, cudaMemcpyToSymbol(c_px, &pc, sizeof pc));
+    }
+    // the single-pass 65536-point kernel: > 48 KB of dynamic shared memory, clusters of 16 CTAs
+    // (above the portable 8); failures here only switch that path off
+    {
+        bool ok = true;
+        const void *fns[6] = {(const void *)big_cluster_kernel<KIND_U8_RAW, false>, (const void *)big_cluster_kernel<KIND_C64_RAW, false>,
+                              (const void *)big_cluster_kernel<KIND_C64_MID, false>, (const void *)big_cluster_kernel<KIND_U8_RAW, true>,
+                              (const void *)big_cluster_kernel<KIND_C64_RAW, true>, (const void *)big_cluster_kernel<KIND_C64_MID, true>};
+        for (const void *fn : fns) {
+            ok &= cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BIGC_SMEM) == cudaSuccess;
+            ok &= cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+        }
+        if (ok) ok = cluster_max_active(fns[1], dim3(BIGC_CX, 1, 1), dim3(BIGC_NT), BIGC_CX, BIGC_SMEM) >= 1;
+        cudaGetLastError();
+        e->big_cluster_ok = ok ? 1 : 0;
     }
     for (int kind = 0; kind < 3; ++kind)
         for (int nt : {NTHR_BIG, NTHR_SMALL})
@@ -1535,6 +1552,48 @@ int run_group_front(zfb_engine *e, const void *d_in, int gf, float *d_rows, int 
         r.partial = r.scratch + ((size_t)e->group * (size_t)e->nseg << e->log2N);
         r.means = r.partial + (size_t)e->group * (size_t)e->nseg * (size_t)(S / 256);
         r.dc = r.means + (size_t)e->group * (size_t)e->nseg;
+        if (e->big_cluster && e->big_cluster_ok == 1 && e->log2N == 16) {
+            // one pass: clusters of 16 CTAs exchange the radix-16 blocks through shared memory
+            BigClusterParams cp{};
+            cp.r = r;
+            cp.twiddle_sub = (const float2 *)e->twiddle_sub.p;
+            cp.pow16 = (float *)e->pow16.p;
+            cp.seg_per_split = per;
+            cp.nsplit = ns16;
+            cp.wf16 = (const float2 *)e->winfft16.p;
+            cp.wf_n = e->wf_sparse_n;
+            cp.wf_bin = (const int *)e->wf_sparse.p;
+            cp.wf_val = (const float2 *)((const char *)e->wf_sparse.p + WF_SPARSE_MAX * sizeof(int));
+            const int prc = prof_begin(e, 16);
+            const dim3 gc((unsigned)BIGC_CX, (unsigned)ns16, (unsigned)gf);
+            if (kind == KIND_C64_RAW) {
+                ZFB_LAUNCH(big_dc_kernel<KIND_C64_RAW>, dim3((unsigned)gf), dim3(1024), 0, st, r);
+                if (e->big_cluster == 2) CK(e, ZFB_LAUNCH_CLUSTER((big_cluster_kernel<KIND_C64_RAW, true>), gc, dim3(BIGC_NT), BIGC_CX, BIGC_SMEM, st, cp));
+                else CK(e, ZFB_LAUNCH_CLUSTER((big_cluster_kernel<KIND_C64_RAW, false>), gc, dim3(BIGC_NT), BIGC_CX, BIGC_SMEM, st, cp));
+            } else if (kind == KIND_U8_RAW) {
+                ZFB_LAUNCH(big_dc_kernel<KIND_U8_RAW>, dim3((unsigned)gf), dim3(1024), 0, st, r);
+                if (e->big_cluster == 2) CK(e, ZFB_LAUNCH_CLUSTER((big_cluster_kernel<KIND_U8_RAW, true>), gc, dim3(BIGC_NT), BIGC_CX, BIGC_SMEM, st, cp));
+                else CK(e, ZFB_LAUNCH_CLUSTER((big_cluster_kernel<KIND_U8_RAW, false>), gc, dim3(BIGC_NT), BIGC_CX, BIGC_SMEM, st, cp));
+            } else {
+                ZFB_LAUNCH(big_dc_kernel<KIND_C64_MID>, dim3((unsigned)gf), dim3(1024), 0, st, r);
+                if (e->big_cluster == 2) CK(e, ZFB_LAUNCH_CLUSTER((big_cluster_kernel<KIND_C64_MID, true>), gc, dim3(BIGC_NT), BIGC_CX, BIGC_SMEM, st, cp));
+                else CK(e, ZFB_LAUNCH_CLUSTER((big_cluster_kernel<KIND_C64_MID, false>), gc, dim3(BIGC_NT), BIGC_CX, BIGC_SMEM, st, cp));
+            }
+            prof_end(e, prc);
+            const int prg = prof_begin(e, 17);
+            BigGatherParams g{};
+            g.pow16 = (const float *)e->pow16.p;
+            g.pow_out = (float *)e->pow.p;
+            g.log2N = e->log2N;
+            g.nsplit = ns16;
+            g.W = e->W;
+            g.frames = gf;
+            const long long cellsg = (long long)gf * e->W;
+            ZFB_LAUNCH(big_gather_kernel, dim3((unsigned)((cellsg + 255) / 256)), dim3(256), 0, st, g);
+            prof_end(e, prg);
+            e->counters[2] += 3;
+            nsplit = 1;
+        } else {
         const int pr = prof_begin(e, 16);
         const dim3 gr((unsigned)(S / 256), (unsigned)e->nseg, (unsigned)gf);
         if (kind == KIND_C64_RAW) {
@@ -1586,6 +1645,7 @@ int run_group_front(zfb_engine *e, const void *d_in, int gf, float *d_rows, int 
         prof_end(e, pr2);
         e->counters[2] += 5;
         nsplit = 1;
+        }
     } else {
         int want = e->welch_splits > 0 ? e->welch_splits : 4;
         if (want > e->nseg) want = e->nseg;
@@ -2640,6 +2700,11 @@ int zfb_set_option(zfb_engine *e, const char *name, long long value) {
     if (strcmp(name, "fir_threads") == 0) {
         if (value != 128 && value != FIR_NT) return fail(e, ZFB_EINVAL, "fir_threads must be 128 or %d", FIR_NT);
         e->fir_threads = (int)value;
+        return ZFB_OK;
+    }
+    if (strcmp(name, "big_cluster") == 0) {
+        if (value < 0 || value > 2) return fail(e, ZFB_EINVAL, "big_cluster must be 0, 1 or 2 (split-phase barrier with prefetch)");
+        e->big_cluster = (int)value;
         return ZFB_OK;
     }
     if (strcmp(name, "fir_generic") == 0) {

@@ -648,6 +648,38 @@ def pipeline_random_ops(engine, dev, seed=0, nops=40):
         engine.ring_configure(256)
 
 
+def big_cluster_equals_scratch(engine, nframes=3):
+    """N = 65536 in one pass over a 16-CTA cluster (option ``big_cluster``; blocks of the radix-16
+    front pass exchanged through distributed shared memory) == the two-kernel path through the
+    scratch buffer, bit for bit (same arithmetic, only the data movement differs); and parity against
+    the oracle.  Sparse (hann) and dense (kaiser) FFT(window) tables, uint8 + flip and complex64."""
+    fs, N = 2.4e6, 65536
+    for window, dtype, nsegs in (("hann", "c64", 7), (("kaiser", 8.6), "c64", 3), ("hamming", "u8", 4)):
+        n = N * (nsegs + 1) // 2 + 321
+        xs = []
+        for i in range(nframes):
+            x = gc.tone_noise(n, fs, [(0.11 * fs, 0.3), (-0.23 * fs, 0.02)], 2e-3, 4300 + i, np.complex64)
+            xs.append((x + np.complex64(0.2 - 0.1j)).astype(np.complex64) * np.complex64(0.6))
+        x = np.stack(xs)
+        wire = np.stack([synth.quantise_u8(f) for f in x]) if dtype == "u8" else x
+        rows = {}
+        try:
+            engine.set_option("precise", 0)                  # keep few-segment rows on the fp32 path
+            for on in (0, 1, 2):                             # 2: split-phase barrier, next segment prefetched
+                engine.set_option("big_cluster", on)
+                engine.configure(fs, N, 1, n, window, dtype=dtype, flip=(dtype == "u8"), crop=None)
+                rows[on] = engine.process(wire)
+        finally:
+            engine.set_option("big_cluster", 0)
+            engine.set_option("precise", -1)
+        assert np.array_equal(rows[0], rows[1]), (window, dtype)
+        assert np.array_equal(rows[0], rows[2]), (window, dtype)
+        if dtype == "c64":
+            want = zo.zoom_psd(x[0], fs, N, 1, window, crop=None)
+            parity.assert_row_parity(rows[1][0].astype(np.float64), want, parity.floor_db20(fs, window, N, False) + 30.0,
+                                     "big cluster %s" % (window,))
+
+
 def random_configs(engine, seed, count):
     """Seeded sweep over frame length (ragged/odd), N, R, window, wire dtype, flip,
     crop, f_demod and decimator mode against the oracle."""

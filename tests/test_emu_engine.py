@@ -40,6 +40,10 @@ def test_pipeline_random_ops(emu_engine, seed):
     es.pipeline_random_ops(emu_engine, es.HostAsDevice(), seed=seed, nops=30)
 
 
+def test_big_cluster_equals_scratch(emu_engine):
+    es.big_cluster_equals_scratch(emu_engine, nframes=2)
+
+
 def test_ema_batch_independent(emu_engine):
     es.ema_batch_independent(emu_engine)
 

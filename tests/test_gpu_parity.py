@@ -115,6 +115,10 @@ def test_pipeline_full_size_and_join_stream(gpu_engine):
     assert np.isfinite(out[1]).all()
 
 
+def test_big_cluster_equals_scratch(gpu_engine):
+    es.big_cluster_equals_scratch(gpu_engine, nframes=5)
+
+
 def test_batch_equals_single(gpu_engine, gpu_lib):
     es.batch_equals_single(gpu_engine, gpu_lib)
 
