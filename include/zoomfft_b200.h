@@ -164,6 +164,10 @@ int  zfb_reset_ema(zfb_engine *e);
  * two lane engines (own workspaces and streams) at the same time, the rows
  * finished in frame order on the engine's stream -- bit-identical to one lane.
  * "pipeline": see zfb_join.
+ * "big_cluster" = 0 (default) | 1 | 2: N = 65536 in one pass over clusters of
+ * 16 CTAs exchanging the radix-16 blocks through distributed shared memory
+ * (2: split-phase cluster barrier with the next segment prefetched); rows are
+ * bit-identical to the default two-kernel path, which measured faster.
  * Unknown names: ZFB_EINVAL. */
 int  zfb_set_option(zfb_engine *e, const char *name, long long value);
 /* Lanes the last zfb_process_device batch ran through: 2 (slabs, pipeline) or 1. */
