@@ -164,6 +164,9 @@ int  zfb_reset_ema(zfb_engine *e);
  * two lane engines (own workspaces and streams) at the same time, the rows
  * finished in frame order on the engine's stream -- bit-identical to one lane.
  * "pipeline": see zfb_join.
+ * "host_taper" = 1 (default): zfb_process_host cuts a batch into sub-groups
+ * that halve towards its end (copies overlap compute; only the last, smallest
+ * sub-group's kernels are left after the last copy); 0: four equal sub-groups.
  * "big_cluster" = 0 (default) | 1 | 2: N = 65536 in one pass over clusters of
  * 16 CTAs exchanging the radix-16 blocks through distributed shared memory
  * (2: split-phase cluster barrier with the next segment prefetched); rows are

@@ -130,6 +130,7 @@ struct zfb_engine {
     int wf_sparse_bin[WF_SPARSE_MAX] = {0};
     float2 wf_sparse_val[WF_SPARSE_MAX] = {};
     int welch_prune = 2;               // 0: all bins accumulated; 1: only keepable ones; 2: + 3 CTAs/SM where it fits
+    int host_taper = 1;                // zfb_set_option("host_taper"): host batches end in ever smaller sub-groups
     int big_cluster = 0;               // zfb_set_option("big_cluster"): N = 65536 in one pass over a 16-CTA cluster (DSMEM)
     int big_cluster_ok = -1;           // -1: not probed yet; 0: the device cannot hold such a cluster; 1: it can
     int fir_generic = 0;               // 1: never use the register-blocked FIR kernel (tests)
@@ -2702,6 +2703,10 @@ int zfb_set_option(zfb_engine *e, const char *name, long long value) {
         e->fir_threads = (int)value;
         return ZFB_OK;
     }
+    if (strcmp(name, "host_taper") == 0) {
+        e->host_taper = value ? 1 : 0;
+        return ZFB_OK;
+    }
     if (strcmp(name, "big_cluster") == 0) {
         if (value < 0 || value > 2) return fail(e, ZFB_EINVAL, "big_cluster must be 0, 1 or 2 (split-phase barrier with prefetch)");
         e->big_cluster = (int)value;
@@ -2961,8 +2966,17 @@ static int process_host_impl(zfb_engine *e, const void *h_in, int nframes, const
     }
 
     int it = 0;
-    for (int g0 = 0; g0 < nframes && rc == ZFB_OK; g0 += hg, ++it) {
-        const int gf = (nframes - g0 < hg) ? nframes - g0 : hg;
+    // The copies run back to back; what the call still pays after the last of them is the compute of
+    // the last sub-group -- so the sub-groups taper towards the end (half of what is left, down to 8
+    // frames): 128 128 128 64 32 16 8 8 for 512 frames.  Rows do not depend on the cut.
+    int gf = 0;
+    for (int g0 = 0; g0 < nframes && rc == ZFB_OK; g0 += gf, ++it) {
+        const int left = nframes - g0;
+        gf = left < hg ? left : hg;
+        if (e->host_taper && left <= 2 * hg && left > 8) {
+            gf = (left + 1) / 2;
+            if (gf > hg) gf = hg;
+        }
         const int slot = it & 1;
         const char *src = (const char *)h_in + (size_t)g0 * fbytes;
         const size_t bytes = (size_t)gf * fbytes;
