@@ -291,6 +291,24 @@ def error_paths(engine):
         engine.ring_quantiles(16, 1, 1, [1.5])                       # quantile outside [0, 1]
     with pytest.raises(ZoomFFTError):
         engine.set_option("no_such_knob", 1)
+    for name, bad in (("slabs", 3), ("slab_min", 1), ("big_cluster", 3), ("welch_splits", 17)):
+        with pytest.raises(ZoomFFTError):
+            engine.set_option(name, bad)
+    # pipelined batches fall back to the plain path where there are no lanes (mode exact, fft_ratio 2):
+    # the batch is ordered on the engine's stream at once and zfb_join has nothing to wait for
+    engine.set_option("pipeline", 1)
+    try:
+        engine.configure(2.4e6, 64, 2, 256, "hamming")
+        x = np.ones((3, 256), dtype=np.complex64)
+        rows = np.zeros((3, engine.row_width), dtype=np.float32)
+        if engine._lib.zfb_build_kind() == b"emulated":              # host memory is device memory there
+            engine.process_device(x.ctypes.data, 3, rows.ctypes.data)
+            assert engine.slab_lanes == 1
+        engine.join()
+        engine.join()
+        engine.synchronize()
+    finally:
+        engine.set_option("pipeline", 0)
     # unknown wire format / decimator mode: rejected before anything is planned
     with pytest.raises(ValueError):
         engine.configure(2.4e6, 64, 2, 256, "hamming", dtype="cf64")
