@@ -179,7 +179,7 @@ def pipeline_equals_one_lane(engine, dev, nframes=9, w=None, n=None):
         engine.set_option("pipeline", pipeline)
         engine.set_group(group)
         engine.ring_configure(4)
-        engine.configure(w.fs, w.fft_size, w.fft_ratio, n, w.window, dtype="u8", flip=True, crop="thread",
+        engine.configure(w.fs, w.fft_size, w.fft_ratio, n, w.window, dtype=w.dtype, flip=w.flip, crop="thread",
                          ema_alpha=0.3)
         assert engine.fast_active
         engine.reset_ema()

@@ -31,6 +31,13 @@ def test_pipeline_equals_one_lane(emu_engine):
     es.pipeline_equals_one_lane(emu_engine, es.HostAsDevice())
 
 
+def test_pipeline_equals_one_lane_other_wire_formats(emu_engine):
+    # int16 IQ read by the FIR interior itself (each lane widens its own chunk ends), complex64
+    from pypanadapter_b200 import synth
+    es.pipeline_equals_one_lane(emu_engine, es.HostAsDevice(), nframes=9, w=synth.CFG2_CS16)
+    es.pipeline_equals_one_lane(emu_engine, es.HostAsDevice(), nframes=9, w=synth.CFG1, n=2048 * 8 * 4 + 77)
+
+
 def test_pipeline_channels_equal_plain(emu_engine):
     es.pipeline_channels_equal_plain(emu_engine, es.HostAsDevice())
 
