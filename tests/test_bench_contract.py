@@ -52,3 +52,30 @@ def test_gpu_arm_has_no_cpu_fallback():
         pytest.skip("a CUDA device is present")
     r = _run(["--steps", "1", "--warmup", "3", "--no-cpu-baseline"])
     assert r.returncode != 0 and "no CPU fallback" in (r.stdout + r.stderr)
+
+
+def test_committed_gpu_arm_line_carries_the_contract():
+    """The line the GPU arm printed on the B200 for the build the round ends on (profiles/r02am_*):
+    every key the bench contract names, with consistent arithmetic."""
+    with open(os.path.join(ROOT, "profiles", "r02am_bench_cfg2.json")) as f:
+        line = json.loads([ln for ln in f if ln.startswith("{")][-1])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+              "scaling", "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "roofline",
+              "roofline_fp32", "cpu_baseline", "clocks"):
+        assert k in line, k
+    assert line["higher_is_better"] is True and line["scaling"] == "weak" and line["vs_baseline"] is None
+    assert line["data"] == "synthetic" and line["config"]["workload"].startswith("cfg2") and "model" not in line["config"]
+    assert line["warmup"] >= 3 and line["n_gpus"] == 1 and line["gpu_launches"] > 0
+    e = line["e2e"]
+    assert e["value"] > 0 and e["unit"] == line["unit"] and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0
+    assert e["value"] < line["value"]                       # host buffers cross PCIe: never the device-resident figure
+    r = line["roofline"]
+    assert r["bound"] in ("hbm", "tensor") and r["unit"] == "GB/s" and r["peak"] > 0
+    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    assert r["traffic"] is None or r["traffic"] >= r["algorithmic_bytes_per_launch"]
+    cb = line["cpu_baseline"]
+    assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["value"] > 0 and cb["sample"]
+    c = line["clocks"]
+    assert c["sm_mhz"] and c["sm_max_mhz"] and not set(c["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    samples = line["config"]["frames_per_step_per_gpu"] * line["config"]["frame_len"]
+    assert abs(line["value"] - samples / (line["ms_per_step"] * 1e-3) / 1e6) / line["value"] < 1e-6
